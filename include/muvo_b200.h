@@ -1,0 +1,180 @@
+/*
+ * muvo_b200.h -- C ABI of libmuvo_b200.so: B200 (sm_100a) kernels for MUVO's
+ * geometric sensor-to-grid hot path.
+ *
+ * The reference (fzi-forschungszentrum-informatik/muvo) is pure Python and has no
+ * FFI layer; each entry point below names the reference function it replaces
+ * (file:line, relative to the MUVO checkout).  The Python wrappers in
+ * muvo_b200/ keep the reference call signatures and bind these symbols with
+ * ctypes; INTEGRATION.md shows the binding a MUVO maintainer would add.
+ *
+ * Conventions
+ *  - Pointers are DEVICE pointers unless the name ends in _h (host).
+ *  - The caller owns every buffer (inputs, outputs, workspace); nothing is
+ *    allocated or freed inside the library and no global mutable state is kept.
+ *  - Every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *    returns without synchronising.  Calls are re-entrant; concurrent callers
+ *    must use distinct workspaces.
+ *  - Return value: 0 = OK, <0 = MUVO_E_* below, >0 = cudaError_t of a launch.
+ *    muvo_strerror() maps both to text.
+ *  - Workspaces are "self-cleaning": muvo_ws_reset() must be enqueued once
+ *    after allocation (and after any failed call); every successful call
+ *    leaves the workspace ready for the next one.
+ *  - Frames are ragged: point p of frame f lives at rows
+ *    [frame_offsets[f], frame_offsets[f+1]) of the packed point arrays.
+ */
+#ifndef MUVO_B200_H
+#define MUVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MUVO_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MUVO_API __attribute__((visibility("default")))
+#else
+#define MUVO_API
+#endif
+
+enum {
+  MUVO_OK = 0,
+  MUVO_E_NULL = -1,      /* required pointer is NULL */
+  MUVO_E_ARG = -2,       /* invalid scalar argument / unsupported dtype */
+  MUVO_E_SHAPE = -3,     /* shape overflow (e.g. > 2^31 voxels per frame) */
+  MUVO_E_WORKSPACE = -4, /* workspace too small */
+  MUVO_E_ALIGN = -5      /* pointer not aligned as documented */
+};
+
+enum { MUVO_F32 = 0, MUVO_F64 = 1, MUVO_F16 = 2, MUVO_BF16 = 3 };                 /* floating dtypes */
+enum { MUVO_I64 = 0, MUVO_I32 = 1, MUVO_U8 = 2, MUVO_I16 = 3 };                   /* integer dtypes (pred) */
+enum { MUVO_RANGE_LAYOUT_HWC = 0, /* depth[F,H,W] f32, xyz[F,H,W,3] f32, sem[F,H,W] u8: do_range_projection's returns */
+       MUVO_RANGE_LAYOUT_XYZD = 1 /* xyz := [F,4,H,W] f32 planes x,y,z,depth (dataset.py:301-303); depth may be NULL   */ };
+
+/* Occupancy-grid description.  Replaces the (voxel_resolution, voxel_size, offset)
+ * arguments of voxel_filter(), data/data_preprocessing.py:172-178.  The host
+ * computes offset/upper in float64 exactly as numpy does there:
+ *   offset = user_offset + res*size/2 ; upper = size*res.                          */
+typedef struct MuvoGrid {
+  double res;
+  double offset[3];
+  double upper[3];
+  int32_t size[3];      /* Dx, Dy, Dz */
+  int32_t roadline_id;  /* label that overrides the nearest-point label (6, :198); <0 disables */
+} MuvoGrid;
+
+/* Range-image description.  Replaces PointCloud.__init__, muvo/utils/geometry_utils.py:167-173. */
+typedef struct MuvoRangeCfg {
+  int32_t H, W;
+  double fov_down_abs;  /* abs(fov_down) in rad          (:169,:190) */
+  double fov;           /* fov_up - fov_down in rad      (:170)      */
+  double lidar_pos[3];  /* (:173,:178)                               */
+} MuvoRangeCfg;
+
+/* diag[] slots written by the point kernels (int64 each) */
+enum { MUVO_DIAG_DROPPED_NONFINITE = 0, /* points with NaN/Inf coordinates or at the sensor origin (reference: IndexError) */
+       MUVO_DIAG_NEAR_EDGE_W = 1,       /* |frac(proj_w)| within 1e-9 of a column edge (incl. exactly on it)               */
+       MUVO_DIAG_NEAR_EDGE_H = 2,       /* same for rows                                                                   */
+       MUVO_DIAG_IN_GRID = 3,           /* points inside the occupancy grid                                                */
+       MUVO_DIAG_COUNT = 8 };
+
+MUVO_API int muvo_abi_version(void);
+MUVO_API const char* muvo_strerror(int code);
+
+/* ---- workspace ------------------------------------------------------------------ */
+/* Bytes needed by the point kernels for `n_frames` frames / `n_points_total` points.
+ * grid_h or range_h may be NULL when that stage is not used.                        */
+MUVO_API int muvo_points_workspace_bytes(int64_t n_points_total, int32_t n_frames, const MuvoGrid* grid_h,
+                                const MuvoRangeCfg* range_h, size_t* bytes_out_h);
+/* Put a freshly allocated (or dirty) workspace into the clean state. */
+MUVO_API int muvo_ws_reset(void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (a) voxelisation ------------------------------------------------------------
+ * Replaces voxel_filter(), data/data_preprocessing.py:172-228, batched over frames, and
+ * (dense_out) the densify step of muvo/data/dataset.py:317-327.
+ *   xyz        [P,3]  float32 or float64 (xyz_dtype), ego frame
+ *   sem        [P]    uint8
+ *   remap256   [256]  uint8 label remap applied to dense_out only, or NULL
+ *   dense_out  [F,Dx,Dy,Dz] uint8 (fully written, 0 = empty), or NULL
+ *   sparse_out [P,4]  uint16 rows (x,y,z,label) ; frame f's n_occ[f] rows start at row
+ *                     frame_offsets[f], ordered by x + y*Dx + z*Dx*Dy (:184,:187), or NULL
+ *   n_occ_out  [F]    int64 occupied voxels per frame, or NULL
+ *   diag       [MUVO_DIAG_COUNT] int64, accumulated into (caller zeroes), or NULL        */
+MUVO_API int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* sem, const int64_t* frame_offsets,
+                  int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
+                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* diag,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (b) range-view projection ---------------------------------------------------
+ * Replaces PointCloud.do_range_projection(), muvo/utils/geometry_utils.py:175-220.
+ *   xyz [P,3] float32 ego frame; outputs per `layout` above (all pixels written:
+ *   empty = depth -1, xyz 0, sem 0).                                                */
+MUVO_API int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
+                       int64_t n_points_total, const MuvoRangeCfg* cfg_h, int32_t layout, float* depth_out,
+                       float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (a)+(b) fused: one read of the point stream feeds both stages ---------------- */
+MUVO_API int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
+                      int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
+                      const MuvoRangeCfg* cfg_h, int32_t layout, uint8_t* dense_out, uint16_t* sparse_out,
+                      int64_t* n_occ_out, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/* ---- (c) lift-splat BEV pooling ---------------------------------------------------
+ * Replaces FrustumPooling.voxel_pooling + QuickCumsum (muvo/models/frustum_pooling.py:34-60,
+ * 131-187; twin: VoxelsSumming, muvo/layers/layers.py:326-357).
+ *   x        lifted features viewed as [B, n_pts, C] with element strides
+ *            (x_stride_b, x_stride_p, x_stride_c); n_pts = N*D*H*W frustum points per frame
+ *   cell     [B, n_pts] int32 flat BEV cell ((z*ny + y)*nx + x) or -1 = dropped
+ *            (masked out or out of bounds, :153-163)
+ *   out      [B, C*nz, ny, nx] float32, fully written (empty cells = 0, :180-185)
+ * The sum over a cell's points is taken in ascending point order (deterministic).   */
+MUVO_API int muvo_bev_pool_workspace_bytes(int32_t B, int64_t n_pts, int32_t n_cells, size_t* bytes_out_h);
+MUVO_API int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
+                      const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells, float* out,
+                      void* ws, size_t ws_bytes, void* stream);
+/* grad_x[b,p,c] = cell[b,p] >= 0 ? grad_out[b,c,cell[b,p]] : 0  (frustum_pooling.py:52-60 + index bwd);
+ * grad_x is written with the given element strides (every element written).         */
+MUVO_API int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C,
+                      int32_t n_cells, void* grad_x, int32_t gx_dtype, int64_t gx_stride_b, int64_t gx_stride_p,
+                      int64_t gx_stride_c, void* stream);
+
+/* Sorted-rank segment sum: QuickCumsum.forward / cumsum_trick (frustum_pooling.py:23-42).
+ *   x [n,C] float32 row-major, ranks [n] int64 non-decreasing.
+ *   seg_id_out [n] int32 (segment index of each row; scratch + used by the backward),
+ *   n_seg_out  [1] int32, x_seg_out [>=n_seg, C] (caller sizes it for n rows),
+ *   last_row_out [>=n_seg] int64 = index of the LAST row of each segment (geom_feats[kept], :40). */
+MUVO_API int muvo_segment_sum_workspace_bytes(int64_t n, size_t* bytes_out_h);
+MUVO_API int muvo_segment_sum_fwd(const float* x, const int64_t* ranks, int64_t n, int32_t C, int32_t* seg_id_out,
+                         int32_t* n_seg_out, float* x_seg_out, int64_t* last_row_out, void* ws, size_t ws_bytes,
+                         void* stream);
+/* grad_x[i,:] = grad_seg[seg_id[i],:]  (QuickCumsum.backward, :52-60) */
+MUVO_API int muvo_segment_sum_bwd(const float* grad_seg, const int32_t* seg_id, int64_t n, int32_t C, float* grad_x,
+                         void* stream);
+
+/* ---- (d) SSC / IoU counts ---------------------------------------------------------
+ * Replaces SSCMetrics.get_score_completion + get_score_semantic_and_completion,
+ * muvo/metrics.py:143-216, summed over all frames.
+ *   pred      [n] integer labels (pred_dtype), target [n] uint8
+ *   nonempty  [n] uint8/bool or NULL : restricts completion AND per-class counts
+ *   nonsurface[n] uint8/bool or NULL : restricts completion only (add_batch, :79-95)
+ *   ignore255 != 0 : additionally drop target==255 voxels (add_batch's y_true != 255)
+ *   counts_out[3+3C] int64, ACCUMULATED into (caller zeroes):
+ *              completion tp,fp,fn ; tp[C] ; fp[C] ; fn[C]                            */
+MUVO_API int muvo_ssc_counts(const void* pred, int32_t pred_dtype, const uint8_t* target, const uint8_t* nonempty,
+                    const uint8_t* nonsurface, int32_t ignore255, int64_t n_voxels, int32_t n_classes,
+                    int64_t* counts_out, void* stream);
+/* Fused argmax + counts over logits [F, C, S] (S voxels per frame), trainer.py:483-490:
+ * never materialises the int64 prediction.  target [F,S] uint8.                      */
+MUVO_API int muvo_ssc_counts_from_logits(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames,
+                                int32_t n_classes, int64_t voxels_per_frame, int32_t ignore255,
+                                int64_t* counts_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MUVO_B200_H */

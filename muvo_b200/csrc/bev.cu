@@ -1,0 +1,539 @@
+// Stage (c): lift-splat BEV pooling (forward + backward) and the sorted-rank segment sum.
+//
+// Replaces FrustumPooling.voxel_pooling / QuickCumsum / cumsum_trick
+// (muvo/models/frustum_pooling.py:23-60,131-187) and VoxelsSumming (muvo/layers/layers.py:326-357).
+//
+// The reference reshapes the lifted tensor to channels-last (a 236 MB/frame copy), compacts it twice,
+// argsorts and gathers the *feature rows*, prefix-sums every row and differences the prefix sums.
+// Here only point INDICES are sorted (stable counting sort by BEV cell, 4 B/point), and each cell's
+// features are summed directly in ascending point order from wherever they live (any strides): the
+// result is deterministic, more accurate than the cumsum trick, and x is read exactly once.
+//
+// Forward kernels
+//   S1 k_cell_hist   : per warp-chunk (1024 consecutive points) histogram over cells (shared memory)
+//   S2 k_cell_scan   : per (frame, cell) exclusive scan over warp-chunks  -> chunk bases + cell totals
+//   S3 k_cell_starts : per frame exclusive scan over cells                -> cell_start[n_cells+1]
+//   S4 k_cell_place  : stable placement of point ids                      -> sorted[b][...]
+//   P  k_pool_*      : per (frame, cell) ordered sum over its points, all C channels; writes every
+//                      output element (zeros for empty cells), so `out` needs no memset.
+// Backward: pure gather, every grad_x element written once, in the producer's memory format.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace muvo {
+namespace {
+
+constexpr int kWarpChunk = 1024;   // points per warp-chunk (32 rounds of 32 lanes)
+constexpr int kSortWarps = 4;      // warps per block in S1/S4
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ T cvt(float v);
+template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half cvt<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+struct BevWs {
+  uint32_t* chunk_base = nullptr;   // [B, n_wc, n_cells]  exclusive offset of (chunk, cell) inside its cell
+  uint32_t* cell_total = nullptr;   // [B, n_cells]
+  uint32_t* cell_start = nullptr;   // [B, n_cells + 1]
+  int32_t* sorted = nullptr;        // [B, n_pts]  point ids grouped by cell, ascending inside a cell
+  int n_wc = 0;
+  size_t bytes = 0;
+};
+
+static BevWs carve_bev(void* base, int B, int64_t n_pts, int n_cells) {
+  BevWs w;
+  char* b = (char*)base;
+  size_t o = 0;
+  w.n_wc = (int)ceil_div64(n_pts, kWarpChunk);
+  w.chunk_base = (uint32_t*)(b + o); o = align_up(o + (size_t)B * w.n_wc * n_cells * 4, 256);
+  w.cell_total = (uint32_t*)(b + o); o = align_up(o + (size_t)B * n_cells * 4, 256);
+  w.cell_start = (uint32_t*)(b + o); o = align_up(o + (size_t)B * (n_cells + 1) * 4, 256);
+  w.sorted = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
+  w.bytes = o;
+  return w;
+}
+
+// S1: histogram of one warp-chunk; counts (<= 1024) written as u32 into chunk_base (scanned in place by S2).
+__global__ void __launch_bounds__(kSortWarps * 32)
+k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc, uint32_t* __restrict__ chunk_base) {
+  extern __shared__ uint32_t sm[];                 // [kSortWarps][n_cells]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t wc_global = (int64_t)blockIdx.x * kSortWarps + warp;
+  uint32_t* h = sm + (size_t)warp * n_cells;
+  for (int i = lane; i < n_cells; i += 32) h[i] = 0;
+  __syncwarp();
+  if (wc_global >= (int64_t)B * n_wc) return;
+  const int b = (int)(wc_global / n_wc), wc = (int)(wc_global % n_wc);
+  const int32_t* cp = cell + (size_t)b * n_pts;
+  const int64_t p0 = (int64_t)wc * kWarpChunk;
+  for (int r = 0; r < kWarpChunk / 32; ++r) {
+    int64_t p = p0 + r * 32 + lane;
+    int c = (p < n_pts) ? __ldg(cp + p) : -1;
+    if (c >= n_cells) c = -1;
+    unsigned m = __match_any_sync(0xffffffffu, c);
+    if (c >= 0 && lane == (__ffs(m) - 1)) h[c] += __popc(m);
+    __syncwarp();
+  }
+  uint32_t* dst = chunk_base + ((size_t)b * n_wc + wc) * n_cells;
+  for (int i = lane; i < n_cells; i += 32) dst[i] = h[i];
+}
+
+// S2: per (frame, cell) exclusive scan over the warp-chunks (in place) + total.
+__global__ void k_cell_scan(uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ cell_total, int B, int n_cells, int n_wc) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * n_cells) return;
+  int b = (int)(t / n_cells), c = (int)(t % n_cells);
+  uint32_t* col = chunk_base + (size_t)b * n_wc * n_cells + c;
+  uint32_t run = 0;
+  for (int k = 0; k < n_wc; ++k) { uint32_t v = col[(size_t)k * n_cells]; col[(size_t)k * n_cells] = run; run += v; }
+  cell_total[t] = run;
+}
+
+// S3: per frame exclusive scan over cells (one block per frame).
+__global__ void __launch_bounds__(1024)
+k_cell_starts(const uint32_t* __restrict__ cell_total, uint32_t* __restrict__ cell_start, int n_cells) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t* tot = cell_total + (size_t)b * n_cells;
+  uint32_t* st = cell_start + (size_t)b * (n_cells + 1);
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n_cells; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < n_cells ? tot[i] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t carry = carry_s;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+      wsum[lane] = wi - w;
+      if (lane == 31) carry_s = carry + wi;
+    }
+    __syncthreads();
+    if (i < n_cells) st[i] = carry + wsum[warp] + incl - v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) st[n_cells] = carry_s;
+}
+
+// S4: stable placement.
+__global__ void __launch_bounds__(kSortWarps * 32)
+k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc,
+             const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ sorted) {
+  extern __shared__ uint32_t sm[];                 // running count per cell inside this warp-chunk
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t wc_global = (int64_t)blockIdx.x * kSortWarps + warp;
+  uint32_t* run = sm + (size_t)warp * n_cells;
+  for (int i = lane; i < n_cells; i += 32) run[i] = 0;
+  __syncwarp();
+  if (wc_global >= (int64_t)B * n_wc) return;
+  const int b = (int)(wc_global / n_wc), wc = (int)(wc_global % n_wc);
+  const int32_t* cp = cell + (size_t)b * n_pts;
+  const uint32_t* cb = chunk_base + ((size_t)b * n_wc + wc) * n_cells;
+  const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+  int32_t* out = sorted + (size_t)b * n_pts;
+  const int64_t p0 = (int64_t)wc * kWarpChunk;
+  for (int r = 0; r < kWarpChunk / 32; ++r) {
+    int64_t p = p0 + r * 32 + lane;
+    int c = (p < n_pts) ? __ldg(cp + p) : -1;
+    if (c >= n_cells) c = -1;
+    unsigned m = __match_any_sync(0xffffffffu, c);
+    if (c >= 0) {
+      uint32_t before = __popc(m & ((1u << lane) - 1u));
+      uint32_t pos = cs[c] + cb[c] + run[c] + before;
+      out[pos] = (int32_t)p;
+    }
+    __syncwarp();
+    if (c >= 0 && lane == (__ffs(m) - 1)) run[c] += __popc(m);
+    __syncwarp();
+  }
+}
+
+// P (point-major, x_stride_p == 1): one warp per (frame, cell); lanes over the cell's points (coalesced
+// along runs of consecutive points), channels in the outer loop with 4 independent loads in flight;
+// lane-strided partial sums + xor tree -> deterministic.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pool_point_major(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* __restrict__ cell_start,
+                   const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C, int n_cells, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (int64_t)B * n_cells) return;
+  const int b = (int)(wid / n_cells), c = (int)(wid % n_cells);
+  const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+  const uint32_t s0 = cs[c], s1 = cs[c + 1];
+  const int32_t* list = sorted + (size_t)b * n_pts;
+  float* o = out + (size_t)b * C * n_cells + c;
+  const T* xb = x + (size_t)b * sb;
+  if (s0 == s1) {
+    for (int ch = lane; ch < C; ch += 32) o[(size_t)ch * n_cells] = 0.f;
+    return;
+  }
+  for (int ch = 0; ch < C; ch += 4) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const T* x0 = xb + (size_t)ch * sc;
+    for (uint32_t j = s0 + lane; j < s1; j += 32) {
+      const int64_t p = list[j];
+      a0 += ldf<T>(x0 + p);
+      if (ch + 1 < C) a1 += ldf<T>(x0 + sc + p);
+      if (ch + 2 < C) a2 += ldf<T>(x0 + 2 * sc + p);
+      if (ch + 3 < C) a3 += ldf<T>(x0 + 3 * sc + p);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, d); a3 += __shfl_xor_sync(0xffffffffu, a3, d);
+    }
+    if (lane == 0) {
+      o[(size_t)ch * n_cells] = a0;
+      if (ch + 1 < C) o[(size_t)(ch + 1) * n_cells] = a1;
+      if (ch + 2 < C) o[(size_t)(ch + 2) * n_cells] = a2;
+      if (ch + 3 < C) o[(size_t)(ch + 3) * n_cells] = a3;
+    }
+  }
+}
+
+// P (generic strides; coalesced when x_stride_c == 1): one block per (frame, cell), threads over channels,
+// sequential ascending-point sum.
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_pool_channel_major(const T* __restrict__ x, int64_t sb, int64_t sp, int64_t sc, const uint32_t* __restrict__ cell_start,
+                     const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C, int n_cells, float* __restrict__ out) {
+  const int b = blockIdx.x / n_cells, c = blockIdx.x % n_cells;
+  const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+  const uint32_t s0 = cs[c], s1 = cs[c + 1];
+  const int32_t* list = sorted + (size_t)b * n_pts;
+  float* o = out + (size_t)b * C * n_cells + c;
+  const T* xb = x + (size_t)b * sb;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float acc = 0.f;
+    for (uint32_t j = s0; j < s1; ++j) acc += ldf<T>(xb + (size_t)list[j] * sp + (size_t)ch * sc);
+    o[(size_t)ch * n_cells] = acc;
+  }
+}
+
+// Backward: grad_x[b,p,c] = cell >= 0 ? grad_out[b,c,cell] : 0.
+// FAST_P: grad_x point-contiguous (stride_p == 1): thread per 4 consecutive points of one channel.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pool_bwd_point_major(const float* __restrict__ gout, const int32_t* __restrict__ cell, int B, int64_t n_pts, int C,
+                       int n_cells, T* __restrict__ gx, int64_t sb, int64_t sc) {
+  const int64_t quads = ceil_div64(n_pts, 4);
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * C * quads) return;
+  const int64_t q = t % quads;
+  const int64_t bc = t / quads;
+  const int ch = (int)(bc % C), b = (int)(bc / C);
+  const int64_t p0 = q * 4;
+  const int32_t* cp = cell + (size_t)b * n_pts + p0;
+  const float* g = gout + ((size_t)b * C + ch) * n_cells;
+  T* dst = gx + (size_t)b * sb + (size_t)ch * sc + p0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (p0 + k < n_pts) {
+      int c = __ldg(cp + k);
+      dst[k] = cvt<T>((c >= 0 && c < n_cells) ? __ldg(g + c) : 0.f);
+    }
+  }
+}
+template <>
+__global__ void __launch_bounds__(256)
+k_pool_bwd_point_major<float>(const float* __restrict__ gout, const int32_t* __restrict__ cell, int B, int64_t n_pts, int C,
+                              int n_cells, float* __restrict__ gx, int64_t sb, int64_t sc) {
+  const int64_t quads = ceil_div64(n_pts, 4);
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * C * quads) return;
+  const int64_t q = t % quads;
+  const int64_t bc = t / quads;
+  const int ch = (int)(bc % C), b = (int)(bc / C);
+  const int64_t p0 = q * 4;
+  const int32_t* cp = cell + (size_t)b * n_pts + p0;
+  const float* g = gout + ((size_t)b * C + ch) * n_cells;
+  float* dst = gx + (size_t)b * sb + (size_t)ch * sc + p0;
+  const bool vec = (p0 + 4 <= n_pts) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
+  if (vec) {
+    int4 c4 = __ldg(reinterpret_cast<const int4*>(cp));
+    float4 v;
+    v.x = (c4.x >= 0 && c4.x < n_cells) ? __ldg(g + c4.x) : 0.f;
+    v.y = (c4.y >= 0 && c4.y < n_cells) ? __ldg(g + c4.y) : 0.f;
+    v.z = (c4.z >= 0 && c4.z < n_cells) ? __ldg(g + c4.z) : 0.f;
+    v.w = (c4.w >= 0 && c4.w < n_cells) ? __ldg(g + c4.w) : 0.f;
+    st_stream_f4(reinterpret_cast<float4*>(dst), v);
+  } else {
+    for (int k = 0; k < 4; ++k)
+      if (p0 + k < n_pts) { int c = __ldg(cp + k); dst[k] = (c >= 0 && c < n_cells) ? __ldg(g + c) : 0.f; }
+  }
+}
+
+// generic strides: thread per (b, p, c) with c fastest (coalesced when stride_c == 1)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_pool_bwd_generic(const float* __restrict__ gout, const int32_t* __restrict__ cell, int B, int64_t n_pts, int C, int n_cells,
+                   T* __restrict__ gx, int64_t sb, int64_t sp, int64_t sc) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)B * n_pts * C) return;
+  const int ch = (int)(t % C);
+  const int64_t bp = t / C;
+  const int64_t p = bp % n_pts;
+  const int b = (int)(bp / n_pts);
+  int c = __ldg(cell + (size_t)b * n_pts + p);
+  float v = (c >= 0 && c < n_cells) ? __ldg(gout + ((size_t)b * C + ch) * n_cells + c) : 0.f;
+  gx[(size_t)b * sb + (size_t)p * sp + (size_t)ch * sc] = cvt<T>(v);
+}
+
+// ---------------------------------------------------------------- sorted-rank segment sum (QuickCumsum API)
+constexpr int kScanBlock = 1024;
+
+// kept[i] = (i == n-1) || ranks[i+1] != ranks[i]  (frustum_pooling.py:38-39); per-block count of kept flags
+__global__ void __launch_bounds__(kScanBlock)
+k_seg_block_count(const int64_t* __restrict__ ranks, int64_t n, uint32_t* __restrict__ block_cnt) {
+  __shared__ uint32_t ws[32];
+  int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  uint32_t k = 0;
+  if (i < n) k = (i == n - 1) || (ranks[i + 1] != ranks[i]);
+  unsigned bal = __ballot_sync(0xffffffffu, k);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t v = ws[threadIdx.x];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = v;
+  }
+}
+// single block: exclusive scan of block counts (in place) + n_seg
+__global__ void __launch_bounds__(1024)
+k_seg_scan_blocks(uint32_t* __restrict__ block_cnt, int nblocks, int32_t* __restrict__ n_seg_out) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < nblocks ? block_cnt[i] : 0, incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t carry = carry_s;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+      wsum[lane] = wi - w;
+      if (lane == 31) carry_s = carry + wi;
+    }
+    __syncthreads();
+    if (i < nblocks) block_cnt[i] = carry + wsum[warp] + incl - v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *n_seg_out = (int32_t)carry_s;
+}
+// seg_id[i] = #kept before i ; last_row[seg_id] = i for kept rows
+__global__ void __launch_bounds__(kScanBlock)
+k_seg_assign(const int64_t* __restrict__ ranks, int64_t n, const uint32_t* __restrict__ block_off, int32_t* __restrict__ seg_id,
+             int64_t* __restrict__ last_row) {
+  __shared__ uint32_t ws[32];
+  int64_t i = (int64_t)blockIdx.x * kScanBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t k = 0;
+  if (i < n) k = (i == n - 1) || (ranks[i + 1] != ranks[i]);
+  unsigned bal = __ballot_sync(0xffffffffu, k);
+  if (lane == 0) ws[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t v = ws[lane], incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    ws[lane] = incl - v;
+  }
+  __syncthreads();
+  if (i < n) {
+    uint32_t id = block_off[blockIdx.x] + ws[warp] + __popc(bal & ((1u << lane) - 1u));
+    seg_id[i] = (int32_t)id;
+    if (k) last_row[id] = i;
+  }
+}
+// x_seg[s, :] = sum of rows (last_row[s-1], last_row[s]] in ascending row order; threads over channels
+__global__ void __launch_bounds__(256)
+k_seg_sum(const float* __restrict__ x, const int64_t* __restrict__ last_row, const int32_t* __restrict__ n_seg, int C,
+          float* __restrict__ x_seg) {
+  const int ns = *n_seg;
+  for (int s = blockIdx.x; s < ns; s += gridDim.x) {
+    const int64_t r1 = last_row[s], r0 = s ? last_row[s - 1] + 1 : 0;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      float acc = 0.f;
+      for (int64_t r = r0; r <= r1; ++r) acc += __ldg(x + (size_t)r * C + ch);
+      x_seg[(size_t)s * C + ch] = acc;
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+k_seg_bwd(const float* __restrict__ gseg, const int32_t* __restrict__ seg_id, int64_t n, int C, float* __restrict__ gx) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * C) return;
+  int64_t i = t / C;
+  int ch = (int)(t - i * C);
+  gx[t] = __ldg(gseg + (size_t)__ldg(seg_id + i) * C + ch);
+}
+
+template <typename T>
+static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const int32_t* cell, int B, int64_t n_pts, int C,
+                        int n_cells, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  BevWs w = carve_bev(ws, B, n_pts, n_cells);
+  if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+  const size_t smem = (size_t)kSortWarps * n_cells * 4;
+  if (smem > 200 * 1024) return MUVO_E_SHAPE;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_cell_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cell_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int64_t n_chunks = (int64_t)B * w.n_wc;
+  const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
+  k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base);
+  MUVO_LAUNCH_CHECK();
+  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
+  MUVO_LAUNCH_CHECK();
+  k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells);
+  MUVO_LAUNCH_CHECK();
+  k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted);
+  MUVO_LAUNCH_CHECK();
+  if (sp == 1) {
+    const int64_t warps = (int64_t)B * n_cells;
+    k_pool_point_major<T><<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(x, sb, sc, w.cell_start, w.sorted, B, n_pts, C,
+                                                                                n_cells, out);
+  } else {
+    k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,
+                                                                             C, n_cells, out);
+  }
+  MUVO_LAUNCH_CHECK();
+  return MUVO_OK;
+}
+
+template <typename T>
+static int run_pool_bwd(const float* gout, const int32_t* cell, int B, int64_t n_pts, int C, int n_cells, T* gx, int64_t sb,
+                        int64_t sp, int64_t sc, cudaStream_t st) {
+  if (sp == 1) {
+    int64_t n = (int64_t)B * C * ceil_div64(n_pts, 4);
+    k_pool_bwd_point_major<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(gout, cell, B, n_pts, C, n_cells, gx, sb, sc);
+  } else {
+    int64_t n = (int64_t)B * n_pts * C;
+    k_pool_bwd_generic<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(gout, cell, B, n_pts, C, n_cells, gx, sb, sp, sc);
+  }
+  MUVO_LAUNCH_CHECK();
+  return MUVO_OK;
+}
+
+struct SegWs { uint32_t* block_cnt; size_t bytes; int nblocks; };
+static SegWs carve_seg(void* base, int64_t n) {
+  SegWs w;
+  w.nblocks = (int)ceil_div64(n > 0 ? n : 1, kScanBlock);
+  w.block_cnt = (uint32_t*)base;
+  w.bytes = align_up((size_t)w.nblocks * 4, 256);
+  return w;
+}
+
+}  // namespace
+}  // namespace muvo
+
+using namespace muvo;
+
+extern "C" {
+
+int muvo_bev_pool_workspace_bytes(int32_t B, int64_t n_pts, int32_t n_cells, size_t* bytes_out_h) {
+  if (!bytes_out_h) return MUVO_E_NULL;
+  if (B < 0 || n_pts < 0 || n_cells <= 0) return MUVO_E_ARG;
+  *bytes_out_h = carve_bev(nullptr, B, n_pts, n_cells).bytes + 256;
+  return MUVO_OK;
+}
+
+int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
+                      const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells, float* out, void* ws,
+                      size_t ws_bytes, void* stream) {
+  if (B < 0 || n_pts < 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || C == 0) return MUVO_OK;
+  if (!out || !ws) return MUVO_E_NULL;
+  if (n_pts > 0 && (!x || !cell)) return MUVO_E_NULL;
+  if (n_pts >= ((int64_t)1 << 31) || (int64_t)B * n_cells >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (x_dtype) {
+    case MUVO_F32:  return run_pool_fwd<float>((const float*)x, x_stride_b, x_stride_p, x_stride_c, cell, B, n_pts, C, n_cells, out, ws, ws_bytes, st);
+    case MUVO_F16:  return run_pool_fwd<__half>((const __half*)x, x_stride_b, x_stride_p, x_stride_c, cell, B, n_pts, C, n_cells, out, ws, ws_bytes, st);
+    case MUVO_BF16: return run_pool_fwd<__nv_bfloat16>((const __nv_bfloat16*)x, x_stride_b, x_stride_p, x_stride_c, cell, B, n_pts, C, n_cells, out, ws, ws_bytes, st);
+    default: return MUVO_E_ARG;
+  }
+}
+
+int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells,
+                      void* grad_x, int32_t gx_dtype, int64_t gx_stride_b, int64_t gx_stride_p, int64_t gx_stride_c,
+                      void* stream) {
+  if (B < 0 || n_pts < 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || C == 0 || n_pts == 0) return MUVO_OK;
+  if (!grad_out || !cell || !grad_x) return MUVO_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (gx_dtype) {
+    case MUVO_F32:  return run_pool_bwd<float>(grad_out, cell, B, n_pts, C, n_cells, (float*)grad_x, gx_stride_b, gx_stride_p, gx_stride_c, st);
+    case MUVO_F16:  return run_pool_bwd<__half>(grad_out, cell, B, n_pts, C, n_cells, (__half*)grad_x, gx_stride_b, gx_stride_p, gx_stride_c, st);
+    case MUVO_BF16: return run_pool_bwd<__nv_bfloat16>(grad_out, cell, B, n_pts, C, n_cells, (__nv_bfloat16*)grad_x, gx_stride_b, gx_stride_p, gx_stride_c, st);
+    default: return MUVO_E_ARG;
+  }
+}
+
+int muvo_segment_sum_workspace_bytes(int64_t n, size_t* bytes_out_h) {
+  if (!bytes_out_h) return MUVO_E_NULL;
+  if (n < 0) return MUVO_E_ARG;
+  *bytes_out_h = carve_seg(nullptr, n).bytes + 256;
+  return MUVO_OK;
+}
+
+int muvo_segment_sum_fwd(const float* x, const int64_t* ranks, int64_t n, int32_t C, int32_t* seg_id_out,
+                         int32_t* n_seg_out, float* x_seg_out, int64_t* last_row_out, void* ws, size_t ws_bytes,
+                         void* stream) {
+  if (n < 0 || C < 0) return MUVO_E_ARG;
+  if (!n_seg_out) return MUVO_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) { cudaError_t e = cudaMemsetAsync(n_seg_out, 0, 4, st); return e == cudaSuccess ? MUVO_OK : (int)e; }
+  if (!ranks || !seg_id_out || !last_row_out || !ws || (C > 0 && (!x || !x_seg_out))) return MUVO_E_NULL;
+  if (n >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
+  SegWs w = carve_seg(ws, n);
+  if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+  k_seg_block_count<<<w.nblocks, kScanBlock, 0, st>>>(ranks, n, w.block_cnt);
+  MUVO_LAUNCH_CHECK();
+  k_seg_scan_blocks<<<1, 1024, 0, st>>>(w.block_cnt, w.nblocks, n_seg_out);
+  MUVO_LAUNCH_CHECK();
+  k_seg_assign<<<w.nblocks, kScanBlock, 0, st>>>(ranks, n, w.block_cnt, seg_id_out, last_row_out);
+  MUVO_LAUNCH_CHECK();
+  if (C > 0) {
+    int64_t grid = n < (int64_t)kNumSMsB200 * 16 ? n : (int64_t)kNumSMsB200 * 16;
+    k_seg_sum<<<(unsigned)grid, 256, 0, st>>>(x, last_row_out, n_seg_out, C, x_seg_out);
+    MUVO_LAUNCH_CHECK();
+  }
+  return MUVO_OK;
+}
+
+int muvo_segment_sum_bwd(const float* grad_seg, const int32_t* seg_id, int64_t n, int32_t C, float* grad_x, void* stream) {
+  if (n < 0 || C < 0) return MUVO_E_ARG;
+  if (n == 0 || C == 0) return MUVO_OK;
+  if (!grad_seg || !seg_id || !grad_x) return MUVO_E_NULL;
+  k_seg_bwd<<<(unsigned)ceil_div64(n * C, 256), 256, 0, (cudaStream_t)stream>>>(grad_seg, seg_id, n, C, grad_x);
+  MUVO_LAUNCH_CHECK();
+  return MUVO_OK;
+}
+
+}  // extern "C"

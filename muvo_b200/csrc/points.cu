@@ -1,0 +1,789 @@
+// Stages (a) voxelisation and (b) range-view projection, batched over ragged frames.
+//
+// Reference behaviour being reproduced (bit-exact):
+//   (a) voxel_filter            data/data_preprocessing.py:172-228
+//       densify                 muvo/data/dataset.py:317-327
+//   (b) do_range_projection     muvo/utils/geometry_utils.py:175-220
+//
+// Algorithm (no float atomics, no sort of the point stream, deterministic result):
+//   K1  point pass    : per point, float64 voxel id + range pixel/depth (numpy's op order, no FMA
+//                       contraction: this file is compiled with -fmad=false).  Occupied voxels are
+//                       marked in a 1-bit-per-voxel frame bitmap (295 KB/frame); the range pixel is
+//                       resolved on the spot with a compare-and-swap on a u32 "winner index" table
+//                       (nearest depth wins, ties -> lowest point index), comparing against the
+//                       current winner by re-deriving its key from its coordinates.
+//   K2  bitmap scan   : popcount prefix per 128-bit bitmap chunk -> every occupied voxel gets a
+//                       dense slot id = its rank (in output order); n_occ per frame.
+//   K3  voxel resolve : second point pass (cheap: no trig); same CAS-on-index on slot `rank`,
+//                       key = (not roadline, |p mod res|^2, point index).
+//   K4  emit          : bitmap-ordered, fully coalesced write of the dense uint8 grid (zeros
+//                       included, so no memset + scatter) and/or the sorted sparse (n,4) list;
+//                       pixel-ordered write of the range image.  Emit kernels put every table
+//                       entry they consume back to 0, so the workspace is clean for the next call.
+#include <math.h>
+#include "common.cuh"
+
+namespace muvo {
+namespace {
+
+constexpr int kBlock = 256;
+constexpr double kPi = 3.141592653589793;            // np.pi
+constexpr double kPiOver4 = 0x1.921fb54442d18p-1;    // correctly rounded pi/4 (numpy/glibc value on diagonals)
+constexpr double k3PiOver4 = 0x1.2d97c7f3321d2p+1;   // correctly rounded 3pi/4
+constexpr double kEdgeEps = 1e-9;
+
+enum BitOrder { ORDER_DENSE = 0 /* (x*Dy+y)*Dz+z */, ORDER_LINEAR = 1 /* x + Dx*(y + Dy*z) */ };
+
+struct GridDev {
+  double res, inv_res;
+  double off[3], up[3];
+  int dx, dy, dz;
+  int road;
+  int pow2;
+  int order;
+  int gw;        // bitmap words per frame (multiple of 32)
+  int64_t G;     // voxels per frame
+};
+
+struct RangeDev {
+  int H, W;
+  double fda, fov;
+  double L[3];
+};
+
+struct PointsWs {
+  uint32_t* bitmap = nullptr;   // [F, gw]
+  uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk
+  uint32_t* win = nullptr;      // [P]   slot = frame_offsets[f] + rank ; value = local point index + 1 (0 = empty)
+  uint32_t* pixtab = nullptr;   // [F, H*W] value = local point index + 1 (0 = empty)
+  size_t bytes = 0;
+};
+
+static int bitmap_words(int64_t G) { return (int)(ceil_div64(G, 1024) * 32); }
+
+static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const MuvoRangeCfg* r) {
+  PointsWs w;
+  size_t o = 0;
+  char* b = (char*)base;
+  if (g) {
+    int64_t G = (int64_t)g->size[0] * g->size[1] * g->size[2];
+    size_t gw = (size_t)bitmap_words(G);
+    w.bitmap = (uint32_t*)(b + o); o = align_up(o + (size_t)F * gw * 4, 256);
+    w.prefix = (uint32_t*)(b + o); o = align_up(o + (size_t)F * (gw / 4) * 4, 256);
+    w.win = (uint32_t*)(b + o);    o = align_up(o + (size_t)(P > 0 ? P : 1) * 4, 256);
+  }
+  if (r) {
+    w.pixtab = (uint32_t*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 4, 256);
+  }
+  w.bytes = o;
+  return w;
+}
+
+// ---------------------------------------------------------------- per-point arithmetic
+// numpy's npy_divmod (numpy/_core/src/npymath/npy_math_internal.h.src), the scalar behind np.divmod
+// at data_preprocessing.py:183; needed when res is not a power of two.  fmod is exact on both sides.
+__device__ __forceinline__ double npy_divmod_dev(double a, double b, double* modulus) {
+  double mod = fmod(a, b);
+  double div = (a - mod) / b;
+  if (mod != 0.0) {
+    if ((b < 0) != (mod < 0)) { mod += b; div -= 1.0; }
+  } else {
+    mod = copysign(0.0, b);
+  }
+  double fl;
+  if (div != 0.0) {
+    fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+  } else {
+    fl = copysign(0.0, a / b);
+  }
+  *modulus = mod;
+  return fl;
+}
+
+struct VoxKey {
+  uint32_t bit;   // bit index inside the frame bitmap (order per GridDev::order)
+  double dis;     // (mx^2 + my^2) + mz^2, float64, np.sum(axis=1) order (:212)
+  bool in;
+};
+
+__device__ __forceinline__ VoxKey vox_of(double px, double py, double pz, const GridDev& g) {
+  VoxKey k;
+  double bx = px + g.off[0], by = py + g.off[1], bz = pz + g.off[2];          // :177
+  k.in = (bx >= 0.0) && (bx < g.up[0]) && (by >= 0.0) && (by < g.up[1]) && (bz >= 0.0) && (bz < g.up[2]);   // :178
+  k.bit = 0; k.dis = 0.0;
+  if (!k.in) return k;
+  double cx, cy, cz, mx, my, mz;
+  if (g.pow2) {  // floor(b/res) and b - floor*res carry no rounding for a power-of-two res
+    cx = floor(bx * g.inv_res); cy = floor(by * g.inv_res); cz = floor(bz * g.inv_res);
+    mx = bx - cx * g.res; my = by - cy * g.res; mz = bz - cz * g.res;
+  } else {
+    cx = npy_divmod_dev(bx, g.res, &mx);
+    cy = npy_divmod_dev(by, g.res, &my);
+    cz = npy_divmod_dev(bz, g.res, &mz);
+  }
+  k.dis = (mx * mx + my * my) + mz * mz;
+  int ix = (int)cx, iy = (int)cy, iz = (int)cz;
+  if (ix < 0 || ix >= g.dx || iy < 0 || iy >= g.dy || iz < 0 || iz >= g.dz) { k.in = false; return k; }
+  k.bit = (g.order == ORDER_DENSE) ? (uint32_t)((ix * g.dy + iy) * g.dz + iz)
+                                   : (uint32_t)(ix + g.dx * (iy + g.dy * iz));
+  return k;
+}
+
+// LiDAR-frame coordinates + depth (for the point itself and for re-deriving a competitor's key)
+template <typename T>
+__device__ __forceinline__ double range_depth_of(T x, T y, T z, const RangeDev& r, double* xc_o, double* yc_o,
+                                                 double* zc_o) {
+  double xc = (double)x - r.L[0];          // :177-178  (x * 1) - L0
+  double yc = (-(double)y) - r.L[1];       //           (y * -1) - L1   (keeps the sign of zero)
+  double zc = (double)z - r.L[2];
+  *xc_o = xc; *yc_o = yc; *zc_o = zc;
+  return sqrt((xc * xc + yc * yc) + zc * zc);   // :180  np.linalg.norm(., 2, axis=1)
+}
+
+__device__ __forceinline__ double atan2_np(double y, double x) {
+  // Exact bin edges exist only on the axes and diagonals; numpy returns the correctly rounded
+  // multiples of pi/4 there.  CUDA's atan2 is exact on the axes; pin the diagonals explicitly.
+  if (fabs(y) == fabs(x) && x != 0.0 && isfinite(x)) return copysign(x > 0.0 ? kPiOver4 : k3PiOver4, y);
+  return atan2(y, x);
+}
+
+struct PixKey {
+  int pix;        // h*W + w
+  double depth;
+  bool ok;
+  bool near_w, near_h;
+};
+
+template <typename T>
+__device__ __forceinline__ PixKey pix_of(T x, T y, T z, const RangeDev& r) {
+  PixKey k;
+  double xc, yc, zc;
+  k.depth = range_depth_of(x, y, z, r, &xc, &yc, &zc);
+  k.ok = isfinite(k.depth) && k.depth > 0.0;
+  k.pix = 0; k.near_w = k.near_h = false;
+  if (!k.ok) return k;
+  double yy = -yc;                                        // :183
+  double yaw = atan2_np(yy, xc);                          // :186
+  double pitch = asin(zc / k.depth);                      // :187
+  double pw = 0.5 * (1.0 - yaw / kPi);                    // :189
+  double ph = 1.0 - (pitch + r.fda) / r.fov;              // :190
+  pw *= (double)r.W;                                      // :191
+  ph *= (double)r.H;                                      // :192
+  if (!(pw == pw) || !(ph == ph)) { k.ok = false; return k; }
+  double fw = floor(pw), fh = floor(ph);                  // :194,:198
+  k.near_w = (pw > 0.0 && pw < (double)r.W) && ((pw - fw) < kEdgeEps || (pw - fw) > 1.0 - kEdgeEps);
+  k.near_h = (ph > 0.0 && ph < (double)r.H) && ((ph - fh) < kEdgeEps || (ph - fh) > 1.0 - kEdgeEps);
+  fw = fmax(0.0, fmin((double)(r.W - 1), fw));            // :195-196
+  fh = fmax(0.0, fmin((double)(r.H - 1), fh));            // :199-200
+  k.pix = (int)fh * r.W + (int)fw;
+  return k;
+}
+
+__device__ __forceinline__ int find_frame(const int64_t* __restrict__ off, int F, int64_t i) {
+  int lo = 0, hi = F;   // largest f with off[f] <= i
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------- point loads (4 points / thread)
+template <typename T> struct Quad { T x[4], y[4], z[4]; uint32_t sem4; };
+
+template <typename T>
+__device__ __forceinline__ void load_quad_scalar(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t i0,
+                                                 int n, Quad<T>& q) {
+  q.sem4 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) {
+      q.x[k] = __ldg(xyz + 3 * (i0 + k)); q.y[k] = __ldg(xyz + 3 * (i0 + k) + 1); q.z[k] = __ldg(xyz + 3 * (i0 + k) + 2);
+      q.sem4 |= (uint32_t)__ldg(sem + i0 + k) << (8 * k);
+    } else { q.x[k] = q.y[k] = q.z[k] = (T)0; }
+  }
+}
+__device__ __forceinline__ void load_quad(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t i0,
+                                          int n, bool vec_ok, Quad<float>& q) {
+  if (vec_ok && n == 4) {   // 4 points = 48 B = three 16-byte loads
+    const float4* p = reinterpret_cast<const float4*>(xyz + 3 * i0);
+    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    q.x[0] = a.x; q.y[0] = a.y; q.z[0] = a.z;
+    q.x[1] = a.w; q.y[1] = b.x; q.z[1] = b.y;
+    q.x[2] = b.z; q.y[2] = b.w; q.z[2] = c.x;
+    q.x[3] = c.y; q.y[3] = c.z; q.z[3] = c.w;
+    q.sem4 = __ldg(reinterpret_cast<const uint32_t*>(sem + i0));
+  } else {
+    load_quad_scalar(xyz, sem, i0, n, q);
+  }
+}
+__device__ __forceinline__ void load_quad(const double* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t i0,
+                                          int n, bool vec_ok, Quad<double>& q) {
+  if (vec_ok && n == 4) {   // 4 points = 96 B = six 16-byte loads
+    const double2* p = reinterpret_cast<const double2*>(xyz + 3 * i0);
+    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5);
+    q.x[0] = a.x; q.y[0] = a.y; q.z[0] = b.x;
+    q.x[1] = b.y; q.y[1] = c.x; q.z[1] = c.y;
+    q.x[2] = d.x; q.y[2] = d.y; q.z[2] = e.x;
+    q.x[3] = e.y; q.y[3] = f.x; q.z[3] = f.y;
+    q.sem4 = __ldg(reinterpret_cast<const uint32_t*>(sem + i0));
+  } else {
+    load_quad_scalar(xyz, sem, i0, n, q);
+  }
+}
+
+__device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
+  unsigned tot = __reduce_add_sync(0xffffffffu, v);
+  if (tot && lane_id() == 0) atomicAdd(reinterpret_cast<unsigned long long*>(diag + slot), (unsigned long long)tot);
+}
+
+// ---------------------------------------------------------------- K1: point pass
+template <typename T, bool DO_VOX, bool DO_RANGE>
+__global__ void __launch_bounds__(kBlock)
+k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
+             bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ pixtab,
+             int64_t* __restrict__ diag) {
+  int64_t i0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * 4;
+  unsigned n_drop = 0, n_nw = 0, n_nh = 0, n_in = 0;
+  if (i0 < P) {
+    int n = (int)min((int64_t)4, P - i0);
+    Quad<T> q;
+    load_quad(xyz, sem, i0, n, vec_ok, q);
+    int f = find_frame(off, F, i0);
+    int64_t fbeg = __ldg(off + f), fend = __ldg(off + f + 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < n) {
+        int64_t i = i0 + k;
+        while (i >= fend) { ++f; fbeg = fend; fend = __ldg(off + f + 1); }
+        if (DO_VOX) {
+          VoxKey v = vox_of((double)q.x[k], (double)q.y[k], (double)q.z[k], g);
+          if (v.in) {
+            ++n_in;
+            atomicOr(bitmap + (size_t)f * g.gw + (v.bit >> 5), 1u << (v.bit & 31));
+          }
+        }
+        if (DO_RANGE) {
+          PixKey pk = pix_of(q.x[k], q.y[k], q.z[k], r);
+          if (!pk.ok) {
+            ++n_drop;
+          } else {
+            n_nw += pk.near_w; n_nh += pk.near_h;
+            uint32_t* slot = pixtab + (size_t)f * r.H * r.W + pk.pix;
+            uint32_t me1 = (uint32_t)(i - fbeg) + 1u;
+            uint32_t old = atomicCAS(slot, 0u, me1);
+            while (old != 0u) {   // occupied: compare against the current winner's key
+              const T* qp = xyz + 3 * (fbeg + (int64_t)(old - 1u));
+              double a, b, c;
+              double dq = range_depth_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c);
+              bool better = (pk.depth < dq) || (pk.depth == dq && me1 < old);
+              if (!better) break;
+              uint32_t prev = atomicCAS(slot, old, me1);
+              if (prev == old) break;
+              old = prev;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (diag) {
+    if (DO_RANGE) {
+      diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
+      diag_add(diag, MUVO_DIAG_NEAR_EDGE_W, n_nw);
+      diag_add(diag, MUVO_DIAG_NEAR_EDGE_H, n_nh);
+    }
+    if (DO_VOX) diag_add(diag, MUVO_DIAG_IN_GRID, n_in);
+  }
+}
+
+// ---------------------------------------------------------------- K2: bitmap scan (one CTA per frame)
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+k_bitmap_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw, int64_t* __restrict__ n_occ_out) {
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
+  __shared__ uint32_t carry_s;
+  const int f = blockIdx.x;
+  const int chunks = gw / 4;
+  const uint4* bm = reinterpret_cast<const uint4*>(bitmap + (size_t)f * gw);
+  uint32_t* pf = prefix + (size_t)f * chunks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  constexpr int kPer = 4;  // chunks per thread per tile (64 contiguous bytes)
+  for (int base = 0; base < chunks; base += kScanThreads * kPer) {
+    int c0 = base + threadIdx.x * kPer;
+    uint32_t cnt[kPer];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      uint32_t c = 0;
+      if (c0 + k < chunks) { uint4 v = bm[c0 + k]; c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+      cnt[k] = c; tsum += c;
+    }
+    uint32_t incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    uint32_t carry = carry_s;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_tot[lane];
+      uint32_t wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+      warp_tot[lane] = wi - w;   // exclusive warp offsets
+      if (lane == 31) carry_s = carry + wi;
+    }
+    __syncthreads();
+    uint32_t ex = carry + warp_tot[warp] + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (c0 + k < chunks) pf[c0 + k] = ex;
+      ex += cnt[k];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && n_occ_out) n_occ_out[f] = (int64_t)carry_s;
+}
+
+// rank of set bit `bit` within its frame (= number of set bits before it)
+__device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_f, const uint32_t* __restrict__ prefix_f,
+                                            uint32_t bit) {
+  uint32_t chunk = bit >> 7;
+  uint4 v = *reinterpret_cast<const uint4*>(bitmap_f + chunk * 4);
+  uint32_t w = (bit >> 5) & 3u;
+  uint32_t below = 0;
+  uint32_t word = v.x;
+  if (w >= 1) { below += __popc(v.x); word = v.y; }
+  if (w >= 2) { below += __popc(v.y); word = v.z; }
+  if (w >= 3) { below += __popc(v.z); word = v.w; }
+  below += __popc(word & ((1u << (bit & 31)) - 1u));
+  return prefix_f[chunk] + below;
+}
+
+// ---------------------------------------------------------------- K3: voxel resolve
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
+                bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                uint32_t* __restrict__ win) {
+  int64_t i0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * 4;
+  if (i0 >= P) return;
+  int n = (int)min((int64_t)4, P - i0);
+  Quad<T> q;
+  load_quad(xyz, sem, i0, n, vec_ok, q);
+  int f = find_frame(off, F, i0);
+  int64_t fbeg = __ldg(off + f), fend = __ldg(off + f + 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) {
+      int64_t i = i0 + k;
+      while (i >= fend) { ++f; fbeg = fend; fend = __ldg(off + f + 1); }
+      VoxKey v = vox_of((double)q.x[k], (double)q.y[k], (double)q.z[k], g);
+      if (v.in) {
+        uint32_t rank = rank_of(bitmap + (size_t)f * g.gw, prefix + (size_t)f * (g.gw / 4), v.bit);
+        uint32_t* slot = win + fbeg + rank;
+        uint32_t me1 = (uint32_t)(i - fbeg) + 1u;
+        bool my_notroad = (int)((q.sem4 >> (8 * k)) & 0xffu) != g.road;
+        uint32_t old = atomicCAS(slot, 0u, me1);
+        while (old != 0u) {
+          int64_t qi = fbeg + (int64_t)(old - 1u);
+          const T* qp = xyz + 3 * qi;
+          VoxKey o = vox_of((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
+          bool o_notroad = (int)__ldg(sem + qi) != g.road;
+          bool better;
+          if (my_notroad != o_notroad) better = !my_notroad;                 // any roadline point wins (:217)
+          else better = (v.dis < o.dis) || (v.dis == o.dis && me1 < old);    // argmin, first minimum (:217)
+          if (!better) break;
+          uint32_t prev = atomicCAS(slot, old, me1);
+          if (prev == old) break;
+          old = prev;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K4: emit
+// Shared by the emit kernels: lane L owns bitmap word (warp_word0 + L); returns the word and the rank of
+// its first bit.  Ranks of the 4 words of a chunk are built with shuffles, so no lane ever re-reads a
+// word that its owner may already have cleared.
+__device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                                                   int64_t word_global, bool valid, uint32_t* word_o, uint32_t* rank_o) {
+  uint32_t word = valid ? bitmap[word_global] : 0u;
+  uint32_t base = valid ? prefix[word_global >> 2] : 0u;
+  uint32_t pc = __popc(word);
+  unsigned lane = lane_id();
+  uint32_t p1 = __shfl_up_sync(0xffffffffu, pc, 1);
+  uint32_t p2 = __shfl_up_sync(0xffffffffu, pc, 2);
+  uint32_t p3 = __shfl_up_sync(0xffffffffu, pc, 3);
+  unsigned k = lane & 3u;
+  uint32_t rank = base + (k >= 1 ? p1 : 0u) + (k >= 2 ? p2 : 0u) + (k >= 3 ? p3 : 0u);
+  *word_o = word; *rank_o = rank;
+}
+
+__device__ __forceinline__ uint32_t label_of_slot(uint32_t* __restrict__ win, const uint8_t* __restrict__ sem,
+                                                  const uint8_t* __restrict__ remap, int64_t fbeg, uint32_t rank, bool clean) {
+  uint32_t* slot = win + fbeg + rank;
+  uint32_t w1 = *slot;
+  if (clean) *slot = 0u;
+  uint32_t lab = 0;
+  if (w1) {
+    lab = __ldg(sem + fbeg + (int64_t)(w1 - 1u));
+    if (remap) lab = __ldg(remap + lab);
+  }
+  return lab;
+}
+
+// 16 voxels (a half word) -> 16 label bytes
+__device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, uint32_t* __restrict__ win,
+                                             const uint8_t* __restrict__ sem, const uint8_t* __restrict__ remap,
+                                             int64_t fbeg, bool clean) {
+  uint32_t o[4] = {0u, 0u, 0u, 0u};
+  while (bits16) {
+    int j = __ffs(bits16) - 1;
+    bits16 &= bits16 - 1;
+    uint32_t lab = label_of_slot(win, sem, remap, fbeg, rank++, clean);
+    o[j >> 2] |= lab << (8 * (j & 3));
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as
+// two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).
+__global__ void __launch_bounds__(kBlock)
+k_emit_dense(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
+             const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, const uint8_t* __restrict__ remap,
+             uint8_t* __restrict__ dense, GridDev g, int F, bool clean) {
+  int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;     // global word index over [F, gw]
+  int64_t total = (int64_t)F * g.gw;
+  bool valid = wg < total;
+  uint32_t word, rank;
+  load_word_and_rank(bitmap, prefix, wg, valid, &word, &rank);
+  unsigned lane = lane_id();
+  int64_t warp_w0 = wg - lane;                                  // first word of this warp (same frame: gw % 32 == 0)
+  if (warp_w0 >= total) return;                                 // whole warp out of range
+  int f = (int)(warp_w0 / g.gw);
+  int64_t fbeg = __ldg(off + f);
+  int64_t vox0 = (warp_w0 - (int64_t)f * g.gw) * 32;            // first voxel of the warp inside the frame
+  uint8_t* dst = dense + (size_t)f * g.G + vox0;
+  bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    unsigned src = (unsigned)half * 16u + (lane >> 1);          // lane j handles piece p = half*32 + j -> word p/2
+    uint32_t w = __shfl_sync(0xffffffffu, word, src);
+    uint32_t rk = __shfl_sync(0xffffffffu, rank, src);
+    uint32_t bits = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
+    if (lane & 1u) rk += __popc(w & 0xffffu);
+    uint4 o = expand_half(bits, rk, win, sem, remap, fbeg, clean);
+    int64_t v = vox0 + ((int64_t)half * 32 + lane) * 16;        // first voxel of this piece
+    if (fast) {
+      if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + ((int64_t)half * 32 + lane) * 16), o);
+    } else {
+      uint32_t oo[4] = {o.x, o.y, o.z, o.w};
+      for (int j = 0; j < 16; ++j)
+        if (v + j < g.G) dense[(size_t)f * g.G + v + j] = (uint8_t)(oo[j >> 2] >> (8 * (j & 3)));
+    }
+  }
+  if (clean && valid && word) bitmap[wg] = 0u;
+}
+
+// Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(frame_offsets[f] + rank)].
+__global__ void __launch_bounds__(kBlock)
+k_emit_sparse(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
+              const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, uint16_t* __restrict__ sparse,
+              GridDev g, int F, bool clean) {
+  int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int64_t total = (int64_t)F * g.gw;
+  bool valid = wg < total;
+  uint32_t word, rank;
+  load_word_and_rank(bitmap, prefix, wg, valid, &word, &rank);
+  if (!valid || !word) return;
+  int f = (int)(wg / g.gw);
+  int64_t fbeg = __ldg(off + f);
+  uint32_t bit0 = (uint32_t)(wg - (int64_t)f * g.gw) * 32u;
+  uint32_t b = word;
+  while (b) {
+    int j = __ffs(b) - 1;
+    b &= b - 1;
+    uint32_t lin = bit0 + (uint32_t)j;
+    uint32_t x = lin % (uint32_t)g.dx;
+    uint32_t yz = lin / (uint32_t)g.dx;
+    uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
+    uint32_t lab = label_of_slot(win, sem, nullptr, fbeg, rank, clean);
+    if (sparse) {
+      uint2 row = make_uint2(x | (y << 16), z | (lab << 16));
+      *reinterpret_cast<uint2*>(sparse + (size_t)(fbeg + rank) * 4) = row;
+    }
+    ++rank;
+  }
+  if (clean) bitmap[wg] = 0u;
+}
+
+// Dense grid when the bitmap is in linear-id order (both outputs requested): per-voxel lookup.
+__global__ void __launch_bounds__(kBlock)
+k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+                         const uint32_t* __restrict__ win, const uint8_t* __restrict__ sem,
+                         const int64_t* __restrict__ off, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense,
+                         GridDev g, int F) {
+  int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (t >= (int64_t)F * g.G) return;
+  int f = (int)(t / g.G);
+  uint32_t d = (uint32_t)(t - (int64_t)f * g.G);
+  uint32_t z = d % (uint32_t)g.dz, xy = d / (uint32_t)g.dz;
+  uint32_t y = xy % (uint32_t)g.dy, x = xy / (uint32_t)g.dy;
+  uint32_t lin = x + (uint32_t)g.dx * (y + (uint32_t)g.dy * z);
+  const uint32_t* bm = bitmap + (size_t)f * g.gw;
+  uint32_t lab = 0;
+  if ((bm[lin >> 5] >> (lin & 31)) & 1u) {
+    uint32_t rank = rank_of(bm, prefix + (size_t)f * (g.gw / 4), lin);
+    int64_t fbeg = __ldg(off + f);
+    uint32_t w1 = win[fbeg + rank];
+    if (w1) { lab = __ldg(sem + fbeg + (int64_t)(w1 - 1u)); if (remap) lab = __ldg(remap + lab); }
+  }
+  dense[t] = (uint8_t)lab;
+}
+
+// Range image: one thread per NP pixels (NP = 4: 16-byte stores; NP = 1: generic fallback).
+template <typename T, int NP, int LAYOUT>
+__global__ void __launch_bounds__(kBlock)
+k_emit_range(uint32_t* __restrict__ pixtab, const T* __restrict__ xyz, const uint8_t* __restrict__ sem,
+             const int64_t* __restrict__ off, RangeDev r, int F, float* __restrict__ depth_out, float* __restrict__ xyz_out,
+             uint8_t* __restrict__ sem_out, bool clean) {
+  const int64_t HW = (int64_t)r.H * r.W;
+  int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int64_t p0 = t * NP;                 // global pixel index over [F, H*W]
+  if (p0 >= (int64_t)F * HW) return;
+  int f = (int)(p0 / HW);
+  int64_t pin = p0 - (int64_t)f * HW;  // pixel inside the frame
+  int64_t fbeg = __ldg(off + f);
+  uint32_t idx[NP];
+  if (NP == 4) {
+    uint4 v = *reinterpret_cast<uint4*>(pixtab + p0);
+    idx[0] = v.x; idx[1 % NP] = v.y; idx[2 % NP] = v.z; idx[3 % NP] = v.w;
+    if (clean && (v.x | v.y | v.z | v.w)) *reinterpret_cast<uint4*>(pixtab + p0) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    idx[0] = pixtab[p0];
+    if (clean && idx[0]) pixtab[p0] = 0u;
+  }
+  float px[NP], py[NP], pz[NP], pd[NP];
+  uint32_t ps = 0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    px[k] = py[k] = pz[k] = 0.f; pd[k] = -1.f;                 // :210-212 initial values
+    if (idx[k]) {
+      int64_t qi = fbeg + (int64_t)(idx[k] - 1u);
+      T x = __ldg(xyz + 3 * qi), y = __ldg(xyz + 3 * qi + 1), z = __ldg(xyz + 3 * qi + 2);
+      double a, b, c;
+      pd[k] = (float)range_depth_of(x, y, z, r, &a, &b, &c);   // :217 float32(depth64)
+      px[k] = (float)x; py[k] = (float)y; pz[k] = (float)z;    // :218 the ego-frame input point
+      ps |= (uint32_t)__ldg(sem + qi) << (8 * k);              // :219
+    }
+  }
+  if (NP == 4) {
+    if (depth_out) st_stream_f4(reinterpret_cast<float4*>(depth_out + p0), make_float4(pd[0], pd[1 % NP], pd[2 % NP], pd[3 % NP]));
+    if (LAYOUT == MUVO_RANGE_LAYOUT_HWC) {
+      float4* o = reinterpret_cast<float4*>(xyz_out + p0 * 3);
+      st_stream_f4(o,     make_float4(px[0], py[0], pz[0], px[1 % NP]));
+      st_stream_f4(o + 1, make_float4(py[1 % NP], pz[1 % NP], px[2 % NP], py[2 % NP]));
+      st_stream_f4(o + 2, make_float4(pz[2 % NP], px[3 % NP], py[3 % NP], pz[3 % NP]));
+    } else {
+      float* base = xyz_out + (size_t)f * 4 * HW + pin;
+      st_stream_f4(reinterpret_cast<float4*>(base),          make_float4(px[0], px[1 % NP], px[2 % NP], px[3 % NP]));
+      st_stream_f4(reinterpret_cast<float4*>(base + HW),     make_float4(py[0], py[1 % NP], py[2 % NP], py[3 % NP]));
+      st_stream_f4(reinterpret_cast<float4*>(base + 2 * HW), make_float4(pz[0], pz[1 % NP], pz[2 % NP], pz[3 % NP]));
+      st_stream_f4(reinterpret_cast<float4*>(base + 3 * HW), make_float4(pd[0], pd[1 % NP], pd[2 % NP], pd[3 % NP]));
+    }
+    if (sem_out) st_stream_u32(reinterpret_cast<uint32_t*>(sem_out + p0), ps);
+  } else {
+    if (depth_out) depth_out[p0] = pd[0];
+    if (LAYOUT == MUVO_RANGE_LAYOUT_HWC) {
+      xyz_out[p0 * 3] = px[0]; xyz_out[p0 * 3 + 1] = py[0]; xyz_out[p0 * 3 + 2] = pz[0];
+    } else {
+      float* base = xyz_out + (size_t)f * 4 * HW + pin;
+      base[0] = px[0]; base[HW] = py[0]; base[2 * HW] = pz[0]; base[3 * HW] = pd[0];
+    }
+    if (sem_out) sem_out[p0] = (uint8_t)ps;
+  }
+}
+
+// ---------------------------------------------------------------- host side
+static bool is_pow2_double(double v) {
+  if (!(v > 0.0) || !isfinite(v)) return false;
+  int e;
+  return frexp(v, &e) == 0.5;
+}
+
+static int make_grid_dev(const MuvoGrid* g, int order, GridDev* o) {
+  if (g->size[0] <= 0 || g->size[1] <= 0 || g->size[2] <= 0 || !(g->res > 0.0)) return MUVO_E_ARG;
+  if (g->size[0] > 65535 || g->size[1] > 65535 || g->size[2] > 65535) return MUVO_E_SHAPE;   // uint16 coordinates (:195)
+  int64_t G = (int64_t)g->size[0] * g->size[1] * g->size[2];
+  if (G > ((int64_t)1 << 31) - 1024) return MUVO_E_SHAPE;
+  o->res = g->res; o->inv_res = 1.0 / g->res;
+  for (int k = 0; k < 3; ++k) { o->off[k] = g->offset[k]; o->up[k] = g->upper[k]; }
+  o->dx = g->size[0]; o->dy = g->size[1]; o->dz = g->size[2];
+  o->road = g->roadline_id;
+  o->pow2 = is_pow2_double(g->res) ? 1 : 0;
+  o->order = order;
+  o->gw = bitmap_words(G);
+  o->G = G;
+  return MUVO_OK;
+}
+
+static int make_range_dev(const MuvoRangeCfg* c, RangeDev* o) {
+  if (c->H <= 0 || c->W <= 0 || !(c->fov != 0.0)) return MUVO_E_ARG;
+  if ((int64_t)c->H * c->W > ((int64_t)1 << 30)) return MUVO_E_SHAPE;
+  o->H = c->H; o->W = c->W; o->fda = c->fov_down_abs; o->fov = c->fov;
+  for (int k = 0; k < 3; ++k) o->L[k] = c->lidar_pos[k];
+  return MUVO_OK;
+}
+
+static inline unsigned blocks_for(int64_t n) { return (unsigned)ceil_div64(n, kBlock); }
+
+template <typename T>
+static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int F, int64_t P, const MuvoGrid* grid_h,
+                      const uint8_t* remap, const MuvoRangeCfg* cfg_h, int layout, uint8_t* dense, uint16_t* sparse,
+                      int64_t* n_occ, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  const bool do_vox = grid_h != nullptr, do_range = cfg_h != nullptr;
+  if (!do_vox && !do_range) return MUVO_E_ARG;
+  if (F < 0 || P < 0) return MUVO_E_ARG;
+  if (F == 0) return MUVO_OK;
+  if (!off || !ws) return MUVO_E_NULL;
+  if (P > 0 && (!xyz || !sem)) return MUVO_E_NULL;
+  if (P >= ((int64_t)1 << 40)) return MUVO_E_SHAPE;
+  if (do_vox && !dense && !sparse && !n_occ) return MUVO_E_NULL;
+  if (do_range && (!xyz_out || (layout == MUVO_RANGE_LAYOUT_HWC && (!depth_out || !sem_out)))) return MUVO_E_NULL;
+  if (layout != MUVO_RANGE_LAYOUT_HWC && layout != MUVO_RANGE_LAYOUT_XYZD) return MUVO_E_ARG;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
+  GridDev g{}; RangeDev r{};
+  int rc;
+  const int order = (sparse != nullptr) ? ORDER_LINEAR : ORDER_DENSE;
+  if (do_vox && (rc = make_grid_dev(grid_h, order, &g)) != MUVO_OK) return rc;
+  if (do_range && (rc = make_range_dev(cfg_h, &r)) != MUVO_OK) return rc;
+  PointsWs w = carve(ws, P, F, grid_h, cfg_h);
+  if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 4 == 0);
+  const unsigned pblocks = blocks_for(ceil_div64(P, 4));
+
+  // K1
+  if (P > 0) {
+    if (do_vox && do_range)
+      k_point_pass<T, true, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
+    else if (do_vox)
+      k_point_pass<T, true, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
+    else
+      k_point_pass<T, false, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
+    MUVO_LAUNCH_CHECK();
+  }
+  if (do_vox) {
+    // K2
+    k_bitmap_scan<<<F, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, n_occ);
+    MUVO_LAUNCH_CHECK();
+    // K3
+    if (P > 0) {
+      k_voxel_resolve<T><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.win);
+      MUVO_LAUNCH_CHECK();
+    }
+    // K4 (the last consumer of the tables clears them)
+    const int64_t words = (int64_t)F * g.gw;
+    if (order == ORDER_DENSE) {
+      if (dense) {
+        k_emit_dense<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, remap, dense, g, F, true);
+      } else {  // only n_occ requested: clear through the sparse walker without output
+        k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, nullptr, g, F, true);
+      }
+      MUVO_LAUNCH_CHECK();
+    } else {
+      if (dense) {
+        k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off,
+                                                                                 remap, dense, g, F);
+        MUVO_LAUNCH_CHECK();
+      }
+      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, sparse, g, F, true);
+      MUVO_LAUNCH_CHECK();
+    }
+  }
+  if (do_range) {
+    const int64_t HW = (int64_t)r.H * r.W;
+    const bool vec4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz_out) % 16 == 0) &&
+                      (!depth_out || reinterpret_cast<uintptr_t>(depth_out) % 16 == 0) &&
+                      (!sem_out || reinterpret_cast<uintptr_t>(sem_out) % 4 == 0);
+    const int64_t npix = (int64_t)F * HW;
+    if (vec4) {
+      if (layout == MUVO_RANGE_LAYOUT_HWC)
+        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+      else
+        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+    } else {
+      if (layout == MUVO_RANGE_LAYOUT_HWC)
+        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+      else
+        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+    }
+    MUVO_LAUNCH_CHECK();
+  }
+  return MUVO_OK;
+}
+
+}  // namespace
+}  // namespace muvo
+
+using namespace muvo;
+
+extern "C" {
+
+int muvo_points_workspace_bytes(int64_t n_points_total, int32_t n_frames, const MuvoGrid* grid_h,
+                                const MuvoRangeCfg* range_h, size_t* bytes_out_h) {
+  if (!bytes_out_h) return MUVO_E_NULL;
+  if (n_points_total < 0 || n_frames < 0) return MUVO_E_ARG;
+  PointsWs w = carve(nullptr, n_points_total, n_frames, grid_h, range_h);
+  *bytes_out_h = w.bytes + 256;
+  return MUVO_OK;
+}
+
+int muvo_ws_reset(void* ws, size_t ws_bytes, void* stream) {
+  if (!ws) return MUVO_E_NULL;
+  cudaError_t e = cudaMemsetAsync(ws, 0, ws_bytes, (cudaStream_t)stream);
+  return e == cudaSuccess ? MUVO_OK : (int)e;
+}
+
+int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* sem, const int64_t* frame_offsets,
+                  int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
+                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* diag, void* ws,
+                  size_t ws_bytes, void* stream) {
+  if (!grid_h) return MUVO_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (xyz_dtype == MUVO_F32)
+    return run_points<float>((const float*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256, nullptr,
+                             0, dense_out, sparse_out, n_occ_out, nullptr, nullptr, nullptr, diag, ws, ws_bytes, st);
+  if (xyz_dtype == MUVO_F64)
+    return run_points<double>((const double*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256,
+                              nullptr, 0, dense_out, sparse_out, n_occ_out, nullptr, nullptr, nullptr, diag, ws,
+                              ws_bytes, st);
+  return MUVO_E_ARG;
+}
+
+int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
+                       int64_t n_points_total, const MuvoRangeCfg* cfg_h, int32_t layout, float* depth_out,
+                       float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, void* stream) {
+  if (!cfg_h) return MUVO_E_NULL;
+  return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, nullptr, nullptr, cfg_h, layout, nullptr,
+                           nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
+                      int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
+                      const MuvoRangeCfg* cfg_h, int32_t layout, uint8_t* dense_out, uint16_t* sparse_out,
+                      int64_t* n_occ_out, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws,
+                      size_t ws_bytes, void* stream) {
+  if (!grid_h || !cfg_h) return MUVO_E_NULL;
+  return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256, cfg_h, layout,
+                           dense_out, sparse_out, n_occ_out, depth_out, xyz_out, sem_out, diag, ws, ws_bytes,
+                           (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+// Stage (d): voxel-occupancy IoU / tp-fp-fn counts.
+//
+// Replaces SSCMetrics.get_score_completion + get_score_semantic_and_completion
+// (muvo/metrics.py:143-216): one streaming pass over (pred, target[, masks]) instead of
+// (3 + 3C) masked passes per frame with a host sync each.  Integer counts only -> bit-exact and
+// order-independent.  HBM bound: 9 B/voxel (int64 pred + uint8 target).
+//
+// Per-thread private counters live in shared memory as cnt[bin][thread] (bank = thread -> no
+// conflicts, no atomics); one u64 atomicAdd per (block, bin) at the end.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace muvo {
+namespace {
+
+constexpr int kTileVox = 512;   // voxels per warp tile: 8 x (32 lanes x 2 voxels)
+
+template <typename PT> struct PredVec;   // 2 consecutive predictions per lane per load
+template <> struct PredVec<int64_t> {
+  static __device__ __forceinline__ void load2(const int64_t* p, int64_t v, int64_t n, long long& a, long long& b) {
+    if (v + 1 < n && ((reinterpret_cast<uintptr_t>(p + v) & 15) == 0)) {
+      longlong2 t;
+      asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(t.x), "=l"(t.y) : "l"(p + v));
+      a = t.x; b = t.y;
+    } else { a = v < n ? p[v] : 0; b = v + 1 < n ? p[v + 1] : 0; }
+  }
+};
+template <> struct PredVec<int32_t> {
+  static __device__ __forceinline__ void load2(const int32_t* p, int64_t v, int64_t n, long long& a, long long& b) {
+    a = v < n ? __ldg(p + v) : 0; b = v + 1 < n ? __ldg(p + v + 1) : 0;
+  }
+};
+template <> struct PredVec<int16_t> {
+  static __device__ __forceinline__ void load2(const int16_t* p, int64_t v, int64_t n, long long& a, long long& b) {
+    a = v < n ? __ldg(p + v) : 0; b = v + 1 < n ? __ldg(p + v + 1) : 0;
+  }
+};
+template <> struct PredVec<uint8_t> {
+  static __device__ __forceinline__ void load2(const uint8_t* p, int64_t v, int64_t n, long long& a, long long& b) {
+    a = v < n ? __ldg(p + v) : 0; b = v + 1 < n ? __ldg(p + v + 1) : 0;
+  }
+};
+
+__device__ __forceinline__ void load2_u8(const uint8_t* p, int64_t v, int64_t n, uint32_t& a, uint32_t& b) {
+  if (v + 1 < n && ((reinterpret_cast<uintptr_t>(p + v) & 1) == 0)) {
+    uint16_t t = __ldg(reinterpret_cast<const uint16_t*>(p + v));
+    a = t & 0xffu; b = t >> 8;
+  } else { a = v < n ? __ldg(p + v) : 0; b = v + 1 < n ? __ldg(p + v + 1) : 0; }
+}
+
+struct Comp { unsigned tp, fp, fn; };
+
+// counters: cnt[(bin) * blockDim.x + tid]; bins: tp[0..C), fp[C..2C), fn[2C..3C)
+__device__ __forceinline__ void tally(long long p, uint32_t t, bool sem_valid, bool comp_valid, int C, uint32_t* cnt,
+                                      int nthr, int tid, Comp& c) {
+  const bool is255 = (t == 255u);
+  if (is255) { p = 0; t = 0; }                       // :150-151, :184-185
+  const bool bt = t > 0u, bp = p > 0;                // :157-160
+  if (comp_valid) { c.tp += (bt && bp); c.fp += (!bt && bp); c.fn += (bt && !bp); }   // :170-172
+  if (sem_valid) {                                   // :207-214
+    if (p == (long long)t) {
+      if ((int)t < C) cnt[(int)t * nthr + tid] += 1u;
+    } else {
+      if (p >= 0 && p < C) cnt[(C + (int)p) * nthr + tid] += 1u;
+      if ((int)t < C) cnt[(2 * C + (int)t) * nthr + tid] += 1u;
+    }
+  }
+}
+
+__device__ __forceinline__ void flush_counts(uint32_t* cnt, int C, Comp c, int64_t* out) {
+  const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  __syncthreads();
+  for (int bin = warp; bin < 3 * C; bin += nwarp) {
+    unsigned long long s = 0;
+    for (int t = lane; t < nthr; t += 32) s += cnt[bin * nthr + t];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0 && s) atomicAdd(reinterpret_cast<unsigned long long*>(out + 3 + bin), s);
+  }
+  unsigned long long a = c.tp, b = c.fp, d2 = c.fn;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, d); b += __shfl_xor_sync(0xffffffffu, b, d); d2 += __shfl_xor_sync(0xffffffffu, d2, d);
+  }
+  if (lane == 0) {
+    if (a) atomicAdd(reinterpret_cast<unsigned long long*>(out + 0), a);
+    if (b) atomicAdd(reinterpret_cast<unsigned long long*>(out + 1), b);
+    if (d2) atomicAdd(reinterpret_cast<unsigned long long*>(out + 2), d2);
+  }
+}
+
+template <typename PT>
+__global__ void k_ssc_counts(const PT* __restrict__ pred, const uint8_t* __restrict__ target, const uint8_t* __restrict__ nonempty,
+                             const uint8_t* __restrict__ nonsurface, int ignore255, int64_t n, int C, int64_t* __restrict__ out) {
+  extern __shared__ uint32_t cnt[];
+  const int nthr = blockDim.x, tid = threadIdx.x, lane = tid & 31;
+  for (int i = tid; i < 3 * C * nthr; i += nthr) cnt[i] = 0;
+  __syncthreads();
+  Comp c{0, 0, 0};
+  const int64_t warp_global = ((int64_t)blockIdx.x * nthr + tid) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * nthr) >> 5;
+  const int64_t n_tiles = ceil_div64(n, kTileVox);
+  for (int64_t tile = warp_global; tile < n_tiles; tile += n_warps) {
+    const int64_t base = tile * kTileVox;
+    long long pa[8], pb[8];
+    uint32_t ta[8], tb[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {   // all loads first: 8 x 16 B (pred) + 8 x 2 B (target) in flight per lane
+      int64_t v = base + k * 64 + lane * 2;
+      PredVec<PT>::load2(pred, v, n, pa[k], pb[k]);
+      load2_u8(target, v, n, ta[k], tb[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int64_t v = base + k * 64 + lane * 2;
+      uint32_t ea = 1, eb = 1, sa = 1, sb = 1;
+      if (nonempty) load2_u8(nonempty, v, n, ea, eb);
+      if (nonsurface) load2_u8(nonsurface, v, n, sa, sb);
+      bool va = v < n && ea && !(ignore255 && ta[k] == 255u);
+      bool vb = v + 1 < n && eb && !(ignore255 && tb[k] == 255u);
+      tally(pa[k], ta[k], va, va && sa, C, cnt, nthr, tid, c);
+      tally(pb[k], tb[k], vb, vb && sb, C, cnt, nthr, tid, c);
+    }
+  }
+  flush_counts(cnt, C, c, out);
+}
+
+// Fused argmax + counts: logits [F, C, S]; lane-coalesced along S for every class plane.
+template <typename LT> __device__ __forceinline__ float to_f32(LT v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename LT>
+__global__ void k_ssc_from_logits(const LT* __restrict__ logits, const uint8_t* __restrict__ target, int F, int C, int64_t S,
+                                  int ignore255, int64_t* __restrict__ out) {
+  extern __shared__ uint32_t cnt[];
+  const int nthr = blockDim.x, tid = threadIdx.x;
+  for (int i = tid; i < 3 * C * nthr; i += nthr) cnt[i] = 0;
+  __syncthreads();
+  Comp c{0, 0, 0};
+  const int64_t total = (int64_t)F * S;
+  for (int64_t v = (int64_t)blockIdx.x * nthr + tid; v < total; v += (int64_t)gridDim.x * nthr) {
+    const int64_t f = v / S, s = v - f * S;
+    const LT* lp = logits + (size_t)f * C * S + s;
+    float best = to_f32<LT>(lp[0]);
+    int arg = 0;
+    for (int k = 1; k < C; ++k) {      // torch.argmax: first maximum; NaN counts as maximal
+      float x = to_f32<LT>(lp[(size_t)k * S]);
+      if (x > best || (x != x && best == best)) { best = x; arg = k; }
+    }
+    uint32_t t = __ldg(target + v);
+    bool valid = !(ignore255 && t == 255u);
+    tally((long long)arg, t, valid, valid, C, cnt, nthr, tid, c);
+  }
+  flush_counts(cnt, C, c, out);
+}
+
+static int pick_threads(int C, size_t* smem) {
+  for (int thr = 256; thr >= 64; thr >>= 1) {
+    size_t b = (size_t)3 * C * thr * 4;
+    if (b <= 200 * 1024) { *smem = b; return thr; }
+  }
+  return 0;
+}
+
+static int blocks_per_sm(size_t smem, int thr) {
+  int by_smem = (int)((220 * 1024) / (smem + 1024));
+  int by_thr = 2048 / thr;
+  int v = by_smem < by_thr ? by_smem : by_thr;
+  return v < 1 ? 1 : v;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t smem) {
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return 0;
+}
+
+template <typename PT>
+static int launch_counts(const void* pred, const uint8_t* target, const uint8_t* ne, const uint8_t* ns, int ignore255,
+                         int64_t n, int C, int64_t* out, cudaStream_t st) {
+  size_t smem; int thr = pick_threads(C, &smem);
+  if (!thr) return MUVO_E_ARG;
+  int rc = set_smem(k_ssc_counts<PT>, smem);
+  if (rc) return rc;
+  int per_sm = blocks_per_sm(smem, thr);
+  int64_t want = ceil_div64(ceil_div64(n, kTileVox) * 32, thr);
+  int64_t cap = (int64_t)kNumSMsB200 * per_sm;
+  unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  k_ssc_counts<PT><<<grid, thr, smem, st>>>((const PT*)pred, target, ne, ns, ignore255, n, C, out);
+  MUVO_LAUNCH_CHECK();
+  return MUVO_OK;
+}
+
+template <typename LT>
+static int launch_logits(const void* logits, const uint8_t* target, int F, int C, int64_t S, int ignore255, int64_t* out,
+                         cudaStream_t st) {
+  size_t smem; int thr = pick_threads(C, &smem);
+  if (!thr) return MUVO_E_ARG;
+  int rc = set_smem(k_ssc_from_logits<LT>, smem);
+  if (rc) return rc;
+  int per_sm = blocks_per_sm(smem, thr);
+  int64_t want = ceil_div64((int64_t)F * S, thr);
+  int64_t cap = (int64_t)kNumSMsB200 * per_sm;
+  unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  k_ssc_from_logits<LT><<<grid, thr, smem, st>>>((const LT*)logits, target, F, C, S, ignore255, out);
+  MUVO_LAUNCH_CHECK();
+  return MUVO_OK;
+}
+
+}  // namespace
+}  // namespace muvo
+
+using namespace muvo;
+
+extern "C" {
+
+int muvo_ssc_counts(const void* pred, int32_t pred_dtype, const uint8_t* target, const uint8_t* nonempty,
+                    const uint8_t* nonsurface, int32_t ignore255, int64_t n_voxels, int32_t n_classes,
+                    int64_t* counts_out, void* stream) {
+  if (!counts_out) return MUVO_E_NULL;
+  if (n_voxels < 0 || n_classes <= 0) return MUVO_E_ARG;
+  if (n_voxels == 0) return MUVO_OK;
+  if (!pred || !target) return MUVO_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (pred_dtype) {
+    case MUVO_I64: return launch_counts<int64_t>(pred, target, nonempty, nonsurface, ignore255, n_voxels, n_classes, counts_out, st);
+    case MUVO_I32: return launch_counts<int32_t>(pred, target, nonempty, nonsurface, ignore255, n_voxels, n_classes, counts_out, st);
+    case MUVO_I16: return launch_counts<int16_t>(pred, target, nonempty, nonsurface, ignore255, n_voxels, n_classes, counts_out, st);
+    case MUVO_U8:  return launch_counts<uint8_t>(pred, target, nonempty, nonsurface, ignore255, n_voxels, n_classes, counts_out, st);
+    default: return MUVO_E_ARG;
+  }
+}
+
+int muvo_ssc_counts_from_logits(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames,
+                                int32_t n_classes, int64_t voxels_per_frame, int32_t ignore255, int64_t* counts_out,
+                                void* stream) {
+  if (!counts_out) return MUVO_E_NULL;
+  if (n_frames < 0 || n_classes <= 0 || voxels_per_frame < 0) return MUVO_E_ARG;
+  if (n_frames == 0 || voxels_per_frame == 0) return MUVO_OK;
+  if (!logits || !target) return MUVO_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (logits_dtype) {
+    case MUVO_F32:  return launch_logits<float>(logits, target, n_frames, n_classes, voxels_per_frame, ignore255, counts_out, st);
+    case MUVO_F16:  return launch_logits<__half>(logits, target, n_frames, n_classes, voxels_per_frame, ignore255, counts_out, st);
+    case MUVO_BF16: return launch_logits<__nv_bfloat16>(logits, target, n_frames, n_classes, voxels_per_frame, ignore255, counts_out, st);
+    default: return MUVO_E_ARG;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,276 @@
+"""Stage (c): lift-splat BEV pooling module backed by ``libmuvo_b200.so``.
+
+Drop-in for ``muvo/models/frustum_pooling.py`` (``FrustumPooling``, ``QuickCumsum``,
+``cumsum_trick``, ``quick_cumsum``, ``gen_dx_bx``) and ``VoxelsSumming``
+(muvo/layers/layers.py:326-357).  Same constructor, buffers (``bev_intrinsics`` is the
+only persistent one, so released checkpoints load with ``strict=True``), call
+signatures and output layout ``(B, C*nz, ny, nx)``.
+
+What stays in torch (plumbing): the frustum grid and the camera->ego->BEV geometry, using
+the reference's own op sequence so the integer cell ids are bit-identical on the same
+device (the kernel only ever sees integer cell ids).  What moves into CUDA: everything
+that touches the feature tensor -- no reshape copy, no boolean compaction, no sort of
+feature rows, no prefix sum; x is read once in place through its strides.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, _ws
+
+_FLOAT_DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def bev_params_to_intrinsics(size, scale, offsetx):
+    """muvo/utils/geometry_utils.py:8-19."""
+    return np.array([[1 / scale, 0, size[0] / 2 + offsetx],
+                     [0, -1 / scale, size[1] / 2],
+                     [0, 0, 1]], dtype=np.float32)
+
+
+def intrinsics_inverse(intrinsics):
+    """muvo/utils/geometry_utils.py:22-34 (closed form)."""
+    fx, fy = intrinsics[..., 0, 0], intrinsics[..., 1, 1]
+    cx, cy = intrinsics[..., 0, 2], intrinsics[..., 1, 2]
+    one, zero = torch.ones_like(fx), torch.zeros_like(fx)
+    return torch.stack((torch.stack((1 / fx, zero, -cx / fx), -1),
+                        torch.stack((zero, 1 / fy, -cy / fy), -1),
+                        torch.stack((zero, zero, one), -1)), -2)
+
+
+def gen_dx_bx(size, scale, offsetx):
+    """muvo/models/frustum_pooling.py:10-20."""
+    xbound = [-size[0] * scale / 2 - offsetx * scale, size[0] * scale / 2 - offsetx * scale, scale]
+    ybound = [-size[1] * scale / 2, size[1] * scale / 2, scale]
+    zbound = [-10.0, 10.0, 20.0]
+    rows = [xbound, ybound, zbound]
+    dx = torch.Tensor([row[2] for row in rows])
+    bx = torch.Tensor([row[0] + row[2] / 2.0 for row in rows])
+    nx = torch.LongTensor([np.round((row[1] - row[0]) / row[2]) for row in rows])
+    return dx, bx, nx
+
+
+# --------------------------------------------------------------------------- kernels as autograd functions
+def _strides_bpc(x: torch.Tensor):
+    """View ``x (B,N,D,H,W,C)`` as ``[B, n_pts, C]`` with element strides, without copying when possible."""
+    B, N, D, H, W, Cc = x.shape
+    n_pts = N * D * H * W
+    s = x.stride()
+    # the point index p = ((n*D + d)*H + h)*W + w must be expressible with ONE stride
+    sp = s[4]
+    ok = True
+    ext = W
+    for dim in (3, 2, 1):
+        if x.shape[dim] != 1 and s[dim] != sp * ext:
+            ok = False
+            break
+        ext *= x.shape[dim]
+    if not ok or (B > 1 and s[0] < 0) or sp <= 0 or s[5] <= 0:
+        x = x.contiguous()
+        s = x.stride()
+        sp = s[4]
+    return x, int(s[0]), int(sp), int(s[5]), n_pts
+
+
+class _BevPool(torch.autograd.Function):
+    """out[b, c, cell] = sum over points p of frame b with cell[b,p] == cell of x[b,p,c] (ascending p)."""
+
+    @staticmethod
+    def forward(ctx, x, cell, n_cells):
+        _lib.require_cuda(x, cell)
+        if x.dtype not in _FLOAT_DTYPES:
+            raise TypeError(f"unsupported feature dtype {x.dtype}")
+        lib = _lib.load()
+        xv, sb, sp, sc, n_pts = _strides_bpc(x)
+        B, Cc = x.shape[0], x.shape[5]
+        dev = x.device
+        cell = cell.reshape(B, n_pts).contiguous()
+        out = torch.empty((B, Cc, n_cells), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(dev)
+            nb = C.c_size_t(0)
+            _lib.check(lib.muvo_bev_pool_workspace_bytes(B, n_pts, n_cells, C.byref(nb)), "muvo_bev_pool_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            rc = lib.muvo_bev_pool_fwd(_lib.ptr(xv), _FLOAT_DTYPES[xv.dtype], sb, sp, sc, _lib.ptr(cell), B, n_pts, Cc,
+                                       n_cells, out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "muvo_bev_pool_fwd")
+        ctx.save_for_backward(cell)
+        ctx.meta = (tuple(x.shape), x.dtype, n_cells, x.stride())
+        ctx.mark_non_differentiable(cell)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (cell,) = ctx.saved_tensors
+        shape, dtype, n_cells, xstride = ctx.meta
+        B, N, D, H, W, Cc = shape
+        n_pts = N * D * H * W
+        dev = grad_out.device
+        go = grad_out.contiguous().float()
+        # write the gradient in the producer's memory format: if x was a permuted (B,C,D,H,W) view
+        # (mile.py:517-521) so is grad_x, and the permute/mul backward consume it without a copy.
+        if xstride[5] >= xstride[4] and xstride[4] == 1:
+            base = torch.empty((B, Cc, N, D, H, W), dtype=dtype, device=dev)
+            gx = base.permute(0, 2, 3, 4, 5, 1)
+        else:
+            gx = torch.empty(shape, dtype=dtype, device=dev)
+        gv, sb, sp, sc, _ = _strides_bpc(gx)
+        with torch.cuda.device(dev):
+            rc = _lib.load().muvo_bev_pool_bwd(go.data_ptr(), _lib.ptr(cell), B, n_pts, Cc, n_cells, gv.data_ptr(),
+                                               _FLOAT_DTYPES[dtype], sb, sp, sc, _lib.current_stream(dev))
+        _lib.check(rc, "muvo_bev_pool_bwd")
+        return gx, None, None
+
+
+def bev_pool(x: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
+    """``x (B,N,D,H,W,C)`` any strides, ``cell (B, N*D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
+    return _BevPool.apply(x, cell, int(n_cells))
+
+
+class QuickCumsum(torch.autograd.Function):
+    """Sorted-rank segment sum; drop-in for ``QuickCumsum`` (frustum_pooling.py:34-60)."""
+
+    @staticmethod
+    def forward(ctx, x, geom_feats, ranks):
+        _lib.require_cuda(x, ranks)
+        lib = _lib.load()
+        n = int(x.shape[0])
+        Cc = int(x[0].numel()) if n else int(np.prod(x.shape[1:]))
+        dev = x.device
+        in_dtype = x.dtype
+        xf = x.reshape(n, Cc).contiguous().float()                 # cumsum runs in fp32 under autocast too
+        rk = ranks.contiguous().to(torch.int64)
+        seg_id = torch.empty((max(n, 1),), dtype=torch.int32, device=dev)
+        last_row = torch.empty((max(n, 1),), dtype=torch.int64, device=dev)
+        n_seg_t = torch.zeros((1,), dtype=torch.int32, device=dev)
+        x_seg = torch.empty((max(n, 1), Cc), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(dev)
+            nb = C.c_size_t(0)
+            _lib.check(lib.muvo_segment_sum_workspace_bytes(n, C.byref(nb)), "muvo_segment_sum_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            rc = lib.muvo_segment_sum_fwd(_lib.ptr(xf), _lib.ptr(rk), n, Cc, seg_id.data_ptr(), n_seg_t.data_ptr(),
+                                          x_seg.data_ptr(), last_row.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "muvo_segment_sum_fwd")
+        n_seg = int(n_seg_t.item())          # data-dependent output shape: one sync, as the reference's x[kept]
+        x_seg = x_seg[:n_seg].reshape((n_seg,) + tuple(x.shape[1:])).to(in_dtype)
+        geom_out = geom_feats[last_row[:n_seg]]
+        ctx.save_for_backward(seg_id[:n])
+        ctx.meta = (n, Cc, tuple(x.shape), in_dtype)
+        ctx.mark_non_differentiable(geom_out)
+        return x_seg, geom_out
+
+    @staticmethod
+    def backward(ctx, gradx, gradgeom):
+        (seg_id,) = ctx.saved_tensors
+        n, Cc, shape, in_dtype = ctx.meta
+        dev = gradx.device
+        g = gradx.reshape(-1, Cc).contiguous().float()
+        out = torch.empty((n, Cc), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().muvo_segment_sum_bwd(_lib.ptr(g), _lib.ptr(seg_id), n, Cc, _lib.ptr(out), _lib.current_stream(dev))
+        _lib.check(rc, "muvo_segment_sum_bwd")
+        return out.reshape(shape).to(in_dtype), None, None
+
+
+class VoxelsSumming(QuickCumsum):
+    """Drop-in for ``muvo.layers.layers.VoxelsSumming`` (layers.py:326-357): same op, same signature."""
+
+
+def quick_cumsum(x, geom_feats, ranks):
+    return QuickCumsum.apply(x, geom_feats, ranks)
+
+
+def cumsum_trick(x, geom_feats, ranks):
+    """Eval-mode twin (frustum_pooling.py:23-31): identical values, no autograd bookkeeping needed."""
+    with torch.no_grad():
+        xs, gs = QuickCumsum.apply(x, geom_feats, ranks)
+    return xs, gs
+
+
+# --------------------------------------------------------------------------- the module
+class FrustumPooling(nn.Module):
+    def __init__(self, size, scale, offsetx, dbound, downsample, use_quickcumsum=True):
+        """Pools camera frustums into Birds Eye View (constructor of frustum_pooling.py:68-95)."""
+        super().__init__()
+        self.register_buffer('bev_intrinsics', torch.tensor(bev_params_to_intrinsics(size, scale, offsetx)))
+        dx, bx, nx = gen_dx_bx(size, scale, offsetx)
+        self.nx_constant = nx.numpy().tolist()
+        self.register_buffer('dx', dx, persistent=False)
+        self.register_buffer('bx', bx, persistent=False)
+        self.register_buffer('nx', nx, persistent=False)
+        self.use_quickcumsum = use_quickcumsum
+        self.dbound = dbound
+        ds = torch.arange(self.dbound[0], self.dbound[1], self.dbound[2], dtype=torch.float32)
+        self.D = len(ds)
+        self.register_buffer('ds', ds, persistent=False)
+        self.downsample = downsample
+        self.register_buffer('frustum', torch.zeros(0, ), persistent=False)
+
+    def initialize_frustum(self, image):
+        """frustum_pooling.py:97-109."""
+        if self.frustum.shape[0] == 0:
+            device = image.device
+            fH, fW = image.shape[-3:-1]
+            ogfH, ogfW = fH * self.downsample, fW * self.downsample
+            ds = self.ds.view(-1, 1, 1).expand(-1, fH, fW)
+            xs = torch.linspace(0, ogfW - 1, fW, dtype=torch.float, device=device).view(1, 1, fW).expand(self.D, fH, fW)
+            ys = torch.linspace(0, ogfH - 1, fH, dtype=torch.float, device=device).view(1, fH, 1).expand(self.D, fH, fW)
+            self.frustum = torch.stack((xs, ys, ds), -1)
+
+    def get_geometry(self, rots, trans, intrins):
+        """frustum_pooling.py:111-129: (x,y,z) ego-frame locations, ``B x N x D x H x W x 3``."""
+        B, N = trans.shape[:2]
+        points = self.frustum.unsqueeze(0).unsqueeze(0).unsqueeze(-1)
+        points = torch.cat((points[:, :, :, :, :, :2] * points[:, :, :, :, :, 2:3], points[:, :, :, :, :, 2:3]), 5)
+        combine = rots.matmul(intrinsics_inverse(intrins))
+        points = combine.view(B, N, 1, 1, 1, 3, 3).matmul(points).squeeze(-1)
+        points += trans.view(B, N, 1, 1, 1, 3)
+        return points
+
+    def cell_ids(self, geom_feats, mask):
+        """Integer BEV cell per frustum point, -1 where dropped (frustum_pooling.py:139-163), int32 ``(B, n_pts)``."""
+        B = geom_feats.shape[0]
+        g = geom_feats.reshape(-1, 3)
+        gx = (g[:, 0] * self.bev_intrinsics[0, 0] + self.bev_intrinsics[0, 2]).long()        # :142,:146 (.long() truncates)
+        gy = (g[:, 1] * self.bev_intrinsics[1, 1] + self.bev_intrinsics[1, 2]).long()        # :143
+        gz = ((g[:, 2] - self.bx[2] + self.dx[2] / 2.) / self.dx[2]).long()                  # :145
+        nx, ny, nz = self.nx_constant
+        kept = (gx >= 0) & (gx < nx) & (gy >= 0) & (gy < ny) & (gz >= 0) & (gz < nz)         # :159-161
+        if len(mask) > 0:
+            kept = kept & mask.reshape(-1).bool()                                            # :153-156
+        cell = (gz * ny + gy) * nx + gx
+        cell = torch.where(kept, cell, torch.full_like(cell, -1)).to(torch.int32)
+        return cell.view(B, -1)
+
+    def voxel_pooling(self, geom_feats, x, mask):
+        """frustum_pooling.py:131-187 -> ``(B, C*nz, ny, nx)``."""
+        B, N, D, H, W, Cc = x.shape
+        nx, ny, nz = self.nx_constant
+        cell = self.cell_ids(geom_feats, mask)
+        out = bev_pool(x, cell, nx * ny * nz)                 # (B, C, nz*ny*nx), fp32 (cumsum's autocast dtype)
+        # (B, C, nz, ny, nx) -> cat(unbind(dim=2), 1) == (B, nz*C, ny, nx) with z-major channel blocks (:185)
+        out = out.view(B, Cc, nz, ny, nx)
+        if nz == 1:
+            return out.view(B, Cc, ny, nx)
+        return out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
+
+    def forward(self, x, intrinsics, pose, mask=torch.zeros(0)):
+        """frustum_pooling.py:189-209."""
+        self.initialize_frustum(x)
+        rots = pose[..., :3, :3]
+        trans = pose[..., :3, 3:]
+        geom = self.get_geometry(rots, trans, intrinsics)
+        x = self.voxel_pooling(geom, x, mask).type_as(x)
+        return x
+
+    def get_depth_map(self, depth):
+        """frustum_pooling.py:211-217."""
+        ds = self.ds.view(1, -1, 1, 1)
+        depth = (ds * depth).sum(1, keepdim=True)
+        depth = nn.functional.interpolate(depth, scale_factor=float(self.downsample), mode='bilinear', align_corners=False)
+        return depth

@@ -1,0 +1,325 @@
+"""Stages (a) voxelisation and (b) range-view projection: host side.
+
+Drop-in replacements (same names / arguments / returns as the reference):
+
+* :func:`voxel_filter`                  <- ``data/data_preprocessing.py:172-228``
+* :class:`PointCloud` ``.do_range_projection`` <- ``muvo/utils/geometry_utils.py:167-220``
+
+plus the batched device API the B200 pipeline actually uses
+(:func:`sensor_to_grid`: ragged frames in, dense grids + range images out, one
+read of the point stream).  All arithmetic happens in ``libmuvo_b200.so``;
+this module only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, _ws
+
+ROADLINE_ID = 6  # data/data_preprocessing.py:198: np.where(LABEL_CLASS == 'roadlines')[0][0]
+
+
+@dataclass(frozen=True)
+class GridSpec:
+    """(voxel_resolution, voxel_size, offset) of ``voxel_filter`` (data_preprocessing.py:172)."""
+    voxel_resolution: float = 0.5
+    voxel_size: Sequence[int] = (192, 192, 64)
+    offset: Sequence[float] = (0.0, 0.0, -10.0)
+    roadline_id: int = ROADLINE_ID
+
+    def to_c(self) -> _lib.MuvoGrid:
+        size = np.asarray(self.voxel_size)
+        res = np.asarray(self.voxel_resolution)
+        # data_preprocessing.py:176-178, evaluated by numpy in float64 exactly as the reference does;
+        # the caller's offset object is never mutated.
+        off = np.array(self.offset, dtype=np.float64, copy=True)
+        off = off + res * size / 2
+        upper = (size * res).astype(np.float64)
+        g = _lib.MuvoGrid()
+        g.res = float(res)
+        for k in range(3):
+            g.offset[k] = float(off[k])
+            g.upper[k] = float(upper[k])
+            g.size[k] = int(size[k])
+        g.roadline_id = int(self.roadline_id)
+        return g
+
+    @property
+    def n_voxels(self) -> int:
+        return int(np.prod(np.asarray(self.voxel_size, dtype=np.int64)))
+
+
+@dataclass(frozen=True)
+class RangeSpec:
+    """Constructor arguments of ``PointCloud`` (geometry_utils.py:167-173)."""
+    H: int = 64
+    W: int = 1024
+    fov_down: float = -30
+    fov_up: float = 10
+    lidar_position: Sequence[float] = (1, 0, 2)
+
+    def to_c(self) -> _lib.MuvoRangeCfg:
+        up = self.fov_up / 180.0 * np.pi         # :168
+        down = self.fov_down / 180.0 * np.pi     # :169
+        c = _lib.MuvoRangeCfg()
+        c.H, c.W = int(self.H), int(self.W)
+        c.fov_down_abs = float(abs(down))        # :190
+        c.fov = float(up - down)                 # :170
+        lp = np.asarray(self.lidar_position, dtype=np.float64)
+        for k in range(3):
+            c.lidar_pos[k] = float(lp[k])
+        return c
+
+
+def _as_offsets(frame_offsets, n_points: int, device) -> torch.Tensor:
+    if frame_offsets is None:
+        return torch.tensor([0, n_points], dtype=torch.int64, device=device)
+    if isinstance(frame_offsets, torch.Tensor):
+        off = frame_offsets.to(device=device, dtype=torch.int64)
+    else:
+        off = torch.as_tensor(np.asarray(frame_offsets, dtype=np.int64), device=device)
+    return off.contiguous()
+
+
+def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=None, *,
+                   grid: Optional[GridSpec] = None, range_spec: Optional[RangeSpec] = None,
+                   dense: bool = True, sparse: bool = False, remap: Optional[torch.Tensor] = None,
+                   layout: str = "xyzd", want_diag: bool = False, out: Optional[dict] = None) -> dict:
+    """Batched (a)+(b) on the current CUDA stream.  Nothing synchronises.
+
+    points ``(P,3)`` float32 (float64 allowed when only ``grid`` is given), semantics ``(P,)`` uint8,
+    ``frame_offsets`` int64 ``[F+1]`` (device tensor, or host sequence).  Returns a dict with
+    ``voxel (F,Dx,Dy,Dz) u8`` | ``voxel_sparse (P,4) u16`` + ``n_occ (F,) i64`` and
+    ``range_xyzd (F,4,H,W) f32`` + ``range_sem (F,H,W) u8`` (layout "xyzd") or
+    ``range_depth (F,H,W)``, ``range_xyz (F,H,W,3)``, ``range_sem`` (layout "hwc").
+    ``out`` may carry preallocated tensors under the same keys.
+    """
+    _lib.require_cuda(points, semantics)
+    if grid is None and range_spec is None:
+        raise ValueError("nothing to do: pass grid and/or range_spec")
+    lib = _lib.load()
+    dev = points.device
+    if points.dim() != 2 or points.shape[1] != 3:
+        raise ValueError("points must be (P, 3)")
+    if points.dtype not in (torch.float32, torch.float64):
+        raise TypeError("points must be float32 or float64")
+    if points.dtype == torch.float64 and range_spec is not None:
+        raise TypeError("range projection takes float32 points (muvo/data/dataset.py:275-300 feeds float32)")
+    points = points.contiguous()
+    semantics = semantics.reshape(-1).contiguous()
+    if semantics.dtype != torch.uint8:
+        raise TypeError("semantics must be uint8")
+    P = points.shape[0]
+    if semantics.shape[0] != P:
+        raise ValueError("points / semantics length mismatch")
+    off = _as_offsets(frame_offsets, P, dev)
+    F = off.numel() - 1
+    res = dict(out) if out else {}
+    with torch.cuda.device(dev):
+        stream = _lib.current_stream(dev)
+        g_c = grid.to_c() if grid is not None else None
+        r_c = range_spec.to_c() if range_spec is not None else None
+        nbytes = C.c_size_t(0)
+        _lib.check(lib.muvo_points_workspace_bytes(P, F, C.byref(g_c) if g_c else None, C.byref(r_c) if r_c else None,
+                                                   C.byref(nbytes)), "muvo_points_workspace_bytes")
+        ws = _ws.get(nbytes.value, dev, stream)
+        diag = torch.zeros(_lib.DIAG_COUNT, dtype=torch.int64, device=dev) if want_diag else None
+        dense_t = sparse_t = nocc_t = depth_t = xyz_t = sem_t = None
+        if grid is not None:
+            dx, dy, dz = (int(v) for v in grid.voxel_size)
+            if dense:
+                dense_t = res.get("voxel")
+                if dense_t is None:
+                    dense_t = torch.empty((F, dx, dy, dz), dtype=torch.uint8, device=dev)
+            if sparse:
+                sparse_t = res.get("voxel_sparse")
+                if sparse_t is None:
+                    sparse_t = torch.empty((max(P, 1), 4), dtype=torch.int16, device=dev)   # viewed as uint16 by the caller
+            nocc_t = res.get("n_occ")
+            if nocc_t is None:
+                nocc_t = torch.empty((F,), dtype=torch.int64, device=dev)
+            if remap is not None:
+                remap = remap.to(device=dev, dtype=torch.uint8).contiguous()
+                if remap.numel() != 256:
+                    raise ValueError("remap must have 256 entries")
+        if range_spec is not None:
+            H, W = int(range_spec.H), int(range_spec.W)
+            sem_t = res.get("range_sem")
+            if sem_t is None:
+                sem_t = torch.empty((F, H, W), dtype=torch.uint8, device=dev)
+            if layout == "xyzd":
+                xyz_t = res.get("range_xyzd")
+                if xyz_t is None:
+                    xyz_t = torch.empty((F, 4, H, W), dtype=torch.float32, device=dev)
+                lay = _lib.RANGE_LAYOUT_XYZD
+            elif layout == "hwc":
+                xyz_t = res.get("range_xyz")
+                if xyz_t is None:
+                    xyz_t = torch.empty((F, H, W, 3), dtype=torch.float32, device=dev)
+                depth_t = res.get("range_depth")
+                if depth_t is None:
+                    depth_t = torch.empty((F, H, W), dtype=torch.float32, device=dev)
+                lay = _lib.RANGE_LAYOUT_HWC
+            else:
+                raise ValueError("layout must be 'xyzd' or 'hwc'")
+        p = _lib.ptr
+        if grid is not None and range_spec is not None:
+            rc = lib.muvo_points_fused(p(points), p(semantics), p(off), F, P, C.byref(g_c), p(remap), C.byref(r_c), lay,
+                                       p(dense_t), p(sparse_t), p(nocc_t), p(depth_t), p(xyz_t), p(sem_t), p(diag),
+                                       ws.data_ptr(), ws.numel(), stream)
+        elif grid is not None:
+            dt = _lib.F32 if points.dtype == torch.float32 else _lib.F64
+            rc = lib.muvo_voxelize(p(points), dt, p(semantics), p(off), F, P, C.byref(g_c), p(remap), p(dense_t),
+                                   p(sparse_t), p(nocc_t), p(diag), ws.data_ptr(), ws.numel(), stream)
+        else:
+            rc = lib.muvo_range_project(p(points), p(semantics), p(off), F, P, C.byref(r_c), lay, p(depth_t), p(xyz_t),
+                                        p(sem_t), p(diag), ws.data_ptr(), ws.numel(), stream)
+        if rc != 0:
+            _ws.invalidate(dev, stream)
+        _lib.check(rc, "muvo points kernels")
+    if dense_t is not None:
+        res["voxel"] = dense_t
+    if sparse_t is not None:
+        res["voxel_sparse"] = sparse_t
+    if nocc_t is not None:
+        res["n_occ"] = nocc_t
+    if range_spec is not None:
+        res["range_sem"] = sem_t
+        if layout == "xyzd":
+            res["range_xyzd"] = xyz_t
+        else:
+            res["range_xyz"], res["range_depth"] = xyz_t, depth_t
+    if diag is not None:
+        res["diag"] = diag
+    res["frame_offsets"] = off
+    return res
+
+
+def _default_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.MuvoError("muvo_b200 kernels need a CUDA device (sm_100a); no CPU fallback exists")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def voxel_filter(pcd, sem, voxel_resolution, voxel_size, offset):
+    """Drop-in for ``voxel_filter`` (data/data_preprocessing.py:172-228): NumPy in, NumPy out.
+
+    Returns ``(voxels uint16 (n,3), semantics uint8 (n,))`` ordered by ``x + y*Dx + z*Dx*Dy``.
+    Unlike the reference, a caller-supplied ``offset`` ndarray is not modified in place.
+    """
+    pcd = np.asarray(pcd)
+    if pcd.ndim != 2 or pcd.shape[1] != 3:
+        raise ValueError("pcd must be (N, 3)")
+    if pcd.dtype != np.float32:
+        pcd = pcd.astype(np.float64, copy=False)     # `pcd + offset` promotes to float64 in the reference (:177)
+    sem = np.asarray(sem).reshape(pcd.shape[0], -1)[:, 0] if pcd.shape[0] else np.zeros((0,), np.uint8)
+    sem = sem.astype(np.uint8, copy=False)
+    dev = _default_device()
+    spec = GridSpec(voxel_resolution, tuple(int(v) for v in np.asarray(voxel_size)), tuple(np.asarray(offset, dtype=np.float64).tolist()))
+    pts_t = torch.from_numpy(np.ascontiguousarray(pcd)).to(dev)
+    sem_t = torch.from_numpy(np.ascontiguousarray(sem)).to(dev)
+    r = sensor_to_grid(pts_t, sem_t, None, grid=spec, dense=False, sparse=True)
+    n = int(r["n_occ"][0].item())
+    rows = r["voxel_sparse"][:n].cpu().numpy().view(np.uint16)
+    return np.ascontiguousarray(rows[:, :3]), rows[:, 3].astype(np.uint8)
+
+
+def voxelize_one_array(pcd, sem, voxel_resolution, voxel_size, offset):
+    """``(n,4) uint16 [x,y,z,label]`` as saved by ``voxelize_one`` (data/generate_voxels.py:64-73)."""
+    vox, lab = voxel_filter(pcd, sem, voxel_resolution, voxel_size, offset)
+    return np.concatenate([vox, lab[:, None]], axis=1)
+
+
+@dataclass(frozen=True)
+class _RadianRangeSpec:
+    """Range description taken verbatim (radians) from a PointCloud-like object, so that a patched reference
+    instance and :class:`PointCloud` feed bit-identical constants to the kernel."""
+    H: int
+    W: int
+    fov_down_rad: float
+    fov_rad: float
+    lidar_position: tuple
+
+    def to_c(self) -> _lib.MuvoRangeCfg:
+        c = _lib.MuvoRangeCfg()
+        c.H, c.W = int(self.H), int(self.W)
+        c.fov_down_abs = float(abs(self.fov_down_rad))
+        c.fov = float(self.fov_rad)
+        for k in range(3):
+            c.lidar_pos[k] = float(self.lidar_position[k])
+        return c
+
+
+def do_range_projection(pc, points, semantics):
+    """``PointCloud.do_range_projection`` for any object exposing H, W, fov_down, fov, lidar_position
+    (the reference class or ours): geometry_utils.py:175-220, NumPy in / NumPy out."""
+    points = np.asarray(points)
+    if points.ndim != 2 or points.shape[1] != 3:
+        raise ValueError("points must be (N, 3)")
+    if points.dtype != np.float32:
+        raise TypeError("do_range_projection expects float32 points (as produced by muvo/data/dataset.py:275-290)")
+    semantics = np.asarray(semantics).reshape(-1).astype(np.uint8, copy=False)
+    spec = _RadianRangeSpec(pc.H, pc.W, float(pc.fov_down), float(pc.fov),
+                            tuple(float(v) for v in np.asarray(pc.lidar_position, dtype=np.float64).reshape(-1)))
+    dev = _default_device()
+    pts_t = torch.from_numpy(np.ascontiguousarray(points)).to(dev)
+    sem_t = torch.from_numpy(np.ascontiguousarray(semantics)).to(dev)
+    r = sensor_to_grid(pts_t, sem_t, None, range_spec=spec, layout="hwc", want_diag=True)
+    diag = r["diag"].cpu().numpy()
+    if diag[_lib.DIAG_DROPPED_NONFINITE] > 0:
+        # the reference hits `IndexError` here: NaN -> int32 min index (geometry_utils.py:187-217)
+        raise IndexError("point(s) at the sensor origin or with non-finite coordinates cannot be projected")
+    try:
+        pc.last_diag = diag
+    except Exception:
+        pass
+    return (r["range_depth"][0].cpu().numpy(), r["range_xyz"][0].cpu().numpy(), r["range_sem"][0].cpu().numpy())
+
+
+class PointCloud(object):
+    """Drop-in for ``muvo.utils.geometry_utils.PointCloud`` (geometry_utils.py:166-244)."""
+
+    def __init__(self, H=64, W=1024, fov_down=-30, fov_up=10, lidar_position=(1, 0, 2)):
+        self.fov_up = fov_up / 180.0 * np.pi  # in rad
+        self.fov_down = fov_down / 180.0 * np.pi
+        self.fov = self.fov_up - self.fov_down
+        self.H = H
+        self.W = W
+        self.lidar_position = np.asarray(lidar_position)
+        self._spec = _RadianRangeSpec(H, W, float(self.fov_down), float(self.fov),
+                                      tuple(float(v) for v in np.asarray(lidar_position, dtype=np.float64).reshape(-1)))
+
+    @property
+    def spec(self):
+        return self._spec
+
+    def do_range_projection(self, points, semantics):
+        """NumPy in / NumPy out: ``(range_depth (H,W) f32, range_xyz (H,W,3) f32, range_sem (H,W) u8)``."""
+        return do_range_projection(self, points, semantics)
+
+    def project_batch(self, points: torch.Tensor, semantics: torch.Tensor, frame_offsets=None, layout: str = "xyzd"):
+        """Device-side batched projection (no host round trip); see :func:`sensor_to_grid`."""
+        return sensor_to_grid(points, semantics, frame_offsets, range_spec=self._spec, layout=layout)
+
+    def restore_pcd_coor(self, range_depth):
+        """Inverse projection (geometry_utils.py:223-244); plain NumPy, not on the hot path."""
+        rows = np.arange(self.H, dtype=float)[:, None] / self.H
+        cols = np.arange(self.W, dtype=float)[None, :] / self.W
+        pitch = (1.0 - rows) * self.fov - abs(self.fov_down)
+        yaw = (1.0 - cols / 0.5) * np.pi
+        pitch = np.broadcast_to(pitch, (self.H, self.W))[None, None]
+        yaw = np.broadcast_to(yaw, (self.H, self.W))[None, None]
+        depth = range_depth
+        z = depth * np.sin(pitch)
+        planar = depth * np.cos(pitch)
+        x = planar * np.cos(yaw)
+        y = planar * np.sin(yaw)
+        pts = np.stack([x, -y, z], axis=-1)
+        pts = pts + self.lidar_position.reshape((1, 1, 1, 1, -1))
+        pts = pts * np.array([1, -1, 1]).reshape((1, 1, 1, 1, -1))
+        return np.concatenate([pts, depth[..., None]], axis=-1)

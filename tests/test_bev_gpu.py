@@ -1,0 +1,170 @@
+"""GPU parity for stage (c): BEV pooling forward / backward and the sorted-rank segment sum.
+
+Tolerances (BASELINE.json north_star: 1e-5 relative for fp32 BEV features and gradients):
+  * forward, element-wise vs the float64 oracle:  |out - exact| <= 1e-5 * sum_i |x_i|  (the pooled magnitude;
+    a plain per-element relative bound is meaningless where a cell's terms cancel)
+  * forward, norm-wise vs the reference's own fp32 output (golden): max|out - ref| <= 1e-5 * max|ref|
+  * backward: the gradient w.r.t. the lifted tensor is a pure gather -> bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import muvo_b200
+import oracle as O
+from muvo_b200 import synth
+from muvo_b200.frustum_pooling import bev_pool
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def module():
+    return muvo_b200.FrustumPooling(**synth.BEV_POOL_ARGS).cuda()
+
+
+def exact_pool(feat, depth, mask, K, E, absval=False):
+    x = synth.lift(feat.double(), depth.double())
+    if absval:
+        x = x.abs()
+    return O.frustum_pooling_forward(x.float() if False else x, K[:, None], E[:, None], mask, exact=True, **synth.BEV_POOL_ARGS)
+
+
+def test_module_forward_golden(golden, lib):
+    g = golden("bev.npz")
+    feat, depth, mask = (torch.from_numpy(g[k]) for k in ("pool_feat", "pool_depth", "pool_mask"))
+    K, E = torch.from_numpy(g["pool_K"]), torch.from_numpy(g["pool_E"])
+    fp = module()
+    for tag, m in (("mask", mask), ("nomask", torch.zeros(0))):
+        x = synth.lift(feat.cuda(), depth.cuda())
+        out = fp(x, K.cuda()[:, None], E.cuda()[:, None], m.cuda())
+        ref = torch.from_numpy(g[f"pool_{tag}_out"])
+        assert out.shape == ref.shape == (1, 6, 48, 48) and out.dtype == torch.float32
+        assert (out.cpu() - ref).abs().max() <= TOL * ref.abs().max()
+        assert torch.equal(out.cpu() == 0, ref == 0)                    # same set of empty cells
+        xl = synth.lift(feat, depth)                                     # fp32 products, as the kernel sees them
+        exact = O.frustum_pooling_forward(xl.double(), K[:, None], E[:, None], m, exact=True, **synth.BEV_POOL_ARGS)
+        mag = O.frustum_pooling_forward(xl.double().abs(), K[:, None], E[:, None], m, exact=True, **synth.BEV_POOL_ARGS)
+        assert torch.all((out.cpu().double() - exact).abs() <= TOL * mag + 1e-30)
+
+
+def test_cell_ids_on_gpu_match_reference(golden, lib):
+    g = golden("bev.npz")
+    fp = module()
+    feat, depth, mask, K, E = synth.bev_inputs(1, 2, 3000, device="cuda")
+    fp.initialize_frustum(synth.lift(feat, depth))
+    geom = fp.get_geometry(E[:, None, :3, :3], E[:, None, :3, 3:], K[:, None])
+    cell = fp.cell_ids(geom, torch.zeros(0, device="cuda"))[0].cpu().numpy()
+    ref = g["cells"].astype(np.int64)
+    inb = (ref[:, 0] >= 0) & (ref[:, 0] < 48) & (ref[:, 1] >= 0) & (ref[:, 1] < 48) & (ref[:, 2] == 0)
+    assert np.array_equal(cell, np.where(inb, ref[:, 1] * 48 + ref[:, 0], -1))
+
+
+def test_module_backward_golden(golden, lib):
+    g = golden("bev.npz")
+    K, E = torch.from_numpy(g["pool_K"]).cuda(), torch.from_numpy(g["pool_E"]).cuda()
+    mask = torch.from_numpy(g["pool_mask"]).cuda()
+    fp = module()
+    fp.train()
+    for tag, m in (("mask", mask), ("nomask", torch.zeros(0, device="cuda"))):
+        feat = torch.from_numpy(g["pool_feat"]).cuda().requires_grad_(True)
+        depth = torch.from_numpy(g["pool_depth"]).cuda().requires_grad_(True)
+        out = fp(synth.lift(feat, depth), K[:, None], E[:, None], m)
+        gout = torch.from_numpy(g[f"pool_{tag}_gout"]).cuda()
+        (out * gout).sum().backward()
+        gf, gd = torch.from_numpy(g[f"pool_{tag}_gfeat"]), torch.from_numpy(g[f"pool_{tag}_gdepth_sub"])
+        assert (feat.grad.cpu() - gf).abs().max() <= TOL * gf.abs().max()
+        assert (depth.grad.cpu()[:, :, ::4, ::4] - gd).abs().max() <= TOL * gd.abs().max()
+
+
+@pytest.mark.parametrize("layout", ["point_major", "channels_last"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_pool_kernel_fwd_bwd_exact_gather(layout, dtype, lib):
+    B, C, D, H, W, n_cells = 2, 10, 5, 6, 33, 37
+    g = torch.Generator().manual_seed(7)
+    base = torch.randn(B, C, D, H, W, generator=g).to(dtype).cuda()
+    x = base.unsqueeze(1).permute(0, 1, 3, 4, 5, 2)
+    if layout == "channels_last":
+        x = x.contiguous()
+    x.requires_grad_(True)
+    cell = torch.randint(-1, n_cells, (B, D * H * W), generator=g, dtype=torch.int32).cuda()
+    out = bev_pool(x, cell, n_cells)
+    assert out.shape == (B, C, n_cells) and out.dtype == torch.float32
+    xf = x.detach().reshape(B, -1, C).double().cpu()
+    want = torch.zeros(B, n_cells, C, dtype=torch.float64)
+    mag = torch.zeros(B, n_cells, C, dtype=torch.float64)
+    cc = cell.cpu().long()
+    for b in range(B):
+        keep = cc[b] >= 0
+        want[b].index_add_(0, cc[b][keep], xf[b][keep])
+        mag[b].index_add_(0, cc[b][keep], xf[b][keep].abs())
+    assert torch.all((out.cpu().double() - want.permute(0, 2, 1)).abs() <= TOL * mag.permute(0, 2, 1) + 1e-30)
+    gout = torch.randn(out.shape, generator=g).cuda()
+    (gx,) = torch.autograd.grad(out, x, gout)
+    assert gx.shape == x.shape and gx.dtype == dtype
+    exp = torch.zeros(B, D * H * W, C)
+    for b in range(B):
+        keep = cc[b] >= 0
+        exp[b][keep] = gout.cpu()[b].t()[cc[b][keep]]
+    assert torch.equal(gx.reshape(B, -1, C).cpu(), exp.to(dtype))       # bit-exact gather
+    out2 = bev_pool(x, cell, n_cells)
+    assert torch.equal(out, out2)                                        # deterministic
+
+
+def test_empty_and_all_dropped(lib):
+    fp = module()
+    feat, depth, mask, K, E = synth.bev_inputs(1, 4, 3100, device="cuda")
+    out = fp(synth.lift(feat, depth), K[:, None], E[:, None], torch.zeros_like(mask))
+    assert out.shape == (1, 4, 48, 48) and torch.count_nonzero(out) == 0
+    out = fp(synth.lift(feat, depth), K[:, None], E[:, None])            # mask = zeros(0): no sparsification
+    assert (out[0, 0] != 0).sum().item() == 1036
+    assert fp.training and out.dtype == torch.float32
+
+
+def test_quick_cumsum_known_answers_and_random(golden, lib):
+    g = golden("bev.npz")
+    for fn in (muvo_b200.QuickCumsum.apply, muvo_b200.VoxelsSumming.apply, muvo_b200.cumsum_trick):
+        x = torch.from_numpy(g["qc_x"]).cuda().requires_grad_(fn is not muvo_b200.cumsum_trick)
+        xs, gs = fn(x, torch.from_numpy(g["qc_geom"]).cuda(), torch.from_numpy(g["qc_ranks"]).cuda())
+        assert np.array_equal(xs.detach().cpu().numpy(), g["qc_xseg"]) and np.array_equal(gs.cpu().numpy(), g["qc_gseg"])
+        if x.requires_grad:
+            (xs * torch.tensor([[1.], [2.], [3.]]).cuda()).sum().backward()
+            assert np.array_equal(x.grad.cpu().numpy(), g["qc_gradx"])
+    x, rk, gm = (torch.from_numpy(g[k]).cuda() for k in ("seg_x", "seg_ranks", "seg_geom"))
+    xs, gs = muvo_b200.quick_cumsum(x, gm, rk)
+    assert np.array_equal(gs.cpu().numpy(), g["seg_gseg"])
+    ref = torch.from_numpy(g["seg_xseg"])
+    assert (xs.cpu() - ref).abs().max() <= 1e-4 * ref.abs().max()        # the reference's cumsum differencing is the noisy side
+    uniq, inv = torch.unique_consecutive(rk.cpu(), return_inverse=True)
+    exact = torch.zeros(len(uniq), x.shape[1], dtype=torch.float64).index_add_(0, inv, x.cpu().double())
+    mag = torch.zeros(len(uniq), x.shape[1], dtype=torch.float64).index_add_(0, inv, x.cpu().double().abs())
+    assert torch.all((xs.cpu().double() - exact).abs() <= TOL * mag)
+    # N = 0 and N = 1
+    xs, gs = muvo_b200.quick_cumsum(torch.zeros(0, 5).cuda(), torch.zeros(0, 4, dtype=torch.long).cuda(), torch.zeros(0, dtype=torch.long).cuda())
+    assert xs.shape == (0, 5) and gs.shape == (0, 4)
+    xs, gs = muvo_b200.quick_cumsum(torch.ones(1, 5).cuda(), torch.ones(1, 4, dtype=torch.long).cuda(), torch.zeros(1, dtype=torch.long).cuda())
+    assert xs.shape == (1, 5) and torch.all(xs == 1)
+
+
+def test_full_size_cfg3(lib):
+    """muvo.yml shapes: B_f = 6, C = 384, D = 37, 40 x 104, top-10 mask; fwd + bwd, checked against float64 on a channel subset."""
+    B, C = 6, 384
+    feat, depth, mask, K, E = synth.bev_inputs(B, C, 3000, device="cuda")
+    feat.requires_grad_(True)
+    fp = module()
+    x = synth.lift(feat, depth)
+    out = fp(x, K[:, None], E[:, None], mask)
+    assert out.shape == (B, C, 48, 48)
+    sub = [0, 1, 191, 383]
+    xl = synth.lift(feat.detach()[:, sub].cpu(), depth.cpu())
+    exact = O.frustum_pooling_forward(xl.double(), K.cpu()[:, None], E.cpu()[:, None], mask.cpu(), exact=True, **synth.BEV_POOL_ARGS)
+    mag = O.frustum_pooling_forward(xl.double().abs(), K.cpu()[:, None], E.cpu()[:, None], mask.cpu(), exact=True, **synth.BEV_POOL_ARGS)
+    assert torch.all((out[:, sub].cpu().double() - exact).abs() <= TOL * mag + 1e-30)
+    out.sum().backward()
+    # d(sum out)/d feat[b,c,h,w] = sum over kept depth bins of depth[b,d,h,w]
+    geom = fp.get_geometry(E[:, None, :3, :3], E[:, None, :3, 3:], K[:, None])
+    kept = (fp.cell_ids(geom, mask) >= 0).view(B, 37, 40, 104)
+    want = (depth * kept).sum(1, keepdim=True).expand(-1, C, -1, -1)
+    assert (feat.grad - want).abs().max() <= TOL * want.abs().max()
+    out2 = fp(synth.lift(feat, depth), K[:, None], E[:, None], mask)
+    assert torch.equal(out, out2)

@@ -1,0 +1,123 @@
+"""The CPU oracle against the committed golden vectors (produced by the unmodified reference,
+tests/golden/make_golden.py) and the known-answer vectors of SURVEY.md Appendix A."""
+import numpy as np
+import torch
+
+import oracle as O
+from muvo_b200 import synth
+
+GRID = (0.5, [192, 192, 64], [0.0, 0, -10.0])
+
+
+def test_voxel_known_answers(golden):
+    g = golden("voxel.npz")
+    for fn in (O.voxel_filter_loop, O.voxel_filter_fast):
+        v, l = fn(g["known_pts"], g["known_sem"], *GRID)
+        assert np.array_equal(v, g["known_vox"]) and np.array_equal(l, g["known_lab"])
+    assert g["known_vox"].tolist() == [[0, 0, 0], [96, 96, 12], [98, 96, 12], [191, 191, 63]]
+    assert g["known_lab"].tolist() == [1, 7, 6, 2]
+
+
+def test_voxel_golden_frames(golden):
+    g = golden("voxel.npz")
+    for fn in (O.voxel_filter_loop, O.voxel_filter_fast):
+        v, l = fn(g["pts32"], g["sem32"], *GRID)
+        assert v.dtype == np.uint16 and l.dtype == np.uint8
+        assert np.array_equal(v, g["vox32"]) and np.array_equal(l, g["lab32"])
+        v, l = fn(g["pts64"], g["sem64"], *GRID)
+        assert np.array_equal(v, g["vox64"]) and np.array_equal(l, g["lab64"])
+        v, l = fn(g["pts32"], g["sem32"], 0.25, [96, 128, 32], [2.0, 0, -1.0])
+        assert np.array_equal(v, g["vox_alt"]) and np.array_equal(l, g["lab_alt"])
+        v, l = fn(g["pts64"], g["sem64"], 0.2, [200, 200, 40], [0.0, 0, -1.0])
+        assert np.array_equal(v, g["vox_np2"]) and np.array_equal(l, g["lab_np2"])
+
+
+def test_voxel_edge_cases():
+    v, l = O.voxel_filter_fast(np.zeros((0, 3), np.float32), np.zeros((0,), np.uint8), *GRID)
+    assert v.shape == (0, 3) and l.shape == (0,)
+    # all points outside the grid
+    v, l = O.voxel_filter_loop(np.full((5, 3), 1000.0, np.float32), np.ones(5, np.uint8), *GRID)
+    assert v.shape == (0, 3)
+    # exact ties: lowest original index wins (stable contract)
+    p = np.array([[0.1, 0.1, 0.1], [0.1, 0.1, 0.1], [0.1, 0.1, 0.1]], np.float32)
+    for fn in (O.voxel_filter_loop, O.voxel_filter_fast):
+        _, l = fn(p, np.array([3, 4, 5], np.uint8), *GRID)
+        assert l.tolist() == [3]
+    # offset list is not mutated
+    off = [0.0, 0, -10.0]
+    O.voxel_filter_fast(p, np.array([3, 4, 5], np.uint8), 0.5, [192, 192, 64], off)
+    assert off == [0.0, 0, -10.0]
+
+
+def test_densify(golden):
+    g = golden("voxel.npz")
+    data = np.concatenate([g["vox32"], g["lab32"][:, None].astype(np.uint16)], 1)
+    grid = O.densify_voxels(data, (192, 192, 64), synth.label_remap256())
+    assert grid.dtype == np.uint8 and grid.shape == (192, 192, 64)
+    assert grid.sum() == (synth.label_remap256()[g["lab32"]] > 0).sum()
+
+
+def test_range_golden(golden):
+    g = golden("range.npz")
+    d, x, s = O.range_projection(g["known_pts"], g["known_sem"], lidar_position=[1.0, 0.0, 2.0])
+    assert np.array_equal(d, g["known_depth"]) and np.array_equal(x, g["known_xyz"]) and np.array_equal(s, g["known_semimg"])
+    hw = {tuple(r) for r in np.argwhere(d >= 0)}
+    # SURVEY.md A.2 item 8 + axis/diagonal bins
+    assert {(16, 512), (16, 256), (16, 768), (0, 512), (63, 512), (16, 0), (16, 1023)} <= hw
+    d, x, s = O.range_projection(g["pts"], g["sem"], lidar_position=[1.0, 0.0, 2.0])
+    assert np.array_equal(d, g["depth"]) and np.array_equal(x, g["xyz"]) and np.array_equal(s, g["semimg"])
+    d, x, s = O.range_projection(g["dense_pts"], g["dense_sem"], lidar_position=[1.0, 0.0, 2.0])
+    assert np.array_equal(d, g["dense_depth"]) and np.array_equal(x, g["dense_xyz"]) and np.array_equal(s, g["dense_semimg"])
+    d, x, s = O.range_projection(g["pts"], g["sem"], 32, 256, -25, 3, [0.5, 0.25, 1.75])
+    assert np.array_equal(d, g["alt_depth"]) and np.array_equal(x, g["alt_xyz"]) and np.array_equal(s, g["alt_semimg"])
+
+
+def test_bev_known_answers(golden):
+    g = golden("bev.npz")
+    xs, gs = O.cumsum_trick(torch.from_numpy(g["qc_x"]), torch.from_numpy(g["qc_geom"]), torch.from_numpy(g["qc_ranks"]))
+    assert np.array_equal(xs.numpy(), g["qc_xseg"]) and np.array_equal(gs.numpy(), g["qc_gseg"])
+    assert g["qc_xseg"].tolist() == [[3, 30], [3, 30], [4, 40]]
+    gx = O.quick_cumsum_backward(torch.tensor([[1., 1.], [2., 2.], [3., 3.]]), torch.from_numpy(g["qc_ranks"]))
+    assert np.array_equal(gx.numpy(), g["qc_gradx"])
+    xs, gs = O.cumsum_trick(torch.from_numpy(g["seg_x"]), torch.from_numpy(g["seg_geom"]), torch.from_numpy(g["seg_ranks"]))
+    assert np.array_equal(xs.numpy(), g["seg_xseg"]) and np.array_equal(gs.numpy(), g["seg_gseg"])
+
+
+def test_bev_module_golden(golden):
+    g = golden("bev.npz")
+    feat, depth, mask = (torch.from_numpy(g[k]) for k in ("pool_feat", "pool_depth", "pool_mask"))
+    K, E = torch.from_numpy(g["pool_K"]), torch.from_numpy(g["pool_E"])
+    # the seeded generator reproduces the stored inputs
+    f2, d2, m2, K2, E2 = synth.bev_inputs(1, 6, 3000)
+    assert torch.equal(f2, feat) and torch.equal(d2, depth) and torch.equal(m2, mask) and torch.equal(K2, K)
+    for tag, m in (("mask", mask), ("nomask", torch.zeros(0))):
+        x = synth.lift(feat, depth)
+        o = O.frustum_pooling_forward(x, K[:, None], E[:, None], m, **synth.BEV_POOL_ARGS)
+        assert np.array_equal(o.numpy(), g[f"pool_{tag}_out"])
+        oe = O.frustum_pooling_forward(x, K[:, None], E[:, None], m, exact=True, **synth.BEV_POOL_ARGS)
+        ref = torch.from_numpy(g[f"pool_{tag}_out"]).double()
+        assert (oe - ref).abs().max() <= 1e-5 * ref.abs().max()
+    assert np.allclose(O.bev_intrinsics(**{k: synth.BEV_POOL_ARGS[k] for k in ("size", "scale", "offsetx")}), g["bev_intrinsics"])
+    dx, bx, nx = O.gen_dx_bx(synth.BEV_POOL_ARGS["size"], synth.BEV_POOL_ARGS["scale"], synth.BEV_POOL_ARGS["offsetx"])
+    assert np.array_equal(dx.numpy(), g["dx"]) and np.array_equal(bx.numpy(), g["bx"]) and np.array_equal(nx.numpy(), g["nx"])
+    # geometry -> cell ids
+    fr = O.frustum_grid(synth.BEV_POOL_ARGS["dbound"], 40, 104, 8)
+    geom = O.frustum_geometry(fr, K[:1, None], E[:1, None])
+    cells = O.bev_cell_ids(geom, torch.from_numpy(g["bev_intrinsics"]), bx, dx)
+    assert np.array_equal(cells.numpy().astype(np.int16), g["cells"])
+
+
+def test_ssc_golden(golden):
+    g = golden("ssc.npz")
+    for C in (2, 9):
+        yp, yt = g[f"c{C}_pred"].astype(np.int64), g[f"c{C}_true"]
+        assert np.array_equal(O.ssc_counts(yp, yt, C), g[f"c{C}_raw"])
+        assert np.array_equal(O.ssc_counts_loop(yp, yt, C), g[f"c{C}_raw"])
+        ne, ns = g[f"c{C}_nonempty"], g[f"c{C}_nonsurface"]
+        assert np.array_equal(O.ssc_counts(yp, yt, C, nonempty=ne), g[f"c{C}_masked"])
+        assert np.array_equal(O.ssc_counts_loop(yp, yt, C, nonempty=ne), g[f"c{C}_masked"])
+        acc = O.ssc_add_batch_counts(yp, yt, C) + O.ssc_add_batch_counts(yp, yt, C, ne, ns)
+        assert np.array_equal(acc.astype(np.float64), g[f"c{C}_acc2"])
+        st = O.ssc_stats_from_counts(acc, C)
+        assert st["iou"] == float(g[f"c{C}_iou"]) and st["precision"] == float(g[f"c{C}_precision"])
+        assert np.allclose(st["iou_ssc"].numpy(), g[f"c{C}_iou_ssc"], rtol=1e-6)

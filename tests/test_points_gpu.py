@@ -1,0 +1,258 @@
+"""GPU parity for stages (a) voxelisation and (b) range-view projection, through the reference-facing
+wrappers (which call the C ABI).  Bit-exact against the golden vectors and the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+import muvo_b200
+import oracle as O
+from muvo_b200 import synth
+from muvo_b200.points import GridSpec, RangeSpec, PointCloud, sensor_to_grid
+
+pytestmark = pytest.mark.gpu
+GRID = (0.5, [192, 192, 64], [0.0, 0, -10.0])
+LIDAR = [1.0, 0.0, 2.0]
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+# ------------------------------------------------------------------ (a)
+def test_voxel_known_answers(golden, lib):
+    g = golden("voxel.npz")
+    v, l = muvo_b200.voxel_filter(g["known_pts"], g["known_sem"], *GRID)
+    assert v.dtype == np.uint16 and l.dtype == np.uint8
+    assert v.tolist() == [[0, 0, 0], [96, 96, 12], [98, 96, 12], [191, 191, 63]] and l.tolist() == [1, 7, 6, 2]
+
+
+def test_voxel_golden(golden, lib):
+    g = golden("voxel.npz")
+    v, l = muvo_b200.voxel_filter(g["pts32"], g["sem32"], *GRID)
+    assert np.array_equal(v, g["vox32"]) and np.array_equal(l, g["lab32"])
+    v, l = muvo_b200.voxel_filter(g["pts64"], g["sem64"], *GRID)          # float64 cloud, (N,1) semantics
+    assert np.array_equal(v, g["vox64"]) and np.array_equal(l, g["lab64"])
+    v, l = muvo_b200.voxel_filter(g["pts32"], g["sem32"], 0.25, [96, 128, 32], [2.0, 0, -1.0])
+    assert np.array_equal(v, g["vox_alt"]) and np.array_equal(l, g["lab_alt"])
+    v, l = muvo_b200.voxel_filter(g["pts64"], g["sem64"], 0.2, [200, 200, 40], [0.0, 0, -1.0])   # general np.divmod path
+    assert np.array_equal(v, g["vox_np2"]) and np.array_equal(l, g["lab_np2"])
+
+
+@pytest.mark.parametrize("n,seed", [(100000, 1000), (1, 1001), (33, 1002), (4097, 1003)])
+def test_voxel_vs_oracle(n, seed, lib):
+    p, s = synth.carla_lidar_frame(n, seed)
+    v0, l0 = O.voxel_filter_fast(p, s, *GRID)
+    v, l = muvo_b200.voxel_filter(p, s, *GRID)
+    assert np.array_equal(v, v0) and np.array_equal(l, l0)
+    arr = muvo_b200.voxelize_one_array(p, s, *GRID)
+    assert arr.dtype == np.uint16 and arr.shape == (len(v0), 4)
+
+
+def test_voxel_edge_cases(lib):
+    v, l = muvo_b200.voxel_filter(np.zeros((0, 3), np.float32), np.zeros((0,), np.uint8), *GRID)
+    assert v.shape == (0, 3) and l.shape == (0,)
+    v, l = muvo_b200.voxel_filter(np.full((7, 3), 1000.0, np.float32), np.ones(7, np.uint8), *GRID)
+    assert v.shape == (0, 3)
+    # exact ties -> lowest original index; a roadline point anywhere in the voxel overrides
+    p = np.array([[0.1, 0.1, 0.1]] * 5, np.float32)
+    _, l = muvo_b200.voxel_filter(p, np.array([3, 4, 5, 9, 9], np.uint8), *GRID)
+    assert l.tolist() == [3]
+    _, l = muvo_b200.voxel_filter(p, np.array([3, 4, 5, 6, 9], np.uint8), *GRID)
+    assert l.tolist() == [6]
+    # many points in one voxel (contended resolve) + unaligned tail
+    rng = np.random.default_rng(0)
+    p = (rng.random((5003, 3)) * 0.5).astype(np.float32)
+    s = rng.integers(0, 23, 5003).astype(np.uint8)
+    s[s == 6] = 7
+    v0, l0 = O.voxel_filter_fast(p, s, *GRID)
+    v, l = muvo_b200.voxel_filter(p, s, *GRID)
+    assert len(v0) == 1 and np.array_equal(v, v0) and np.array_equal(l, l0)
+    # boundaries: lower inclusive, upper exclusive
+    p = np.array([[-48, -48, -6], [48, 0, 0], [47.999996, 47.999996, 25.999998], [0, 0, 26]], np.float32)
+    v0, l0 = O.voxel_filter_fast(p, np.array([1, 2, 3, 4], np.uint8), *GRID)
+    v, l = muvo_b200.voxel_filter(p, np.array([1, 2, 3, 4], np.uint8), *GRID)
+    assert np.array_equal(v, v0) and np.array_equal(l, l0) and len(v) == 2
+
+
+def _batch(F, nmin, nmax, seed):
+    pts, sem, off = synth.lidar_batch(F, nmin, nmax, seed)
+    return pts, sem, off
+
+
+def test_batched_dense_sparse_and_range_vs_oracle(lib):
+    pts, sem, off = _batch(5, 3000, 9000, 2100)
+    # insert an empty frame in the middle
+    off = np.r_[off[:3], off[2], off[3:]]
+    F = len(off) - 1
+    remap = synth.label_remap256()
+    r = sensor_to_grid(torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev()), off, grid=GridSpec(),
+                       range_spec=RangeSpec(lidar_position=tuple(LIDAR)), dense=True, sparse=True,
+                       remap=torch.from_numpy(remap), layout="hwc", want_diag=True)
+    torch.cuda.synchronize()
+    dense, sparse, nocc = r["voxel"].cpu().numpy(), r["voxel_sparse"].cpu().numpy().view(np.uint16), r["n_occ"].cpu().numpy()
+    n_in = 0
+    for f in range(F):
+        p, s = pts[off[f]:off[f + 1]], sem[off[f]:off[f + 1]]
+        v0, l0 = O.voxel_filter_fast(p, s, *GRID)
+        assert nocc[f] == len(v0)
+        rows = sparse[off[f]:off[f] + nocc[f]]
+        assert np.array_equal(rows[:, :3], v0) and np.array_equal(rows[:, 3].astype(np.uint8), l0)
+        want = O.densify_voxels(np.concatenate([v0, l0[:, None].astype(np.uint16)], 1), (192, 192, 64), remap)
+        assert np.array_equal(dense[f], want)
+        d0, x0, s0 = O.range_projection(p, s, lidar_position=LIDAR)
+        assert np.array_equal(r["range_depth"][f].cpu().numpy(), d0)
+        assert np.array_equal(r["range_xyz"][f].cpu().numpy(), x0)
+        assert np.array_equal(r["range_sem"][f].cpu().numpy(), s0)
+        sh = p.astype(np.float64) + np.array([48.0, 48.0, 6.0])
+        n_in += int(((sh >= 0) & (sh < np.array([96.0, 96.0, 32.0]))).all(1).sum())
+    diag = r["diag"].cpu().numpy()
+    assert diag[3] == n_in and diag[0] == 0
+
+
+def test_dense_only_fast_path_and_workspace_self_cleaning(lib):
+    """Dense-order bitmap path; repeated calls on the same (self-cleaning) workspace with different batches."""
+    remap = torch.from_numpy(synth.label_remap256())
+    outs = []
+    for seed, F in ((2200, 4), (2300, 2), (2200, 4)):
+        pts, sem, off = _batch(F, 2000, 6000, seed)
+        r = sensor_to_grid(torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev()), off, grid=GridSpec(),
+                           range_spec=RangeSpec(lidar_position=tuple(LIDAR)), remap=remap, layout="xyzd")
+        torch.cuda.synchronize()
+        for f in range(F):
+            p, s = pts[off[f]:off[f + 1]], sem[off[f]:off[f + 1]]
+            v0, l0 = O.voxel_filter_fast(p, s, *GRID)
+            want = O.densify_voxels(np.concatenate([v0, l0[:, None].astype(np.uint16)], 1), (192, 192, 64), remap.numpy())
+            assert np.array_equal(r["voxel"][f].cpu().numpy(), want)
+            d0, x0, s0 = O.range_projection(p, s, lidar_position=LIDAR)
+            assert np.array_equal(r["range_xyzd"][f].cpu().numpy(), O.pack_range_view(d0, x0))
+            assert np.array_equal(r["range_sem"][f].cpu().numpy(), s0)
+        outs.append((r["voxel"].clone(), r["range_xyzd"].clone()))
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])     # deterministic
+
+
+def test_raw_labels_without_remap_and_small_odd_grid(lib):
+    """No remap (raw CARLA tags in the dense grid) and a grid whose size is not a multiple of 16/1024."""
+    pts, sem, off = _batch(2, 4000, 5000, 2400)
+    spec = GridSpec(0.5, (50, 30, 7), (1.0, 0, -1.0))
+    r = sensor_to_grid(torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev()), off, grid=spec)
+    torch.cuda.synchronize()
+    for f in range(2):
+        p, s = pts[off[f]:off[f + 1]], sem[off[f]:off[f + 1]]
+        v0, l0 = O.voxel_filter_fast(p, s, 0.5, [50, 30, 7], [1.0, 0, -1.0])
+        want = np.zeros((50, 30, 7), np.uint8)
+        want[v0[:, 0], v0[:, 1], v0[:, 2]] = l0
+        assert np.array_equal(r["voxel"][f].cpu().numpy(), want)
+        assert int(r["n_occ"][f]) == len(v0)
+
+
+# ------------------------------------------------------------------ (b)
+def test_range_known_and_golden(golden, lib):
+    g = golden("range.npz")
+    pc = PointCloud(64, 1024, -30, 10, LIDAR)
+    d, x, s = pc.do_range_projection(g["known_pts"], g["known_sem"])
+    assert d.dtype == np.float32 and x.shape == (64, 1024, 3) and s.dtype == np.uint8
+    assert np.array_equal(d, g["known_depth"]) and np.array_equal(x, g["known_xyz"]) and np.array_equal(s, g["known_semimg"])
+    d, x, s = pc.do_range_projection(g["pts"], g["sem"])
+    assert np.array_equal(d, g["depth"]) and np.array_equal(x, g["xyz"]) and np.array_equal(s, g["semimg"])
+    d, x, s = pc.do_range_projection(g["dense_pts"], g["dense_sem"])
+    assert np.array_equal(d, g["dense_depth"]) and np.array_equal(x, g["dense_xyz"]) and np.array_equal(s, g["dense_semimg"])
+    pc2 = PointCloud(32, 256, -25, 3, [0.5, 0.25, 1.75])
+    d, x, s = pc2.do_range_projection(g["pts"], g["sem"])
+    assert np.array_equal(d, g["alt_depth"]) and np.array_equal(x, g["alt_xyz"]) and np.array_equal(s, g["alt_semimg"])
+
+
+def test_range_axes_diagonals_and_signed_zero(lib):
+    """Exact bin edges (axes / diagonals) and the sign of zero behind the sensor."""
+    L = np.float32(LIDAR)
+    dirs = []
+    for a in (1.0, 2.5, 7.0):
+        for sx, sy in ((1, 0), (-1, 0), (0, 1), (0, -1), (1, 1), (1, -1), (-1, 1), (-1, -1)):
+            for z in (0.0, 0.5, -1.0):
+                dirs.append((a * sx, a * sy, z))
+    pts = (np.array(dirs, np.float32) + L).astype(np.float32)
+    pts = np.concatenate([pts, np.float32([[-9, 0.0, 2], [-9, -0.0, 2]])])
+    sem = (np.arange(len(pts)) % 23).astype(np.uint8)
+    pc = PointCloud(64, 1024, -30, 10, LIDAR)
+    d, x, s = pc.do_range_projection(pts, sem)
+    d0, x0, s0 = O.range_projection(pts, sem, lidar_position=LIDAR)
+    assert np.array_equal(d, d0) and np.array_equal(x, x0) and np.array_equal(s, s0)
+    ph, pw, _ = O.range_projection_indices(np.float32([[-9, 0.0, 2], [-9, -0.0, 2]]), lidar_position=LIDAR)
+    assert pw.tolist() == [0, 1023]
+    assert pc.last_diag[1] > 0          # points exactly on a column edge are reported
+
+
+def test_range_random_directions_vs_oracle(lib):
+    rng = np.random.default_rng(11)
+    pts = (rng.normal(0, 1, (200000, 3)) * np.array([30, 30, 4]) + np.array(LIDAR)).astype(np.float32)
+    sem = rng.integers(0, 23, len(pts)).astype(np.uint8)
+    pc = PointCloud(64, 1024, -30, 10, LIDAR)
+    d, x, s = pc.do_range_projection(pts, sem)
+    d0, x0, s0 = O.range_projection(pts, sem, lidar_position=LIDAR)
+    assert np.array_equal(d, d0) and np.array_equal(x, x0) and np.array_equal(s, s0)
+    assert pc.last_diag[0] == 0
+
+
+def test_range_ties_and_origin(lib):
+    pc = PointCloud(64, 1024, -30, 10, LIDAR)
+    # exact duplicates: lowest index wins
+    pts = np.float32([[11, 0, 2]] * 4 + [[6, 0, 2]] * 3)
+    d, x, s = pc.do_range_projection(pts, np.uint8([1, 2, 3, 4, 5, 6, 7]))
+    assert s[16, 512] == 5 and d[16, 512] == 5.0
+    # equal depth from mirrored points lands in different pixels
+    d0, x0, s0 = O.range_projection(pts, np.uint8([1, 2, 3, 4, 5, 6, 7]), lidar_position=LIDAR)
+    assert np.array_equal(s, s0) and np.array_equal(d, d0)
+    with pytest.raises(IndexError):
+        pc.do_range_projection(np.float32([[1, 0, 2], [5, 5, 5]]), np.uint8([1, 2]))     # a point AT the sensor
+    # empty input -> all-empty images
+    d, x, s = pc.do_range_projection(np.zeros((0, 3), np.float32), np.zeros((0,), np.uint8))
+    assert np.all(d == -1) and np.all(x == 0) and np.all(s == 0)
+
+
+def test_error_paths(lib):
+    with pytest.raises(TypeError):
+        PointCloud().do_range_projection(np.ones((3, 3), np.float64), np.zeros(3, np.uint8))
+    with pytest.raises(ValueError):
+        muvo_b200.voxel_filter(np.ones((3, 2), np.float32), np.zeros(3, np.uint8), *GRID)
+    with pytest.raises(muvo_b200.MuvoError):     # > 65535 voxels per axis cannot be uint16 coordinates
+        muvo_b200.voxel_filter(np.ones((3, 3), np.float32), np.zeros(3, np.uint8), 0.5, [70000, 2, 2], [0.0, 0, 0])
+
+
+# ------------------------------------------------------------------ full BASELINE size: properties
+def test_full_size_batch_properties(lib):
+    """cfg2 shape (8 x 12 frames, 60-100 k points each): size-independent invariants + oracle on a few frames."""
+    F = 96
+    pts, sem, off = synth.lidar_batch(F, 60000, 100000, 2000)
+    tp, ts = torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev())
+    r = sensor_to_grid(tp, ts, off, grid=GridSpec(), range_spec=RangeSpec(lidar_position=tuple(LIDAR)), layout="xyzd",
+                       want_diag=True)
+    r2 = sensor_to_grid(tp, ts, off, grid=GridSpec(), range_spec=RangeSpec(lidar_position=tuple(LIDAR)), layout="xyzd")
+    torch.cuda.synchronize()
+    vox, xyzd, rsem = r["voxel"], r["range_xyzd"], r["range_sem"]
+    assert torch.equal(vox, r2["voxel"]) and torch.equal(xyzd, r2["range_xyzd"]) and torch.equal(rsem, r2["range_sem"])
+    # (1) raw labels are never 0 in this generator -> occupied voxel count == n_occ
+    assert torch.equal((vox != 0).flatten(1).sum(1), r["n_occ"])
+    # (2) independent float64 voxel ids in torch: same set of occupied voxels per frame
+    sh = tp.double() + torch.tensor([48.0, 48.0, 6.0], device=dev(), dtype=torch.float64)
+    inside = ((sh >= 0) & (sh < torch.tensor([96.0, 96.0, 32.0], device=dev(), dtype=torch.float64))).all(1)
+    ijk = torch.floor(sh * 2.0).long()
+    frame = torch.bucketize(torch.arange(len(pts), device=dev()), torch.from_numpy(off[1:]).to(dev()), right=True)
+    lin = ((frame * 192 + ijk[:, 0]) * 192 + ijk[:, 1]) * 64 + ijk[:, 2]
+    occ = torch.zeros(F * 192 * 192 * 64, dtype=torch.bool, device=dev())
+    occ[lin[inside]] = True
+    assert torch.equal(occ.view(F, 192, 192, 64), vox != 0)
+    assert int(r["diag"][3]) == int(inside.sum())
+    # (3) range image: stored depth == |xyz - lidar| of the stored point; empty pixels are (-1, 0, 0, 0)
+    x, y, z, d = xyzd[:, 0], xyzd[:, 1], xyzd[:, 2], xyzd[:, 3]
+    filled = d >= 0
+    dd = torch.sqrt(((x.double() - 1.0) ** 2 + (-y.double() - 0.0) ** 2) + (z.double() - 2.0) ** 2).float()
+    assert torch.equal(dd[filled], d[filled])
+    assert torch.all(x[~filled] == 0) and torch.all(rsem[~filled] == 0) and torch.all(d[~filled] == -1)
+    # (4) oracle on three frames
+    for f in (0, 47, 95):
+        p, s = pts[off[f]:off[f + 1]], sem[off[f]:off[f + 1]]
+        v0, l0 = O.voxel_filter_fast(p, s, *GRID)
+        want = O.densify_voxels(np.concatenate([v0, l0[:, None].astype(np.uint16)], 1), (192, 192, 64))
+        assert np.array_equal(vox[f].cpu().numpy(), want)
+        d0, x0, s0 = O.range_projection(p, s, lidar_position=LIDAR)
+        assert np.array_equal(xyzd[f].cpu().numpy(), O.pack_range_view(d0, x0))
+        assert np.array_equal(rsem[f].cpu().numpy(), s0)
