@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Headline benchmark: LiDAR points/s voxelised + range-projected (BASELINE.json configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # ours   (torchrun launches N ranks)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU reference arm (oracle port, rank 0 only)
+
+A "step" = stages (a)+(b) over one batch of 8 x 12 = 96 ragged synthetic CARLA-style frames
+(60-100 k points each): dense 192x192x64 uint8 occupancy grids + (4,64,1024) range views.
+One JSON line on rank 0.  Extra stage numbers (BEV pool fwd/bwd GB/s, IoU counts) ride along
+under "stages".  See DESIGN.md for the byte accounting.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lidar_points_per_sec_voxelised_projected"
+UNIT = "points/s"
+F_BATCH, F_SEQ = 8, 12
+N_MIN, N_MAX = 60000, 100000
+G = 192 * 192 * 64
+HW = 64 * 1024
+LIDAR = (1.0, 0.0, 2.0)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(rank: int, n_frames: int = F_BATCH * F_SEQ, n_min: int = N_MIN, n_max: int = N_MAX):
+    from muvo_b200 import synth
+    return synth.lidar_batch(n_frames, n_min, n_max, 2000 + 100000 * rank)
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def _cpu_frame(args):
+    import warnings
+    warnings.filterwarnings("ignore")
+    import oracle as O
+    p, s = args
+    v, l = O.voxel_filter_loop(p, s, 0.5, [192, 192, 64], [0.0, 0, -10.0])           # (a) data_preprocessing.py:172-228
+    data = np.concatenate([v, l[:, None].astype(np.uint16)], 1)
+    from muvo_b200 import synth
+    grid = O.densify_voxels(data, (192, 192, 64), synth.label_remap256())             # dataset.py:317-327
+    d, x, sm = O.range_projection(p, s, lidar_position=list(LIDAR))                    # (b) geometry_utils.py:175-220
+    O.pack_range_view(d, x)
+    return int(grid.sum()) + int(sm.sum())
+
+
+def cpu_reference(frames, pool, cores):
+    """One bounded sample: `frames` = list of (points, sem); returns (points, seconds)."""
+    t0 = time.perf_counter()
+    list(pool.map(_cpu_frame, frames, chunksize=1))
+    dt = time.perf_counter() - t0
+    return sum(len(p) for p, _ in frames), dt
+
+
+def cpu_sample_frames(n_frames):
+    pts, sem, off = make_batch(0, n_frames)
+    return [(pts[off[f]:off[f + 1]].copy(), sem[off[f]:off[f + 1]].copy()) for f in range(n_frames)]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_frames = max(cores, 8)                      # one frame per worker per step: ~0.3-0.6 s of CPU work per frame
+    frames = cpu_sample_frames(n_frames)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1) if args.warmup else 0):
+            cpu_reference(frames[:cores], pool, cores)
+        tot_pts, tot_s = 0, 0.0
+        for _ in range(args.steps):
+            n, dt = cpu_reference(frames, pool, cores)
+            tot_pts += n
+            tot_s += dt
+    value = tot_pts / tot_s
+    sample = (f"{n_frames} frames/step of the cfg2 generator ({tot_pts // max(args.steps, 1)} points/step), "
+              f"multiprocessing.Pool({cores}) over frames like data/generate_voxels.py:134; oracle *_loop port "
+              f"(voxel_filter + densify + do_range_projection), numpy {np.__version__}")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg2: range-view projection + occupancy voxelisation (CPU oracle port, bounded sample)",
+                       "frames_per_step": n_frames, "points_per_frame": f"{N_MIN}-{N_MAX}"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import muvo_b200
+    from muvo_b200 import _lib, synth
+    from muvo_b200.distributed import init_distributed
+    from muvo_b200.points import GridSpec, RangeSpec, sensor_to_grid
+    from muvo_b200.pipeline import HostPipeline
+
+    rank, world, device = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (no CPU fallback for the muvo_b200 kernels)")
+    hbm_peak, peak_src = peaks()
+    n_frames = F_BATCH * F_SEQ
+    pts, sem, off = make_batch(rank)
+    P = int(pts.shape[0])
+    d_pts, d_sem = torch.from_numpy(pts).to(device), torch.from_numpy(sem).to(device)
+    d_off = torch.from_numpy(off).to(device)
+    grid, rspec = GridSpec(), RangeSpec(lidar_position=LIDAR)
+    remap = torch.from_numpy(synth.label_remap256()).to(device)
+    out = {"voxel": torch.empty((n_frames, 192, 192, 64), dtype=torch.uint8, device=device),
+           "n_occ": torch.empty((n_frames,), dtype=torch.int64, device=device),
+           "range_xyzd": torch.empty((n_frames, 4, 64, 1024), dtype=torch.float32, device=device),
+           "range_sem": torch.empty((n_frames, 64, 1024), dtype=torch.uint8, device=device)}
+
+    def step():
+        return sensor_to_grid(d_pts, d_sem, d_off, grid=grid, range_spec=rspec, dense=True, sparse=False, remap=remap,
+                              layout="xyzd", out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+
+    # per-kernel durations, CUDA events on the launching stream, same step repeated
+    stream = _lib.current_stream(device)
+    per_kernel = {}
+    n_launch_per_step = 0
+    for _ in range(args.steps):
+        with _lib.profile(stream) as prof:
+            step()
+        n_launch_per_step = len(prof.kernels)
+        for name, ms in prof.kernels:
+            per_kernel.setdefault(name, []).append(ms)
+    clocks = sampler.stop()
+    kern = {k: float(np.mean(v)) for k, v in per_kernel.items()}
+    n_total_pts = torch.tensor([P], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(n_total_pts)
+    total_pts = float(n_total_pts.item())
+    value = total_pts / (ms_step * 1e-3)
+
+    # algorithmic bytes: 13 B/point + G + 64*1024*17 per frame
+    alg_step = 13 * P + n_frames * (G + HW * 17)
+    alg_kernel = {"k_point_pass": 13 * P, "k_voxel_resolve": 13 * P, "k_emit_dense": n_frames * G,
+                  "k_emit_range": n_frames * HW * 17, "k_bitmap_scan": n_frames * (G // 8)}
+    top = max(kern, key=kern.get)
+    achieved = alg_kernel.get(top, 0) / (kern[top] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_kernel.get(top, 0), "ms_per_launch": kern[top],
+                "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (ms_step * 1e-3) / 1e9,
+                         "frac": alg_step / (ms_step * 1e-3) / 1e9 / hbm_peak},
+                "kernels_ms": kern}
+
+    # end to end through the host-buffer API: pinned staging, H2D, kernels, D2H of the reference-facing results
+    pipe = HostPipeline(device, grid=grid, range_spec=rspec, dense=False, sparse=True, layout="hwc")
+    for _ in range(3):
+        pipe.submit(pts, sem, off)
+        pipe.result()
+    barrier()
+    e2e_steps = max(args.steps, 4)
+    t0 = time.perf_counter()
+    pipe.submit(pts, sem, off)
+    for _ in range(e2e_steps - 1):
+        pipe.submit(pts, sem, off)
+        res = pipe.result()
+    res = pipe.result()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": total_pts * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes),
+           "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
+           "api": "muvo_b200.pipeline.HostPipeline.submit/result (numpy in, pinned host out: sparse voxel lists + "
+                  "HWC range images = the returns of voxel_filter / do_range_projection)"}
+
+    stages = {}
+    if not args.no_stages:
+        stages = other_stages(device, rank, world, hbm_peak, args)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_base = cpu_baseline_leg()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "cfg2: range-view projection + occupancy voxelisation, batch 8 x seq 12 frames per GPU",
+                           "frames_per_gpu": n_frames, "points_per_gpu": P, "points_per_frame": f"{N_MIN}-{N_MAX} (ragged)",
+                           "grid": "192x192x64 @0.5m uint8 dense", "range_image": "4x64x1024 f32 + 64x1024 u8",
+                           "l2": "inputs+outputs %.0f MB per step > 126 MB L2 (no explicit flush)" % (alg_step / 1e6),
+                           "sharding": "frames sharded by rank, no data-path collective"},
+                "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
+                "gpu_launches": n_launch_per_step * args.steps, "kernels_per_step": n_launch_per_step, "stages": stages}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_leg():
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_frames = max(cores, 8)
+    frames = cpu_sample_frames(n_frames)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        cpu_reference(frames[:cores], pool, cores)
+        n, dt = cpu_reference(frames, pool, cores)
+    t0 = time.perf_counter()
+    _cpu_frame(frames[0])
+    one = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_frames} cfg2 frames ({n} points) through the oracle *_loop port with multiprocessing.Pool({cores}); "
+                      f"single core: {len(frames[0][0]) / one:.3g} points/s",
+            "single_core_value": len(frames[0][0]) / one}
+
+
+def other_stages(device, rank, world, hbm_peak, args):
+    """BEV pool fwd/bwd at cfg3 shapes and the IoU count reduction at cfg4 per-rank shapes (+ NCCL all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    import muvo_b200
+    from muvo_b200 import synth
+    from muvo_b200.metrics import ssc_counts, all_reduce_counts
+    res = {}
+    steps = max(3, min(args.steps, 10))
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # (c) cfg3: B_f = 6, C = 384
+    B, C, D, H, W = 6, 384, 37, 40, 104
+    feat, depth, mask, K, E = synth.bev_inputs(B, C, 3000 + rank, device=device)
+    fp = muvo_b200.FrustumPooling(**synth.BEV_POOL_ARGS).to(device)
+    x = synth.lift(feat, depth)                                  # materialised once; the pool reads it in place
+    fp.initialize_frustum(x)
+    geom = fp.get_geometry(E[:, None, :3, :3], E[:, None, :3, 3:], K[:, None])
+    cell = fp.cell_ids(geom, mask)
+    n_kept = int((cell >= 0).sum())
+    n_pts = D * H * W
+    from muvo_b200.frustum_pooling import bev_pool
+    xg = x.detach().requires_grad_(True)
+    ms_f = timed(lambda: bev_pool(x, cell, 2304), steps)
+    out = bev_pool(xg, cell, 2304)
+    gout = torch.randn_like(out)
+    ms_b = timed(lambda: torch.autograd.grad(out, xg, gout, retain_graph=True), steps)
+    bytes_f = n_kept * C * 4 + B * n_pts * 5 + B * C * 2304 * 4
+    bytes_f_sector = B * n_pts * C * 4 + B * n_pts * 4 + B * C * 2304 * 4
+    bytes_b = B * C * 2304 * 4 + B * n_pts * C * 4
+    res["bev_pool_fwd"] = {"ms": ms_f, "algorithmic_GBps": bytes_f / ms_f / 1e6, "frac": bytes_f / ms_f / 1e6 / hbm_peak,
+                           "dense_read_GBps": bytes_f_sector / ms_f / 1e6, "frames": B, "C": C, "n_kept": n_kept,
+                           "note": "kernel only (cell ids precomputed); dense_read = whole lifted tensor, the sector-granular bound for a random top-k mask"}
+    res["bev_pool_bwd"] = {"ms": ms_b, "algorithmic_GBps": bytes_b / ms_b / 1e6, "frac": bytes_b / ms_b / 1e6 / hbm_peak}
+    del x, xg, out, gout, feat, depth
+    torch.cuda.empty_cache()
+    # (d) cfg4: 16 frames per rank, C = 2, counts all-reduced
+    yp, yt = synth.occupancy_pair(16, 2, 4000 + rank)
+    tp, tt = torch.from_numpy(yp).to(device), torch.from_numpy(yt).to(device)
+    acc = torch.zeros(9, dtype=torch.int64, device=device)
+
+    def ssc():
+        acc.zero_()
+        ssc_counts(tp, tt, 2, ignore255=True, out=acc)
+        all_reduce_counts(acc)
+    ms_d = timed(ssc, steps)
+    bytes_d = tp.numel() * 9
+    res["ssc_counts"] = {"ms": ms_d, "algorithmic_GBps": bytes_d / ms_d / 1e6, "frac": bytes_d / ms_d / 1e6 / hbm_peak,
+                         "voxels_per_s": tp.numel() * world / (ms_d * 1e-3), "frames_per_rank": 16,
+                         "allreduce": "nccl int64[9]" if world > 1 else "none (1 rank)"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-stages", action="store_true", help="skip the BEV-pool / IoU stage numbers")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

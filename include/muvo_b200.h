@@ -85,6 +85,15 @@ enum { MUVO_DIAG_DROPPED_NONFINITE = 0, /* points with NaN/Inf coordinates or at
 MUVO_API int muvo_abi_version(void);
 MUVO_API const char* muvo_strerror(int code);
 
+/* ---- per-kernel timing (bench / profiling only) ------------------------------------
+ * Between begin and end, every kernel launched by this host thread through the library is followed
+ * by a CUDA event on its stream.  end() synchronises the stream and returns, per launch in order,
+ * the elapsed milliseconds since the previous mark and the kernel's name (static strings).
+ * Thread-local; at most 63 launches are recorded.                                       */
+MUVO_API int muvo_profile_begin(void* stream);
+MUVO_API int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char** names_out_h,
+                              int32_t* n_out_h);
+
 /* ---- workspace ------------------------------------------------------------------ */
 /* Bytes needed by the point kernels for `n_frames` frames / `n_points_total` points.
  * grid_h or range_h may be NULL when that stage is not used.                        */

@@ -41,6 +41,8 @@ _I32, _I64, _SZ = C.c_int32, C.c_int64, C.c_size_t
 SIGNATURES = {
     "muvo_abi_version": (C.c_int, []),
     "muvo_strerror": (C.c_char_p, [C.c_int]),
+    "muvo_profile_begin": (C.c_int, [_P]),
+    "muvo_profile_end": (C.c_int, [_P, _I32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(_I32)]),
     "muvo_points_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(MuvoGrid), C.POINTER(MuvoRangeCfg), C.POINTER(_SZ)]),
     "muvo_ws_reset": (C.c_int, [_P, _SZ, _P]),
     "muvo_voxelize": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -108,3 +110,26 @@ def require_cuda(*tensors) -> None:
 def current_stream(device=None) -> int:
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class profile:
+    """``with _lib.profile(stream) as p: ...`` -> ``p.kernels`` = [(kernel name, milliseconds), ...] per launch."""
+
+    def __init__(self, stream: int):
+        self.stream = stream
+        self.kernels = []
+
+    def __enter__(self):
+        check(load().muvo_profile_begin(self.stream), "muvo_profile_begin")
+        return self
+
+    def __exit__(self, *exc):
+        cap = 64
+        ms = (C.c_float * cap)()
+        names = (C.c_char_p * cap)()
+        n = _I32(0)
+        rc = load().muvo_profile_end(self.stream, cap, ms, names, C.byref(n))
+        if exc[0] is None:
+            check(rc, "muvo_profile_end")
+        self.kernels = [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+        return False

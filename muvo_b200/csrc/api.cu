@@ -1,7 +1,42 @@
 // ABI version + error strings.
 #include "common.cuh"
 
+namespace muvo {
+Profile& profile_state() {
+  static thread_local Profile p;
+  return p;
+}
+}  // namespace muvo
+
 extern "C" {
+
+int muvo_profile_begin(void* stream) {
+  muvo::Profile& p = muvo::profile_state();
+  p.n = 0;
+  p.on = true;
+  muvo::prof_mark("begin", (cudaStream_t)stream);
+  return p.n == 1 ? MUVO_OK : MUVO_E_ARG;
+}
+
+int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char** names_out_h, int32_t* n_out_h) {
+  muvo::Profile& p = muvo::profile_state();
+  if (!p.on) return MUVO_E_ARG;
+  p.on = false;
+  if (!n_out_h) return MUVO_E_NULL;
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  int n = p.n - 1;
+  if (n > capacity) n = capacity;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    e = cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+    if (e != cudaSuccess) return (int)e;
+    if (ms_out_h) ms_out_h[i] = ms;
+    if (names_out_h) names_out_h[i] = p.name[i + 1];
+  }
+  *n_out_h = n;
+  return MUVO_OK;
+}
 
 int muvo_abi_version(void) { return MUVO_B200_ABI_VERSION; }
 

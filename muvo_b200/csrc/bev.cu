@@ -406,13 +406,13 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   const int64_t n_chunks = (int64_t)B * w.n_wc;
   const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
   k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_cell_hist", st);
   k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_cell_scan", st);
   k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_cell_starts", st);
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_cell_place", st);
   if (sp == 1) {
     const int64_t warps = (int64_t)B * n_cells;
     k_pool_point_major<T><<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(x, sb, sc, w.cell_start, w.sorted, B, n_pts, C,
@@ -421,7 +421,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
     k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,
                                                                              C, n_cells, out);
   }
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH(sp == 1 ? "k_pool_point_major" : "k_pool_channel_major", st);
   return MUVO_OK;
 }
 
@@ -435,7 +435,7 @@ static int run_pool_bwd(const float* gout, const int32_t* cell, int B, int64_t n
     int64_t n = (int64_t)B * n_pts * C;
     k_pool_bwd_generic<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(gout, cell, B, n_pts, C, n_cells, gx, sb, sp, sc);
   }
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH(sp == 1 ? "k_pool_bwd_point_major" : "k_pool_bwd_generic", st);
   return MUVO_OK;
 }
 
@@ -514,15 +514,15 @@ int muvo_segment_sum_fwd(const float* x, const int64_t* ranks, int64_t n, int32_
   SegWs w = carve_seg(ws, n);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
   k_seg_block_count<<<w.nblocks, kScanBlock, 0, st>>>(ranks, n, w.block_cnt);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_seg_block_count", st);
   k_seg_scan_blocks<<<1, 1024, 0, st>>>(w.block_cnt, w.nblocks, n_seg_out);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_seg_scan_blocks", st);
   k_seg_assign<<<w.nblocks, kScanBlock, 0, st>>>(ranks, n, w.block_cnt, seg_id_out, last_row_out);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_seg_assign", st);
   if (C > 0) {
     int64_t grid = n < (int64_t)kNumSMsB200 * 16 ? n : (int64_t)kNumSMsB200 * 16;
     k_seg_sum<<<(unsigned)grid, 256, 0, st>>>(x, last_row_out, n_seg_out, C, x_seg_out);
-    MUVO_LAUNCH_CHECK();
+    MUVO_AFTER_LAUNCH("k_seg_sum", st);
   }
   return MUVO_OK;
 }
@@ -531,8 +531,9 @@ int muvo_segment_sum_bwd(const float* grad_seg, const int32_t* seg_id, int64_t n
   if (n < 0 || C < 0) return MUVO_E_ARG;
   if (n == 0 || C == 0) return MUVO_OK;
   if (!grad_seg || !seg_id || !grad_x) return MUVO_E_NULL;
-  k_seg_bwd<<<(unsigned)ceil_div64(n * C, 256), 256, 0, (cudaStream_t)stream>>>(grad_seg, seg_id, n, C, grad_x);
-  MUVO_LAUNCH_CHECK();
+  cudaStream_t st = (cudaStream_t)stream;
+  k_seg_bwd<<<(unsigned)ceil_div64(n * C, 256), 256, 0, st>>>(grad_seg, seg_id, n, C, grad_x);
+  MUVO_AFTER_LAUNCH("k_seg_bwd", st);
   return MUVO_OK;
 }
 

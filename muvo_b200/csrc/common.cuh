@@ -9,10 +9,36 @@
     cudaError_t e__ = cudaPeekAtLastError();                  \
     if (e__ != cudaSuccess) return (int)cudaGetLastError();   \
   } while (0)
+// launch check + optional profiling mark named after the kernel
+#define MUVO_AFTER_LAUNCH(name, st)                           \
+  do {                                                        \
+    MUVO_LAUNCH_CHECK();                                      \
+    ::muvo::prof_mark(name, st);                              \
+  } while (0)
 
 namespace muvo {
 
 constexpr int kNumSMsB200 = 148;
+
+// Optional per-kernel timing (muvo_profile_begin/end): when active on this host thread, every launch site
+// records a CUDA event on the launching stream right after its kernel.  Inactive -> a single branch.
+constexpr int kProfMax = 64;
+struct Profile {
+  cudaEvent_t ev[kProfMax];
+  const char* name[kProfMax];
+  int n = 0;
+  int created = 0;
+  bool on = false;
+};
+Profile& profile_state();
+inline void prof_mark(const char* name, cudaStream_t st) {
+  Profile& p = profile_state();
+  if (!p.on || p.n >= kProfMax) return;
+  if (p.n >= p.created) { if (cudaEventCreate(&p.ev[p.created]) != cudaSuccess) return; ++p.created; }
+  p.name[p.n] = name;
+  cudaEventRecord(p.ev[p.n], st);
+  ++p.n;
+}
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -411,10 +411,14 @@ k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, cons
 // Shared by the emit kernels: lane L owns bitmap word (warp_word0 + L); returns the word and the rank of
 // its first bit.  Ranks of the 4 words of a chunk are built with shuffles, so no lane ever re-reads a
 // word that its owner may already have cleared.
-__device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-                                                   int64_t word_global, bool valid, uint32_t* word_o, uint32_t* rank_o) {
+__device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix,
+                                                   int64_t word_global, bool valid, bool clean, uint32_t* word_o,
+                                                   uint32_t* rank_o) {
   uint32_t word = valid ? bitmap[word_global] : 0u;
   uint32_t base = valid ? prefix[word_global >> 2] : 0u;
+  // the workspace is shared by calls with different layouts, so the prefix table is cleared as well
+  // (the 4 lanes of a chunk read the entry in the same instruction; its first lane clears it afterwards)
+  if (clean && valid && base && (lane_id() & 3u) == 0u) prefix[word_global >> 2] = 0u;
   uint32_t pc = __popc(word);
   unsigned lane = lane_id();
   uint32_t p1 = __shfl_up_sync(0xffffffffu, pc, 1);
@@ -455,14 +459,14 @@ __device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, uin
 // Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as
 // two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).
 __global__ void __launch_bounds__(kBlock)
-k_emit_dense(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
+k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
              const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, const uint8_t* __restrict__ remap,
              uint8_t* __restrict__ dense, GridDev g, int F, bool clean) {
   int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;     // global word index over [F, gw]
   int64_t total = (int64_t)F * g.gw;
   bool valid = wg < total;
   uint32_t word, rank;
-  load_word_and_rank(bitmap, prefix, wg, valid, &word, &rank);
+  load_word_and_rank(bitmap, prefix, wg, valid, clean, &word, &rank);
   unsigned lane = lane_id();
   int64_t warp_w0 = wg - lane;                                  // first word of this warp (same frame: gw % 32 == 0)
   if (warp_w0 >= total) return;                                 // whole warp out of range
@@ -493,14 +497,14 @@ k_emit_dense(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
 
 // Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(frame_offsets[f] + rank)].
 __global__ void __launch_bounds__(kBlock)
-k_emit_sparse(uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
+k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
               const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, uint16_t* __restrict__ sparse,
               GridDev g, int F, bool clean) {
   int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   int64_t total = (int64_t)F * g.gw;
   bool valid = wg < total;
   uint32_t word, rank;
-  load_word_and_rank(bitmap, prefix, wg, valid, &word, &rank);
+  load_word_and_rank(bitmap, prefix, wg, valid, clean, &word, &rank);
   if (!valid || !word) return;
   int f = (int)(wg / g.gw);
   int64_t fbeg = __ldg(off + f);
@@ -677,16 +681,16 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       k_point_pass<T, true, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
     else
       k_point_pass<T, false, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
-    MUVO_LAUNCH_CHECK();
+    MUVO_AFTER_LAUNCH("k_point_pass", st);
   }
   if (do_vox) {
     // K2
     k_bitmap_scan<<<F, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, n_occ);
-    MUVO_LAUNCH_CHECK();
+    MUVO_AFTER_LAUNCH("k_bitmap_scan", st);
     // K3
     if (P > 0) {
       k_voxel_resolve<T><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.win);
-      MUVO_LAUNCH_CHECK();
+      MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
     }
     // K4 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;
@@ -696,15 +700,15 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       } else {  // only n_occ requested: clear through the sparse walker without output
         k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, nullptr, g, F, true);
       }
-      MUVO_LAUNCH_CHECK();
+      MUVO_AFTER_LAUNCH(dense ? "k_emit_dense" : "k_emit_sparse", st);
     } else {
       if (dense) {
         k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off,
                                                                                  remap, dense, g, F);
-        MUVO_LAUNCH_CHECK();
+        MUVO_AFTER_LAUNCH("k_emit_dense_from_linear", st);
       }
       k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, sparse, g, F, true);
-      MUVO_LAUNCH_CHECK();
+      MUVO_AFTER_LAUNCH("k_emit_sparse", st);
     }
   }
   if (do_range) {
@@ -724,7 +728,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       else
         k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
     }
-    MUVO_LAUNCH_CHECK();
+    MUVO_AFTER_LAUNCH("k_emit_range", st);
   }
   return MUVO_OK;
 }

@@ -193,7 +193,7 @@ static int launch_counts(const void* pred, const uint8_t* target, const uint8_t*
   int64_t cap = (int64_t)kNumSMsB200 * per_sm;
   unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
   k_ssc_counts<PT><<<grid, thr, smem, st>>>((const PT*)pred, target, ne, ns, ignore255, n, C, out);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_ssc_counts", st);
   return MUVO_OK;
 }
 
@@ -209,7 +209,7 @@ static int launch_logits(const void* logits, const uint8_t* target, int F, int C
   int64_t cap = (int64_t)kNumSMsB200 * per_sm;
   unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
   k_ssc_from_logits<LT><<<grid, thr, smem, st>>>((const LT*)logits, target, F, C, S, ignore255, out);
-  MUVO_LAUNCH_CHECK();
+  MUVO_AFTER_LAUNCH("k_ssc_from_logits", st);
   return MUVO_OK;
 }
 

@@ -1,0 +1,135 @@
+"""Host-buffer front end for stages (a)+(b): the call a data-loading process makes.
+
+``HostPipeline.submit(points_np, sem_np, frame_offsets_np)`` stages the ragged batch through pinned host
+memory, runs the fused point kernels and copies the reference-facing results back into pinned host
+buffers: the sparse ``(n,4) uint16`` voxel lists (what ``voxel_filter`` returns) and/or the dense grids,
+and the range images (what ``do_range_projection`` returns).  Two slots are double-buffered over three
+streams (H2D / kernels / D2H), so the copies of batch i+1 overlap the kernels of batch i and the
+read-back of batch i-1; PCIe is full duplex.  ``result()`` blocks on the oldest in-flight batch.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .points import GridSpec, RangeSpec, sensor_to_grid
+
+
+class _Slot:
+    def __init__(self):
+        self.cap_pts = 0
+        self.cap_frames = 0
+        self.h_pts = self.h_sem = self.h_off = None
+        self.d_pts = self.d_sem = self.d_off = None
+        self.dev_out = {}
+        self.host_out = {}
+        self.done = None
+        self.busy = False
+        self.meta = None
+
+
+class HostPipeline:
+    def __init__(self, device=None, grid: Optional[GridSpec] = GridSpec(), range_spec: Optional[RangeSpec] = RangeSpec(),
+                 dense: bool = False, sparse: bool = True, layout: str = "hwc", remap: Optional[np.ndarray] = None,
+                 depth: int = 2):
+        if not torch.cuda.is_available():
+            raise _lib.MuvoError("muvo_b200 kernels need a CUDA device (sm_100a); no CPU fallback exists")
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MuvoError("HostPipeline needs a CUDA device")
+        self.grid, self.range_spec = grid, range_spec
+        self.dense, self.sparse, self.layout = dense, sparse, layout
+        self.remap = torch.from_numpy(np.ascontiguousarray(remap)).to(self.device) if remap is not None else None
+        self.s_in = torch.cuda.Stream(self.device)
+        self.s_run = torch.cuda.Stream(self.device)
+        self.s_out = torch.cuda.Stream(self.device)
+        self.slots = [_Slot() for _ in range(depth)]
+        self.queue = []
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _ensure(self, slot: _Slot, n_pts: int, n_frames: int):
+        if n_pts > slot.cap_pts:
+            cap = max(n_pts, int(slot.cap_pts * 1.25), 1024)
+            slot.h_pts = torch.empty((cap, 3), dtype=torch.float32).pin_memory()
+            slot.h_sem = torch.empty((cap,), dtype=torch.uint8).pin_memory()
+            slot.d_pts = torch.empty((cap, 3), dtype=torch.float32, device=self.device)
+            slot.d_sem = torch.empty((cap,), dtype=torch.uint8, device=self.device)
+            slot.cap_pts = cap
+            slot.dev_out.pop("voxel_sparse", None)
+            slot.host_out.pop("voxel_sparse", None)
+        if n_frames > slot.cap_frames:
+            slot.h_off = torch.empty((n_frames + 1,), dtype=torch.int64).pin_memory()
+            slot.d_off = torch.empty((n_frames + 1,), dtype=torch.int64, device=self.device)
+            slot.cap_frames = n_frames
+            slot.dev_out = {}
+            slot.host_out = {}
+
+    def submit(self, points: np.ndarray, semantics: np.ndarray, frame_offsets: np.ndarray):
+        """Enqueue one ragged batch (host arrays).  Returns immediately; see :meth:`result`."""
+        slot = next((s for s in self.slots if not s.busy), None)
+        if slot is None:
+            raise RuntimeError("all pipeline slots are in flight; call result() first")
+        n_pts, n_frames = int(points.shape[0]), int(len(frame_offsets) - 1)
+        self._ensure(slot, n_pts, n_frames)
+        # host -> pinned staging (the application's arrays are ordinary pageable memory)
+        slot.h_pts[:n_pts].numpy()[...] = points
+        slot.h_sem[:n_pts].numpy()[...] = semantics.reshape(-1)
+        slot.h_off[:n_frames + 1].numpy()[...] = frame_offsets
+        with torch.cuda.device(self.device):
+            if slot.done is not None:
+                self.s_in.wait_event(slot.done)           # previous read-back of this slot finished
+            with torch.cuda.stream(self.s_in):
+                slot.d_pts[:n_pts].copy_(slot.h_pts[:n_pts], non_blocking=True)
+                slot.d_sem[:n_pts].copy_(slot.h_sem[:n_pts], non_blocking=True)
+                slot.d_off[:n_frames + 1].copy_(slot.h_off[:n_frames + 1], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_in)
+            self.h2d_bytes = n_pts * 13 + (n_frames + 1) * 8
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(ev_in)
+                out = {k: v for k, v in slot.dev_out.items() if v.shape[0] in (n_frames, slot.cap_pts)}
+                res = sensor_to_grid(slot.d_pts[:n_pts], slot.d_sem[:n_pts], slot.d_off[:n_frames + 1], grid=self.grid,
+                                     range_spec=self.range_spec, dense=self.dense, sparse=self.sparse, remap=self.remap,
+                                     layout=self.layout, out=out)
+                ev_run = torch.cuda.Event()
+                ev_run.record(self.s_run)
+            keys = [k for k in res if k not in ("frame_offsets", "diag")]
+            slot.dev_out = {k: res[k] for k in keys}
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ev_run)
+                nbytes = 0
+                for k in keys:
+                    t = res[k]
+                    h = slot.host_out.get(k)
+                    if h is None or h.shape != t.shape:
+                        h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                        slot.host_out[k] = h
+                    h.copy_(t, non_blocking=True)
+                    nbytes += t.numel() * t.element_size()
+                slot.done = torch.cuda.Event()
+                slot.done.record(self.s_out)
+            self.d2h_bytes = nbytes
+        slot.busy = True
+        slot.meta = (n_pts, n_frames)
+        self.queue.append(slot)
+
+    def result(self) -> dict:
+        """Blocks until the oldest submitted batch is back in host memory; returns its pinned host tensors.
+
+        ``voxel_sparse`` rows of frame f are ``[frame_offsets[f], frame_offsets[f] + n_occ[f])`` (int16 storage,
+        view as uint16).  The buffers are reused by the next ``submit`` on the same slot.
+        """
+        slot = self.queue.pop(0)
+        slot.done.synchronize()
+        slot.busy = False
+        return dict(slot.host_out)
+
+    def drain(self):
+        while self.queue:
+            self.result()
