@@ -239,6 +239,21 @@ __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
 }
 
 // ---------------------------------------------------------------- K1: point pass
+// Frame of each of the thread's (up to) 4 consecutive points.
+__device__ __forceinline__ void quad_frames(const int64_t* __restrict__ off, int F, int64_t i0, int n, int* fr, int64_t* fb) {
+  int f = find_frame(off, F, i0);
+  int64_t fbeg = __ldg(off + f), fend = __ldg(off + f + 1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < n) {
+      while (i0 + k >= fend) { ++f; fbeg = fend; fend = __ldg(off + f + 1); }
+    }
+    fr[k] = f; fb[k] = fbeg;
+  }
+}
+
+// The 4 points of a thread are processed in lock step so that their atomics and competitor gathers are
+// in flight together (the kernels are latency bound otherwise).
 template <typename T, bool DO_VOX, bool DO_RANGE>
 __global__ void __launch_bounds__(kBlock)
 k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
@@ -250,39 +265,64 @@ k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const i
     int n = (int)min((int64_t)4, P - i0);
     Quad<T> q;
     load_quad(xyz, sem, i0, n, vec_ok, q);
-    int f = find_frame(off, F, i0);
-    int64_t fbeg = __ldg(off + f), fend = __ldg(off + f + 1);
+    int fr[4]; int64_t fb[4];
+    quad_frames(off, F, i0, n, fr, fb);
+    if (DO_VOX) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (k < n) {
-        int64_t i = i0 + k;
-        while (i >= fend) { ++f; fbeg = fend; fend = __ldg(off + f + 1); }
-        if (DO_VOX) {
+      for (int k = 0; k < 4; ++k) {
+        if (k < n) {
           VoxKey v = vox_of((double)q.x[k], (double)q.y[k], (double)q.z[k], g);
           if (v.in) {
             ++n_in;
-            atomicOr(bitmap + (size_t)f * g.gw + (v.bit >> 5), 1u << (v.bit & 31));
+            atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), 1u << (v.bit & 31));
           }
         }
-        if (DO_RANGE) {
+      }
+    }
+    if (DO_RANGE) {
+      double depth[4];
+      uint32_t* slot[4];
+      uint32_t me1[4], old[4];
+      bool act[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        act[k] = false; depth[k] = 0.0; slot[k] = pixtab; me1[k] = 0;
+        if (k < n) {
           PixKey pk = pix_of(q.x[k], q.y[k], q.z[k], r);
-          if (!pk.ok) {
-            ++n_drop;
-          } else {
+          if (!pk.ok) { ++n_drop; }
+          else {
             n_nw += pk.near_w; n_nh += pk.near_h;
-            uint32_t* slot = pixtab + (size_t)f * r.H * r.W + pk.pix;
-            uint32_t me1 = (uint32_t)(i - fbeg) + 1u;
-            uint32_t old = atomicCAS(slot, 0u, me1);
-            while (old != 0u) {   // occupied: compare against the current winner's key
-              const T* qp = xyz + 3 * (fbeg + (int64_t)(old - 1u));
-              double a, b, c;
-              double dq = range_depth_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c);
-              bool better = (pk.depth < dq) || (pk.depth == dq && me1 < old);
-              if (!better) break;
-              uint32_t prev = atomicCAS(slot, old, me1);
-              if (prev == old) break;
-              old = prev;
-            }
+            act[k] = true; depth[k] = pk.depth;
+            slot[k] = pixtab + (size_t)fr[k] * r.H * r.W + pk.pix;
+            me1[k] = (uint32_t)(i0 + k - fb[k]) + 1u;
+          }
+        }
+      }
+      // duplicates inside the quad (scan-ordered clouds put neighbours in the same pixel): keep the better key
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = k + 1; j < 4; ++j)
+          if (act[k] && act[j] && slot[k] == slot[j]) { if (depth[j] < depth[k]) act[k] = false; else act[j] = false; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicCAS(slot[k], 0u, me1[k]) : 0u;
+      while (old[0] | old[1] | old[2] | old[3]) {     // occupied slots: compare against the current winner's key
+        double dq[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          dq[k] = 0.0;
+          if (old[k]) {
+            const T* qp = xyz + 3 * (fb[k] + (int64_t)(old[k] - 1u));
+            double a, b, c;
+            dq[k] = range_depth_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (old[k]) {
+            bool better = (depth[k] < dq[k]) || (depth[k] == dq[k] && me1[k] < old[k]);
+            if (!better) old[k] = 0u;
+            else { uint32_t prev = atomicCAS(slot[k], old[k], me1[k]); old[k] = (prev == old[k]) ? 0u : prev; }
           }
         }
       }
@@ -365,6 +405,12 @@ __device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_
 }
 
 // ---------------------------------------------------------------- K3: voxel resolve
+__device__ __forceinline__ bool vox_better(bool my_notroad, double my_dis, uint32_t my1, bool o_notroad, double o_dis,
+                                           uint32_t o1) {
+  if (my_notroad != o_notroad) return !my_notroad;                 // any roadline point wins (:217)
+  return (my_dis < o_dis) || (my_dis == o_dis && my1 < o1);        // argmin, first minimum (:217)
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
@@ -375,36 +421,75 @@ k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, cons
   int n = (int)min((int64_t)4, P - i0);
   Quad<T> q;
   load_quad(xyz, sem, i0, n, vec_ok, q);
-  int f = find_frame(off, F, i0);
-  int64_t fbeg = __ldg(off + f), fend = __ldg(off + f + 1);
+  int fr[4]; int64_t fb[4];
+  quad_frames(off, F, i0, n, fr, fb);
+  double dis[4];
+  uint32_t bit[4], me1[4], old[4];
+  uint32_t* slot[4];
+  bool act[4], notroad[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
+    act[k] = false; dis[k] = 0.0; bit[k] = 0; me1[k] = 0; slot[k] = win; notroad[k] = true;
     if (k < n) {
-      int64_t i = i0 + k;
-      while (i >= fend) { ++f; fbeg = fend; fend = __ldg(off + f + 1); }
       VoxKey v = vox_of((double)q.x[k], (double)q.y[k], (double)q.z[k], g);
-      if (v.in) {
-        uint32_t rank = rank_of(bitmap + (size_t)f * g.gw, prefix + (size_t)f * (g.gw / 4), v.bit);
-        uint32_t* slot = win + fbeg + rank;
-        uint32_t me1 = (uint32_t)(i - fbeg) + 1u;
-        bool my_notroad = (int)((q.sem4 >> (8 * k)) & 0xffu) != g.road;
-        uint32_t old = atomicCAS(slot, 0u, me1);
-        while (old != 0u) {
-          int64_t qi = fbeg + (int64_t)(old - 1u);
-          const T* qp = xyz + 3 * qi;
-          VoxKey o = vox_of((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
-          bool o_notroad = (int)__ldg(sem + qi) != g.road;
-          bool better;
-          if (my_notroad != o_notroad) better = !my_notroad;                 // any roadline point wins (:217)
-          else better = (v.dis < o.dis) || (v.dis == o.dis && me1 < old);    // argmin, first minimum (:217)
-          if (!better) break;
-          uint32_t prev = atomicCAS(slot, old, me1);
-          if (prev == old) break;
-          old = prev;
-        }
+      act[k] = v.in; dis[k] = v.dis; bit[k] = v.bit;
+      me1[k] = (uint32_t)(i0 + k - fb[k]) + 1u;
+      notroad[k] = (int)((q.sem4 >> (8 * k)) & 0xffu) != g.road;
+    }
+  }
+  // duplicates inside the quad: keep the better key
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int j = k + 1; j < 4; ++j)
+      if (act[k] && act[j] && fr[k] == fr[j] && bit[k] == bit[j]) {
+        if (vox_better(notroad[j], dis[j], me1[j], notroad[k], dis[k], me1[k])) act[k] = false; else act[j] = false;
+      }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {   // rank lookups of the 4 points are independent loads
+    if (act[k]) {
+      uint32_t rank = rank_of(bitmap + (size_t)fr[k] * g.gw, prefix + (size_t)fr[k] * (g.gw / 4), bit[k]);
+      slot[k] = win + fb[k] + rank;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicCAS(slot[k], 0u, me1[k]) : 0u;
+  while (old[0] | old[1] | old[2] | old[3]) {
+    double od[4]; bool onr[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      od[k] = 0.0; onr[k] = true;
+      if (old[k]) {
+        int64_t qi = fb[k] + (int64_t)(old[k] - 1u);
+        const T* qp = xyz + 3 * qi;
+        VoxKey o = vox_of((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
+        od[k] = o.dis;
+        onr[k] = (int)__ldg(sem + qi) != g.road;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (old[k]) {
+        if (!vox_better(notroad[k], dis[k], me1[k], onr[k], od[k], old[k])) old[k] = 0u;
+        else { uint32_t prev = atomicCAS(slot[k], old[k], me1[k]); old[k] = (prev == old[k]) ? 0u : prev; }
       }
     }
   }
+}
+
+// ---------------------------------------------------------------- K3b: slot labels
+// One thread per winner slot: replace the winner's point index by (0x80000000 | its raw label), so that the
+// emit kernels need a single gather per occupied voxel.  Slots that were never claimed stay 0.
+constexpr uint32_t kLabelTag = 0x80000000u;
+__global__ void __launch_bounds__(kBlock)
+k_slot_labels(uint32_t* __restrict__ win, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P) {
+  int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (s >= P) return;
+  uint32_t w1 = win[s];
+  if (!w1) return;
+  int f = find_frame(off, F, s);
+  uint32_t lab = __ldg(sem + __ldg(off + f) + (int64_t)(w1 - 1u));
+  win[s] = kLabelTag | lab;
 }
 
 // ---------------------------------------------------------------- K4: emit
@@ -429,29 +514,34 @@ __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap
   *word_o = word; *rank_o = rank;
 }
 
-__device__ __forceinline__ uint32_t label_of_slot(uint32_t* __restrict__ win, const uint8_t* __restrict__ sem,
-                                                  const uint8_t* __restrict__ remap, int64_t fbeg, uint32_t rank, bool clean) {
+__device__ __forceinline__ uint32_t label_of_slot(uint32_t* __restrict__ win, const uint8_t* __restrict__ remap,
+                                                  int64_t fbeg, uint32_t rank, bool clean) {
   uint32_t* slot = win + fbeg + rank;
-  uint32_t w1 = *slot;
+  uint32_t v = *slot;                       // kLabelTag | raw label (k_slot_labels)
   if (clean) *slot = 0u;
-  uint32_t lab = 0;
-  if (w1) {
-    lab = __ldg(sem + fbeg + (int64_t)(w1 - 1u));
-    if (remap) lab = __ldg(remap + lab);
-  }
+  uint32_t lab = v & 0xffu;
+  if (remap) lab = __ldg(remap + lab);
   return lab;
 }
 
-// 16 voxels (a half word) -> 16 label bytes
+// 16 voxels (a half word) -> 16 label bytes.  The loads of all set bits are independent (rank + c).
 __device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, uint32_t* __restrict__ win,
-                                             const uint8_t* __restrict__ sem, const uint8_t* __restrict__ remap,
-                                             int64_t fbeg, bool clean) {
+                                             const uint8_t* __restrict__ remap, int64_t fbeg, bool clean) {
   uint32_t o[4] = {0u, 0u, 0u, 0u};
-  while (bits16) {
-    int j = __ffs(bits16) - 1;
-    bits16 &= bits16 - 1;
-    uint32_t lab = label_of_slot(win, sem, remap, fbeg, rank++, clean);
-    o[j >> 2] |= lab << (8 * (j & 3));
+  if (bits16) {
+    uint32_t* slots = win + fbeg + rank;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if ((bits16 >> j) & 1u) {
+        uint32_t v = slots[c];
+        if (clean) slots[c] = 0u;
+        ++c;
+        uint32_t lab = v & 0xffu;
+        if (remap) lab = __ldg(remap + lab);
+        o[j >> 2] |= lab << (8 * (j & 3));
+      }
+    }
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -482,7 +572,8 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint3
     uint32_t rk = __shfl_sync(0xffffffffu, rank, src);
     uint32_t bits = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
     if (lane & 1u) rk += __popc(w & 0xffffu);
-    uint4 o = expand_half(bits, rk, win, sem, remap, fbeg, clean);
+    uint4 o = expand_half(bits, rk, win, remap, fbeg, clean);
+    __syncwarp();   // reconverge after the data-dependent gathers so that the store below is one 512-byte request
     int64_t v = vox0 + ((int64_t)half * 32 + lane) * 16;        // first voxel of this piece
     if (fast) {
       if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + ((int64_t)half * 32 + lane) * 16), o);
@@ -517,7 +608,7 @@ k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint
     uint32_t x = lin % (uint32_t)g.dx;
     uint32_t yz = lin / (uint32_t)g.dx;
     uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
-    uint32_t lab = label_of_slot(win, sem, nullptr, fbeg, rank, clean);
+    uint32_t lab = label_of_slot(win, nullptr, fbeg, rank, clean);
     if (sparse) {
       uint2 row = make_uint2(x | (y << 16), z | (lab << 16));
       *reinterpret_cast<uint2*>(sparse + (size_t)(fbeg + rank) * 4) = row;
@@ -545,8 +636,8 @@ k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __
   if ((bm[lin >> 5] >> (lin & 31)) & 1u) {
     uint32_t rank = rank_of(bm, prefix + (size_t)f * (g.gw / 4), lin);
     int64_t fbeg = __ldg(off + f);
-    uint32_t w1 = win[fbeg + rank];
-    if (w1) { lab = __ldg(sem + fbeg + (int64_t)(w1 - 1u)); if (remap) lab = __ldg(remap + lab); }
+    lab = win[fbeg + rank] & 0xffu;
+    if (remap) lab = __ldg(remap + lab);
   }
   dense[t] = (uint8_t)lab;
 }
@@ -691,6 +782,8 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     if (P > 0) {
       k_voxel_resolve<T><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.win);
       MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
+      k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.win, sem, off, F, P);
+      MUVO_AFTER_LAUNCH("k_slot_labels", st);
     }
     // K4 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;

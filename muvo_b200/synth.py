@@ -32,7 +32,8 @@ def carla_lidar_frame(n_points: int, seed: int, beams: int = 64):
 
     64 beams with pitch linspace(-30 deg, +10 deg), uniform azimuth; each ray hits the
     ground plane (LiDAR 2 m above it) or a per-azimuth-sector wall, whichever is
-    nearer; rays hitting nothing are dropped and resampled.  Returns
+    nearer; rays hitting nothing are dropped and resampled.  Points come out in SCAN ORDER (channel-major,
+    azimuth ascending), as CARLA's ray-cast LiDAR delivers them (carla_gym/.../lidar/ray_cast_semantic.py:197-219).  Returns
     ``(points float32 (n,3), semantics uint8 (n,))`` with raw CARLA tags: road 7,
     road lines 6 (stripes), walls 1, 2 % vehicles 10.
     """
@@ -41,11 +42,12 @@ def carla_lidar_frame(n_points: int, seed: int, beams: int = 64):
     wall_dist = rng.uniform(5.0, 80.0, n_sectors)
     wall_height = rng.uniform(3.0, 15.0, n_sectors)
     pitches = np.deg2rad(np.linspace(RANGE_FOV[0], RANGE_FOV[1], beams))
-    pts, sems = [], []
+    pts, sems, keys = [], [], []
     have = 0
     while have < n_points:
         m = int((n_points - have) * 1.6) + 64
-        pitch = pitches[rng.integers(0, beams, m)]
+        beam = rng.integers(0, beams, m)
+        pitch = pitches[beam]
         az = rng.uniform(-np.pi, np.pi, m)
         sector = np.minimum(((az + np.pi) / (2 * np.pi) * n_sectors).astype(np.int64), n_sectors - 1)
         with np.errstate(divide="ignore"):
@@ -65,9 +67,13 @@ def carla_lidar_frame(n_points: int, seed: int, beams: int = 64):
         sem = np.where(hit_ground, 7, 1).astype(np.uint8)[ok]
         pts.append(p)
         sems.append(sem)
+        keys.append(np.stack([beam[ok].astype(np.float64), az[ok]], 1))
         have += p.shape[0]
     p = np.concatenate(pts)[:n_points]
     sem = np.concatenate(sems)[:n_points]
+    key = np.concatenate(keys)[:n_points]
+    order = np.lexsort((key[:, 1], key[:, 0]))          # channel-major, azimuth ascending
+    p, sem = p[order], sem[order]
     # data/data_preprocessing.py:119-122 (convert_coor_lidar): += lidar_pos ; y *= -1 (float32)
     p = p + np.asarray(LIDAR_POSITION, dtype=np.float32)
     p[:, 1] *= -1

@@ -1,0 +1,48 @@
+"""Run a few cfg2 steps (for ncu): python tools/prof_step.py [--frames 96] [--steps 4] [--stage points|bev|ssc]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import muvo_b200  # noqa: E402
+from muvo_b200 import synth  # noqa: E402
+from muvo_b200.points import GridSpec, RangeSpec, sensor_to_grid  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--frames", type=int, default=96)
+ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--stage", default="points")
+ap.add_argument("--nmin", type=int, default=60000)
+ap.add_argument("--nmax", type=int, default=100000)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+if a.stage == "points":
+    pts, sem, off = synth.lidar_batch(a.frames, a.nmin, a.nmax, 2000)
+    tp, ts, to = torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev), torch.from_numpy(off).to(dev)
+    remap = torch.from_numpy(synth.label_remap256()).to(dev)
+    out = {}
+    for _ in range(a.steps):
+        r = sensor_to_grid(tp, ts, to, grid=GridSpec(), range_spec=RangeSpec(lidar_position=(1.0, 0.0, 2.0)), remap=remap,
+                           layout="xyzd", out=out)
+        out = {k: r[k] for k in ("voxel", "n_occ", "range_xyzd", "range_sem")}
+elif a.stage == "bev":
+    from muvo_b200.frustum_pooling import bev_pool
+    B, C = 6, 384
+    feat, depth, mask, K, E = synth.bev_inputs(B, C, 3000, device=dev)
+    fp = muvo_b200.FrustumPooling(**synth.BEV_POOL_ARGS).to(dev)
+    x = synth.lift(feat, depth).detach().requires_grad_(True)
+    fp.initialize_frustum(x)
+    cell = fp.cell_ids(fp.get_geometry(E[:, None, :3, :3], E[:, None, :3, 3:], K[:, None]), mask)
+    for _ in range(a.steps):
+        out = bev_pool(x, cell, 2304)
+        torch.autograd.grad(out, x, torch.ones_like(out))
+else:
+    from muvo_b200.metrics import ssc_counts
+    yp, yt = synth.occupancy_pair(16, 2, 4000)
+    tp, tt = torch.from_numpy(yp).to(dev), torch.from_numpy(yt).to(dev)
+    for _ in range(a.steps):
+        ssc_counts(tp, tt, 2, ignore255=True)
+torch.cuda.synchronize()
+print("done")
