@@ -189,48 +189,96 @@ __device__ __forceinline__ int find_frame(const int64_t* __restrict__ off, int F
   return lo;
 }
 
-// ---------------------------------------------------------------- point loads (4 points / thread)
-template <typename T> struct Quad { T x[4], y[4], z[4]; uint32_t sem4; };
+// ---------------------------------------------------------------- point loads
+// A warp owns 128 consecutive points; lane L works on points base + 32k + L (k = 0..3), so that in every
+// round k the 32 lanes hold 32 CONSECUTIVE points.  Scan-ordered clouds put long runs of consecutive points
+// into the same voxel / pixel: with this layout such a run sits in adjacent lanes and is reduced inside the
+// warp (match_any + redux) before a single lane touches the table.
+// Global loads stay 16-byte vectors (3 x float4 per lane = 4 points), staged through shared memory and read
+// back with a stride of 3 words (conflict free since gcd(3, 32) = 1).
+constexpr int kWarpsPerBlock = kBlock / 32;
+constexpr int kPtsPerWarp = 128;
+constexpr int kStageWords = 3 * kPtsPerWarp + kPtsPerWarp / 4;   // xyz floats + packed semantics
+
+template <typename T> struct WarpPts { T x[4], y[4], z[4]; uint32_t sem[4]; bool valid[4]; };
 
 template <typename T>
-__device__ __forceinline__ void load_quad_scalar(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t i0,
-                                                 int n, Quad<T>& q) {
-  q.sem4 = 0;
+__device__ __forceinline__ void load_warp_points(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base,
+                                                 int64_t P, bool vec_ok, uint32_t* stage, WarpPts<T>& w) {
+  const unsigned lane = lane_id();
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (k < n) {
-      q.x[k] = __ldg(xyz + 3 * (i0 + k)); q.y[k] = __ldg(xyz + 3 * (i0 + k) + 1); q.z[k] = __ldg(xyz + 3 * (i0 + k) + 2);
-      q.sem4 |= (uint32_t)__ldg(sem + i0 + k) << (8 * k);
-    } else { q.x[k] = q.y[k] = q.z[k] = (T)0; }
+    int64_t i = base + 32 * k + lane;
+    w.valid[k] = i < P;
+    w.x[k] = w.y[k] = w.z[k] = (T)0; w.sem[k] = 0;
+    if (w.valid[k]) {
+      w.x[k] = __ldg(xyz + 3 * i); w.y[k] = __ldg(xyz + 3 * i + 1); w.z[k] = __ldg(xyz + 3 * i + 2);
+      w.sem[k] = __ldg(sem + i);
+    }
   }
 }
-__device__ __forceinline__ void load_quad(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t i0,
-                                          int n, bool vec_ok, Quad<float>& q) {
-  if (vec_ok && n == 4) {   // 4 points = 48 B = three 16-byte loads
-    const float4* p = reinterpret_cast<const float4*>(xyz + 3 * i0);
-    float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    q.x[0] = a.x; q.y[0] = a.y; q.z[0] = a.z;
-    q.x[1] = a.w; q.y[1] = b.x; q.z[1] = b.y;
-    q.x[2] = b.z; q.y[2] = b.w; q.z[2] = c.x;
-    q.x[3] = c.y; q.y[3] = c.z; q.z[3] = c.w;
-    q.sem4 = __ldg(reinterpret_cast<const uint32_t*>(sem + i0));
+template <>
+__device__ __forceinline__ void load_warp_points<float>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem,
+                                                        int64_t base, int64_t P, bool vec_ok, uint32_t* stage,
+                                                        WarpPts<float>& w) {
+  const unsigned lane = lane_id();
+  if (vec_ok && base + kPtsPerWarp <= P) {
+    const float4* src = reinterpret_cast<const float4*>(xyz + 3 * base) + 3 * lane;
+    float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    uint32_t s4 = __ldg(reinterpret_cast<const uint32_t*>(sem + base) + lane);
+    float4* dst = reinterpret_cast<float4*>(stage) + 3 * lane;
+    dst[0] = a; dst[1] = b; dst[2] = c;
+    stage[3 * kPtsPerWarp + lane] = s4;
+    __syncwarp();
+    const float* sf = reinterpret_cast<const float*>(stage);
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage + 3 * kPtsPerWarp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int j = 32 * k + lane;
+      w.valid[k] = true;
+      w.x[k] = sf[3 * j]; w.y[k] = sf[3 * j + 1]; w.z[k] = sf[3 * j + 2];
+      w.sem[k] = sb[j];
+    }
+    __syncwarp();
   } else {
-    load_quad_scalar(xyz, sem, i0, n, q);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      int64_t i = base + 32 * k + lane;
+      w.valid[k] = i < P;
+      w.x[k] = w.y[k] = w.z[k] = 0.f; w.sem[k] = 0;
+      if (w.valid[k]) {
+        w.x[k] = __ldg(xyz + 3 * i); w.y[k] = __ldg(xyz + 3 * i + 1); w.z[k] = __ldg(xyz + 3 * i + 2);
+        w.sem[k] = __ldg(sem + i);
+      }
+    }
   }
 }
-__device__ __forceinline__ void load_quad(const double* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t i0,
-                                          int n, bool vec_ok, Quad<double>& q) {
-  if (vec_ok && n == 4) {   // 4 points = 96 B = six 16-byte loads
-    const double2* p = reinterpret_cast<const double2*>(xyz + 3 * i0);
-    double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5);
-    q.x[0] = a.x; q.y[0] = a.y; q.z[0] = b.x;
-    q.x[1] = b.y; q.y[1] = c.x; q.z[1] = c.y;
-    q.x[2] = d.x; q.y[2] = d.y; q.z[2] = e.x;
-    q.x[3] = e.y; q.y[3] = f.x; q.z[3] = f.y;
-    q.sem4 = __ldg(reinterpret_cast<const uint32_t*>(sem + i0));
-  } else {
-    load_quad_scalar(xyz, sem, i0, n, q);
+
+// frames of the warp's points: one search for the first point, then a (rare) walk at frame boundaries
+__device__ __forceinline__ void warp_frames(const int64_t* __restrict__ off, int F, int64_t base, int64_t P, int* fr,
+                                            int64_t* fb) {
+  int f0 = find_frame(off, F, base < P ? base : P - 1);
+  const unsigned lane = lane_id();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int64_t i = base + 32 * k + lane;
+    int f = f0;
+    if (i < P) { while (i >= __ldg(off + f + 1)) ++f; }
+    fr[k] = f; fb[k] = __ldg(off + f);
   }
+}
+
+// Among the lanes whose `slot_id` is equal, keep only the one with the smallest 64-bit key (ties -> lowest lane,
+// i.e. lowest point index).  Uniform control flow: every lane of the warp must call this.
+__device__ __forceinline__ bool warp_group_winner(unsigned long long slot_id, unsigned long long key) {
+  const unsigned peers = __match_any_sync(0xffffffffu, slot_id);
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_min_sync(peers, hi);
+  const bool c1 = hi == mhi;
+  const unsigned mlo = __reduce_min_sync(peers, c1 ? lo : 0xffffffffu);
+  const bool c2 = c1 && lo == mlo;
+  const unsigned cand = __ballot_sync(0xffffffffu, c2) & peers;
+  return lane_id() == (unsigned)(__ffs(cand) - 1);
 }
 
 __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
@@ -239,44 +287,33 @@ __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
 }
 
 // ---------------------------------------------------------------- K1: point pass
-// Frame of each of the thread's (up to) 4 consecutive points.
-__device__ __forceinline__ void quad_frames(const int64_t* __restrict__ off, int F, int64_t i0, int n, int* fr, int64_t* fb) {
-  int f = find_frame(off, F, i0);
-  int64_t fbeg = __ldg(off + f), fend = __ldg(off + f + 1);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    if (k < n) {
-      while (i0 + k >= fend) { ++f; fbeg = fend; fend = __ldg(off + f + 1); }
-    }
-    fr[k] = f; fb[k] = fbeg;
-  }
-}
-
-// The 4 points of a thread are processed in lock step so that their atomics and competitor gathers are
-// in flight together (the kernels are latency bound otherwise).
 template <typename T, bool DO_VOX, bool DO_RANGE>
 __global__ void __launch_bounds__(kBlock)
 k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ pixtab,
              int64_t* __restrict__ diag) {
-  int64_t i0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * 4;
+  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * kStageWords];
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * kPtsPerWarp;
   unsigned n_drop = 0, n_nw = 0, n_nh = 0, n_in = 0;
-  if (i0 < P) {
-    int n = (int)min((int64_t)4, P - i0);
-    Quad<T> q;
-    load_quad(xyz, sem, i0, n, vec_ok, q);
+  if (base < P) {   // warp-uniform
+    WarpPts<T> w;
+    load_warp_points<T>(xyz, sem, base, P, vec_ok, stage_all + warp * kStageWords, w);
     int fr[4]; int64_t fb[4];
-    quad_frames(off, F, i0, n, fr, fb);
+    warp_frames(off, F, base, P, fr, fb);
     if (DO_VOX) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (k < n) {
-          VoxKey v = vox_of((double)q.x[k], (double)q.y[k], (double)q.z[k], g);
-          if (v.in) {
-            ++n_in;
-            atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), 1u << (v.bit & 31));
-          }
-        }
+        VoxKey v; v.in = false; v.bit = 0;
+        if (w.valid[k]) v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
+        n_in += v.in;
+        // one atomicOr per distinct bitmap word in the warp
+        unsigned long long wid = v.in ? ((unsigned long long)fr[k] << 32) | (v.bit >> 5) : (0xffffffff00000000ull | lane);
+        unsigned peers = __match_any_sync(0xffffffffu, wid);
+        unsigned m = v.in ? (1u << (v.bit & 31)) : 0u;
+        unsigned m_all = __reduce_or_sync(peers, m);
+        if (v.in && lane == (unsigned)(__ffs(peers) - 1)) atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), m_all);
       }
     }
     if (DO_RANGE) {
@@ -287,23 +324,23 @@ k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const i
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         act[k] = false; depth[k] = 0.0; slot[k] = pixtab; me1[k] = 0;
-        if (k < n) {
-          PixKey pk = pix_of(q.x[k], q.y[k], q.z[k], r);
+        unsigned long long sid = 0xffffffff00000000ull | lane;
+        if (w.valid[k]) {
+          PixKey pk = pix_of(w.x[k], w.y[k], w.z[k], r);
           if (!pk.ok) { ++n_drop; }
           else {
             n_nw += pk.near_w; n_nh += pk.near_h;
             act[k] = true; depth[k] = pk.depth;
-            slot[k] = pixtab + (size_t)fr[k] * r.H * r.W + pk.pix;
-            me1[k] = (uint32_t)(i0 + k - fb[k]) + 1u;
+            size_t so = (size_t)fr[k] * r.H * r.W + pk.pix;
+            slot[k] = pixtab + so;
+            sid = (unsigned long long)so;
+            me1[k] = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
           }
         }
+        // nearest point of each pixel inside the warp (depth > 0: its bit pattern orders like the value)
+        bool win = warp_group_winner(sid, (unsigned long long)__double_as_longlong(depth[k]));
+        act[k] = act[k] && win;
       }
-      // duplicates inside the quad (scan-ordered clouds put neighbours in the same pixel): keep the better key
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-#pragma unroll
-        for (int j = k + 1; j < 4; ++j)
-          if (act[k] && act[j] && slot[k] == slot[j]) { if (depth[j] < depth[k]) act[k] = false; else act[j] = false; }
 #pragma unroll
       for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicCAS(slot[k], 0u, me1[k]) : 0u;
       while (old[0] | old[1] | old[2] | old[3]) {     // occupied slots: compare against the current winner's key
@@ -328,6 +365,7 @@ k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const i
       }
     }
   }
+  __syncwarp();
   if (diag) {
     if (DO_RANGE) {
       diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
@@ -416,13 +454,15 @@ __global__ void __launch_bounds__(kBlock)
 k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
                 bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
                 uint32_t* __restrict__ win) {
-  int64_t i0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * 4;
-  if (i0 >= P) return;
-  int n = (int)min((int64_t)4, P - i0);
-  Quad<T> q;
-  load_quad(xyz, sem, i0, n, vec_ok, q);
+  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * kStageWords];
+  const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * kPtsPerWarp;
+  if (base >= P) return;   // warp-uniform
+  WarpPts<T> w;
+  load_warp_points<T>(xyz, sem, base, P, vec_ok, stage_all + warp * kStageWords, w);
   int fr[4]; int64_t fb[4];
-  quad_frames(off, F, i0, n, fr, fb);
+  warp_frames(off, F, base, P, fr, fb);
   double dis[4];
   uint32_t bit[4], me1[4], old[4];
   uint32_t* slot[4];
@@ -430,23 +470,21 @@ k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, cons
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     act[k] = false; dis[k] = 0.0; bit[k] = 0; me1[k] = 0; slot[k] = win; notroad[k] = true;
-    if (k < n) {
-      VoxKey v = vox_of((double)q.x[k], (double)q.y[k], (double)q.z[k], g);
+    unsigned long long sid = 0xffffffff00000000ull | lane;
+    if (w.valid[k]) {
+      VoxKey v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
       act[k] = v.in; dis[k] = v.dis; bit[k] = v.bit;
-      me1[k] = (uint32_t)(i0 + k - fb[k]) + 1u;
-      notroad[k] = (int)((q.sem4 >> (8 * k)) & 0xffu) != g.road;
+      me1[k] = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
+      notroad[k] = (int)w.sem[k] != g.road;
+      if (v.in) sid = ((unsigned long long)fr[k] << 32) | v.bit;
     }
+    // best point of each voxel inside the warp: key = (not roadline, dis); dis >= 0 so bit 63 is free
+    unsigned long long key = (unsigned long long)__double_as_longlong(dis[k]) | (notroad[k] ? (1ull << 63) : 0ull);
+    bool winr = warp_group_winner(sid, key);
+    act[k] = act[k] && winr;
   }
-  // duplicates inside the quad: keep the better key
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-#pragma unroll
-    for (int j = k + 1; j < 4; ++j)
-      if (act[k] && act[j] && fr[k] == fr[j] && bit[k] == bit[j]) {
-        if (vox_better(notroad[j], dis[j], me1[j], notroad[k], dis[k], me1[k])) act[k] = false; else act[j] = false;
-      }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {   // rank lookups of the 4 points are independent loads
+  for (int k = 0; k < 4; ++k) {   // rank lookups of the surviving points are independent loads
     if (act[k]) {
       uint32_t rank = rank_of(bitmap + (size_t)fr[k] * g.gw, prefix + (size_t)fr[k] * (g.gw / 4), bit[k]);
       slot[k] = win + fb[k] + rank;
@@ -762,7 +800,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   PointsWs w = carve(ws, P, F, grid_h, cfg_h);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 4 == 0);
-  const unsigned pblocks = blocks_for(ceil_div64(P, 4));
+  const unsigned pblocks = (unsigned)ceil_div64(P, (int64_t)kWarpsPerBlock * kPtsPerWarp);
 
   // K1
   if (P > 0) {
