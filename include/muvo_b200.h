@@ -18,8 +18,10 @@
  *  - Return value: 0 = OK, <0 = MUVO_E_* below, >0 = cudaError_t of a launch.
  *    muvo_strerror() maps both to text.
  *  - Workspaces are "self-cleaning": muvo_ws_reset() must be enqueued once
- *    after allocation (and after any failed call); every successful call
- *    leaves the workspace ready for the next one.
+ *    after allocation, after any failed call, and whenever (n_frames, grid
+ *    size, H*W) differ from the previous call on that workspace (the table
+ *    layout depends on them; the number of points may vary freely).  Every
+ *    successful call leaves the workspace ready for the next one.
  *  - Frames are ragged: point p of frame f lives at rows
  *    [frame_offsets[f], frame_offsets[f+1]) of the packed point arrays.
  */

@@ -5,21 +5,26 @@
 //       densify                 muvo/data/dataset.py:317-327
 //   (b) do_range_projection     muvo/utils/geometry_utils.py:175-220
 //
-// Algorithm (no float atomics, no sort of the point stream, deterministic result):
-//   K1  point pass    : per point, float64 voxel id + range pixel/depth (numpy's op order, no FMA
-//                       contraction: this file is compiled with -fmad=false).  Occupied voxels are
-//                       marked in a 1-bit-per-voxel frame bitmap (295 KB/frame); the range pixel is
-//                       resolved on the spot with a compare-and-swap on a u32 "winner index" table
-//                       (nearest depth wins, ties -> lowest point index), comparing against the
-//                       current winner by re-deriving its key from its coordinates.
-//   K2  bitmap scan   : popcount prefix per 128-bit bitmap chunk -> every occupied voxel gets a
-//                       dense slot id = its rank (in output order); n_occ per frame.
-//   K3  voxel resolve : second point pass (cheap: no trig); same CAS-on-index on slot `rank`,
-//                       key = (not roadline, |p mod res|^2, point index).
-//   K4  emit          : bitmap-ordered, fully coalesced write of the dense uint8 grid (zeros
-//                       included, so no memset + scatter) and/or the sorted sparse (n,4) list;
-//                       pixel-ordered write of the range image.  Emit kernels put every table
-//                       entry they consume back to 0, so the workspace is clean for the next call.
+// Both stages are "arg-min with payload" scatters: per voxel the point nearest to the voxel's lower
+// corner (roadline points first), per pixel the point nearest to the sensor; ties go to the lowest point
+// index.  No float atomics, no sort of the point stream, deterministic result:
+//
+//   K1  k_point_pass    : per point, float64 voxel id + range pixel / depth in numpy's operation order (no
+//                         FMA contraction: this file is compiled with -fmad=false; an f32 pre-filter skips
+//                         the f64 trigonometry for points that are provably far from a bin edge).
+//                         Occupied voxels are marked in a 1-bit-per-voxel frame bitmap; the range pixel is
+//                         resolved with ONE 64-bit atomicMax on   (~top32(depth bits) << 32) | ~(index+1).
+//                         That packed order equals the exact (depth, index) order unless two points of a
+//                         pixel agree in the top 32 key bits; those (rare) run an exact tie protocol.
+//   K2  k_bitmap_scan   : popcount prefix per 128-bit bitmap chunk -> every occupied voxel gets a dense
+//                         slot id = its rank in output order; n_occ per frame.
+//   K3  k_voxel_resolve : second point pass (no trigonometry): same packed atomicMax on slot `rank`,
+//                         key = (not roadline, |p mod res|^2).
+//   K4  k_slot_labels   : one thread per winner slot: point index -> label byte.
+//   K5  k_emit_*        : bitmap-ordered, fully coalesced write of the dense uint8 grid (zeros included,
+//                         so no memset + scatter) and/or the sorted sparse (n,4) list; pixel-ordered write
+//                         of the range image.  Emit kernels put every table entry they consume back to 0,
+//                         so the workspace is clean for the next call.
 #include <math.h>
 #include "common.cuh"
 
@@ -30,7 +35,8 @@ constexpr int kBlock = 256;
 constexpr double kPi = 3.141592653589793;            // np.pi
 constexpr double kPiOver4 = 0x1.921fb54442d18p-1;    // correctly rounded pi/4 (numpy/glibc value on diagonals)
 constexpr double k3PiOver4 = 0x1.2d97c7f3321d2p+1;   // correctly rounded 3pi/4
-constexpr double kEdgeEps = 1e-9;
+constexpr double kEdgeEps = 1e-9;                    // diagnostics: "on a bin edge"
+constexpr float kFastEps = 2e-3f;                    // f32 pre-filter: distance to a bin edge below which f64 decides
 
 enum BitOrder { ORDER_DENSE = 0 /* (x*Dy+y)*Dz+z */, ORDER_LINEAR = 1 /* x + Dx*(y + Dy*z) */ };
 
@@ -49,18 +55,23 @@ struct RangeDev {
   int H, W;
   double fda, fov;
   double L[3];
+  float inv_pi_f, fda_f, inv_fov_f;   // f32 pre-filter constants
 };
+
+typedef unsigned long long u64;
 
 struct PointsWs {
   uint32_t* bitmap = nullptr;   // [F, gw]
   uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk
-  uint32_t* win = nullptr;      // [P]   slot = frame_offsets[f] + rank ; value = local point index + 1 (0 = empty)
-  uint32_t* pixtab = nullptr;   // [F, H*W] value = local point index + 1 (0 = empty)
+  u64* pixtab = nullptr;        // [F, H*W]   packed winner per pixel (0 = empty)
+  u64* vslot = nullptr;         // [P]        packed winner per occupied voxel, slot = frame_offsets[f] + rank
   size_t bytes = 0;
 };
 
 static int bitmap_words(int64_t G) { return (int)(ceil_div64(G, 1024) * 32); }
 
+// Region offsets depend only on (F, grid size, H*W); the per-point region comes last so that ragged batches
+// (different P) keep every table at the same address.
 static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const MuvoRangeCfg* r) {
   PointsWs w;
   size_t o = 0;
@@ -70,19 +81,29 @@ static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const Muv
     size_t gw = (size_t)bitmap_words(G);
     w.bitmap = (uint32_t*)(b + o); o = align_up(o + (size_t)F * gw * 4, 256);
     w.prefix = (uint32_t*)(b + o); o = align_up(o + (size_t)F * (gw / 4) * 4, 256);
-    w.win = (uint32_t*)(b + o);    o = align_up(o + (size_t)(P > 0 ? P : 1) * 4, 256);
   }
   if (r) {
-    w.pixtab = (uint32_t*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 4, 256);
+    w.pixtab = (u64*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 8, 256);
+  }
+  if (g) {
+    w.vslot = (u64*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 8, 256);
   }
   w.bytes = o;
   return w;
 }
 
+// ---------------------------------------------------------------- packed winner words
+// word = (~top32(key) << 32) | ~(idx + 1), key = positive float64 bit pattern (optionally with bit 63 set).
+// Larger word <=> smaller key, then smaller index; 0 = empty.
+__device__ __forceinline__ uint32_t key_top_inv(u64 key) { return ~(uint32_t)(key >> 32); }
+__device__ __forceinline__ u64 pack_word(uint32_t top_inv, uint32_t idx1) { return ((u64)top_inv << 32) | (uint32_t)(~idx1); }
+__device__ __forceinline__ uint32_t word_idx1(u64 w) { return ~(uint32_t)w; }
+__device__ __forceinline__ uint32_t word_top(u64 w) { return (uint32_t)(w >> 32); }
+
 // ---------------------------------------------------------------- per-point arithmetic
 // numpy's npy_divmod (numpy/_core/src/npymath/npy_math_internal.h.src), the scalar behind np.divmod
 // at data_preprocessing.py:183; needed when res is not a power of two.  fmod is exact on both sides.
-__device__ __forceinline__ double npy_divmod_dev(double a, double b, double* modulus) {
+__device__ __noinline__ double npy_divmod_dev(double a, double b, double* modulus) {
   double mod = fmod(a, b);
   double div = (a - mod) / b;
   if (mod != 0.0) {
@@ -129,6 +150,10 @@ __device__ __forceinline__ VoxKey vox_of(double px, double py, double pz, const 
                                    : (uint32_t)(ix + g.dx * (iy + g.dy * iz));
   return k;
 }
+// voxel ordering key: bit 63 = "not a roadline point" (dis >= 0 leaves it free), rest = dis bits
+__device__ __forceinline__ u64 vox_key(double dis, bool notroad) {
+  return (u64)__double_as_longlong(dis) | (notroad ? (1ull << 63) : 0ull);
+}
 
 // LiDAR-frame coordinates + depth (for the point itself and for re-deriving a competitor's key)
 template <typename T>
@@ -155,6 +180,26 @@ struct PixKey {
   bool near_w, near_h;
 };
 
+// float64 pixel exactly as the reference computes it (geometry_utils.py:183-200)
+__device__ __noinline__ void pix_exact(double xc, double yc, double zc, double depth, int H, int W, double fda, double fov,
+                                       int* pw_o, int* ph_o, int* flags_o) {
+  double yy = -yc;                                        // :183
+  double yaw = atan2_np(yy, xc);                          // :186
+  double pitch = asin(zc / depth);                        // :187
+  double pw = 0.5 * (1.0 - yaw / kPi);                    // :189
+  double ph = 1.0 - (pitch + fda) / fov;                  // :190
+  pw *= (double)W;                                        // :191
+  ph *= (double)H;                                        // :192
+  int flags = 0;
+  if (!(pw == pw) || !(ph == ph)) { *flags_o = 4; *pw_o = 0; *ph_o = 0; return; }
+  double fw = floor(pw), fh = floor(ph);                  // :194,:198
+  if ((pw > 0.0 && pw < (double)W) && ((pw - fw) < kEdgeEps || (pw - fw) > 1.0 - kEdgeEps)) flags |= 1;
+  if ((ph > 0.0 && ph < (double)H) && ((ph - fh) < kEdgeEps || (ph - fh) > 1.0 - kEdgeEps)) flags |= 2;
+  fw = fmax(0.0, fmin((double)(W - 1), fw));              // :195-196
+  fh = fmax(0.0, fmin((double)(H - 1), fh));              // :199-200
+  *pw_o = (int)fw; *ph_o = (int)fh; *flags_o = flags;
+}
+
 template <typename T>
 __device__ __forceinline__ PixKey pix_of(T x, T y, T z, const RangeDev& r) {
   PixKey k;
@@ -163,20 +208,26 @@ __device__ __forceinline__ PixKey pix_of(T x, T y, T z, const RangeDev& r) {
   k.ok = isfinite(k.depth) && k.depth > 0.0;
   k.pix = 0; k.near_w = k.near_h = false;
   if (!k.ok) return k;
-  double yy = -yc;                                        // :183
-  double yaw = atan2_np(yy, xc);                          // :186
-  double pitch = asin(zc / k.depth);                      // :187
-  double pw = 0.5 * (1.0 - yaw / kPi);                    // :189
-  double ph = 1.0 - (pitch + r.fda) / r.fov;              // :190
-  pw *= (double)r.W;                                      // :191
-  ph *= (double)r.H;                                      // :192
-  if (!(pw == pw) || !(ph == ph)) { k.ok = false; return k; }
-  double fw = floor(pw), fh = floor(ph);                  // :194,:198
-  k.near_w = (pw > 0.0 && pw < (double)r.W) && ((pw - fw) < kEdgeEps || (pw - fw) > 1.0 - kEdgeEps);
-  k.near_h = (ph > 0.0 && ph < (double)r.H) && ((ph - fh) < kEdgeEps || (ph - fh) > 1.0 - kEdgeEps);
-  fw = fmax(0.0, fmin((double)(r.W - 1), fw));            // :195-196
-  fh = fmax(0.0, fmin((double)(r.H - 1), fh));            // :199-200
-  k.pix = (int)fh * r.W + (int)fw;
+  // f32 pre-filter.  |error| of pw_f / ph_f vs the float64 value is < 5e-4 bins (atan2f/asinf <= 3 ulp, a few
+  // f32 roundings at magnitude <= W); if both are farther than kFastEps from an interior integer the floor
+  // cannot differ from the float64 floor.  Values beyond the image clamp to the border bins on both paths.
+  const float xf = (float)xc, yf = (float)(-yc), zf = (float)zc, df = (float)k.depth;
+  const float pw_f = 0.5f * (1.0f - atan2f(yf, xf) * r.inv_pi_f) * (float)r.W;
+  const float ph_f = (1.0f - (asinf(zf / df) + r.fda_f) * r.inv_fov_f) * (float)r.H;
+  const float fw = floorf(pw_f), fh = floorf(ph_f);
+  const bool safe_w = (pw_f <= 0.5f) || (pw_f >= (float)r.W - 0.5f) || (pw_f - fw > kFastEps && pw_f - fw < 1.0f - kFastEps);
+  const bool safe_h = (ph_f <= 0.5f) || (ph_f >= (float)r.H - 0.5f) || (ph_f - fh > kFastEps && ph_f - fh < 1.0f - kFastEps);
+  int iw, ih;
+  if (safe_w && safe_h) {   // NaN compares false -> exact path
+    iw = (int)fminf(fmaxf(fw, 0.0f), (float)(r.W - 1));
+    ih = (int)fminf(fmaxf(fh, 0.0f), (float)(r.H - 1));
+  } else {
+    int flags;
+    pix_exact(xc, yc, zc, k.depth, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
+    if (flags & 4) { k.ok = false; return k; }
+    k.near_w = flags & 1; k.near_h = flags & 2;
+  }
+  k.pix = ih * r.W + iw;
   return k;
 }
 
@@ -190,12 +241,10 @@ __device__ __forceinline__ int find_frame(const int64_t* __restrict__ off, int F
 }
 
 // ---------------------------------------------------------------- point loads
-// A warp owns 128 consecutive points; lane L works on points base + 32k + L (k = 0..3), so that in every
-// round k the 32 lanes hold 32 CONSECUTIVE points.  Scan-ordered clouds put long runs of consecutive points
-// into the same voxel / pixel: with this layout such a run sits in adjacent lanes and is reduced inside the
-// warp (match_any + redux) before a single lane touches the table.
-// Global loads stay 16-byte vectors (3 x float4 per lane = 4 points), staged through shared memory and read
-// back with a stride of 3 words (conflict free since gcd(3, 32) = 1).
+// A warp owns 128 consecutive points; lane L works on points base + 32k + L (k = 0..3).  Global loads are
+// 16-byte vectors (3 x float4 per lane = 4 points), staged through shared memory and read back with a stride
+// of 3 words (conflict free since gcd(3, 32) = 1); the 4 points of a lane are processed in lock step so that
+// their atomics are in flight together.
 constexpr int kWarpsPerBlock = kBlock / 32;
 constexpr int kPtsPerWarp = 128;
 constexpr int kStageWords = 3 * kPtsPerWarp + kPtsPerWarp / 4;   // xyz floats + packed semantics
@@ -268,29 +317,45 @@ __device__ __forceinline__ void warp_frames(const int64_t* __restrict__ off, int
   }
 }
 
-// Among the lanes whose `slot_id` is equal, keep only the one with the smallest 64-bit key (ties -> lowest lane,
-// i.e. lowest point index).  Uniform control flow: every lane of the warp must call this.
-__device__ __forceinline__ bool warp_group_winner(unsigned long long slot_id, unsigned long long key) {
-  const unsigned peers = __match_any_sync(0xffffffffu, slot_id);
-  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-  const unsigned mhi = __reduce_min_sync(peers, hi);
-  const bool c1 = hi == mhi;
-  const unsigned mlo = __reduce_min_sync(peers, c1 ? lo : 0xffffffffu);
-  const bool c2 = c1 && lo == mlo;
-  const unsigned cand = __ballot_sync(0xffffffffu, c2) & peers;
-  return lane_id() == (unsigned)(__ffs(cand) - 1);
-}
-
 __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
   unsigned tot = __reduce_add_sync(0xffffffffu, v);
   if (tot && lane_id() == 0) atomicAdd(reinterpret_cast<unsigned long long*>(diag + slot), (unsigned long long)tot);
 }
 
+// ---------------------------------------------------------------- exact tie protocol (rare path)
+// Called by a point whose atomicMax met a slot holder with the SAME top-32 key bits.  `Key(idx1)` re-derives
+// the exact 64-bit key of point idx1 from its coordinates.  On return the slot holds a point that is exactly
+// <= this point and the one it may have displaced (smaller key, then smaller index), or a point from a
+// strictly better top-32 class.  Every tied point runs this, so the final holder is the exact arg-min.
+template <typename KeyFn>
+__device__ __noinline__ void tie_protocol(u64* slot, uint32_t top_inv, uint32_t me1, u64 my_key, u64 old_word, KeyFn key_of) {
+  uint32_t cand1 = me1;
+  u64 cand_key = my_key;
+  {
+    uint32_t o1 = word_idx1(old_word);
+    u64 ok = key_of(o1);
+    if (ok < cand_key || (ok == cand_key && o1 < cand1)) { cand1 = o1; cand_key = ok; }
+  }
+  u64 mine = pack_word(top_inv, me1);
+  u64 cur = old_word > mine ? old_word : mine;     // content right after this point's atomicMax
+  for (;;) {
+    if (word_top(cur) != top_inv) break;           // a strictly better class took the slot
+    uint32_t h1 = word_idx1(cur);
+    if (h1 == cand1) break;                        // the slot holds the candidate
+    u64 hk = key_of(h1);
+    bool cand_better = cand_key < hk || (cand_key == hk && cand1 < h1);
+    if (!cand_better) break;                       // holder is exactly better: already in place
+    u64 prev = atomicCAS(slot, cur, pack_word(top_inv, cand1));
+    if (prev == cur) break;
+    cur = prev;
+  }
+}
+
 // ---------------------------------------------------------------- K1: point pass
 template <typename T, bool DO_VOX, bool DO_RANGE>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-             bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, uint32_t* __restrict__ pixtab,
+             bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
              int64_t* __restrict__ diag) {
   __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * kStageWords];
   const unsigned lane = lane_id();
@@ -305,62 +370,46 @@ k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const i
     if (DO_VOX) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        VoxKey v; v.in = false; v.bit = 0;
-        if (w.valid[k]) v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
-        n_in += v.in;
-        // one atomicOr per distinct bitmap word in the warp
-        unsigned long long wid = v.in ? ((unsigned long long)fr[k] << 32) | (v.bit >> 5) : (0xffffffff00000000ull | lane);
-        unsigned peers = __match_any_sync(0xffffffffu, wid);
-        unsigned m = v.in ? (1u << (v.bit & 31)) : 0u;
-        unsigned m_all = __reduce_or_sync(peers, m);
-        if (v.in && lane == (unsigned)(__ffs(peers) - 1)) atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), m_all);
+        if (w.valid[k]) {
+          VoxKey v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
+          if (v.in) {
+            ++n_in;
+            atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), 1u << (v.bit & 31));   // RED, no return value
+          }
+        }
       }
     }
     if (DO_RANGE) {
-      double depth[4];
-      uint32_t* slot[4];
-      uint32_t me1[4], old[4];
+      u64* slot[4];
+      u64 mine[4], key[4], old[4];
       bool act[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        act[k] = false; depth[k] = 0.0; slot[k] = pixtab; me1[k] = 0;
-        unsigned long long sid = 0xffffffff00000000ull | lane;
+        act[k] = false; slot[k] = pixtab; mine[k] = 0; key[k] = 0;
         if (w.valid[k]) {
           PixKey pk = pix_of(w.x[k], w.y[k], w.z[k], r);
           if (!pk.ok) { ++n_drop; }
           else {
             n_nw += pk.near_w; n_nh += pk.near_h;
-            act[k] = true; depth[k] = pk.depth;
-            size_t so = (size_t)fr[k] * r.H * r.W + pk.pix;
-            slot[k] = pixtab + so;
-            sid = (unsigned long long)so;
-            me1[k] = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
+            act[k] = true;
+            key[k] = (u64)__double_as_longlong(pk.depth);     // depth > 0: the bit pattern orders like the value
+            slot[k] = pixtab + (size_t)fr[k] * r.H * r.W + pk.pix;
+            mine[k] = pack_word(key_top_inv(key[k]), (uint32_t)(base + 32 * k + lane - fb[k]) + 1u);
           }
         }
-        // nearest point of each pixel inside the warp (depth > 0: its bit pattern orders like the value)
-        bool win = warp_group_winner(sid, (unsigned long long)__double_as_longlong(depth[k]));
-        act[k] = act[k] && win;
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicCAS(slot[k], 0u, me1[k]) : 0u;
-      while (old[0] | old[1] | old[2] | old[3]) {     // occupied slots: compare against the current winner's key
-        double dq[4];
+      for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          dq[k] = 0.0;
-          if (old[k]) {
-            const T* qp = xyz + 3 * (fb[k] + (int64_t)(old[k] - 1u));
+      for (int k = 0; k < 4; ++k) {
+        if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k])) {   // same top-32 class: exact protocol
+          const T* fx = xyz + 3 * fb[k];
+          auto key_of = [&](uint32_t q1) -> u64 {
+            const T* qp = fx + 3 * (int64_t)(q1 - 1u);
             double a, b, c;
-            dq[k] = range_depth_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (old[k]) {
-            bool better = (depth[k] < dq[k]) || (depth[k] == dq[k] && me1[k] < old[k]);
-            if (!better) old[k] = 0u;
-            else { uint32_t prev = atomicCAS(slot[k], old[k], me1[k]); old[k] = (prev == old[k]) ? 0u : prev; }
-          }
+            return (u64)__double_as_longlong(range_depth_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c));
+          };
+          tie_protocol(slot[k], word_top(mine[k]), word_idx1(mine[k]), key[k], old[k], key_of);
         }
       }
     }
@@ -443,17 +492,11 @@ __device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_
 }
 
 // ---------------------------------------------------------------- K3: voxel resolve
-__device__ __forceinline__ bool vox_better(bool my_notroad, double my_dis, uint32_t my1, bool o_notroad, double o_dis,
-                                           uint32_t o1) {
-  if (my_notroad != o_notroad) return !my_notroad;                 // any roadline point wins (:217)
-  return (my_dis < o_dis) || (my_dis == o_dis && my1 < o1);        // argmin, first minimum (:217)
-}
-
 template <typename T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 3)
 k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
                 bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-                uint32_t* __restrict__ win) {
+                u64* __restrict__ vslot) {
   __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * kStageWords];
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
@@ -463,74 +506,57 @@ k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, cons
   load_warp_points<T>(xyz, sem, base, P, vec_ok, stage_all + warp * kStageWords, w);
   int fr[4]; int64_t fb[4];
   warp_frames(off, F, base, P, fr, fb);
-  double dis[4];
-  uint32_t bit[4], me1[4], old[4];
-  uint32_t* slot[4];
-  bool act[4], notroad[4];
+  u64* slot[4];
+  u64 mine[4], key[4], old[4];
+  uint32_t bit[4];
+  bool act[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    act[k] = false; dis[k] = 0.0; bit[k] = 0; me1[k] = 0; slot[k] = win; notroad[k] = true;
-    unsigned long long sid = 0xffffffff00000000ull | lane;
+    act[k] = false; slot[k] = vslot; mine[k] = 0; key[k] = 0; bit[k] = 0;
     if (w.valid[k]) {
       VoxKey v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
-      act[k] = v.in; dis[k] = v.dis; bit[k] = v.bit;
-      me1[k] = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
-      notroad[k] = (int)w.sem[k] != g.road;
-      if (v.in) sid = ((unsigned long long)fr[k] << 32) | v.bit;
-    }
-    // best point of each voxel inside the warp: key = (not roadline, dis); dis >= 0 so bit 63 is free
-    unsigned long long key = (unsigned long long)__double_as_longlong(dis[k]) | (notroad[k] ? (1ull << 63) : 0ull);
-    bool winr = warp_group_winner(sid, key);
-    act[k] = act[k] && winr;
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {   // rank lookups of the surviving points are independent loads
-    if (act[k]) {
-      uint32_t rank = rank_of(bitmap + (size_t)fr[k] * g.gw, prefix + (size_t)fr[k] * (g.gw / 4), bit[k]);
-      slot[k] = win + fb[k] + rank;
+      act[k] = v.in; bit[k] = v.bit;
+      key[k] = vox_key(v.dis, (int)w.sem[k] != g.road);
+      mine[k] = pack_word(key_top_inv(key[k]), (uint32_t)(base + 32 * k + lane - fb[k]) + 1u);
     }
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicCAS(slot[k], 0u, me1[k]) : 0u;
-  while (old[0] | old[1] | old[2] | old[3]) {
-    double od[4]; bool onr[4];
+  for (int k = 0; k < 4; ++k) {   // rank lookups of the 4 points are independent loads
+    if (act[k]) slot[k] = vslot + fb[k] + rank_of(bitmap + (size_t)fr[k] * g.gw, prefix + (size_t)fr[k] * (g.gw / 4), bit[k]);
+  }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      od[k] = 0.0; onr[k] = true;
-      if (old[k]) {
-        int64_t qi = fb[k] + (int64_t)(old[k] - 1u);
-        const T* qp = xyz + 3 * qi;
+  for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k])) {
+      const T* fx = xyz + 3 * fb[k];
+      const uint8_t* fs = sem + fb[k];
+      auto key_of = [&](uint32_t q1) -> u64 {
+        const T* qp = fx + 3 * (int64_t)(q1 - 1u);
         VoxKey o = vox_of((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
-        od[k] = o.dis;
-        onr[k] = (int)__ldg(sem + qi) != g.road;
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (old[k]) {
-        if (!vox_better(notroad[k], dis[k], me1[k], onr[k], od[k], old[k])) old[k] = 0u;
-        else { uint32_t prev = atomicCAS(slot[k], old[k], me1[k]); old[k] = (prev == old[k]) ? 0u : prev; }
-      }
+        return vox_key(o.dis, (int)__ldg(fs + (q1 - 1u)) != g.road);
+      };
+      tie_protocol(slot[k], word_top(mine[k]), word_idx1(mine[k]), key[k], old[k], key_of);
     }
   }
 }
 
-// ---------------------------------------------------------------- K3b: slot labels
-// One thread per winner slot: replace the winner's point index by (0x80000000 | its raw label), so that the
-// emit kernels need a single gather per occupied voxel.  Slots that were never claimed stay 0.
-constexpr uint32_t kLabelTag = 0x80000000u;
+// ---------------------------------------------------------------- K4: slot labels
+// One thread per winner slot: replace the packed winner by (kLabelTag | raw label of the winning point) so that
+// the emit kernels need a single gather per occupied voxel.  Slots that were never claimed stay 0.
+constexpr u64 kLabelTag = 0xffffffff00000000ull;
 __global__ void __launch_bounds__(kBlock)
-k_slot_labels(uint32_t* __restrict__ win, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P) {
+k_slot_labels(u64* __restrict__ vslot, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P) {
   int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (s >= P) return;
-  uint32_t w1 = win[s];
-  if (!w1) return;
+  u64 wv = vslot[s];
+  if (!wv) return;
   int f = find_frame(off, F, s);
-  uint32_t lab = __ldg(sem + __ldg(off + f) + (int64_t)(w1 - 1u));
-  win[s] = kLabelTag | lab;
+  uint32_t lab = __ldg(sem + __ldg(off + f) + (int64_t)(word_idx1(wv) - 1u));
+  vslot[s] = kLabelTag | lab;
 }
 
-// ---------------------------------------------------------------- K4: emit
+// ---------------------------------------------------------------- K5: emit
 // Shared by the emit kernels: lane L owns bitmap word (warp_word0 + L); returns the word and the rank of
 // its first bit.  Ranks of the 4 words of a chunk are built with shuffles, so no lane ever re-reads a
 // word that its owner may already have cleared.
@@ -539,8 +565,8 @@ __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap
                                                    uint32_t* rank_o) {
   uint32_t word = valid ? bitmap[word_global] : 0u;
   uint32_t base = valid ? prefix[word_global >> 2] : 0u;
-  // the workspace is shared by calls with different layouts, so the prefix table is cleared as well
-  // (the 4 lanes of a chunk read the entry in the same instruction; its first lane clears it afterwards)
+  // the prefix table is cleared as well (the 4 lanes of a chunk read the entry in the same instruction; its
+  // first lane clears it afterwards)
   if (clean && valid && base && (lane_id() & 3u) == 0u) prefix[word_global >> 2] = 0u;
   uint32_t pc = __popc(word);
   unsigned lane = lane_id();
@@ -552,44 +578,30 @@ __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap
   *word_o = word; *rank_o = rank;
 }
 
-__device__ __forceinline__ uint32_t label_of_slot(uint32_t* __restrict__ win, const uint8_t* __restrict__ remap,
-                                                  int64_t fbeg, uint32_t rank, bool clean) {
-  uint32_t* slot = win + fbeg + rank;
-  uint32_t v = *slot;                       // kLabelTag | raw label (k_slot_labels)
-  if (clean) *slot = 0u;
-  uint32_t lab = v & 0xffu;
-  if (remap) lab = __ldg(remap + lab);
-  return lab;
-}
-
-// 16 voxels (a half word) -> 16 label bytes.  The loads of all set bits are independent (rank + c).
-__device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, uint32_t* __restrict__ win,
-                                             const uint8_t* __restrict__ remap, int64_t fbeg, bool clean) {
-  uint32_t o[4] = {0u, 0u, 0u, 0u};
-  if (bits16) {
-    uint32_t* slots = win + fbeg + rank;
-    uint32_t c = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if ((bits16 >> j) & 1u) {
-        uint32_t v = slots[c];
-        if (clean) slots[c] = 0u;
-        ++c;
-        uint32_t lab = v & 0xffu;
-        if (remap) lab = __ldg(remap + lab);
-        o[j >> 2] |= lab << (8 * (j & 3));
-      }
-    }
+// 16 voxels (a half word) -> 16 label bytes (two 64-bit halves); one gather per set bit
+__device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, u64* __restrict__ vslot_f,
+                                             const uint8_t* __restrict__ remap, bool clean) {
+  u64 lo = 0, hi = 0;
+  u64* sl = vslot_f + rank;
+  while (bits16) {
+    int j = __ffs(bits16) - 1;
+    bits16 &= bits16 - 1;
+    uint32_t lab = (uint32_t)(*sl) & 0xffu;
+    if (clean) *sl = 0ull;
+    ++sl;
+    if (remap) lab = __ldg(remap + lab);
+    u64 add = (u64)lab << (8 * (j & 7));
+    if (j < 8) lo |= add; else hi |= add;
   }
-  return make_uint4(o[0], o[1], o[2], o[3]);
+  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
 // Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as
 // two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).
 __global__ void __launch_bounds__(kBlock)
-k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
-             const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, const uint8_t* __restrict__ remap,
-             uint8_t* __restrict__ dense, GridDev g, int F, bool clean) {
+k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
+             const int64_t* __restrict__ off, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
+             bool clean) {
   int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;     // global word index over [F, gw]
   int64_t total = (int64_t)F * g.gw;
   bool valid = wg < total;
@@ -599,7 +611,7 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint3
   int64_t warp_w0 = wg - lane;                                  // first word of this warp (same frame: gw % 32 == 0)
   if (warp_w0 >= total) return;                                 // whole warp out of range
   int f = (int)(warp_w0 / g.gw);
-  int64_t fbeg = __ldg(off + f);
+  u64* vslot_f = vslot + __ldg(off + f);
   int64_t vox0 = (warp_w0 - (int64_t)f * g.gw) * 32;            // first voxel of the warp inside the frame
   uint8_t* dst = dense + (size_t)f * g.G + vox0;
   bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
@@ -610,7 +622,7 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint3
     uint32_t rk = __shfl_sync(0xffffffffu, rank, src);
     uint32_t bits = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
     if (lane & 1u) rk += __popc(w & 0xffffu);
-    uint4 o = expand_half(bits, rk, win, remap, fbeg, clean);
+    uint4 o = expand_half(bits, rk, vslot_f, remap, clean);
     __syncwarp();   // reconverge after the data-dependent gathers so that the store below is one 512-byte request
     int64_t v = vox0 + ((int64_t)half * 32 + lane) * 16;        // first voxel of this piece
     if (fast) {
@@ -626,9 +638,8 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint3
 
 // Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(frame_offsets[f] + rank)].
 __global__ void __launch_bounds__(kBlock)
-k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint32_t* __restrict__ win,
-              const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, uint16_t* __restrict__ sparse,
-              GridDev g, int F, bool clean) {
+k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
+              const int64_t* __restrict__ off, uint16_t* __restrict__ sparse, GridDev g, int F, bool clean) {
   int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   int64_t total = (int64_t)F * g.gw;
   bool valid = wg < total;
@@ -646,7 +657,9 @@ k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint
     uint32_t x = lin % (uint32_t)g.dx;
     uint32_t yz = lin / (uint32_t)g.dx;
     uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
-    uint32_t lab = label_of_slot(win, nullptr, fbeg, rank, clean);
+    u64* sl = vslot + fbeg + rank;
+    uint32_t lab = (uint32_t)(*sl) & 0xffu;
+    if (clean) *sl = 0ull;
     if (sparse) {
       uint2 row = make_uint2(x | (y << 16), z | (lab << 16));
       *reinterpret_cast<uint2*>(sparse + (size_t)(fbeg + rank) * 4) = row;
@@ -659,9 +672,8 @@ k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, uint
 // Dense grid when the bitmap is in linear-id order (both outputs requested): per-voxel lookup.
 __global__ void __launch_bounds__(kBlock)
 k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-                         const uint32_t* __restrict__ win, const uint8_t* __restrict__ sem,
-                         const int64_t* __restrict__ off, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense,
-                         GridDev g, int F) {
+                         const u64* __restrict__ vslot, const int64_t* __restrict__ off, const uint8_t* __restrict__ remap,
+                         uint8_t* __restrict__ dense, GridDev g, int F) {
   int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (t >= (int64_t)F * g.G) return;
   int f = (int)(t / g.G);
@@ -673,8 +685,7 @@ k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __
   uint32_t lab = 0;
   if ((bm[lin >> 5] >> (lin & 31)) & 1u) {
     uint32_t rank = rank_of(bm, prefix + (size_t)f * (g.gw / 4), lin);
-    int64_t fbeg = __ldg(off + f);
-    lab = win[fbeg + rank] & 0xffu;
+    lab = (uint32_t)vslot[__ldg(off + f) + rank] & 0xffu;
     if (remap) lab = __ldg(remap + lab);
   }
   dense[t] = (uint8_t)lab;
@@ -683,7 +694,7 @@ k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __
 // Range image: one thread per NP pixels (NP = 4: 16-byte stores; NP = 1: generic fallback).
 template <typename T, int NP, int LAYOUT>
 __global__ void __launch_bounds__(kBlock)
-k_emit_range(uint32_t* __restrict__ pixtab, const T* __restrict__ xyz, const uint8_t* __restrict__ sem,
+k_emit_range(u64* __restrict__ pixtab, const T* __restrict__ xyz, const uint8_t* __restrict__ sem,
              const int64_t* __restrict__ off, RangeDev r, int F, float* __restrict__ depth_out, float* __restrict__ xyz_out,
              uint8_t* __restrict__ sem_out, bool clean) {
   const int64_t HW = (int64_t)r.H * r.W;
@@ -693,22 +704,26 @@ k_emit_range(uint32_t* __restrict__ pixtab, const T* __restrict__ xyz, const uin
   int f = (int)(p0 / HW);
   int64_t pin = p0 - (int64_t)f * HW;  // pixel inside the frame
   int64_t fbeg = __ldg(off + f);
-  uint32_t idx[NP];
+  u64 wv[NP];
   if (NP == 4) {
-    uint4 v = *reinterpret_cast<uint4*>(pixtab + p0);
-    idx[0] = v.x; idx[1 % NP] = v.y; idx[2 % NP] = v.z; idx[3 % NP] = v.w;
-    if (clean && (v.x | v.y | v.z | v.w)) *reinterpret_cast<uint4*>(pixtab + p0) = make_uint4(0u, 0u, 0u, 0u);
+    ulonglong2 a = *reinterpret_cast<ulonglong2*>(pixtab + p0);
+    ulonglong2 b = *reinterpret_cast<ulonglong2*>(pixtab + p0 + 2);
+    wv[0] = a.x; wv[1 % NP] = a.y; wv[2 % NP] = b.x; wv[3 % NP] = b.y;
+    if (clean) {
+      if (a.x | a.y) *reinterpret_cast<ulonglong2*>(pixtab + p0) = make_ulonglong2(0ull, 0ull);
+      if (b.x | b.y) *reinterpret_cast<ulonglong2*>(pixtab + p0 + 2) = make_ulonglong2(0ull, 0ull);
+    }
   } else {
-    idx[0] = pixtab[p0];
-    if (clean && idx[0]) pixtab[p0] = 0u;
+    wv[0] = pixtab[p0];
+    if (clean && wv[0]) pixtab[p0] = 0ull;
   }
   float px[NP], py[NP], pz[NP], pd[NP];
   uint32_t ps = 0;
 #pragma unroll
   for (int k = 0; k < NP; ++k) {
     px[k] = py[k] = pz[k] = 0.f; pd[k] = -1.f;                 // :210-212 initial values
-    if (idx[k]) {
-      int64_t qi = fbeg + (int64_t)(idx[k] - 1u);
+    if (wv[k]) {
+      int64_t qi = fbeg + (int64_t)(word_idx1(wv[k]) - 1u);
       T x = __ldg(xyz + 3 * qi), y = __ldg(xyz + 3 * qi + 1), z = __ldg(xyz + 3 * qi + 2);
       double a, b, c;
       pd[k] = (float)range_depth_of(x, y, z, r, &a, &b, &c);   // :217 float32(depth64)
@@ -770,6 +785,7 @@ static int make_range_dev(const MuvoRangeCfg* c, RangeDev* o) {
   if (c->H <= 0 || c->W <= 0 || !(c->fov != 0.0)) return MUVO_E_ARG;
   if ((int64_t)c->H * c->W > ((int64_t)1 << 30)) return MUVO_E_SHAPE;
   o->H = c->H; o->W = c->W; o->fda = c->fov_down_abs; o->fov = c->fov;
+  o->inv_pi_f = (float)(1.0 / kPi); o->fda_f = (float)c->fov_down_abs; o->inv_fov_f = (float)(1.0 / c->fov);
   for (int k = 0; k < 3; ++k) o->L[k] = c->lidar_pos[k];
   return MUVO_OK;
 }
@@ -818,27 +834,27 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     MUVO_AFTER_LAUNCH("k_bitmap_scan", st);
     // K3
     if (P > 0) {
-      k_voxel_resolve<T><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.win);
+      k_voxel_resolve<T><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot);
       MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
-      k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.win, sem, off, F, P);
+      k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.vslot, sem, off, F, P);
       MUVO_AFTER_LAUNCH("k_slot_labels", st);
     }
     // K4 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;
     if (order == ORDER_DENSE) {
       if (dense) {
-        k_emit_dense<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, remap, dense, g, F, true);
+        k_emit_dense<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, remap, dense, g, F, true);
       } else {  // only n_occ requested: clear through the sparse walker without output
-        k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, nullptr, g, F, true);
+        k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, nullptr, g, F, true);
       }
       MUVO_AFTER_LAUNCH(dense ? "k_emit_dense" : "k_emit_sparse", st);
     } else {
       if (dense) {
-        k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off,
+        k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off,
                                                                                  remap, dense, g, F);
         MUVO_AFTER_LAUNCH("k_emit_dense_from_linear", st);
       }
-      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.win, sem, off, sparse, g, F, true);
+      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, sparse, g, F, true);
       MUVO_AFTER_LAUNCH("k_emit_sparse", st);
     }
   }

@@ -127,7 +127,9 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
         nbytes = C.c_size_t(0)
         _lib.check(lib.muvo_points_workspace_bytes(P, F, C.byref(g_c) if g_c else None, C.byref(r_c) if r_c else None,
                                                    C.byref(nbytes)), "muvo_points_workspace_bytes")
-        ws = _ws.get(nbytes.value, dev, stream)
+        sig = (F, tuple(int(v) for v in grid.voxel_size) if grid is not None else None,
+               (int(range_spec.H), int(range_spec.W)) if range_spec is not None else None)
+        ws = _ws.get(nbytes.value, dev, stream, sig)
         diag = torch.zeros(_lib.DIAG_COUNT, dtype=torch.int64, device=dev) if want_diag else None
         dense_t = sparse_t = nocc_t = depth_t = xyz_t = sem_t = None
         if grid is not None:

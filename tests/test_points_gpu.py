@@ -256,3 +256,45 @@ def test_full_size_batch_properties(lib):
         d0, x0, s0 = O.range_projection(p, s, lidar_position=LIDAR)
         assert np.array_equal(xyzd[f].cpu().numpy(), O.pack_range_view(d0, x0))
         assert np.array_equal(rsem[f].cpu().numpy(), s0)
+
+
+# ------------------------------------------------------------------ near-ties: the packed atomicMax + exact tie protocol
+def test_voxel_near_ties_resolve_exactly(lib):
+    """Thousands of points whose |p mod res|^2 agree in the top 32 key bits (and many exact ties) in a handful
+    of voxels: the fast packed order is ambiguous there, the tie protocol must reproduce the exact arg-min."""
+    rng = np.random.default_rng(21)
+    n = 6000
+    base = np.float32([0.25, 0.25, 0.25]) + rng.integers(0, 3, (n, 1)).astype(np.float32) * np.float32(0.5)
+    ulp = np.spacing(np.float32(0.25))
+    pts = (base + rng.integers(-4, 5, (n, 3)).astype(np.float32) * ulp).astype(np.float32)
+    sem = rng.integers(0, 23, n).astype(np.uint8)
+    for with_road in (False, True):
+        s = sem.copy()
+        if not with_road:
+            s[s == 6] = 7
+        v0, l0 = O.voxel_filter_fast(pts, s, *GRID)
+        v, l = muvo_b200.voxel_filter(pts, s, *GRID)
+        assert len(v0) == 3 and np.array_equal(v, v0) and np.array_equal(l, l0)
+    # all points identical: pure index tie-break under heavy contention
+    same = np.repeat(np.float32([[3.3, -7.1, 0.2]]), 4000, 0)
+    s = (np.arange(4000) % 5 + 1).astype(np.uint8)
+    v, l = muvo_b200.voxel_filter(same, s, *GRID)
+    assert l.tolist() == [1]
+
+
+def test_range_near_ties_resolve_exactly(lib):
+    rng = np.random.default_rng(22)
+    n = 5000
+    ulp = np.spacing(np.float32(11.0))
+    pts = np.zeros((n, 3), np.float32)
+    pts[:, 0] = np.float32(11.0) + rng.integers(-6, 7, n).astype(np.float32) * ulp
+    pts[:, 2] = 2.0
+    # a second bundle in another pixel, plus exact duplicates
+    pts[n // 2:, 1] = np.float32(5.0)
+    pts[n // 2:, 0] = np.float32(1.0) + rng.integers(-6, 7, n - n // 2).astype(np.float32) * np.spacing(np.float32(1.0))
+    sem = rng.integers(1, 23, n).astype(np.uint8)
+    pc = PointCloud(64, 1024, -30, 10, LIDAR)
+    d, x, s = pc.do_range_projection(pts, sem)
+    d0, x0, s0 = O.range_projection(pts, sem, lidar_position=LIDAR)
+    assert np.array_equal(d, d0) and np.array_equal(x, x0) and np.array_equal(s, s0)
+    assert (d >= 0).sum() <= 4
