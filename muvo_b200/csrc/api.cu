@@ -14,7 +14,7 @@ int muvo_profile_begin(void* stream) {
   muvo::Profile& p = muvo::profile_state();
   p.n = 0;
   p.on = true;
-  muvo::prof_mark("begin", (cudaStream_t)stream);
+  muvo::prof_mark("<begin>", (cudaStream_t)stream);
   return p.n == 1 ? MUVO_OK : MUVO_E_ARG;
 }
 
@@ -25,14 +25,17 @@ int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char
   if (!n_out_h) return MUVO_E_NULL;
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  int n = p.n - 1;
-  if (n > capacity) n = capacity;
-  for (int i = 0; i < n; ++i) {
+  // marks whose name starts with '<' are baselines (recorded right before the first launch of an entry point):
+  // they are not reported, but the next kernel's time is measured from them, so host-side gaps are excluded.
+  int n = 0;
+  for (int i = 1; i < p.n && n < capacity; ++i) {
+    if (p.name[i][0] == '<') continue;
     float ms = 0.f;
-    e = cudaEventElapsedTime(&ms, p.ev[i], p.ev[i + 1]);
+    e = cudaEventElapsedTime(&ms, p.ev[i - 1], p.ev[i]);
     if (e != cudaSuccess) return (int)e;
-    if (ms_out_h) ms_out_h[i] = ms;
-    if (names_out_h) names_out_h[i] = p.name[i + 1];
+    if (ms_out_h) ms_out_h[n] = ms;
+    if (names_out_h) names_out_h[n] = p.name[i];
+    ++n;
   }
   *n_out_h = n;
   return MUVO_OK;

@@ -71,13 +71,20 @@ k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells,
   const int b = (int)(wc_global / n_wc), wc = (int)(wc_global % n_wc);
   const int32_t* cp = cell + (size_t)b * n_pts;
   const int64_t p0 = (int64_t)wc * kWarpChunk;
-  for (int r = 0; r < kWarpChunk / 32; ++r) {
-    int64_t p = p0 + r * 32 + lane;
-    int c = (p < n_pts) ? __ldg(cp + p) : -1;
-    if (c >= n_cells) c = -1;
-    unsigned m = __match_any_sync(0xffffffffu, c);
-    if (c >= 0 && lane == (__ffs(m) - 1)) h[c] += __popc(m);
-    __syncwarp();
+  for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
+    int cc[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {           // 8 independent loads in flight
+      int64_t p = p0 + (r0 + u) * 32 + lane;
+      int c = (p < n_pts) ? __ldg(cp + p) : -1;
+      cc[u] = (c >= n_cells) ? -1 : c;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      unsigned m = __match_any_sync(0xffffffffu, cc[u]);
+      if (cc[u] >= 0 && lane == (__ffs(m) - 1)) h[cc[u]] += __popc(m);
+      __syncwarp();
+    }
   }
   uint32_t* dst = chunk_base + ((size_t)b * n_wc + wc) * n_cells;
   for (int i = lane; i < n_cells; i += 32) dst[i] = h[i];
@@ -90,7 +97,15 @@ __global__ void k_cell_scan(uint32_t* __restrict__ chunk_base, uint32_t* __restr
   int b = (int)(t / n_cells), c = (int)(t % n_cells);
   uint32_t* col = chunk_base + (size_t)b * n_wc * n_cells + c;
   uint32_t run = 0;
-  for (int k = 0; k < n_wc; ++k) { uint32_t v = col[(size_t)k * n_cells]; col[(size_t)k * n_cells] = run; run += v; }
+  int k = 0;
+  for (; k + 8 <= n_wc; k += 8) {           // 8 independent loads, then the dependent stores
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(k + u) * n_cells];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { col[(size_t)(k + u) * n_cells] = run; run += v[u]; }
+  }
+  for (; k < n_wc; ++k) { uint32_t v = col[(size_t)k * n_cells]; col[(size_t)k * n_cells] = run; run += v; }
   cell_total[t] = run;
 }
 
@@ -145,63 +160,80 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
   int32_t* out = sorted + (size_t)b * n_pts;
   const int64_t p0 = (int64_t)wc * kWarpChunk;
-  for (int r = 0; r < kWarpChunk / 32; ++r) {
-    int64_t p = p0 + r * 32 + lane;
-    int c = (p < n_pts) ? __ldg(cp + p) : -1;
-    if (c >= n_cells) c = -1;
-    unsigned m = __match_any_sync(0xffffffffu, c);
-    if (c >= 0) {
-      uint32_t before = __popc(m & ((1u << lane) - 1u));
-      uint32_t pos = cs[c] + cb[c] + run[c] + before;
-      out[pos] = (int32_t)p;
+  for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
+    int cc[8];
+    uint32_t basepos[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      int64_t p = p0 + (r0 + u) * 32 + lane;
+      int c = (p < n_pts) ? __ldg(cp + p) : -1;
+      cc[u] = (c >= n_cells) ? -1 : c;
     }
-    __syncwarp();
-    if (c >= 0 && lane == (__ffs(m) - 1)) run[c] += __popc(m);
-    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < 8; ++u) basepos[u] = cc[u] >= 0 ? __ldg(cs + cc[u]) + __ldg(cb + cc[u]) : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = cc[u];
+      unsigned m = __match_any_sync(0xffffffffu, c);
+      if (c >= 0) {
+        uint32_t before = __popc(m & ((1u << lane) - 1u));
+        out[basepos[u] + run[c] + before] = (int32_t)(p0 + (r0 + u) * 32 + lane);
+      }
+      __syncwarp();
+      if (c >= 0 && lane == (__ffs(m) - 1)) run[c] += __popc(m);
+      __syncwarp();
+    }
   }
 }
 
-// P (point-major, x_stride_p == 1): one warp per (frame, cell); lanes over the cell's points (coalesced
-// along runs of consecutive points), channels in the outer loop with 4 independent loads in flight;
-// lane-strided partial sums + xor tree -> deterministic.
+// P (point-major, x_stride_p == 1): one warp per (frame, cell, group of kPoolCG channels); lanes over the cell's
+// points (coalesced along runs of consecutive points), kPoolU channels per step so that kPoolU independent loads
+// are in flight per lane; lane-strided partial sums + fixed xor tree -> deterministic.
+constexpr int kPoolCG = 96;
+constexpr int kPoolU = 16;
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_pool_point_major(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* __restrict__ cell_start,
-                   const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C, int n_cells, float* __restrict__ out) {
+                   const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C, int n_cells, int n_cg,
+                   float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= (int64_t)B * n_cells) return;
-  const int b = (int)(wid / n_cells), c = (int)(wid % n_cells);
+  if (wid >= (int64_t)B * n_cells * n_cg) return;
+  const int cg = (int)(wid % n_cg);
+  const int64_t bc = wid / n_cg;
+  const int b = (int)(bc / n_cells), c = (int)(bc % n_cells);
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
   const uint32_t s0 = cs[c], s1 = cs[c + 1];
   const int32_t* list = sorted + (size_t)b * n_pts;
   float* o = out + (size_t)b * C * n_cells + c;
   const T* xb = x + (size_t)b * sb;
+  const int ch0 = cg * kPoolCG;
+  const int ch1 = min(C, ch0 + kPoolCG);
   if (s0 == s1) {
-    for (int ch = lane; ch < C; ch += 32) o[(size_t)ch * n_cells] = 0.f;
+    for (int ch = ch0 + lane; ch < ch1; ch += 32) o[(size_t)ch * n_cells] = 0.f;
     return;
   }
-  for (int ch = 0; ch < C; ch += 4) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int ch = ch0; ch < ch1; ch += kPoolU) {
+    float acc[kPoolU];
+#pragma unroll
+    for (int u = 0; u < kPoolU; ++u) acc[u] = 0.f;
     const T* x0 = xb + (size_t)ch * sc;
     for (uint32_t j = s0 + lane; j < s1; j += 32) {
       const int64_t p = list[j];
-      a0 += ldf<T>(x0 + p);
-      if (ch + 1 < C) a1 += ldf<T>(x0 + sc + p);
-      if (ch + 2 < C) a2 += ldf<T>(x0 + 2 * sc + p);
-      if (ch + 3 < C) a3 += ldf<T>(x0 + 3 * sc + p);
+#pragma unroll
+      for (int u = 0; u < kPoolU; ++u)
+        if (ch + u < ch1) acc[u] += ldf<T>(x0 + (size_t)u * sc + p);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, d); a1 += __shfl_xor_sync(0xffffffffu, a1, d);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, d); a3 += __shfl_xor_sync(0xffffffffu, a3, d);
+#pragma unroll
+      for (int u = 0; u < kPoolU; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], d);
     }
-    if (lane == 0) {
-      o[(size_t)ch * n_cells] = a0;
-      if (ch + 1 < C) o[(size_t)(ch + 1) * n_cells] = a1;
-      if (ch + 2 < C) o[(size_t)(ch + 2) * n_cells] = a2;
-      if (ch + 3 < C) o[(size_t)(ch + 3) * n_cells] = a3;
-    }
+    // lane u writes channel ch + u
+    float mine = 0.f;
+#pragma unroll
+    for (int u = 0; u < kPoolU; ++u) mine = (lane == u) ? acc[u] : mine;
+    if (lane < kPoolU && ch + lane < ch1) o[(size_t)(ch + lane) * n_cells] = mine;
   }
 }
 
@@ -405,6 +437,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   }
   const int64_t n_chunks = (int64_t)B * w.n_wc;
   const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
+  prof_mark("<bev_fwd>", st);
   k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base);
   MUVO_AFTER_LAUNCH("k_cell_hist", st);
   k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
@@ -414,9 +447,10 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
   if (sp == 1) {
-    const int64_t warps = (int64_t)B * n_cells;
+    const int n_cg = (int)ceil_div64(C, kPoolCG);
+    const int64_t warps = (int64_t)B * n_cells * n_cg;
     k_pool_point_major<T><<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(x, sb, sc, w.cell_start, w.sorted, B, n_pts, C,
-                                                                                n_cells, out);
+                                                                                n_cells, n_cg, out);
   } else {
     k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,
                                                                              C, n_cells, out);
@@ -428,6 +462,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
 template <typename T>
 static int run_pool_bwd(const float* gout, const int32_t* cell, int B, int64_t n_pts, int C, int n_cells, T* gx, int64_t sb,
                         int64_t sp, int64_t sc, cudaStream_t st) {
+  prof_mark("<bev_bwd>", st);
   if (sp == 1) {
     int64_t n = (int64_t)B * C * ceil_div64(n_pts, 4);
     k_pool_bwd_point_major<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(gout, cell, B, n_pts, C, n_cells, gx, sb, sc);
@@ -513,6 +548,7 @@ int muvo_segment_sum_fwd(const float* x, const int64_t* ranks, int64_t n, int32_
   if (n >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
   SegWs w = carve_seg(ws, n);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+  prof_mark("<seg>", st);
   k_seg_block_count<<<w.nblocks, kScanBlock, 0, st>>>(ranks, n, w.block_cnt);
   MUVO_AFTER_LAUNCH("k_seg_block_count", st);
   k_seg_scan_blocks<<<1, 1024, 0, st>>>(w.block_cnt, w.nblocks, n_seg_out);

@@ -818,6 +818,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 4 == 0);
   const unsigned pblocks = (unsigned)ceil_div64(P, (int64_t)kWarpsPerBlock * kPtsPerWarp);
 
+  prof_mark("<points>", st);
   // K1
   if (P > 0) {
     if (do_vox && do_range)

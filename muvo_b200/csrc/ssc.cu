@@ -278,6 +278,7 @@ static int set_smem(K kern, size_t smem) {
 template <typename PT, int NW>
 static int launch_counts_reg(const void* pred, const uint8_t* target, const uint8_t* ne, const uint8_t* ns, int ignore255,
                              int64_t n, int C, int64_t* out, cudaStream_t st, unsigned grid) {
+  prof_mark("<ssc>", st);
   k_ssc_counts_reg<PT, NW><<<grid, 256, 0, st>>>((const PT*)pred, target, ne, ns, ignore255, n, C, out);
   MUVO_AFTER_LAUNCH("k_ssc_counts_reg", st);
   return MUVO_OK;
@@ -305,6 +306,7 @@ static int launch_counts(const void* pred, const uint8_t* target, const uint8_t*
   int64_t want = ceil_div64(ceil_div64(n, kTileVox) * 32, thr);
   int64_t cap = (int64_t)kNumSMsB200 * per_sm;
   unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  prof_mark("<ssc>", st);
   k_ssc_counts<PT><<<grid, thr, smem, st>>>((const PT*)pred, target, ne, ns, ignore255, n, C, out);
   MUVO_AFTER_LAUNCH("k_ssc_counts", st);
   return MUVO_OK;
@@ -321,6 +323,7 @@ static int launch_logits(const void* logits, const uint8_t* target, int F, int C
   int64_t want = ceil_div64((int64_t)F * S, thr);
   int64_t cap = (int64_t)kNumSMsB200 * per_sm;
   unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+  prof_mark("<ssc>", st);
   k_ssc_from_logits<LT><<<grid, thr, smem, st>>>((const LT*)logits, target, F, C, S, ignore255, out);
   MUVO_AFTER_LAUNCH("k_ssc_from_logits", st);
   return MUVO_OK;

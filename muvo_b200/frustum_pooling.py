@@ -107,23 +107,30 @@ class _BevPool(torch.autograd.Function):
     def backward(ctx, grad_out):
         (cell,) = ctx.saved_tensors
         shape, dtype, n_cells, xstride = ctx.meta
-        B, N, D, H, W, Cc = shape
-        n_pts = N * D * H * W
-        dev = grad_out.device
-        go = grad_out.contiguous().float()
-        # write the gradient in the producer's memory format: if x was a permuted (B,C,D,H,W) view
-        # (mile.py:517-521) so is grad_x, and the permute/mul backward consume it without a copy.
-        if xstride[5] >= xstride[4] and xstride[4] == 1:
-            base = torch.empty((B, Cc, N, D, H, W), dtype=dtype, device=dev)
-            gx = base.permute(0, 2, 3, 4, 5, 1)
-        else:
-            gx = torch.empty(shape, dtype=dtype, device=dev)
-        gv, sb, sp, sc, _ = _strides_bpc(gx)
-        with torch.cuda.device(dev):
-            rc = _lib.load().muvo_bev_pool_bwd(go.data_ptr(), _lib.ptr(cell), B, n_pts, Cc, n_cells, gv.data_ptr(),
-                                               _FLOAT_DTYPES[dtype], sb, sp, sc, _lib.current_stream(dev))
-        _lib.check(rc, "muvo_bev_pool_bwd")
-        return gx, None, None
+        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None
+
+
+def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
+    """``grad_x[b,p,c] = cell[b,p] >= 0 ? grad_out[b,c,cell[b,p]] : 0`` (frustum_pooling.py:52-60 + index backward).
+
+    The gradient is written in the producer's memory format: if x was a permuted ``(B,C,D,H,W)`` view
+    (mile.py:517-521) so is grad_x, and the permute / mul backward consume it without a copy.
+    """
+    B, N, D, H, W, Cc = shape
+    n_pts = N * D * H * W
+    dev = grad_out.device
+    go = grad_out.contiguous().float()
+    if xstride is None or (xstride[5] >= xstride[4] and xstride[4] == 1):
+        base = torch.empty((B, Cc, N, D, H, W), dtype=dtype, device=dev)
+        gx = base.permute(0, 2, 3, 4, 5, 1)
+    else:
+        gx = torch.empty(shape, dtype=dtype, device=dev)
+    gv, sb, sp, sc, _ = _strides_bpc(gx)
+    with torch.cuda.device(dev):
+        rc = _lib.load().muvo_bev_pool_bwd(go.data_ptr(), _lib.ptr(cell), B, n_pts, Cc, n_cells, gv.data_ptr(),
+                                           _FLOAT_DTYPES[dtype], sb, sp, sc, _lib.current_stream(dev))
+    _lib.check(rc, "muvo_bev_pool_bwd")
+    return gx
 
 
 def bev_pool(x: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:

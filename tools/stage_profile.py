@@ -41,7 +41,8 @@ cell = fp.cell_ids(fp.get_geometry(E[:, None, :3, :3], E[:, None, :3, 3:], K[:, 
 out = bev_pool(x, cell, 2304)
 g = torch.ones_like(out)
 show("bev_fwd", lambda: bev_pool(x.detach(), cell, 2304))
-show("bev_bwd", lambda: torch.autograd.grad(out, x, g, retain_graph=True))
+from muvo_b200.frustum_pooling import bev_pool_backward  # noqa: E402
+show("bev_bwd", lambda: bev_pool_backward(g, cell, tuple(x.shape), x.dtype, 2304, x.stride()))
 xc = x.detach().contiguous()
 show("bev_fwd_cl", lambda: bev_pool(xc, cell, 2304))
 for Cn in (2, 9, 23):
