@@ -41,6 +41,7 @@ struct BevWs {
   uint32_t* cell_total = nullptr;   // [B, n_cells]
   uint32_t* cell_start = nullptr;   // [B, n_cells + 1]
   int32_t* sorted = nullptr;        // [B, n_pts]  point ids grouped by cell, ascending inside a cell
+  int32_t* pos_of = nullptr;        // [B, n_pts]  inverse: position of point p in `sorted`, -1 = dropped
   int n_wc = 0;
   size_t bytes = 0;
 };
@@ -54,6 +55,7 @@ static BevWs carve_bev(void* base, int B, int64_t n_pts, int n_cells) {
   w.cell_total = (uint32_t*)(b + o); o = align_up(o + (size_t)B * n_cells * 4, 256);
   w.cell_start = (uint32_t*)(b + o); o = align_up(o + (size_t)B * (n_cells + 1) * 4, 256);
   w.sorted = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
+  w.pos_of = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
   w.bytes = o;
   return w;
 }
@@ -146,7 +148,8 @@ k_cell_starts(const uint32_t* __restrict__ cell_total, uint32_t* __restrict__ ce
 // S4: stable placement.
 __global__ void __launch_bounds__(kSortWarps * 32)
 k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc,
-             const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ sorted) {
+             const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ sorted,
+             int32_t* __restrict__ pos_of) {
   extern __shared__ uint32_t sm[];                 // running count per cell inside this warp-chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t wc_global = (int64_t)blockIdx.x * kSortWarps + warp;
@@ -159,6 +162,7 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
   const uint32_t* cb = chunk_base + ((size_t)b * n_wc + wc) * n_cells;
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
   int32_t* out = sorted + (size_t)b * n_pts;
+  int32_t* inv = pos_of + (size_t)b * n_pts;
   const int64_t p0 = (int64_t)wc * kWarpChunk;
   for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
     int cc[8];
@@ -175,9 +179,13 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
     for (int u = 0; u < 8; ++u) {
       const int c = cc[u];
       unsigned m = __match_any_sync(0xffffffffu, c);
+      const int64_t pp = p0 + (r0 + u) * 32 + lane;
       if (c >= 0) {
-        uint32_t before = __popc(m & ((1u << lane) - 1u));
-        out[basepos[u] + run[c] + before] = (int32_t)(p0 + (r0 + u) * 32 + lane);
+        uint32_t pos = basepos[u] + run[c] + __popc(m & ((1u << lane) - 1u));
+        out[pos] = (int32_t)pp;
+        inv[pp] = (int32_t)pos;
+      } else if (pp < n_pts) {
+        inv[pp] = -1;
       }
       __syncwarp();
       if (c >= 0 && lane == (__ffs(m) - 1)) run[c] += __popc(m);
@@ -186,54 +194,80 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
   }
 }
 
-// P (point-major, x_stride_p == 1): one warp per (frame, cell, group of kPoolCG channels); lanes over the cell's
-// points (coalesced along runs of consecutive points), kPoolU channels per step so that kPoolU independent loads
-// are in flight per lane; lane-strided partial sums + fixed xor tree -> deterministic.
-constexpr int kPoolCG = 96;
-constexpr int kPoolU = 16;
+// P (point-major, x_stride_p == 1): one CTA per (frame, channel).  The channel's row x[b, c, :] is streamed in
+// ADDRESS ORDER (HBM friendly; only sectors that hold a kept point are requested), every kept value is dropped
+// into shared memory at its position in the cell-sorted order, and each cell's now contiguous segment is summed
+// (lane-strided partials + fixed xor tree -> deterministic).  Frames with more kept points than fit in shared
+// memory are processed in windows of whole cells.
+constexpr int kRowThreads = 1024;
+constexpr int kRowCap = 54 * 1024;   // floats of staging (216 KB)
 template <typename T>
-__global__ void __launch_bounds__(256)
-k_pool_point_major(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* __restrict__ cell_start,
-                   const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C, int n_cells, int n_cg,
-                   float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (wid >= (int64_t)B * n_cells * n_cg) return;
-  const int cg = (int)(wid % n_cg);
-  const int64_t bc = wid / n_cg;
-  const int b = (int)(bc / n_cells), c = (int)(bc % n_cells);
+__global__ void __launch_bounds__(kRowThreads, 1)
+k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ pos_of,
+            const uint32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C,
+            int n_cells, float* __restrict__ out) {
+  extern __shared__ float buf[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x / C, c = blockIdx.x % C;
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
-  const uint32_t s0 = cs[c], s1 = cs[c + 1];
-  const int32_t* list = sorted + (size_t)b * n_pts;
-  float* o = out + (size_t)b * C * n_cells + c;
-  const T* xb = x + (size_t)b * sb;
-  const int ch0 = cg * kPoolCG;
-  const int ch1 = min(C, ch0 + kPoolCG);
-  if (s0 == s1) {
-    for (int ch = ch0 + lane; ch < ch1; ch += 32) o[(size_t)ch * n_cells] = 0.f;
-    return;
-  }
-  for (int ch = ch0; ch < ch1; ch += kPoolU) {
-    float acc[kPoolU];
+  const int32_t* pos = pos_of + (size_t)b * n_pts;
+  const T* xr = x + (size_t)b * sb + (size_t)c * sc;
+  float* o = out + ((size_t)b * C + c) * n_cells;
+  int c0 = 0;
+  while (c0 < n_cells) {
+    const uint32_t w0 = cs[c0];
+    int lo = c0 + 1, hi = n_cells;            // largest c1 in [c0+1, n_cells] with cs[c1] - w0 <= kRowCap
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cs[mid] - w0 <= (uint32_t)kRowCap) lo = mid; else hi = mid - 1; }
+    const int c1 = lo;
+    const uint32_t w1 = cs[c1];
+    if (w1 - w0 <= (uint32_t)kRowCap) {
+      if (w1 > w0) {
+        const int iw0 = (int)w0, iw1 = (int)w1;
+        for (int64_t p0 = 0; p0 < n_pts; p0 += (int64_t)kRowThreads * 8) {
+          int d[8];
 #pragma unroll
-    for (int u = 0; u < kPoolU; ++u) acc[u] = 0.f;
-    const T* x0 = xb + (size_t)ch * sc;
-    for (uint32_t j = s0 + lane; j < s1; j += 32) {
-      const int64_t p = list[j];
+          for (int u = 0; u < 8; ++u) {          // coalesced positions, 8 in flight
+            int64_t p = p0 + (int64_t)u * kRowThreads + tid;
+            d[u] = (p < n_pts) ? __ldg(pos + p) : -1;
+          }
+          float v[8];
 #pragma unroll
-      for (int u = 0; u < kPoolU; ++u)
-        if (ch + u < ch1) acc[u] += ldf<T>(x0 + (size_t)u * sc + p);
+          for (int u = 0; u < 8; ++u) {          // predicated, address-ordered feature loads
+            int64_t p = p0 + (int64_t)u * kRowThreads + tid;
+            v[u] = (d[u] >= iw0 && d[u] < iw1) ? ldf<T>(xr + p) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            if (d[u] >= iw0 && d[u] < iw1) buf[d[u] - iw0] = v[u];
+        }
+      }
+      __syncthreads();
+      // 32 consecutive cells per warp step -> one coalesced 128-byte store
+      for (int cb = c0 + warp * 32; cb < c1; cb += (kRowThreads / 32) * 32) {
+        float mine = 0.f;
+        for (int i = 0; i < 32 && cb + i < c1; ++i) {
+          const uint32_t s0 = cs[cb + i] - w0, s1 = cs[cb + i + 1] - w0;
+          float acc = 0.f;
+          for (uint32_t j = s0 + lane; j < s1; j += 32) acc += buf[j];
+#pragma unroll
+          for (int dd = 16; dd; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
+          if (lane == i) mine = acc;
+        }
+        if (cb + lane < c1) o[cb + lane] = mine;
+      }
+      __syncthreads();
+    } else {
+      // a single cell larger than the staging buffer: gather it straight from global memory (rare)
+      if (warp == 0) {
+        const int32_t* list = sorted + (size_t)b * n_pts;
+        float acc = 0.f;
+        for (uint32_t j = w0 + lane; j < w1; j += 32) acc += ldf<T>(xr + list[j]);
+#pragma unroll
+        for (int dd = 16; dd; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
+        if (lane == 0) o[c0] = acc;
+      }
     }
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-#pragma unroll
-      for (int u = 0; u < kPoolU; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], d);
-    }
-    // lane u writes channel ch + u
-    float mine = 0.f;
-#pragma unroll
-    for (int u = 0; u < kPoolU; ++u) mine = (lane == u) ? acc[u] : mine;
-    if (lane < kPoolU && ch + lane < ch1) o[(size_t)(ch + lane) * n_cells] = mine;
+    c0 = c1;
   }
 }
 
@@ -444,18 +478,20 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   MUVO_AFTER_LAUNCH("k_cell_scan", st);
   k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells);
   MUVO_AFTER_LAUNCH("k_cell_starts", st);
-  k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted);
+  k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
+                                                             w.pos_of);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
   if (sp == 1) {
-    const int n_cg = (int)ceil_div64(C, kPoolCG);
-    const int64_t warps = (int64_t)B * n_cells * n_cg;
-    k_pool_point_major<T><<<(unsigned)ceil_div64(warps * 32, 256), 256, 0, st>>>(x, sb, sc, w.cell_start, w.sorted, B, n_pts, C,
-                                                                                n_cells, n_cg, out);
+    const size_t rsmem = (size_t)kRowCap * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+    if (e != cudaSuccess) return (int)e;
+    k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.pos_of, w.cell_start, w.sorted, B, n_pts,
+                                                                         C, n_cells, out);
   } else {
     k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,
                                                                              C, n_cells, out);
   }
-  MUVO_AFTER_LAUNCH(sp == 1 ? "k_pool_point_major" : "k_pool_channel_major", st);
+  MUVO_AFTER_LAUNCH(sp == 1 ? "k_pool_rows" : "k_pool_channel_major", st);
   return MUVO_OK;
 }
 

@@ -126,55 +126,48 @@ __global__ void k_ssc_counts(const PT* __restrict__ pred, const uint8_t* __restr
   flush_counts(cnt, C, c, out);
 }
 
-// ---- register path (C <= 16): tp/fp/fn live in 64-bit registers as packed 16-bit fields (NW words of 4 classes
-// per family), so a voxel costs a shift and a few predicated adds -- no shared-memory read-modify-write chain.
-template <int NW> struct Packed {
-  unsigned long long tp[NW], fp[NW], fn[NW];
-  __device__ __forceinline__ void clear() {
-#pragma unroll
-    for (int i = 0; i < NW; ++i) tp[i] = fp[i] = fn[i] = 0ull;
-  }
-};
-template <int NW>
-__device__ __forceinline__ void bump(unsigned long long* a, unsigned j, bool on) {
-  const unsigned long long add = on ? (1ull << (16u * (j & 3u))) : 0ull;
-  const unsigned w = j >> 2;
-#pragma unroll
-  for (int i = 0; i < NW; ++i) a[i] += (w == (unsigned)i) ? add : 0ull;
-}
-template <int NW>
-__device__ __forceinline__ void tally_reg(long long p, uint32_t t, bool sem_valid, bool comp_valid, int C, Packed<NW>& k,
-                                          Comp& c) {
+// ---- warp-vote path (C <= 32): the warp's 32 voxels of a step are classified together -- per class j,
+// ballot(t == j) and ballot(p == j) give tp/fp/fn of that class with three popcounts, and lane j keeps the
+// counters of class j.  Cost ~ (13 C + 20) warp instructions per 32 voxels instead of ~60 per voxel.
+struct VoteAcc { unsigned tp, fp, fn; unsigned ctp, cfp, cfn; };
+
+__device__ __forceinline__ void vote_step(long long p, uint32_t t, bool sem_valid, bool comp_valid, int C, unsigned lane,
+                                          VoteAcc& a) {
   const bool is255 = (t == 255u);
-  if (is255) { p = 0; t = 0; }
-  const bool bt = t > 0u, bp = p > 0;
-  c.tp += (comp_valid && bt && bp); c.fp += (comp_valid && !bt && bp); c.fn += (comp_valid && bt && !bp);
-  const bool eq = (p == (long long)t);
-  const bool t_in = (int)t < C, p_in = (p >= 0 && p < C);
-  bump<NW>(k.tp, t, sem_valid && eq && t_in);
-  bump<NW>(k.fp, (unsigned)p, sem_valid && !eq && p_in);
-  bump<NW>(k.fn, t, sem_valid && !eq && t_in);
+  if (is255) { p = 0; t = 0; }                                   // :150-151, :184-185
+  const int pc = (p >= 0 && p < (long long)C) ? (int)p : -1;      // class of the prediction, -1 = none
+  const int tc = ((int)t < C) ? (int)t : -2;                      // class of the target, -2 = none
+  const unsigned vs = __ballot_sync(0xffffffffu, sem_valid);
+  const unsigned vc = __ballot_sync(0xffffffffu, comp_valid);
+  const unsigned bt = __ballot_sync(0xffffffffu, t > 0u) & vc;    // :157-160
+  const unsigned bp = __ballot_sync(0xffffffffu, p > 0) & vc;
+  a.ctp += __popc(bt & bp); a.cfp += __popc(~bt & bp); a.cfn += __popc(bt & ~bp);   // :170-172 (lane-uniform)
+  for (int j = 0; j < C; ++j) {                                   // :207-214
+    const unsigned mt = __ballot_sync(0xffffffffu, tc == j) & vs;
+    const unsigned mp = __ballot_sync(0xffffffffu, pc == j) & vs;
+    if (lane == (unsigned)j) { a.tp += __popc(mt & mp); a.fp += __popc(~mt & mp & vs); a.fn += __popc(mt & ~mp); }
+  }
 }
 
-template <typename PT, int NW>
+template <typename PT>
 __global__ void __launch_bounds__(256)
-k_ssc_counts_reg(const PT* __restrict__ pred, const uint8_t* __restrict__ target, const uint8_t* __restrict__ nonempty,
-                 const uint8_t* __restrict__ nonsurface, int ignore255, int64_t n, int C, int64_t* __restrict__ out) {
-  __shared__ unsigned long long red[3 * 4 * NW + 3];
-  const int tid = threadIdx.x, lane = tid & 31;
-  for (int i = tid; i < 3 * 4 * NW + 3; i += blockDim.x) red[i] = 0ull;
+k_ssc_counts_vote(const PT* __restrict__ pred, const uint8_t* __restrict__ target, const uint8_t* __restrict__ nonempty,
+                  const uint8_t* __restrict__ nonsurface, int ignore255, int64_t n, int C, int64_t* __restrict__ out) {
+  __shared__ unsigned long long red[3 * 32 + 3];
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31;
+  for (int i = tid; i < 3 * 32 + 3; i += blockDim.x) red[i] = 0ull;
   __syncthreads();
-  Packed<NW> k; k.clear();
-  Comp c{0, 0, 0};
+  VoteAcc a{0, 0, 0, 0, 0, 0};
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + tid) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int64_t n_tiles = ceil_div64(n, kTileVox);
-  for (int64_t tile = warp_global; tile < n_tiles; tile += n_warps) {   // <= 4000 tiles per warp (host guarantees): no 16-bit overflow
+  for (int64_t tile = warp_global; tile < n_tiles; tile += n_warps) {
     const int64_t base = tile * kTileVox;
     long long pa[8], pb[8];
     uint32_t ta[8], tb[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
+    for (int q = 0; q < 8; ++q) {   // all loads first: 8 x 16 B (pred) + 8 x 2 B (target) in flight per lane
       int64_t v = base + q * 64 + lane * 2;
       PredVec<PT>::load2(pred, v, n, pa[q], pb[q]);
       load2_u8(target, v, n, ta[q], tb[q]);
@@ -187,34 +180,29 @@ k_ssc_counts_reg(const PT* __restrict__ pred, const uint8_t* __restrict__ target
       if (nonsurface) load2_u8(nonsurface, v, n, sa, sb);
       bool va = v < n && ea && !(ignore255 && ta[q] == 255u);
       bool vb = v + 1 < n && eb && !(ignore255 && tb[q] == 255u);
-      tally_reg<NW>(pa[q], ta[q], va, va && sa, C, k, c);
-      tally_reg<NW>(pb[q], tb[q], vb, vb && sb, C, k, c);
+      vote_step(pa[q], ta[q], va, va && sa, C, lane, a);
+      vote_step(pb[q], tb[q], vb, vb && sb, C, lane, a);
     }
   }
-  // unpack + warp reduce + block reduce (shared u64 atomics: integer, order independent) + one global atomic per bin
-#pragma unroll
-  for (int fam = 0; fam < 3; ++fam) {
-    unsigned long long* a = fam == 0 ? k.tp : (fam == 1 ? k.fp : k.fn);
-#pragma unroll
-    for (int j = 0; j < 4 * NW; ++j) {
-      unsigned v = (unsigned)((a[j >> 2] >> (16 * (j & 3))) & 0xffffull);
-      v = __reduce_add_sync(0xffffffffu, v);
-      if (lane == 0 && v) atomicAdd(&red[fam * 4 * NW + j], (unsigned long long)v);
-    }
+  // lane j holds class j; completion counters are lane-uniform.  Block-level integer reduction, then one global
+  // atomic per (block, bin).
+  if ((int)lane < C) {
+    if (a.tp) atomicAdd(&red[lane], (unsigned long long)a.tp);
+    if (a.fp) atomicAdd(&red[32 + lane], (unsigned long long)a.fp);
+    if (a.fn) atomicAdd(&red[64 + lane], (unsigned long long)a.fn);
   }
-  unsigned ctp = __reduce_add_sync(0xffffffffu, c.tp), cfp = __reduce_add_sync(0xffffffffu, c.fp), cfn = __reduce_add_sync(0xffffffffu, c.fn);
   if (lane == 0) {
-    if (ctp) atomicAdd(&red[3 * 4 * NW + 0], (unsigned long long)ctp);
-    if (cfp) atomicAdd(&red[3 * 4 * NW + 1], (unsigned long long)cfp);
-    if (cfn) atomicAdd(&red[3 * 4 * NW + 2], (unsigned long long)cfn);
+    if (a.ctp) atomicAdd(&red[96], (unsigned long long)a.ctp);
+    if (a.cfp) atomicAdd(&red[97], (unsigned long long)a.cfp);
+    if (a.cfn) atomicAdd(&red[98], (unsigned long long)a.cfn);
   }
   __syncthreads();
-  for (int i = tid; i < 3 * 4 * NW + 3; i += blockDim.x) {
+  for (int i = tid; i < 99; i += blockDim.x) {
     unsigned long long v = red[i];
     if (!v) continue;
-    if (i >= 3 * 4 * NW) atomicAdd(reinterpret_cast<unsigned long long*>(out + (i - 3 * 4 * NW)), v);
+    if (i >= 96) atomicAdd(reinterpret_cast<unsigned long long*>(out + (i - 96)), v);
     else {
-      int fam = i / (4 * NW), j = i % (4 * NW);
+      int fam = i >> 5, j = i & 31;
       if (j < C) atomicAdd(reinterpret_cast<unsigned long long*>(out + 3 + fam * C + j), v);
     }
   }
@@ -275,28 +263,18 @@ static int set_smem(K kern, size_t smem) {
   return 0;
 }
 
-template <typename PT, int NW>
-static int launch_counts_reg(const void* pred, const uint8_t* target, const uint8_t* ne, const uint8_t* ns, int ignore255,
-                             int64_t n, int C, int64_t* out, cudaStream_t st, unsigned grid) {
-  prof_mark("<ssc>", st);
-  k_ssc_counts_reg<PT, NW><<<grid, 256, 0, st>>>((const PT*)pred, target, ne, ns, ignore255, n, C, out);
-  MUVO_AFTER_LAUNCH("k_ssc_counts_reg", st);
-  return MUVO_OK;
-}
-
 template <typename PT>
 static int launch_counts(const void* pred, const uint8_t* target, const uint8_t* ne, const uint8_t* ns, int ignore255,
                          int64_t n, int C, int64_t* out, cudaStream_t st) {
-  if (C <= 16) {
+  if (C <= 32 && n < ((int64_t)1 << 40)) {                      // u32 per-warp counters cannot overflow below 2^40 voxels
     const int64_t tiles = ceil_div64(n, kTileVox);
     int64_t want = ceil_div64(tiles, 8);                       // 8 warps per block, >= 1 tile per warp
     int64_t cap = (int64_t)kNumSMsB200 * 8;
     unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
-    if (ceil_div64(tiles, (int64_t)grid * 8) <= 2000) {        // 16 voxels/lane/tile * 2000 < 65536: fields cannot overflow
-      if (C <= 4) return launch_counts_reg<PT, 1>(pred, target, ne, ns, ignore255, n, C, out, st, grid);
-      if (C <= 8) return launch_counts_reg<PT, 2>(pred, target, ne, ns, ignore255, n, C, out, st, grid);
-      return launch_counts_reg<PT, 4>(pred, target, ne, ns, ignore255, n, C, out, st, grid);
-    }
+    prof_mark("<ssc>", st);
+    k_ssc_counts_vote<PT><<<grid, 256, 0, st>>>((const PT*)pred, target, ne, ns, ignore255, n, C, out);
+    MUVO_AFTER_LAUNCH("k_ssc_counts_vote", st);
+    return MUVO_OK;
   }
   size_t smem; int thr = pick_threads(C, &smem);
   if (!thr) return MUVO_E_ARG;

@@ -168,3 +168,27 @@ def test_full_size_cfg3(lib):
     assert (feat.grad - want).abs().max() <= TOL * want.abs().max()
     out2 = fp(synth.lift(feat, depth), K[:, None], E[:, None], mask)
     assert torch.equal(out, out2)
+
+
+def test_windowed_and_oversized_cells(lib):
+    """More kept points than the shared-memory staging holds (windows of whole cells) and a single cell larger
+    than the staging buffer (direct gather path)."""
+    fp = module()
+    feat, depth, mask, K, E = synth.bev_inputs(1, 4, 3200)
+    out = fp(synth.lift(feat.cuda(), depth.cuda()), K.cuda()[:, None], E.cuda()[:, None])      # no mask: ~110 k kept points
+    xl = synth.lift(feat, depth).double()
+    exact = O.frustum_pooling_forward(xl, K[:, None], E[:, None], torch.zeros(0), exact=True, **synth.BEV_POOL_ARGS)
+    mag = O.frustum_pooling_forward(xl.abs(), K[:, None], E[:, None], torch.zeros(0), exact=True, **synth.BEV_POOL_ARGS)
+    assert torch.all((out.cpu().double() - exact).abs() <= TOL * mag + 1e-30)
+    # everything in one cell
+    g = torch.Generator().manual_seed(9)
+    base = torch.randn(1, 3, 1, 1, 70000, generator=g).cuda()
+    x = base.unsqueeze(1).permute(0, 1, 3, 4, 5, 2)
+    cell = torch.full((1, 70000), 5, dtype=torch.int32).cuda()
+    cell[0, ::7] = -1
+    out = bev_pool(x, cell, 9)
+    keep = (cell[0] >= 0).cpu()
+    want = base[0, :, 0, 0].cpu().double()[:, keep].sum(1)
+    mg = base[0, :, 0, 0].cpu().double()[:, keep].abs().sum(1)
+    assert torch.all((out[0, :, 5].cpu().double() - want).abs() <= TOL * mg)
+    assert torch.count_nonzero(out[0, :, :5]) == 0 and torch.count_nonzero(out[0, :, 6:]) == 0
