@@ -41,7 +41,9 @@ struct BevWs {
   uint32_t* cell_total = nullptr;   // [B, n_cells]
   uint32_t* cell_start = nullptr;   // [B, n_cells + 1]
   int32_t* sorted = nullptr;        // [B, n_pts]  point ids grouped by cell, ascending inside a cell
-  int32_t* pos_of = nullptr;        // [B, n_pts]  inverse: position of point p in `sorted`, -1 = dropped
+  int32_t* kp = nullptr;            // [B, n_pts]  kept points in ascending point order ...
+  int32_t* dest = nullptr;          // [B, n_pts]  ... and their position in `sorted`
+  uint32_t* chunk_kept = nullptr;   // [B, n_wc]   kept points per warp-chunk, scanned in place by S3
   int n_wc = 0;
   size_t bytes = 0;
 };
@@ -55,14 +57,17 @@ static BevWs carve_bev(void* base, int B, int64_t n_pts, int n_cells) {
   w.cell_total = (uint32_t*)(b + o); o = align_up(o + (size_t)B * n_cells * 4, 256);
   w.cell_start = (uint32_t*)(b + o); o = align_up(o + (size_t)B * (n_cells + 1) * 4, 256);
   w.sorted = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
-  w.pos_of = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
+  w.kp = (int32_t*)(b + o);          o = align_up(o + (size_t)B * n_pts * 4, 256);
+  w.dest = (int32_t*)(b + o);        o = align_up(o + (size_t)B * n_pts * 4, 256);
+  w.chunk_kept = (uint32_t*)(b + o); o = align_up(o + (size_t)B * w.n_wc * 4, 256);
   w.bytes = o;
   return w;
 }
 
 // S1: histogram of one warp-chunk; counts (<= 1024) written as u32 into chunk_base (scanned in place by S2).
 __global__ void __launch_bounds__(kSortWarps * 32)
-k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc, uint32_t* __restrict__ chunk_base) {
+k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc, uint32_t* __restrict__ chunk_base,
+            uint32_t* __restrict__ chunk_kept) {
   extern __shared__ uint32_t sm[];                 // [kSortWarps][n_cells]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t wc_global = (int64_t)blockIdx.x * kSortWarps + warp;
@@ -73,6 +78,7 @@ k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells,
   const int b = (int)(wc_global / n_wc), wc = (int)(wc_global % n_wc);
   const int32_t* cp = cell + (size_t)b * n_pts;
   const int64_t p0 = (int64_t)wc * kWarpChunk;
+  uint32_t kept = 0;
   for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
     int cc[8];
 #pragma unroll
@@ -84,10 +90,12 @@ k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells,
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       unsigned m = __match_any_sync(0xffffffffu, cc[u]);
+      kept += __popc(__ballot_sync(0xffffffffu, cc[u] >= 0));
       if (cc[u] >= 0 && lane == (__ffs(m) - 1)) h[cc[u]] += __popc(m);
       __syncwarp();
     }
   }
+  if (lane == 0) chunk_kept[(size_t)b * n_wc + wc] = kept;
   uint32_t* dst = chunk_base + ((size_t)b * n_wc + wc) * n_cells;
   for (int i = lane; i < n_cells; i += 32) dst[i] = h[i];
 }
@@ -113,7 +121,8 @@ __global__ void k_cell_scan(uint32_t* __restrict__ chunk_base, uint32_t* __restr
 
 // S3: per frame exclusive scan over cells (one block per frame).
 __global__ void __launch_bounds__(1024)
-k_cell_starts(const uint32_t* __restrict__ cell_total, uint32_t* __restrict__ cell_start, int n_cells) {
+k_cell_starts(const uint32_t* __restrict__ cell_total, uint32_t* __restrict__ cell_start, int n_cells,
+              uint32_t* __restrict__ chunk_kept, int n_wc) {
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry_s;
   const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -143,13 +152,39 @@ k_cell_starts(const uint32_t* __restrict__ cell_total, uint32_t* __restrict__ ce
     __syncthreads();
   }
   if (threadIdx.x == 0) st[n_cells] = carry_s;
+  // exclusive scan of the kept-per-chunk counts (in place): rank of every kept point in ascending point order
+  __syncthreads();
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  uint32_t* ck = chunk_kept + (size_t)b * n_wc;
+  for (int base = 0; base < n_wc; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < n_wc ? ck[i] : 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t carry = carry_s;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
+      wsum[lane] = wi - w;
+      if (lane == 31) carry_s = carry + wi;
+    }
+    __syncthreads();
+    if (i < n_wc) ck[i] = carry + wsum[warp] + incl - v;
+    __syncthreads();
+  }
 }
 
 // S4: stable placement.
 __global__ void __launch_bounds__(kSortWarps * 32)
 k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc,
              const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ sorted,
-             int32_t* __restrict__ pos_of) {
+             const uint32_t* __restrict__ chunk_kept, int32_t* __restrict__ kp, int32_t* __restrict__ dest) {
   extern __shared__ uint32_t sm[];                 // running count per cell inside this warp-chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t wc_global = (int64_t)blockIdx.x * kSortWarps + warp;
@@ -162,7 +197,9 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
   const uint32_t* cb = chunk_base + ((size_t)b * n_wc + wc) * n_cells;
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
   int32_t* out = sorted + (size_t)b * n_pts;
-  int32_t* inv = pos_of + (size_t)b * n_pts;
+  int32_t* kpo = kp + (size_t)b * n_pts;
+  int32_t* dso = dest + (size_t)b * n_pts;
+  uint32_t krun = chunk_kept[(size_t)b * n_wc + wc];   // kept points before this chunk (frame-relative)
   const int64_t p0 = (int64_t)wc * kWarpChunk;
   for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
     int cc[8];
@@ -180,13 +217,15 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
       const int c = cc[u];
       unsigned m = __match_any_sync(0xffffffffu, c);
       const int64_t pp = p0 + (r0 + u) * 32 + lane;
+      const unsigned vb = __ballot_sync(0xffffffffu, c >= 0);
       if (c >= 0) {
         uint32_t pos = basepos[u] + run[c] + __popc(m & ((1u << lane) - 1u));
+        uint32_t kr = krun + __popc(vb & ((1u << lane) - 1u));
         out[pos] = (int32_t)pp;
-        inv[pp] = (int32_t)pos;
-      } else if (pp < n_pts) {
-        inv[pp] = -1;
+        kpo[kr] = (int32_t)pp;
+        dso[kr] = (int32_t)pos;
       }
+      krun += __popc(vb);
       __syncwarp();
       if (c >= 0 && lane == (__ffs(m) - 1)) run[c] += __popc(m);
       __syncwarp();
@@ -203,14 +242,16 @@ constexpr int kRowThreads = 1024;
 constexpr int kRowCap = 54 * 1024;   // floats of staging (216 KB)
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads, 1)
-k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ pos_of,
+k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ kp_all, const int32_t* __restrict__ dest_all,
             const uint32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C,
             int n_cells, float* __restrict__ out) {
   extern __shared__ float buf[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / C, c = blockIdx.x % C;
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
-  const int32_t* pos = pos_of + (size_t)b * n_pts;
+  const int32_t* kp = kp_all + (size_t)b * n_pts;
+  const int32_t* ds = dest_all + (size_t)b * n_pts;
+  const int n_kept = (int)cs[n_cells];
   const T* xr = x + (size_t)b * sb + (size_t)c * sc;
   float* o = out + ((size_t)b * C + c) * n_cells;
   int c0 = 0;
@@ -223,19 +264,19 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
     if (w1 - w0 <= (uint32_t)kRowCap) {
       if (w1 > w0) {
         const int iw0 = (int)w0, iw1 = (int)w1;
-        for (int64_t p0 = 0; p0 < n_pts; p0 += (int64_t)kRowThreads * 8) {
-          int d[8];
+        for (int j0 = 0; j0 < n_kept; j0 += kRowThreads * 8) {
+          int d[8], pp[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {          // coalesced positions, 8 in flight
-            int64_t p = p0 + (int64_t)u * kRowThreads + tid;
-            d[u] = (p < n_pts) ? __ldg(pos + p) : -1;
+          for (int u = 0; u < 8; ++u) {          // coalesced index loads, 16 in flight
+            int j = j0 + u * kRowThreads + tid;
+            bool in = j < n_kept;
+            d[u] = in ? __ldg(ds + j) : -1;
+            pp[u] = in ? __ldg(kp + j) : 0;
           }
           float v[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {          // predicated, address-ordered feature loads
-            int64_t p = p0 + (int64_t)u * kRowThreads + tid;
-            v[u] = (d[u] >= iw0 && d[u] < iw1) ? ldf<T>(xr + p) : 0.f;
-          }
+          for (int u = 0; u < 8; ++u)            // address-ordered gathers of the kept points only
+            v[u] = (d[u] >= iw0 && d[u] < iw1) ? ldf<T>(xr + pp[u]) : 0.f;
 #pragma unroll
           for (int u = 0; u < 8; ++u)
             if (d[u] >= iw0 && d[u] < iw1) buf[d[u] - iw0] = v[u];
@@ -472,20 +513,20 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   const int64_t n_chunks = (int64_t)B * w.n_wc;
   const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
   prof_mark("<bev_fwd>", st);
-  k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base);
+  k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.chunk_kept);
   MUVO_AFTER_LAUNCH("k_cell_hist", st);
   k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_scan", st);
-  k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells);
+  k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_starts", st);
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
-                                                             w.pos_of);
+                                                             w.chunk_kept, w.kp, w.dest);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
   if (sp == 1) {
     const size_t rsmem = (size_t)kRowCap * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
     if (e != cudaSuccess) return (int)e;
-    k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.pos_of, w.cell_start, w.sorted, B, n_pts,
+    k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.kp, w.dest, w.cell_start, w.sorted, B, n_pts,
                                                                          C, n_cells, out);
   } else {
     k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,

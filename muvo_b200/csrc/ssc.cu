@@ -126,6 +126,106 @@ __global__ void k_ssc_counts(const PT* __restrict__ pred, const uint8_t* __restr
   flush_counts(cnt, C, c, out);
 }
 
+// ---- pair-histogram path (C <= 16): ONE private counter update per voxel.  Each thread owns a column of
+// u16 counters in shared memory, bin = tb * (C + 2) + pb with
+//   tb in {0..C-1, C = "other target (>= C)"},  pb in {0..C-1, C = "prediction >= C", C+1 = "prediction < 0"},
+// for the per-class mask and (when a nonsurface mask is given) a second histogram for the completion mask.
+// tp/fp/fn per class and the completion counts are linear in these bins and are derived once per block.
+template <typename PT, bool ALIGNED, bool TWO>
+__global__ void __launch_bounds__(256)
+k_ssc_pairhist(const PT* __restrict__ pred, const uint8_t* __restrict__ target, const uint8_t* __restrict__ nonempty,
+               const uint8_t* __restrict__ nonsurface, int ignore255, int64_t n, int C, int64_t* __restrict__ out) {
+  extern __shared__ uint16_t hist[];                    // [TWO ? 2 : 1][nbins][256]
+  __shared__ unsigned long long red[3 * 16 + 3];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int PB = C + 2, nbins = (C + 1) * PB;
+  const int nh = TWO ? 2 : 1;
+  for (int i = tid; i < nh * nbins * 256; i += 256) hist[i] = 0;
+  for (int i = tid; i < 51; i += 256) red[i] = 0ull;
+  __syncthreads();
+  uint16_t* mine = hist + tid;
+  uint16_t* mine2 = hist + (size_t)nbins * 256 + tid;
+  const int64_t warp_global = ((int64_t)blockIdx.x * 256 + tid) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
+  const int64_t n_tiles = ceil_div64(n, kTileVox);
+  for (int64_t tile = warp_global; tile < n_tiles; tile += n_warps) {
+    const int64_t base = tile * kTileVox;
+    const bool full = ALIGNED && (base + kTileVox <= n);
+    long long pv[16];
+    uint32_t tv[16];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {   // all loads first: 8 x 16 B (pred) + 8 x 2 B (target) in flight per lane
+      int64_t v = base + q * 64 + lane * 2;
+      if (full) {
+        if (sizeof(PT) == 8) {
+          longlong2 t2;
+          asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(t2.x), "=l"(t2.y) : "l"(pred + v));
+          pv[2 * q] = t2.x; pv[2 * q + 1] = t2.y;
+        } else { pv[2 * q] = (long long)pred[v]; pv[2 * q + 1] = (long long)pred[v + 1]; }
+        uint16_t t16 = __ldg(reinterpret_cast<const uint16_t*>(target + v));
+        tv[2 * q] = t16 & 0xffu; tv[2 * q + 1] = t16 >> 8;
+      } else {
+        pv[2 * q] = v < n ? (long long)pred[v] : 0; pv[2 * q + 1] = v + 1 < n ? (long long)pred[v + 1] : 0;
+        tv[2 * q] = v < n ? target[v] : 0; tv[2 * q + 1] = v + 1 < n ? target[v + 1] : 0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int64_t v = base + (e >> 1) * 64 + lane * 2 + (e & 1);
+      uint32_t t = tv[e];
+      long long p = pv[e];
+      bool valid = full || v < n;
+      if (nonempty) valid = valid && (v < n) && nonempty[v];
+      const bool is255 = (t == 255u);
+      valid = valid && !(ignore255 && is255);
+      if (is255) { t = 0; p = 0; }                                     // :150-151, :184-185
+      const int tb = min((int)t, C);
+      const int pb = p < 0 ? C + 1 : (p < (long long)C ? (int)p : C);
+      const int bin = tb * PB + pb;
+      if (valid) mine[bin * 256] += 1;
+      if (TWO) { if (valid && nonsurface[v]) mine2[bin * 256] += 1; }
+    }
+  }
+  __syncthreads();
+  // block reduction: warp w sums bins w, w+8, ...; contributions go to red[] (tp | fp | fn | completion)
+  const int warp = tid >> 5;
+  for (int hsel = 0; hsel < nh; ++hsel) {
+    const uint16_t* hh = hist + (size_t)hsel * nbins * 256;
+    for (int bin = warp; bin < nbins; bin += 8) {
+      unsigned sum = 0;
+      for (int t = lane; t < 256; t += 32) sum += hh[bin * 256 + t];
+      sum = __reduce_add_sync(0xffffffffu, sum);
+      if (lane == 0 && sum) {
+        const int tb = bin / PB, pb = bin % PB;
+        const unsigned long long v = sum;
+        if (hsel == 0) {                                                // per-class counts (:207-214)
+          if (tb == pb && tb < C) atomicAdd(&red[tb], v);
+          else {
+            if (pb < C) atomicAdd(&red[16 + pb], v);
+            if (tb < C) atomicAdd(&red[32 + tb], v);
+          }
+        }
+        if (hsel == nh - 1) {                                           // completion counts (:157-172)
+          const bool bt = tb > 0, bp = (pb > 0 && pb <= C);
+          if (bt && bp) atomicAdd(&red[48], v);
+          else if (!bt && bp) atomicAdd(&red[49], v);
+          else if (bt && !bp) atomicAdd(&red[50], v);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < 51; i += 256) {
+    unsigned long long v = red[i];
+    if (!v) continue;
+    if (i >= 48) atomicAdd(reinterpret_cast<unsigned long long*>(out + (i - 48)), v);
+    else {
+      int fam = i >> 4, j = i & 15;
+      if (j < C) atomicAdd(reinterpret_cast<unsigned long long*>(out + 3 + fam * C + j), v);
+    }
+  }
+}
+
 // ---- warp-vote path (C <= 32): the warp's 32 voxels of a step are classified together -- per class j,
 // ballot(t == j) and ballot(p == j) give tp/fp/fn of that class with three popcounts, and lane j keeps the
 // counters of class j.  Cost ~ (13 C + 20) warp instructions per 32 voxels instead of ~60 per voxel.
@@ -266,6 +366,32 @@ static int set_smem(K kern, size_t smem) {
 template <typename PT>
 static int launch_counts(const void* pred, const uint8_t* target, const uint8_t* ne, const uint8_t* ns, int ignore255,
                          int64_t n, int C, int64_t* out, cudaStream_t st) {
+  if (C <= 16) {
+    // u16 private counters: at most 2^31 voxels per launch (<= 7 k voxels per thread)
+    const int nbins = (C + 1) * (C + 2);
+    const bool two = ns != nullptr;
+    const size_t smem = (size_t)(two ? 2 : 1) * nbins * 256 * sizeof(uint16_t);
+    if (smem <= 200 * 1024) {
+      const bool aligned = (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && (reinterpret_cast<uintptr_t>(target) % 2 == 0);
+      auto kern = two ? (aligned ? k_ssc_pairhist<PT, true, true> : k_ssc_pairhist<PT, false, true>)
+                      : (aligned ? k_ssc_pairhist<PT, true, false> : k_ssc_pairhist<PT, false, false>);
+      int rc = set_smem(kern, smem);
+      if (rc) return rc;
+      const int per_sm = blocks_per_sm(smem, 256);
+      const int64_t chunk = (int64_t)1 << 31;
+      for (int64_t o = 0; o < n; o += chunk) {
+        const int64_t m = (n - o) < chunk ? (n - o) : chunk;
+        int64_t want = ceil_div64(ceil_div64(m, kTileVox), 8);
+        int64_t cap = (int64_t)kNumSMsB200 * per_sm;
+        unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+        prof_mark("<ssc>", st);
+        kern<<<grid, 256, smem, st>>>((const PT*)pred + o, target + o, ne ? ne + o : nullptr, ns ? ns + o : nullptr, ignore255, m,
+                                      C, out);
+        MUVO_AFTER_LAUNCH("k_ssc_pairhist", st);
+      }
+      return MUVO_OK;
+    }
+  }
   if (C <= 32 && n < ((int64_t)1 << 40)) {                      // u32 per-warp counters cannot overflow below 2^40 voxels
     const int64_t tiles = ceil_div64(n, kTileVox);
     int64_t want = ceil_div64(tiles, 8);                       // 8 warps per block, >= 1 tile per warp
