@@ -240,6 +240,7 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
 // memory are processed in windows of whole cells.
 constexpr int kRowThreads = 1024;
 constexpr int kRowCap = 54 * 1024;   // floats of staging (216 KB)
+constexpr int kBigCell = 64;         // cells above this many points are summed by the whole warp
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads, 1)
 k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ kp_all, const int32_t* __restrict__ dest_all,
@@ -283,18 +284,28 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
         }
       }
       __syncthreads();
-      // 32 consecutive cells per warp step -> one coalesced 128-byte store
+      // Segment sums: one THREAD per cell for the common small cells (sequential, ascending point order), the
+      // warp cooperates (lane-strided partials + fixed xor tree) only on cells above kBigCell points.  A warp
+      // step covers 32 consecutive cells -> one coalesced 128-byte store.
       for (int cb = c0 + warp * 32; cb < c1; cb += (kRowThreads / 32) * 32) {
-        float mine = 0.f;
-        for (int i = 0; i < 32 && cb + i < c1; ++i) {
-          const uint32_t s0 = cs[cb + i] - w0, s1 = cs[cb + i + 1] - w0;
-          float acc = 0.f;
-          for (uint32_t j = s0 + lane; j < s1; j += 32) acc += buf[j];
+        const int cell = cb + lane;
+        uint32_t s0 = 0, s1 = 0;
+        if (cell < c1) { s0 = cs[cell] - w0; s1 = cs[cell + 1] - w0; }
+        const bool big = (s1 - s0) > (uint32_t)kBigCell;
+        float acc = 0.f;
+        if (!big) for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
+        unsigned todo = __ballot_sync(0xffffffffu, big);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src);
+          float part = 0.f;
+          for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
 #pragma unroll
-          for (int dd = 16; dd; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
-          if (lane == i) mine = acc;
+          for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+          if (lane == src) acc = part;
         }
-        if (cb + lane < c1) o[cb + lane] = mine;
+        if (cell < c1) o[cell] = acc;
       }
       __syncthreads();
     } else {

@@ -129,68 +129,76 @@ __global__ void k_ssc_counts(const PT* __restrict__ pred, const uint8_t* __restr
 // ---- pair-histogram path (C <= 16): ONE private counter update per voxel.  Each thread owns a column of
 // u16 counters in shared memory, bin = tb * (C + 2) + pb with
 //   tb in {0..C-1, C = "other target (>= C)"},  pb in {0..C-1, C = "prediction >= C", C+1 = "prediction < 0"},
-// for the per-class mask and (when a nonsurface mask is given) a second histogram for the completion mask.
-// tp/fp/fn per class and the completion counts are linear in these bins and are derived once per block.
+// plus one dummy bin for voxels that are masked out, for the per-class mask and (when a nonsurface mask is
+// given) a second histogram for the completion mask.  tp/fp/fn per class and the completion counts are linear
+// in these bins and are derived once per block.
+constexpr int kPairTile = 256;   // voxels per warp step: 4 x (32 lanes x 2 voxels)
+
+template <typename PT>
+__device__ __forceinline__ int pred_bucket(PT p, int C) {     // class, C = ">= C", C + 1 = "negative"
+  long long v = (long long)p;
+  return v < 0 ? C + 1 : (v < (long long)C ? (int)v : C);
+}
+
 template <typename PT, bool ALIGNED, bool TWO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_ssc_pairhist(const PT* __restrict__ pred, const uint8_t* __restrict__ target, const uint8_t* __restrict__ nonempty,
                const uint8_t* __restrict__ nonsurface, int ignore255, int64_t n, int C, int64_t* __restrict__ out) {
-  extern __shared__ uint16_t hist[];                    // [TWO ? 2 : 1][nbins][256]
+  extern __shared__ uint16_t hist[];                    // [TWO ? 2 : 1][nbins + 1][256]
   __shared__ unsigned long long red[3 * 16 + 3];
   const int tid = threadIdx.x, lane = tid & 31;
-  const int PB = C + 2, nbins = (C + 1) * PB;
+  const int PB = C + 2, nbins = (C + 1) * PB, dummy = nbins;
   const int nh = TWO ? 2 : 1;
-  for (int i = tid; i < nh * nbins * 256; i += 256) hist[i] = 0;
+  for (int i = tid; i < nh * (nbins + 1) * 256; i += 256) hist[i] = 0;
   for (int i = tid; i < 51; i += 256) red[i] = 0ull;
   __syncthreads();
   uint16_t* mine = hist + tid;
-  uint16_t* mine2 = hist + (size_t)nbins * 256 + tid;
+  uint16_t* mine2 = hist + (size_t)(nbins + 1) * 256 + tid;
+  const int bin255 = ignore255 ? dummy : 0;             // target == 255: rewritten to (0,0) (:150-151) or ignored (:79)
   const int64_t warp_global = ((int64_t)blockIdx.x * 256 + tid) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * 256) >> 5;
-  const int64_t n_tiles = ceil_div64(n, kTileVox);
+  const int64_t n_tiles = ceil_div64(n, kPairTile);
   for (int64_t tile = warp_global; tile < n_tiles; tile += n_warps) {
-    const int64_t base = tile * kTileVox;
-    const bool full = ALIGNED && (base + kTileVox <= n);
-    long long pv[16];
-    uint32_t tv[16];
+    const int64_t base = tile * kPairTile;
+    if (ALIGNED && !TWO && nonempty == nullptr && base + kPairTile <= n) {
+      // fast path: full tile, no masks -> no bounds checks, no predicates
+      PT pv[8];
+      uint32_t tv[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {   // all loads first: 8 x 16 B (pred) + 8 x 2 B (target) in flight per lane
-      int64_t v = base + q * 64 + lane * 2;
-      if (full) {
+      for (int q = 0; q < 4; ++q) {
+        const int64_t v = base + q * 64 + lane * 2;
         if (sizeof(PT) == 8) {
           longlong2 t2;
           asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0,%1}, [%2];" : "=l"(t2.x), "=l"(t2.y) : "l"(pred + v));
-          pv[2 * q] = t2.x; pv[2 * q + 1] = t2.y;
-        } else { pv[2 * q] = (long long)pred[v]; pv[2 * q + 1] = (long long)pred[v + 1]; }
-        uint16_t t16 = __ldg(reinterpret_cast<const uint16_t*>(target + v));
-        tv[2 * q] = t16 & 0xffu; tv[2 * q + 1] = t16 >> 8;
-      } else {
-        pv[2 * q] = v < n ? (long long)pred[v] : 0; pv[2 * q + 1] = v + 1 < n ? (long long)pred[v + 1] : 0;
-        tv[2 * q] = v < n ? target[v] : 0; tv[2 * q + 1] = v + 1 < n ? target[v + 1] : 0;
+          pv[2 * q] = (PT)t2.x; pv[2 * q + 1] = (PT)t2.y;
+        } else { pv[2 * q] = pred[v]; pv[2 * q + 1] = pred[v + 1]; }
+        tv[q] = __ldg(reinterpret_cast<const uint16_t*>(target + v));
       }
-    }
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const int64_t v = base + (e >> 1) * 64 + lane * 2 + (e & 1);
-      uint32_t t = tv[e];
-      long long p = pv[e];
-      bool valid = full || v < n;
-      if (nonempty) valid = valid && (v < n) && nonempty[v];
-      const bool is255 = (t == 255u);
-      valid = valid && !(ignore255 && is255);
-      if (is255) { t = 0; p = 0; }                                     // :150-151, :184-185
-      const int tb = min((int)t, C);
-      const int pb = p < 0 ? C + 1 : (p < (long long)C ? (int)p : C);
-      const int bin = tb * PB + pb;
-      if (valid) mine[bin * 256] += 1;
-      if (TWO) { if (valid && nonsurface[v]) mine2[bin * 256] += 1; }
+      for (int e = 0; e < 8; ++e) {
+        const uint32_t t = (tv[e >> 1] >> (8 * (e & 1))) & 0xffu;
+        const int bin = (t == 255u) ? bin255 : min((int)t, C) * PB + pred_bucket<PT>(pv[e], C);
+        mine[bin * 256] += 1;
+      }
+    } else {
+#pragma unroll 1
+      for (int e = 0; e < 8; ++e) {
+        const int64_t v = base + (e >> 1) * 64 + lane * 2 + (e & 1);
+        if (v >= n) continue;
+        const uint32_t t = target[v];
+        const bool valid = !(nonempty && !nonempty[v]);
+        int bin = (t == 255u) ? bin255 : min((int)t, C) * PB + pred_bucket<PT>(pred[v], C);
+        if (!valid) bin = dummy;
+        mine[bin * 256] += 1;
+        if (TWO) mine2[((valid && nonsurface[v]) ? bin : dummy) * 256] += 1;
+      }
     }
   }
   __syncthreads();
   // block reduction: warp w sums bins w, w+8, ...; contributions go to red[] (tp | fp | fn | completion)
   const int warp = tid >> 5;
   for (int hsel = 0; hsel < nh; ++hsel) {
-    const uint16_t* hh = hist + (size_t)hsel * nbins * 256;
+    const uint16_t* hh = hist + (size_t)hsel * (nbins + 1) * 256;
     for (int bin = warp; bin < nbins; bin += 8) {
       unsigned sum = 0;
       for (int t = lane; t < 256; t += 32) sum += hh[bin * 256 + t];
@@ -370,7 +378,7 @@ static int launch_counts(const void* pred, const uint8_t* target, const uint8_t*
     // u16 private counters: at most 2^31 voxels per launch (<= 7 k voxels per thread)
     const int nbins = (C + 1) * (C + 2);
     const bool two = ns != nullptr;
-    const size_t smem = (size_t)(two ? 2 : 1) * nbins * 256 * sizeof(uint16_t);
+    const size_t smem = (size_t)(two ? 2 : 1) * (nbins + 1) * 256 * sizeof(uint16_t);
     if (smem <= 200 * 1024) {
       const bool aligned = (reinterpret_cast<uintptr_t>(pred) % 16 == 0) && (reinterpret_cast<uintptr_t>(target) % 2 == 0);
       auto kern = two ? (aligned ? k_ssc_pairhist<PT, true, true> : k_ssc_pairhist<PT, false, true>)
@@ -381,7 +389,7 @@ static int launch_counts(const void* pred, const uint8_t* target, const uint8_t*
       const int64_t chunk = (int64_t)1 << 31;
       for (int64_t o = 0; o < n; o += chunk) {
         const int64_t m = (n - o) < chunk ? (n - o) : chunk;
-        int64_t want = ceil_div64(ceil_div64(m, kTileVox), 8);
+        int64_t want = ceil_div64(ceil_div64(m, kPairTile), 8);
         int64_t cap = (int64_t)kNumSMsB200 * per_sm;
         unsigned grid = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
         prof_mark("<ssc>", st);
