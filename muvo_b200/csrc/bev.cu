@@ -366,32 +366,37 @@ k_pool_bwd_point_major(const float* __restrict__ gout, const int32_t* __restrict
     }
   }
 }
-template <>
+// float32 fast path: a thread owns 4 consecutive points and walks kBwdCh channels with them, so the cell ids are
+// read once per kBwdCh channels (not once per channel); the grad_out planes of those channels (9 KB each) stay
+// in L1; every store is a coalesced 16-byte streaming store.
+constexpr int kBwdCh = 8;
 __global__ void __launch_bounds__(256)
-k_pool_bwd_point_major<float>(const float* __restrict__ gout, const int32_t* __restrict__ cell, int B, int64_t n_pts, int C,
-                              int n_cells, float* __restrict__ gx, int64_t sb, int64_t sc) {
-  const int64_t quads = ceil_div64(n_pts, 4);
+k_pool_bwd_rows_f32(const float* __restrict__ gout, const int32_t* __restrict__ cell, int B, int64_t n_pts, int C,
+                    int n_cells, float* __restrict__ gx, int64_t sb, int64_t sc) {
+  const int64_t quads = n_pts / 4;                      // host guarantees n_pts % 4 == 0 and 16-byte alignment
+  const int n_cg = (C + kBwdCh - 1) / kBwdCh;
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (int64_t)B * C * quads) return;
+  if (t >= (int64_t)B * n_cg * quads) return;
   const int64_t q = t % quads;
-  const int64_t bc = t / quads;
-  const int ch = (int)(bc % C), b = (int)(bc / C);
+  const int64_t bg = t / quads;
+  const int cg = (int)(bg % n_cg), b = (int)(bg / n_cg);
   const int64_t p0 = q * 4;
-  const int32_t* cp = cell + (size_t)b * n_pts + p0;
-  const float* g = gout + ((size_t)b * C + ch) * n_cells;
-  float* dst = gx + (size_t)b * sb + (size_t)ch * sc + p0;
-  const bool vec = (p0 + 4 <= n_pts) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0);
-  if (vec) {
-    int4 c4 = __ldg(reinterpret_cast<const int4*>(cp));
-    float4 v;
-    v.x = (c4.x >= 0 && c4.x < n_cells) ? __ldg(g + c4.x) : 0.f;
-    v.y = (c4.y >= 0 && c4.y < n_cells) ? __ldg(g + c4.y) : 0.f;
-    v.z = (c4.z >= 0 && c4.z < n_cells) ? __ldg(g + c4.z) : 0.f;
-    v.w = (c4.w >= 0 && c4.w < n_cells) ? __ldg(g + c4.w) : 0.f;
-    st_stream_f4(reinterpret_cast<float4*>(dst), v);
-  } else {
-    for (int k = 0; k < 4; ++k)
-      if (p0 + k < n_pts) { int c = __ldg(cp + k); dst[k] = (c >= 0 && c < n_cells) ? __ldg(g + c) : 0.f; }
+  const int4 c4 = __ldg(reinterpret_cast<const int4*>(cell + (size_t)b * n_pts + p0));
+  const bool k0 = c4.x >= 0 && c4.x < n_cells, k1 = c4.y >= 0 && c4.y < n_cells, k2 = c4.z >= 0 && c4.z < n_cells,
+             k3 = c4.w >= 0 && c4.w < n_cells;
+  const int ch0 = cg * kBwdCh;
+#pragma unroll
+  for (int u = 0; u < kBwdCh; ++u) {
+    const int ch = ch0 + u;
+    if (ch < C) {
+      const float* g = gout + ((size_t)b * C + ch) * n_cells;
+      float4 v;
+      v.x = k0 ? __ldg(g + c4.x) : 0.f;
+      v.y = k1 ? __ldg(g + c4.y) : 0.f;
+      v.z = k2 ? __ldg(g + c4.z) : 0.f;
+      v.w = k3 ? __ldg(g + c4.w) : 0.f;
+      st_stream_f4(reinterpret_cast<float4*>(gx + (size_t)b * sb + (size_t)ch * sc + p0), v);
+    }
   }
 }
 
@@ -551,6 +556,14 @@ template <typename T>
 static int run_pool_bwd(const float* gout, const int32_t* cell, int B, int64_t n_pts, int C, int n_cells, T* gx, int64_t sb,
                         int64_t sp, int64_t sc, cudaStream_t st) {
   prof_mark("<bev_bwd>", st);
+  if (sp == 1 && sizeof(T) == 4 && n_pts % 4 == 0 && sb % 4 == 0 && sc % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(gx) & 15) == 0 && (reinterpret_cast<uintptr_t>(cell) & 15) == 0) {
+    const int n_cg = (C + kBwdCh - 1) / kBwdCh;
+    int64_t n = (int64_t)B * n_cg * (n_pts / 4);
+    k_pool_bwd_rows_f32<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(gout, cell, B, n_pts, C, n_cells, (float*)gx, sb, sc);
+    MUVO_AFTER_LAUNCH("k_pool_bwd_rows_f32", st);
+    return MUVO_OK;
+  }
   if (sp == 1) {
     int64_t n = (int64_t)B * C * ceil_div64(n_pts, 4);
     k_pool_bwd_point_major<T><<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(gout, cell, B, n_pts, C, n_cells, gx, sb, sc);

@@ -31,6 +31,9 @@
 namespace muvo {
 namespace {
 
+#ifndef MUVO_KPL
+#define MUVO_KPL 2
+#endif
 constexpr int kBlock = 256;
 constexpr double kPi = 3.141592653589793;            // np.pi
 constexpr double kPiOver4 = 0x1.921fb54442d18p-1;    // correctly rounded pi/4 (numpy/glibc value on diagonals)
@@ -99,6 +102,13 @@ __device__ __forceinline__ uint32_t key_top_inv(u64 key) { return ~(uint32_t)(ke
 __device__ __forceinline__ u64 pack_word(uint32_t top_inv, uint32_t idx1) { return ((u64)top_inv << 32) | (uint32_t)(~idx1); }
 __device__ __forceinline__ uint32_t word_idx1(u64 w) { return ~(uint32_t)w; }
 __device__ __forceinline__ uint32_t word_top(u64 w) { return (uint32_t)(w >> 32); }
+// voxel words also carry the point's label in the low byte (index limited to 24 bits per frame), so the emit
+// kernels read the label straight from the slot: word = top_inv << 32 | (~idx1 & 0xffffff) << 8 | label
+constexpr uint32_t kVoxIdxMask = 0xffffffu;
+__device__ __forceinline__ u64 pack_vox(uint32_t top_inv, uint32_t idx1, uint32_t label) {
+  return ((u64)top_inv << 32) | (u64)(((~idx1) & kVoxIdxMask) << 8) | (label & 0xffu);
+}
+__device__ __forceinline__ uint32_t vox_idx1(u64 w) { return (~((uint32_t)w >> 8)) & kVoxIdxMask; }
 
 // ---------------------------------------------------------------- per-point arithmetic
 // numpy's npy_divmod (numpy/_core/src/npymath/npy_math_internal.h.src), the scalar behind np.divmod
@@ -128,6 +138,7 @@ struct VoxKey {
   bool in;
 };
 
+template <bool NEED_DIS = true>
 __device__ __forceinline__ VoxKey vox_of(double px, double py, double pz, const GridDev& g) {
   VoxKey k;
   double bx = px + g.off[0], by = py + g.off[1], bz = pz + g.off[2];          // :177
@@ -143,7 +154,7 @@ __device__ __forceinline__ VoxKey vox_of(double px, double py, double pz, const 
     cy = npy_divmod_dev(by, g.res, &my);
     cz = npy_divmod_dev(bz, g.res, &mz);
   }
-  k.dis = (mx * mx + my * my) + mz * mz;
+  if (NEED_DIS) k.dis = (mx * mx + my * my) + mz * mz;
   int ix = (int)cx, iy = (int)cy, iz = (int)cz;
   if (ix < 0 || ix >= g.dx || iy < 0 || iy >= g.dy || iz < 0 || iz >= g.dz) { k.in = false; return k; }
   k.bit = (g.order == ORDER_DENSE) ? (uint32_t)((ix * g.dy + iy) * g.dz + iz)
@@ -175,14 +186,15 @@ __device__ __forceinline__ double atan2_np(double y, double x) {
 
 struct PixKey {
   int pix;        // h*W + w
-  double depth;
+  double s;       // squared range (xc^2 + yc^2) + zc^2: orders like the depth; sqrt only where exactness needs it
   bool ok;
   bool near_w, near_h;
 };
 
-// float64 pixel exactly as the reference computes it (geometry_utils.py:183-200)
-__device__ __noinline__ void pix_exact(double xc, double yc, double zc, double depth, int H, int W, double fda, double fov,
+// float64 pixel exactly as the reference computes it (geometry_utils.py:180-200)
+__device__ __noinline__ void pix_exact(double xc, double yc, double zc, double s, int H, int W, double fda, double fov,
                                        int* pw_o, int* ph_o, int* flags_o) {
+  double depth = sqrt(s);                                 // :180
   double yy = -yc;                                        // :183
   double yaw = atan2_np(yy, xc);                          // :186
   double pitch = asin(zc / depth);                        // :187
@@ -201,17 +213,26 @@ __device__ __noinline__ void pix_exact(double xc, double yc, double zc, double d
 }
 
 template <typename T>
+__device__ __forceinline__ double range_sq_of(T x, T y, T z, const RangeDev& r, double* xc_o, double* yc_o, double* zc_o) {
+  double xc = (double)x - r.L[0];          // :177-178  (x * 1) - L0
+  double yc = (-(double)y) - r.L[1];       //           (y * -1) - L1   (keeps the sign of zero)
+  double zc = (double)z - r.L[2];
+  *xc_o = xc; *yc_o = yc; *zc_o = zc;
+  return (xc * xc + yc * yc) + zc * zc;
+}
+
+template <typename T>
 __device__ __forceinline__ PixKey pix_of(T x, T y, T z, const RangeDev& r) {
   PixKey k;
   double xc, yc, zc;
-  k.depth = range_depth_of(x, y, z, r, &xc, &yc, &zc);
-  k.ok = isfinite(k.depth) && k.depth > 0.0;
+  k.s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
+  k.ok = isfinite(k.s) && k.s > 0.0;
   k.pix = 0; k.near_w = k.near_h = false;
   if (!k.ok) return k;
   // f32 pre-filter.  |error| of pw_f / ph_f vs the float64 value is < 5e-4 bins (atan2f/asinf <= 3 ulp, a few
   // f32 roundings at magnitude <= W); if both are farther than kFastEps from an interior integer the floor
   // cannot differ from the float64 floor.  Values beyond the image clamp to the border bins on both paths.
-  const float xf = (float)xc, yf = (float)(-yc), zf = (float)zc, df = (float)k.depth;
+  const float xf = (float)xc, yf = (float)(-yc), zf = (float)zc, df = sqrtf((float)k.s);
   const float pw_f = 0.5f * (1.0f - atan2f(yf, xf) * r.inv_pi_f) * (float)r.W;
   const float ph_f = (1.0f - (asinf(zf / df) + r.fda_f) * r.inv_fov_f) * (float)r.H;
   const float fw = floorf(pw_f), fh = floorf(ph_f);
@@ -223,7 +244,7 @@ __device__ __forceinline__ PixKey pix_of(T x, T y, T z, const RangeDev& r) {
     ih = (int)fminf(fmaxf(fh, 0.0f), (float)(r.H - 1));
   } else {
     int flags;
-    pix_exact(xc, yc, zc, k.depth, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
+    pix_exact(xc, yc, zc, k.s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
     if (flags & 4) { k.ok = false; return k; }
     k.near_w = flags & 1; k.near_h = flags & 2;
   }
@@ -241,22 +262,21 @@ __device__ __forceinline__ int find_frame(const int64_t* __restrict__ off, int F
 }
 
 // ---------------------------------------------------------------- point loads
-// A warp owns 128 consecutive points; lane L works on points base + 32k + L (k = 0..3).  Global loads are
-// 16-byte vectors (3 x float4 per lane = 4 points), staged through shared memory and read back with a stride
-// of 3 words (conflict free since gcd(3, 32) = 1); the 4 points of a lane are processed in lock step so that
-// their atomics are in flight together.
+// A warp owns 32*KPL consecutive points; lane L works on points base + 32k + L (k < KPL).  Global loads are
+// 16-byte vectors staged through shared memory and read back with a stride of 3 words (conflict free since
+// gcd(3, 32) = 1); the KPL points of a lane are processed in lock step so that their atomics are in flight
+// together.
 constexpr int kWarpsPerBlock = kBlock / 32;
-constexpr int kPtsPerWarp = 128;
-constexpr int kStageWords = 3 * kPtsPerWarp + kPtsPerWarp / 4;   // xyz floats + packed semantics
+template <int KPL> struct Stage { static constexpr int words = 3 * 32 * KPL + 8 * KPL; };   // xyz floats + packed semantics
 
-template <typename T> struct WarpPts { T x[4], y[4], z[4]; uint32_t sem[4]; bool valid[4]; };
+template <typename T, int KPL> struct WarpPts { T x[KPL], y[KPL], z[KPL]; uint32_t sem[KPL]; bool valid[KPL]; };
 
-template <typename T>
-__device__ __forceinline__ void load_warp_points(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base,
-                                                 int64_t P, bool vec_ok, uint32_t* stage, WarpPts<T>& w) {
+template <typename T, int KPL>
+__device__ __forceinline__ void load_warp_points_scalar(const T* __restrict__ xyz, const uint8_t* __restrict__ sem,
+                                                        int64_t base, int64_t P, WarpPts<T, KPL>& w) {
   const unsigned lane = lane_id();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < KPL; ++k) {
     int64_t i = base + 32 * k + lane;
     w.valid[k] = i < P;
     w.x[k] = w.y[k] = w.z[k] = (T)0; w.sem[k] = 0;
@@ -266,23 +286,31 @@ __device__ __forceinline__ void load_warp_points(const T* __restrict__ xyz, cons
     }
   }
 }
-template <>
-__device__ __forceinline__ void load_warp_points<float>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem,
-                                                        int64_t base, int64_t P, bool vec_ok, uint32_t* stage,
-                                                        WarpPts<float>& w) {
+template <typename T, int KPL>
+__device__ __forceinline__ void load_warp_points(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base,
+                                                 int64_t P, bool vec_ok, uint32_t* stage, WarpPts<T, KPL>& w) {
+  load_warp_points_scalar<T, KPL>(xyz, sem, base, P, w);
+}
+template <int KPL>
+__device__ __forceinline__ void load_warp_points_f32(const float* __restrict__ xyz, const uint8_t* __restrict__ sem,
+                                                     int64_t base, int64_t P, bool vec_ok, uint32_t* stage,
+                                                     WarpPts<float, KPL>& w) {
   const unsigned lane = lane_id();
-  if (vec_ok && base + kPtsPerWarp <= P) {
-    const float4* src = reinterpret_cast<const float4*>(xyz + 3 * base) + 3 * lane;
-    float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-    uint32_t s4 = __ldg(reinterpret_cast<const uint32_t*>(sem + base) + lane);
-    float4* dst = reinterpret_cast<float4*>(stage) + 3 * lane;
-    dst[0] = a; dst[1] = b; dst[2] = c;
-    stage[3 * kPtsPerWarp + lane] = s4;
+  constexpr int kPts = 32 * KPL;
+  if (vec_ok && base + kPts <= P) {
+    const float4* src = reinterpret_cast<const float4*>(xyz + 3 * base);
+    float4* dst = reinterpret_cast<float4*>(stage);
+#pragma unroll
+    for (int m = 0; m < (24 * KPL + 31) / 32; ++m) {          // 24*KPL float4 per warp
+      int q = m * 32 + lane;
+      if (q < 24 * KPL) dst[q] = __ldg(src + q);
+    }
+    if (lane < 8 * KPL) stage[3 * kPts + lane] = __ldg(reinterpret_cast<const uint32_t*>(sem + base) + lane);
     __syncwarp();
     const float* sf = reinterpret_cast<const float*>(stage);
-    const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage + 3 * kPtsPerWarp);
+    const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage + 3 * kPts);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < KPL; ++k) {
       int j = 32 * k + lane;
       w.valid[k] = true;
       w.x[k] = sf[3 * j]; w.y[k] = sf[3 * j + 1]; w.z[k] = sf[3 * j + 2];
@@ -290,26 +318,21 @@ __device__ __forceinline__ void load_warp_points<float>(const float* __restrict_
     }
     __syncwarp();
   } else {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      int64_t i = base + 32 * k + lane;
-      w.valid[k] = i < P;
-      w.x[k] = w.y[k] = w.z[k] = 0.f; w.sem[k] = 0;
-      if (w.valid[k]) {
-        w.x[k] = __ldg(xyz + 3 * i); w.y[k] = __ldg(xyz + 3 * i + 1); w.z[k] = __ldg(xyz + 3 * i + 2);
-        w.sem[k] = __ldg(sem + i);
-      }
-    }
+    load_warp_points_scalar<float, KPL>(xyz, sem, base, P, w);
   }
 }
+template <> __device__ __forceinline__ void load_warp_points<float, 1>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base, int64_t P, bool vec_ok, uint32_t* stage, WarpPts<float, 1>& w) { load_warp_points_f32<1>(xyz, sem, base, P, vec_ok, stage, w); }
+template <> __device__ __forceinline__ void load_warp_points<float, 2>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base, int64_t P, bool vec_ok, uint32_t* stage, WarpPts<float, 2>& w) { load_warp_points_f32<2>(xyz, sem, base, P, vec_ok, stage, w); }
+template <> __device__ __forceinline__ void load_warp_points<float, 4>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base, int64_t P, bool vec_ok, uint32_t* stage, WarpPts<float, 4>& w) { load_warp_points_f32<4>(xyz, sem, base, P, vec_ok, stage, w); }
 
 // frames of the warp's points: one search for the first point, then a (rare) walk at frame boundaries
+template <int KPL>
 __device__ __forceinline__ void warp_frames(const int64_t* __restrict__ off, int F, int64_t base, int64_t P, int* fr,
                                             int64_t* fb) {
   int f0 = find_frame(off, F, base < P ? base : P - 1);
   const unsigned lane = lane_id();
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < KPL; ++k) {
     int64_t i = base + 32 * k + lane;
     int f = f0;
     if (i < P) { while (i >= __ldg(off + f + 1)) ++f; }
@@ -323,55 +346,56 @@ __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
 }
 
 // ---------------------------------------------------------------- exact tie protocol (rare path)
-// Called by a point whose atomicMax met a slot holder with the SAME top-32 key bits.  `Key(idx1)` re-derives
-// the exact 64-bit key of point idx1 from its coordinates.  On return the slot holds a point that is exactly
-// <= this point and the one it may have displaced (smaller key, then smaller index), or a point from a
-// strictly better top-32 class.  Every tied point runs this, so the final holder is the exact arg-min.
-template <typename KeyFn>
-__device__ __noinline__ void tie_protocol(u64* slot, uint32_t top_inv, uint32_t me1, u64 my_key, u64 old_word, KeyFn key_of) {
+// Called by a point whose atomicMax met a slot holder with the SAME top-32 key bits.  `key_of(idx1)` re-derives
+// the exact 64-bit key of point idx1 from its coordinates, `pack(idx1)` builds its slot word, `idx_of(word)`
+// extracts the index.  On return the slot holds a point that is exactly <= this point and the one it may have
+// displaced (smaller key, then smaller index), or a point from a strictly better top-32 class.  Every tied
+// point runs this, so the final holder is the exact arg-min.
+template <typename KeyFn, typename PackFn, typename IdxFn>
+__device__ __noinline__ void tie_protocol(u64* slot, uint32_t top_inv, uint32_t me1, u64 mine, u64 old_word, KeyFn key_of,
+                                          PackFn pack, IdxFn idx_of) {
   uint32_t cand1 = me1;
-  u64 cand_key = my_key;
+  u64 cand_key = key_of(me1);
   {
-    uint32_t o1 = word_idx1(old_word);
+    uint32_t o1 = idx_of(old_word);
     u64 ok = key_of(o1);
     if (ok < cand_key || (ok == cand_key && o1 < cand1)) { cand1 = o1; cand_key = ok; }
   }
-  u64 mine = pack_word(top_inv, me1);
   u64 cur = old_word > mine ? old_word : mine;     // content right after this point's atomicMax
   for (;;) {
     if (word_top(cur) != top_inv) break;           // a strictly better class took the slot
-    uint32_t h1 = word_idx1(cur);
+    uint32_t h1 = idx_of(cur);
     if (h1 == cand1) break;                        // the slot holds the candidate
     u64 hk = key_of(h1);
     bool cand_better = cand_key < hk || (cand_key == hk && cand1 < h1);
     if (!cand_better) break;                       // holder is exactly better: already in place
-    u64 prev = atomicCAS(slot, cur, pack_word(top_inv, cand1));
+    u64 prev = atomicCAS(slot, cur, pack(cand1));
     if (prev == cur) break;
     cur = prev;
   }
 }
 
 // ---------------------------------------------------------------- K1: point pass
-template <typename T, bool DO_VOX, bool DO_RANGE>
-__global__ void __launch_bounds__(kBlock, 3)
+template <typename T, int KPL, bool DO_VOX, bool DO_RANGE>
+__global__ void __launch_bounds__(kBlock)
 k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
              int64_t* __restrict__ diag) {
-  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * kStageWords];
+  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * Stage<KPL>::words];
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * kPtsPerWarp;
+  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * (32 * KPL);
   unsigned n_drop = 0, n_nw = 0, n_nh = 0, n_in = 0;
   if (base < P) {   // warp-uniform
-    WarpPts<T> w;
-    load_warp_points<T>(xyz, sem, base, P, vec_ok, stage_all + warp * kStageWords, w);
-    int fr[4]; int64_t fb[4];
-    warp_frames(off, F, base, P, fr, fb);
+    WarpPts<T, KPL> w;
+    load_warp_points<T, KPL>(xyz, sem, base, P, vec_ok, stage_all + warp * Stage<KPL>::words, w);
+    int fr[KPL]; int64_t fb[KPL];
+    warp_frames<KPL>(off, F, base, P, fr, fb);
     if (DO_VOX) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < KPL; ++k) {
         if (w.valid[k]) {
-          VoxKey v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
+          VoxKey v = vox_of<false>((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
           if (v.in) {
             ++n_in;
             atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), 1u << (v.bit & 31));   // RED, no return value
@@ -380,36 +404,39 @@ k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const i
       }
     }
     if (DO_RANGE) {
-      u64* slot[4];
-      u64 mine[4], key[4], old[4];
-      bool act[4];
+      u64* slot[KPL];
+      u64 mine[KPL], old[KPL];
+      bool act[KPL];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        act[k] = false; slot[k] = pixtab; mine[k] = 0; key[k] = 0;
+      for (int k = 0; k < KPL; ++k) {
+        act[k] = false; slot[k] = pixtab; mine[k] = 0;
         if (w.valid[k]) {
           PixKey pk = pix_of(w.x[k], w.y[k], w.z[k], r);
           if (!pk.ok) { ++n_drop; }
           else {
             n_nw += pk.near_w; n_nh += pk.near_h;
             act[k] = true;
-            key[k] = (u64)__double_as_longlong(pk.depth);     // depth > 0: the bit pattern orders like the value
             slot[k] = pixtab + (size_t)fr[k] * r.H * r.W + pk.pix;
-            mine[k] = pack_word(key_top_inv(key[k]), (uint32_t)(base + 32 * k + lane - fb[k]) + 1u);
+            // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
+            mine[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), (uint32_t)(base + 32 * k + lane - fb[k]) + 1u);
           }
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+      for (int k = 0; k < KPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < KPL; ++k) {
         if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k])) {   // same top-32 class: exact protocol
           const T* fx = xyz + 3 * fb[k];
-          auto key_of = [&](uint32_t q1) -> u64 {
+          const uint32_t top = word_top(mine[k]);
+          auto key_of = [&](uint32_t q1) -> u64 {     // exact key: the float64 depth (geometry_utils.py:180)
             const T* qp = fx + 3 * (int64_t)(q1 - 1u);
             double a, b, c;
-            return (u64)__double_as_longlong(range_depth_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c));
+            return (u64)__double_as_longlong(sqrt(range_sq_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c)));
           };
-          tie_protocol(slot[k], word_top(mine[k]), word_idx1(mine[k]), key[k], old[k], key_of);
+          auto pack = [&](uint32_t q1) -> u64 { return pack_word(top, q1); };
+          auto idx_of = [](u64 wv) -> uint32_t { return word_idx1(wv); };
+          tie_protocol(slot[k], top, word_idx1(mine[k]), mine[k], old[k], key_of, pack, idx_of);
         }
       }
     }
@@ -492,51 +519,58 @@ __device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_
 }
 
 // ---------------------------------------------------------------- K3: voxel resolve
-template <typename T>
-__global__ void __launch_bounds__(kBlock, 3)
+// PACKL: the slot word also carries the point's label (needs < 2^24 points per frame); otherwise the label pass
+// (k_slot_labels) fills it in afterwards.
+template <typename T, int KPL, bool PACKL>
+__global__ void __launch_bounds__(kBlock)
 k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
                 bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
                 u64* __restrict__ vslot) {
-  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * kStageWords];
+  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * Stage<KPL>::words];
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
-  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * kPtsPerWarp;
+  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * (32 * KPL);
   if (base >= P) return;   // warp-uniform
-  WarpPts<T> w;
-  load_warp_points<T>(xyz, sem, base, P, vec_ok, stage_all + warp * kStageWords, w);
-  int fr[4]; int64_t fb[4];
-  warp_frames(off, F, base, P, fr, fb);
-  u64* slot[4];
-  u64 mine[4], key[4], old[4];
-  uint32_t bit[4];
-  bool act[4];
+  WarpPts<T, KPL> w;
+  load_warp_points<T, KPL>(xyz, sem, base, P, vec_ok, stage_all + warp * Stage<KPL>::words, w);
+  int fr[KPL]; int64_t fb[KPL];
+  warp_frames<KPL>(off, F, base, P, fr, fb);
+  u64* slot[KPL];
+  u64 mine[KPL], old[KPL];
+  uint32_t bit[KPL];
+  bool act[KPL];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    act[k] = false; slot[k] = vslot; mine[k] = 0; key[k] = 0; bit[k] = 0;
+  for (int k = 0; k < KPL; ++k) {
+    act[k] = false; slot[k] = vslot; mine[k] = 0; bit[k] = 0;
     if (w.valid[k]) {
-      VoxKey v = vox_of((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
+      VoxKey v = vox_of<true>((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
       act[k] = v.in; bit[k] = v.bit;
-      key[k] = vox_key(v.dis, (int)w.sem[k] != g.road);
-      mine[k] = pack_word(key_top_inv(key[k]), (uint32_t)(base + 32 * k + lane - fb[k]) + 1u);
+      const uint32_t top = key_top_inv(vox_key(v.dis, (int)w.sem[k] != g.road));
+      const uint32_t me1 = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
+      mine[k] = PACKL ? pack_vox(top, me1, w.sem[k]) : pack_word(top, me1);
     }
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {   // rank lookups of the 4 points are independent loads
+  for (int k = 0; k < KPL; ++k) {   // rank lookups of the lane's points are independent loads
     if (act[k]) slot[k] = vslot + fb[k] + rank_of(bitmap + (size_t)fr[k] * g.gw, prefix + (size_t)fr[k] * (g.gw / 4), bit[k]);
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+  for (int k = 0; k < KPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < KPL; ++k) {
     if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k])) {
       const T* fx = xyz + 3 * fb[k];
       const uint8_t* fs = sem + fb[k];
+      const uint32_t top = word_top(mine[k]);
       auto key_of = [&](uint32_t q1) -> u64 {
         const T* qp = fx + 3 * (int64_t)(q1 - 1u);
-        VoxKey o = vox_of((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
+        VoxKey o = vox_of<true>((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
         return vox_key(o.dis, (int)__ldg(fs + (q1 - 1u)) != g.road);
       };
-      tie_protocol(slot[k], word_top(mine[k]), word_idx1(mine[k]), key[k], old[k], key_of);
+      auto pack = [&](uint32_t q1) -> u64 { return PACKL ? pack_vox(top, q1, __ldg(fs + (q1 - 1u))) : pack_word(top, q1); };
+      auto idx_of = [](u64 wv) -> uint32_t { return PACKL ? vox_idx1(wv) : word_idx1(wv); };
+      const uint32_t me1 = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
+      tie_protocol(slot[k], top, me1, mine[k], old[k], key_of, pack, idx_of);
     }
   }
 }
@@ -598,23 +632,24 @@ __device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, u64
 
 // Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as
 // two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).
+// grid = (gw / kBlock, F): blockIdx.y is the frame, so no 64-bit division is needed.
 __global__ void __launch_bounds__(kBlock)
 k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
              const int64_t* __restrict__ off, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
              bool clean) {
-  int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;     // global word index over [F, gw]
-  int64_t total = (int64_t)F * g.gw;
-  bool valid = wg < total;
+  const int f = blockIdx.y;
+  const uint32_t wi = blockIdx.x * kBlock + threadIdx.x;        // word index inside the frame
+  const bool valid = wi < (uint32_t)g.gw;
+  const int64_t wg = (int64_t)f * g.gw + wi;
   uint32_t word, rank;
   load_word_and_rank(bitmap, prefix, wg, valid, clean, &word, &rank);
-  unsigned lane = lane_id();
-  int64_t warp_w0 = wg - lane;                                  // first word of this warp (same frame: gw % 32 == 0)
-  if (warp_w0 >= total) return;                                 // whole warp out of range
-  int f = (int)(warp_w0 / g.gw);
+  const unsigned lane = lane_id();
+  const uint32_t warp_w0 = wi - lane;                           // gw % 32 == 0: a warp never straddles frames
+  if (warp_w0 >= (uint32_t)g.gw) return;                        // whole warp out of range
   u64* vslot_f = vslot + __ldg(off + f);
-  int64_t vox0 = (warp_w0 - (int64_t)f * g.gw) * 32;            // first voxel of the warp inside the frame
+  const uint32_t vox0 = warp_w0 * 32u;                          // first voxel of the warp inside the frame
   uint8_t* dst = dense + (size_t)f * g.G + vox0;
-  bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+  const bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     unsigned src = (unsigned)half * 16u + (lane >> 1);          // lane j handles piece p = half*32 + j -> word p/2
@@ -624,9 +659,10 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* 
     if (lane & 1u) rk += __popc(w & 0xffffu);
     uint4 o = expand_half(bits, rk, vslot_f, remap, clean);
     __syncwarp();   // reconverge after the data-dependent gathers so that the store below is one 512-byte request
-    int64_t v = vox0 + ((int64_t)half * 32 + lane) * 16;        // first voxel of this piece
+    const uint32_t piece = (uint32_t)half * 32u + lane;
+    const int64_t v = (int64_t)vox0 + piece * 16;               // first voxel of this piece
     if (fast) {
-      if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + ((int64_t)half * 32 + lane) * 16), o);
+      if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + piece * 16), o);
     } else {
       uint32_t oo[4] = {o.x, o.y, o.z, o.w};
       for (int j = 0; j < 16; ++j)
@@ -801,6 +837,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   if (!do_vox && !do_range) return MUVO_E_ARG;
   if (F < 0 || P < 0) return MUVO_E_ARG;
   if (F == 0) return MUVO_OK;
+  if (F > 65535) return MUVO_E_SHAPE;   // frames are a grid dimension of the emit kernels
   if (!off || !ws) return MUVO_E_NULL;
   if (P > 0 && (!xyz || !sem)) return MUVO_E_NULL;
   if (P >= ((int64_t)1 << 40)) return MUVO_E_SHAPE;
@@ -816,35 +853,43 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   PointsWs w = carve(ws, P, F, grid_h, cfg_h);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 4 == 0);
-  const unsigned pblocks = (unsigned)ceil_div64(P, (int64_t)kWarpsPerBlock * kPtsPerWarp);
+  constexpr int KPL = MUVO_KPL;                                  // points per lane (lock-step ILP vs occupancy)
+  const unsigned pblocks = (unsigned)ceil_div64(P, (int64_t)kWarpsPerBlock * 32 * KPL);
+  const bool packl = P < ((int64_t)1 << 24) - 1;                 // label rides in the voxel word (24-bit index)
 
   prof_mark("<points>", st);
   // K1
   if (P > 0) {
     if (do_vox && do_range)
-      k_point_pass<T, true, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
+      k_point_pass<T, KPL, true, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
     else if (do_vox)
-      k_point_pass<T, true, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
+      k_point_pass<T, KPL, true, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
     else
-      k_point_pass<T, false, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
+      k_point_pass<T, KPL, false, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
     MUVO_AFTER_LAUNCH("k_point_pass", st);
   }
   if (do_vox) {
     // K2
     k_bitmap_scan<<<F, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, n_occ);
     MUVO_AFTER_LAUNCH("k_bitmap_scan", st);
-    // K3
+    // K3 (+ K4 when the label does not fit in the slot word)
     if (P > 0) {
-      k_voxel_resolve<T><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot);
-      MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
-      k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.vslot, sem, off, F, P);
-      MUVO_AFTER_LAUNCH("k_slot_labels", st);
+      if (packl) {
+        k_voxel_resolve<T, KPL, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot);
+        MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
+      } else {
+        k_voxel_resolve<T, KPL, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot);
+        MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
+        k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.vslot, sem, off, F, P);
+        MUVO_AFTER_LAUNCH("k_slot_labels", st);
+      }
     }
-    // K4 (the last consumer of the tables clears them)
+    // K5 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;
     if (order == ORDER_DENSE) {
       if (dense) {
-        k_emit_dense<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, remap, dense, g, F, true);
+        dim3 grid((unsigned)ceil_div64(g.gw, kBlock), (unsigned)F);
+        k_emit_dense<<<grid, kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, remap, dense, g, F, true);
       } else {  // only n_occ requested: clear through the sparse walker without output
         k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, nullptr, g, F, true);
       }
