@@ -221,7 +221,7 @@ def run_ours(args):
 
     # algorithmic bytes: 13 B/point + G + 64*1024*17 per frame
     alg_step = 13 * P + n_frames * (G + HW * 17)
-    alg_kernel = {"k_point_pass": 13 * P, "k_voxel_resolve": 13 * P, "k_emit_dense": n_frames * G,
+    alg_kernel = {"k_points_tile": 13 * P, "k_voxel_tile": 13 * P, "k_emit_dense": n_frames * G,
                   "k_emit_range": n_frames * HW * 17, "k_bitmap_scan": n_frames * (G // 8)}
     top = max(kern, key=kern.get)
     achieved = alg_kernel.get(top, 0) / (kern[top] * 1e-3) / 1e9

@@ -185,6 +185,17 @@ MUVO_API int muvo_ssc_counts_from_logits(const void* logits, int32_t logits_dtyp
                                 int32_t n_classes, int64_t voxels_per_frame, int32_t ignore255,
                                 int64_t* counts_out, void* stream);
 
+/* ---- test / tuning hooks (not part of the drop-in surface) ------------------------------
+ * muvo_debug_pixel_check: runs the f32 pixel path of the range projection next to the float64 formula of
+ * geometry_utils.py:180-200 on n_points float32 ego-frame points and ACCUMULATES into counts_out[4] (device, int64):
+ * [0] points decided by the f32 path, [1] points deferred to the float64 formula (near a bin edge),
+ * [2] f32-decided points whose pixel differs from the float64 one (must stay 0), [3] dropped (non-finite / at the sensor).
+ * muvo_debug_set_tuning: process-wide launch knobs for benchmarking sweeps; key 0 = CTAs per SM of the persistent
+ * point-tile kernels (0 = as many as fit).                                              */
+MUVO_API int muvo_debug_pixel_check(const float* xyz, int64_t n_points, const MuvoRangeCfg* cfg_h, int64_t* counts_out,
+                                    void* stream);
+MUVO_API int muvo_debug_set_tuning(int32_t key, int32_t value);
+
 #ifdef __cplusplus
 }
 #endif

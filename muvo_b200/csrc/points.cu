@@ -9,37 +9,42 @@
 // corner (roadline points first), per pixel the point nearest to the sensor; ties go to the lowest point
 // index.  No float atomics, no sort of the point stream, deterministic result:
 //
-//   K1  k_point_pass    : per point, float64 voxel id + range pixel / depth in numpy's operation order (no
-//                         FMA contraction: this file is compiled with -fmad=false; an f32 pre-filter skips
-//                         the f64 trigonometry for points that are provably far from a bin edge).
-//                         Occupied voxels are marked in a 1-bit-per-voxel frame bitmap; the range pixel is
-//                         resolved with ONE 64-bit atomicMax on   (~top32(depth bits) << 32) | ~(index+1).
-//                         That packed order equals the exact (depth, index) order unless two points of a
-//                         pixel agree in the top 32 key bits; those (rare) run an exact tie protocol.
+//   K1  k_points_tile   : persistent CTAs, each owning a contiguous run of 1024-point tiles that arrive in
+//                         shared memory through a two-stage cp.async.bulk (TMA) + mbarrier pipeline.  Per
+//                         point: float64 voxel id in numpy's operation order (this file is compiled with
+//                         -fmad=false) -> 1-bit-per-voxel frame bitmap (RED.OR); range pixel from an f32
+//                         polynomial atan2 that is PROVABLY on the same side of every bin edge as the float64
+//                         reference formula (points closer than eps to an edge are queued in shared memory and
+//                         finished by the CTA with the exact float64 trigonometry), squared range in float64 ->
+//                         ONE 64-bit atomicMax of (~top32(key) << 32) | ~(index+1) on the pixel word.  That
+//                         packed order equals the exact (depth, index) order unless two points of a pixel
+//                         agree in the top 32 key bits; those (rare) run an exact tie protocol.
 //   K2  k_bitmap_scan   : popcount prefix per 128-bit bitmap chunk -> every occupied voxel gets a dense
 //                         slot id = its rank in output order; n_occ per frame.
-//   K3  k_voxel_resolve : second point pass (no trigonometry): same packed atomicMax on slot `rank`,
-//                         key = (not roadline, |p mod res|^2).
-//   K4  k_slot_labels   : one thread per winner slot: point index -> label byte.
+//   K3  k_voxel_tile    : second tile pass (no trigonometry): same packed atomicMax on slot `rank`,
+//                         key = (not roadline, |p mod res|^2), label carried in the low byte.
+//   K4  k_slot_labels   : only for >= 2^24 points per call: winner index -> label byte.
 //   K5  k_emit_*        : bitmap-ordered, fully coalesced write of the dense uint8 grid (zeros included,
-//                         so no memset + scatter) and/or the sorted sparse (n,4) list; pixel-ordered write
-//                         of the range image.  Emit kernels put every table entry they consume back to 0,
-//                         so the workspace is clean for the next call.
+//                         so no memset + scatter; winner slots of a 1024-voxel span are contiguous and are
+//                         read with one coalesced load) and/or the sorted sparse (n,4) list; pixel-ordered
+//                         write of the range image.  Emit kernels put every table entry they consume back
+//                         to 0, so the workspace is clean for the next call.
 #include <math.h>
 #include "common.cuh"
 
 namespace muvo {
+
+// debug / tuning knobs (muvo_debug_set_tuning): 0 = CTAs per SM of the tile kernels (0 = default)
+int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
 namespace {
 
-#ifndef MUVO_KPL
-#define MUVO_KPL 2
-#endif
 constexpr int kBlock = 256;
+constexpr int kMaxTileCtas = 4096;                   // upper bound of the persistent tile grid (queue length slots)
 constexpr double kPi = 3.141592653589793;            // np.pi
 constexpr double kPiOver4 = 0x1.921fb54442d18p-1;    // correctly rounded pi/4 (numpy/glibc value on diagonals)
 constexpr double k3PiOver4 = 0x1.2d97c7f3321d2p+1;   // correctly rounded 3pi/4
 constexpr double kEdgeEps = 1e-9;                    // diagnostics: "on a bin edge"
-constexpr float kFastEps = 2e-3f;                    // f32 pre-filter: distance to a bin edge below which f64 decides
 
 enum BitOrder { ORDER_DENSE = 0 /* (x*Dy+y)*Dz+z */, ORDER_LINEAR = 1 /* x + Dx*(y + Dy*z) */ };
 
@@ -49,6 +54,7 @@ struct GridDev {
   int dx, dy, dz;
   int road;
   int pow2;
+  int regular;   // pow2 res and upper == size*res exactly: in-grid test and voxel id from one floor per axis
   int order;
   int gw;        // bitmap words per frame (multiple of 32)
   int64_t G;     // voxels per frame
@@ -58,7 +64,10 @@ struct RangeDev {
   int H, W;
   double fda, fov;
   double L[3];
-  float inv_pi_f, fda_f, inv_fov_f;   // f32 pre-filter constants
+  // f32 fast path (see pix_fast): pw = (1 - yaw/pi) * half_w ; ph = h_bias - (pitch/pi) * h_scale
+  float half_w, h_scale, h_bias;
+  float eps_w, eps_h;     // distance to a bin edge (in bins) below which the float64 formula decides
+  float w_hi, h_hi;       // W - 0.5, H - 0.5: beyond these (or below 0.5) both paths clamp to the border bin
 };
 
 typedef unsigned long long u64;
@@ -68,6 +77,8 @@ struct PointsWs {
   uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk
   u64* pixtab = nullptr;        // [F, H*W]   packed winner per pixel (0 = empty)
   u64* vslot = nullptr;         // [P]        packed winner per occupied voxel, slot = frame_offsets[f] + rank
+  uint32_t* qcount = nullptr;   // [kMaxTileCtas] rare-path queue length per tile CTA (rewritten by every call)
+  uint2* queue = nullptr;       // [P]        rare-path queue, CTA b's segment starts at its first point
   size_t bytes = 0;
 };
 
@@ -88,9 +99,11 @@ static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const Muv
   if (r) {
     w.pixtab = (u64*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 8, 256);
   }
+  w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxTileCtas * 4, 256);
   if (g) {
     w.vslot = (u64*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 8, 256);
   }
+  w.queue = (uint2*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 8, 256);
   w.bytes = o;
   return w;
 }
@@ -184,12 +197,26 @@ __device__ __forceinline__ double atan2_np(double y, double x) {
   return atan2(y, x);
 }
 
-struct PixKey {
-  int pix;        // h*W + w
-  double s;       // squared range (xc^2 + yc^2) + zc^2: orders like the depth; sqrt only where exactness needs it
-  bool ok;
-  bool near_w, near_h;
-};
+// voxel id for a "regular" grid (power-of-two res, upper == size*res): floor((p+off)/res) is exact, so
+// 0 <= b < upper  <=>  0 <= floor(b/res) < size  (:178,:183); NaN coordinates fail x == x.
+struct VoxFast { uint32_t bit; bool in; double bx, by, bz; int ix, iy, iz; };
+template <typename T>
+__device__ __forceinline__ VoxFast vox_regular(T x, T y, T z, const GridDev& g) {
+  VoxFast v;
+  v.bx = (double)x + g.off[0]; v.by = (double)y + g.off[1]; v.bz = (double)z + g.off[2];   // :177
+  v.ix = __double2int_rd(v.bx * g.inv_res); v.iy = __double2int_rd(v.by * g.inv_res); v.iz = __double2int_rd(v.bz * g.inv_res);
+  v.in = ((unsigned)v.ix < (unsigned)g.dx) & ((unsigned)v.iy < (unsigned)g.dy) & ((unsigned)v.iz < (unsigned)g.dz) &
+         (x == x) & (y == y) & (z == z);
+  v.bit = (g.order == ORDER_DENSE) ? (uint32_t)((v.ix * g.dy + v.iy) * g.dz + v.iz)
+                                   : (uint32_t)(v.ix + g.dx * (v.iy + g.dy * v.iz));
+  return v;
+}
+// |p mod res|^2 for a regular grid: b - floor(b/res)*res is exact (fma == mul + sub here), then numpy's
+// (mx^2 + my^2) + mz^2 with separate roundings (:212)
+__device__ __forceinline__ double vox_regular_dis(const VoxFast& v, const GridDev& g) {
+  double mx = v.bx - (double)v.ix * g.res, my = v.by - (double)v.iy * g.res, mz = v.bz - (double)v.iz * g.res;
+  return (mx * mx + my * my) + mz * mz;
+}
 
 // float64 pixel exactly as the reference computes it (geometry_utils.py:180-200)
 __device__ __noinline__ void pix_exact(double xc, double yc, double zc, double s, int H, int W, double fda, double fov,
@@ -221,33 +248,57 @@ __device__ __forceinline__ double range_sq_of(T x, T y, T z, const RangeDev& r, 
   return (xc * xc + yc * yc) + zc * zc;
 }
 
+// ---- f32 fast path of the pixel computation
+// atan(t)/pi on [0,1] as t*Q(t^2), Q of degree 6 (tools/fit_atan.py: |error| < 1.2e-7 including the f32 Horner
+// rounding).  Together with the quotient (2 ulp), the f32 coordinates (0.5 ulp each) and the final scaling the
+// column error stays below 2e-4 bins at W = 1024 and the row error below 1e-4 bins at H/fov = 64/40deg; eps_w / eps_h
+// (1e-3 bins at those sizes, scaled up for larger images) leave a 5x margin.  tests/test_points_gpu.py checks the
+// claim on tens of millions of points through muvo_debug_pixel_check.
+__device__ __forceinline__ float atan_over_pi_unit(float t) {
+  const float t2 = __fmul_rn(t, t);
+  float q = 0.002143867f;
+  q = __fmaf_rn(q, t2, -0.010623431f);
+  q = __fmaf_rn(q, t2, 0.025261912f);
+  q = __fmaf_rn(q, t2, -0.042078603f);
+  q = __fmaf_rn(q, t2, 0.063039005f);
+  q = __fmaf_rn(q, t2, -0.10605131f);
+  q = __fmaf_rn(q, t2, 0.31830862f);
+  return __fmul_rn(q, t);
+}
+// atan2(y, x)/pi in [-1, 1]; NaN when x == y == 0 (the caller then takes the exact path)
+__device__ __forceinline__ float atan2_over_pi(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
+  float p = atan_over_pi_unit(__fdividef(mn, mx));
+  if (ay > ax) p = 0.5f - p;
+  if (x < 0.f) p = 1.0f - p;
+  return copysignf(p, y);
+}
+
+struct PixFast { int pix; bool ok; bool slow; double s; };
+// s = squared range (float64, reference order): orders like the depth; `ok` = finite and non-zero; `slow` = the f32
+// pixel is not provably the float64 one (near an edge, NaN, or magnitudes where f32 squares over/underflow).
 template <typename T>
-__device__ __forceinline__ PixKey pix_of(T x, T y, T z, const RangeDev& r) {
-  PixKey k;
+__device__ __forceinline__ PixFast pix_fast(T x, T y, T z, const RangeDev& r) {
+  PixFast k;
   double xc, yc, zc;
   k.s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
-  k.ok = isfinite(k.s) && k.s > 0.0;
-  k.pix = 0; k.near_w = k.near_h = false;
-  if (!k.ok) return k;
-  // f32 pre-filter.  |error| of pw_f / ph_f vs the float64 value is < 5e-4 bins (atan2f/asinf <= 3 ulp, a few
-  // f32 roundings at magnitude <= W); if both are farther than kFastEps from an interior integer the floor
-  // cannot differ from the float64 floor.  Values beyond the image clamp to the border bins on both paths.
-  const float xf = (float)xc, yf = (float)(-yc), zf = (float)zc, df = sqrtf((float)k.s);
-  const float pw_f = 0.5f * (1.0f - atan2f(yf, xf) * r.inv_pi_f) * (float)r.W;
-  const float ph_f = (1.0f - (asinf(zf / df) + r.fda_f) * r.inv_fov_f) * (float)r.H;
-  const float fw = floorf(pw_f), fh = floorf(ph_f);
-  const bool safe_w = (pw_f <= 0.5f) || (pw_f >= (float)r.W - 0.5f) || (pw_f - fw > kFastEps && pw_f - fw < 1.0f - kFastEps);
-  const bool safe_h = (ph_f <= 0.5f) || (ph_f >= (float)r.H - 0.5f) || (ph_f - fh > kFastEps && ph_f - fh < 1.0f - kFastEps);
-  int iw, ih;
-  if (safe_w && safe_h) {   // NaN compares false -> exact path
-    iw = (int)fminf(fmaxf(fw, 0.0f), (float)(r.W - 1));
-    ih = (int)fminf(fmaxf(fh, 0.0f), (float)(r.H - 1));
-  } else {
-    int flags;
-    pix_exact(xc, yc, zc, k.s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
-    if (flags & 4) { k.ok = false; return k; }
-    k.near_w = flags & 1; k.near_h = flags & 2;
-  }
+  const uint32_t hi = (uint32_t)__double2hiint(k.s);
+  k.ok = (k.s > 0.0) & (hi < 0x7ff00000u);
+  const float xf = (float)xc, yf = (float)(-yc), zf = (float)zc;
+  const float pw = __fmul_rn(1.0f - atan2_over_pi(yf, xf), r.half_w);
+  float rho;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rho) : "f"(__fmaf_rn(xf, xf, __fmul_rn(yf, yf))));
+  const float ph = __fmaf_rn(-atan2_over_pi(zf, rho), r.h_scale, r.h_bias);
+  const float fw = floorf(pw), fh = floorf(ph);
+  const float dw = pw - fw, dh = ph - fh;
+  const bool safe_w = (pw <= 0.5f) | (pw >= r.w_hi) | ((dw > r.eps_w) & (dw < 1.0f - r.eps_w));
+  const bool safe_h = (ph <= 0.5f) | (ph >= r.h_hi) | ((dh > r.eps_h) & (dh < 1.0f - r.eps_h));
+  // 1e-12 < s < 1e12 (metres^2): inside, no f32 square over/underflows in a way that could move a pixel
+  const bool mag_ok = (hi - 0x3d719799u) < (0x426d1a94u - 0x3d719799u);
+  k.slow = !(safe_w & safe_h & mag_ok);     // NaN compares false -> slow
+  const int iw = (int)fminf(fmaxf(fw, 0.0f), (float)(r.W - 1));
+  const int ih = (int)fminf(fmaxf(fh, 0.0f), (float)(r.H - 1));
   k.pix = ih * r.W + iw;
   return k;
 }
@@ -261,89 +312,144 @@ __device__ __forceinline__ int find_frame(const int64_t* __restrict__ off, int F
   return lo;
 }
 
-// ---------------------------------------------------------------- point loads
-// A warp owns 32*KPL consecutive points; lane L works on points base + 32k + L (k < KPL).  Global loads are
-// 16-byte vectors staged through shared memory and read back with a stride of 3 words (conflict free since
-// gcd(3, 32) = 1); the KPL points of a lane are processed in lock step so that their atomics are in flight
-// together.
-constexpr int kWarpsPerBlock = kBlock / 32;
-template <int KPL> struct Stage { static constexpr int words = 3 * 32 * KPL + 8 * KPL; };   // xyz floats + packed semantics
-
-template <typename T, int KPL> struct WarpPts { T x[KPL], y[KPL], z[KPL]; uint32_t sem[KPL]; bool valid[KPL]; };
-
-template <typename T, int KPL>
-__device__ __forceinline__ void load_warp_points_scalar(const T* __restrict__ xyz, const uint8_t* __restrict__ sem,
-                                                        int64_t base, int64_t P, WarpPts<T, KPL>& w) {
-  const unsigned lane = lane_id();
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) {
-    int64_t i = base + 32 * k + lane;
-    w.valid[k] = i < P;
-    w.x[k] = w.y[k] = w.z[k] = (T)0; w.sem[k] = 0;
-    if (w.valid[k]) {
-      w.x[k] = __ldg(xyz + 3 * i); w.y[k] = __ldg(xyz + 3 * i + 1); w.z[k] = __ldg(xyz + 3 * i + 2);
-      w.sem[k] = __ldg(sem + i);
-    }
-  }
-}
-template <typename T, int KPL>
-__device__ __forceinline__ void load_warp_points(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base,
-                                                 int64_t P, bool vec_ok, uint32_t* stage, WarpPts<T, KPL>& w) {
-  load_warp_points_scalar<T, KPL>(xyz, sem, base, P, w);
-}
-template <int KPL>
-__device__ __forceinline__ void load_warp_points_f32(const float* __restrict__ xyz, const uint8_t* __restrict__ sem,
-                                                     int64_t base, int64_t P, bool vec_ok, uint32_t* stage,
-                                                     WarpPts<float, KPL>& w) {
-  const unsigned lane = lane_id();
-  constexpr int kPts = 32 * KPL;
-  if (vec_ok && base + kPts <= P) {
-    const float4* src = reinterpret_cast<const float4*>(xyz + 3 * base);
-    float4* dst = reinterpret_cast<float4*>(stage);
-#pragma unroll
-    for (int m = 0; m < (24 * KPL + 31) / 32; ++m) {          // 24*KPL float4 per warp
-      int q = m * 32 + lane;
-      if (q < 24 * KPL) dst[q] = __ldg(src + q);
-    }
-    if (lane < 8 * KPL) stage[3 * kPts + lane] = __ldg(reinterpret_cast<const uint32_t*>(sem + base) + lane);
-    __syncwarp();
-    const float* sf = reinterpret_cast<const float*>(stage);
-    const uint8_t* sb = reinterpret_cast<const uint8_t*>(stage + 3 * kPts);
-#pragma unroll
-    for (int k = 0; k < KPL; ++k) {
-      int j = 32 * k + lane;
-      w.valid[k] = true;
-      w.x[k] = sf[3 * j]; w.y[k] = sf[3 * j + 1]; w.z[k] = sf[3 * j + 2];
-      w.sem[k] = sb[j];
-    }
-    __syncwarp();
-  } else {
-    load_warp_points_scalar<float, KPL>(xyz, sem, base, P, w);
-  }
-}
-template <> __device__ __forceinline__ void load_warp_points<float, 1>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base, int64_t P, bool vec_ok, uint32_t* stage, WarpPts<float, 1>& w) { load_warp_points_f32<1>(xyz, sem, base, P, vec_ok, stage, w); }
-template <> __device__ __forceinline__ void load_warp_points<float, 2>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base, int64_t P, bool vec_ok, uint32_t* stage, WarpPts<float, 2>& w) { load_warp_points_f32<2>(xyz, sem, base, P, vec_ok, stage, w); }
-template <> __device__ __forceinline__ void load_warp_points<float, 4>(const float* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base, int64_t P, bool vec_ok, uint32_t* stage, WarpPts<float, 4>& w) { load_warp_points_f32<4>(xyz, sem, base, P, vec_ok, stage, w); }
-
-// frames of the warp's points: one search for the first point, then a (rare) walk at frame boundaries
-template <int KPL>
-__device__ __forceinline__ void warp_frames(const int64_t* __restrict__ off, int F, int64_t base, int64_t P, int* fr,
-                                            int64_t* fb) {
-  int f0 = find_frame(off, F, base < P ? base : P - 1);
-  const unsigned lane = lane_id();
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) {
-    int64_t i = base + 32 * k + lane;
-    int f = f0;
-    if (i < P) { while (i >= __ldg(off + f + 1)) ++f; }
-    fr[k] = f; fb[k] = __ldg(off + f);
-  }
-}
-
 __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
   unsigned tot = __reduce_add_sync(0xffffffffu, v);
   if (tot && lane_id() == 0) atomicAdd(reinterpret_cast<unsigned long long*>(diag + slot), (unsigned long long)tot);
 }
+
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "MUVO_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra MUVO_DONE;\n"
+      "bra MUVO_WAIT;\n"
+      "MUVO_DONE:\n"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// ---------------------------------------------------------------- point tiles
+// A CTA owns a contiguous run of tiles (so the frame of its points advances monotonically); tile t+1 is in flight
+// while tile t is processed.  Thread `tid` handles points tid, tid+256, ... of the tile (stride-3 word reads of the
+// staged xyz are bank-conflict free).  Tiles that are partial (the last one) or whose source is not 16-byte aligned
+// are read straight from global memory.
+constexpr int kTileThreads = 256;
+constexpr int kKPL = 4;                          // points per thread per tile
+constexpr int kTile = kTileThreads * kKPL;       // 1024 points
+
+template <typename T> struct TileLayout {
+  static constexpr size_t xyz_bytes = (size_t)3 * kTile * sizeof(T);
+  static constexpr size_t off_sem = 2 * xyz_bytes;
+  static constexpr size_t off_bar = off_sem + 2 * (size_t)kTile;
+  static constexpr size_t off_qn = off_bar + 16;                 // length of this CTA's segment of the rare-path queue
+  static constexpr size_t bytes = off_qn + 16;
+};
+
+// Rare-path queue (global memory, one segment per CTA = the CTA's own point range, so appends need no global atomics):
+// entry.x = CTA-relative point index, entry.y = kQExact (pixel must come from the float64 formula) or the 1-based
+// frame-relative index of the same-class slot holder that the point's atomicMax met (exact tie protocol needed).
+// Doing this work inline would put the float64 atan2/asin (or the protocol) on the hot kernel's call graph and
+// cost it ~25 registers per thread; k_range_queued / k_voxel_queued finish the queues instead.
+constexpr uint32_t kQExact = 0xffffffffu;
+
+template <typename T>
+__device__ __forceinline__ void tile_issue(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, int64_t base,
+                                           unsigned char* smem, int st) {
+  using L = TileLayout<T>;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::off_bar) + st;
+  mbar_expect_tx(bar, (uint32_t)(L::xyz_bytes + kTile));
+  bulk_g2s(smem + (size_t)st * L::xyz_bytes, xyz + 3 * base, (uint32_t)L::xyz_bytes, bar);
+  bulk_g2s(smem + L::off_sem + (size_t)st * kTile, sem + base, (uint32_t)kTile, bar);
+}
+
+// Tile iterator shared by K1 and K3 (all members are CTA-uniform).
+template <typename T>
+struct Tiles {
+  unsigned char* smem;
+  const T* xyz; const uint8_t* sem; const int64_t* off;
+  int F; int64_t P; bool vec_ok;
+  int t0, t1, t;           // this CTA's tiles [t0, t1), current tile (n_tiles < 2^26)
+  int f;                   // frame of the current tile's first point
+  int64_t fbeg, fend;      // its [begin, end) point range
+  int64_t base; bool full, one_frame; int st;
+
+  __device__ __forceinline__ bool init(unsigned char* smem_, const T* xyz_, const uint8_t* sem_, const int64_t* off_, int F_,
+                                       int64_t P_, bool vec_ok_) {
+    smem = smem_; xyz = xyz_; sem = sem_; off = off_; F = F_; P = P_; vec_ok = vec_ok_;
+    const int64_t n_tiles = ceil_div64(P, kTile);
+    const int64_t per = ceil_div64(n_tiles, (int64_t)gridDim.x);
+    t0 = (int)((int64_t)blockIdx.x * per < n_tiles ? (int64_t)blockIdx.x * per : n_tiles);
+    t1 = (int)((int64_t)t0 + per < n_tiles ? (int64_t)t0 + per : n_tiles);
+    if (t0 >= t1) return false;
+    using L = TileLayout<T>;
+    if (threadIdx.x == 0) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::off_bar);
+      mbar_init(bar, 1); mbar_init(bar + 1, 1);
+      *reinterpret_cast<uint32_t*>(smem + L::off_qn) = 0u;
+      mbar_fence_init();
+    }
+    __syncthreads();
+    f = find_frame(off, F, (int64_t)t0 * kTile);
+    if (threadIdx.x == 0 && is_full(t0)) tile_issue<T>(xyz, sem, (int64_t)t0 * kTile, smem, 0);
+    t = t0 - 1;
+    return true;
+  }
+  __device__ __forceinline__ bool is_full(int tt) const { return vec_ok && ((int64_t)tt + 1) * kTile <= P; }
+  // advance to the next tile; returns false at the end.  The caller ends every tile with __syncthreads().
+  __device__ __forceinline__ bool next() {
+    ++t;
+    if (t >= t1) return false;
+    using L = TileLayout<T>;
+    st = (t - t0) & 1;
+    base = (int64_t)t * kTile;
+    full = is_full(t);
+    if (threadIdx.x == 0 && t + 1 < t1 && is_full(t + 1)) tile_issue<T>(xyz, sem, base + kTile, smem, st ^ 1);
+    while (f + 1 < F && base >= __ldg(off + f + 1)) ++f;
+    fbeg = __ldg(off + f); fend = __ldg(off + f + 1);
+    one_frame = base + kTile <= fend;
+    if (full) mbar_wait(reinterpret_cast<uint64_t*>(smem + L::off_bar) + st, (uint32_t)(((t - t0) >> 1) & 1));
+    return true;
+  }
+  // point j of the current tile
+  __device__ __forceinline__ bool load(int j, T* x, T* y, T* z, uint32_t* lab) const {
+    using L = TileLayout<T>;
+    if (full) {
+      const T* sx = reinterpret_cast<const T*>(smem + (size_t)st * L::xyz_bytes);
+      *x = sx[3 * j]; *y = sx[3 * j + 1]; *z = sx[3 * j + 2];
+      *lab = (smem + L::off_sem + (size_t)st * kTile)[j];
+      return true;
+    }
+    const int64_t i = base + j;
+    *x = *y = *z = (T)0; *lab = 0;
+    if (i >= P) return false;
+    *x = __ldg(xyz + 3 * i); *y = __ldg(xyz + 3 * i + 1); *z = __ldg(xyz + 3 * i + 2);
+    *lab = __ldg(sem + i);
+    return true;
+  }
+  // frame of point i of the current tile: (index, first point)
+  __device__ __forceinline__ void frame_of(int64_t i, int* fk, int64_t* fb) const {
+    *fk = f; *fb = fbeg;
+    if (!one_frame && i >= fend) {
+      int ff = f + 1;
+      while (ff + 1 < F && i >= __ldg(off + ff + 1)) ++ff;
+      *fk = ff; *fb = __ldg(off + ff);
+    }
+  }
+};
 
 // ---------------------------------------------------------------- exact tie protocol (rare path)
 // Called by a point whose atomicMax met a slot holder with the SAME top-32 key bits.  `key_of(idx1)` re-derives
@@ -372,83 +478,6 @@ __device__ __noinline__ void tie_protocol(u64* slot, uint32_t top_inv, uint32_t 
     u64 prev = atomicCAS(slot, cur, pack(cand1));
     if (prev == cur) break;
     cur = prev;
-  }
-}
-
-// ---------------------------------------------------------------- K1: point pass
-template <typename T, int KPL, bool DO_VOX, bool DO_RANGE>
-__global__ void __launch_bounds__(kBlock)
-k_point_pass(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-             bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
-             int64_t* __restrict__ diag) {
-  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * Stage<KPL>::words];
-  const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * (32 * KPL);
-  unsigned n_drop = 0, n_nw = 0, n_nh = 0, n_in = 0;
-  if (base < P) {   // warp-uniform
-    WarpPts<T, KPL> w;
-    load_warp_points<T, KPL>(xyz, sem, base, P, vec_ok, stage_all + warp * Stage<KPL>::words, w);
-    int fr[KPL]; int64_t fb[KPL];
-    warp_frames<KPL>(off, F, base, P, fr, fb);
-    if (DO_VOX) {
-#pragma unroll
-      for (int k = 0; k < KPL; ++k) {
-        if (w.valid[k]) {
-          VoxKey v = vox_of<false>((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
-          if (v.in) {
-            ++n_in;
-            atomicOr(bitmap + (size_t)fr[k] * g.gw + (v.bit >> 5), 1u << (v.bit & 31));   // RED, no return value
-          }
-        }
-      }
-    }
-    if (DO_RANGE) {
-      u64* slot[KPL];
-      u64 mine[KPL], old[KPL];
-      bool act[KPL];
-#pragma unroll
-      for (int k = 0; k < KPL; ++k) {
-        act[k] = false; slot[k] = pixtab; mine[k] = 0;
-        if (w.valid[k]) {
-          PixKey pk = pix_of(w.x[k], w.y[k], w.z[k], r);
-          if (!pk.ok) { ++n_drop; }
-          else {
-            n_nw += pk.near_w; n_nh += pk.near_h;
-            act[k] = true;
-            slot[k] = pixtab + (size_t)fr[k] * r.H * r.W + pk.pix;
-            // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
-            mine[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), (uint32_t)(base + 32 * k + lane - fb[k]) + 1u);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < KPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
-#pragma unroll
-      for (int k = 0; k < KPL; ++k) {
-        if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k])) {   // same top-32 class: exact protocol
-          const T* fx = xyz + 3 * fb[k];
-          const uint32_t top = word_top(mine[k]);
-          auto key_of = [&](uint32_t q1) -> u64 {     // exact key: the float64 depth (geometry_utils.py:180)
-            const T* qp = fx + 3 * (int64_t)(q1 - 1u);
-            double a, b, c;
-            return (u64)__double_as_longlong(sqrt(range_sq_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c)));
-          };
-          auto pack = [&](uint32_t q1) -> u64 { return pack_word(top, q1); };
-          auto idx_of = [](u64 wv) -> uint32_t { return word_idx1(wv); };
-          tie_protocol(slot[k], top, word_idx1(mine[k]), mine[k], old[k], key_of, pack, idx_of);
-        }
-      }
-    }
-  }
-  __syncwarp();
-  if (diag) {
-    if (DO_RANGE) {
-      diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
-      diag_add(diag, MUVO_DIAG_NEAR_EDGE_W, n_nw);
-      diag_add(diag, MUVO_DIAG_NEAR_EDGE_H, n_nh);
-    }
-    if (DO_VOX) diag_add(diag, MUVO_DIAG_IN_GRID, n_in);
   }
 }
 
@@ -518,60 +547,231 @@ __device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_
   return prefix_f[chunk] + below;
 }
 
+// ---------------------------------------------------------------- K1: point pass
+// CTA's tile range, shared by the tile kernels and the queue kernels (same grid size)
+__device__ __forceinline__ void cta_tile_range(int64_t P, int* t0, int* t1) {
+  const int64_t n_tiles = ceil_div64(P, kTile);
+  const int64_t per = ceil_div64(n_tiles, (int64_t)gridDim.x);
+  const int64_t a = (int64_t)blockIdx.x * per;
+  *t0 = (int)(a < n_tiles ? a : n_tiles);
+  *t1 = (int)(a + per < n_tiles ? a + per : n_tiles);
+}
+
+template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
+__global__ void __launch_bounds__(kTileThreads, 4)
+k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
+              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
+              uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ diag) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using L = TileLayout<T>;
+  Tiles<T> tl;
+  if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
+    if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
+    return;
+  }
+  uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
+  const int tid = threadIdx.x;
+  const int64_t blk_first = (int64_t)tl.t0 * kTile;
+  uint2* q = queue + blk_first;
+  const int64_t HW = (int64_t)r.H * r.W;
+  unsigned n_drop = 0, n_in = 0;
+
+  while (tl.next()) {
+    u64* slot[kKPL];
+    u64 mine[kKPL], old[kKPL];
+    bool act[kKPL];
+#pragma unroll
+    for (int k = 0; k < kKPL; ++k) {
+      const int j = k * kTileThreads + tid;
+      const int64_t i = tl.base + j;
+      T x, y, z; uint32_t lab;
+      const bool valid = tl.load(j, &x, &y, &z, &lab);
+      int fk; int64_t fb;
+      tl.frame_of(i, &fk, &fb);
+      act[k] = false; slot[k] = pixtab; mine[k] = 0ull;
+      if (DO_VOX && valid) {
+        uint32_t bit; bool in;
+        if (REG) { VoxFast v = vox_regular(x, y, z, g); bit = v.bit; in = v.in; }
+        else { VoxKey v = vox_of<false>((double)x, (double)y, (double)z, g); bit = v.bit; in = v.in; }
+        if (in) {
+          ++n_in;
+          atomicOr(bitmap + (size_t)fk * g.gw + (bit >> 5), 1u << (bit & 31));   // RED, no return value
+        }
+      }
+      if (DO_RANGE && valid) {
+        const PixFast pk = pix_fast(x, y, z, r);
+        if (!pk.ok) ++n_drop;
+        else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2((uint32_t)(i - blk_first), kQExact);
+        else {
+          act[k] = true;
+          slot[k] = pixtab + (size_t)fk * HW + pk.pix;
+          // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
+          mine[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), (uint32_t)(i - fb) + 1u);
+        }
+      }
+    }
+    if (DO_RANGE) {
+#pragma unroll
+      for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+#pragma unroll
+      for (int k = 0; k < kKPL; ++k) {
+        if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))   // same top-32 class: exact protocol
+          q[atomicAdd(qn, 1u)] = make_uint2((uint32_t)(tl.base + k * kTileThreads + tid - blk_first), word_idx1(old[k]));
+      }
+    }
+    __syncthreads();                         // tile buffer free for the copy issued by the next next()
+  }
+  if (tid == 0) qcount[blockIdx.x] = *qn;
+  if (diag) {
+    if (DO_RANGE) diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
+    if (DO_VOX) diag_add(diag, MUVO_DIAG_IN_GRID, n_in);
+  }
+}
+
+// K1q: finishes the range-image queue.  Same grid as K1.
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_range_queued(const T* __restrict__ xyz, const int64_t* __restrict__ off, int F, int64_t P, RangeDev r, u64* __restrict__ pixtab,
+               const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount, int64_t* __restrict__ diag) {
+  const uint32_t n = qcount[blockIdx.x];
+  if (n == 0u) return;   // CTA-uniform
+  int t0, t1;
+  cta_tile_range(P, &t0, &t1);
+  const int64_t blk_first = (int64_t)t0 * kTile;
+  const uint2* q = queue + blk_first;
+  unsigned n_drop = 0, n_nw = 0, n_nh = 0;
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const uint2 ent = q[e];
+    const int64_t i = blk_first + (int64_t)ent.x;
+    const T x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    double xc, yc, zc;
+    const double s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
+    int pix;
+    if (ent.y == kQExact) {   // the reference's float64 formula decides the pixel
+      int iw, ih, flags;
+      pix_exact(xc, yc, zc, s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
+      if (flags & 4) { ++n_drop; continue; }
+      n_nw += (flags & 1) ? 1u : 0u; n_nh += (flags & 2) ? 1u : 0u;
+      pix = ih * r.W + iw;
+    } else {
+      pix = pix_fast(x, y, z, r).pix;
+    }
+    const int f = find_frame(off, F, i);
+    const int64_t fb = __ldg(off + f);
+    u64* slot = pixtab + (size_t)f * r.H * r.W + pix;
+    const uint32_t top = key_top_inv((u64)__double_as_longlong(s));
+    const uint32_t me1 = (uint32_t)(i - fb) + 1u;
+    const u64 mine = pack_word(top, me1);
+    u64 old_word = (ent.y == kQExact) ? atomicMax(slot, mine) : pack_word(top, ent.y);
+    if (old_word != 0ull && word_top(old_word) == top) {
+      const T* fx = xyz + 3 * fb;
+      auto key_of = [&](uint32_t q1) -> u64 {     // exact key: the float64 depth (geometry_utils.py:180)
+        const T* qp = fx + 3 * (int64_t)(q1 - 1u);
+        double a, b, c;
+        return (u64)__double_as_longlong(sqrt(range_sq_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c)));
+      };
+      auto pack = [&](uint32_t q1) -> u64 { return pack_word(top, q1); };
+      auto idx_of = [](u64 wv) -> uint32_t { return word_idx1(wv); };
+      tie_protocol(slot, top, me1, mine, old_word, key_of, pack, idx_of);
+    }
+  }
+  if (diag) {
+    __syncwarp();
+    diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
+    diag_add(diag, MUVO_DIAG_NEAR_EDGE_W, n_nw);
+    diag_add(diag, MUVO_DIAG_NEAR_EDGE_H, n_nh);
+  }
+}
+
 // ---------------------------------------------------------------- K3: voxel resolve
 // PACKL: the slot word also carries the point's label (needs < 2^24 points per frame); otherwise the label pass
 // (k_slot_labels) fills it in afterwards.
-template <typename T, int KPL, bool PACKL>
-__global__ void __launch_bounds__(kBlock)
-k_voxel_resolve(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-                bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-                u64* __restrict__ vslot) {
-  __shared__ __align__(16) uint32_t stage_all[kWarpsPerBlock * Stage<KPL>::words];
-  const unsigned lane = lane_id();
-  const int warp = threadIdx.x >> 5;
-  const int64_t base = ((int64_t)blockIdx.x * kWarpsPerBlock + warp) * (32 * KPL);
-  if (base >= P) return;   // warp-uniform
-  WarpPts<T, KPL> w;
-  load_warp_points<T, KPL>(xyz, sem, base, P, vec_ok, stage_all + warp * Stage<KPL>::words, w);
-  int fr[KPL]; int64_t fb[KPL];
-  warp_frames<KPL>(off, F, base, P, fr, fb);
-  u64* slot[KPL];
-  u64 mine[KPL], old[KPL];
-  uint32_t bit[KPL];
-  bool act[KPL];
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) {
-    act[k] = false; slot[k] = vslot; mine[k] = 0; bit[k] = 0;
-    if (w.valid[k]) {
-      VoxKey v = vox_of<true>((double)w.x[k], (double)w.y[k], (double)w.z[k], g);
-      act[k] = v.in; bit[k] = v.bit;
-      const uint32_t top = key_top_inv(vox_key(v.dis, (int)w.sem[k] != g.road));
-      const uint32_t me1 = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
-      mine[k] = PACKL ? pack_vox(top, me1, w.sem[k]) : pack_word(top, me1);
-    }
+template <typename T, bool REG, bool PACKL>
+__global__ void __launch_bounds__(kTileThreads, 4)
+k_voxel_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
+             bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
+             u64* __restrict__ vslot, uint2* __restrict__ queue, uint32_t* __restrict__ qcount) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using L = TileLayout<T>;
+  Tiles<T> tl;
+  if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
+    if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
+    return;
   }
+  uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
+  const int tid = threadIdx.x;
+  const int64_t blk_first = (int64_t)tl.t0 * kTile;
+  uint2* q = queue + blk_first;
+  while (tl.next()) {
+    u64* slot[kKPL];
+    u64 mine[kKPL], old[kKPL];
+    bool act[kKPL];
 #pragma unroll
-  for (int k = 0; k < KPL; ++k) {   // rank lookups of the lane's points are independent loads
-    if (act[k]) slot[k] = vslot + fb[k] + rank_of(bitmap + (size_t)fr[k] * g.gw, prefix + (size_t)fr[k] * (g.gw / 4), bit[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
-#pragma unroll
-  for (int k = 0; k < KPL; ++k) {
-    if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k])) {
-      const T* fx = xyz + 3 * fb[k];
-      const uint8_t* fs = sem + fb[k];
-      const uint32_t top = word_top(mine[k]);
-      auto key_of = [&](uint32_t q1) -> u64 {
-        const T* qp = fx + 3 * (int64_t)(q1 - 1u);
-        VoxKey o = vox_of<true>((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
-        return vox_key(o.dis, (int)__ldg(fs + (q1 - 1u)) != g.road);
-      };
-      auto pack = [&](uint32_t q1) -> u64 { return PACKL ? pack_vox(top, q1, __ldg(fs + (q1 - 1u))) : pack_word(top, q1); };
-      auto idx_of = [](u64 wv) -> uint32_t { return PACKL ? vox_idx1(wv) : word_idx1(wv); };
-      const uint32_t me1 = (uint32_t)(base + 32 * k + lane - fb[k]) + 1u;
-      tie_protocol(slot[k], top, me1, mine[k], old[k], key_of, pack, idx_of);
+    for (int k = 0; k < kKPL; ++k) {
+      const int j = k * kTileThreads + tid;
+      const int64_t i = tl.base + j;
+      T x, y, z; uint32_t lab;
+      const bool valid = tl.load(j, &x, &y, &z, &lab);
+      int fk; int64_t fb;
+      tl.frame_of(i, &fk, &fb);
+      act[k] = false; slot[k] = vslot; mine[k] = 0ull;
+      if (valid) {
+        uint32_t bit; bool in; double dis;
+        if (REG) { VoxFast v = vox_regular(x, y, z, g); bit = v.bit; in = v.in; dis = vox_regular_dis(v, g); }
+        else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); bit = v.bit; in = v.in; dis = v.dis; }
+        if (in) {
+          act[k] = true;
+          const uint32_t top = key_top_inv(vox_key(dis, (int)lab != g.road));
+          const uint32_t me1 = (uint32_t)(i - fb) + 1u;
+          mine[k] = PACKL ? pack_vox(top, me1, lab) : pack_word(top, me1);
+          slot[k] = vslot + fb + rank_of(bitmap + (size_t)fk * g.gw, prefix + (size_t)fk * (g.gw / 4), bit);
+        }
+      }
     }
+#pragma unroll
+    for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+#pragma unroll
+    for (int k = 0; k < kKPL; ++k) {
+      if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))
+        q[atomicAdd(qn, 1u)] = make_uint2((uint32_t)(tl.base + k * kTileThreads + tid - blk_first),
+                                          PACKL ? vox_idx1(old[k]) : word_idx1(old[k]));
+    }
+    __syncthreads();
+  }
+  if (tid == 0) qcount[blockIdx.x] = *qn;
+}
+
+// K3q: exact tie protocol for the queued voxel ties: key = (not roadline, float64 |p mod res|^2).  Same grid as K3.
+template <typename T, bool PACKL>
+__global__ void __launch_bounds__(128)
+k_voxel_queued(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
+               GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
+               const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount) {
+  const uint32_t n = qcount[blockIdx.x];
+  if (n == 0u) return;
+  int t0, t1;
+  cta_tile_range(P, &t0, &t1);
+  const int64_t blk_first = (int64_t)t0 * kTile;
+  const uint2* q = queue + blk_first;
+  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+    const uint2 ent = q[e];
+    const int64_t i = blk_first + (int64_t)ent.x;
+    const int f = find_frame(off, F, i);
+    const int64_t fb = __ldg(off + f);
+    const T* fx = xyz + 3 * fb;
+    const uint8_t* fs = sem + fb;
+    const uint32_t me1 = (uint32_t)(i - fb) + 1u;
+    auto key_of = [&](uint32_t q1) -> u64 {
+      const T* qp = fx + 3 * (int64_t)(q1 - 1u);
+      VoxKey o = vox_of<true>((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
+      return vox_key(o.dis, (int)__ldg(fs + (q1 - 1u)) != g.road);
+    };
+    const VoxKey v = vox_of<true>((double)__ldg(xyz + 3 * i), (double)__ldg(xyz + 3 * i + 1), (double)__ldg(xyz + 3 * i + 2), g);
+    const uint32_t top = key_top_inv(vox_key(v.dis, (int)__ldg(sem + i) != g.road));
+    auto pack = [&](uint32_t q1) -> u64 { return PACKL ? pack_vox(top, q1, __ldg(fs + (q1 - 1u))) : pack_word(top, q1); };
+    auto idx_of = [](u64 wv) -> uint32_t { return PACKL ? vox_idx1(wv) : word_idx1(wv); };
+    u64* slot = vslot + fb + rank_of(bitmap + (size_t)f * g.gw, prefix + (size_t)f * (g.gw / 4), v.bit);
+    tie_protocol(slot, top, me1, pack(me1), pack(ent.y), key_of, pack, idx_of);
   }
 }
 
@@ -612,31 +812,17 @@ __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap
   *word_o = word; *rank_o = rank;
 }
 
-// 16 voxels (a half word) -> 16 label bytes (two 64-bit halves); one gather per set bit
-__device__ __forceinline__ uint4 expand_half(uint32_t bits16, uint32_t rank, u64* __restrict__ vslot_f,
-                                             const uint8_t* __restrict__ remap, bool clean) {
-  u64 lo = 0, hi = 0;
-  u64* sl = vslot_f + rank;
-  while (bits16) {
-    int j = __ffs(bits16) - 1;
-    bits16 &= bits16 - 1;
-    uint32_t lab = (uint32_t)(*sl) & 0xffu;
-    if (clean) *sl = 0ull;
-    ++sl;
-    if (remap) lab = __ldg(remap + lab);
-    u64 add = (u64)lab << (8 * (j & 7));
-    if (j < 8) lo |= add; else hi |= add;
-  }
-  return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
-}
-
 // Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as
-// two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).
+// two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).  The winner
+// slots of the span are contiguous in rank order: they are read (and cleared) with coalesced 8-byte
+// accesses, their (remapped) label bytes staged in shared memory, and every lane then picks the labels of
+// its set bits from there -- no dependent global gathers.
 // grid = (gw / kBlock, F): blockIdx.y is the frame, so no 64-bit division is needed.
 __global__ void __launch_bounds__(kBlock)
 k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
              const int64_t* __restrict__ off, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
              bool clean) {
+  __shared__ uint8_t lab_s[kBlock / 32][1024];
   const int f = blockIdx.y;
   const uint32_t wi = blockIdx.x * kBlock + threadIdx.x;        // word index inside the frame
   const bool valid = wi < (uint32_t)g.gw;
@@ -646,7 +832,19 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* 
   const unsigned lane = lane_id();
   const uint32_t warp_w0 = wi - lane;                           // gw % 32 == 0: a warp never straddles frames
   if (warp_w0 >= (uint32_t)g.gw) return;                        // whole warp out of range
-  u64* vslot_f = vslot + __ldg(off + f);
+  uint8_t* labs = lab_s[threadIdx.x >> 5];
+  const uint32_t r0 = __shfl_sync(0xffffffffu, rank, 0);
+  const uint32_t cnt = __shfl_sync(0xffffffffu, rank + __popc(word), 31) - r0;
+  if (cnt) {
+    u64* sl = vslot + __ldg(off + f) + r0;
+    for (uint32_t j = lane; j < cnt; j += 32) {
+      uint32_t lab = (uint32_t)sl[j] & 0xffu;
+      if (clean) sl[j] = 0ull;
+      if (remap) lab = __ldg(remap + lab);
+      labs[j] = (uint8_t)lab;
+    }
+    __syncwarp();
+  }
   const uint32_t vox0 = warp_w0 * 32u;                          // first voxel of the warp inside the frame
   uint8_t* dst = dense + (size_t)f * g.G + vox0;
   const bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
@@ -654,19 +852,23 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* 
   for (int half = 0; half < 2; ++half) {
     unsigned src = (unsigned)half * 16u + (lane >> 1);          // lane j handles piece p = half*32 + j -> word p/2
     uint32_t w = __shfl_sync(0xffffffffu, word, src);
-    uint32_t rk = __shfl_sync(0xffffffffu, rank, src);
+    uint32_t rk = __shfl_sync(0xffffffffu, rank, src) - r0;
     uint32_t bits = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
     if (lane & 1u) rk += __popc(w & 0xffffu);
-    uint4 o = expand_half(bits, rk, vslot_f, remap, clean);
-    __syncwarp();   // reconverge after the data-dependent gathers so that the store below is one 512-byte request
+    uint32_t o[4] = {0u, 0u, 0u, 0u};
+    while (bits) {
+      const int j = __ffs(bits) - 1;
+      bits &= bits - 1;
+      o[j >> 2] |= (uint32_t)labs[rk++] << (8 * (j & 3));
+    }
     const uint32_t piece = (uint32_t)half * 32u + lane;
     const int64_t v = (int64_t)vox0 + piece * 16;               // first voxel of this piece
+    __syncwarp();   // reconverge after the data-dependent loop so that the store below is one 512-byte request
     if (fast) {
-      if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + piece * 16), o);
+      if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + piece * 16), make_uint4(o[0], o[1], o[2], o[3]));
     } else {
-      uint32_t oo[4] = {o.x, o.y, o.z, o.w};
       for (int j = 0; j < 16; ++j)
-        if (v + j < g.G) dense[(size_t)f * g.G + v + j] = (uint8_t)(oo[j >> 2] >> (8 * (j & 3)));
+        if (v + j < g.G) dense[(size_t)f * g.G + v + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
     }
   }
   if (clean && valid && word) bitmap[wg] = 0u;
@@ -794,6 +996,30 @@ k_emit_range(u64* __restrict__ pixtab, const T* __restrict__ xyz, const uint8_t*
   }
 }
 
+// ---------------------------------------------------------------- test hook: f32 pixel path vs float64 formula
+__global__ void __launch_bounds__(kBlock)
+k_debug_pixel_check(const float* __restrict__ xyz, int64_t n, RangeDev r, unsigned long long* __restrict__ out) {
+  unsigned n_fast = 0, n_slow = 0, n_bad = 0, n_drop = 0;
+  for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (int64_t)gridDim.x * kBlock) {
+    const float x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    const PixFast pk = pix_fast(x, y, z, r);
+    if (!pk.ok) { ++n_drop; continue; }
+    if (pk.slow) { ++n_slow; continue; }
+    double xc, yc, zc;
+    const double s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
+    int iw, ih, flags;
+    pix_exact(xc, yc, zc, s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
+    ++n_fast;
+    if ((flags & 4) || pk.pix != ih * r.W + iw) ++n_bad;
+  }
+  unsigned v[4] = {n_fast, n_slow, n_bad, n_drop};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned tot = __reduce_add_sync(0xffffffffu, v[k]);
+    if (tot && lane_id() == 0) atomicAdd(out + k, (unsigned long long)tot);
+  }
+}
+
 // ---------------------------------------------------------------- host side
 static bool is_pow2_double(double v) {
   if (!(v > 0.0) || !isfinite(v)) return false;
@@ -811,6 +1037,9 @@ static int make_grid_dev(const MuvoGrid* g, int order, GridDev* o) {
   o->dx = g->size[0]; o->dy = g->size[1]; o->dz = g->size[2];
   o->road = g->roadline_id;
   o->pow2 = is_pow2_double(g->res) ? 1 : 0;
+  o->regular = o->pow2;
+  for (int k = 0; k < 3; ++k)
+    if (!(g->upper[k] == (double)g->size[k] * g->res) || !isfinite(g->offset[k])) o->regular = 0;
   o->order = order;
   o->gw = bitmap_words(G);
   o->G = G;
@@ -821,7 +1050,13 @@ static int make_range_dev(const MuvoRangeCfg* c, RangeDev* o) {
   if (c->H <= 0 || c->W <= 0 || !(c->fov != 0.0)) return MUVO_E_ARG;
   if ((int64_t)c->H * c->W > ((int64_t)1 << 30)) return MUVO_E_SHAPE;
   o->H = c->H; o->W = c->W; o->fda = c->fov_down_abs; o->fov = c->fov;
-  o->inv_pi_f = (float)(1.0 / kPi); o->fda_f = (float)c->fov_down_abs; o->inv_fov_f = (float)(1.0 / c->fov);
+  o->half_w = (float)(0.5 * c->W);
+  o->h_scale = (float)(kPi * c->H / c->fov);
+  o->h_bias = (float)((double)c->H * (1.0 - c->fov_down_abs / c->fov));
+  const double sw = (double)c->W / 1024.0, sh = fabs((double)c->H / c->fov) / (64.0 / (40.0 * kPi / 180.0));
+  o->eps_w = (float)(1e-3 * (sw > 1.0 ? sw : 1.0));
+  o->eps_h = (float)(1e-3 * (sh > 1.0 ? sh : 1.0));
+  o->w_hi = (float)c->W - 0.5f; o->h_hi = (float)c->H - 0.5f;
   for (int k = 0; k < 3; ++k) o->L[k] = c->lidar_pos[k];
   return MUVO_OK;
 }
@@ -840,7 +1075,6 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   if (F > 65535) return MUVO_E_SHAPE;   // frames are a grid dimension of the emit kernels
   if (!off || !ws) return MUVO_E_NULL;
   if (P > 0 && (!xyz || !sem)) return MUVO_E_NULL;
-  if (P >= ((int64_t)1 << 40)) return MUVO_E_SHAPE;
   if (do_vox && !dense && !sparse && !n_occ) return MUVO_E_NULL;
   if (do_range && (!xyz_out || (layout == MUVO_RANGE_LAYOUT_HWC && (!depth_out || !sem_out)))) return MUVO_E_NULL;
   if (layout != MUVO_RANGE_LAYOUT_HWC && layout != MUVO_RANGE_LAYOUT_XYZD) return MUVO_E_ARG;
@@ -852,21 +1086,54 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   if (do_range && (rc = make_range_dev(cfg_h, &r)) != MUVO_OK) return rc;
   PointsWs w = carve(ws, P, F, grid_h, cfg_h);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
-  const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 4 == 0);
-  constexpr int KPL = MUVO_KPL;                                  // points per lane (lock-step ILP vs occupancy)
-  const unsigned pblocks = (unsigned)ceil_div64(P, (int64_t)kWarpsPerBlock * 32 * KPL);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 16 == 0);
+  if (P >= ((int64_t)1 << 36)) return MUVO_E_SHAPE;              // exact-path queue entries are 32-bit CTA-relative
   const bool packl = P < ((int64_t)1 << 24) - 1;                 // label rides in the voxel word (24-bit index)
+  // persistent tile kernels: one contiguous run of tiles per CTA, CTAs = SMs x resident CTAs per SM
+  const int64_t n_tiles = ceil_div64(P, kTile);
+  const size_t tsmem = TileLayout<T>::bytes;
+  auto tile_grid = [&](const void* fn, int want_per_sm, unsigned* grid_o) -> int {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTileThreads, tsmem);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    if (g_tuning[0] > 0 && g_tuning[0] < per_sm) per_sm = g_tuning[0];
+    if (want_per_sm > 0 && want_per_sm < per_sm && g_tuning[0] <= 0) per_sm = want_per_sm;
+    int dev = 0, sms = kNumSMsB200;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid > kMaxTileCtas) grid = kMaxTileCtas;
+    *grid_o = (unsigned)(grid > 0 ? grid : 1);
+    return MUVO_OK;
+  };
 
   prof_mark("<points>", st);
   // K1
   if (P > 0) {
-    if (do_vox && do_range)
-      k_point_pass<T, KPL, true, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
-    else if (do_vox)
-      k_point_pass<T, KPL, true, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
-    else
-      k_point_pass<T, KPL, false, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, diag);
-    MUVO_AFTER_LAUNCH("k_point_pass", st);
+    const void* fn;
+    const bool reg = do_vox ? g.regular != 0 : true;
+    if (do_vox && do_range) fn = reg ? (const void*)k_points_tile<T, true, true, true> : (const void*)k_points_tile<T, true, true, false>;
+    else if (do_vox)        fn = reg ? (const void*)k_points_tile<T, true, false, true> : (const void*)k_points_tile<T, true, false, false>;
+    else                    fn = (const void*)k_points_tile<T, false, true, true>;
+    unsigned grid;
+    if ((rc = tile_grid(fn, 0, &grid)) != MUVO_OK) return rc;
+    if (do_vox && do_range) {
+      if (reg) k_points_tile<T, true, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+      else     k_points_tile<T, true, true, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+    } else if (do_vox) {
+      if (reg) k_points_tile<T, true, false, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+      else     k_points_tile<T, true, false, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+    } else {
+      k_points_tile<T, false, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+    }
+    MUVO_AFTER_LAUNCH("k_points_tile", st);
+    if (do_range) {
+      k_range_queued<T><<<grid, 128, 0, st>>>(xyz, off, F, P, r, w.pixtab, w.queue, w.qcount, diag);
+      MUVO_AFTER_LAUNCH("k_range_queued", st);
+    }
   }
   if (do_vox) {
     // K2
@@ -874,12 +1141,23 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     MUVO_AFTER_LAUNCH("k_bitmap_scan", st);
     // K3 (+ K4 when the label does not fit in the slot word)
     if (P > 0) {
+      const bool reg = g.regular != 0;
+      const void* fn = packl ? (reg ? (const void*)k_voxel_tile<T, true, true> : (const void*)k_voxel_tile<T, false, true>)
+                             : (reg ? (const void*)k_voxel_tile<T, true, false> : (const void*)k_voxel_tile<T, false, false>);
+      unsigned grid;
+      if ((rc = tile_grid(fn, 0, &grid)) != MUVO_OK) return rc;
       if (packl) {
-        k_voxel_resolve<T, KPL, true><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot);
-        MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
+        if (reg) k_voxel_tile<T, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
+        else     k_voxel_tile<T, false, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
+        MUVO_AFTER_LAUNCH("k_voxel_tile", st);
+        k_voxel_queued<T, true><<<grid, 128, 0, st>>>(xyz, sem, off, F, P, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
+        MUVO_AFTER_LAUNCH("k_voxel_queued", st);
       } else {
-        k_voxel_resolve<T, KPL, false><<<pblocks, kBlock, 0, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot);
-        MUVO_AFTER_LAUNCH("k_voxel_resolve", st);
+        if (reg) k_voxel_tile<T, true, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
+        else     k_voxel_tile<T, false, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
+        MUVO_AFTER_LAUNCH("k_voxel_tile", st);
+        k_voxel_queued<T, false><<<grid, 128, 0, st>>>(xyz, sem, off, F, P, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
+        MUVO_AFTER_LAUNCH("k_voxel_queued", st);
         k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.vslot, sem, off, F, P);
         MUVO_AFTER_LAUNCH("k_slot_labels", st);
       }
@@ -932,6 +1210,24 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
 using namespace muvo;
 
 extern "C" {
+
+int muvo_debug_pixel_check(const float* xyz, int64_t n_points, const MuvoRangeCfg* cfg_h, int64_t* counts_out, void* stream) {
+  if (!cfg_h || !counts_out || (n_points > 0 && !xyz)) return MUVO_E_NULL;
+  if (n_points < 0) return MUVO_E_ARG;
+  RangeDev r{};
+  int rc = make_range_dev(cfg_h, &r);
+  if (rc != MUVO_OK) return rc;
+  if (n_points == 0) return MUVO_OK;
+  k_debug_pixel_check<<<kNumSMsB200 * 8, kBlock, 0, (cudaStream_t)stream>>>(xyz, n_points, r, reinterpret_cast<unsigned long long*>(counts_out));
+  MUVO_LAUNCH_CHECK();
+  return MUVO_OK;
+}
+
+int muvo_debug_set_tuning(int32_t key, int32_t value) {
+  if (key < 0 || key >= 8) return MUVO_E_ARG;
+  g_tuning[key] = value;
+  return MUVO_OK;
+}
 
 int muvo_points_workspace_bytes(int64_t n_points_total, int32_t n_frames, const MuvoGrid* grid_h,
                                 const MuvoRangeCfg* range_h, size_t* bytes_out_h) {

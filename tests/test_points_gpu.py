@@ -298,3 +298,68 @@ def test_range_near_ties_resolve_exactly(lib):
     d0, x0, s0 = O.range_projection(pts, sem, lidar_position=LIDAR)
     assert np.array_equal(d, d0) and np.array_equal(x, x0) and np.array_equal(s, s0)
     assert (d >= 0).sum() <= 4
+
+
+def test_f32_pixel_path_never_disagrees_with_float64(lib):
+    """The f32 polynomial pixel path may only decide points that the float64 formula puts in the same pixel;
+    everything near a bin edge must be deferred.  40 M points: random directions at all ranges, points generated ON
+    column/row edges (+- a few f32 ulps), and tiny / huge magnitudes."""
+    import ctypes as C
+    rng = torch.Generator(device="cuda").manual_seed(5)
+    d = dev()
+    n = 10_000_000
+    cfgs = [RangeSpec(), RangeSpec(H=128, W=2048, fov_down=-25, fov_up=15, lidar_position=(0.5, -0.25, 1.75))]
+    for spec in cfgs:
+        L = torch.tensor(spec.lidar_position, dtype=torch.float64, device=d)
+        clouds = []
+        # (1) isotropic directions, log-uniform range 0.05 .. 300 m
+        v = torch.randn(n, 3, generator=rng, device=d, dtype=torch.float64)
+        v /= v.norm(dim=1, keepdim=True)
+        rr = torch.exp(torch.empty(n, 1, device=d, dtype=torch.float64).uniform_(np.log(0.05), np.log(300.0), generator=rng))
+        clouds.append(v * rr)
+        # (2) LiDAR-like: pitch inside the FOV, uniform azimuth
+        az = torch.empty(n, device=d, dtype=torch.float64).uniform_(-np.pi, np.pi, generator=rng)
+        pit = torch.empty(n, device=d, dtype=torch.float64).uniform_(np.deg2rad(spec.fov_down - 2), np.deg2rad(spec.fov_up + 2), generator=rng)
+        r2 = torch.empty(n, device=d, dtype=torch.float64).uniform_(0.5, 100.0, generator=rng)
+        clouds.append(torch.stack([r2 * pit.cos() * az.cos(), r2 * pit.cos() * az.sin(), r2 * pit.sin()], 1))
+        # (3) directions exactly on column edges and row edges, perturbed by ~1e-7 relative
+        kcol = torch.randint(0, spec.W + 1, (n,), generator=rng, device=d).double()
+        yaw = np.pi * (1.0 - 2.0 * kcol / spec.W)
+        krow = torch.randint(0, spec.H + 1, (n,), generator=rng, device=d).double()
+        fov = np.deg2rad(spec.fov_up - spec.fov_down)
+        pitch_e = (1.0 - krow / spec.H) * fov - abs(np.deg2rad(spec.fov_down))
+        on_col = torch.stack([r2 * pit.cos() * yaw.cos(), r2 * pit.cos() * yaw.sin(), r2 * pit.sin()], 1)
+        on_row = torch.stack([r2 * pitch_e.cos() * az.cos(), r2 * pitch_e.cos() * az.sin(), r2 * pitch_e.sin()], 1)
+        jit = 1.0 + 2e-7 * torch.randn(n, 3, generator=rng, device=d, dtype=torch.float64)
+        clouds.append(on_col * jit)
+        clouds.append(on_row * jit)
+        counts = torch.zeros(4, dtype=torch.int64, device=d)
+        cfg = spec.to_c()
+        for c in clouds:
+            # LiDAR frame -> ego frame as the reference inverts it (geometry_utils.py:177-178): x + L0, -(y + L1), z + L2
+            ego = torch.stack([c[:, 0] + L[0], -(c[:, 1] + L[1]), c[:, 2] + L[2]], 1).float().contiguous()
+            rc = lib.muvo_debug_pixel_check(ego.data_ptr(), ego.shape[0], C.byref(cfg), counts.data_ptr(),
+                                            torch.cuda.current_stream().cuda_stream)
+            assert rc == 0
+        # extreme magnitudes must all be deferred or dropped, never decided in f32
+        ext = torch.tensor([[1e-20, 1e-20, 1e-20], [1e19, 1e19, 1e19], [3e38, 0, 0], [1e-30, 0, 1e-10]], device=d).float()
+        ext = (ext * torch.tensor([1.0, -1.0, 1.0], device=d) + L.float() * torch.tensor([1.0, -1.0, 1.0], device=d)).contiguous()
+        c_ext = torch.zeros(4, dtype=torch.int64, device=d)
+        assert lib.muvo_debug_pixel_check(ext.data_ptr(), ext.shape[0], C.byref(cfg), c_ext.data_ptr(),
+                                          torch.cuda.current_stream().cuda_stream) == 0
+        assert c_ext[2].item() == 0
+        n_fast, n_slow, n_bad, n_drop = counts.tolist()
+        assert n_bad == 0
+        assert n_fast + n_slow + n_drop == 4 * n
+        # clouds (1)+(2) are generic: only a small fraction may take the float64 path
+        assert n_slow < 0.6 * 4 * n and n_fast > 0.4 * 4 * n
+    # generic clouds alone: deferral rate is 2*eps per axis (~0.4 %)
+    counts = torch.zeros(4, dtype=torch.int64, device=d)
+    spec = RangeSpec()
+    cfg = spec.to_c()
+    pts, _ = synth.carla_lidar_frame(200000, 77)
+    ego = torch.from_numpy(pts).to(d)
+    assert lib.muvo_debug_pixel_check(ego.data_ptr(), ego.shape[0], C.byref(cfg), counts.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream) == 0
+    n_fast, n_slow, n_bad, n_drop = counts.tolist()
+    assert n_bad == 0 and n_slow < 0.02 * 200000

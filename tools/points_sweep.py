@@ -1,0 +1,56 @@
+"""cfg2 step, per-kernel CUDA-event times for several values of a tuning knob:
+python tools/points_sweep.py [--key 0] [--values 0,2,3,4,5,6] [--frames 96]"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from muvo_b200 import _lib, synth  # noqa: E402
+from muvo_b200.points import GridSpec, RangeSpec, sensor_to_grid  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--key", type=int, default=0)
+ap.add_argument("--values", default="0,2,3,4,5,6")
+ap.add_argument("--frames", type=int, default=96)
+ap.add_argument("--nmin", type=int, default=60000)
+ap.add_argument("--nmax", type=int, default=100000)
+ap.add_argument("--reps", type=int, default=10)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+lib = _lib.load()
+pts, sem, off = synth.lidar_batch(a.frames, a.nmin, a.nmax, 2000)
+tp, ts, to = torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev), torch.from_numpy(off).to(dev)
+remap = torch.from_numpy(synth.label_remap256()).to(dev)
+stream = _lib.current_stream(dev)
+out = {}
+
+
+def step():
+    global out
+    r = sensor_to_grid(tp, ts, to, grid=GridSpec(), range_spec=RangeSpec(lidar_position=(1.0, 0.0, 2.0)), remap=remap,
+                       layout="xyzd", out=out)
+    out = {k: r[k] for k in ("voxel", "n_occ", "range_xyzd", "range_sem")}
+
+
+for v in [int(x) for x in a.values.split(",")]:
+    lib.muvo_debug_set_tuning(a.key, v)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    acc = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    for _ in range(a.reps):
+        with _lib.profile(stream) as p:
+            step()
+        for i, (k, ms) in enumerate(p.kernels):
+            acc.setdefault((i, k), []).append(ms)
+    parts = "  ".join(f"{k}={1e3 * sum(x) / len(x):.1f}" for (i, k), x in sorted(acc.items()))
+    print(f"knob{a.key}={v}: step {1e3 * e0.elapsed_time(e1) / a.reps:.1f} us | {parts}", flush=True)
+lib.muvo_debug_set_tuning(a.key, 0)
