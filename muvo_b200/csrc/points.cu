@@ -30,7 +30,11 @@
 //                         write of the range image.  Emit kernels put every table entry they consume back
 //                         to 0, so the workspace is clean for the next call.
 #include <math.h>
+#include <cooperative_groups.h>
+#include <type_traits>
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace muvo {
 
@@ -68,6 +72,9 @@ struct RangeDev {
   float half_w, h_scale, h_bias;
   float eps_w, eps_h;     // distance to a bin edge (in bins) below which the float64 formula decides
   float w_hi, h_hi;       // W - 0.5, H - 0.5: beyond these (or below 0.5) both paths clamp to the border bin
+  float w_max, h_max;     // W - 1, H - 1
+  float Lf[3];            // sensor position in f32
+  int lf_exact;           // ... and whether that is exact
 };
 
 typedef unsigned long long u64;
@@ -198,23 +205,28 @@ __device__ __forceinline__ double atan2_np(double y, double x) {
 }
 
 // voxel id for a "regular" grid (power-of-two res, upper == size*res): floor((p+off)/res) is exact, so
-// 0 <= b < upper  <=>  0 <= floor(b/res) < size  (:178,:183); NaN coordinates fail x == x.
-struct VoxFast { uint32_t bit; bool in; double bx, by, bz; int ix, iy, iz; };
+// 0 <= b < upper  <=>  0 <= floor(b/res) < size  (:178,:183).  The floor comes from the "add 2^52, round down" trick:
+// for 0 <= q < 2^32 the sum stays in [2^52, 2^52 + 2^32), i.e. its high word is exactly 0x43300000 and its low word
+// is floor(q); negative, huge, infinite or NaN q change the high word.  No f64 -> int conversions (quarter-rate pipe).
+constexpr double kTwo52 = 4503599627370496.0;
+struct VoxFast { uint32_t bit; bool in; double bx, by, bz, sx, sy, sz; };
 template <typename T>
 __device__ __forceinline__ VoxFast vox_regular(T x, T y, T z, const GridDev& g) {
   VoxFast v;
   v.bx = (double)x + g.off[0]; v.by = (double)y + g.off[1]; v.bz = (double)z + g.off[2];   // :177
-  v.ix = __double2int_rd(v.bx * g.inv_res); v.iy = __double2int_rd(v.by * g.inv_res); v.iz = __double2int_rd(v.bz * g.inv_res);
-  v.in = ((unsigned)v.ix < (unsigned)g.dx) & ((unsigned)v.iy < (unsigned)g.dy) & ((unsigned)v.iz < (unsigned)g.dz) &
-         (x == x) & (y == y) & (z == z);
-  v.bit = (g.order == ORDER_DENSE) ? (uint32_t)((v.ix * g.dy + v.iy) * g.dz + v.iz)
-                                   : (uint32_t)(v.ix + g.dx * (v.iy + g.dy * v.iz));
+  v.sx = __dadd_rd(v.bx * g.inv_res, kTwo52); v.sy = __dadd_rd(v.by * g.inv_res, kTwo52); v.sz = __dadd_rd(v.bz * g.inv_res, kTwo52);
+  const uint32_t ix = (uint32_t)__double2loint(v.sx), iy = (uint32_t)__double2loint(v.sy), iz = (uint32_t)__double2loint(v.sz);
+  v.in = (__double2hiint(v.sx) == 0x43300000) & (__double2hiint(v.sy) == 0x43300000) & (__double2hiint(v.sz) == 0x43300000) &
+         (ix < (uint32_t)g.dx) & (iy < (uint32_t)g.dy) & (iz < (uint32_t)g.dz);
+  v.bit = (g.order == ORDER_DENSE) ? (ix * (uint32_t)g.dy + iy) * (uint32_t)g.dz + iz
+                                   : ix + (uint32_t)g.dx * (iy + (uint32_t)g.dy * iz);
   return v;
 }
-// |p mod res|^2 for a regular grid: b - floor(b/res)*res is exact (fma == mul + sub here), then numpy's
-// (mx^2 + my^2) + mz^2 with separate roundings (:212)
+// |p mod res|^2 for an in-grid point of a regular grid: b - floor(b/res)*res is exact (so the fma equals numpy's
+// mul + sub), then numpy's (mx^2 + my^2) + mz^2 with separate roundings (:212)
 __device__ __forceinline__ double vox_regular_dis(const VoxFast& v, const GridDev& g) {
-  double mx = v.bx - (double)v.ix * g.res, my = v.by - (double)v.iy * g.res, mz = v.bz - (double)v.iz * g.res;
+  const double mx = __fma_rn(kTwo52 - v.sx, g.res, v.bx), my = __fma_rn(kTwo52 - v.sy, g.res, v.by),
+               mz = __fma_rn(kTwo52 - v.sz, g.res, v.bz);
   return (mx * mx + my * my) + mz * mz;
 }
 
@@ -269,7 +281,9 @@ __device__ __forceinline__ float atan_over_pi_unit(float t) {
 __device__ __forceinline__ float atan2_over_pi(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mn = fminf(ax, ay), mx = fmaxf(ax, ay);
-  float p = atan_over_pi_unit(__fdividef(mn, mx));
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));
+  float p = atan_over_pi_unit(__fmul_rn(mn, rc));
   if (ay > ax) p = 0.5f - p;
   if (x < 0.f) p = 1.0f - p;
   return copysignf(p, y);
@@ -285,10 +299,15 @@ __device__ __forceinline__ PixFast pix_fast(T x, T y, T z, const RangeDev& r) {
   k.s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
   const uint32_t hi = (uint32_t)__double2hiint(k.s);
   k.ok = (k.s > 0.0) & (hi < 0x7ff00000u);
-  const float xf = (float)xc, yf = (float)(-yc), zf = (float)zc;
+  float xf, yf, zf;
+  if (sizeof(T) == 4 && r.lf_exact) {   // sensor position exact in f32: the f32 difference is the correctly rounded one
+    xf = (float)x - r.Lf[0]; yf = -((-(float)y) - r.Lf[1]); zf = (float)z - r.Lf[2];   // same zero signs as :177-183
+  } else {
+    xf = (float)xc; yf = (float)(-yc); zf = (float)zc;
+  }
   const float pw = __fmul_rn(1.0f - atan2_over_pi(yf, xf), r.half_w);
   float rho;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(rho) : "f"(__fmaf_rn(xf, xf, __fmul_rn(yf, yf))));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rho) : "f"(__fmaf_rn(xf, xf, __fmul_rn(yf, yf))));
   const float ph = __fmaf_rn(-atan2_over_pi(zf, rho), r.h_scale, r.h_bias);
   const float fw = floorf(pw), fh = floorf(ph);
   const float dw = pw - fw, dh = ph - fh;
@@ -297,8 +316,8 @@ __device__ __forceinline__ PixFast pix_fast(T x, T y, T z, const RangeDev& r) {
   // 1e-12 < s < 1e12 (metres^2): inside, no f32 square over/underflows in a way that could move a pixel
   const bool mag_ok = (hi - 0x3d719799u) < (0x426d1a94u - 0x3d719799u);
   k.slow = !(safe_w & safe_h & mag_ok);     // NaN compares false -> slow
-  const int iw = (int)fminf(fmaxf(fw, 0.0f), (float)(r.W - 1));
-  const int ih = (int)fminf(fmaxf(fh, 0.0f), (float)(r.H - 1));
+  const int iw = (int)fminf(fmaxf(fw, 0.0f), r.w_max);
+  const int ih = (int)fminf(fmaxf(fh, 0.0f), r.h_max);
   k.pix = ih * r.W + iw;
   return k;
 }
@@ -326,9 +345,15 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// read-once stream: evict-first in L2 so that the L2-resident tables (bitmap, pixel words, slots) survive next to it
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -371,9 +396,10 @@ __device__ __forceinline__ void tile_issue(const T* __restrict__ xyz, const uint
                                            unsigned char* smem, int st) {
   using L = TileLayout<T>;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::off_bar) + st;
+  const uint64_t pol = l2_evict_first_policy();
   mbar_expect_tx(bar, (uint32_t)(L::xyz_bytes + kTile));
-  bulk_g2s(smem + (size_t)st * L::xyz_bytes, xyz + 3 * base, (uint32_t)L::xyz_bytes, bar);
-  bulk_g2s(smem + L::off_sem + (size_t)st * kTile, sem + base, (uint32_t)kTile, bar);
+  bulk_g2s(smem + (size_t)st * L::xyz_bytes, xyz + 3 * base, (uint32_t)L::xyz_bytes, bar, pol);
+  bulk_g2s(smem + L::off_sem + (size_t)st * kTile, sem + base, (uint32_t)kTile, bar, pol);
 }
 
 // Tile iterator shared by K1 and K3 (all members are CTA-uniform).
@@ -481,162 +507,102 @@ __device__ __noinline__ void tie_protocol(u64* slot, uint32_t top_inv, uint32_t 
   }
 }
 
-// ---------------------------------------------------------------- K2: bitmap scan (one CTA per frame)
-constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads)
-k_bitmap_scan(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw, int64_t* __restrict__ n_occ_out) {
-  __shared__ uint32_t warp_tot[kScanThreads / 32];
-  __shared__ uint32_t carry_s;
-  const int f = blockIdx.x;
-  const int chunks = gw / 4;
-  const uint4* bm = reinterpret_cast<const uint4*>(bitmap + (size_t)f * gw);
-  uint32_t* pf = prefix + (size_t)f * chunks;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  constexpr int kPer = 4;  // chunks per thread per tile (64 contiguous bytes)
-  for (int base = 0; base < chunks; base += kScanThreads * kPer) {
-    int c0 = base + threadIdx.x * kPer;
-    uint32_t cnt[kPer];
-    uint32_t tsum = 0;
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      uint32_t c = 0;
-      if (c0 + k < chunks) { uint4 v = bm[c0 + k]; c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
-      cnt[k] = c; tsum += c;
-    }
-    uint32_t incl = tsum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    uint32_t carry = carry_s;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_tot[lane];
-      uint32_t wi = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += t; }
-      warp_tot[lane] = wi - w;   // exclusive warp offsets
-      if (lane == 31) carry_s = carry + wi;
-    }
-    __syncthreads();
-    uint32_t ex = carry + warp_tot[warp] + (incl - tsum);
-#pragma unroll
-    for (int k = 0; k < kPer; ++k) {
-      if (c0 + k < chunks) pf[c0 + k] = ex;
-      ex += cnt[k];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && n_occ_out) n_occ_out[f] = (int64_t)carry_s;
-}
+// ---------------------------------------------------------------- K2: bitmap scan (+ K1q: range-image queue)
+// One thread-block CLUSTER of 8 CTAs per frame: every CTA counts the set bits of its eighth of the frame bitmap,
+// the eight totals are exchanged through distributed shared memory, and every CTA then writes the exclusive
+// popcount prefix of its 128-bit chunks.  The same launch carries the CTAs that finish K1's rare-path queue
+// (the two jobs are independent and both latency bound, so they share the machine instead of serialising).
+constexpr int kScanCluster = 8;
+constexpr int kScanThreads = 256;
 
-// rank of set bit `bit` within its frame (= number of set bits before it)
-__device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_f, const uint32_t* __restrict__ prefix_f,
-                                            uint32_t bit) {
-  uint32_t chunk = bit >> 7;
-  uint4 v = *reinterpret_cast<const uint4*>(bitmap_f + chunk * 4);
-  uint32_t w = (bit >> 5) & 3u;
-  uint32_t below = 0;
-  uint32_t word = v.x;
-  if (w >= 1) { below += __popc(v.x); word = v.y; }
-  if (w >= 2) { below += __popc(v.y); word = v.z; }
-  if (w >= 3) { below += __popc(v.z); word = v.w; }
-  below += __popc(word & ((1u << (bit & 31)) - 1u));
-  return prefix_f[chunk] + below;
-}
-
-// ---------------------------------------------------------------- K1: point pass
-// CTA's tile range, shared by the tile kernels and the queue kernels (same grid size)
-__device__ __forceinline__ void cta_tile_range(int64_t P, int* t0, int* t1) {
+__device__ __forceinline__ void cta_tile_range(int64_t P, int n_ctas, int cta, int* t0, int* t1) {
   const int64_t n_tiles = ceil_div64(P, kTile);
-  const int64_t per = ceil_div64(n_tiles, (int64_t)gridDim.x);
-  const int64_t a = (int64_t)blockIdx.x * per;
+  const int64_t per = ceil_div64(n_tiles, (int64_t)n_ctas);
+  const int64_t a = (int64_t)cta * per;
   *t0 = (int)(a < n_tiles ? a : n_tiles);
   *t1 = (int)(a + per < n_tiles ? a + per : n_tiles);
 }
 
-template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
-__global__ void __launch_bounds__(kTileThreads, 4)
-k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
-              uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ diag) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  using L = TileLayout<T>;
-  Tiles<T> tl;
-  if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
-    if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
-    return;
+__device__ __forceinline__ void scan_role(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw,
+                                          int64_t* __restrict__ n_occ_out) {
+  __shared__ uint32_t totals[kScanCluster];
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
+  __shared__ uint32_t carry_s;
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned rank = cluster.block_rank();
+  const int f = blockIdx.x / kScanCluster;
+  const int per = (gw / 4) / kScanCluster;                       // gw % 32 == 0 -> chunks % 8 == 0
+  const int c_begin = (int)rank * per, c_end = c_begin + per;
+  const uint4* bm = reinterpret_cast<const uint4*>(bitmap + (size_t)f * gw);
+  uint32_t* pf = prefix + (size_t)f * (gw / 4);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // phase 1: set bits of this CTA's range
+  uint32_t cnt = 0;
+  for (int c = c_begin + tid; c < c_end; c += kScanThreads) {
+    const uint4 v = bm[c];
+    cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
   }
-  uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
-  const int tid = threadIdx.x;
-  const int64_t blk_first = (int64_t)tl.t0 * kTile;
-  uint2* q = queue + blk_first;
-  const int64_t HW = (int64_t)r.H * r.W;
-  unsigned n_drop = 0, n_in = 0;
-
-  while (tl.next()) {
-    u64* slot[kKPL];
-    u64 mine[kKPL], old[kKPL];
-    bool act[kKPL];
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if (lane == 0) warp_tot[warp] = cnt;
+  __syncthreads();
+  if (tid < kScanCluster) {                                      // thread k posts this CTA's total into CTA k
+    uint32_t tot = 0;
 #pragma unroll
-    for (int k = 0; k < kKPL; ++k) {
-      const int j = k * kTileThreads + tid;
-      const int64_t i = tl.base + j;
-      T x, y, z; uint32_t lab;
-      const bool valid = tl.load(j, &x, &y, &z, &lab);
-      int fk; int64_t fb;
-      tl.frame_of(i, &fk, &fb);
-      act[k] = false; slot[k] = pixtab; mine[k] = 0ull;
-      if (DO_VOX && valid) {
-        uint32_t bit; bool in;
-        if (REG) { VoxFast v = vox_regular(x, y, z, g); bit = v.bit; in = v.in; }
-        else { VoxKey v = vox_of<false>((double)x, (double)y, (double)z, g); bit = v.bit; in = v.in; }
-        if (in) {
-          ++n_in;
-          atomicOr(bitmap + (size_t)fk * g.gw + (bit >> 5), 1u << (bit & 31));   // RED, no return value
-        }
-      }
-      if (DO_RANGE && valid) {
-        const PixFast pk = pix_fast(x, y, z, r);
-        if (!pk.ok) ++n_drop;
-        else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2((uint32_t)(i - blk_first), kQExact);
-        else {
-          act[k] = true;
-          slot[k] = pixtab + (size_t)fk * HW + pk.pix;
-          // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
-          mine[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), (uint32_t)(i - fb) + 1u);
-        }
-      }
+    for (int w = 0; w < kScanThreads / 32; ++w) tot += warp_tot[w];
+    cluster.map_shared_rank(totals, tid)[rank] = tot;
+  }
+  cluster.sync();
+  uint32_t base = 0, all = 0;
+#pragma unroll
+  for (int k = 0; k < kScanCluster; ++k) { const uint32_t t = totals[k]; all += t; if (k < (int)rank) base += t; }
+  if (tid == 0) carry_s = base;
+  __syncthreads();
+  // phase 2: exclusive prefix per chunk (the second read of the range comes from L1/L2)
+  constexpr int kPer = 4;   // chunks per thread per round (64 contiguous bytes)
+  for (int c0r = c_begin; c0r < c_end; c0r += kScanThreads * kPer) {
+    const int c0 = c0r + tid * kPer;
+    uint32_t pc[kPer];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      uint32_t c = 0;
+      if (c0 + k < c_end) { const uint4 v = bm[c0 + k]; c = __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+      pc[k] = c; tsum += c;
     }
-    if (DO_RANGE) {
+    uint32_t incl = tsum;
 #pragma unroll
-      for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    uint32_t wbase = 0;
 #pragma unroll
-      for (int k = 0; k < kKPL; ++k) {
-        if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))   // same top-32 class: exact protocol
-          q[atomicAdd(qn, 1u)] = make_uint2((uint32_t)(tl.base + k * kTileThreads + tid - blk_first), word_idx1(old[k]));
-      }
+    for (int w = 0; w < kScanThreads / 32; ++w) if (w < warp) wbase += warp_tot[w];
+    __syncthreads();
+    if (tid == kScanThreads - 1) carry_s = carry + wbase + incl;
+    uint32_t ex = carry + wbase + (incl - tsum);
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      if (c0 + k < c_end) pf[c0 + k] = ex;
+      ex += pc[k];
     }
-    __syncthreads();                         // tile buffer free for the copy issued by the next next()
+    __syncthreads();
   }
-  if (tid == 0) qcount[blockIdx.x] = *qn;
-  if (diag) {
-    if (DO_RANGE) diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
-    if (DO_VOX) diag_add(diag, MUVO_DIAG_IN_GRID, n_in);
-  }
+  if (rank == 0 && tid == 0 && n_occ_out) n_occ_out[f] = (int64_t)all;
 }
 
-// K1q: finishes the range-image queue.  Same grid as K1.
+// One queued point of the range image: kQExact = the reference's float64 formula decides the pixel and the atomicMax
+// happens here; otherwise the f32 pixel stands and the atomicMax already met a same-class holder (exact tie protocol).
 template <typename T>
-__global__ void __launch_bounds__(128)
-k_range_queued(const T* __restrict__ xyz, const int64_t* __restrict__ off, int F, int64_t P, RangeDev r, u64* __restrict__ pixtab,
-               const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount, int64_t* __restrict__ diag) {
-  const uint32_t n = qcount[blockIdx.x];
+__device__ __forceinline__ void range_queue_role(int cta, int n_tile_ctas, const T* __restrict__ xyz, const int64_t* __restrict__ off,
+                                                 int F, int64_t P, const RangeDev& r, u64* __restrict__ pixtab,
+                                                 const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount,
+                                                 int64_t* __restrict__ diag) {
+  if (cta >= n_tile_ctas) return;
+  const uint32_t n = qcount[cta];
   if (n == 0u) return;   // CTA-uniform
   int t0, t1;
-  cta_tile_range(P, &t0, &t1);
+  cta_tile_range(P, n_tile_ctas, cta, &t0, &t1);
   const int64_t blk_first = (int64_t)t0 * kTile;
   const uint2* q = queue + blk_first;
   unsigned n_drop = 0, n_nw = 0, n_nh = 0;
@@ -647,7 +613,7 @@ k_range_queued(const T* __restrict__ xyz, const int64_t* __restrict__ off, int F
     double xc, yc, zc;
     const double s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
     int pix;
-    if (ent.y == kQExact) {   // the reference's float64 formula decides the pixel
+    if (ent.y == kQExact) {
       int iw, ih, flags;
       pix_exact(xc, yc, zc, s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
       if (flags & 4) { ++n_drop; continue; }
@@ -662,7 +628,7 @@ k_range_queued(const T* __restrict__ xyz, const int64_t* __restrict__ off, int F
     const uint32_t top = key_top_inv((u64)__double_as_longlong(s));
     const uint32_t me1 = (uint32_t)(i - fb) + 1u;
     const u64 mine = pack_word(top, me1);
-    u64 old_word = (ent.y == kQExact) ? atomicMax(slot, mine) : pack_word(top, ent.y);
+    const u64 old_word = (ent.y == kQExact) ? atomicMax(slot, mine) : pack_word(top, ent.y);
     if (old_word != 0ull && word_top(old_word) == top) {
       const T* fx = xyz + 3 * fb;
       auto key_of = [&](uint32_t q1) -> u64 {     // exact key: the float64 depth (geometry_utils.py:180)
@@ -683,7 +649,155 @@ k_range_queued(const T* __restrict__ xyz, const int64_t* __restrict__ off, int F
   }
 }
 
+// grid = n_scan_frames * 8 scan CTAs, then the queue CTAs (padded to a multiple of the cluster size)
+template <typename T>
+__global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThreads)
+k_scan_queue(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw, int n_scan_frames,
+             int64_t* __restrict__ n_occ_out, const T* __restrict__ xyz, const int64_t* __restrict__ off, int F, int64_t P,
+             RangeDev r, u64* __restrict__ pixtab, const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount,
+             int n_tile_ctas, int64_t* __restrict__ diag) {
+  const int scan_ctas = n_scan_frames * kScanCluster;
+  if ((int)blockIdx.x < scan_ctas) scan_role(bitmap, prefix, gw, n_occ_out);
+  else range_queue_role<T>((int)blockIdx.x - scan_ctas, n_tile_ctas, xyz, off, F, P, r, pixtab, queue, qcount, diag);
+}
+
+// rank of set bit `bit` within its frame (= number of set bits before it)
+__device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_f, const uint32_t* __restrict__ prefix_f,
+                                            uint32_t bit) {
+  uint32_t chunk = bit >> 7;
+  uint4 v = *reinterpret_cast<const uint4*>(bitmap_f + chunk * 4);
+  uint32_t w = (bit >> 5) & 3u;
+  uint32_t below = 0;
+  uint32_t word = v.x;
+  if (w >= 1) { below += __popc(v.x); word = v.y; }
+  if (w >= 2) { below += __popc(v.y); word = v.z; }
+  if (w >= 3) { below += __popc(v.z); word = v.w; }
+  below += __popc(word & ((1u << (bit & 31)) - 1u));
+  return prefix_f[chunk] + below;
+}
+
+// ---------------------------------------------------------------- K1: point pass
+template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
+__global__ void __launch_bounds__(kTileThreads, 4)
+k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
+              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
+              uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ diag) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  using L = TileLayout<T>;
+  Tiles<T> tl;
+  if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
+    if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
+    return;
+  }
+  uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
+  const int tid = threadIdx.x;
+  const int64_t blk_first = (int64_t)tl.t0 * kTile;
+  uint2* q = queue + blk_first;
+  const int64_t HW = (int64_t)r.H * r.W;
+  unsigned n_drop = 0, n_in = 0;
+
+  const unsigned lane = lane_id();
+  while (tl.next()) {
+    // FAST = the tile is staged in shared memory and lies inside one frame (all but a handful of tiles): frame
+    // bases, table rows and the shared-memory cursor are CTA-uniform and hoisted out of the per-point code.
+    auto body = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+      const T* sx = reinterpret_cast<const T*>(smem + (size_t)tl.st * L::xyz_bytes) + 3 * tid;
+      const uint8_t* ss = smem + L::off_sem + (size_t)tl.st * kTile + tid;
+      uint32_t* bitmap_f = bitmap + (size_t)tl.f * g.gw;
+      u64* pixtab_f = pixtab + (size_t)tl.f * HW;
+      const uint32_t idx1_0 = (uint32_t)(tl.base - tl.fbeg) + (uint32_t)tid + 1u;     // 1-based frame-relative index, k = 0
+      const uint32_t rel_0 = (uint32_t)(tl.base - blk_first) + (uint32_t)tid;         // CTA-relative index, k = 0
+      u64* slot[kKPL];
+      u64 mine[kKPL], old[kKPL];
+      bool act[kKPL];
+#pragma unroll
+      for (int k = 0; k < kKPL; ++k) {
+        T x, y, z; uint32_t lab;
+        bool valid = true;
+        int fk = tl.f; int64_t fb = tl.fbeg;
+        if (FAST) {
+          x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
+          lab = ss[k * kTileThreads];
+        } else {
+          valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
+          tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
+        }
+        (void)lab;
+        act[k] = false; slot[k] = pixtab; mine[k] = 0ull;
+        if (DO_VOX) {
+          uint32_t bit = 0xffffffffu; bool in = false;
+          if (valid) {
+            if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; if (in) bit = v.bit; }
+            else { VoxKey v = vox_of<false>((double)x, (double)y, (double)z, g); in = v.in; if (in) bit = v.bit; }
+          }
+          // scan-ordered clouds put runs of consecutive points into one voxel: only the first lane of a run sets the bit
+          const uint32_t bit_prev = __shfl_up_sync(0xffffffffu, bit, 1);
+          bool dup = lane > 0 && bit == bit_prev;
+          if (!FAST) { const int fk_prev = __shfl_up_sync(0xffffffffu, fk, 1); dup = dup && fk == fk_prev; }
+          if (in) {
+            ++n_in;
+            uint32_t* bm = FAST ? bitmap_f : bitmap + (size_t)fk * g.gw;
+            if (!dup) atomicOr(bm + (bit >> 5), 1u << (bit & 31));   // RED, no return value
+          }
+        }
+        if (DO_RANGE && valid) {
+          const PixFast pk = pix_fast(x, y, z, r);
+          if (!pk.ok) ++n_drop;
+          else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, kQExact);
+          else {
+            act[k] = true;
+            slot[k] = (FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix;
+            // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
+            const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
+            mine[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), me1);
+          }
+        }
+      }
+      if (DO_RANGE) {
+#pragma unroll
+        for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+#pragma unroll
+        for (int k = 0; k < kKPL; ++k) {
+          if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))   // same top-32 class: exact protocol
+            q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, word_idx1(old[k]));
+        }
+      }
+    };
+    if (tl.full && tl.one_frame) body(std::true_type{}); else body(std::false_type{});
+    __syncthreads();                         // tile buffer free for the copy issued by the next next()
+  }
+  if (tid == 0) qcount[blockIdx.x] = *qn;
+  if (diag) {
+    if (DO_RANGE) diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
+    if (DO_VOX) diag_add(diag, MUVO_DIAG_IN_GRID, n_in);
+  }
+}
+
 // ---------------------------------------------------------------- K3: voxel resolve
+// Scan-ordered clouds put runs of consecutive points (= adjacent lanes) into one voxel.  Within such a run only the
+// lanes holding the run's best top-32 key class (usually exactly one) still have to compete for the slot; the others
+// could never win it.  Returns that predicate (segmented max-scan over the run with shuffles).
+template <bool ONE_FRAME>
+__device__ __forceinline__ bool run_leader(bool in, uint32_t bit /* 0xffffffff when !in */, int fk, uint32_t top_inv) {
+  const unsigned lane = lane_id();
+  const uint32_t bit_prev = __shfl_up_sync(0xffffffffu, bit, 1);
+  bool joins = in && lane > 0 && bit == bit_prev;
+  if (!ONE_FRAME) { const int fk_prev = __shfl_up_sync(0xffffffffu, fk, 1); joins = joins && fk == fk_prev; }
+  const unsigned heads = __ballot_sync(0xffffffffu, !joins);                 // bit 0 is always set
+  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));         // head of this lane's run
+  uint32_t v = in ? top_inv : 0u;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+    if ((int)lane - d >= start) v = v > t ? v : t;
+  }
+  const unsigned rest = lane == 31 ? 0u : (heads >> (lane + 1));
+  const int end = rest ? (int)lane + __ffs(rest) - 1 : 31;                   // last lane of the run
+  const uint32_t best = __shfl_sync(0xffffffffu, v, end);
+  return in && top_inv == best;
+}
+
 // PACKL: the slot word also carries the point's label (needs < 2^24 points per frame); otherwise the label pass
 // (k_slot_labels) fills it in afterwards.
 template <typename T, bool REG, bool PACKL>
@@ -703,39 +817,55 @@ k_voxel_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const i
   const int64_t blk_first = (int64_t)tl.t0 * kTile;
   uint2* q = queue + blk_first;
   while (tl.next()) {
-    u64* slot[kKPL];
-    u64 mine[kKPL], old[kKPL];
-    bool act[kKPL];
+    auto body = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+      const T* sx = reinterpret_cast<const T*>(smem + (size_t)tl.st * L::xyz_bytes) + 3 * tid;
+      const uint8_t* ss = smem + L::off_sem + (size_t)tl.st * kTile + tid;
+      const uint32_t* bitmap_f = bitmap + (size_t)tl.f * g.gw;
+      const uint32_t* prefix_f = prefix + (size_t)tl.f * (g.gw / 4);
+      u64* vslot_f = vslot + tl.fbeg;
+      const uint32_t idx1_0 = (uint32_t)(tl.base - tl.fbeg) + (uint32_t)tid + 1u;
+      const uint32_t rel_0 = (uint32_t)(tl.base - blk_first) + (uint32_t)tid;
+      u64* slot[kKPL];
+      u64 mine[kKPL], old[kKPL];
+      bool act[kKPL];
 #pragma unroll
-    for (int k = 0; k < kKPL; ++k) {
-      const int j = k * kTileThreads + tid;
-      const int64_t i = tl.base + j;
-      T x, y, z; uint32_t lab;
-      const bool valid = tl.load(j, &x, &y, &z, &lab);
-      int fk; int64_t fb;
-      tl.frame_of(i, &fk, &fb);
-      act[k] = false; slot[k] = vslot; mine[k] = 0ull;
-      if (valid) {
-        uint32_t bit; bool in; double dis;
-        if (REG) { VoxFast v = vox_regular(x, y, z, g); bit = v.bit; in = v.in; dis = vox_regular_dis(v, g); }
-        else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); bit = v.bit; in = v.in; dis = v.dis; }
-        if (in) {
+      for (int k = 0; k < kKPL; ++k) {
+        T x, y, z; uint32_t lab;
+        bool valid = true;
+        int fk = tl.f; int64_t fb = tl.fbeg;
+        if (FAST) {
+          x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
+          lab = ss[k * kTileThreads];
+        } else {
+          valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
+          tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
+        }
+        act[k] = false; slot[k] = vslot; mine[k] = 0ull;
+        uint32_t bit = 0xffffffffu, top = 0; bool in = false;
+        if (valid) {
+          double dis;
+          if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) bit = v.bit; }
+          else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); in = v.in; dis = v.dis; if (in) bit = v.bit; }
+          top = key_top_inv(vox_key(dis, (int)lab != g.road));
+        }
+        if (run_leader<FAST>(in, bit, fk, top)) {
           act[k] = true;
-          const uint32_t top = key_top_inv(vox_key(dis, (int)lab != g.road));
-          const uint32_t me1 = (uint32_t)(i - fb) + 1u;
+          const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
           mine[k] = PACKL ? pack_vox(top, me1, lab) : pack_word(top, me1);
-          slot[k] = vslot + fb + rank_of(bitmap + (size_t)fk * g.gw, prefix + (size_t)fk * (g.gw / 4), bit);
+          slot[k] = FAST ? vslot_f + rank_of(bitmap_f, prefix_f, bit)
+                         : vslot + fb + rank_of(bitmap + (size_t)fk * g.gw, prefix + (size_t)fk * (g.gw / 4), bit);
         }
       }
-    }
 #pragma unroll
-    for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
+      for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
 #pragma unroll
-    for (int k = 0; k < kKPL; ++k) {
-      if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))
-        q[atomicAdd(qn, 1u)] = make_uint2((uint32_t)(tl.base + k * kTileThreads + tid - blk_first),
-                                          PACKL ? vox_idx1(old[k]) : word_idx1(old[k]));
-    }
+      for (int k = 0; k < kKPL; ++k) {
+        if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))
+          q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, PACKL ? vox_idx1(old[k]) : word_idx1(old[k]));
+      }
+    };
+    if (tl.full && tl.one_frame) body(std::true_type{}); else body(std::false_type{});
     __syncthreads();
   }
   if (tid == 0) qcount[blockIdx.x] = *qn;
@@ -750,7 +880,7 @@ k_voxel_queued(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const
   const uint32_t n = qcount[blockIdx.x];
   if (n == 0u) return;
   int t0, t1;
-  cta_tile_range(P, &t0, &t1);
+  cta_tile_range(P, (int)gridDim.x, (int)blockIdx.x, &t0, &t1);
   const int64_t blk_first = (int64_t)t0 * kTile;
   const uint2* q = queue + blk_first;
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
@@ -1057,6 +1187,9 @@ static int make_range_dev(const MuvoRangeCfg* c, RangeDev* o) {
   o->eps_w = (float)(1e-3 * (sw > 1.0 ? sw : 1.0));
   o->eps_h = (float)(1e-3 * (sh > 1.0 ? sh : 1.0));
   o->w_hi = (float)c->W - 0.5f; o->h_hi = (float)c->H - 0.5f;
+  o->w_max = (float)(c->W - 1); o->h_max = (float)(c->H - 1);
+  o->lf_exact = 1;
+  for (int k = 0; k < 3; ++k) { o->Lf[k] = (float)c->lidar_pos[k]; if ((double)o->Lf[k] != c->lidar_pos[k]) o->lf_exact = 0; }
   for (int k = 0; k < 3; ++k) o->L[k] = c->lidar_pos[k];
   return MUVO_OK;
 }
@@ -1110,7 +1243,29 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     return MUVO_OK;
   };
 
+  auto emit_range = [&]() -> int {
+    const int64_t HW = (int64_t)r.H * r.W;
+    const bool vec4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz_out) % 16 == 0) &&
+                      (!depth_out || reinterpret_cast<uintptr_t>(depth_out) % 16 == 0) &&
+                      (!sem_out || reinterpret_cast<uintptr_t>(sem_out) % 4 == 0);
+    const int64_t npix = (int64_t)F * HW;
+    if (vec4) {
+      if (layout == MUVO_RANGE_LAYOUT_HWC)
+        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+      else
+        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+    } else {
+      if (layout == MUVO_RANGE_LAYOUT_HWC)
+        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+      else
+        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+    }
+    MUVO_AFTER_LAUNCH("k_emit_range", st);
+    return MUVO_OK;
+  };
+
   prof_mark("<points>", st);
+  int n_tile_ctas = 0;
   // K1
   if (P > 0) {
     const void* fn;
@@ -1130,15 +1285,21 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       k_points_tile<T, false, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
     }
     MUVO_AFTER_LAUNCH("k_points_tile", st);
-    if (do_range) {
-      k_range_queued<T><<<grid, 128, 0, st>>>(xyz, off, F, P, r, w.pixtab, w.queue, w.qcount, diag);
-      MUVO_AFTER_LAUNCH("k_range_queued", st);
+    n_tile_ctas = (int)grid;
+  }
+  // K2 + K1q in one launch
+  {
+    const int scan_frames = do_vox ? F : 0;
+    const int queue_ctas = (do_range && P > 0) ? (n_tile_ctas + kScanCluster - 1) / kScanCluster * kScanCluster : 0;
+    const unsigned sgrid = (unsigned)(scan_frames * kScanCluster + queue_ctas);
+    if (sgrid > 0) {
+      k_scan_queue<T><<<sgrid, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, scan_frames, n_occ, xyz, off, F, P, r, w.pixtab,
+                                                     w.queue, w.qcount, queue_ctas ? n_tile_ctas : 0, diag);
+      MUVO_AFTER_LAUNCH("k_scan_queue", st);
     }
   }
+  if (do_range && (rc = emit_range()) != MUVO_OK) return rc;   // right after its producers: the pixel words are still L2 resident
   if (do_vox) {
-    // K2
-    k_bitmap_scan<<<F, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, n_occ);
-    MUVO_AFTER_LAUNCH("k_bitmap_scan", st);
     // K3 (+ K4 when the label does not fit in the slot word)
     if (P > 0) {
       const bool reg = g.regular != 0;
@@ -1181,25 +1342,6 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, sparse, g, F, true);
       MUVO_AFTER_LAUNCH("k_emit_sparse", st);
     }
-  }
-  if (do_range) {
-    const int64_t HW = (int64_t)r.H * r.W;
-    const bool vec4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz_out) % 16 == 0) &&
-                      (!depth_out || reinterpret_cast<uintptr_t>(depth_out) % 16 == 0) &&
-                      (!sem_out || reinterpret_cast<uintptr_t>(sem_out) % 4 == 0);
-    const int64_t npix = (int64_t)F * HW;
-    if (vec4) {
-      if (layout == MUVO_RANGE_LAYOUT_HWC)
-        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
-      else
-        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
-    } else {
-      if (layout == MUVO_RANGE_LAYOUT_HWC)
-        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
-      else
-        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
-    }
-    MUVO_AFTER_LAUNCH("k_emit_range", st);
   }
   return MUVO_OK;
 }
