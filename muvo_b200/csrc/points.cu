@@ -80,12 +80,12 @@ struct RangeDev {
 typedef unsigned long long u64;
 
 struct PointsWs {
-  uint32_t* bitmap = nullptr;   // [F, gw]
-  uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk
+  uint32_t* bitmap = nullptr;   // [F, gw]    occupancy, 1 bit per voxel
+  uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk (sparse output only)
+  u64* vtab = nullptr;          // [F, G]     packed winner per voxel, addressed by the voxel's bit index (0 = empty)
   u64* pixtab = nullptr;        // [F, H*W]   packed winner per pixel (0 = empty)
-  u64* vslot = nullptr;         // [P]        packed winner per occupied voxel, slot = frame_offsets[f] + rank
   uint32_t* qcount = nullptr;   // [kMaxTileCtas] rare-path queue length per tile CTA (rewritten by every call)
-  uint2* queue = nullptr;       // [P]        rare-path queue, CTA b's segment starts at its first point
+  uint2* queue = nullptr;       // [2P]       rare-path queue, CTA b's segment starts at 2 * (its first point)
   size_t bytes = 0;
 };
 
@@ -102,15 +102,13 @@ static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const Muv
     size_t gw = (size_t)bitmap_words(G);
     w.bitmap = (uint32_t*)(b + o); o = align_up(o + (size_t)F * gw * 4, 256);
     w.prefix = (uint32_t*)(b + o); o = align_up(o + (size_t)F * (gw / 4) * 4, 256);
+    w.vtab = (u64*)(b + o); o = align_up(o + (size_t)F * (size_t)G * 8, 256);
   }
   if (r) {
     w.pixtab = (u64*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 8, 256);
   }
   w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxTileCtas * 4, 256);
-  if (g) {
-    w.vslot = (u64*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 8, 256);
-  }
-  w.queue = (uint2*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 8, 256);
+  w.queue = (uint2*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 16, 256);
   w.bytes = o;
   return w;
 }
@@ -129,6 +127,16 @@ __device__ __forceinline__ u64 pack_vox(uint32_t top_inv, uint32_t idx1, uint32_
   return ((u64)top_inv << 32) | (u64)(((~idx1) & kVoxIdxMask) << 8) | (label & 0xffu);
 }
 __device__ __forceinline__ uint32_t vox_idx1(u64 w) { return (~((uint32_t)w >> 8)) & kVoxIdxMask; }
+// The label-carrying format is used per FRAME, whenever the frame has fewer than 2^24 - 1 points (decided on the
+// device from frame_offsets); larger frames keep the 32-bit index and the emit kernels fetch the label through it.
+constexpr int64_t kPackLimit = ((int64_t)1 << 24) - 1;
+__device__ __forceinline__ u64 vox_word(bool packl, uint32_t top_inv, uint32_t idx1, uint32_t label) {
+  return packl ? pack_vox(top_inv, idx1, label) : pack_word(top_inv, idx1);
+}
+__device__ __forceinline__ uint32_t vox_word_idx1(bool packl, u64 w) { return packl ? vox_idx1(w) : word_idx1(w); }
+__device__ __forceinline__ uint32_t vox_word_label(bool packl, u64 w, const uint8_t* __restrict__ sem_f) {
+  return packl ? ((uint32_t)w & 0xffu) : (uint32_t)__ldg(sem_f + (word_idx1(w) - 1u));
+}
 
 // ---------------------------------------------------------------- per-point arithmetic
 // numpy's npy_divmod (numpy/_core/src/npymath/npy_math_internal.h.src), the scalar behind np.divmod
@@ -591,25 +599,52 @@ __device__ __forceinline__ void scan_role(const uint32_t* __restrict__ bitmap, u
   if (rank == 0 && tid == 0 && n_occ_out) n_occ_out[f] = (int64_t)all;
 }
 
-// One queued point of the range image: kQExact = the reference's float64 formula decides the pixel and the atomicMax
-// happens here; otherwise the f32 pixel stands and the atomicMax already met a same-class holder (exact tie protocol).
+// Rare-path queue entries.  x = CTA-relative point index, bit 31 set for a voxel event;
+//   range : y = kQExact -> the reference's float64 formula decides the pixel and the atomicMax happens here;
+//           otherwise y = 1-based frame-relative index of the same-class holder met by the point's atomicMax (the f32
+//           pixel stands): exact tie protocol.
+//   voxel : y = index of the same-class holder met on the voxel's word: exact tie protocol,
+//           key = (not roadline, float64 |p mod res|^2).
+constexpr uint32_t kQVoxel = 0x80000000u;
 template <typename T>
-__device__ __forceinline__ void range_queue_role(int cta, int n_tile_ctas, const T* __restrict__ xyz, const int64_t* __restrict__ off,
-                                                 int F, int64_t P, const RangeDev& r, u64* __restrict__ pixtab,
-                                                 const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount,
-                                                 int64_t* __restrict__ diag) {
-  if (cta >= n_tile_ctas) return;
-  const uint32_t n = qcount[cta];
+struct QueueArgs {
+  const T* xyz; const uint8_t* sem; const int64_t* off; int F; int64_t P;
+  u64* pixtab; u64* vtab; const uint2* queue; const uint32_t* qcount; int n_tile_ctas; int64_t* diag;
+};
+
+template <typename T>
+__device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const GridDev& g, const RangeDev& r) {
+  if (cta >= a.n_tile_ctas) return;
+  const uint32_t n = a.qcount[cta];
   if (n == 0u) return;   // CTA-uniform
   int t0, t1;
-  cta_tile_range(P, n_tile_ctas, cta, &t0, &t1);
+  cta_tile_range(a.P, a.n_tile_ctas, cta, &t0, &t1);
   const int64_t blk_first = (int64_t)t0 * kTile;
-  const uint2* q = queue + blk_first;
+  const uint2* q = a.queue + 2 * blk_first;
   unsigned n_drop = 0, n_nw = 0, n_nh = 0;
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     const uint2 ent = q[e];
-    const int64_t i = blk_first + (int64_t)ent.x;
-    const T x = __ldg(xyz + 3 * i), y = __ldg(xyz + 3 * i + 1), z = __ldg(xyz + 3 * i + 2);
+    const int64_t i = blk_first + (int64_t)(ent.x & ~kQVoxel);
+    const T x = __ldg(a.xyz + 3 * i), y = __ldg(a.xyz + 3 * i + 1), z = __ldg(a.xyz + 3 * i + 2);
+    const int f = find_frame(a.off, a.F, i);
+    const int64_t fb = __ldg(a.off + f);
+    const T* fx = a.xyz + 3 * fb;
+    const uint32_t me1 = (uint32_t)(i - fb) + 1u;
+    if (ent.x & kQVoxel) {
+      const uint8_t* fs = a.sem + fb;
+      const bool packl = (__ldg(a.off + f + 1) - fb) < kPackLimit;
+      auto key_of = [&](uint32_t q1) -> u64 {
+        const T* qp = fx + 3 * (int64_t)(q1 - 1u);
+        VoxKey o = vox_of<true>((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
+        return vox_key(o.dis, (int)__ldg(fs + (q1 - 1u)) != g.road);
+      };
+      const VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g);
+      const uint32_t top = key_top_inv(vox_key(v.dis, (int)__ldg(a.sem + i) != g.road));
+      auto pack = [&](uint32_t q1) -> u64 { return vox_word(packl, top, q1, packl ? __ldg(fs + (q1 - 1u)) : 0u); };
+      auto idx_of = [&](u64 wv) -> uint32_t { return vox_word_idx1(packl, wv); };
+      tie_protocol(a.vtab + (size_t)f * g.G + v.bit, top, me1, pack(me1), pack(ent.y), key_of, pack, idx_of);
+      continue;
+    }
     double xc, yc, zc;
     const double s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
     int pix;
@@ -622,68 +657,68 @@ __device__ __forceinline__ void range_queue_role(int cta, int n_tile_ctas, const
     } else {
       pix = pix_fast(x, y, z, r).pix;
     }
-    const int f = find_frame(off, F, i);
-    const int64_t fb = __ldg(off + f);
-    u64* slot = pixtab + (size_t)f * r.H * r.W + pix;
+    u64* slot = a.pixtab + (size_t)f * r.H * r.W + pix;
     const uint32_t top = key_top_inv((u64)__double_as_longlong(s));
-    const uint32_t me1 = (uint32_t)(i - fb) + 1u;
     const u64 mine = pack_word(top, me1);
     const u64 old_word = (ent.y == kQExact) ? atomicMax(slot, mine) : pack_word(top, ent.y);
     if (old_word != 0ull && word_top(old_word) == top) {
-      const T* fx = xyz + 3 * fb;
       auto key_of = [&](uint32_t q1) -> u64 {     // exact key: the float64 depth (geometry_utils.py:180)
         const T* qp = fx + 3 * (int64_t)(q1 - 1u);
-        double a, b, c;
-        return (u64)__double_as_longlong(sqrt(range_sq_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &a, &b, &c)));
+        double aa, bb, cc;
+        return (u64)__double_as_longlong(sqrt(range_sq_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &aa, &bb, &cc)));
       };
       auto pack = [&](uint32_t q1) -> u64 { return pack_word(top, q1); };
       auto idx_of = [](u64 wv) -> uint32_t { return word_idx1(wv); };
       tie_protocol(slot, top, me1, mine, old_word, key_of, pack, idx_of);
     }
   }
-  if (diag) {
+  if (a.diag) {
     __syncwarp();
-    diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
-    diag_add(diag, MUVO_DIAG_NEAR_EDGE_W, n_nw);
-    diag_add(diag, MUVO_DIAG_NEAR_EDGE_H, n_nh);
+    diag_add(a.diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
+    diag_add(a.diag, MUVO_DIAG_NEAR_EDGE_W, n_nw);
+    diag_add(a.diag, MUVO_DIAG_NEAR_EDGE_H, n_nh);
   }
 }
 
-// grid = n_scan_frames * 8 scan CTAs, then the queue CTAs (padded to a multiple of the cluster size)
+// K2: grid = n_scan_frames * 8 scan CTAs (only when the sorted sparse list is wanted), then the queue CTAs (padded to a
+// multiple of the cluster size)
 template <typename T>
 __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThreads)
 k_scan_queue(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw, int n_scan_frames,
-             int64_t* __restrict__ n_occ_out, const T* __restrict__ xyz, const int64_t* __restrict__ off, int F, int64_t P,
-             RangeDev r, u64* __restrict__ pixtab, const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount,
-             int n_tile_ctas, int64_t* __restrict__ diag) {
+             int64_t* __restrict__ n_occ_out, QueueArgs<T> qa, GridDev g, RangeDev r) {
   const int scan_ctas = n_scan_frames * kScanCluster;
   if ((int)blockIdx.x < scan_ctas) scan_role(bitmap, prefix, gw, n_occ_out);
-  else range_queue_role<T>((int)blockIdx.x - scan_ctas, n_tile_ctas, xyz, off, F, P, r, pixtab, queue, qcount, diag);
-}
-
-// rank of set bit `bit` within its frame (= number of set bits before it)
-__device__ __forceinline__ uint32_t rank_of(const uint32_t* __restrict__ bitmap_f, const uint32_t* __restrict__ prefix_f,
-                                            uint32_t bit) {
-  uint32_t chunk = bit >> 7;
-  uint4 v = *reinterpret_cast<const uint4*>(bitmap_f + chunk * 4);
-  uint32_t w = (bit >> 5) & 3u;
-  uint32_t below = 0;
-  uint32_t word = v.x;
-  if (w >= 1) { below += __popc(v.x); word = v.y; }
-  if (w >= 2) { below += __popc(v.y); word = v.z; }
-  if (w >= 3) { below += __popc(v.z); word = v.w; }
-  below += __popc(word & ((1u << (bit & 31)) - 1u));
-  return prefix_f[chunk] + below;
+  else queue_role<T>((int)blockIdx.x - scan_ctas, qa, g, r);
 }
 
 // ---------------------------------------------------------------- K1: point pass
+// Scan-ordered clouds put runs of consecutive points (= adjacent lanes) into one voxel.  A lane whose neighbour in
+// the same voxel holds a strictly better top-32 key class can never win the voxel: it skips its atomicMax.
+template <bool ONE_FRAME>
+__device__ __forceinline__ bool pair_filter(bool in, uint32_t bit /* 0xffffffff when !in */, int fk, uint32_t top_inv) {
+  const unsigned lane = lane_id();
+  const uint32_t bit_up = __shfl_up_sync(0xffffffffu, bit, 1), top_up = __shfl_up_sync(0xffffffffu, top_inv, 1);
+  const uint32_t bit_dn = __shfl_down_sync(0xffffffffu, bit, 1), top_dn = __shfl_down_sync(0xffffffffu, top_inv, 1);
+  bool beaten = (lane > 0 && bit == bit_up && top_up > top_inv) || (lane < 31 && bit == bit_dn && top_dn > top_inv);
+  if (!ONE_FRAME) {
+    const int fk_up = __shfl_up_sync(0xffffffffu, fk, 1), fk_dn = __shfl_down_sync(0xffffffffu, fk, 1);
+    beaten = (lane > 0 && bit == bit_up && fk == fk_up && top_up > top_inv) ||
+             (lane < 31 && bit == bit_dn && fk == fk_dn && top_dn > top_inv);
+  }
+  return in && !beaten;
+}
+
+constexpr int kLock = 2;   // points of a thread whose atomics are in flight together
+
 template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
 __global__ void __launch_bounds__(kTileThreads, 4)
 k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ pixtab,
-              uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ diag) {
+              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, u64* __restrict__ pixtab,
+              uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ n_occ_zero, int flags,
+              int64_t* __restrict__ diag) {
   extern __shared__ __align__(128) unsigned char smem[];
   using L = TileLayout<T>;
+  if (n_occ_zero && blockIdx.x == 0) for (int f = threadIdx.x; f < F; f += kTileThreads) n_occ_zero[f] = 0;
   Tiles<T> tl;
   if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
     if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
@@ -692,11 +727,11 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
   uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
   const int tid = threadIdx.x;
   const int64_t blk_first = (int64_t)tl.t0 * kTile;
-  uint2* q = queue + blk_first;
+  uint2* q = queue + 2 * blk_first;
   const int64_t HW = (int64_t)r.H * r.W;
+  const bool use_filter = (flags & 1) != 0;
   unsigned n_drop = 0, n_in = 0;
 
-  const unsigned lane = lane_id();
   while (tl.next()) {
     // FAST = the tile is staged in shared memory and lies inside one frame (all but a handful of tiles): frame
     // bases, table rows and the shared-memory cursor are CTA-uniform and hoisted out of the per-point code.
@@ -705,62 +740,88 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
       const T* sx = reinterpret_cast<const T*>(smem + (size_t)tl.st * L::xyz_bytes) + 3 * tid;
       const uint8_t* ss = smem + L::off_sem + (size_t)tl.st * kTile + tid;
       uint32_t* bitmap_f = bitmap + (size_t)tl.f * g.gw;
+      u64* vtab_f = vtab + (size_t)tl.f * g.G;
       u64* pixtab_f = pixtab + (size_t)tl.f * HW;
+      const bool packl_f = (tl.fend - tl.fbeg) < kPackLimit;
       const uint32_t idx1_0 = (uint32_t)(tl.base - tl.fbeg) + (uint32_t)tid + 1u;     // 1-based frame-relative index, k = 0
       const uint32_t rel_0 = (uint32_t)(tl.base - blk_first) + (uint32_t)tid;         // CTA-relative index, k = 0
-      u64* slot[kKPL];
-      u64 mine[kKPL], old[kKPL];
-      bool act[kKPL];
 #pragma unroll
-      for (int k = 0; k < kKPL; ++k) {
-        T x, y, z; uint32_t lab;
-        bool valid = true;
-        int fk = tl.f; int64_t fb = tl.fbeg;
-        if (FAST) {
-          x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
-          lab = ss[k * kTileThreads];
-        } else {
-          valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
-          tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
+      for (int h = 0; h < kKPL / kLock; ++h) {
+        u64 *pslot[kLock], *vslot[kLock];
+        uint32_t* bword[kLock];
+        u64 pmine[kLock], vmine[kLock], pold[kLock], vold[kLock];
+        uint32_t vbit[kLock];
+        bool pact[kLock], vact[kLock], vpackl[kLock];
+#pragma unroll
+        for (int u = 0; u < kLock; ++u) {
+          const int k = h * kLock + u;
+          T x, y, z; uint32_t lab;
+          bool valid = true;
+          int fk = tl.f; int64_t fb = tl.fbeg;
+          bool packl = packl_f;
+          if (FAST) {
+            x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
+            lab = ss[k * kTileThreads];
+          } else {
+            valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
+            tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
+            packl = (__ldg(off + fk + 1) - fb) < kPackLimit;
+          }
+          const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
+          pact[u] = false; pslot[u] = pixtab; pmine[u] = 0ull;
+          vact[u] = false; vslot[u] = vtab; vmine[u] = 0ull; vbit[u] = 0u; bword[u] = bitmap; vpackl[u] = packl;
+          if (DO_VOX) {
+            uint32_t bit = 0xffffffffu, top = 0u; bool in = false;
+            if (valid) {
+              double dis;
+              if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) bit = v.bit; }
+              else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); in = v.in; dis = v.dis; if (in) bit = v.bit; }
+              top = key_top_inv(vox_key(dis, (int)lab != g.road));
+            }
+            n_in += in ? 1u : 0u;
+            const bool go = use_filter ? pair_filter<FAST>(in, bit, fk, top) : in;
+            if (go) {
+              vact[u] = true;
+              vbit[u] = bit;
+              vslot[u] = (FAST ? vtab_f : vtab + (size_t)fk * g.G) + bit;
+              bword[u] = (FAST ? bitmap_f : bitmap + (size_t)fk * g.gw) + (bit >> 5);
+              vmine[u] = vox_word(packl, top, me1, lab);
+            }
+          }
+          if (DO_RANGE && valid) {
+            const PixFast pk = pix_fast(x, y, z, r);
+            if (!pk.ok) ++n_drop;
+            else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, kQExact);
+            else {
+              pact[u] = true;
+              pslot[u] = (FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix;
+              // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
+              pmine[u] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), me1);
+            }
+          }
         }
-        (void)lab;
-        act[k] = false; slot[k] = pixtab; mine[k] = 0ull;
         if (DO_VOX) {
-          uint32_t bit = 0xffffffffu; bool in = false;
-          if (valid) {
-            if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; if (in) bit = v.bit; }
-            else { VoxKey v = vox_of<false>((double)x, (double)y, (double)z, g); in = v.in; if (in) bit = v.bit; }
-          }
-          // scan-ordered clouds put runs of consecutive points into one voxel: only the first lane of a run sets the bit
-          const uint32_t bit_prev = __shfl_up_sync(0xffffffffu, bit, 1);
-          bool dup = lane > 0 && bit == bit_prev;
-          if (!FAST) { const int fk_prev = __shfl_up_sync(0xffffffffu, fk, 1); dup = dup && fk == fk_prev; }
-          if (in) {
-            ++n_in;
-            uint32_t* bm = FAST ? bitmap_f : bitmap + (size_t)fk * g.gw;
-            if (!dup) atomicOr(bm + (bit >> 5), 1u << (bit & 31));   // RED, no return value
+#pragma unroll
+          for (int u = 0; u < kLock; ++u) vold[u] = vact[u] ? atomicMax(vslot[u], vmine[u]) : 1ull;
+        }
+        if (DO_RANGE) {
+#pragma unroll
+          for (int u = 0; u < kLock; ++u) pold[u] = pact[u] ? atomicMax(pslot[u], pmine[u]) : 0ull;
+        }
+        if (DO_VOX) {
+#pragma unroll
+          for (int u = 0; u < kLock; ++u) {
+            if (vold[u] == 0ull) atomicOr(bword[u], 1u << (vbit[u] & 31));     // first claim of the voxel marks it occupied
+            else if (vact[u] && word_top(vold[u]) == word_top(vmine[u]))       // same top-32 class: exact protocol
+              q[atomicAdd(qn, 1u)] = make_uint2((rel_0 + (h * kLock + u) * kTileThreads) | kQVoxel, vox_word_idx1(vpackl[u], vold[u]));
           }
         }
-        if (DO_RANGE && valid) {
-          const PixFast pk = pix_fast(x, y, z, r);
-          if (!pk.ok) ++n_drop;
-          else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, kQExact);
-          else {
-            act[k] = true;
-            slot[k] = (FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix;
-            // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
-            const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
-            mine[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), me1);
+        if (DO_RANGE) {
+#pragma unroll
+          for (int u = 0; u < kLock; ++u) {
+            if (pact[u] && pold[u] != 0ull && word_top(pold[u]) == word_top(pmine[u]))
+              q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + (h * kLock + u) * kTileThreads, word_idx1(pold[u]));
           }
-        }
-      }
-      if (DO_RANGE) {
-#pragma unroll
-        for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
-#pragma unroll
-        for (int k = 0; k < kKPL; ++k) {
-          if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))   // same top-32 class: exact protocol
-            q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, word_idx1(old[k]));
         }
       }
     };
@@ -774,154 +835,8 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
   }
 }
 
-// ---------------------------------------------------------------- K3: voxel resolve
-// Scan-ordered clouds put runs of consecutive points (= adjacent lanes) into one voxel.  Within such a run only the
-// lanes holding the run's best top-32 key class (usually exactly one) still have to compete for the slot; the others
-// could never win it.  Returns that predicate (segmented max-scan over the run with shuffles).
-template <bool ONE_FRAME>
-__device__ __forceinline__ bool run_leader(bool in, uint32_t bit /* 0xffffffff when !in */, int fk, uint32_t top_inv) {
-  const unsigned lane = lane_id();
-  const uint32_t bit_prev = __shfl_up_sync(0xffffffffu, bit, 1);
-  bool joins = in && lane > 0 && bit == bit_prev;
-  if (!ONE_FRAME) { const int fk_prev = __shfl_up_sync(0xffffffffu, fk, 1); joins = joins && fk == fk_prev; }
-  const unsigned heads = __ballot_sync(0xffffffffu, !joins);                 // bit 0 is always set
-  const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));         // head of this lane's run
-  uint32_t v = in ? top_inv : 0u;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-    if ((int)lane - d >= start) v = v > t ? v : t;
-  }
-  const unsigned rest = lane == 31 ? 0u : (heads >> (lane + 1));
-  const int end = rest ? (int)lane + __ffs(rest) - 1 : 31;                   // last lane of the run
-  const uint32_t best = __shfl_sync(0xffffffffu, v, end);
-  return in && top_inv == best;
-}
-
-// PACKL: the slot word also carries the point's label (needs < 2^24 points per frame); otherwise the label pass
-// (k_slot_labels) fills it in afterwards.
-template <typename T, bool REG, bool PACKL>
-__global__ void __launch_bounds__(kTileThreads, 4)
-k_voxel_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-             bool vec_ok, GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-             u64* __restrict__ vslot, uint2* __restrict__ queue, uint32_t* __restrict__ qcount) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  using L = TileLayout<T>;
-  Tiles<T> tl;
-  if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
-    if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
-    return;
-  }
-  uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
-  const int tid = threadIdx.x;
-  const int64_t blk_first = (int64_t)tl.t0 * kTile;
-  uint2* q = queue + blk_first;
-  while (tl.next()) {
-    auto body = [&](auto fast_tag) {
-      constexpr bool FAST = decltype(fast_tag)::value;
-      const T* sx = reinterpret_cast<const T*>(smem + (size_t)tl.st * L::xyz_bytes) + 3 * tid;
-      const uint8_t* ss = smem + L::off_sem + (size_t)tl.st * kTile + tid;
-      const uint32_t* bitmap_f = bitmap + (size_t)tl.f * g.gw;
-      const uint32_t* prefix_f = prefix + (size_t)tl.f * (g.gw / 4);
-      u64* vslot_f = vslot + tl.fbeg;
-      const uint32_t idx1_0 = (uint32_t)(tl.base - tl.fbeg) + (uint32_t)tid + 1u;
-      const uint32_t rel_0 = (uint32_t)(tl.base - blk_first) + (uint32_t)tid;
-      u64* slot[kKPL];
-      u64 mine[kKPL], old[kKPL];
-      bool act[kKPL];
-#pragma unroll
-      for (int k = 0; k < kKPL; ++k) {
-        T x, y, z; uint32_t lab;
-        bool valid = true;
-        int fk = tl.f; int64_t fb = tl.fbeg;
-        if (FAST) {
-          x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
-          lab = ss[k * kTileThreads];
-        } else {
-          valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
-          tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
-        }
-        act[k] = false; slot[k] = vslot; mine[k] = 0ull;
-        uint32_t bit = 0xffffffffu, top = 0; bool in = false;
-        if (valid) {
-          double dis;
-          if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) bit = v.bit; }
-          else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); in = v.in; dis = v.dis; if (in) bit = v.bit; }
-          top = key_top_inv(vox_key(dis, (int)lab != g.road));
-        }
-        if (run_leader<FAST>(in, bit, fk, top)) {
-          act[k] = true;
-          const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
-          mine[k] = PACKL ? pack_vox(top, me1, lab) : pack_word(top, me1);
-          slot[k] = FAST ? vslot_f + rank_of(bitmap_f, prefix_f, bit)
-                         : vslot + fb + rank_of(bitmap + (size_t)fk * g.gw, prefix + (size_t)fk * (g.gw / 4), bit);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kKPL; ++k) old[k] = act[k] ? atomicMax(slot[k], mine[k]) : 0ull;
-#pragma unroll
-      for (int k = 0; k < kKPL; ++k) {
-        if (act[k] && old[k] != 0ull && word_top(old[k]) == word_top(mine[k]))
-          q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, PACKL ? vox_idx1(old[k]) : word_idx1(old[k]));
-      }
-    };
-    if (tl.full && tl.one_frame) body(std::true_type{}); else body(std::false_type{});
-    __syncthreads();
-  }
-  if (tid == 0) qcount[blockIdx.x] = *qn;
-}
-
-// K3q: exact tie protocol for the queued voxel ties: key = (not roadline, float64 |p mod res|^2).  Same grid as K3.
-template <typename T, bool PACKL>
-__global__ void __launch_bounds__(128)
-k_voxel_queued(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-               GridDev g, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
-               const uint2* __restrict__ queue, const uint32_t* __restrict__ qcount) {
-  const uint32_t n = qcount[blockIdx.x];
-  if (n == 0u) return;
-  int t0, t1;
-  cta_tile_range(P, (int)gridDim.x, (int)blockIdx.x, &t0, &t1);
-  const int64_t blk_first = (int64_t)t0 * kTile;
-  const uint2* q = queue + blk_first;
-  for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
-    const uint2 ent = q[e];
-    const int64_t i = blk_first + (int64_t)ent.x;
-    const int f = find_frame(off, F, i);
-    const int64_t fb = __ldg(off + f);
-    const T* fx = xyz + 3 * fb;
-    const uint8_t* fs = sem + fb;
-    const uint32_t me1 = (uint32_t)(i - fb) + 1u;
-    auto key_of = [&](uint32_t q1) -> u64 {
-      const T* qp = fx + 3 * (int64_t)(q1 - 1u);
-      VoxKey o = vox_of<true>((double)__ldg(qp), (double)__ldg(qp + 1), (double)__ldg(qp + 2), g);
-      return vox_key(o.dis, (int)__ldg(fs + (q1 - 1u)) != g.road);
-    };
-    const VoxKey v = vox_of<true>((double)__ldg(xyz + 3 * i), (double)__ldg(xyz + 3 * i + 1), (double)__ldg(xyz + 3 * i + 2), g);
-    const uint32_t top = key_top_inv(vox_key(v.dis, (int)__ldg(sem + i) != g.road));
-    auto pack = [&](uint32_t q1) -> u64 { return PACKL ? pack_vox(top, q1, __ldg(fs + (q1 - 1u))) : pack_word(top, q1); };
-    auto idx_of = [](u64 wv) -> uint32_t { return PACKL ? vox_idx1(wv) : word_idx1(wv); };
-    u64* slot = vslot + fb + rank_of(bitmap + (size_t)f * g.gw, prefix + (size_t)f * (g.gw / 4), v.bit);
-    tie_protocol(slot, top, me1, pack(me1), pack(ent.y), key_of, pack, idx_of);
-  }
-}
-
-// ---------------------------------------------------------------- K4: slot labels
-// One thread per winner slot: replace the packed winner by (kLabelTag | raw label of the winning point) so that
-// the emit kernels need a single gather per occupied voxel.  Slots that were never claimed stay 0.
-constexpr u64 kLabelTag = 0xffffffff00000000ull;
-__global__ void __launch_bounds__(kBlock)
-k_slot_labels(u64* __restrict__ vslot, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P) {
-  int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  if (s >= P) return;
-  u64 wv = vslot[s];
-  if (!wv) return;
-  int f = find_frame(off, F, s);
-  uint32_t lab = __ldg(sem + __ldg(off + f) + (int64_t)(word_idx1(wv) - 1u));
-  vslot[s] = kLabelTag | lab;
-}
-
 // ---------------------------------------------------------------- K5: emit
-// Shared by the emit kernels: lane L owns bitmap word (warp_word0 + L); returns the word and the rank of
+// Shared by the sparse emit: lane L owns bitmap word (warp_word0 + L); returns the word and the rank of
 // its first bit.  Ranks of the 4 words of a chunk are built with shuffles, so no lane ever re-reads a
 // word that its owner may already have cleared.
 __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix,
@@ -942,56 +857,69 @@ __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap
   *word_o = word; *rank_o = rank;
 }
 
-// Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as
-// two fully coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).  The winner
-// slots of the span are contiguous in rank order: they are read (and cleared) with coalesced 8-byte
-// accesses, their (remapped) label bytes staged in shared memory, and every lane then picks the labels of
-// its set bits from there -- no dependent global gathers.
+// Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as two fully
+// coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).  The winner word of every set bit
+// is fetched from (and cleared in) the voxel table; the first gathers of a piece are issued back to back.
 // grid = (gw / kBlock, F): blockIdx.y is the frame, so no 64-bit division is needed.
 __global__ void __launch_bounds__(kBlock)
-k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
-             const int64_t* __restrict__ off, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
-             bool clean) {
-  __shared__ uint8_t lab_s[kBlock / 32][1024];
+k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_t* __restrict__ off,
+             const uint8_t* __restrict__ sem, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
+             int64_t* __restrict__ n_occ) {
+  __shared__ uint32_t occ_s[kBlock / 32];
   const int f = blockIdx.y;
   const uint32_t wi = blockIdx.x * kBlock + threadIdx.x;        // word index inside the frame
   const bool valid = wi < (uint32_t)g.gw;
   const int64_t wg = (int64_t)f * g.gw + wi;
-  uint32_t word, rank;
-  load_word_and_rank(bitmap, prefix, wg, valid, clean, &word, &rank);
+  const uint32_t word = valid ? bitmap[wg] : 0u;
+  if (word) bitmap[wg] = 0u;
   const unsigned lane = lane_id();
+  if (n_occ) {                                                  // occupied voxels of the frame: one atomic per CTA
+    const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(word));
+    if (lane == 0) occ_s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+#pragma unroll
+      for (int k = 0; k < kBlock / 32; ++k) t += occ_s[k];
+      if (t) atomicAdd(reinterpret_cast<unsigned long long*>(n_occ + f), (unsigned long long)t);
+    }
+  }
   const uint32_t warp_w0 = wi - lane;                           // gw % 32 == 0: a warp never straddles frames
   if (warp_w0 >= (uint32_t)g.gw) return;                        // whole warp out of range
-  uint8_t* labs = lab_s[threadIdx.x >> 5];
-  const uint32_t r0 = __shfl_sync(0xffffffffu, rank, 0);
-  const uint32_t cnt = __shfl_sync(0xffffffffu, rank + __popc(word), 31) - r0;
-  if (cnt) {
-    u64* sl = vslot + __ldg(off + f) + r0;
-    for (uint32_t j = lane; j < cnt; j += 32) {
-      uint32_t lab = (uint32_t)sl[j] & 0xffu;
-      if (clean) sl[j] = 0ull;
-      if (remap) lab = __ldg(remap + lab);
-      labs[j] = (uint8_t)lab;
-    }
-    __syncwarp();
-  }
+  const int64_t fb = __ldg(off + f);
+  const bool packl = (__ldg(off + f + 1) - fb) < kPackLimit;
+  const uint8_t* sem_f = sem + fb;
   const uint32_t vox0 = warp_w0 * 32u;                          // first voxel of the warp inside the frame
+  u64* vt = vtab + (size_t)f * g.G + vox0;
   uint8_t* dst = dense + (size_t)f * g.G + vox0;
   const bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    unsigned src = (unsigned)half * 16u + (lane >> 1);          // lane j handles piece p = half*32 + j -> word p/2
-    uint32_t w = __shfl_sync(0xffffffffu, word, src);
-    uint32_t rk = __shfl_sync(0xffffffffu, rank, src) - r0;
+    const unsigned src = (unsigned)half * 16u + (lane >> 1);    // lane j handles piece p = half*32 + j -> word p/2
+    const uint32_t w = __shfl_sync(0xffffffffu, word, src);
     uint32_t bits = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
-    if (lane & 1u) rk += __popc(w & 0xffffu);
+    const uint32_t piece = (uint32_t)half * 32u + lane;
+    u64* pv = vt + piece * 16;
     uint32_t o[4] = {0u, 0u, 0u, 0u};
     while (bits) {
-      const int j = __ffs(bits) - 1;
-      bits &= bits - 1;
-      o[j >> 2] |= (uint32_t)labs[rk++] << (8 * (j & 3));
+      int js[4];
+      u64 ws[4];
+      int n = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {                              // up to 4 independent gathers in flight
+        js[u] = 0; ws[u] = 0ull;
+        if (bits) { js[u] = __ffs(bits) - 1; bits &= bits - 1; ws[u] = pv[js[u]]; ++n; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (u < n) {
+          pv[js[u]] = 0ull;
+          uint32_t lab = vox_word_label(packl, ws[u], sem_f);
+          if (remap) lab = __ldg(remap + lab);
+          o[js[u] >> 2] |= lab << (8 * (js[u] & 3));
+        }
+      }
     }
-    const uint32_t piece = (uint32_t)half * 32u + lane;
     const int64_t v = (int64_t)vox0 + piece * 16;               // first voxel of this piece
     __syncwarp();   // reconverge after the data-dependent loop so that the store below is one 512-byte request
     if (fast) {
@@ -1001,47 +929,50 @@ k_emit_dense(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* 
         if (v + j < g.G) dense[(size_t)f * g.G + v + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
     }
   }
-  if (clean && valid && word) bitmap[wg] = 0u;
 }
 
 // Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(frame_offsets[f] + rank)].
+// sparse == nullptr: only clears the tables (n_occ-only calls).
 __global__ void __launch_bounds__(kBlock)
-k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vslot,
-              const int64_t* __restrict__ off, uint16_t* __restrict__ sparse, GridDev g, int F, bool clean) {
+k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vtab,
+              const int64_t* __restrict__ off, const uint8_t* __restrict__ sem, uint16_t* __restrict__ sparse, GridDev g, int F) {
   int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   int64_t total = (int64_t)F * g.gw;
   bool valid = wg < total;
   uint32_t word, rank;
-  load_word_and_rank(bitmap, prefix, wg, valid, clean, &word, &rank);
+  load_word_and_rank(bitmap, prefix, wg, valid, true, &word, &rank);
   if (!valid || !word) return;
   int f = (int)(wg / g.gw);
   int64_t fbeg = __ldg(off + f);
+  const bool packl = (__ldg(off + f + 1) - fbeg) < kPackLimit;
   uint32_t bit0 = (uint32_t)(wg - (int64_t)f * g.gw) * 32u;
+  u64* vt = vtab + (size_t)f * g.G + bit0;
   uint32_t b = word;
   while (b) {
     int j = __ffs(b) - 1;
     b &= b - 1;
-    uint32_t lin = bit0 + (uint32_t)j;
-    uint32_t x = lin % (uint32_t)g.dx;
-    uint32_t yz = lin / (uint32_t)g.dx;
-    uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
-    u64* sl = vslot + fbeg + rank;
-    uint32_t lab = (uint32_t)(*sl) & 0xffu;
-    if (clean) *sl = 0ull;
+    const u64 wv = vt[j];
+    vt[j] = 0ull;
     if (sparse) {
+      uint32_t lin = bit0 + (uint32_t)j;
+      uint32_t x = lin % (uint32_t)g.dx;
+      uint32_t yz = lin / (uint32_t)g.dx;
+      uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
+      uint32_t lab = vox_word_label(packl, wv, sem + fbeg);
       uint2 row = make_uint2(x | (y << 16), z | (lab << 16));
       *reinterpret_cast<uint2*>(sparse + (size_t)(fbeg + rank) * 4) = row;
     }
     ++rank;
   }
-  if (clean) bitmap[wg] = 0u;
+  bitmap[wg] = 0u;
 }
 
-// Dense grid when the bitmap is in linear-id order (both outputs requested): per-voxel lookup.
+// Dense grid when the bitmap is in linear-id order (both outputs requested): per-voxel lookup, nothing is cleared
+// (k_emit_sparse runs afterwards).
 __global__ void __launch_bounds__(kBlock)
-k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix,
-                         const u64* __restrict__ vslot, const int64_t* __restrict__ off, const uint8_t* __restrict__ remap,
-                         uint8_t* __restrict__ dense, GridDev g, int F) {
+k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const u64* __restrict__ vtab, const int64_t* __restrict__ off,
+                         const uint8_t* __restrict__ sem, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense,
+                         GridDev g, int F) {
   int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (t >= (int64_t)F * g.G) return;
   int f = (int)(t / g.G);
@@ -1052,8 +983,9 @@ k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const uint32_t* __
   const uint32_t* bm = bitmap + (size_t)f * g.gw;
   uint32_t lab = 0;
   if ((bm[lin >> 5] >> (lin & 31)) & 1u) {
-    uint32_t rank = rank_of(bm, prefix + (size_t)f * (g.gw / 4), lin);
-    lab = (uint32_t)vslot[__ldg(off + f) + rank] & 0xffu;
+    const int64_t fb = __ldg(off + f);
+    const bool packl = (__ldg(off + f + 1) - fb) < kPackLimit;
+    lab = vox_word_label(packl, vtab[(size_t)f * g.G + lin], sem + fb);
     if (remap) lab = __ldg(remap + lab);
   }
   dense[t] = (uint8_t)lab;
@@ -1214,14 +1146,13 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
   GridDev g{}; RangeDev r{};
   int rc;
-  const int order = (sparse != nullptr) ? ORDER_LINEAR : ORDER_DENSE;
+  const int order = (sparse != nullptr) ? ORDER_LINEAR : ORDER_DENSE;   // bit index = output order of the list that is emitted
   if (do_vox && (rc = make_grid_dev(grid_h, order, &g)) != MUVO_OK) return rc;
   if (do_range && (rc = make_range_dev(cfg_h, &r)) != MUVO_OK) return rc;
   PointsWs w = carve(ws, P, F, grid_h, cfg_h);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 16 == 0);
   if (P >= ((int64_t)1 << 36)) return MUVO_E_SHAPE;              // exact-path queue entries are 32-bit CTA-relative
-  const bool packl = P < ((int64_t)1 << 24) - 1;                 // label rides in the voxel word (24-bit index)
   // persistent tile kernels: one contiguous run of tiles per CTA, CTAs = SMs x resident CTAs per SM
   const int64_t n_tiles = ceil_div64(P, kTile);
   const size_t tsmem = TileLayout<T>::bytes;
@@ -1266,6 +1197,10 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
 
   prof_mark("<points>", st);
   int n_tile_ctas = 0;
+  // the sorted sparse list needs ranks (bitmap scan); a dense-only call counts n_occ while it emits
+  const bool need_scan = do_vox && (sparse != nullptr || dense == nullptr);
+  int64_t* n_occ_emit = (do_vox && !need_scan) ? n_occ : nullptr;
+  const int flags = (g_tuning[1] == 1) ? 0 : 1;
   // K1
   if (P > 0) {
     const void* fn;
@@ -1275,71 +1210,48 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     else                    fn = (const void*)k_points_tile<T, false, true, true>;
     unsigned grid;
     if ((rc = tile_grid(fn, 0, &grid)) != MUVO_OK) return rc;
+#define MUVO_K1_ARGS xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.vtab, w.pixtab, w.queue, w.qcount, n_occ_emit, flags, diag
     if (do_vox && do_range) {
-      if (reg) k_points_tile<T, true, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
-      else     k_points_tile<T, true, true, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+      if (reg) k_points_tile<T, true, true, true><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
+      else     k_points_tile<T, true, true, false><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
     } else if (do_vox) {
-      if (reg) k_points_tile<T, true, false, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
-      else     k_points_tile<T, true, false, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+      if (reg) k_points_tile<T, true, false, true><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
+      else     k_points_tile<T, true, false, false><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
     } else {
-      k_points_tile<T, false, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.pixtab, w.queue, w.qcount, diag);
+      k_points_tile<T, false, true, true><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
     }
+#undef MUVO_K1_ARGS
     MUVO_AFTER_LAUNCH("k_points_tile", st);
     n_tile_ctas = (int)grid;
+  } else if (n_occ_emit) {
+    cudaError_t e = cudaMemsetAsync(n_occ_emit, 0, (size_t)F * sizeof(int64_t), st);
+    if (e != cudaSuccess) return (int)e;
   }
-  // K2 + K1q in one launch
+  // K2: bitmap scan (when ranks are needed) + the rare-path queues, one launch
   {
-    const int scan_frames = do_vox ? F : 0;
-    const int queue_ctas = (do_range && P > 0) ? (n_tile_ctas + kScanCluster - 1) / kScanCluster * kScanCluster : 0;
+    const int scan_frames = need_scan ? F : 0;
+    const int queue_ctas = P > 0 ? (n_tile_ctas + kScanCluster - 1) / kScanCluster * kScanCluster : 0;
     const unsigned sgrid = (unsigned)(scan_frames * kScanCluster + queue_ctas);
     if (sgrid > 0) {
-      k_scan_queue<T><<<sgrid, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, scan_frames, n_occ, xyz, off, F, P, r, w.pixtab,
-                                                     w.queue, w.qcount, queue_ctas ? n_tile_ctas : 0, diag);
+      QueueArgs<T> qa{xyz, sem, off, F, P, w.pixtab, w.vtab, w.queue, w.qcount, queue_ctas ? n_tile_ctas : 0, diag};
+      k_scan_queue<T><<<sgrid, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, scan_frames, n_occ, qa, g, r);
       MUVO_AFTER_LAUNCH("k_scan_queue", st);
     }
   }
   if (do_range && (rc = emit_range()) != MUVO_OK) return rc;   // right after its producers: the pixel words are still L2 resident
   if (do_vox) {
-    // K3 (+ K4 when the label does not fit in the slot word)
-    if (P > 0) {
-      const bool reg = g.regular != 0;
-      const void* fn = packl ? (reg ? (const void*)k_voxel_tile<T, true, true> : (const void*)k_voxel_tile<T, false, true>)
-                             : (reg ? (const void*)k_voxel_tile<T, true, false> : (const void*)k_voxel_tile<T, false, false>);
-      unsigned grid;
-      if ((rc = tile_grid(fn, 0, &grid)) != MUVO_OK) return rc;
-      if (packl) {
-        if (reg) k_voxel_tile<T, true, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
-        else     k_voxel_tile<T, false, true><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
-        MUVO_AFTER_LAUNCH("k_voxel_tile", st);
-        k_voxel_queued<T, true><<<grid, 128, 0, st>>>(xyz, sem, off, F, P, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
-        MUVO_AFTER_LAUNCH("k_voxel_queued", st);
-      } else {
-        if (reg) k_voxel_tile<T, true, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
-        else     k_voxel_tile<T, false, false><<<grid, kTileThreads, tsmem, st>>>(xyz, sem, off, F, P, vec_ok, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
-        MUVO_AFTER_LAUNCH("k_voxel_tile", st);
-        k_voxel_queued<T, false><<<grid, 128, 0, st>>>(xyz, sem, off, F, P, g, w.bitmap, w.prefix, w.vslot, w.queue, w.qcount);
-        MUVO_AFTER_LAUNCH("k_voxel_queued", st);
-        k_slot_labels<<<blocks_for(P), kBlock, 0, st>>>(w.vslot, sem, off, F, P);
-        MUVO_AFTER_LAUNCH("k_slot_labels", st);
-      }
-    }
     // K5 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;
-    if (order == ORDER_DENSE) {
-      if (dense) {
-        dim3 grid((unsigned)ceil_div64(g.gw, kBlock), (unsigned)F);
-        k_emit_dense<<<grid, kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, remap, dense, g, F, true);
-      } else {  // only n_occ requested: clear through the sparse walker without output
-        k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, nullptr, g, F, true);
-      }
-      MUVO_AFTER_LAUNCH(dense ? "k_emit_dense" : "k_emit_sparse", st);
+    if (!need_scan) {
+      dim3 grid((unsigned)ceil_div64(g.gw, kBlock), (unsigned)F);
+      k_emit_dense<<<grid, kBlock, 0, st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F, n_occ_emit);
+      MUVO_AFTER_LAUNCH("k_emit_dense", st);
     } else {
       if (dense) {
-        k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off,
-                                                                                 remap, dense, g, F);
+        k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F);
         MUVO_AFTER_LAUNCH("k_emit_dense_from_linear", st);
       }
-      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vslot, off, sparse, g, F, true);
+      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vtab, off, sem, sparse, g, F);
       MUVO_AFTER_LAUNCH("k_emit_sparse", st);
     }
   }

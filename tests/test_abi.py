@@ -69,10 +69,10 @@ def test_workspace_size_and_argument_errors(lib):
     g, r = GridSpec().to_c(), RangeSpec().to_c()
     n = C.c_size_t(0)
     assert lib.muvo_points_workspace_bytes(100000, 1, C.byref(g), C.byref(r), C.byref(n)) == 0
-    # bitmap (G/8) + chunk prefix (G/32) + winner table (8 B/pt) + rare-path queue (8 B/pt) + pixel table (8 B/px)
-    # + queue length slots (16 KiB)
+    # bitmap (G/8) + chunk prefix (G/32) + voxel winner table (8 B/voxel) + pixel table (8 B/px)
+    # + queue length slots (16 KiB) + rare-path queue (16 B/pt)
     G = 192 * 192 * 64
-    need = G // 8 + G // 32 + 16 * 100000 + 8 * 64 * 1024 + 16384
+    need = G // 8 + G // 32 + 8 * G + 8 * 64 * 1024 + 16384 + 16 * 100000
     assert need <= n.value < need + 4096
     assert lib.muvo_points_workspace_bytes(-1, 1, C.byref(g), C.byref(r), C.byref(n)) == -2
     assert lib.muvo_points_workspace_bytes(10, 1, C.byref(g), C.byref(r), None) == -1
