@@ -708,8 +708,6 @@ __device__ __forceinline__ bool pair_filter(bool in, uint32_t bit /* 0xffffffff 
   return in && !beaten;
 }
 
-constexpr int kLock = 2;   // points of a thread whose atomics are in flight together
-
 template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
 __global__ void __launch_bounds__(kTileThreads, 4)
 k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
@@ -745,85 +743,66 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
       const bool packl_f = (tl.fend - tl.fbeg) < kPackLimit;
       const uint32_t idx1_0 = (uint32_t)(tl.base - tl.fbeg) + (uint32_t)tid + 1u;     // 1-based frame-relative index, k = 0
       const uint32_t rel_0 = (uint32_t)(tl.base - blk_first) + (uint32_t)tid;         // CTA-relative index, k = 0
-#pragma unroll
-      for (int h = 0; h < kKPL / kLock; ++h) {
-        u64 *pslot[kLock], *vslot[kLock];
-        uint32_t* bword[kLock];
-        u64 pmine[kLock], vmine[kLock], pold[kLock], vold[kLock];
-        uint32_t vbit[kLock];
-        bool pact[kLock], vact[kLock], vpackl[kLock];
-#pragma unroll
-        for (int u = 0; u < kLock; ++u) {
-          const int k = h * kLock + u;
-          T x, y, z; uint32_t lab;
-          bool valid = true;
-          int fk = tl.f; int64_t fb = tl.fbeg;
-          bool packl = packl_f;
-          if (FAST) {
-            x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
-            lab = ss[k * kTileThreads];
-          } else {
-            valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
-            tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
-            packl = (__ldg(off + fk + 1) - fb) < kPackLimit;
-          }
-          const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
-          pact[u] = false; pslot[u] = pixtab; pmine[u] = 0ull;
-          vact[u] = false; vslot[u] = vtab; vmine[u] = 0ull; vbit[u] = 0u; bword[u] = bitmap; vpackl[u] = packl;
-          if (DO_VOX) {
-            uint32_t bit = 0xffffffffu, top = 0u; bool in = false;
-            if (valid) {
-              double dis;
-              if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) bit = v.bit; }
-              else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); in = v.in; dis = v.dis; if (in) bit = v.bit; }
-              top = key_top_inv(vox_key(dis, (int)lab != g.road));
-            }
-            n_in += in ? 1u : 0u;
-            const bool go = use_filter ? pair_filter<FAST>(in, bit, fk, top) : in;
-            if (go) {
-              vact[u] = true;
-              vbit[u] = bit;
-              vslot[u] = (FAST ? vtab_f : vtab + (size_t)fk * g.G) + bit;
-              bword[u] = (FAST ? bitmap_f : bitmap + (size_t)fk * g.gw) + (bit >> 5);
-              vmine[u] = vox_word(packl, top, me1, lab);
-            }
-          }
-          if (DO_RANGE && valid) {
-            const PixFast pk = pix_fast(x, y, z, r);
-            if (!pk.ok) ++n_drop;
-            else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, kQExact);
-            else {
-              pact[u] = true;
-              pslot[u] = (FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix;
-              // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
-              pmine[u] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), me1);
-            }
-          }
-        }
+      // results of the previous point's atomics, looked at one point later so that their latency is covered by the
+      // next point's arithmetic
+      struct Pending { u64 vold, pold; uint32_t bit, vtop, ptop, rel; int fk; bool vgo, pgo, packl; };
+      auto settle = [&](const Pending& d) {
         if (DO_VOX) {
-#pragma unroll
-          for (int u = 0; u < kLock; ++u) vold[u] = vact[u] ? atomicMax(vslot[u], vmine[u]) : 1ull;
+          if (d.vold == 0ull)                                               // first claim of the voxel marks it occupied
+            atomicOr((FAST ? bitmap_f : bitmap + (size_t)d.fk * g.gw) + (d.bit >> 5), 1u << (d.bit & 31));
+          else if (d.vgo && word_top(d.vold) == d.vtop)                     // same top-32 class: exact protocol
+            q[atomicAdd(qn, 1u)] = make_uint2(d.rel | kQVoxel, vox_word_idx1(d.packl, d.vold));
         }
         if (DO_RANGE) {
-#pragma unroll
-          for (int u = 0; u < kLock; ++u) pold[u] = pact[u] ? atomicMax(pslot[u], pmine[u]) : 0ull;
+          if (d.pgo && d.pold != 0ull && word_top(d.pold) == d.ptop) q[atomicAdd(qn, 1u)] = make_uint2(d.rel, word_idx1(d.pold));
         }
+      };
+      Pending prev{1ull, 0ull, 0u, 0u, 0u, 0u, 0, false, false, false};
+#pragma unroll
+      for (int k = 0; k < kKPL; ++k) {
+        T x, y, z; uint32_t lab;
+        bool valid = true;
+        int fk = tl.f; int64_t fb = tl.fbeg;
+        bool packl = packl_f;
+        if (FAST) {
+          x = sx[3 * k * kTileThreads]; y = sx[3 * k * kTileThreads + 1]; z = sx[3 * k * kTileThreads + 2];
+          lab = ss[k * kTileThreads];
+        } else {
+          valid = tl.load(k * kTileThreads + tid, &x, &y, &z, &lab);
+          tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
+          packl = (__ldg(off + fk + 1) - fb) < kPackLimit;
+        }
+        const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
+        Pending cur{1ull, 0ull, 0xffffffffu, 0u, 0u, rel_0 + k * kTileThreads, fk, false, false, packl};
         if (DO_VOX) {
-#pragma unroll
-          for (int u = 0; u < kLock; ++u) {
-            if (vold[u] == 0ull) atomicOr(bword[u], 1u << (vbit[u] & 31));     // first claim of the voxel marks it occupied
-            else if (vact[u] && word_top(vold[u]) == word_top(vmine[u]))       // same top-32 class: exact protocol
-              q[atomicAdd(qn, 1u)] = make_uint2((rel_0 + (h * kLock + u) * kTileThreads) | kQVoxel, vox_word_idx1(vpackl[u], vold[u]));
+          bool in = false;
+          uint32_t top = 0u;
+          if (valid) {
+            double dis;
+            if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) cur.bit = v.bit; }
+            else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); in = v.in; dis = v.dis; if (in) cur.bit = v.bit; }
+            top = key_top_inv(vox_key(dis, (int)lab != g.road));
+          }
+          n_in += in ? 1u : 0u;
+          cur.vgo = use_filter ? pair_filter<FAST>(in, cur.bit, fk, top) : in;
+          cur.vtop = top;
+          if (cur.vgo) cur.vold = atomicMax((FAST ? vtab_f : vtab + (size_t)fk * g.G) + cur.bit, vox_word(packl, top, me1, lab));
+        }
+        if (DO_RANGE && valid) {
+          const PixFast pk = pix_fast(x, y, z, r);
+          if (!pk.ok) ++n_drop;
+          else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(cur.rel, kQExact);
+          else {
+            cur.pgo = true;
+            // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
+            cur.ptop = key_top_inv((u64)__double_as_longlong(pk.s));
+            cur.pold = atomicMax((FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix, pack_word(cur.ptop, me1));
           }
         }
-        if (DO_RANGE) {
-#pragma unroll
-          for (int u = 0; u < kLock; ++u) {
-            if (pact[u] && pold[u] != 0ull && word_top(pold[u]) == word_top(pmine[u]))
-              q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + (h * kLock + u) * kTileThreads, word_idx1(pold[u]));
-          }
-        }
+        if (k > 0) settle(prev);
+        prev = cur;
       }
+      settle(prev);
     };
     if (tl.full && tl.one_frame) body(std::true_type{}); else body(std::false_type{});
     __syncthreads();                         // tile buffer free for the copy issued by the next next()
@@ -857,76 +836,128 @@ __device__ __forceinline__ void load_word_and_rank(uint32_t* __restrict__ bitmap
   *word_o = word; *rank_o = rank;
 }
 
-// Dense grid, bitmap in dense order.  A warp owns 32 words = 1024 voxels = 1 KiB of output, written as two fully
-// coalesced 512-byte store instructions (lane j writes 16-byte pieces j and 32+j).  The winner word of every set bit
-// is fetched from (and cleared in) the voxel table; the first gathers of a piece are issued back to back.
+// Dense grid, bitmap in dense order.  A lane owns one bitmap word = 32 voxels = 32 output bytes, written with ONE
+// 256-bit store (sm_100 st.global.v8.b32), so a warp store is a fully coalesced 1 KiB; zeros are part of the
+// store (no memset + scatter).  The winner word of every set bit is fetched from (and cleared in) the voxel table,
+// up to 4 independent gathers in flight per lane.
 // grid = (gw / kBlock, F): blockIdx.y is the frame, so no 64-bit division is needed.
+__device__ __forceinline__ void st_stream_u8x32(void* p, const uint32_t (&o)[8]) {
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+constexpr int kEmitWords = 2;       // bitmap words per lane: a warp owns 64 words = 2048 voxels = 2 KiB of output (3+ words per lane is 5x slower: measured)
+constexpr int kEmitList = 512;     // set-bit positions staged per warp (more than that: rounds)
+struct EmitSmem {
+  uint8_t tile[kBlock / 32][kEmitWords * 1024];   // per warp: the 4 KiB it is about to store, assembled from label bytes
+  uint16_t list[kBlock / 32][kEmitList];          // per warp: positions (voxel offset inside the warp's span) of set bits
+  uint32_t occ[kBlock / 32];
+};
+// byte `pos` of a warp tile: rows of 32 bytes (one bitmap word); the two 16-byte halves of a row are swapped on every
+// other group of 4 rows so that the 128-bit row reads of 8 consecutive lanes hit 8 different bank groups
+__device__ __forceinline__ uint32_t tile_swz(uint32_t pos) { return pos ^ ((pos >> 3) & 16u); }
+
+__device__ __forceinline__ void st_plain_u8x32(void* p, const uint32_t (&o)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+__device__ __forceinline__ void st_cg_u8x32(void* p, const uint32_t (&o)[8]) {
+  asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
 __global__ void __launch_bounds__(kBlock)
 k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_t* __restrict__ off,
              const uint8_t* __restrict__ sem, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
-             int64_t* __restrict__ n_occ) {
-  __shared__ uint32_t occ_s[kBlock / 32];
+             int64_t* __restrict__ n_occ, int dbg) {
+  extern __shared__ __align__(16) unsigned char emit_raw[];
+  EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_raw);
   const int f = blockIdx.y;
-  const uint32_t wi = blockIdx.x * kBlock + threadIdx.x;        // word index inside the frame
-  const bool valid = wi < (uint32_t)g.gw;
-  const int64_t wg = (int64_t)f * g.gw + wi;
-  const uint32_t word = valid ? bitmap[wg] : 0u;
-  if (word) bitmap[wg] = 0u;
   const unsigned lane = lane_id();
+  const int warp = threadIdx.x >> 5;
+  // lane L takes words L, L+32, L+64, L+96 of the warp's 128, so that every load / store instruction of the warp is
+  // contiguous; row r = k*32 + L of the tile belongs to word (warp_w0 + r)
+  const uint32_t warp_w0 = (blockIdx.x * (kBlock / 32) + warp) * (32 * kEmitWords);
+  uint32_t* bm = bitmap + (size_t)f * g.gw;
+  uint32_t bits[kEmitWords];
+  uint32_t pc = 0;
+#pragma unroll
+  for (int k = 0; k < kEmitWords; ++k) {
+    const uint32_t wi = warp_w0 + 32u * k + lane;
+    bits[k] = wi < (uint32_t)g.gw ? bm[wi] : 0u;
+    pc += __popc(bits[k]);
+  }
+  uint8_t* tile = sm.tile[warp];
+#pragma unroll
+  for (int k = 0; k < kEmitWords; ++k) {                        // zero this lane's rows
+    uint4* row = reinterpret_cast<uint4*>(tile + (k * 32 + lane) * 32);
+    row[0] = make_uint4(0u, 0u, 0u, 0u); row[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (bits[k] && !(dbg & 8)) bm[warp_w0 + 32u * k + lane] = 0u;
+  }
+  uint32_t incl = pc;                                           // position of this lane's set bits in the warp's list
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
   if (n_occ) {                                                  // occupied voxels of the frame: one atomic per CTA
-    const uint32_t c = __reduce_add_sync(0xffffffffu, __popc(word));
-    if (lane == 0) occ_s[threadIdx.x >> 5] = c;
+    if (lane == 0) sm.occ[warp] = total;
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t t = 0;
 #pragma unroll
-      for (int k = 0; k < kBlock / 32; ++k) t += occ_s[k];
+      for (int k = 0; k < kBlock / 32; ++k) t += sm.occ[k];
       if (t) atomicAdd(reinterpret_cast<unsigned long long*>(n_occ + f), (unsigned long long)t);
     }
   }
-  const uint32_t warp_w0 = wi - lane;                           // gw % 32 == 0: a warp never straddles frames
-  if (warp_w0 >= (uint32_t)g.gw) return;                        // whole warp out of range
-  const int64_t fb = __ldg(off + f);
-  const bool packl = (__ldg(off + f + 1) - fb) < kPackLimit;
-  const uint8_t* sem_f = sem + fb;
-  const uint32_t vox0 = warp_w0 * 32u;                          // first voxel of the warp inside the frame
-  u64* vt = vtab + (size_t)f * g.G + vox0;
-  uint8_t* dst = dense + (size_t)f * g.G + vox0;
-  const bool fast = ((g.G & 15) == 0) && ((reinterpret_cast<uintptr_t>(dense) & 15) == 0);
+  if (warp_w0 >= (uint32_t)g.gw) return;                        // whole warp out of range (gw % 32 == 0)
+  if (total) {                                                  // warp-uniform
+    const int64_t fb = __ldg(off + f);
+    const bool packl = (__ldg(off + f + 1) - fb) < kPackLimit;
+    const uint8_t* sem_f = sem + fb;
+    u64* vt = vtab + (size_t)f * g.G + (size_t)warp_w0 * 32;
+    uint16_t* list = sm.list[warp];
+    // the set bits of the whole span are gathered cooperatively: lane t takes the t-th, t+32-th, ... set bit, so all
+    // gathers of a round are in flight together no matter how they are spread over the words
+    for (uint32_t done = 0; done < total; done += kEmitList) {  // rounds only for spans with > kEmitList set bits
+      uint32_t n = incl - pc;                                   // list index of this lane's first set bit
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const unsigned src = (unsigned)half * 16u + (lane >> 1);    // lane j handles piece p = half*32 + j -> word p/2
-    const uint32_t w = __shfl_sync(0xffffffffu, word, src);
-    uint32_t bits = (lane & 1u) ? (w >> 16) : (w & 0xffffu);
-    const uint32_t piece = (uint32_t)half * 32u + lane;
-    u64* pv = vt + piece * 16;
-    uint32_t o[4] = {0u, 0u, 0u, 0u};
-    while (bits) {
-      int js[4];
-      u64 ws[4];
-      int n = 0;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {                              // up to 4 independent gathers in flight
-        js[u] = 0; ws[u] = 0ull;
-        if (bits) { js[u] = __ffs(bits) - 1; bits &= bits - 1; ws[u] = pv[js[u]]; ++n; }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (u < n) {
-          pv[js[u]] = 0ull;
-          uint32_t lab = vox_word_label(packl, ws[u], sem_f);
-          if (remap) lab = __ldg(remap + lab);
-          o[js[u] >> 2] |= lab << (8 * (js[u] & 3));
+      for (int k = 0; k < kEmitWords; ++k) {
+        uint32_t b = bits[k];
+        while (b) {
+          const int j = __ffs(b) - 1;
+          b &= b - 1;
+          if (n - done < (uint32_t)kEmitList) list[n - done] = (uint16_t)((k * 32 + lane) * 32 + j);
+          ++n;
         }
       }
+      __syncwarp();
+      const uint32_t cnt = total - done < (uint32_t)kEmitList ? total - done : (uint32_t)kEmitList;
+      for (uint32_t t = lane; t < cnt; t += 32) {
+        const uint32_t pos = list[t];
+        const u64 wv = (dbg & 1) ? (u64)pos : vt[pos];
+        if (!(dbg & 2)) vt[pos] = 0ull;
+        uint32_t lab = vox_word_label(packl, wv, sem_f);
+        if (remap && !(dbg & 4)) lab = __ldg(remap + lab);
+        tile[tile_swz(pos)] = (uint8_t)lab;
+      }
+      __syncwarp();
     }
-    const int64_t v = (int64_t)vox0 + piece * 16;               // first voxel of this piece
-    __syncwarp();   // reconverge after the data-dependent loop so that the store below is one 512-byte request
-    if (fast) {
-      if (v + 16 <= g.G) st_stream_u4(reinterpret_cast<uint4*>(dst + piece * 16), make_uint4(o[0], o[1], o[2], o[3]));
+  }
+  uint8_t* df = dense + (size_t)f * g.G;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(df) & 31) == 0);
+#pragma unroll
+  for (int k = 0; k < kEmitWords; ++k) {
+    const uint32_t r = k * 32 + lane, wi = warp_w0 + r;
+    if (wi >= (uint32_t)g.gw) continue;
+    const uint32_t sw = (r >> 2) & 1u;                          // this row's halves are swapped
+    const uint4 h0 = *reinterpret_cast<const uint4*>(tile + r * 32 + 16 * sw);
+    const uint4 h1 = *reinterpret_cast<const uint4*>(tile + r * 32 + 16 * (sw ^ 1u));
+    const uint32_t o[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+    const int64_t vox = (int64_t)wi * 32;                       // first voxel of the word inside the frame
+    uint8_t* dst = df + vox;
+    if (dbg & 16) { if (o[0] == 0x12345678u) dst[0] = 1; continue; }
+    if (vox + 32 <= g.G && aligned) {
+      if (dbg & 32) st_plain_u8x32(dst, o); else if (dbg & 64) st_cg_u8x32(dst, o); else st_stream_u8x32(dst, o);
     } else {
-      for (int j = 0; j < 16; ++j)
-        if (v + j < g.G) dense[(size_t)f * g.G + v + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+      for (int j = 0; j < 32; ++j)
+        if (vox + j < g.G) dst[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
     }
   }
 }
@@ -1238,13 +1269,15 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       MUVO_AFTER_LAUNCH("k_scan_queue", st);
     }
   }
-  if (do_range && (rc = emit_range()) != MUVO_OK) return rc;   // right after its producers: the pixel words are still L2 resident
+  if (do_range && !(g_tuning[3] & 1) && (rc = emit_range()) != MUVO_OK) return rc;   // right after its producers: the pixel words are still L2 resident
   if (do_vox) {
     // K5 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;
     if (!need_scan) {
-      dim3 grid((unsigned)ceil_div64(g.gw, kBlock), (unsigned)F);
-      k_emit_dense<<<grid, kBlock, 0, st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F, n_occ_emit);
+      dim3 grid((unsigned)ceil_div64(g.gw, kBlock * kEmitWords), (unsigned)F);
+      cudaError_t e = cudaFuncSetAttribute(k_emit_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
+      if (e != cudaSuccess) return (int)e;
+      k_emit_dense<<<grid, kBlock, sizeof(EmitSmem), st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F, n_occ_emit, g_tuning[2]);
       MUVO_AFTER_LAUNCH("k_emit_dense", st);
     } else {
       if (dense) {
@@ -1255,6 +1288,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       MUVO_AFTER_LAUNCH("k_emit_sparse", st);
     }
   }
+  if (do_range && (g_tuning[3] & 1) && (rc = emit_range()) != MUVO_OK) return rc;
   return MUVO_OK;
 }
 
