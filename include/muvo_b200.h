@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MUVO_B200_ABI_VERSION 1
+#define MUVO_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MUVO_API __attribute__((visibility("default")))
@@ -96,6 +96,11 @@ MUVO_API int muvo_profile_begin(void* stream);
 MUVO_API int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char** names_out_h,
                               int32_t* n_out_h);
 
+/* ---- host staging ---------------------------------------------------------------
+ * memcpy of `bytes` split over up to n_threads host threads (0 = one per core, capped): fills pinned staging buffers
+ * from the application's pageable arrays at several times the single-thread rate.  Blocking; no CUDA call inside. */
+MUVO_API int muvo_host_copy(void* dst_h, const void* src_h, size_t bytes, int32_t n_threads);
+
 /* ---- workspace ------------------------------------------------------------------ */
 /* Bytes needed by the point kernels for `n_frames` frames / `n_points_total` points.
  * grid_h or range_h may be NULL when that stage is not used.                        */
@@ -111,14 +116,16 @@ MUVO_API int muvo_ws_reset(void* ws, size_t ws_bytes, void* stream);
  *   sem        [P]    uint8
  *   remap256   [256]  uint8 label remap applied to dense_out only, or NULL
  *   dense_out  [F,Dx,Dy,Dz] uint8 (fully written, 0 = empty), or NULL
- *   sparse_out [P,4]  uint16 rows (x,y,z,label) ; frame f's n_occ[f] rows start at row
- *                     frame_offsets[f], ordered by x + y*Dx + z*Dx*Dy (:184,:187), or NULL
+ *   sparse_out [P,4]  uint16 rows (x,y,z,label), ordered by x + y*Dx + z*Dx*Dy (:184,:187), or NULL; frame f's
+ *                     n_occ[f] rows start at row frame_offsets[f], or -- when sparse_start_out is given -- at row
+ *                     sparse_start_out[f]: the frames' lists back to back (a read-back then moves only the rows used)
  *   n_occ_out  [F]    int64 occupied voxels per frame, or NULL
+ *   sparse_start_out [F+1] int64 exclusive prefix of n_occ (needs sparse_out and n_occ_out), or NULL
  *   diag       [MUVO_DIAG_COUNT] int64, accumulated into (caller zeroes), or NULL        */
 MUVO_API int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* sem, const int64_t* frame_offsets,
                   int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
-                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* diag,
-                  void* ws, size_t ws_bytes, void* stream);
+                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* sparse_start_out,
+                  int64_t* diag, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- (b) range-view projection ---------------------------------------------------
  * Replaces PointCloud.do_range_projection(), muvo/utils/geometry_utils.py:175-220.
@@ -132,8 +139,8 @@ MUVO_API int muvo_range_project(const float* xyz, const uint8_t* sem, const int6
 MUVO_API int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
                       int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
                       const MuvoRangeCfg* cfg_h, int32_t layout, uint8_t* dense_out, uint16_t* sparse_out,
-                      int64_t* n_occ_out, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag,
-                      void* ws, size_t ws_bytes, void* stream);
+                      int64_t* n_occ_out, int64_t* sparse_start_out, float* depth_out, float* xyz_out, uint8_t* sem_out,
+                      int64_t* diag, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- (c) lift-splat BEV pooling ---------------------------------------------------
  * Replaces FrustumPooling.voxel_pooling + QuickCumsum (muvo/models/frustum_pooling.py:34-60,

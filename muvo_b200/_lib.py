@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmuvo_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 # dtype codes (include/muvo_b200.h)
 F32, F64, F16, BF16 = 0, 1, 2, 3
 I64, I32, U8, I16 = 0, 1, 2, 3
@@ -45,10 +45,11 @@ SIGNATURES = {
     "muvo_profile_end": (C.c_int, [_P, _I32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(_I32)]),
     "muvo_points_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(MuvoGrid), C.POINTER(MuvoRangeCfg), C.POINTER(_SZ)]),
     "muvo_ws_reset": (C.c_int, [_P, _SZ, _P]),
-    "muvo_voxelize": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "muvo_voxelize": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_range_project": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoRangeCfg), _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_points_fused": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, C.POINTER(MuvoRangeCfg), _I32,
-                                    _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "muvo_host_copy": (C.c_int, [_P, _P, _SZ, _I32]),
     "muvo_bev_pool_workspace_bytes": (C.c_int, [_I32, _I64, _I32, C.POINTER(_SZ)]),
     "muvo_bev_pool_fwd": (C.c_int, [_P, _I32, _I64, _I64, _I64, _P, _I32, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "muvo_bev_pool_bwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _I32, _I64, _I64, _I64, _P]),

@@ -1,5 +1,8 @@
 // ABI version + error strings.
 #include "common.cuh"
+#include <cstring>
+#include <thread>
+#include <vector>
 
 namespace muvo {
 Profile& profile_state() {
@@ -38,6 +41,32 @@ int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char
     ++n;
   }
   *n_out_h = n;
+  return MUVO_OK;
+}
+
+int muvo_host_copy(void* dst_h, const void* src_h, size_t bytes, int32_t n_threads) {
+  if (bytes == 0) return MUVO_OK;
+  if (!dst_h || !src_h) return MUVO_E_NULL;
+  if (n_threads < 0) return MUVO_E_ARG;
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  size_t nt = n_threads > 0 ? (size_t)n_threads : (hw > 16 ? 16 : hw);
+  const size_t min_chunk = (size_t)1 << 20;                       // below 1 MiB per thread the spawn costs more than it saves
+  if (nt > (bytes + min_chunk - 1) / min_chunk) nt = (bytes + min_chunk - 1) / min_chunk;
+  if (nt <= 1) { std::memcpy(dst_h, src_h, bytes); return MUVO_OK; }
+  const size_t chunk = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  char* d = (char*)dst_h;
+  const char* s = (const char*)src_h;
+  for (size_t t = 1; t < nt; ++t) {
+    const size_t o = t * chunk;
+    if (o >= bytes) break;
+    const size_t n = bytes - o < chunk ? bytes - o : chunk;
+    th.emplace_back([=] { std::memcpy(d + o, s + o, n); });
+  }
+  std::memcpy(d, s, chunk < bytes ? chunk : bytes);
+  for (auto& t : th) t.join();
   return MUVO_OK;
 }
 

@@ -43,6 +43,9 @@ int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
 
+#ifndef MUVO_K1_MINB
+#define MUVO_K1_MINB 4
+#endif
 constexpr int kBlock = 256;
 constexpr int kMaxTileCtas = 4096;                   // upper bound of the persistent tile grid (queue length slots)
 constexpr double kPi = 3.141592653589793;            // np.pi
@@ -60,6 +63,7 @@ struct GridDev {
   int pow2;
   int regular;   // pow2 res and upper == size*res exactly: in-grid test and voxel id from one floor per axis
   int order;
+  uint32_t sx, sy, sz;   // bit index = ix*sx + iy*sy + iz*sz (per `order`)
   int gw;        // bitmap words per frame (multiple of 32)
   int64_t G;     // voxels per frame
 };
@@ -226,8 +230,7 @@ __device__ __forceinline__ VoxFast vox_regular(T x, T y, T z, const GridDev& g) 
   const uint32_t ix = (uint32_t)__double2loint(v.sx), iy = (uint32_t)__double2loint(v.sy), iz = (uint32_t)__double2loint(v.sz);
   v.in = (__double2hiint(v.sx) == 0x43300000) & (__double2hiint(v.sy) == 0x43300000) & (__double2hiint(v.sz) == 0x43300000) &
          (ix < (uint32_t)g.dx) & (iy < (uint32_t)g.dy) & (iz < (uint32_t)g.dz);
-  v.bit = (g.order == ORDER_DENSE) ? (ix * (uint32_t)g.dy + iy) * (uint32_t)g.dz + iz
-                                   : ix + (uint32_t)g.dx * (iy + (uint32_t)g.dy * iz);
+  v.bit = ix * g.sx + iy * g.sy + iz * g.sz;
   return v;
 }
 // |p mod res|^2 for an in-grid point of a regular grid: b - floor(b/res)*res is exact (so the fma equals numpy's
@@ -622,11 +625,13 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
   const int64_t blk_first = (int64_t)t0 * kTile;
   const uint2* q = a.queue + 2 * blk_first;
   unsigned n_drop = 0, n_nw = 0, n_nh = 0;
+  const int f_first = find_frame(a.off, a.F, blk_first);      // a CTA's points span few frames: walk from its first one
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     const uint2 ent = q[e];
     const int64_t i = blk_first + (int64_t)(ent.x & ~kQVoxel);
     const T x = __ldg(a.xyz + 3 * i), y = __ldg(a.xyz + 3 * i + 1), z = __ldg(a.xyz + 3 * i + 2);
-    const int f = find_frame(a.off, a.F, i);
+    int f = f_first;
+    while (f + 1 < a.F && i >= __ldg(a.off + f + 1)) ++f;
     const int64_t fb = __ldg(a.off + f);
     const T* fx = a.xyz + 3 * fb;
     const uint32_t me1 = (uint32_t)(i - fb) + 1u;
@@ -709,7 +714,7 @@ __device__ __forceinline__ bool pair_filter(bool in, uint32_t bit /* 0xffffffff 
 }
 
 template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
-__global__ void __launch_bounds__(kTileThreads, 4)
+__global__ void __launch_bounds__(kTileThreads, MUVO_K1_MINB)
 k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
               bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, u64* __restrict__ pixtab,
               uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ n_occ_zero, int flags,
@@ -733,14 +738,18 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
   while (tl.next()) {
     // FAST = the tile is staged in shared memory and lies inside one frame (all but a handful of tiles): frame
     // bases, table rows and the shared-memory cursor are CTA-uniform and hoisted out of the per-point code.
-    auto body = [&](auto fast_tag) {
+    const bool packl_tile = (tl.fend - tl.fbeg) < kPackLimit;
+    auto body = [&](auto fast_tag, auto packl_tag) {
       constexpr bool FAST = decltype(fast_tag)::value;
+      constexpr bool PACKL_T = decltype(packl_tag)::value;          // FAST only: the tile's frame uses the label-carrying word
       const T* sx = reinterpret_cast<const T*>(smem + (size_t)tl.st * L::xyz_bytes) + 3 * tid;
       const uint8_t* ss = smem + L::off_sem + (size_t)tl.st * kTile + tid;
       uint32_t* bitmap_f = bitmap + (size_t)tl.f * g.gw;
       u64* vtab_f = vtab + (size_t)tl.f * g.G;
       u64* pixtab_f = pixtab + (size_t)tl.f * HW;
-      const bool packl_f = (tl.fend - tl.fbeg) < kPackLimit;
+      // keep the three table rows in registers (the compiler would otherwise re-derive them from f for every point)
+      asm volatile("" : "+l"(bitmap_f), "+l"(vtab_f), "+l"(pixtab_f));
+      const bool packl_f = FAST ? PACKL_T : packl_tile;
       const uint32_t idx1_0 = (uint32_t)(tl.base - tl.fbeg) + (uint32_t)tid + 1u;     // 1-based frame-relative index, k = 0
       const uint32_t rel_0 = (uint32_t)(tl.base - blk_first) + (uint32_t)tid;         // CTA-relative index, k = 0
       // results of the previous point's atomics, looked at one point later so that their latency is covered by the
@@ -804,7 +813,11 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
       }
       settle(prev);
     };
-    if (tl.full && tl.one_frame) body(std::true_type{}); else body(std::false_type{});
+    if (tl.full && tl.one_frame) {
+      if (packl_tile) body(std::true_type{}, std::true_type{}); else body(std::true_type{}, std::false_type{});
+    } else {
+      body(std::false_type{}, std::false_type{});
+    }
     __syncthreads();                         // tile buffer free for the copy issued by the next next()
   }
   if (tid == 0) qcount[blockIdx.x] = *qn;
@@ -856,26 +869,20 @@ struct EmitSmem {
 // other group of 4 rows so that the 128-bit row reads of 8 consecutive lanes hit 8 different bank groups
 __device__ __forceinline__ uint32_t tile_swz(uint32_t pos) { return pos ^ ((pos >> 3) & 16u); }
 
-__device__ __forceinline__ void st_plain_u8x32(void* p, const uint32_t (&o)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
-               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-}
-__device__ __forceinline__ void st_cg_u8x32(void* p, const uint32_t (&o)[8]) {
-  asm volatile("st.global.cg.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
-               "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
-}
-__global__ void __launch_bounds__(kBlock)
-k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_t* __restrict__ off,
-             const uint8_t* __restrict__ sem, const uint8_t* __restrict__ remap, uint8_t* __restrict__ dense, GridDev g, int F,
-             int64_t* __restrict__ n_occ, int dbg) {
-  extern __shared__ __align__(16) unsigned char emit_raw[];
-  EmitSmem& sm = *reinterpret_cast<EmitSmem*>(emit_raw);
-  const int f = blockIdx.y;
+struct EmitDenseArgs {
+  uint32_t* bitmap; u64* vtab; const int64_t* off; const uint8_t* sem; const uint8_t* remap; uint8_t* dense; int64_t* n_occ;
+  int blocks_per_frame;
+};
+// CTA `bx` of frame `f`
+__device__ __forceinline__ void emit_dense_body(int bx, int f, EmitSmem& sm, const EmitDenseArgs& a, const GridDev& g) {
+  uint32_t* __restrict__ bitmap = a.bitmap; u64* __restrict__ vtab = a.vtab; const int64_t* __restrict__ off = a.off;
+  const uint8_t* __restrict__ sem = a.sem; const uint8_t* __restrict__ remap = a.remap; uint8_t* __restrict__ dense = a.dense;
+  int64_t* __restrict__ n_occ = a.n_occ;
   const unsigned lane = lane_id();
   const int warp = threadIdx.x >> 5;
   // lane L takes words L, L+32, L+64, L+96 of the warp's 128, so that every load / store instruction of the warp is
   // contiguous; row r = k*32 + L of the tile belongs to word (warp_w0 + r)
-  const uint32_t warp_w0 = (blockIdx.x * (kBlock / 32) + warp) * (32 * kEmitWords);
+  const uint32_t warp_w0 = ((uint32_t)bx * (kBlock / 32) + warp) * (32 * kEmitWords);
   uint32_t* bm = bitmap + (size_t)f * g.gw;
   uint32_t bits[kEmitWords];
   uint32_t pc = 0;
@@ -890,7 +897,7 @@ k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_
   for (int k = 0; k < kEmitWords; ++k) {                        // zero this lane's rows
     uint4* row = reinterpret_cast<uint4*>(tile + (k * 32 + lane) * 32);
     row[0] = make_uint4(0u, 0u, 0u, 0u); row[1] = make_uint4(0u, 0u, 0u, 0u);
-    if (bits[k] && !(dbg & 8)) bm[warp_w0 + 32u * k + lane] = 0u;
+    if (bits[k]) bm[warp_w0 + 32u * k + lane] = 0u;
   }
   uint32_t incl = pc;                                           // position of this lane's set bits in the warp's list
 #pragma unroll
@@ -931,10 +938,10 @@ k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_
       const uint32_t cnt = total - done < (uint32_t)kEmitList ? total - done : (uint32_t)kEmitList;
       for (uint32_t t = lane; t < cnt; t += 32) {
         const uint32_t pos = list[t];
-        const u64 wv = (dbg & 1) ? (u64)pos : vt[pos];
-        if (!(dbg & 2)) vt[pos] = 0ull;
+        const u64 wv = vt[pos];
+        vt[pos] = 0ull;
         uint32_t lab = vox_word_label(packl, wv, sem_f);
-        if (remap && !(dbg & 4)) lab = __ldg(remap + lab);
+        if (remap) lab = __ldg(remap + lab);
         tile[tile_swz(pos)] = (uint8_t)lab;
       }
       __syncwarp();
@@ -952,9 +959,8 @@ k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_
     const uint32_t o[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
     const int64_t vox = (int64_t)wi * 32;                       // first voxel of the word inside the frame
     uint8_t* dst = df + vox;
-    if (dbg & 16) { if (o[0] == 0x12345678u) dst[0] = 1; continue; }
     if (vox + 32 <= g.G && aligned) {
-      if (dbg & 32) st_plain_u8x32(dst, o); else if (dbg & 64) st_cg_u8x32(dst, o); else st_stream_u8x32(dst, o);
+      st_stream_u8x32(dst, o);
     } else {
       for (int j = 0; j < 32; ++j)
         if (vox + j < g.G) dst[j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
@@ -962,11 +968,46 @@ k_emit_dense(uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, const int64_
   }
 }
 
-// Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(frame_offsets[f] + rank)].
+__global__ void __launch_bounds__(kBlock)
+k_emit_dense(EmitDenseArgs a, GridDev g) {
+  extern __shared__ __align__(16) unsigned char emit_raw[];
+  emit_dense_body((int)blockIdx.x, (int)blockIdx.y, *reinterpret_cast<EmitSmem*>(emit_raw), a, g);
+}
+
+// Packed sparse output: start[f] = number of occupied voxels in frames < f (start[F] = total).  One CTA.
+__global__ void __launch_bounds__(1024)
+k_frame_prefix(const int64_t* __restrict__ n_occ, int F, int64_t* __restrict__ start) {
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < F; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int64_t v = i < F ? n_occ[i] : 0;
+    int64_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int64_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    const int64_t carry = carry_s;
+    int64_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += wsum[w];
+    __syncthreads();
+    if (i < F) start[i] = carry + wbase + incl - v;
+    if (threadIdx.x == 1023) carry_s = carry + wbase + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) start[F] = carry_s;
+}
+
+// Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(row0[f] + rank)], row0 = frame_offsets
+// (frame f's rows start where its points start) or `start` (packed: frames back to back).
 // sparse == nullptr: only clears the tables (n_occ-only calls).
 __global__ void __launch_bounds__(kBlock)
 k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vtab,
-              const int64_t* __restrict__ off, const uint8_t* __restrict__ sem, uint16_t* __restrict__ sparse, GridDev g, int F) {
+              const int64_t* __restrict__ off, const uint8_t* __restrict__ sem, uint16_t* __restrict__ sparse,
+              const int64_t* __restrict__ start, GridDev g, int F) {
   int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   int64_t total = (int64_t)F * g.gw;
   bool valid = wg < total;
@@ -978,6 +1019,7 @@ k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64*
   const bool packl = (__ldg(off + f + 1) - fbeg) < kPackLimit;
   uint32_t bit0 = (uint32_t)(wg - (int64_t)f * g.gw) * 32u;
   u64* vt = vtab + (size_t)f * g.G + bit0;
+  const int64_t row0 = start ? __ldg(start + f) : fbeg;
   uint32_t b = word;
   while (b) {
     int j = __ffs(b) - 1;
@@ -991,7 +1033,7 @@ k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64*
       uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
       uint32_t lab = vox_word_label(packl, wv, sem + fbeg);
       uint2 row = make_uint2(x | (y << 16), z | (lab << 16));
-      *reinterpret_cast<uint2*>(sparse + (size_t)(fbeg + rank) * 4) = row;
+      *reinterpret_cast<uint2*>(sparse + (size_t)(row0 + rank) * 4) = row;
     }
     ++rank;
   }
@@ -1023,13 +1065,18 @@ k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const u64* __restr
 }
 
 // Range image: one thread per NP pixels (NP = 4: 16-byte stores; NP = 1: generic fallback).
+template <typename T>
+struct EmitRangeArgs {
+  u64* pixtab; const T* xyz; const uint8_t* sem; const int64_t* off; int F; float* depth_out; float* xyz_out; uint8_t* sem_out;
+};
 template <typename T, int NP, int LAYOUT>
-__global__ void __launch_bounds__(kBlock)
-k_emit_range(u64* __restrict__ pixtab, const T* __restrict__ xyz, const uint8_t* __restrict__ sem,
-             const int64_t* __restrict__ off, RangeDev r, int F, float* __restrict__ depth_out, float* __restrict__ xyz_out,
-             uint8_t* __restrict__ sem_out, bool clean) {
+__device__ __forceinline__ void emit_range_body(int64_t vblock, const EmitRangeArgs<T>& a, const RangeDev& r) {
+  u64* __restrict__ pixtab = a.pixtab; const T* __restrict__ xyz = a.xyz; const uint8_t* __restrict__ sem = a.sem;
+  const int64_t* __restrict__ off = a.off; const int F = a.F;
+  float* __restrict__ depth_out = a.depth_out; float* __restrict__ xyz_out = a.xyz_out; uint8_t* __restrict__ sem_out = a.sem_out;
+  constexpr bool clean = true;
   const int64_t HW = (int64_t)r.H * r.W;
-  int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  int64_t t = vblock * kBlock + threadIdx.x;
   int64_t p0 = t * NP;                 // global pixel index over [F, H*W]
   if (p0 >= (int64_t)F * HW) return;
   int f = (int)(p0 / HW);
@@ -1089,6 +1136,10 @@ k_emit_range(u64* __restrict__ pixtab, const T* __restrict__ xyz, const uint8_t*
   }
 }
 
+template <typename T, int NP, int LAYOUT>
+__global__ void __launch_bounds__(kBlock)
+k_emit_range(EmitRangeArgs<T> a, RangeDev r) { emit_range_body<T, NP, LAYOUT>((int64_t)blockIdx.x, a, r); }
+
 // ---------------------------------------------------------------- test hook: f32 pixel path vs float64 formula
 __global__ void __launch_bounds__(kBlock)
 k_debug_pixel_check(const float* __restrict__ xyz, int64_t n, RangeDev r, unsigned long long* __restrict__ out) {
@@ -1134,6 +1185,8 @@ static int make_grid_dev(const MuvoGrid* g, int order, GridDev* o) {
   for (int k = 0; k < 3; ++k)
     if (!(g->upper[k] == (double)g->size[k] * g->res) || !isfinite(g->offset[k])) o->regular = 0;
   o->order = order;
+  if (order == ORDER_DENSE) { o->sx = (uint32_t)(g->size[1] * g->size[2]); o->sy = (uint32_t)g->size[2]; o->sz = 1u; }
+  else { o->sx = 1u; o->sy = (uint32_t)g->size[0]; o->sz = (uint32_t)(g->size[0] * g->size[1]); }
   o->gw = bitmap_words(G);
   o->G = G;
   return MUVO_OK;
@@ -1162,7 +1215,7 @@ static inline unsigned blocks_for(int64_t n) { return (unsigned)ceil_div64(n, kB
 template <typename T>
 static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int F, int64_t P, const MuvoGrid* grid_h,
                       const uint8_t* remap, const MuvoRangeCfg* cfg_h, int layout, uint8_t* dense, uint16_t* sparse,
-                      int64_t* n_occ, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws,
+                      int64_t* n_occ, int64_t* sparse_start, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   const bool do_vox = grid_h != nullptr, do_range = cfg_h != nullptr;
   if (!do_vox && !do_range) return MUVO_E_ARG;
@@ -1172,6 +1225,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   if (!off || !ws) return MUVO_E_NULL;
   if (P > 0 && (!xyz || !sem)) return MUVO_E_NULL;
   if (do_vox && !dense && !sparse && !n_occ) return MUVO_E_NULL;
+  if (sparse_start && (!sparse || !n_occ)) return MUVO_E_NULL;   // the packed layout needs the per-frame counts
   if (do_range && (!xyz_out || (layout == MUVO_RANGE_LAYOUT_HWC && (!depth_out || !sem_out)))) return MUVO_E_NULL;
   if (layout != MUVO_RANGE_LAYOUT_HWC && layout != MUVO_RANGE_LAYOUT_XYZD) return MUVO_E_ARG;
   if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
@@ -1205,22 +1259,19 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     return MUVO_OK;
   };
 
+  const int64_t HWr = do_range ? (int64_t)r.H * r.W : 0;
+  const bool range_vec4 = do_range && (HWr % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz_out) % 16 == 0) &&
+                          (!depth_out || reinterpret_cast<uintptr_t>(depth_out) % 16 == 0) &&
+                          (!sem_out || reinterpret_cast<uintptr_t>(sem_out) % 4 == 0);
+  EmitRangeArgs<T> era{w.pixtab, xyz, sem, off, F, depth_out, xyz_out, sem_out};
   auto emit_range = [&]() -> int {
-    const int64_t HW = (int64_t)r.H * r.W;
-    const bool vec4 = (HW % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz_out) % 16 == 0) &&
-                      (!depth_out || reinterpret_cast<uintptr_t>(depth_out) % 16 == 0) &&
-                      (!sem_out || reinterpret_cast<uintptr_t>(sem_out) % 4 == 0);
-    const int64_t npix = (int64_t)F * HW;
-    if (vec4) {
-      if (layout == MUVO_RANGE_LAYOUT_HWC)
-        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
-      else
-        k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+    const int64_t npix = (int64_t)F * HWr;
+    if (range_vec4) {
+      if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, st>>>(era, r);
+      else                                 k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, st>>>(era, r);
     } else {
-      if (layout == MUVO_RANGE_LAYOUT_HWC)
-        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
-      else
-        k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(w.pixtab, xyz, sem, off, r, F, depth_out, xyz_out, sem_out, true);
+      if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, st>>>(era, r);
+      else                                 k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(era, r);
     }
     MUVO_AFTER_LAUNCH("k_emit_range", st);
     return MUVO_OK;
@@ -1231,7 +1282,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   // the sorted sparse list needs ranks (bitmap scan); a dense-only call counts n_occ while it emits
   const bool need_scan = do_vox && (sparse != nullptr || dense == nullptr);
   int64_t* n_occ_emit = (do_vox && !need_scan) ? n_occ : nullptr;
-  const int flags = (g_tuning[1] == 1) ? 0 : 1;
+  const int flags = (g_tuning[1] & 1) ? 0 : 1;   // bit 0: neighbour filter before the voxel atomicMax
   // K1
   if (P > 0) {
     const void* fn;
@@ -1269,26 +1320,34 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       MUVO_AFTER_LAUNCH("k_scan_queue", st);
     }
   }
-  if (do_range && !(g_tuning[3] & 1) && (rc = emit_range()) != MUVO_OK) return rc;   // right after its producers: the pixel words are still L2 resident
+  const bool dense_fast = do_vox && !need_scan;                  // dense-order bitmap, dense grid (and n_occ) from k_emit_dense
+  // (running the two emits in one launch, CTAs interleaved, was measured: 150 us vs 61 + 75 us back to back)
+  if (do_range && (rc = emit_range()) != MUVO_OK) return rc;
   if (do_vox) {
     // K5 (the last consumer of the tables clears them)
     const int64_t words = (int64_t)F * g.gw;
-    if (!need_scan) {
-      dim3 grid((unsigned)ceil_div64(g.gw, kBlock * kEmitWords), (unsigned)F);
-      cudaError_t e = cudaFuncSetAttribute(k_emit_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
-      if (e != cudaSuccess) return (int)e;
-      k_emit_dense<<<grid, kBlock, sizeof(EmitSmem), st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F, n_occ_emit, g_tuning[2]);
-      MUVO_AFTER_LAUNCH("k_emit_dense", st);
+    if (dense_fast) {
+      const int bpf = (int)ceil_div64(g.gw, kBlock * kEmitWords);
+      EmitDenseArgs eda{w.bitmap, w.vtab, off, sem, remap, dense, n_occ_emit, bpf};
+      {
+        cudaError_t e = cudaFuncSetAttribute(k_emit_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
+        if (e != cudaSuccess) return (int)e;
+        k_emit_dense<<<dim3((unsigned)bpf, (unsigned)F), kBlock, sizeof(EmitSmem), st>>>(eda, g);
+        MUVO_AFTER_LAUNCH("k_emit_dense", st);
+      }
     } else {
       if (dense) {
         k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F);
         MUVO_AFTER_LAUNCH("k_emit_dense_from_linear", st);
       }
-      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vtab, off, sem, sparse, g, F);
+      if (sparse && sparse_start) {
+        k_frame_prefix<<<1, 1024, 0, st>>>(n_occ, F, sparse_start);
+        MUVO_AFTER_LAUNCH("k_frame_prefix", st);
+      }
+      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vtab, off, sem, sparse, sparse ? sparse_start : nullptr, g, F);
       MUVO_AFTER_LAUNCH("k_emit_sparse", st);
     }
   }
-  if (do_range && (g_tuning[3] & 1) && (rc = emit_range()) != MUVO_OK) return rc;
   return MUVO_OK;
 }
 
@@ -1334,16 +1393,16 @@ int muvo_ws_reset(void* ws, size_t ws_bytes, void* stream) {
 
 int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* sem, const int64_t* frame_offsets,
                   int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
-                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* diag, void* ws,
-                  size_t ws_bytes, void* stream) {
+                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* sparse_start_out, int64_t* diag,
+                  void* ws, size_t ws_bytes, void* stream) {
   if (!grid_h) return MUVO_E_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   if (xyz_dtype == MUVO_F32)
     return run_points<float>((const float*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256, nullptr,
-                             0, dense_out, sparse_out, n_occ_out, nullptr, nullptr, nullptr, diag, ws, ws_bytes, st);
+                             0, dense_out, sparse_out, n_occ_out, sparse_start_out, nullptr, nullptr, nullptr, diag, ws, ws_bytes, st);
   if (xyz_dtype == MUVO_F64)
     return run_points<double>((const double*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256,
-                              nullptr, 0, dense_out, sparse_out, n_occ_out, nullptr, nullptr, nullptr, diag, ws,
+                              nullptr, 0, dense_out, sparse_out, n_occ_out, sparse_start_out, nullptr, nullptr, nullptr, diag, ws,
                               ws_bytes, st);
   return MUVO_E_ARG;
 }
@@ -1353,17 +1412,17 @@ int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* fram
                        float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, void* stream) {
   if (!cfg_h) return MUVO_E_NULL;
   return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, nullptr, nullptr, cfg_h, layout, nullptr,
-                           nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes, (cudaStream_t)stream);
+                           nullptr, nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
                       int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
                       const MuvoRangeCfg* cfg_h, int32_t layout, uint8_t* dense_out, uint16_t* sparse_out,
-                      int64_t* n_occ_out, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws,
-                      size_t ws_bytes, void* stream) {
+                      int64_t* n_occ_out, int64_t* sparse_start_out, float* depth_out, float* xyz_out, uint8_t* sem_out,
+                      int64_t* diag, void* ws, size_t ws_bytes, void* stream) {
   if (!grid_h || !cfg_h) return MUVO_E_NULL;
   return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256, cfg_h, layout,
-                           dense_out, sparse_out, n_occ_out, depth_out, xyz_out, sem_out, diag, ws, ws_bytes,
+                           dense_out, sparse_out, n_occ_out, sparse_start_out, depth_out, xyz_out, sem_out, diag, ws, ws_bytes,
                            (cudaStream_t)stream);
 }
 

@@ -6,6 +6,10 @@ buffers: the sparse ``(n,4) uint16`` voxel lists (what ``voxel_filter`` returns)
 and the range images (what ``do_range_projection`` returns).  Two slots are double-buffered over three
 streams (H2D / kernels / D2H), so the copies of batch i+1 overlap the kernels of batch i and the
 read-back of batch i-1; PCIe is full duplex.  ``result()`` blocks on the oldest in-flight batch.
+
+Two things keep the host side off the critical path: the pageable -> pinned staging copy is split over host
+threads (``muvo_host_copy``), and the sparse voxel lists are written back to back (``sparse_start``) so that the
+read-back moves only about as many rows as there are occupied voxels instead of one row per input point.
 """
 from __future__ import annotations
 
@@ -34,7 +38,7 @@ class _Slot:
 class HostPipeline:
     def __init__(self, device=None, grid: Optional[GridSpec] = GridSpec(), range_spec: Optional[RangeSpec] = RangeSpec(),
                  dense: bool = False, sparse: bool = True, layout: str = "hwc", remap: Optional[np.ndarray] = None,
-                 depth: int = 2):
+                 depth: int = 2, host_threads: int = 0):
         if not torch.cuda.is_available():
             raise _lib.MuvoError("muvo_b200 kernels need a CUDA device (sm_100a); no CPU fallback exists")
         if device is None:
@@ -52,6 +56,8 @@ class HostPipeline:
         self.queue = []
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self.host_threads = int(host_threads)   # 0 = one per core (capped at 16)
+        self.row_cap = None                     # sparse rows read back per batch: 1.25 x the largest total seen so far
 
     def _ensure(self, slot: _Slot, n_pts: int, n_frames: int):
         if n_pts > slot.cap_pts:
@@ -61,14 +67,17 @@ class HostPipeline:
             slot.d_pts = torch.empty((cap, 3), dtype=torch.float32, device=self.device)
             slot.d_sem = torch.empty((cap,), dtype=torch.uint8, device=self.device)
             slot.cap_pts = cap
-            slot.dev_out.pop("voxel_sparse", None)
             slot.host_out.pop("voxel_sparse", None)
+            if self.sparse and self.grid is not None:      # sized for the slot, so ragged batches reuse it (and its pinned twin)
+                slot.dev_out["voxel_sparse"] = torch.empty((cap, 4), dtype=torch.int16, device=self.device)
+            else:
+                slot.dev_out.pop("voxel_sparse", None)
         if n_frames > slot.cap_frames:
             slot.h_off = torch.empty((n_frames + 1,), dtype=torch.int64).pin_memory()
             slot.d_off = torch.empty((n_frames + 1,), dtype=torch.int64, device=self.device)
             slot.cap_frames = n_frames
-            slot.dev_out = {}
-            slot.host_out = {}
+            slot.dev_out = {k: v for k, v in slot.dev_out.items() if k == "voxel_sparse"}
+            slot.host_out = {k: v for k, v in slot.host_out.items() if k == "voxel_sparse"}
 
     def submit(self, points: np.ndarray, semantics: np.ndarray, frame_offsets: np.ndarray):
         """Enqueue one ragged batch (host arrays).  Returns immediately; see :meth:`result`."""
@@ -78,8 +87,11 @@ class HostPipeline:
         n_pts, n_frames = int(points.shape[0]), int(len(frame_offsets) - 1)
         self._ensure(slot, n_pts, n_frames)
         # host -> pinned staging (the application's arrays are ordinary pageable memory)
-        slot.h_pts[:n_pts].numpy()[...] = points
-        slot.h_sem[:n_pts].numpy()[...] = semantics.reshape(-1)
+        lib = _lib.load()
+        pts_c = np.ascontiguousarray(points, dtype=np.float32)
+        sem_c = np.ascontiguousarray(semantics.reshape(-1), dtype=np.uint8)
+        _lib.check(lib.muvo_host_copy(slot.h_pts.data_ptr(), pts_c.ctypes.data, pts_c.nbytes, self.host_threads), "muvo_host_copy")
+        _lib.check(lib.muvo_host_copy(slot.h_sem.data_ptr(), sem_c.ctypes.data, sem_c.nbytes, self.host_threads), "muvo_host_copy")
         slot.h_off[:n_frames + 1].numpy()[...] = frame_offsets
         with torch.cuda.device(self.device):
             if slot.done is not None:
@@ -96,7 +108,7 @@ class HostPipeline:
                 out = {k: v for k, v in slot.dev_out.items() if v.shape[0] in (n_frames, slot.cap_pts)}
                 res = sensor_to_grid(slot.d_pts[:n_pts], slot.d_sem[:n_pts], slot.d_off[:n_frames + 1], grid=self.grid,
                                      range_spec=self.range_spec, dense=self.dense, sparse=self.sparse, remap=self.remap,
-                                     layout=self.layout, out=out)
+                                     layout=self.layout, out=out, packed_sparse=self.sparse)
                 ev_run = torch.cuda.Event()
                 ev_run.record(self.s_run)
             keys = [k for k in res if k not in ("frame_offsets", "diag")]
@@ -104,31 +116,53 @@ class HostPipeline:
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(ev_run)
                 nbytes = 0
+                rows = n_pts if self.row_cap is None else min(n_pts, self.row_cap)
                 for k in keys:
                     t = res[k]
                     h = slot.host_out.get(k)
                     if h is None or h.shape != t.shape:
                         h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
                         slot.host_out[k] = h
-                    h.copy_(t, non_blocking=True)
-                    nbytes += t.numel() * t.element_size()
+                    if k == "voxel_sparse":          # packed: only the leading rows can be in use
+                        h[:rows].copy_(t[:rows], non_blocking=True)
+                        nbytes += rows * t.shape[1] * t.element_size()
+                    else:
+                        h.copy_(t, non_blocking=True)
+                        nbytes += t.numel() * t.element_size()
                 slot.done = torch.cuda.Event()
                 slot.done.record(self.s_out)
             self.d2h_bytes = nbytes
         slot.busy = True
-        slot.meta = (n_pts, n_frames)
+        slot.meta = (n_pts, n_frames, rows)
         self.queue.append(slot)
 
     def result(self) -> dict:
         """Blocks until the oldest submitted batch is back in host memory; returns its pinned host tensors.
 
-        ``voxel_sparse`` rows of frame f are ``[frame_offsets[f], frame_offsets[f] + n_occ[f])`` (int16 storage,
+        ``voxel_sparse`` rows of frame f are ``[sparse_start[f], sparse_start[f] + n_occ[f])`` (int16 storage,
         view as uint16).  The buffers are reused by the next ``submit`` on the same slot.
         """
         slot = self.queue.pop(0)
         slot.done.synchronize()
+        if self.sparse and "sparse_start" in slot.host_out:
+            n_pts, n_frames, rows = slot.meta
+            total = int(slot.host_out["sparse_start"][n_frames].item())
+            if total > rows:                         # more occupied voxels than the rows read back so far: top up
+                with torch.cuda.device(self.device), torch.cuda.stream(self.s_out):
+                    slot.host_out["voxel_sparse"][rows:total].copy_(slot.dev_out["voxel_sparse"][rows:total], non_blocking=True)
+                    self.s_out.synchronize()
+            cap = max(1024, int(total * 1.25))
+            self.row_cap = cap if self.row_cap is None else max(self.row_cap, cap)
         slot.busy = False
         return dict(slot.host_out)
+
+    def warmup(self, points: np.ndarray, semantics: np.ndarray, frame_offsets: np.ndarray):
+        """Run one batch through EVERY slot so that all pinned / device buffers exist before timing-sensitive use
+        (cudaHostAlloc of a 100 MB staging buffer costs tens of milliseconds)."""
+        self.drain()
+        for _ in range(len(self.slots)):
+            self.submit(points, semantics, frame_offsets)
+        self.drain()
 
     def drain(self):
         while self.queue:

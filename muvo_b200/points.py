@@ -89,7 +89,8 @@ def _as_offsets(frame_offsets, n_points: int, device) -> torch.Tensor:
 def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=None, *,
                    grid: Optional[GridSpec] = None, range_spec: Optional[RangeSpec] = None,
                    dense: bool = True, sparse: bool = False, remap: Optional[torch.Tensor] = None,
-                   layout: str = "xyzd", want_diag: bool = False, out: Optional[dict] = None) -> dict:
+                   layout: str = "xyzd", want_diag: bool = False, out: Optional[dict] = None,
+                   packed_sparse: bool = False) -> dict:
     """Batched (a)+(b) on the current CUDA stream.  Nothing synchronises.
 
     points ``(P,3)`` float32 (float64 allowed when only ``grid`` is given), semantics ``(P,)`` uint8,
@@ -97,7 +98,9 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
     ``voxel (F,Dx,Dy,Dz) u8`` | ``voxel_sparse (P,4) u16`` + ``n_occ (F,) i64`` and
     ``range_xyzd (F,4,H,W) f32`` + ``range_sem (F,H,W) u8`` (layout "xyzd") or
     ``range_depth (F,H,W)``, ``range_xyz (F,H,W,3)``, ``range_sem`` (layout "hwc").
-    ``out`` may carry preallocated tensors under the same keys.
+    ``out`` may carry preallocated tensors under the same keys.  Frame f's sparse rows start at row
+    ``frame_offsets[f]``; with ``packed_sparse`` the frames' lists are stored back to back instead and
+    ``sparse_start (F+1,) i64`` gives the first row of every frame (a read-back then moves only the rows used).
     """
     _lib.require_cuda(points, semantics)
     if grid is None and range_spec is None:
@@ -131,7 +134,7 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
                (int(range_spec.H), int(range_spec.W)) if range_spec is not None else None)
         ws = _ws.get(nbytes.value, dev, stream, sig)
         diag = torch.zeros(_lib.DIAG_COUNT, dtype=torch.int64, device=dev) if want_diag else None
-        dense_t = sparse_t = nocc_t = depth_t = xyz_t = sem_t = None
+        dense_t = sparse_t = nocc_t = depth_t = xyz_t = sem_t = start_t = None
         if grid is not None:
             dx, dy, dz = (int(v) for v in grid.voxel_size)
             if dense:
@@ -145,6 +148,10 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
             nocc_t = res.get("n_occ")
             if nocc_t is None:
                 nocc_t = torch.empty((F,), dtype=torch.int64, device=dev)
+            if sparse and packed_sparse:
+                start_t = res.get("sparse_start")
+                if start_t is None:
+                    start_t = torch.empty((F + 1,), dtype=torch.int64, device=dev)
             if remap is not None:
                 remap = remap.to(device=dev, dtype=torch.uint8).contiguous()
                 if remap.numel() != 256:
@@ -172,12 +179,12 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
         p = _lib.ptr
         if grid is not None and range_spec is not None:
             rc = lib.muvo_points_fused(p(points), p(semantics), p(off), F, P, C.byref(g_c), p(remap), C.byref(r_c), lay,
-                                       p(dense_t), p(sparse_t), p(nocc_t), p(depth_t), p(xyz_t), p(sem_t), p(diag),
+                                       p(dense_t), p(sparse_t), p(nocc_t), p(start_t), p(depth_t), p(xyz_t), p(sem_t), p(diag),
                                        ws.data_ptr(), ws.numel(), stream)
         elif grid is not None:
             dt = _lib.F32 if points.dtype == torch.float32 else _lib.F64
             rc = lib.muvo_voxelize(p(points), dt, p(semantics), p(off), F, P, C.byref(g_c), p(remap), p(dense_t),
-                                   p(sparse_t), p(nocc_t), p(diag), ws.data_ptr(), ws.numel(), stream)
+                                   p(sparse_t), p(nocc_t), p(start_t), p(diag), ws.data_ptr(), ws.numel(), stream)
         else:
             rc = lib.muvo_range_project(p(points), p(semantics), p(off), F, P, C.byref(r_c), lay, p(depth_t), p(xyz_t),
                                         p(sem_t), p(diag), ws.data_ptr(), ws.numel(), stream)
@@ -190,6 +197,8 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
         res["voxel_sparse"] = sparse_t
     if nocc_t is not None:
         res["n_occ"] = nocc_t
+    if start_t is not None:
+        res["sparse_start"] = start_t
     if range_spec is not None:
         res["range_sem"] = sem_t
         if layout == "xyzd":

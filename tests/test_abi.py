@@ -77,8 +77,8 @@ def test_workspace_size_and_argument_errors(lib):
     assert lib.muvo_points_workspace_bytes(-1, 1, C.byref(g), C.byref(r), C.byref(n)) == -2
     assert lib.muvo_points_workspace_bytes(10, 1, C.byref(g), C.byref(r), None) == -1
     # NULL / bad-argument paths return before touching the device
-    assert lib.muvo_voxelize(None, 0, None, None, 1, 10, None, None, None, None, None, None, None, 0, None) == -1
-    assert lib.muvo_voxelize(None, 7, None, None, 1, 10, C.byref(g), None, None, None, None, None, None, 0, None) == -2
+    assert lib.muvo_voxelize(None, 0, None, None, 1, 10, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.muvo_voxelize(None, 7, None, None, 1, 10, C.byref(g), None, None, None, None, None, None, None, 0, None) == -2
     assert lib.muvo_ssc_counts(None, 0, None, None, None, 0, 10, 2, None, None) == -1
     assert lib.muvo_ssc_counts(None, 0, None, None, None, 0, -5, 2, C.c_void_p(8), None) == -2
     assert lib.muvo_bev_pool_workspace_bytes(1, 100, 0, C.byref(n)) == -2

@@ -363,3 +363,35 @@ def test_f32_pixel_path_never_disagrees_with_float64(lib):
                                       torch.cuda.current_stream().cuda_stream) == 0
     n_fast, n_slow, n_bad, n_drop = counts.tolist()
     assert n_bad == 0 and n_slow < 0.02 * 200000
+
+
+def test_host_pipeline_packed_sparse_and_range(lib):
+    """numpy in -> pinned staging -> kernels -> pinned host out: three batches through two slots; the second and third
+    read back only ~1.25 x the rows the first one needed (packed sparse lists), one of them with MORE occupied voxels
+    than that (top-up path)."""
+    from muvo_b200.pipeline import HostPipeline
+    pipe = HostPipeline(dev(), grid=GridSpec(), range_spec=RangeSpec(lidar_position=tuple(LIDAR)), dense=False, sparse=True,
+                        layout="hwc", host_threads=3)
+    batches = [_batch(3, 2000, 3000, 2200), _batch(4, 2000, 3000, 2300), _batch(4, 20000, 30000, 2400)]
+    outs = []
+    pipe.submit(*batches[0])
+    outs.append({k: v.clone() for k, v in pipe.result().items()})     # first batch alone: establishes the row cap
+    pipe.submit(*batches[1])
+    pipe.submit(*batches[2])
+    outs.append({k: v.clone() for k, v in pipe.result().items()})
+    outs.append({k: v.clone() for k, v in pipe.result().items()})
+    for (pts, sem, off), r in zip(batches, outs):
+        F = len(off) - 1
+        start, nocc = r["sparse_start"].numpy(), r["n_occ"].numpy()
+        rows_all = r["voxel_sparse"].numpy().view(np.uint16)
+        assert start[0] == 0 and np.array_equal(np.diff(start), nocc)
+        for f in range(F):
+            p, s = pts[off[f]:off[f + 1]], sem[off[f]:off[f + 1]]
+            v0, l0 = O.voxel_filter_fast(p, s, *GRID)
+            rows = rows_all[start[f]:start[f] + nocc[f]]
+            assert nocc[f] == len(v0)
+            assert np.array_equal(rows[:, :3], v0) and np.array_equal(rows[:, 3].astype(np.uint8), l0)
+            d0, x0, s0 = O.range_projection(p, s, lidar_position=LIDAR)
+            assert np.array_equal(r["range_depth"][f].numpy(), d0)
+            assert np.array_equal(r["range_xyz"][f].numpy(), x0)
+            assert np.array_equal(r["range_sem"][f].numpy(), s0)
