@@ -11,7 +11,8 @@
  * Conventions
  *  - Pointers are DEVICE pointers unless the name ends in _h (host).
  *  - The caller owns every buffer (inputs, outputs, workspace); nothing is
- *    allocated or freed inside the library and no global mutable state is kept.
+ *    allocated or freed inside the library and no global mutable state is kept
+ *    (except the debug tuning knobs at the end of this header).
  *  - Every call enqueues work on `stream` (a cudaStream_t passed as void*) and
  *    returns without synchronising.  Calls are re-entrant; concurrent callers
  *    must use distinct workspaces.

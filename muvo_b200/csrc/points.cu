@@ -47,6 +47,7 @@ namespace {
 #define MUVO_K1_MINB 4
 #endif
 constexpr int kBlock = 256;
+constexpr int kMaxChunks = 1;                         // point sub-ranges per call (the kernels take [p0, p1) x [f0, f1))
 constexpr int kMaxTileCtas = 4096;                   // upper bound of the persistent tile grid (queue length slots)
 constexpr double kPi = 3.141592653589793;            // np.pi
 constexpr double kPiOver4 = 0x1.921fb54442d18p-1;    // correctly rounded pi/4 (numpy/glibc value on diagonals)
@@ -88,7 +89,7 @@ struct PointsWs {
   uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk (sparse output only)
   u64* vtab = nullptr;          // [F, G]     packed winner per voxel, addressed by the voxel's bit index (0 = empty)
   u64* pixtab = nullptr;        // [F, H*W]   packed winner per pixel (0 = empty)
-  uint32_t* qcount = nullptr;   // [kMaxTileCtas] rare-path queue length per tile CTA (rewritten by every call)
+  uint32_t* qcount = nullptr;   // [kMaxChunks, kMaxTileCtas] rare-path queue length per tile CTA (rewritten by every call)
   uint2* queue = nullptr;       // [2P]       rare-path queue, CTA b's segment starts at 2 * (its first point)
   size_t bytes = 0;
 };
@@ -111,7 +112,7 @@ static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const Muv
   if (r) {
     w.pixtab = (u64*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 8, 256);
   }
-  w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxTileCtas * 4, 256);
+  w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxChunks * kMaxTileCtas * 4, 256);
   w.queue = (uint2*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 16, 256);
   w.bytes = o;
   return w;
@@ -413,24 +414,31 @@ __device__ __forceinline__ void tile_issue(const T* __restrict__ xyz, const uint
   bulk_g2s(smem + L::off_sem + (size_t)st * kTile, sem + base, (uint32_t)kTile, bar, pol);
 }
 
-// Tile iterator shared by K1 and K3 (all members are CTA-uniform).
+// Tiles [t0, t1) of CTA `cta` out of n_ctas for the points [p0, p1): absolute tile indices, contiguous runs.
+__device__ __forceinline__ void cta_tile_range(int64_t p0, int64_t p1, int n_ctas, int cta, int* t0, int* t1) {
+  const int64_t lo = p0 / kTile, hi = ceil_div64(p1, kTile);
+  const int64_t per = ceil_div64(hi - lo, (int64_t)n_ctas);
+  const int64_t a = lo + (int64_t)cta * per;
+  *t0 = (int)(a < hi ? a : hi);
+  *t1 = (int)(a + per < hi ? a + per : hi);
+}
+
+// Tile iterator of the point pass (all members are CTA-uniform).
 template <typename T>
 struct Tiles {
   unsigned char* smem;
   const T* xyz; const uint8_t* sem; const int64_t* off;
-  int F; int64_t P; bool vec_ok;
-  int t0, t1, t;           // this CTA's tiles [t0, t1), current tile (n_tiles < 2^26)
+  int F; int64_t P0, P; bool vec_ok;   // points [P0, P) of the packed arrays are this launch's (a chunk of the batch)
+  int t0, t1, t;           // this CTA's tiles [t0, t1) (absolute tile index = point index / kTile), current tile
   int f;                   // frame of the current tile's first point
   int64_t fbeg, fend;      // its [begin, end) point range
   int64_t base; bool full, one_frame; int st;
+  uint32_t phase;          // bit s = parity of the next completion of stage s's mbarrier (flips per waited copy)
 
   __device__ __forceinline__ bool init(unsigned char* smem_, const T* xyz_, const uint8_t* sem_, const int64_t* off_, int F_,
-                                       int64_t P_, bool vec_ok_) {
-    smem = smem_; xyz = xyz_; sem = sem_; off = off_; F = F_; P = P_; vec_ok = vec_ok_;
-    const int64_t n_tiles = ceil_div64(P, kTile);
-    const int64_t per = ceil_div64(n_tiles, (int64_t)gridDim.x);
-    t0 = (int)((int64_t)blockIdx.x * per < n_tiles ? (int64_t)blockIdx.x * per : n_tiles);
-    t1 = (int)((int64_t)t0 + per < n_tiles ? (int64_t)t0 + per : n_tiles);
+                                       int64_t P0_, int64_t P_, bool vec_ok_) {
+    smem = smem_; xyz = xyz_; sem = sem_; off = off_; F = F_; P0 = P0_; P = P_; vec_ok = vec_ok_;
+    cta_tile_range(P0, P, (int)gridDim.x, (int)blockIdx.x, &t0, &t1);
     if (t0 >= t1) return false;
     using L = TileLayout<T>;
     if (threadIdx.x == 0) {
@@ -440,12 +448,14 @@ struct Tiles {
       mbar_fence_init();
     }
     __syncthreads();
-    f = find_frame(off, F, (int64_t)t0 * kTile);
-    if (threadIdx.x == 0 && is_full(t0)) tile_issue<T>(xyz, sem, (int64_t)t0 * kTile, smem, 0);
+    const int64_t first = (int64_t)t0 * kTile;
+    f = find_frame(off, F, first > P0 ? first : P0);
+    if (threadIdx.x == 0 && is_full(t0)) tile_issue<T>(xyz, sem, first, smem, 0);
     t = t0 - 1;
+    phase = 0u;
     return true;
   }
-  __device__ __forceinline__ bool is_full(int tt) const { return vec_ok && ((int64_t)tt + 1) * kTile <= P; }
+  __device__ __forceinline__ bool is_full(int tt) const { return vec_ok && (int64_t)tt * kTile >= P0 && ((int64_t)tt + 1) * kTile <= P; }
   // advance to the next tile; returns false at the end.  The caller ends every tile with __syncthreads().
   __device__ __forceinline__ bool next() {
     ++t;
@@ -457,8 +467,11 @@ struct Tiles {
     if (threadIdx.x == 0 && t + 1 < t1 && is_full(t + 1)) tile_issue<T>(xyz, sem, base + kTile, smem, st ^ 1);
     while (f + 1 < F && base >= __ldg(off + f + 1)) ++f;
     fbeg = __ldg(off + f); fend = __ldg(off + f + 1);
-    one_frame = base + kTile <= fend;
-    if (full) mbar_wait(reinterpret_cast<uint64_t*>(smem + L::off_bar) + st, (uint32_t)(((t - t0) >> 1) & 1));
+    one_frame = base >= fbeg && base + kTile <= fend;
+    if (full) {   // (not every tile is staged: a chunk's first and last tiles may be partial)
+      mbar_wait(reinterpret_cast<uint64_t*>(smem + L::off_bar) + st, (phase >> st) & 1u);
+      phase ^= 1u << st;
+    }
     return true;
   }
   // point j of the current tile
@@ -472,7 +485,7 @@ struct Tiles {
     }
     const int64_t i = base + j;
     *x = *y = *z = (T)0; *lab = 0;
-    if (i >= P) return false;
+    if (i < P0 || i >= P) return false;
     *x = __ldg(xyz + 3 * i); *y = __ldg(xyz + 3 * i + 1); *z = __ldg(xyz + 3 * i + 2);
     *lab = __ldg(sem + i);
     return true;
@@ -525,14 +538,6 @@ __device__ __noinline__ void tie_protocol(u64* slot, uint32_t top_inv, uint32_t 
 // (the two jobs are independent and both latency bound, so they share the machine instead of serialising).
 constexpr int kScanCluster = 8;
 constexpr int kScanThreads = 256;
-
-__device__ __forceinline__ void cta_tile_range(int64_t P, int n_ctas, int cta, int* t0, int* t1) {
-  const int64_t n_tiles = ceil_div64(P, kTile);
-  const int64_t per = ceil_div64(n_tiles, (int64_t)n_ctas);
-  const int64_t a = (int64_t)cta * per;
-  *t0 = (int)(a < n_tiles ? a : n_tiles);
-  *t1 = (int)(a + per < n_tiles ? a + per : n_tiles);
-}
 
 __device__ __forceinline__ void scan_role(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw,
                                           int64_t* __restrict__ n_occ_out) {
@@ -611,7 +616,7 @@ __device__ __forceinline__ void scan_role(const uint32_t* __restrict__ bitmap, u
 constexpr uint32_t kQVoxel = 0x80000000u;
 template <typename T>
 struct QueueArgs {
-  const T* xyz; const uint8_t* sem; const int64_t* off; int F; int64_t P;
+  const T* xyz; const uint8_t* sem; const int64_t* off; int F; int64_t P0, P;
   u64* pixtab; u64* vtab; const uint2* queue; const uint32_t* qcount; int n_tile_ctas; int64_t* diag;
 };
 
@@ -621,11 +626,11 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
   const uint32_t n = a.qcount[cta];
   if (n == 0u) return;   // CTA-uniform
   int t0, t1;
-  cta_tile_range(a.P, a.n_tile_ctas, cta, &t0, &t1);
+  cta_tile_range(a.P0, a.P, a.n_tile_ctas, cta, &t0, &t1);
   const int64_t blk_first = (int64_t)t0 * kTile;
-  const uint2* q = a.queue + 2 * blk_first;
+  const uint2* q = a.queue + 2 * (blk_first > a.P0 ? blk_first : a.P0);
   unsigned n_drop = 0, n_nw = 0, n_nh = 0;
-  const int f_first = find_frame(a.off, a.F, blk_first);      // a CTA's points span few frames: walk from its first one
+  const int f_first = find_frame(a.off, a.F, blk_first > a.P0 ? blk_first : a.P0);      // a CTA's points span few frames: walk from its first one
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     const uint2 ent = q[e];
     const int64_t i = blk_first + (int64_t)(ent.x & ~kQVoxel);
@@ -715,22 +720,22 @@ __device__ __forceinline__ bool pair_filter(bool in, uint32_t bit /* 0xffffffff 
 
 template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
 __global__ void __launch_bounds__(kTileThreads, MUVO_K1_MINB)
-k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P,
-              bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, u64* __restrict__ pixtab,
+k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P0,
+              int64_t P, int f_lo, int f_hi, bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, u64* __restrict__ pixtab,
               uint2* __restrict__ queue, uint32_t* __restrict__ qcount, int64_t* __restrict__ n_occ_zero, int flags,
               int64_t* __restrict__ diag) {
   extern __shared__ __align__(128) unsigned char smem[];
   using L = TileLayout<T>;
-  if (n_occ_zero && blockIdx.x == 0) for (int f = threadIdx.x; f < F; f += kTileThreads) n_occ_zero[f] = 0;
+  if (n_occ_zero && blockIdx.x == 0) for (int f = f_lo + threadIdx.x; f < f_hi; f += kTileThreads) n_occ_zero[f] = 0;
   Tiles<T> tl;
-  if (!tl.init(smem, xyz, sem, off, F, P, vec_ok)) {
+  if (!tl.init(smem, xyz, sem, off, F, P0, P, vec_ok)) {
     if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
     return;
   }
   uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
   const int tid = threadIdx.x;
   const int64_t blk_first = (int64_t)tl.t0 * kTile;
-  uint2* q = queue + 2 * blk_first;
+  uint2* q = queue + 2 * (blk_first > P0 ? blk_first : P0);
   const int64_t HW = (int64_t)r.H * r.W;
   const bool use_filter = (flags & 1) != 0;
   unsigned n_drop = 0, n_in = 0;
@@ -871,7 +876,7 @@ __device__ __forceinline__ uint32_t tile_swz(uint32_t pos) { return pos ^ ((pos 
 
 struct EmitDenseArgs {
   uint32_t* bitmap; u64* vtab; const int64_t* off; const uint8_t* sem; const uint8_t* remap; uint8_t* dense; int64_t* n_occ;
-  int blocks_per_frame;
+  int f_lo;   // first frame of this launch (grid.y counts frames from here)
 };
 // CTA `bx` of frame `f`
 __device__ __forceinline__ void emit_dense_body(int bx, int f, EmitSmem& sm, const EmitDenseArgs& a, const GridDev& g) {
@@ -971,7 +976,7 @@ __device__ __forceinline__ void emit_dense_body(int bx, int f, EmitSmem& sm, con
 __global__ void __launch_bounds__(kBlock)
 k_emit_dense(EmitDenseArgs a, GridDev g) {
   extern __shared__ __align__(16) unsigned char emit_raw[];
-  emit_dense_body((int)blockIdx.x, (int)blockIdx.y, *reinterpret_cast<EmitSmem*>(emit_raw), a, g);
+  emit_dense_body((int)blockIdx.x, a.f_lo + (int)blockIdx.y, *reinterpret_cast<EmitSmem*>(emit_raw), a, g);
 }
 
 // Packed sparse output: start[f] = number of occupied voxels in frames < f (start[F] = total).  One CTA.
@@ -1067,18 +1072,19 @@ k_emit_dense_from_linear(const uint32_t* __restrict__ bitmap, const u64* __restr
 // Range image: one thread per NP pixels (NP = 4: 16-byte stores; NP = 1: generic fallback).
 template <typename T>
 struct EmitRangeArgs {
-  u64* pixtab; const T* xyz; const uint8_t* sem; const int64_t* off; int F; float* depth_out; float* xyz_out; uint8_t* sem_out;
+  u64* pixtab; const T* xyz; const uint8_t* sem; const int64_t* off; int f_lo, f_hi;   // frames [f_lo, f_hi) of this launch
+  float* depth_out; float* xyz_out; uint8_t* sem_out;
 };
 template <typename T, int NP, int LAYOUT>
 __device__ __forceinline__ void emit_range_body(int64_t vblock, const EmitRangeArgs<T>& a, const RangeDev& r) {
   u64* __restrict__ pixtab = a.pixtab; const T* __restrict__ xyz = a.xyz; const uint8_t* __restrict__ sem = a.sem;
-  const int64_t* __restrict__ off = a.off; const int F = a.F;
+  const int64_t* __restrict__ off = a.off;
   float* __restrict__ depth_out = a.depth_out; float* __restrict__ xyz_out = a.xyz_out; uint8_t* __restrict__ sem_out = a.sem_out;
   constexpr bool clean = true;
   const int64_t HW = (int64_t)r.H * r.W;
   int64_t t = vblock * kBlock + threadIdx.x;
-  int64_t p0 = t * NP;                 // global pixel index over [F, H*W]
-  if (p0 >= (int64_t)F * HW) return;
+  int64_t p0 = (int64_t)a.f_lo * HW + t * NP;   // global pixel index over [F, H*W]
+  if (p0 >= (int64_t)a.f_hi * HW) return;
   int f = (int)(p0 / HW);
   int64_t pin = p0 - (int64_t)f * HW;  // pixel inside the frame
   int64_t fbeg = __ldg(off + f);
@@ -1213,10 +1219,10 @@ static int make_range_dev(const MuvoRangeCfg* c, RangeDev* o) {
 static inline unsigned blocks_for(int64_t n) { return (unsigned)ceil_div64(n, kBlock); }
 
 template <typename T>
-static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int F, int64_t P, const MuvoGrid* grid_h,
-                      const uint8_t* remap, const MuvoRangeCfg* cfg_h, int layout, uint8_t* dense, uint16_t* sparse,
-                      int64_t* n_occ, int64_t* sparse_start, float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws,
-                      size_t ws_bytes, cudaStream_t st) {
+static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int F, int64_t P,
+                      const MuvoGrid* grid_h, const uint8_t* remap, const MuvoRangeCfg* cfg_h, int layout, uint8_t* dense,
+                      uint16_t* sparse, int64_t* n_occ, int64_t* sparse_start, float* depth_out, float* xyz_out,
+                      uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, cudaStream_t st) {
   const bool do_vox = grid_h != nullptr, do_range = cfg_h != nullptr;
   if (!do_vox && !do_range) return MUVO_E_ARG;
   if (F < 0 || P < 0) return MUVO_E_ARG;
@@ -1229,6 +1235,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   if (do_range && (!xyz_out || (layout == MUVO_RANGE_LAYOUT_HWC && (!depth_out || !sem_out)))) return MUVO_E_NULL;
   if (layout != MUVO_RANGE_LAYOUT_HWC && layout != MUVO_RANGE_LAYOUT_XYZD) return MUVO_E_ARG;
   if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
+  if (P >= ((int64_t)1 << 36)) return MUVO_E_SHAPE;              // rare-path queue entries are 32-bit CTA-relative
   GridDev g{}; RangeDev r{};
   int rc;
   const int order = (sparse != nullptr) ? ORDER_LINEAR : ORDER_DENSE;   // bit index = output order of the list that is emitted
@@ -1237,118 +1244,118 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   PointsWs w = carve(ws, P, F, grid_h, cfg_h);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 16 == 0);
-  if (P >= ((int64_t)1 << 36)) return MUVO_E_SHAPE;              // exact-path queue entries are 32-bit CTA-relative
-  // persistent tile kernels: one contiguous run of tiles per CTA, CTAs = SMs x resident CTAs per SM
-  const int64_t n_tiles = ceil_div64(P, kTile);
   const size_t tsmem = TileLayout<T>::bytes;
-  auto tile_grid = [&](const void* fn, int want_per_sm, unsigned* grid_o) -> int {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-    if (e != cudaSuccess) return (int)e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kTileThreads, tsmem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
-    if (g_tuning[0] > 0 && g_tuning[0] < per_sm) per_sm = g_tuning[0];
-    if (want_per_sm > 0 && want_per_sm < per_sm && g_tuning[0] <= 0) per_sm = want_per_sm;
-    int dev = 0, sms = kNumSMsB200;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t grid = (int64_t)sms * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    if (grid > kMaxTileCtas) grid = kMaxTileCtas;
-    *grid_o = (unsigned)(grid > 0 ? grid : 1);
-    return MUVO_OK;
-  };
-
   const int64_t HWr = do_range ? (int64_t)r.H * r.W : 0;
   const bool range_vec4 = do_range && (HWr % 4 == 0) && (reinterpret_cast<uintptr_t>(xyz_out) % 16 == 0) &&
                           (!depth_out || reinterpret_cast<uintptr_t>(depth_out) % 16 == 0) &&
                           (!sem_out || reinterpret_cast<uintptr_t>(sem_out) % 4 == 0);
-  EmitRangeArgs<T> era{w.pixtab, xyz, sem, off, F, depth_out, xyz_out, sem_out};
-  auto emit_range = [&]() -> int {
-    const int64_t npix = (int64_t)F * HWr;
-    if (range_vec4) {
-      if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, st>>>(era, r);
-      else                                 k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, st>>>(era, r);
-    } else {
-      if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, st>>>(era, r);
-      else                                 k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, st>>>(era, r);
+  // the sorted sparse list needs ranks (bitmap scan); a dense-only call counts n_occ while it emits
+  const bool need_scan = do_vox && (sparse != nullptr || dense == nullptr);
+  const bool dense_fast = do_vox && !need_scan;                  // dense-order bitmap, dense grid (and n_occ) from k_emit_dense
+  int64_t* n_occ_emit = dense_fast ? n_occ : nullptr;
+  const int flags = (g_tuning[1] & 1) ? 0 : 1;                   // bit 0: neighbour filter before the voxel atomicMax
+  int sms = kNumSMsB200;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+
+  // K1 kernel of this call (persistent tile kernel: one contiguous run of tiles per CTA)
+  const bool reg = do_vox ? g.regular != 0 : true;
+  typedef void (*K1Fn)(const T*, const uint8_t*, const int64_t*, int, int64_t, int64_t, int, int, bool, GridDev, RangeDev, uint32_t*,
+                       u64*, u64*, uint2*, uint32_t*, int64_t*, int, int64_t*);
+  K1Fn k1;
+  if (do_vox && do_range) k1 = reg ? k_points_tile<T, true, true, true> : k_points_tile<T, true, true, false>;
+  else if (do_vox)        k1 = reg ? k_points_tile<T, true, false, true> : k_points_tile<T, true, false, false>;
+  else                    k1 = k_points_tile<T, false, true, true>;
+  int k1_per_sm = 0;
+  {
+    cudaError_t e = cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1_per_sm, (const void*)k1, kTileThreads, tsmem);
+    if (e != cudaSuccess) return (int)e;
+    if (k1_per_sm < 1) k1_per_sm = 1;
+    if (g_tuning[0] > 0 && g_tuning[0] < k1_per_sm) k1_per_sm = g_tuning[0];
+  }
+  if (dense_fast) {
+    cudaError_t e = cudaFuncSetAttribute(k_emit_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
+    if (e != cudaSuccess) return (int)e;
+  }
+
+  // One chunk = frames [f0, f1) = points [p0, p1): point pass, rare-path queues, emits, all on stream `cs`.
+  int chunk_ctas[kMaxChunks] = {0};
+  auto run_pass = [&](int chunk, int f0, int f1, int64_t p0, int64_t p1, cudaStream_t cs) -> int {
+    int n_tile_ctas = 0;
+    uint32_t* qcount = w.qcount + (size_t)chunk * kMaxTileCtas;
+    if (p1 > p0) {
+      const int64_t n_tiles = ceil_div64(p1, kTile) - p0 / kTile;
+      int64_t grid = (int64_t)sms * k1_per_sm;
+      if (grid > n_tiles) grid = n_tiles;
+      if (grid > kMaxTileCtas) grid = kMaxTileCtas;
+      grid = ceil_div64(n_tiles, ceil_div64(n_tiles, grid));     // same tiles per CTA, no idle CTAs at the end
+      k1<<<(unsigned)grid, kTileThreads, tsmem, cs>>>(xyz, sem, off, F, p0, p1, f0, f1, vec_ok, g, r, w.bitmap, w.vtab, w.pixtab,
+                                                       w.queue, qcount, n_occ_emit, flags, diag);
+      MUVO_AFTER_LAUNCH("k_points_tile", cs);
+      n_tile_ctas = (int)grid;
+    } else if (n_occ_emit) {
+      cudaError_t e = cudaMemsetAsync(n_occ_emit + f0, 0, (size_t)(f1 - f0) * sizeof(int64_t), cs);
+      if (e != cudaSuccess) return (int)e;
     }
-    MUVO_AFTER_LAUNCH("k_emit_range", st);
+    chunk_ctas[chunk] = n_tile_ctas;
+    return MUVO_OK;
+  };
+  auto run_emit = [&](int chunk, int f0, int f1, int64_t p0, int64_t p1, cudaStream_t cs) -> int {
+    const int n_tile_ctas = chunk_ctas[chunk];
+    uint32_t* qcount = w.qcount + (size_t)chunk * kMaxTileCtas;
+    // K2: bitmap scan (when ranks are needed) + the rare-path queues, one launch
+    {
+      const int scan_frames = need_scan ? F : 0;                 // (the scan path is never chunked)
+      const int queue_ctas = p1 > p0 ? (n_tile_ctas + kScanCluster - 1) / kScanCluster * kScanCluster : 0;
+      const unsigned sgrid = (unsigned)(scan_frames * kScanCluster + queue_ctas);
+      if (sgrid > 0) {
+        QueueArgs<T> qa{xyz, sem, off, F, p0, p1, w.pixtab, w.vtab, w.queue, qcount, queue_ctas ? n_tile_ctas : 0, diag};
+        k_scan_queue<T><<<sgrid, kScanThreads, 0, cs>>>(w.bitmap, w.prefix, g.gw, scan_frames, n_occ, qa, g, r);
+        MUVO_AFTER_LAUNCH("k_scan_queue", cs);
+      }
+    }
+    if (do_range) {              // right after its producers: the pixel words are still L2 resident
+      EmitRangeArgs<T> era{w.pixtab, xyz, sem, off, f0, f1, depth_out, xyz_out, sem_out};
+      const int64_t npix = (int64_t)(f1 - f0) * HWr;
+      if (range_vec4) {
+        if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, cs>>>(era, r);
+        else                                 k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, cs>>>(era, r);
+      } else {
+        if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, cs>>>(era, r);
+        else                                 k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, cs>>>(era, r);
+      }
+      MUVO_AFTER_LAUNCH("k_emit_range", cs);
+    }
+    if (do_vox) {
+      // K5 (the last consumer of the tables clears them)
+      if (dense_fast) {
+        const int bpf = (int)ceil_div64(g.gw, kBlock * kEmitWords);
+        EmitDenseArgs eda{w.bitmap, w.vtab, off, sem, remap, dense, n_occ_emit, f0};
+        k_emit_dense<<<dim3((unsigned)bpf, (unsigned)(f1 - f0)), kBlock, sizeof(EmitSmem), cs>>>(eda, g);
+        MUVO_AFTER_LAUNCH("k_emit_dense", cs);
+      } else {
+        const int64_t words = (int64_t)F * g.gw;
+        if (dense) {
+          k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, cs>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F);
+          MUVO_AFTER_LAUNCH("k_emit_dense_from_linear", cs);
+        }
+        if (sparse && sparse_start) {
+          k_frame_prefix<<<1, 1024, 0, cs>>>(n_occ, F, sparse_start);
+          MUVO_AFTER_LAUNCH("k_frame_prefix", cs);
+        }
+        k_emit_sparse<<<blocks_for(words), kBlock, 0, cs>>>(w.bitmap, w.prefix, w.vtab, off, sem, sparse, sparse ? sparse_start : nullptr, g, F);
+        MUVO_AFTER_LAUNCH("k_emit_sparse", cs);
+      }
+    }
     return MUVO_OK;
   };
 
   prof_mark("<points>", st);
-  int n_tile_ctas = 0;
-  // the sorted sparse list needs ranks (bitmap scan); a dense-only call counts n_occ while it emits
-  const bool need_scan = do_vox && (sparse != nullptr || dense == nullptr);
-  int64_t* n_occ_emit = (do_vox && !need_scan) ? n_occ : nullptr;
-  const int flags = (g_tuning[1] & 1) ? 0 : 1;   // bit 0: neighbour filter before the voxel atomicMax
-  // K1
-  if (P > 0) {
-    const void* fn;
-    const bool reg = do_vox ? g.regular != 0 : true;
-    if (do_vox && do_range) fn = reg ? (const void*)k_points_tile<T, true, true, true> : (const void*)k_points_tile<T, true, true, false>;
-    else if (do_vox)        fn = reg ? (const void*)k_points_tile<T, true, false, true> : (const void*)k_points_tile<T, true, false, false>;
-    else                    fn = (const void*)k_points_tile<T, false, true, true>;
-    unsigned grid;
-    if ((rc = tile_grid(fn, 0, &grid)) != MUVO_OK) return rc;
-#define MUVO_K1_ARGS xyz, sem, off, F, P, vec_ok, g, r, w.bitmap, w.vtab, w.pixtab, w.queue, w.qcount, n_occ_emit, flags, diag
-    if (do_vox && do_range) {
-      if (reg) k_points_tile<T, true, true, true><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
-      else     k_points_tile<T, true, true, false><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
-    } else if (do_vox) {
-      if (reg) k_points_tile<T, true, false, true><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
-      else     k_points_tile<T, true, false, false><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
-    } else {
-      k_points_tile<T, false, true, true><<<grid, kTileThreads, tsmem, st>>>(MUVO_K1_ARGS);
-    }
-#undef MUVO_K1_ARGS
-    MUVO_AFTER_LAUNCH("k_points_tile", st);
-    n_tile_ctas = (int)grid;
-  } else if (n_occ_emit) {
-    cudaError_t e = cudaMemsetAsync(n_occ_emit, 0, (size_t)F * sizeof(int64_t), st);
-    if (e != cudaSuccess) return (int)e;
-  }
-  // K2: bitmap scan (when ranks are needed) + the rare-path queues, one launch
-  {
-    const int scan_frames = need_scan ? F : 0;
-    const int queue_ctas = P > 0 ? (n_tile_ctas + kScanCluster - 1) / kScanCluster * kScanCluster : 0;
-    const unsigned sgrid = (unsigned)(scan_frames * kScanCluster + queue_ctas);
-    if (sgrid > 0) {
-      QueueArgs<T> qa{xyz, sem, off, F, P, w.pixtab, w.vtab, w.queue, w.qcount, queue_ctas ? n_tile_ctas : 0, diag};
-      k_scan_queue<T><<<sgrid, kScanThreads, 0, st>>>(w.bitmap, w.prefix, g.gw, scan_frames, n_occ, qa, g, r);
-      MUVO_AFTER_LAUNCH("k_scan_queue", st);
-    }
-  }
-  const bool dense_fast = do_vox && !need_scan;                  // dense-order bitmap, dense grid (and n_occ) from k_emit_dense
-  // (running the two emits in one launch, CTAs interleaved, was measured: 150 us vs 61 + 75 us back to back)
-  if (do_range && (rc = emit_range()) != MUVO_OK) return rc;
-  if (do_vox) {
-    // K5 (the last consumer of the tables clears them)
-    const int64_t words = (int64_t)F * g.gw;
-    if (dense_fast) {
-      const int bpf = (int)ceil_div64(g.gw, kBlock * kEmitWords);
-      EmitDenseArgs eda{w.bitmap, w.vtab, off, sem, remap, dense, n_occ_emit, bpf};
-      {
-        cudaError_t e = cudaFuncSetAttribute(k_emit_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
-        if (e != cudaSuccess) return (int)e;
-        k_emit_dense<<<dim3((unsigned)bpf, (unsigned)F), kBlock, sizeof(EmitSmem), st>>>(eda, g);
-        MUVO_AFTER_LAUNCH("k_emit_dense", st);
-      }
-    } else {
-      if (dense) {
-        k_emit_dense_from_linear<<<blocks_for((int64_t)F * g.G), kBlock, 0, st>>>(w.bitmap, w.vtab, off, sem, remap, dense, g, F);
-        MUVO_AFTER_LAUNCH("k_emit_dense_from_linear", st);
-      }
-      if (sparse && sparse_start) {
-        k_frame_prefix<<<1, 1024, 0, st>>>(n_occ, F, sparse_start);
-        MUVO_AFTER_LAUNCH("k_frame_prefix", st);
-      }
-      k_emit_sparse<<<blocks_for(words), kBlock, 0, st>>>(w.bitmap, w.prefix, w.vtab, off, sem, sparse, sparse ? sparse_start : nullptr, g, F);
-      MUVO_AFTER_LAUNCH("k_emit_sparse", st);
-    }
-  }
-  return MUVO_OK;
+  // (Cutting the batch into frame chunks and running chunk c+1's point pass on a second stream next to chunk c's emit
+  // kernels was measured, also under CUDA-graph replay: 249 us unchunked vs 275 / 342 us with 2 / 4 chunks -- the
+  // persistent point pass owns the register file, so the kernels do not actually co-run.  Not kept.)
+  if ((rc = run_pass(0, 0, F, 0, P, st)) != MUVO_OK) return rc;
+  return run_emit(0, 0, F, 0, P, st);
 }
 
 }  // namespace
@@ -1392,14 +1399,15 @@ int muvo_ws_reset(void* ws, size_t ws_bytes, void* stream) {
 }
 
 int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* sem, const int64_t* frame_offsets,
-                  int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
-                  uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out, int64_t* sparse_start_out, int64_t* diag,
-                  void* ws, size_t ws_bytes, void* stream) {
+                  int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h,
+                  const uint8_t* remap256, uint8_t* dense_out, uint16_t* sparse_out, int64_t* n_occ_out,
+                  int64_t* sparse_start_out, int64_t* diag, void* ws, size_t ws_bytes, void* stream) {
   if (!grid_h) return MUVO_E_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   if (xyz_dtype == MUVO_F32)
-    return run_points<float>((const float*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256, nullptr,
-                             0, dense_out, sparse_out, n_occ_out, sparse_start_out, nullptr, nullptr, nullptr, diag, ws, ws_bytes, st);
+    return run_points<float>((const float*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256,
+                             nullptr, 0, dense_out, sparse_out, n_occ_out, sparse_start_out, nullptr, nullptr, nullptr, diag, ws,
+                             ws_bytes, st);
   if (xyz_dtype == MUVO_F64)
     return run_points<double>((const double*)xyz, sem, frame_offsets, n_frames, n_points_total, grid_h, remap256,
                               nullptr, 0, dense_out, sparse_out, n_occ_out, sparse_start_out, nullptr, nullptr, nullptr, diag, ws,
@@ -1407,16 +1415,17 @@ int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* sem, const 
   return MUVO_E_ARG;
 }
 
-int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
-                       int64_t n_points_total, const MuvoRangeCfg* cfg_h, int32_t layout, float* depth_out,
+int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets,
+                       int32_t n_frames, int64_t n_points_total, const MuvoRangeCfg* cfg_h, int32_t layout, float* depth_out,
                        float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, void* stream) {
   if (!cfg_h) return MUVO_E_NULL;
-  return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, nullptr, nullptr, cfg_h, layout, nullptr,
-                           nullptr, nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes, (cudaStream_t)stream);
+  return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, nullptr, nullptr, cfg_h, layout,
+                           nullptr, nullptr, nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes,
+                           (cudaStream_t)stream);
 }
 
-int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
-                      int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
+int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets,
+                      int32_t n_frames, int64_t n_points_total, const MuvoGrid* grid_h, const uint8_t* remap256,
                       const MuvoRangeCfg* cfg_h, int32_t layout, uint8_t* dense_out, uint16_t* sparse_out,
                       int64_t* n_occ_out, int64_t* sparse_start_out, float* depth_out, float* xyz_out, uint8_t* sem_out,
                       int64_t* diag, void* ws, size_t ws_bytes, void* stream) {

@@ -17,6 +17,8 @@ ap.add_argument("--frames", type=int, default=96)
 ap.add_argument("--nmin", type=int, default=60000)
 ap.add_argument("--nmax", type=int, default=100000)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--graph", type=int, default=0)
+ap.add_argument("--set", default="", help="other knobs, e.g. 0=3,1=0")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 lib = _lib.load()
@@ -34,8 +36,32 @@ def step():
     out = {k: r[k] for k in ("voxel", "n_occ", "range_xyzd", "range_sem")}
 
 
+for kv in [x for x in a.set.split(",") if x]:
+    lib.muvo_debug_set_tuning(int(kv.split("=")[0]), int(kv.split("=")[1]))
 for v in [int(x) for x in a.values.split(",")]:
     lib.muvo_debug_set_tuning(a.key, v)
+    if a.graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            step()
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"knob{a.key}={v}: graph replay step {1e3 * e0.elapsed_time(e1) / a.reps:.1f} us", flush=True)
+        continue
     for _ in range(3):
         step()
     torch.cuda.synchronize()
