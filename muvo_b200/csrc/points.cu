@@ -1009,40 +1009,61 @@ k_frame_prefix(const int64_t* __restrict__ n_occ, int F, int64_t* __restrict__ s
 // Sparse list, bitmap in linear-id order: rows (x,y,z,label) uint16 at sparse[(row0[f] + rank)], row0 = frame_offsets
 // (frame f's rows start where its points start) or `start` (packed: frames back to back).
 // sparse == nullptr: only clears the tables (n_occ-only calls).
+// One warp = 32 consecutive bitmap words.  The 32 voxels of a word are contiguous in the voxel table (bit index =
+// linear id here), so a non-empty word is finished by the whole warp at once: lane j fetches (and clears) the winner
+// of bit j with one coalesced access and writes its row at rank(word) + popc(bits below j).  Two words per round keep
+// two independent fetches in flight.  (One thread per word with a loop over its bits was 700 us at cfg2: ground rows
+// fill whole words, i.e. 32 dependent DRAM round trips per thread.)
 __global__ void __launch_bounds__(kBlock)
 k_emit_sparse(uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, u64* __restrict__ vtab,
               const int64_t* __restrict__ off, const uint8_t* __restrict__ sem, uint16_t* __restrict__ sparse,
               const int64_t* __restrict__ start, GridDev g, int F) {
-  int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  int64_t total = (int64_t)F * g.gw;
-  bool valid = wg < total;
+  const int64_t wg = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t total = (int64_t)F * g.gw;
+  const bool valid = wg < total;
   uint32_t word, rank;
   load_word_and_rank(bitmap, prefix, wg, valid, true, &word, &rank);
-  if (!valid || !word) return;
-  int f = (int)(wg / g.gw);
-  int64_t fbeg = __ldg(off + f);
+  if (valid && word) bitmap[wg] = 0u;
+  unsigned todo = __ballot_sync(0xffffffffu, valid && word != 0u);
+  if (!todo) return;                                              // warp-uniform
+  const unsigned lane = lane_id();
+  const int64_t warp_wg = wg - lane;                              // gw % 32 == 0: the warp's words belong to one frame
+  const int f = (int)(warp_wg / g.gw);
+  const int64_t fbeg = __ldg(off + f);
   const bool packl = (__ldg(off + f + 1) - fbeg) < kPackLimit;
-  uint32_t bit0 = (uint32_t)(wg - (int64_t)f * g.gw) * 32u;
-  u64* vt = vtab + (size_t)f * g.G + bit0;
+  const uint8_t* sem_f = sem + fbeg;
   const int64_t row0 = start ? __ldg(start + f) : fbeg;
-  uint32_t b = word;
-  while (b) {
-    int j = __ffs(b) - 1;
-    b &= b - 1;
-    const u64 wv = vt[j];
-    vt[j] = 0ull;
+  const uint32_t bit_w0 = (uint32_t)(warp_wg - (int64_t)f * g.gw) * 32u;   // linear id of the warp's first voxel
+  u64* vt = vtab + (size_t)f * g.G + bit_w0;
+  while (todo) {
+    const int s0 = __ffs(todo) - 1; todo &= todo - 1;
+    const int s1 = todo ? __ffs(todo) - 1 : s0; const bool two = todo != 0u; todo &= todo - 1;
+    const uint32_t w0 = __shfl_sync(0xffffffffu, word, s0), w1 = __shfl_sync(0xffffffffu, word, s1);
+    const uint32_t r0 = __shfl_sync(0xffffffffu, rank, s0), r1 = __shfl_sync(0xffffffffu, rank, s1);
+    const bool h0 = (w0 >> lane) & 1u, h1 = two && ((w1 >> lane) & 1u);
+    u64 e0 = 0ull, e1 = 0ull;
+    if (h0) e0 = vt[s0 * 32 + lane];
+    if (h1) e1 = vt[s1 * 32 + lane];
+    if (h0) vt[s0 * 32 + lane] = 0ull;
+    if (h1) vt[s1 * 32 + lane] = 0ull;
     if (sparse) {
-      uint32_t lin = bit0 + (uint32_t)j;
-      uint32_t x = lin % (uint32_t)g.dx;
-      uint32_t yz = lin / (uint32_t)g.dx;
-      uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
-      uint32_t lab = vox_word_label(packl, wv, sem + fbeg);
-      uint2 row = make_uint2(x | (y << 16), z | (lab << 16));
-      *reinterpret_cast<uint2*>(sparse + (size_t)(row0 + rank) * 4) = row;
+      const uint32_t below = (1u << lane) - 1u;
+      if (h0) {
+        const uint32_t lin = bit_w0 + (uint32_t)s0 * 32u + lane;
+        const uint32_t x = lin % (uint32_t)g.dx, yz = lin / (uint32_t)g.dx;
+        const uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
+        const uint32_t lab = vox_word_label(packl, e0, sem_f);
+        *reinterpret_cast<uint2*>(sparse + (size_t)(row0 + r0 + __popc(w0 & below)) * 4) = make_uint2(x | (y << 16), z | (lab << 16));
+      }
+      if (h1) {
+        const uint32_t lin = bit_w0 + (uint32_t)s1 * 32u + lane;
+        const uint32_t x = lin % (uint32_t)g.dx, yz = lin / (uint32_t)g.dx;
+        const uint32_t y = yz % (uint32_t)g.dy, z = yz / (uint32_t)g.dy;
+        const uint32_t lab = vox_word_label(packl, e1, sem_f);
+        *reinterpret_cast<uint2*>(sparse + (size_t)(row0 + r1 + __popc(w1 & below)) * 4) = make_uint2(x | (y << 16), z | (lab << 16));
+      }
     }
-    ++rank;
   }
-  bitmap[wg] = 0u;
 }
 
 // Dense grid when the bitmap is in linear-id order (both outputs requested): per-voxel lookup, nothing is cleared
