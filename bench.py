@@ -211,7 +211,6 @@ def run_ours(args):
         n_launch_per_step = len(prof.kernels)
         for name, ms in prof.kernels:
             per_kernel.setdefault(name, []).append(ms)
-    clocks = sampler.stop()
     kern = {k: float(np.mean(v)) for k, v in per_kernel.items()}
     n_total_pts = torch.tensor([P], dtype=torch.float64, device=device)
     if world > 1:
@@ -225,8 +224,15 @@ def run_ours(args):
                   "k_emit_range": n_frames * HW * 17, "k_bitmap_scan": n_frames * (G // 8)}
     top = max(kern, key=kern.get)
     achieved = alg_kernel.get(top, 0) / (kern[top] * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if top in tj.get("kernels", {}):
+            traffic = tj["kernels"][top]["dram_read_bytes"] + tj["kernels"][top]["dram_write_bytes"]
+            traffic_src = tj.get("source")
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_kernel.get(top, 0), "ms_per_launch": kern[top],
                 "step": {"algorithmic_bytes": alg_step, "achieved": alg_step / (ms_step * 1e-3) / 1e9,
                          "frac": alg_step / (ms_step * 1e-3) / 1e9 / hbm_peak},
@@ -253,6 +259,7 @@ def run_ours(args):
     te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()                     # sampled across the device-timed and the end-to-end timed regions
     e2e = {"value": total_pts * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes),
            "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
            "api": "muvo_b200.pipeline.HostPipeline.submit/result (numpy in, pinned host out: sparse voxel lists + "
