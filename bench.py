@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -145,7 +145,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------- ours
@@ -284,7 +284,7 @@ def run_ours(args):
                            "sharding": "frames sharded by rank, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu_base, "e2e": e2e, "clocks": clocks,
                 "gpu_launches": n_launch_per_step * args.steps, "kernels_per_step": n_launch_per_step, "stages": stages}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -372,7 +372,24 @@ def other_stages(device, rank, world, hbm_peak, args):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line: dict) -> None:
+    """The ONE JSON line, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL's version banner, ...) print to fd 1: keep stdout clean for the single JSON line
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=20)
