@@ -233,43 +233,17 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
   }
 }
 
-constexpr int kRowThreads = 1024;
-constexpr int kRowCap = 54 * 1024;   // floats of staging (216 KB)
-constexpr int kBigCell = 64;         // cells above this many points are summed by the whole warp
-// Segment sums over the cell-sorted staging buffer: one THREAD per cell for the common small cells (sequential,
-// ascending point order), the warp cooperates (lane-strided partials + fixed xor tree) only on cells above kBigCell
-// points.  A warp step covers 32 consecutive cells -> one coalesced 128-byte store.  `w0` = staging index 0's position
-// in the frame's sorted order.
-__device__ __forceinline__ void segment_sums(const float* __restrict__ buf, const uint32_t* __restrict__ cs, int c0, int c1,
-                                             uint32_t w0, float* __restrict__ o) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int cb = c0 + warp * 32; cb < c1; cb += (kRowThreads / 32) * 32) {
-    const int cell = cb + lane;
-    uint32_t s0 = 0, s1 = 0;
-    if (cell < c1) { s0 = cs[cell] - w0; s1 = cs[cell + 1] - w0; }
-    const bool big = (s1 - s0) > (uint32_t)kBigCell;
-    float acc = 0.f;
-    if (!big) for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
-    unsigned todo = __ballot_sync(0xffffffffu, big);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src);
-      float part = 0.f;
-      for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
-#pragma unroll
-      for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
-      if (lane == src) acc = part;
-    }
-    if (cell < c1) o[cell] = acc;
-  }
-}
-
+// (Streaming the whole row through shared memory with cp.async.bulk, 2-3 stages of 32-40 KiB next to the 128 KiB staging
+// buffer, was measured at 436-501 us against 385 us for the gathers below: with one CTA per SM the bulk copies keep
+// < 100 KB in flight per SM, the 16-deep gathers keep ~260 KB.)
 // P (point-major, x_stride_p == 1): one CTA per (frame, channel).  The channel's row x[b, c, :] is streamed in
 // ADDRESS ORDER (HBM friendly; only sectors that hold a kept point are requested), every kept value is dropped
 // into shared memory at its position in the cell-sorted order, and each cell's now contiguous segment is summed
 // (lane-strided partials + fixed xor tree -> deterministic).  Frames with more kept points than fit in shared
 // memory are processed in windows of whole cells.
+constexpr int kRowThreads = 1024;
+constexpr int kRowCap = 54 * 1024;   // floats of staging (216 KB)
+constexpr int kBigCell = 64;         // cells above this many points are summed by the whole warp
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads, 1)
 k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ kp_all, const int32_t* __restrict__ dest_all,
@@ -313,7 +287,29 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
         }
       }
       __syncthreads();
-      segment_sums(buf, cs, c0, c1, w0, o);
+      // Segment sums: one THREAD per cell for the common small cells (sequential, ascending point order), the
+      // warp cooperates (lane-strided partials + fixed xor tree) only on cells above kBigCell points.  A warp
+      // step covers 32 consecutive cells -> one coalesced 128-byte store.
+      for (int cb = c0 + warp * 32; cb < c1; cb += (kRowThreads / 32) * 32) {
+        const int cell = cb + lane;
+        uint32_t s0 = 0, s1 = 0;
+        if (cell < c1) { s0 = cs[cell] - w0; s1 = cs[cell + 1] - w0; }
+        const bool big = (s1 - s0) > (uint32_t)kBigCell;
+        float acc = 0.f;
+        if (!big) for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
+        unsigned todo = __ballot_sync(0xffffffffu, big);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const uint32_t b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src);
+          float part = 0.f;
+          for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
+#pragma unroll
+          for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+          if (lane == src) acc = part;
+        }
+        if (cell < c1) o[cell] = acc;
+      }
       __syncthreads();
     } else {
       // a single cell larger than the staging buffer: gather it straight from global memory (rare)
@@ -328,93 +324,6 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
     }
     c0 = c1;
   }
-}
-
-// P (point-major float32, 16-byte aligned rows, all kept values of the frame fit the staging buffer): the row is
-// STREAMED through shared memory with cp.async.bulk (TMA), two 40 KiB stages, instead of being gathered from global
-// memory: a random top-k mask touches ~92 % of the row's 32-byte sectors anyway, and a bulk copy moves them at full
-// DRAM rate without spending an LSU slot per sector.  Kept values are dropped from the staged chunk into their
-// cell-sorted position; the segment sums are the same as in k_pool_rows (ascending point order, deterministic).
-constexpr int kTmaChunkWc = 10;                         // warp-chunks (1024 points) per stage
-constexpr int kTmaChunk = kTmaChunkWc * kWarpChunk;     // 10240 floats = 40 KiB
-constexpr int kTmaCap = 32 * 1024;                      // floats of cell-sorted staging (128 KiB)
-__device__ __forceinline__ uint32_t bev_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(kRowThreads, 1)
-k_pool_rows_tma(const float* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ kp_all,
-                const int32_t* __restrict__ dest_all, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ chunk_kept,
-                const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C, int n_cells, int n_wc, float* __restrict__ out) {
-  extern __shared__ __align__(128) float smem_f[];
-  float* buf = smem_f;                                   // [kTmaCap]
-  float* stage = smem_f + kTmaCap;                       // [2][kTmaChunk]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + 2 * kTmaChunk);
-  const int tid = threadIdx.x;
-  const int b = blockIdx.x / C, c = blockIdx.x % C;
-  const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
-  const int n_kept = (int)cs[n_cells];
-  const float* xr = x + (size_t)b * sb + (size_t)c * sc;
-  float* o = out + ((size_t)b * C + c) * n_cells;
-  if (n_kept > kTmaCap) {                                // CTA-uniform: rare (no mask): windows of cells, gathers from global
-    const int32_t* list = sorted + (size_t)b * n_pts;
-    const int32_t* kp = kp_all + (size_t)b * n_pts;
-    const int32_t* ds = dest_all + (size_t)b * n_pts;
-    int c0 = 0;
-    while (c0 < n_cells) {
-      const uint32_t w0 = cs[c0];
-      int lo = c0 + 1, hi = n_cells;
-      while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cs[mid] - w0 <= (uint32_t)kTmaCap) lo = mid; else hi = mid - 1; }
-      const int c1 = lo;
-      const uint32_t w1 = cs[c1];
-      if (w1 - w0 <= (uint32_t)kTmaCap) {
-        for (int j = tid; j < n_kept; j += kRowThreads) {
-          const int d = __ldg(ds + j);
-          if (d >= (int)w0 && d < (int)w1) buf[d - (int)w0] = __ldg(xr + __ldg(kp + j));
-        }
-        __syncthreads();
-        segment_sums(buf, cs, c0, c1, w0, o);
-        __syncthreads();
-      } else if (tid < 32) {                             // one cell larger than the staging buffer
-        float acc = 0.f;
-        for (uint32_t j = w0 + tid; j < w1; j += 32) acc += __ldg(xr + list[j]);
-#pragma unroll
-        for (int dd = 16; dd; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
-        if (tid == 0) o[c0] = acc;
-      }
-      c0 = c1;
-    }
-    return;
-  }
-  const int32_t* kp = kp_all + (size_t)b * n_pts;
-  const int32_t* ds = dest_all + (size_t)b * n_pts;
-  const uint32_t* ck = chunk_kept + (size_t)b * n_wc;
-  const int n_chunks = (int)((n_pts + kTmaChunk - 1) / kTmaChunk);
-  auto issue = [&](int i) {                               // one thread: chunk i -> stage i & 1
-    const int64_t p0 = (int64_t)i * kTmaChunk;
-    const uint32_t bytes = (uint32_t)((n_pts - p0 < kTmaChunk ? n_pts - p0 : kTmaChunk) * 4);
-    const uint32_t mb = bev_smem_u32(bar + (i & 1));
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(bev_smem_u32(stage + (size_t)(i & 1) * kTmaChunk)), "l"(xr + p0), "r"(bytes), "r"(mb) : "memory");
-  };
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bev_smem_u32(bar)) : "memory");
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bev_smem_u32(bar + 1)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    issue(0);
-  }
-  __syncthreads();
-  for (int i = 0; i < n_chunks; ++i) {
-    if (tid == 0 && i + 1 < n_chunks) issue(i + 1);       // stage (i+1)&1 was released by the barrier ending chunk i-1
-    const uint32_t mb = bev_smem_u32(bar + (i & 1)), parity = (uint32_t)((i >> 1) & 1);
-    asm volatile("{\n.reg .pred P1;\nBEV_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra BEV_DONE;\nbra BEV_WAIT;\nBEV_DONE:\n}"
-                 ::"r"(mb), "r"(parity) : "memory");
-    const float* sg = stage + (size_t)(i & 1) * kTmaChunk;
-    const int wc0 = i * kTmaChunkWc, wc1 = wc0 + kTmaChunkWc;
-    const int k0 = (int)ck[wc0], k1 = wc1 < n_wc ? (int)ck[wc1] : n_kept;
-    const int p_base = i * kTmaChunk;
-    for (int j = k0 + tid; j < k1; j += kRowThreads) buf[__ldg(ds + j)] = sg[__ldg(kp + j) - p_base];
-    __syncthreads();
-  }
-  segment_sums(buf, cs, 0, n_cells, 0u, o);
 }
 
 // P (generic strides; coalesced when x_stride_c == 1): one block per (frame, cell), threads over channels,
@@ -632,17 +541,6 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
                                                              w.chunk_kept, w.kp, w.dest);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
-  const bool tma_ok = sizeof(T) == 4 && sp == 1 && n_pts % 4 == 0 && sb % 4 == 0 && sc % 4 == 0 && n_pts < ((int64_t)1 << 31) - kTmaChunk &&
-                      (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  if (tma_ok) {
-    const size_t tsmem = (size_t)(kTmaCap + 2 * kTmaChunk) * sizeof(float) + 16;
-    cudaError_t e = cudaFuncSetAttribute(k_pool_rows_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
-    if (e != cudaSuccess) return (int)e;
-    k_pool_rows_tma<<<(unsigned)((int64_t)B * C), kRowThreads, tsmem, st>>>((const float*)x, sb, sc, w.kp, w.dest, w.cell_start,
-                                                                            w.chunk_kept, w.sorted, B, n_pts, C, n_cells, w.n_wc, out);
-    MUVO_AFTER_LAUNCH("k_pool_rows_tma", st);
-    return MUVO_OK;
-  }
   if (sp == 1) {
     const size_t rsmem = (size_t)kRowCap * sizeof(float);
     cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
