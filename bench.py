@@ -353,7 +353,18 @@ def other_stages(device, rank, world, hbm_peak, args):
                            "dense_read_GBps": bytes_f_sector / ms_f / 1e6, "frames": B, "C": C, "n_kept": n_kept,
                            "note": "kernel only (cell ids precomputed); dense_read = whole lifted tensor, the sector-granular bound for a random top-k mask"}
     res["bev_pool_bwd"] = {"ms": ms_b, "algorithmic_GBps": bytes_b / ms_b / 1e6, "frac": bytes_b / ms_b / 1e6 / hbm_peak}
-    del x, xg, out, gout, feat, depth
+    # N2: fused lift-splat on the same inputs (feat, depth -> BEV), forward and backward to feat / depth
+    from muvo_b200.frustum_pooling import lift_splat
+    fl, dl = feat.detach().requires_grad_(True), depth.detach().requires_grad_(True)
+    ms_lf = timed(lambda: lift_splat(fl.detach(), dl.detach(), cell, 2304), steps)
+    ol = lift_splat(fl, dl, cell, 2304)
+    ms_lb = timed(lambda: torch.autograd.grad(ol, (fl, dl), gout, retain_graph=True), steps)
+    bytes_l = B * (C * H * W * 4 + n_pts * 9 + C * 2304 * 4)       # feat + depth + cell ids + out, each once
+    res["lift_splat_fused_fwd"] = {"ms": ms_lf, "algorithmic_GBps": bytes_l / ms_lf / 1e6, "frac": bytes_l / ms_lf / 1e6 / hbm_peak,
+                                   "note": "N2: same output as lift (mile.py:517-521) + bev_pool_fwd, outer product never materialised; "
+                                           "includes the channels-last copy of feat and the cell sort"}
+    res["lift_splat_fused_bwd"] = {"ms": ms_lb, "note": "grad_feat + grad_depth, includes the [B,cells,C] copy of grad_out"}
+    del x, xg, out, gout, feat, depth, fl, dl, ol
     torch.cuda.empty_cache()
     # (d) cfg4: 16 frames per rank, C = 2, counts all-reduced
     yp, yt = synth.occupancy_pair(16, 2, 4000 + rank)

@@ -162,6 +162,19 @@ MUVO_API int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32
                       int32_t n_cells, void* grad_x, int32_t gx_dtype, int64_t gx_stride_b, int64_t gx_stride_p,
                       int64_t gx_stride_c, void* stream);
 
+/* Fused lift-splat (opt-in replacement of the two steps at muvo/models/mile.py:517-523):
+ * out[b,c,cell] = sum over the kept frustum points p = (d, hw) of the cell, ascending p, of depth[b,d,hw] * feat[b,hw,c]
+ * -- the lifted tensor (236 MB per frame at muvo.yml shapes) is never written.
+ *   feat_cl [B, HW, C] float32 (channels-last image features), depth [B, D, HW] float32, cell [B, D*HW] int32 (-1 = dropped)
+ *   out [B, C, n_cells] float32 fully written; workspace = muvo_bev_pool_workspace_bytes(B, D*HW, n_cells).
+ * Backward: gout_cl [B, n_cells, C]; grad_depth [B, D, HW] (0 at dropped points) and grad_feat_cl [B, HW, C], both fully
+ * written, deterministic (no atomics).                                                     */
+MUVO_API int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t* cell, int32_t B, int32_t D,
+                        int32_t HW, int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream);
+MUVO_API int muvo_lift_splat_bwd(const float* gout_cl, const float* feat_cl, const float* depth, const int32_t* cell,
+                        int32_t B, int32_t D, int32_t HW, int32_t C, int32_t n_cells, float* grad_depth,
+                        float* grad_feat_cl, void* stream);
+
 /* Sorted-rank segment sum: QuickCumsum.forward / cumsum_trick (frustum_pooling.py:23-42).
  *   x [n,C] float32 row-major, ranks [n] int64 non-decreasing.
  *   seg_id_out [n] int32 (segment index of each row; scratch + used by the backward),

@@ -14,7 +14,7 @@ from ._lib import MuvoError, load as load_library  # noqa: F401
 from .points import GridSpec, RangeSpec, PointCloud, sensor_to_grid, voxel_filter, voxelize_one_array  # noqa: F401
 from .metrics import SSCMetrics, ssc_counts, ssc_counts_from_logits, all_reduce_counts  # noqa: F401
 from .frustum_pooling import (FrustumPooling, QuickCumsum, VoxelsSumming, cumsum_trick, quick_cumsum, gen_dx_bx,  # noqa: F401
-                              bev_pool, bev_params_to_intrinsics, intrinsics_inverse)
+                              bev_pool, lift_splat, bev_params_to_intrinsics, intrinsics_inverse)
 from .patch import patch, unpatch  # noqa: F401
 from .distributed import shard_frames, init_distributed  # noqa: F401
 

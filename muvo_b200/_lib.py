@@ -53,6 +53,8 @@ SIGNATURES = {
     "muvo_bev_pool_workspace_bytes": (C.c_int, [_I32, _I64, _I32, C.POINTER(_SZ)]),
     "muvo_bev_pool_fwd": (C.c_int, [_P, _I32, _I64, _I64, _I64, _P, _I32, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "muvo_bev_pool_bwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _I32, _I64, _I64, _I64, _P]),
+    "muvo_lift_splat_fwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _SZ, _P]),
+    "muvo_lift_splat_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "muvo_segment_sum_workspace_bytes": (C.c_int, [_I64, C.POINTER(_SZ)]),
     "muvo_segment_sum_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_segment_sum_bwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),

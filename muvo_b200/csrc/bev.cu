@@ -517,6 +517,179 @@ k_seg_bwd(const float* __restrict__ gseg, const int32_t* __restrict__ seg_id, in
   gx[t] = __ldg(gseg + (size_t)__ldg(seg_id + i) * C + ch);
 }
 
+
+// ---------------------------------------------------------------- N2: fused lift-splat (mile.py:508-523 + frustum_pooling.py:131-187)
+// The reference materialises x = depth (B,D,H,W) (outer) feat (B,C,H,W) -- 236 MB per frame at muvo.yml shapes -- and
+// pools it.  Fused: out[b,c,cell] = sum over the cell's kept frustum points p = (d, hw), ascending p, of
+// fl(depth[b,d,hw] * feat[b,c,hw]) -- the same products and the same summation order as lifting and then pooling,
+// without ever writing the product.  feat is taken channels-last ([B, HW, C]) so a point reads one contiguous C-vector.
+//   forward : one CTA per (frame, 8 consecutive cells), threads over channels; every thread owns out[b, c, cell0..cell0+7]
+//             (one 32-byte sector) and walks the cells' sorted point lists.
+//   backward: one warp per pixel (b, hw), lanes over channels; it owns grad_feat[b, hw, :] (sum over the pixel's kept
+//             depth bins in ascending d) and produces grad_depth[b, d, hw] by a fixed xor-tree reduction: no atomics.
+constexpr int kLsCells = 8;
+constexpr int kLsThreads = 512;
+constexpr int kLsStage = 2048;     // points of a cell staged in shared memory per round
+// C % 4 == 0: a thread owns 4 consecutive channels (one 16-byte load per point); the CTA's threads form
+// G = 512 / (C/4) groups that split every cell's point list round-robin (group g takes points g, g+G, ...) -- the
+// heavy cells near the camera hold > 1000 points -- and the G partial sums are added in group order, so the result is
+// a fixed function of the inputs.  The point list and the depth values are staged through shared memory first, so the
+// only global loads in the inner loop are the independent feat vectors.
+__global__ void __launch_bounds__(kLsThreads)
+k_lift_splat_fwd(const float* __restrict__ feat_cl, const float* __restrict__ depth, const uint32_t* __restrict__ cell_start,
+                 const int32_t* __restrict__ sorted, int B, int64_t n_pts, int HW, int C, int n_cells, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char ls_raw[];
+  int* hw_s = reinterpret_cast<int*>(ls_raw);                       // [kLsStage]
+  float* dep_s = reinterpret_cast<float*>(ls_raw) + kLsStage;       // [kLsStage]
+  float4* red = reinterpret_cast<float4*>(dep_s + kLsStage);        // [G][C4]
+  const int C4 = C >> 2;
+  const int G = kLsThreads / C4 > 0 ? kLsThreads / C4 : 1;
+  const int tid = threadIdx.x;
+  const int g = tid / C4, q = tid - g * C4;                          // group, channel quad
+  const bool active = g < G;
+  const int groups = (n_cells + kLsCells - 1) / kLsCells;
+  const int b = blockIdx.x / groups, cell0 = (blockIdx.x % groups) * kLsCells;
+  const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+  const int32_t* list = sorted + (size_t)b * n_pts;
+  const float4* fb = reinterpret_cast<const float4*>(feat_cl + (size_t)b * HW * C);
+  const float* db = depth + (size_t)b * n_pts;
+  float4 res[kLsCells];
+#pragma unroll
+  for (int k = 0; k < kLsCells; ++k) {
+    res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cell = cell0 + k;
+    const uint32_t s0 = cell < n_cells ? cs[cell] : 0u, s1 = cell < n_cells ? cs[cell + 1] : 0u;
+    if (s1 == s0) continue;                                          // CTA-uniform
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t jb = s0; jb < s1; jb += kLsStage) {
+      const int n = (int)(s1 - jb < (uint32_t)kLsStage ? s1 - jb : (uint32_t)kLsStage);
+      __syncthreads();                                               // previous round's readers are done
+      for (int t = tid; t < n; t += kLsThreads) {
+        const int p = list[jb + t];
+        hw_s[t] = p % HW;
+        dep_s[t] = __ldg(db + p);
+      }
+      __syncthreads();
+      if (active) {
+        int t = g;
+        for (; t + 3 * G < n; t += 4 * G) {                          // 4 independent feat loads in flight
+          const float4 f0 = __ldg(fb + (size_t)hw_s[t] * C4 + q), f1 = __ldg(fb + (size_t)hw_s[t + G] * C4 + q),
+                       f2 = __ldg(fb + (size_t)hw_s[t + 2 * G] * C4 + q), f3 = __ldg(fb + (size_t)hw_s[t + 3 * G] * C4 + q);
+          const float d0 = dep_s[t], d1 = dep_s[t + G], d2 = dep_s[t + 2 * G], d3 = dep_s[t + 3 * G];
+          acc.x = __fadd_rn(acc.x, __fmul_rn(d0, f0.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(d0, f0.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(d0, f0.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(d0, f0.w));
+          acc.x = __fadd_rn(acc.x, __fmul_rn(d1, f1.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(d1, f1.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(d1, f1.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(d1, f1.w));
+          acc.x = __fadd_rn(acc.x, __fmul_rn(d2, f2.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(d2, f2.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(d2, f2.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(d2, f2.w));
+          acc.x = __fadd_rn(acc.x, __fmul_rn(d3, f3.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(d3, f3.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(d3, f3.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(d3, f3.w));
+        }
+        for (; t < n; t += G) {
+          const float4 f0 = __ldg(fb + (size_t)hw_s[t] * C4 + q);
+          const float d0 = dep_s[t];
+          acc.x = __fadd_rn(acc.x, __fmul_rn(d0, f0.x)); acc.y = __fadd_rn(acc.y, __fmul_rn(d0, f0.y));
+          acc.z = __fadd_rn(acc.z, __fmul_rn(d0, f0.z)); acc.w = __fadd_rn(acc.w, __fmul_rn(d0, f0.w));
+        }
+      }
+    }
+    if (active) red[g * C4 + q] = acc;
+    __syncthreads();
+    if (g == 0) {                                                    // fixed order over the groups
+      float4 r = red[q];
+      for (int gg = 1; gg < G; ++gg) {
+        const float4 v = red[gg * C4 + q];
+        r.x = __fadd_rn(r.x, v.x); r.y = __fadd_rn(r.y, v.y); r.z = __fadd_rn(r.z, v.z); r.w = __fadd_rn(r.w, v.w);
+      }
+      res[k] = r;
+    }
+  }
+  if (g == 0) {
+    float* o = out + ((size_t)b * C + 4 * q) * n_cells + cell0;
+    const bool vec = (cell0 + kLsCells <= n_cells) && (n_cells % 4 == 0);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      float v[kLsCells];
+#pragma unroll
+      for (int k = 0; k < kLsCells; ++k) v[k] = ch == 0 ? res[k].x : ch == 1 ? res[k].y : ch == 2 ? res[k].z : res[k].w;
+      float* oc = o + (size_t)ch * n_cells;
+      if (vec) {
+        reinterpret_cast<float4*>(oc)[0] = make_float4(v[0], v[1], v[2], v[3]);
+        reinterpret_cast<float4*>(oc)[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kLsCells; ++k) if (cell0 + k < n_cells) oc[k] = v[k];
+      }
+    }
+  }
+}
+
+// C % 4 != 0 or C > 2048: one thread per channel, sequential over the cell's points.
+__global__ void __launch_bounds__(512)
+k_lift_splat_fwd_scalar(const float* __restrict__ feat_cl, const float* __restrict__ depth, const uint32_t* __restrict__ cell_start,
+                        const int32_t* __restrict__ sorted, int B, int64_t n_pts, int HW, int C, int n_cells, float* __restrict__ out) {
+  const int groups = (n_cells + kLsCells - 1) / kLsCells;
+  const int b = blockIdx.x / groups, cell0 = (blockIdx.x % groups) * kLsCells;
+  const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+  const int32_t* list = sorted + (size_t)b * n_pts;
+  const float* fb = feat_cl + (size_t)b * HW * C;
+  const float* db = depth + (size_t)b * n_pts;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int k = 0; k < kLsCells; ++k) {
+      const int cell = cell0 + k;
+      if (cell >= n_cells) break;
+      float acc = 0.f;
+      for (uint32_t j = cs[cell]; j < cs[cell + 1]; ++j) {
+        const int p = list[j];
+        acc = __fadd_rn(acc, __fmul_rn(__ldg(db + p), __ldg(fb + (size_t)(p % HW) * C + c)));
+      }
+      out[((size_t)b * C + c) * n_cells + cell] = acc;
+    }
+  }
+}
+
+// grad_depth[b,d,hw] = kept ? sum_c gout[b,cell,c] * feat[b,hw,c] : 0 ; grad_feat[b,hw,c] = sum_{d kept} depth[b,d,hw] * gout[b,cell,c]
+// gout_cl is the output gradient in [B, n_cells, C] order.  One warp per pixel; lane L owns channels L, L+32, ...
+constexpr int kLsMaxC = 1024;    // channels held in registers per lane: kLsMaxC / 32
+template <int CPL>
+__global__ void __launch_bounds__(256)
+k_lift_splat_bwd(const float* __restrict__ gout_cl, const float* __restrict__ feat_cl, const float* __restrict__ depth,
+                 const int32_t* __restrict__ cell, int B, int D, int HW, int C, int n_cells, float* __restrict__ grad_depth,
+                 float* __restrict__ grad_feat_cl) {
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (wid >= (int64_t)B * HW) return;
+  const int b = (int)(wid / HW), hw = (int)(wid % HW);
+  const float* f = feat_cl + ((size_t)b * HW + hw) * C;
+  float fv[CPL], gf[CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) { const int c = lane + 32 * k; fv[k] = c < C ? __ldg(f + c) : 0.f; gf[k] = 0.f; }
+  const int32_t* cp = cell + (size_t)b * D * HW + hw;
+  const float* dp = depth + (size_t)b * D * HW + hw;
+  float* gd = grad_depth + (size_t)b * D * HW + hw;
+  for (int d = 0; d < D; ++d) {
+    const int cl = __ldg(cp + (size_t)d * HW);
+    float dot = 0.f;
+    if (cl >= 0 && cl < n_cells) {                      // warp-uniform
+      const float dv = __ldg(dp + (size_t)d * HW);
+      const float* g = gout_cl + ((size_t)b * n_cells + cl) * C;
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = lane + 32 * k;
+        const float gv = c < C ? __ldg(g + c) : 0.f;
+        dot = __fadd_rn(dot, __fmul_rn(gv, fv[k]));
+        gf[k] = __fadd_rn(gf[k], __fmul_rn(dv, gv));
+      }
+#pragma unroll
+      for (int dd = 16; dd; dd >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, dd);
+    }
+    if (lane == 0) gd[(size_t)d * HW] = dot;
+  }
+  float* o = grad_feat_cl + ((size_t)b * HW + hw) * C;
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) { const int c = lane + 32 * k; if (c < C) o[c] = gf[k]; }
+}
+
 template <typename T>
 static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const int32_t* cell, int B, int64_t n_pts, int C,
                         int n_cells, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -632,6 +805,74 @@ int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int
     case MUVO_BF16: return run_pool_bwd<__nv_bfloat16>(grad_out, cell, B, n_pts, C, n_cells, (__nv_bfloat16*)grad_x, gx_stride_b, gx_stride_p, gx_stride_c, st);
     default: return MUVO_E_ARG;
   }
+}
+
+int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t* cell, int32_t B, int32_t D, int32_t HW,
+                        int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (B < 0 || D <= 0 || HW <= 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || C == 0) return MUVO_OK;
+  if (!feat_cl || !depth || !cell || !out || !ws) return MUVO_E_NULL;
+  const int64_t n_pts = (int64_t)D * HW;
+  if (n_pts >= ((int64_t)1 << 31) || (int64_t)B * n_cells >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  BevWs w = carve_bev(ws, B, n_pts, n_cells);
+  if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+  const size_t smem = (size_t)kSortWarps * n_cells * 4;
+  if (smem > 200 * 1024) return MUVO_E_SHAPE;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_cell_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cell_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const int64_t n_chunks = (int64_t)B * w.n_wc;
+  const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
+  prof_mark("<lift_splat_fwd>", st);
+  k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.chunk_kept);
+  MUVO_AFTER_LAUNCH("k_cell_hist", st);
+  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
+  MUVO_AFTER_LAUNCH("k_cell_scan", st);
+  k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
+  MUVO_AFTER_LAUNCH("k_cell_starts", st);
+  k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
+                                                             w.chunk_kept, w.kp, w.dest);
+  MUVO_AFTER_LAUNCH("k_cell_place", st);
+  const int groups = (n_cells + kLsCells - 1) / kLsCells;
+  if (C % 4 == 0 && C / 4 <= kLsThreads && (reinterpret_cast<uintptr_t>(feat_cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int C4 = C / 4, G = kLsThreads / C4;
+    const size_t lsmem = (size_t)kLsStage * 8 + (size_t)G * C4 * 16;
+    k_lift_splat_fwd<<<(unsigned)((int64_t)B * groups), kLsThreads, lsmem, st>>>(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW,
+                                                                                 C, n_cells, out);
+  } else {
+    int threads = ((C + 31) / 32) * 32;
+    if (threads > 512) threads = 512;
+    k_lift_splat_fwd_scalar<<<(unsigned)((int64_t)B * groups), threads, 0, st>>>(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW,
+                                                                                 C, n_cells, out);
+  }
+  MUVO_AFTER_LAUNCH("k_lift_splat_fwd", st);
+  return MUVO_OK;
+}
+
+int muvo_lift_splat_bwd(const float* gout_cl, const float* feat_cl, const float* depth, const int32_t* cell, int32_t B,
+                        int32_t D, int32_t HW, int32_t C, int32_t n_cells, float* grad_depth, float* grad_feat_cl,
+                        void* stream) {
+  if (B < 0 || D <= 0 || HW <= 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (C > kLsMaxC) return MUVO_E_SHAPE;
+  if (B == 0) return MUVO_OK;
+  if (!gout_cl || !feat_cl || !depth || !cell || !grad_depth || !grad_feat_cl) return MUVO_E_NULL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t warps = (int64_t)B * HW;
+  const unsigned blocks = (unsigned)ceil_div64(warps * 32, 256);
+  prof_mark("<lift_splat_bwd>", st);
+  const int cpl = (C + 31) / 32;
+  if (cpl <= 2)       k_lift_splat_bwd<2><<<blocks, 256, 0, st>>>(gout_cl, feat_cl, depth, cell, B, D, HW, C, n_cells, grad_depth, grad_feat_cl);
+  else if (cpl <= 4)  k_lift_splat_bwd<4><<<blocks, 256, 0, st>>>(gout_cl, feat_cl, depth, cell, B, D, HW, C, n_cells, grad_depth, grad_feat_cl);
+  else if (cpl <= 8)  k_lift_splat_bwd<8><<<blocks, 256, 0, st>>>(gout_cl, feat_cl, depth, cell, B, D, HW, C, n_cells, grad_depth, grad_feat_cl);
+  else if (cpl <= 12) k_lift_splat_bwd<12><<<blocks, 256, 0, st>>>(gout_cl, feat_cl, depth, cell, B, D, HW, C, n_cells, grad_depth, grad_feat_cl);
+  else if (cpl <= 16) k_lift_splat_bwd<16><<<blocks, 256, 0, st>>>(gout_cl, feat_cl, depth, cell, B, D, HW, C, n_cells, grad_depth, grad_feat_cl);
+  else                k_lift_splat_bwd<32><<<blocks, 256, 0, st>>>(gout_cl, feat_cl, depth, cell, B, D, HW, C, n_cells, grad_depth, grad_feat_cl);
+  MUVO_AFTER_LAUNCH("k_lift_splat_bwd", st);
+  return MUVO_OK;
 }
 
 int muvo_segment_sum_workspace_bytes(int64_t n, size_t* bytes_out_h) {

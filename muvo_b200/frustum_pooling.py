@@ -138,6 +138,57 @@ def bev_pool(x: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
     return _BevPool.apply(x, cell, int(n_cells))
 
 
+class _LiftSplat(torch.autograd.Function):
+    """Fused lift-splat: ``out[b,c,cell] = sum_p depth[b,p] * feat[b,c,hw(p)]`` over the kept frustum
+    points of the cell -- what ``bev_pool`` returns for the lifted tensor of mile.py:517-521, without building it."""
+
+    @staticmethod
+    def forward(ctx, feat, depth, cell, n_cells):
+        _lib.require_cuda(feat, depth, cell)
+        lib = _lib.load()
+        B, Cc, H, W = feat.shape
+        D = depth.shape[1]
+        if depth.shape != (B, D, H, W):
+            raise ValueError("depth must be (B, D, H, W) matching feat (B, C, H, W)")
+        dev = feat.device
+        feat_cl = feat.detach().float().permute(0, 2, 3, 1).contiguous()          # [B, HW, C]: one C-vector per pixel
+        dep = depth.detach().float().contiguous()
+        cell = cell.reshape(B, D * H * W).contiguous()
+        out = torch.empty((B, Cc, n_cells), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(dev)
+            nb = C.c_size_t(0)
+            _lib.check(lib.muvo_bev_pool_workspace_bytes(B, D * H * W, n_cells, C.byref(nb)), "muvo_bev_pool_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            rc = lib.muvo_lift_splat_fwd(feat_cl.data_ptr(), dep.data_ptr(), _lib.ptr(cell), B, D, H * W, Cc, n_cells,
+                                         out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "muvo_lift_splat_fwd")
+        ctx.save_for_backward(feat_cl, dep, cell)
+        ctx.meta = (B, Cc, D, H, W, n_cells, feat.dtype, depth.dtype)
+        ctx.mark_non_differentiable(cell)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        feat_cl, dep, cell = ctx.saved_tensors
+        B, Cc, D, H, W, n_cells, fdt, ddt = ctx.meta
+        dev = grad_out.device
+        gout_cl = grad_out.float().permute(0, 2, 1).contiguous()                    # [B, n_cells, C]
+        gdepth = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+        gfeat_cl = torch.empty((B, H, W, Cc), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.load().muvo_lift_splat_bwd(gout_cl.data_ptr(), feat_cl.data_ptr(), dep.data_ptr(), _lib.ptr(cell), B, D,
+                                                 H * W, Cc, n_cells, gdepth.data_ptr(), gfeat_cl.data_ptr(),
+                                                 _lib.current_stream(dev))
+        _lib.check(rc, "muvo_lift_splat_bwd")
+        return gfeat_cl.permute(0, 3, 1, 2).to(fdt), gdepth.to(ddt), None, None
+
+
+def lift_splat(feat: torch.Tensor, depth: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
+    """``feat (B,C,H,W)``, ``depth (B,D,H,W)``, ``cell (B, D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
+    return _LiftSplat.apply(feat, depth, cell, int(n_cells))
+
+
 class QuickCumsum(torch.autograd.Function):
     """Sorted-rank segment sum; drop-in for ``QuickCumsum`` (frustum_pooling.py:34-60)."""
 
@@ -274,6 +325,19 @@ class FrustumPooling(nn.Module):
         geom = self.get_geometry(rots, trans, intrinsics)
         x = self.voxel_pooling(geom, x, mask).type_as(x)
         return x
+
+    def lift_splat(self, feat, depth, intrinsics, pose, mask=torch.zeros(0)):
+        """Opt-in fused replacement of ``forward((depth[:,None] * feat[:,:,None])[:,None].permute(0,1,3,4,5,2), ...)``
+        (muvo/models/mile.py:517-523): same output, the (B,C,D,H,W) outer product is never materialised and the
+        gradients go straight to ``feat`` and ``depth``.  ``feat (B,C,fH,fW)``, ``depth (B,D,fH,fW)``, one camera."""
+        B, Cc, H, W = feat.shape
+        self.initialize_frustum(feat.new_zeros((1, 1, 1, H, W, 1)))
+        geom = self.get_geometry(pose[..., :3, :3], pose[..., :3, 3:], intrinsics)
+        nx, ny, nz = self.nx_constant
+        cell = self.cell_ids(geom, mask)
+        out = lift_splat(feat, depth, cell, nx * ny * nz).view(B, Cc, nz, ny, nx)
+        out = out.view(B, Cc, ny, nx) if nz == 1 else out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
+        return out.type_as(feat)
 
     def get_depth_map(self, depth):
         """frustum_pooling.py:211-217."""

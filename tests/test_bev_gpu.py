@@ -192,3 +192,38 @@ def test_windowed_and_oversized_cells(lib):
     mg = base[0, :, 0, 0].cpu().double()[:, keep].abs().sum(1)
     assert torch.all((out[0, :, 5].cpu().double() - want).abs() <= TOL * mg)
     assert torch.count_nonzero(out[0, :, :5]) == 0 and torch.count_nonzero(out[0, :, 6:]) == 0
+
+
+# ------------------------------------------------------------------ N2: fused lift-splat
+@pytest.mark.parametrize("B,C,use_mask", [(2, 8, True), (1, 40, False), (1, 384, True)])
+def test_fused_lift_splat_forward_and_gradients(B, C, use_mask, lib):
+    """``FrustumPooling.lift_splat(feat, depth, ...)`` == lifting (mile.py:517-521) + ``FrustumPooling.forward``:
+    forward within 1e-5 of the pooled magnitude against the float64 oracle (and against our unfused path), gradients
+    w.r.t. feat and depth within 1e-5 relative of float64 autograd through the reference formulation."""
+    feat, depth, mask, K, E = synth.bev_inputs(B, C, 3100 + C)
+    m = mask if use_mask else torch.zeros(0)
+    fp = module()
+    f = feat.cuda().requires_grad_(True)
+    d = depth.cuda().requires_grad_(True)
+    out = fp.lift_splat(f, d, K.cuda()[:, None], E.cuda()[:, None], m.cuda())
+    assert out.shape == (B, C, 48, 48) and out.dtype == torch.float32
+    xl = synth.lift(feat, depth)
+    exact = O.frustum_pooling_forward(xl.double(), K[:, None], E[:, None], m, exact=True, **synth.BEV_POOL_ARGS)
+    mag = O.frustum_pooling_forward(xl.double().abs(), K[:, None], E[:, None], m, exact=True, **synth.BEV_POOL_ARGS)
+    assert torch.all((out.detach().cpu().double() - exact).abs() <= TOL * mag + 1e-30)
+    unfused = fp(synth.lift(feat.cuda(), depth.cuda()), K.cuda()[:, None], E.cuda()[:, None], m.cuda())
+    assert torch.all((out.detach() - unfused).abs().cpu().double() <= TOL * mag + 1e-30)
+    assert torch.equal(out.detach() == 0, unfused == 0)
+    # gradients: float64 autograd through lift + exact pooling on the CPU
+    gout = torch.randn(out.shape, generator=torch.Generator().manual_seed(7))
+    out.backward(gout.cuda())
+    f64 = feat.double().requires_grad_(True)
+    d64 = depth.double().requires_grad_(True)
+    ref = O.frustum_pooling_forward(synth.lift(f64, d64), K[:, None], E[:, None], m, exact=True, **synth.BEV_POOL_ARGS)
+    ref.backward(gout.double())
+    for got, want in ((f.grad, f64.grad), (d.grad, d64.grad)):
+        assert got.shape == want.shape
+        assert (got.cpu().double() - want).abs().max() <= TOL * want.abs().max()
+    # dropped points get exactly zero depth gradient
+    cell = fp.cell_ids(fp.get_geometry(E.cuda()[:, None, :3, :3], E.cuda()[:, None, :3, 3:], K.cuda()[:, None]), m.cuda())
+    assert torch.all(d.grad.reshape(B, -1)[cell < 0] == 0)

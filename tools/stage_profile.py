@@ -43,6 +43,12 @@ g = torch.ones_like(out)
 show("bev_fwd", lambda: bev_pool(x.detach(), cell, 2304))
 from muvo_b200.frustum_pooling import bev_pool_backward  # noqa: E402
 show("bev_bwd", lambda: bev_pool_backward(g, cell, tuple(x.shape), x.dtype, 2304, x.stride()))
+fl = feat.detach().requires_grad_(True)
+dl = depth.detach().requires_grad_(True)
+from muvo_b200.frustum_pooling import lift_splat  # noqa: E402
+show("lift_splat_fwd", lambda: lift_splat(fl.detach(), dl.detach(), cell, 2304))
+ol = lift_splat(fl, dl, cell, 2304)
+show("lift_splat_bwd", lambda: torch.autograd.grad(ol, (fl, dl), g.view(ol.shape), retain_graph=True))
 xc = x.detach().contiguous()
 show("bev_fwd_cl", lambda: bev_pool(xc, cell, 2304))
 for Cn in (2, 9, 23):
