@@ -110,6 +110,20 @@ MUVO_API int muvo_points_workspace_bytes(int64_t n_points_total, int32_t n_frame
 /* Put a freshly allocated (or dirty) workspace into the clean state. */
 MUVO_API int muvo_ws_reset(void* ws, size_t ws_bytes, void* stream);
 
+/* ---- N1: camera + LiDAR cloud in front of (a) -------------------------------------
+ * Replaces merge_pcd(), data/data_preprocessing.py:125-139 (depth decode :72-77, depth2pcd :87-106, convert_coor_img
+ * :109-119, convert_coor_lidar :121-123, ego-box mask :133-138), bit-exact in float64, order preserving.
+ *   img_bgra  [H,W,4] uint8 as cv2.imread(file, -1) returns the encoded depth + semantic image
+ *   focal = W / (2 tan(fov pi / 360)) (the host evaluates it as numpy does), range = 100 (:87)
+ *   camera_pos_h [3] (forward, right, up; float32 values, :111), lidar_pos_h [3], ego_box_h [6] = lo xyz, hi xyz or NULL
+ *   lidar_xyz [N,3] float32 in the LiDAR frame, lidar_sem [N] uint8
+ *   xyz_out [H*W + N, 3] float64, sem_out [H*W + N] uint8 (first *n_out rows valid), n_out [1] int64 (device)        */
+MUVO_API int muvo_merge_pcd_workspace_bytes(int32_t H, int32_t W, int64_t n_lidar, size_t* bytes_out_h);
+MUVO_API int muvo_merge_pcd(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, double range,
+                   const double* camera_pos_h, const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar,
+                   const double* lidar_pos_h, const double* ego_box_h, double* xyz_out, uint8_t* sem_out,
+                   int64_t* n_out, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- (a) voxelisation ------------------------------------------------------------
  * Replaces voxel_filter(), data/data_preprocessing.py:172-228, batched over frames, and
  * (dense_out) the densify step of muvo/data/dataset.py:317-327.

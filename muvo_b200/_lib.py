@@ -45,6 +45,9 @@ SIGNATURES = {
     "muvo_profile_end": (C.c_int, [_P, _I32, C.POINTER(C.c_float), C.POINTER(C.c_char_p), C.POINTER(_I32)]),
     "muvo_points_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(MuvoGrid), C.POINTER(MuvoRangeCfg), C.POINTER(_SZ)]),
     "muvo_ws_reset": (C.c_int, [_P, _SZ, _P]),
+    "muvo_merge_pcd_workspace_bytes": (C.c_int, [_I32, _I32, _I64, C.POINTER(_SZ)]),
+    "muvo_merge_pcd": (C.c_int, [_P, _I32, _I32, C.c_double, C.c_double, C.POINTER(C.c_double), _P, _P, _I64, C.POINTER(C.c_double),
+                                 C.POINTER(C.c_double), _P, _P, _P, _P, _SZ, _P]),
     "muvo_voxelize": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_range_project": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoRangeCfg), _I32, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_points_fused": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, C.POINTER(MuvoRangeCfg), _I32,

@@ -20,8 +20,9 @@ OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # points.cu reproduces numpy's float64 arithmetic: no FMA contraction allowed there.
-PER_FILE = {"points.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split()}   # MUVO_NVCC_EXTRA: tuning builds only
-SOURCES = ["api.cu", "points.cu", "ssc.cu", "bev.cu"]
+PER_FILE = {"points.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split(),
+            "merge.cu": ["-fmad=false"]}   # MUVO_NVCC_EXTRA: tuning builds only
+SOURCES = ["api.cu", "points.cu", "ssc.cu", "bev.cu", "merge.cu"]
 
 
 def _nvcc() -> str:

@@ -240,6 +240,83 @@ def voxel_filter(pcd, sem, voxel_resolution, voxel_size, offset):
     return np.ascontiguousarray(rows[:, :3]), rows[:, 3].astype(np.uint8)
 
 
+EGO_VEHICLE_DIMENSION = [4.902, 2.128, 1.511]          # data/data_preprocessing.py:5
+
+
+def merge_pcd_device(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, mask_ego=True, device=None):
+    """Camera + LiDAR cloud of ``merge_pcd`` (data/data_preprocessing.py:125-139) built on the GPU.
+
+    ``img`` = ``cv2.imread(depth_file, -1)`` (uint8 ``(H,W,4)``: encoded depth in B,G,R + semantic tag), ``lidar_xyz``
+    float32 ``(N,3)`` in the LiDAR frame with ``lidar_sem`` uint8.  Returns DEVICE tensors ``(xyz float64 (n,3),
+    sem uint8 (n,))`` in the reference's order (one host sync for ``n``, the data-dependent length)."""
+    if not torch.cuda.is_available():
+        raise _lib.MuvoError("muvo_b200 kernels need a CUDA device (sm_100a); no CPU fallback exists")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    lib = _lib.load()
+    img_t = torch.as_tensor(np.ascontiguousarray(img, dtype=np.uint8)) if not isinstance(img, torch.Tensor) else img
+    if img_t.dim() != 3 or img_t.shape[2] != 4 or img_t.dtype != torch.uint8:
+        raise ValueError("img must be uint8 (H, W, 4) as cv2.imread(file, -1) returns it")
+    H, W = int(img_t.shape[0]), int(img_t.shape[1])
+    img_t = img_t.to(dev).contiguous()
+    lx = torch.as_tensor(np.ascontiguousarray(lidar_xyz, dtype=np.float32)) if not isinstance(lidar_xyz, torch.Tensor) else lidar_xyz
+    ls = torch.as_tensor(np.ascontiguousarray(np.asarray(lidar_sem).reshape(-1), dtype=np.uint8)) if not isinstance(lidar_sem, torch.Tensor) else lidar_sem
+    lx, ls = lx.to(dev, torch.float32).contiguous(), ls.to(dev, torch.uint8).reshape(-1).contiguous()
+    N = int(lx.shape[0])
+    focal = float(W / (2.0 * np.tan(fov * np.pi / 360.0)))                       # :89, evaluated by numpy as the reference does
+    cam = (C.c_double * 3)(*[float(np.float32(v)) for v in camera_pos])          # the 4x4 matrix is np.float32 (:111)
+    lid = (C.c_double * 3)(*[float(v) for v in lidar_pos])
+    box = None
+    if mask_ego:
+        x, y, z = EGO_VEHICLE_DIMENSION
+        box = (C.c_double * 6)(-x / 2, -y / 2, 0.0, x / 2, y / 2, z)
+    n_max = H * W + N
+    xyz = torch.empty((max(n_max, 1), 3), dtype=torch.float64, device=dev)
+    sem = torch.empty((max(n_max, 1),), dtype=torch.uint8, device=dev)
+    n_out = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        nb = C.c_size_t(0)
+        _lib.check(lib.muvo_merge_pcd_workspace_bytes(H, W, N, C.byref(nb)), "muvo_merge_pcd_workspace_bytes")
+        ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+        rc = lib.muvo_merge_pcd(_lib.ptr(img_t), H, W, focal, 100.0, cam, _lib.ptr(lx), _lib.ptr(ls), N, lid, box, xyz.data_ptr(),
+                                sem.data_ptr(), n_out.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream(dev))
+    _lib.check(rc, "muvo_merge_pcd")
+    n = int(n_out.item())
+    return xyz[:n], sem[:n]
+
+
+def merge_pcd_arrays(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, mask_ego=True):
+    """``merge_pcd`` on arrays, NumPy in / NumPy out: ``(pcd float64 (n,3), semantic uint8 (n,1))``."""
+    xyz, sem = merge_pcd_device(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov, mask_ego)
+    return xyz.cpu().numpy(), sem.cpu().numpy()[:, None]
+
+
+def merge_pcd(depth_file, lidar_file, camera_pos, lidar_pos, fov=110, mask_ego=True):
+    """Drop-in for ``merge_pcd`` (data/data_preprocessing.py:125-139): same arguments (file names) and returns."""
+    import cv2
+    img = cv2.imread(depth_file, -1)
+    data = np.load(lidar_file, allow_pickle=True).item()                         # load_lidar, :80-84
+    return merge_pcd_arrays(img, data['points_xyz'], data['ObjTag'], camera_pos, lidar_pos, fov, mask_ego)
+
+
+def voxelize_one(depth_file, lidar_file, cfg, save_name, pipe=None):
+    """Drop-in for ``voxelize_one`` (data/generate_voxels.py:64-77): merge on the GPU, voxelise the float64 cloud on the
+    GPU without a round trip through the host, save the ``(n,4) uint16`` array."""
+    import cv2
+    img = cv2.imread(depth_file, -1)
+    data = np.load(lidar_file, allow_pickle=True).item()
+    xyz, sem = merge_pcd_device(img, data['points_xyz'], data['ObjTag'], cfg.camera_position, cfg.lidar_position, cfg.fov)
+    offset_x = cfg.bev_offset_forward * cfg.bev_resolution
+    offset_z = cfg.offset_z * cfg.voxel_resolution
+    spec = GridSpec(cfg.voxel_resolution, tuple(cfg.voxel_size), (offset_x, 0, offset_z))
+    r = sensor_to_grid(xyz, sem, None, grid=spec, dense=False, sparse=True)
+    n = int(r["n_occ"][0].item())
+    out = r["voxel_sparse"][:n].cpu().numpy().view(np.uint16)
+    np.save(f'{save_name}', out)
+    if pipe is not None:
+        pipe.send(['x'])
+    return out
+
+
 def voxelize_one_array(pcd, sem, voxel_resolution, voxel_size, offset):
     """``(n,4) uint16 [x,y,z,label]`` as saved by ``voxelize_one`` (data/generate_voxels.py:64-73)."""
     vox, lab = voxel_filter(pcd, sem, voxel_resolution, voxel_size, offset)

@@ -97,6 +97,32 @@ def lidar_batch(n_frames: int, n_min: int, n_max: int, seed0: int):
     return np.concatenate(pts), np.concatenate(sems), offsets
 
 
+def carla_depth_image(seed: int, h: int = 600, w: int = 960):
+    """CARLA-style encoded depth + semantic image as ``cv2.imread(file, -1)`` returns it: uint8 ``(h, w, 4)`` with
+    depth = 1000 * (R + 256 G + 256^2 B) / (256^3 - 1) metres in channels [B, G, R] = img[..., :3] read as
+    ``depth_color[..., 2], [..., 1], [..., 0]`` (data/data_preprocessing.py:72-77) and the semantic tag in channel 3.
+    Ground plane below the camera, a far wall, sky (depth 1000 -> dropped), a few exact-range and near-ego pixels."""
+    rng = np.random.default_rng(seed)
+    v, u = np.mgrid[0:h, 0:w]
+    f = w / (2.0 * np.tan(110 * np.pi / 360.0))
+    ray_y = (v - h / 2.0) / f                               # image y down
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d_ground = np.where(ray_y > 1e-3, 2.0 / ray_y, np.inf)      # camera 2 m above the ground
+    d_wall = rng.uniform(15.0, 90.0) + 5.0 * np.sin(u / 37.0)
+    depth = np.minimum(d_ground, d_wall) + rng.normal(0, 0.01, (h, w))
+    depth = np.clip(depth, 0.3, 1000.0)
+    depth[: h // 6] = 1000.0                                 # sky
+    depth[rng.random((h, w)) < 0.01] = rng.uniform(0.5, 3.0)  # close clutter (some of it inside the ego box)
+    code = np.round(depth / 1000.0 * (256 ** 3 - 1)).astype(np.int64)
+    code = np.clip(code, 0, 256 ** 3 - 1)
+    img = np.zeros((h, w, 4), dtype=np.uint8)
+    img[..., 0] = code & 255                                  # depth_color[..., 0]
+    img[..., 1] = (code >> 8) & 255
+    img[..., 2] = (code >> 16) & 255
+    img[..., 3] = np.where(depth >= 1000.0, 13, np.where(d_ground < d_wall, 7, 1)).astype(np.uint8)
+    return img
+
+
 def muvo_camera():
     """Cropped intrinsics / extrinsics used by the BEV lift at muvo.yml geometry.
 

@@ -28,7 +28,7 @@ __all__ = [
     "label_remap_table", "range_projection", "range_projection_indices", "pack_range_view",
     "bev_intrinsics", "gen_dx_bx", "frustum_grid", "frustum_geometry", "bev_cell_ids",
     "cumsum_trick", "quick_cumsum_backward", "voxel_pooling_cumsum", "voxel_pooling_exact",
-    "frustum_pooling_forward", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
+    "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
     "ssc_stats_from_counts",
 ]
 
@@ -130,6 +130,57 @@ def densify_voxels(voxel_data, voxel_size, remap=None):
     grid = np.zeros(tuple(voxel_size), dtype=np.uint8)
     grid[pts[:, 0], pts[:, 1], pts[:, 2]] = lab                     # :326
     return grid
+
+
+# --------------------------------------------------------------------------- N1: camera + LiDAR cloud in front of (a)
+EGO_VEHICLE_DIMENSION = [4.902, 2.128, 1.511]          # data/data_preprocessing.py:5
+
+
+def decode_depth_image(img):
+    """``read_img`` without the file access (data/data_preprocessing.py:72-77): ``img`` = ``cv2.imread(file, -1)``,
+    uint8 ``(H, W, 4)`` [B, G, R, semantic] -> (depth float64 (H,W) in metres, semantic uint8 (H,W))."""
+    depth_color = img[..., :-1].astype(float)
+    semantic = img[..., -1]
+    depth = 1000 * ((256 ** 2 * depth_color[..., 2] + 256 * depth_color[..., 1] + depth_color[..., 0]) / (256 ** 3 - 1))
+    return depth, semantic
+
+
+def depth2pcd(depth, semantic, fov, range=100):
+    """data/data_preprocessing.py:87-106, float64 throughout; pixels in row-major order."""
+    h, w = depth.shape
+    f = w / (2.0 * np.tan(fov * np.pi / 360.0))
+    cx, cy = w / 2.0, h / 2.0
+    d = depth.reshape(-1)
+    valid = d < 1000                                                             # :94
+    yy, xx = np.divmod(np.arange(h * w), w)
+    d, xx, yy = d[valid], xx[valid], yy[valid]
+    x, y = (xx - cx) * d / f, (yy - cy) * d / f                                  # :101
+    pts = np.stack([x, y, d], axis=1)
+    sem = semantic.reshape(-1, 1)[valid]
+    keep = np.sqrt((x * x + y * y) + d * d) < range                              # :104  np.linalg.norm(axis=1)
+    return pts[keep], sem[keep]
+
+
+def merge_pcd_arrays(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, mask_ego=True):
+    """``merge_pcd`` (data/data_preprocessing.py:125-139) on arrays instead of files: camera cloud (float64) followed
+    by the LiDAR cloud (float32 values), ego-box points removed, order preserved.  Returns ``(pcd float64 (n,3),
+    semantic uint8 (n,1))``.  The 4x4 float32 ``mat @ pcd.T`` of convert_coor_img (:109-119) has one non-zero
+    coefficient of +-1 per row besides the translation, so each coordinate is a single rounded float64 sum."""
+    depth, semantic = decode_depth_image(img)
+    ip, isem = depth2pcd(depth, semantic, fov)
+    forward, right, up = (np.float64(np.float32(v)) for v in camera_pos)           # mat is np.float32 (:111)
+    img_pcd = np.stack([ip[:, 2] + forward, -ip[:, 0] + (-right), -ip[:, 1] + up], axis=1)
+    lp = np.array(lidar_xyz, dtype=np.float32, copy=True)
+    lp += np.asarray(lidar_pos)                                                  # :122 float32 in-place add
+    lp[:, 1] *= -1                                                               # :123
+    pcd = np.concatenate([img_pcd, lp], axis=0)
+    sem = np.concatenate([isem, np.asarray(lidar_sem).reshape(-1, 1)], axis=0)
+    if mask_ego:
+        x, y, z = EGO_VEHICLE_DIMENSION
+        box = np.array([[-x / 2, -y / 2, 0], [x / 2, y / 2, z]])
+        ego = ((box[0] < pcd) & (pcd < box[1])).all(axis=1)                      # :136
+        pcd, sem = pcd[~ego], sem[~ego]
+    return pcd, sem
 
 
 # --------------------------------------------------------------------------- (b)

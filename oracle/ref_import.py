@@ -46,6 +46,8 @@ def load() -> types.SimpleNamespace:
         metrics=metrics,
         voxel_filter=data_preprocessing.voxel_filter,
         convert_coor_lidar=data_preprocessing.convert_coor_lidar,
+        merge_pcd=data_preprocessing.merge_pcd,
+        read_img=data_preprocessing.read_img,
         PointCloud=geometry_utils.PointCloud,
         calculate_geometry=geometry_utils.calculate_geometry,
         FrustumPooling=frustum_pooling.FrustumPooling,

@@ -154,8 +154,26 @@ def golden_ssc(R):
     save("ssc.npz", **out)
 
 
+def golden_merge(R):
+    """N1: the reference's merge_pcd (file based) on a synthetic encoded depth image + LiDAR sweep, then its voxel_filter."""
+    import tempfile
+    import cv2
+    img = synth.carla_depth_image(5000, h=150, w=240)                    # small fixture; full size runs in the tests via the oracle
+    pts, sem = synth.carla_lidar_frame(8000, 5001)
+    lid = pts.copy(); lid[:, 1] *= -1; lid -= np.float32([1, 0, 2])      # back to the LiDAR frame (the file format)
+    with tempfile.TemporaryDirectory() as td:
+        cv2.imwrite(os.path.join(td, "d.png"), img)
+        np.save(os.path.join(td, "l.npy"), {"points_xyz": lid.copy(), "ObjTag": sem}, allow_pickle=True)
+        pcd, s = R.merge_pcd(os.path.join(td, "d.png"), os.path.join(td, "l.npy"), [1.0, 0.0, 2.0], [1.0, 0.0, 2.0], fov=110)
+        pcd2, s2 = R.merge_pcd(os.path.join(td, "d.png"), os.path.join(td, "l.npy"), [1.5, 0.25, 1.75], [1.0, 0.0, 2.0], fov=90,
+                               mask_ego=False)
+    vox, lab = R.voxel_filter(pcd.copy(), s, 0.5, [192, 192, 64], [0.0, 0, -10.0])
+    save("merge.npz", img=img, lidar_xyz=lid, lidar_sem=sem, pcd=pcd, sem=s, pcd_nomask=pcd2, sem_nomask=s2, vox=vox, lab=lab)
+
+
 def main():
     R = ref_import.load()
+    golden_merge(R)
     golden_voxel(R)
     golden_range(R)
     golden_bev(R)

@@ -121,3 +121,15 @@ def test_ssc_golden(golden):
         st = O.ssc_stats_from_counts(acc, C)
         assert st["iou"] == float(g[f"c{C}_iou"]) and st["precision"] == float(g[f"c{C}_precision"])
         assert np.allclose(st["iou_ssc"].numpy(), g[f"c{C}_iou_ssc"], rtol=1e-6)
+
+
+def test_merge_pcd_oracle_matches_reference_golden(golden):
+    """N1: the numpy restatement of merge_pcd reproduces the reference's own output (frozen by make_golden.py)."""
+    g = golden("merge.npz")
+    pcd, sem = O.merge_pcd_arrays(g["img"], g["lidar_xyz"], g["lidar_sem"], [1.0, 0.0, 2.0], [1.0, 0.0, 2.0], fov=110)
+    assert pcd.dtype == np.float64 and np.array_equal(pcd, g["pcd"]) and np.array_equal(sem, g["sem"])
+    pcd2, sem2 = O.merge_pcd_arrays(g["img"], g["lidar_xyz"], g["lidar_sem"], [1.5, 0.25, 1.75], [1.0, 0.0, 2.0], fov=90,
+                                    mask_ego=False)
+    assert np.array_equal(pcd2, g["pcd_nomask"]) and np.array_equal(sem2, g["sem_nomask"])
+    v, l = O.voxel_filter_fast(pcd, sem, 0.5, [192, 192, 64], [0.0, 0, -10.0])
+    assert np.array_equal(v, g["vox"]) and np.array_equal(l, g["lab"])

@@ -395,3 +395,31 @@ def test_host_pipeline_packed_sparse_and_range(lib):
             assert np.array_equal(r["range_depth"][f].numpy(), d0)
             assert np.array_equal(r["range_xyz"][f].numpy(), x0)
             assert np.array_equal(r["range_sem"][f].numpy(), s0)
+
+
+# ------------------------------------------------------------------ N1: camera + LiDAR cloud in front of (a)
+def test_merge_pcd_golden_and_full_size_vs_oracle(golden, lib):
+    g = golden("merge.npz")
+    pcd, sem = muvo_b200.merge_pcd_arrays(g["img"], g["lidar_xyz"], g["lidar_sem"], [1.0, 0.0, 2.0], [1.0, 0.0, 2.0], fov=110)
+    assert pcd.dtype == np.float64 and sem.shape == (len(pcd), 1)
+    assert np.array_equal(pcd, g["pcd"]) and np.array_equal(sem, g["sem"])
+    pcd2, sem2 = muvo_b200.merge_pcd_arrays(g["img"], g["lidar_xyz"], g["lidar_sem"], [1.5, 0.25, 1.75], [1.0, 0.0, 2.0], fov=90,
+                                            mask_ego=False)
+    assert np.array_equal(pcd2, g["pcd_nomask"]) and np.array_equal(sem2, g["sem_nomask"])
+    # merged float64 cloud straight into the voxeliser (device tensors, no host round trip) == the reference's chain
+    xyz_d, sem_d = muvo_b200.merge_pcd_device(g["img"], g["lidar_xyz"], g["lidar_sem"], [1.0, 0.0, 2.0], [1.0, 0.0, 2.0])
+    r = sensor_to_grid(xyz_d, sem_d, None, grid=GridSpec(), dense=False, sparse=True)
+    n = int(r["n_occ"][0].item())
+    rows = r["voxel_sparse"][:n].cpu().numpy().view(np.uint16)
+    assert np.array_equal(rows[:, :3], g["vox"]) and np.array_equal(rows[:, 3].astype(np.uint8), g["lab"])
+    # full CARLA image size (600 x 960) + a 60 k LiDAR sweep against the oracle
+    img = synth.carla_depth_image(5100)
+    pts, s = synth.carla_lidar_frame(60000, 5101)
+    lid = pts.copy(); lid[:, 1] *= -1; lid -= np.float32([1, 0, 2])
+    got_p, got_s = muvo_b200.merge_pcd_arrays(img, lid, s, [1.0, 0.0, 2.0], [1.0, 0.0, 2.0])
+    want_p, want_s = O.merge_pcd_arrays(img, lid, s, [1.0, 0.0, 2.0], [1.0, 0.0, 2.0])
+    assert np.array_equal(got_p, want_p) and np.array_equal(got_s, want_s)
+    # empty inputs
+    e_p, e_s = muvo_b200.merge_pcd_arrays(np.zeros((0, 0, 4), np.uint8), np.zeros((0, 3), np.float32), np.zeros((0,), np.uint8),
+                                          [1.0, 0.0, 2.0], [1.0, 0.0, 2.0])
+    assert e_p.shape == (0, 3) and e_s.shape == (0, 1)
