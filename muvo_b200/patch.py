@@ -26,9 +26,12 @@ def patch(verbose: bool = False) -> int:
     m = sys.modules.get("data_preprocessing")
     if m is not None:
         _swap(m, "voxel_filter", points.voxel_filter)
+        _swap(m, "merge_pcd", points.merge_pcd)                   # N1: camera + LiDAR cloud on the device
     m = sys.modules.get("generate_voxels")
     if m is not None:
         _swap(m, "voxel_filter", points.voxel_filter)
+        _swap(m, "merge_pcd", points.merge_pcd)
+        _swap(m, "voxelize_one", points.voxelize_one)             # merge + voxelise without a host round trip
     m = sys.modules.get("muvo.utils.geometry_utils")
     if m is not None and hasattr(m, "PointCloud"):
         _swap(m.PointCloud, "do_range_projection", points.do_range_projection)
