@@ -10,25 +10,22 @@
 // index.  No float atomics, no sort of the point stream, deterministic result:
 //
 //   K1  k_points_tile   : persistent CTAs, each owning a contiguous run of 1024-point tiles that arrive in
-//                         shared memory through a two-stage cp.async.bulk (TMA) + mbarrier pipeline.  Per
-//                         point: float64 voxel id in numpy's operation order (this file is compiled with
-//                         -fmad=false) -> 1-bit-per-voxel frame bitmap (RED.OR); range pixel from an f32
-//                         polynomial atan2 that is PROVABLY on the same side of every bin edge as the float64
-//                         reference formula (points closer than eps to an edge are queued in shared memory and
-//                         finished by the CTA with the exact float64 trigonometry), squared range in float64 ->
-//                         ONE 64-bit atomicMax of (~top32(key) << 32) | ~(index+1) on the pixel word.  That
-//                         packed order equals the exact (depth, index) order unless two points of a pixel
-//                         agree in the top 32 key bits; those (rare) run an exact tie protocol.
-//   K2  k_bitmap_scan   : popcount prefix per 128-bit bitmap chunk -> every occupied voxel gets a dense
-//                         slot id = its rank in output order; n_occ per frame.
-//   K3  k_voxel_tile    : second tile pass (no trigonometry): same packed atomicMax on slot `rank`,
-//                         key = (not roadline, |p mod res|^2), label carried in the low byte.
-//   K4  k_slot_labels   : only for >= 2^24 points per call: winner index -> label byte.
-//   K5  k_emit_*        : bitmap-ordered, fully coalesced write of the dense uint8 grid (zeros included,
-//                         so no memset + scatter; winner slots of a 1024-voxel span are contiguous and are
-//                         read with one coalesced load) and/or the sorted sparse (n,4) list; pixel-ordered
-//                         write of the range image.  Emit kernels put every table entry they consume back
-//                         to 0, so the workspace is clean for the next call.
+//                         shared memory through a two-stage cp.async.bulk (TMA) + mbarrier pipeline.  Per point
+//                         (this file is compiled with -fmad=false, numpy's operation order):
+//                         * voxel id from an exact floor, |p mod res|^2 in float64, ONE 64-bit atomicMax of
+//                           (~top32(key) << 32) | ~(index+1) | label on the voxel's word of a direct table; the first
+//                           claim of a voxel sets its bit in the 1-bit-per-voxel frame bitmap;
+//                         * range pixel from an f32 polynomial atan2 that is PROVABLY on the same side of every
+//                           bin edge as the float64 reference formula (points closer than eps to an edge are
+//                           queued), squared range in float64, the same packed atomicMax on the pixel word.
+//                         The packed order equals the exact (key, index) order unless two competitors agree in the
+//                         top 32 key bits; those (rare) are queued for the exact tie protocol.
+//   K2  k_scan_queue    : finishes the queues (float64 atan2/asin pixels, tie protocol); for the sorted sparse list
+//                         also the bitmap scan: a cluster of 8 CTAs per frame, totals exchanged through DSMEM.
+//   K5  k_emit_*        : bitmap-ordered, fully coalesced write of the dense uint8 grid (zeros included, so no
+//                         memset + scatter; winners fetched cooperatively, 256-bit stores) and/or the sorted sparse
+//                         (n,4) list; pixel-ordered write of the range image.  Emit kernels put every table entry
+//                         they consume back to 0, so the workspace is clean for the next call.
 #include <math.h>
 #include <cooperative_groups.h>
 #include <type_traits>
@@ -38,7 +35,8 @@ namespace cg = cooperative_groups;
 
 namespace muvo {
 
-// debug / tuning knobs (muvo_debug_set_tuning): 0 = CTAs per SM of the tile kernels (0 = default)
+// debug / tuning knobs (muvo_debug_set_tuning): [0] CTAs per SM of the point pass (0 = as many as fit),
+// [1] bit 0 = disable the neighbour filter in front of the voxel atomicMax; the rest is unused
 int g_tuning[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 namespace {
@@ -1185,8 +1183,11 @@ __device__ __forceinline__ void emit_range_body(int64_t vblock, const EmitRangeA
   }
 }
 
+#ifndef MUVO_ER_MINB
+#define MUVO_ER_MINB 1
+#endif
 template <typename T, int NP, int LAYOUT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, MUVO_ER_MINB)
 k_emit_range(EmitRangeArgs<T> a, RangeDev r) { emit_range_body<T, NP, LAYOUT>((int64_t)blockIdx.x, a, r); }
 
 // ---------------------------------------------------------------- test hook: f32 pixel path vs float64 formula
