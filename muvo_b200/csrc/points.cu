@@ -769,6 +769,60 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
           if (d.pgo && d.pold != 0ull && word_top(d.pold) == d.ptop) q[atomicAdd(qn, 1u)] = make_uint2(d.rel, word_idx1(d.pold));
         }
       };
+      if (FAST) {
+        // Two phases.  (1) arithmetic for the thread's 4 points; the operands of their atomics are kept (table offset +
+        // word, ~0 = none).  (2) all 8 atomics are issued back to back and only then are their results looked at: the
+        // round trips to L2 / DRAM overlap each other instead of stalling the thread once per point.
+        uint32_t vbit[kKPL], ppix[kKPL];
+        u64 vword[kKPL], pword[kKPL];
+#pragma unroll
+        for (int k = 0; k < kKPL; ++k) {
+          const T x = sx[3 * k * kTileThreads], y = sx[3 * k * kTileThreads + 1], z = sx[3 * k * kTileThreads + 2];
+          const uint32_t lab = ss[k * kTileThreads];
+          const uint32_t me1 = idx1_0 + k * kTileThreads;
+          vbit[k] = 0xffffffffu; ppix[k] = 0xffffffffu; vword[k] = 0ull; pword[k] = 0ull;
+          if (DO_VOX) {
+            bool in; double dis; uint32_t bit = 0xffffffffu;
+            if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) bit = v.bit; }
+            else { VoxKey v = vox_of<true>((double)x, (double)y, (double)z, g); in = v.in; dis = v.dis; if (in) bit = v.bit; }
+            const uint32_t top = key_top_inv(vox_key(dis, (int)lab != g.road));
+            n_in += in ? 1u : 0u;
+            const bool go = use_filter ? pair_filter<true>(in, bit, 0, top) : in;
+            if (go) { vbit[k] = bit; vword[k] = vox_word(PACKL_T, top, me1, lab); }
+          }
+          if (DO_RANGE) {
+            const PixFast pk = pix_fast(x, y, z, r);
+            if (!pk.ok) ++n_drop;
+            else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, kQExact);
+            else {
+              ppix[k] = (uint32_t)pk.pix;
+              // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
+              pword[k] = pack_word(key_top_inv((u64)__double_as_longlong(pk.s)), me1);
+            }
+          }
+        }
+        u64 vold[kKPL], pold[kKPL];
+#pragma unroll
+        for (int k = 0; k < kKPL; ++k) {
+          vold[k] = 1ull; pold[k] = 0ull;
+          if (DO_VOX && vbit[k] != 0xffffffffu) vold[k] = atomicMax(vtab_f + vbit[k], vword[k]);
+          if (DO_RANGE && ppix[k] != 0xffffffffu) pold[k] = atomicMax(pixtab_f + ppix[k], pword[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kKPL; ++k) {
+          if (DO_VOX) {
+            if (vold[k] == 0ull)                                            // first claim of the voxel marks it occupied
+              atomicOr(bitmap_f + (vbit[k] >> 5), 1u << (vbit[k] & 31));
+            else if (vbit[k] != 0xffffffffu && word_top(vold[k]) == word_top(vword[k]))   // same top-32 class: exact protocol
+              q[atomicAdd(qn, 1u)] = make_uint2((rel_0 + k * kTileThreads) | kQVoxel, vox_word_idx1(PACKL_T, vold[k]));
+          }
+          if (DO_RANGE) {
+            if (ppix[k] != 0xffffffffu && pold[k] != 0ull && word_top(pold[k]) == word_top(pword[k]))
+              q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, word_idx1(pold[k]));
+          }
+        }
+        return;
+      }
       Pending prev{1ull, 0ull, 0u, 0u, 0u, 0u, 0, false, false, false};
 #pragma unroll
       for (int k = 0; k < kKPL; ++k) {
