@@ -423,3 +423,35 @@ def test_merge_pcd_golden_and_full_size_vs_oracle(golden, lib):
     e_p, e_s = muvo_b200.merge_pcd_arrays(np.zeros((0, 0, 4), np.uint8), np.zeros((0, 3), np.float32), np.zeros((0,), np.uint8),
                                           [1.0, 0.0, 2.0], [1.0, 0.0, 2.0])
     assert e_p.shape == (0, 3) and e_s.shape == (0, 1)
+
+
+def test_generate_voxels_cli_on_a_synthetic_run_directory(lib, tmp_path):
+    """N3: the batch voxeliser walks <root>/**/Town*/*/, reads pd_dataframe.pkl and writes voxel/voxel_#########.npy in the
+    format of voxelize_one; every file equals merge_pcd + voxel_filter of the oracle."""
+    import cv2
+    import pandas as pd
+    from muvo_b200 import generate_voxels as gv
+    run = tmp_path / "trainval" / "train" / "Town01" / "0000"
+    (run / "depth_semantic").mkdir(parents=True)
+    (run / "points_semantic").mkdir()
+    rows, inputs = [], []
+    for k in range(3):
+        img = synth.carla_depth_image(5200 + k, h=120, w=200)
+        pts, s = synth.carla_lidar_frame(5000, 5300 + k)
+        lid = pts.copy(); lid[:, 1] *= -1; lid -= np.float32([1, 0, 2])
+        name = f"{k:09d}"
+        cv2.imwrite(str(run / "depth_semantic" / f"depth_semantic_{name}.png"), img)
+        np.save(str(run / "points_semantic" / f"points_semantic_{name}.npy"), {"points_xyz": lid, "ObjTag": s}, allow_pickle=True)
+        rows.append({"depth_semantic_path": f"depth_semantic/depth_semantic_{name}.png",
+                     "points_semantic_path": f"points_semantic/points_semantic_{name}.npy"})
+        inputs.append((img, lid, s))
+    pd.DataFrame(rows).to_pickle(run / "pd_dataframe.pkl")
+    assert gv.main(["--root", str(tmp_path), "--io-threads", "2"]) == 0
+    frame = pd.read_pickle(run / "pd_dataframe.pkl")
+    assert list(frame["voxel_path"]) == [f"voxel/voxel_{k:09d}.npy" for k in range(3)]
+    for k, (img, lid, s) in enumerate(inputs):
+        got = np.load(run / frame["voxel_path"][k])
+        pcd, sem = O.merge_pcd_arrays(img, lid, s, [1.0, 0.0, 2.0], [1.0, 0.0, 2.0], fov=110)
+        v, l = O.voxel_filter_fast(pcd, sem, 0.5, [192, 192, 64], [0 * 0.2, 0, -20 * 0.5])
+        assert got.dtype == np.uint16 and np.array_equal(got, np.concatenate([v, l[:, None].astype(np.uint16)], 1))
+    assert gv.main(["--root", str(tmp_path / "nothing_here")]) == 1
