@@ -87,7 +87,7 @@ struct PointsWs {
   uint32_t* prefix = nullptr;   // [F, gw/4]  exclusive popcount prefix per 128-bit chunk (sparse output only)
   u64* vtab = nullptr;          // [F, G]     packed winner per voxel, addressed by the voxel's bit index (0 = empty)
   u64* pixtab = nullptr;        // [F, H*W]   packed winner per pixel (0 = empty)
-  uint32_t* qcount = nullptr;   // [kMaxChunks, kMaxTileCtas] rare-path queue length per tile CTA (rewritten by every call)
+  uint32_t* qcount = nullptr;   // [kMaxChunks, kMaxTileCtas, 2] (length, frame of the CTA's first point): rare-path queue length per tile CTA (rewritten by every call)
   uint2* queue = nullptr;       // [2P]       rare-path queue, CTA b's segment starts at 2 * (its first point)
   size_t bytes = 0;
 };
@@ -110,7 +110,7 @@ static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const Muv
   if (r) {
     w.pixtab = (u64*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 8, 256);
   }
-  w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxChunks * kMaxTileCtas * 4, 256);
+  w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxChunks * kMaxTileCtas * 8, 256);
   w.queue = (uint2*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 16, 256);
   w.bytes = o;
   return w;
@@ -621,14 +621,14 @@ struct QueueArgs {
 template <typename T>
 __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const GridDev& g, const RangeDev& r) {
   if (cta >= a.n_tile_ctas) return;
-  const uint32_t n = a.qcount[cta];
+  const uint32_t n = a.qcount[2 * cta];
   if (n == 0u) return;   // CTA-uniform
   int t0, t1;
   cta_tile_range(a.P0, a.P, a.n_tile_ctas, cta, &t0, &t1);
   const int64_t blk_first = (int64_t)t0 * kTile;
   const uint2* q = a.queue + 2 * (blk_first > a.P0 ? blk_first : a.P0);
   unsigned n_drop = 0, n_nw = 0, n_nh = 0;
-  const int f_first = find_frame(a.off, a.F, blk_first > a.P0 ? blk_first : a.P0);      // a CTA's points span few frames: walk from its first one
+  const int f_first = (int)a.qcount[2 * cta + 1];              // a CTA's points span few frames: walk from its first one
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     const uint2 ent = q[e];
     const int64_t i = blk_first + (int64_t)(ent.x & ~kQVoxel);
@@ -727,9 +727,10 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
   if (n_occ_zero && blockIdx.x == 0) for (int f = f_lo + threadIdx.x; f < f_hi; f += kTileThreads) n_occ_zero[f] = 0;
   Tiles<T> tl;
   if (!tl.init(smem, xyz, sem, off, F, P0, P, vec_ok)) {
-    if (threadIdx.x == 0) qcount[blockIdx.x] = 0u;
+    if (threadIdx.x == 0) qcount[2 * blockIdx.x] = 0u;
     return;
   }
+  const int f_first = tl.f;                             // frame of this CTA's first point (the queue kernel starts its walks here)
   uint32_t* qn = reinterpret_cast<uint32_t*>(smem + L::off_qn);
   const int tid = threadIdx.x;
   const int64_t blk_first = (int64_t)tl.t0 * kTile;
@@ -877,7 +878,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
     }
     __syncthreads();                         // tile buffer free for the copy issued by the next next()
   }
-  if (tid == 0) qcount[blockIdx.x] = *qn;
+  if (tid == 0) { qcount[2 * blockIdx.x] = *qn; qcount[2 * blockIdx.x + 1] = (uint32_t)f_first; }
   if (diag) {
     if (DO_RANGE) diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
     if (DO_VOX) diag_add(diag, MUVO_DIAG_IN_GRID, n_in);
@@ -1380,7 +1381,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   int chunk_ctas[kMaxChunks] = {0};
   auto run_pass = [&](int chunk, int f0, int f1, int64_t p0, int64_t p1, cudaStream_t cs) -> int {
     int n_tile_ctas = 0;
-    uint32_t* qcount = w.qcount + (size_t)chunk * kMaxTileCtas;
+    uint32_t* qcount = w.qcount + (size_t)chunk * kMaxTileCtas * 2;
     if (p1 > p0) {
       const int64_t n_tiles = ceil_div64(p1, kTile) - p0 / kTile;
       int64_t grid = (int64_t)sms * k1_per_sm;
@@ -1400,7 +1401,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   };
   auto run_emit = [&](int chunk, int f0, int f1, int64_t p0, int64_t p1, cudaStream_t cs) -> int {
     const int n_tile_ctas = chunk_ctas[chunk];
-    uint32_t* qcount = w.qcount + (size_t)chunk * kMaxTileCtas;
+    uint32_t* qcount = w.qcount + (size_t)chunk * kMaxTileCtas * 2;
     // K2: bitmap scan (when ranks are needed) + the rare-path queues, one launch
     {
       const int scan_frames = need_scan ? F : 0;                 // (the scan path is never chunked)

@@ -70,9 +70,9 @@ def test_workspace_size_and_argument_errors(lib):
     n = C.c_size_t(0)
     assert lib.muvo_points_workspace_bytes(100000, 1, C.byref(g), C.byref(r), C.byref(n)) == 0
     # bitmap (G/8) + chunk prefix (G/32) + voxel winner table (8 B/voxel) + pixel table (8 B/px)
-    # + queue length slots (16 KiB) + rare-path queue (16 B/pt)
+    # + queue length / first-frame slots (32 KiB) + rare-path queue (16 B/pt)
     G = 192 * 192 * 64
-    need = G // 8 + G // 32 + 8 * G + 8 * 64 * 1024 + 16384 + 16 * 100000
+    need = G // 8 + G // 32 + 8 * G + 8 * 64 * 1024 + 32768 + 16 * 100000
     assert need <= n.value < need + 4096
     assert lib.muvo_points_workspace_bytes(-1, 1, C.byref(g), C.byref(r), C.byref(n)) == -2
     assert lib.muvo_points_workspace_bytes(10, 1, C.byref(g), C.byref(r), None) == -1
