@@ -124,6 +124,15 @@ MUVO_API int muvo_merge_pcd(const uint8_t* img_bgra, int32_t H, int32_t W, doubl
                    const double* lidar_pos_h, const double* ego_box_h, double* xyz_out, uint8_t* sem_out,
                    int64_t* n_out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- N1: label pyramids behind (a)/(b) --------------------------------------------
+ * Replaces the LIDAR_RE / LIDAR_SEG / VOXEL_SEG blocks of PreProcess.forward, muvo/models/preprocess.py:151-186:
+ * rv1 = range_xyzd / scale, rv2 / rv4 = nearest-neighbour halvings (H/2 x W/2, H/4 x W/4), seg2 / seg4 the same for
+ * range_sem, vox2 / vox4 for the voxel grid (X/2 x Y/2 x Z/2, /4).  Index rule = PyTorch `nearest`.  Either input family
+ * may be NULL (then its outputs are ignored).                                             */
+MUVO_API int muvo_label_pyramids(const float* range_xyzd, const uint8_t* range_sem, const uint8_t* voxel, int32_t F, int32_t H,
+                        int32_t W, int32_t X, int32_t Y, int32_t Z, float scale, float* rv1, float* rv2, float* rv4,
+                        uint8_t* seg2, uint8_t* seg4, uint8_t* vox2, uint8_t* vox4, void* stream);
+
 /* ---- (a) voxelisation ------------------------------------------------------------
  * Replaces voxel_filter(), data/data_preprocessing.py:172-228, batched over frames, and
  * (dense_out) the densify step of muvo/data/dataset.py:317-327.

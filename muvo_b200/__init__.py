@@ -12,7 +12,7 @@ there is no CPU or PyTorch fallback.  Build with ``python -m muvo_b200.build``.
 """
 from ._lib import MuvoError, load as load_library  # noqa: F401
 from .points import (GridSpec, RangeSpec, PointCloud, sensor_to_grid, voxel_filter, voxelize_one_array,  # noqa: F401
-                     merge_pcd, merge_pcd_arrays, merge_pcd_device, voxelize_one)
+                     merge_pcd, merge_pcd_arrays, merge_pcd_device, voxelize_one, label_pyramids)
 from .metrics import SSCMetrics, ssc_counts, ssc_counts_from_logits, all_reduce_counts  # noqa: F401
 from .frustum_pooling import (FrustumPooling, QuickCumsum, VoxelsSumming, cumsum_trick, quick_cumsum, gen_dx_bx,  # noqa: F401
                               bev_pool, lift_splat, bev_params_to_intrinsics, intrinsics_inverse)

@@ -243,6 +243,48 @@ def voxel_filter(pcd, sem, voxel_resolution, voxel_size, offset):
 EGO_VEHICLE_DIMENSION = [4.902, 2.128, 1.511]          # data/data_preprocessing.py:5
 
 
+def label_pyramids(range_xyzd=None, range_sem=None, voxel=None, scale: float = 50.0) -> dict:
+    """The range-view / voxel label pyramids of ``PreProcess.forward`` (muvo/models/preprocess.py:151-186) for a batch
+    of frames: ``range_xyzd (F,4,H,W) f32`` -> ``range_view_label_1`` (= ``/ scale``), ``_2``, ``_4``; ``range_sem (F,H,W)
+    u8`` -> ``range_view_seg_label_2/_4``; ``voxel (F,X,Y,Z) u8`` -> ``voxel_label_2/_4``.  Device tensors in / out."""
+    lib = _lib.load()
+    ref = range_xyzd if range_xyzd is not None else voxel
+    if ref is None:
+        raise ValueError("nothing to do")
+    _lib.require_cuda(ref)
+    dev = ref.device
+    out = {}
+    F = int(ref.shape[0])
+    H = W = X = Y = Z = 0
+    rv1 = rv2 = rv4 = s2 = s4 = v2 = v4 = None
+    if range_xyzd is not None:
+        range_xyzd = range_xyzd.contiguous().float()
+        _, four, H, W = range_xyzd.shape
+        if four != 4:
+            raise ValueError("range_xyzd must be (F, 4, H, W)")
+        rv1 = torch.empty_like(range_xyzd)
+        rv2 = torch.empty((F, 4, H // 2, W // 2), dtype=torch.float32, device=dev)
+        rv4 = torch.empty((F, 4, H // 4, W // 4), dtype=torch.float32, device=dev)
+        out.update(range_view_label_1=rv1, range_view_label_2=rv2, range_view_label_4=rv4)
+        if range_sem is not None:
+            range_sem = range_sem.contiguous()
+            s2 = torch.empty((F, H // 2, W // 2), dtype=torch.uint8, device=dev)
+            s4 = torch.empty((F, H // 4, W // 4), dtype=torch.uint8, device=dev)
+            out.update(range_view_seg_label_1=range_sem, range_view_seg_label_2=s2, range_view_seg_label_4=s4)
+    if voxel is not None:
+        voxel = voxel.contiguous()
+        _, X, Y, Z = voxel.shape
+        v2 = torch.empty((F, X // 2, Y // 2, Z // 2), dtype=torch.uint8, device=dev)
+        v4 = torch.empty((F, X // 4, Y // 4, Z // 4), dtype=torch.uint8, device=dev)
+        out.update(voxel_label_1=voxel, voxel_label_2=v2, voxel_label_4=v4)
+    p = _lib.ptr
+    with torch.cuda.device(dev):
+        rc = lib.muvo_label_pyramids(p(range_xyzd), p(range_sem) if range_xyzd is not None else None, p(voxel), F, H, W, X, Y, Z,
+                                     float(scale), p(rv1), p(rv2), p(rv4), p(s2), p(s4), p(v2), p(v4), _lib.current_stream(dev))
+    _lib.check(rc, "muvo_label_pyramids")
+    return out
+
+
 def merge_pcd_device(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, mask_ego=True, device=None):
     """Camera + LiDAR cloud of ``merge_pcd`` (data/data_preprocessing.py:125-139) built on the GPU.
 

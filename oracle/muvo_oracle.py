@@ -28,7 +28,7 @@ __all__ = [
     "label_remap_table", "range_projection", "range_projection_indices", "pack_range_view",
     "bev_intrinsics", "gen_dx_bx", "frustum_grid", "frustum_geometry", "bev_cell_ids",
     "cumsum_trick", "quick_cumsum_backward", "voxel_pooling_cumsum", "voxel_pooling_exact",
-    "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
+    "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "label_pyramids", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
     "ssc_stats_from_counts",
 ]
 
@@ -181,6 +181,35 @@ def merge_pcd_arrays(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, 
         ego = ((box[0] < pcd) & (pcd < box[1])).all(axis=1)                      # :136
         pcd, sem = pcd[~ego], sem[~ego]
     return pcd, sem
+
+
+def _nearest_idx(n_in, n_out):
+    """PyTorch `nearest` source indices (torchvision resize NEAREST / F.interpolate): min(floor(dst * float32(in/out)), in-1)."""
+    scale = np.float32(n_in) / np.float32(n_out)
+    return np.minimum(np.floor(np.arange(n_out, dtype=np.float32) * scale).astype(np.int64), n_in - 1)
+
+
+def label_pyramids(range_xyzd=None, range_sem=None, voxel=None, scale=50.0):
+    """LIDAR_RE / LIDAR_SEG / VOXEL_SEG blocks of ``PreProcess.forward`` (muvo/models/preprocess.py:151-186) on numpy arrays
+    with a leading frame axis: level 1 (= input, range view divided by ``scale`` in float32), levels 2 and 4 by repeated
+    nearest-neighbour halving."""
+    out = {}
+
+    def halve(a, axes):
+        for ax in axes:
+            a = np.take(a, _nearest_idx(a.shape[ax], a.shape[ax] // 2), axis=ax)
+        return a
+    if range_xyzd is not None:
+        l1 = (np.asarray(range_xyzd, dtype=np.float32) / np.float32(scale)).astype(np.float32)
+        l2 = halve(l1, (2, 3)); l4 = halve(l2, (2, 3))
+        out.update(range_view_label_1=l1, range_view_label_2=l2, range_view_label_4=l4)
+    if range_sem is not None:
+        s2 = halve(np.asarray(range_sem), (1, 2)); s4 = halve(s2, (1, 2))
+        out.update(range_view_seg_label_1=np.asarray(range_sem), range_view_seg_label_2=s2, range_view_seg_label_4=s4)
+    if voxel is not None:
+        v2 = halve(np.asarray(voxel), (1, 2, 3)); v4 = halve(v2, (1, 2, 3))
+        out.update(voxel_label_1=np.asarray(voxel), voxel_label_2=v2, voxel_label_4=v4)
+    return out
 
 
 # --------------------------------------------------------------------------- (b)

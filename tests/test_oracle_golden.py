@@ -133,3 +133,25 @@ def test_merge_pcd_oracle_matches_reference_golden(golden):
     assert np.array_equal(pcd2, g["pcd_nomask"]) and np.array_equal(sem2, g["sem_nomask"])
     v, l = O.voxel_filter_fast(pcd, sem, 0.5, [192, 192, 64], [0.0, 0, -10.0])
     assert np.array_equal(v, g["vox"]) and np.array_equal(l, g["lab"])
+
+
+def test_label_pyramids_oracle_matches_torch_nearest():
+    """N1: the pyramid restatement equals what PreProcess computes with torchvision resize NEAREST / F.interpolate
+    (muvo/models/preprocess.py:151-186), also for sizes that are not multiples of 4."""
+    import torch.nn.functional as Fn
+    rng = np.random.default_rng(3)
+    for (H, W, X, Y, Z) in ((64, 1024, 192, 192, 64), (10, 22, 13, 9, 6)):
+        xyzd = rng.normal(0, 30, (3, 4, H, W)).astype(np.float32)
+        sem = rng.integers(0, 23, (3, H, W)).astype(np.uint8)
+        vox = rng.integers(0, 3, (2, X, Y, Z)).astype(np.uint8)
+        got = O.label_pyramids(xyzd, sem, vox, scale=50.0)
+        l1 = torch.from_numpy(xyzd).float() / 50.0
+        l2 = Fn.interpolate(l1, (H // 2, W // 2), mode="nearest"); l4 = Fn.interpolate(l2, (H // 4, W // 4), mode="nearest")
+        assert np.array_equal(got["range_view_label_1"], l1.numpy()) and np.array_equal(got["range_view_label_2"], l2.numpy())
+        assert np.array_equal(got["range_view_label_4"], l4.numpy())
+        s1 = torch.from_numpy(sem)[:, None]
+        s2 = Fn.interpolate(s1, (H // 2, W // 2), mode="nearest"); s4 = Fn.interpolate(s2, (H // 4, W // 4), mode="nearest")
+        assert np.array_equal(got["range_view_seg_label_2"], s2[:, 0].numpy()) and np.array_equal(got["range_view_seg_label_4"], s4[:, 0].numpy())
+        v1 = torch.from_numpy(vox)[:, None]
+        v2 = Fn.interpolate(v1, (X // 2, Y // 2, Z // 2), mode="nearest"); v4 = Fn.interpolate(v2, (X // 4, Y // 4, Z // 4), mode="nearest")
+        assert np.array_equal(got["voxel_label_2"], v2[:, 0].numpy()) and np.array_equal(got["voxel_label_4"], v4[:, 0].numpy())

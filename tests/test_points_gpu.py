@@ -455,3 +455,22 @@ def test_generate_voxels_cli_on_a_synthetic_run_directory(lib, tmp_path):
         v, l = O.voxel_filter_fast(pcd, sem, 0.5, [192, 192, 64], [0 * 0.2, 0, -20 * 0.5])
         assert got.dtype == np.uint16 and np.array_equal(got, np.concatenate([v, l[:, None].astype(np.uint16)], 1))
     assert gv.main(["--root", str(tmp_path / "nothing_here")]) == 1
+
+
+def test_label_pyramids_match_oracle(lib):
+    """N1: range-view / voxel label pyramids behind the point kernels (PreProcess.forward, preprocess.py:151-186), bit-exact."""
+    pts, sem, off = _batch(3, 20000, 30000, 2600)
+    r = sensor_to_grid(torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev()), off, grid=GridSpec(),
+                       range_spec=RangeSpec(lidar_position=tuple(LIDAR)), remap=torch.from_numpy(synth.label_remap256()), layout="xyzd")
+    got = muvo_b200.label_pyramids(r["range_xyzd"], r["range_sem"], r["voxel"], scale=50.0)
+    want = O.label_pyramids(r["range_xyzd"].cpu().numpy(), r["range_sem"].cpu().numpy(), r["voxel"].cpu().numpy(), scale=50.0)
+    assert set(got) == set(want)
+    for k in want:
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+    rng = np.random.default_rng(4)                      # sizes that are not multiples of 4
+    xyzd = torch.from_numpy(rng.normal(0, 30, (2, 4, 10, 22)).astype(np.float32)).to(dev())
+    vox = torch.from_numpy(rng.integers(0, 3, (2, 13, 9, 6)).astype(np.uint8)).to(dev())
+    got = muvo_b200.label_pyramids(xyzd, None, vox, scale=50.0)
+    want = O.label_pyramids(xyzd.cpu().numpy(), None, vox.cpu().numpy(), scale=50.0)
+    for k in want:
+        assert np.array_equal(got[k].cpu().numpy(), want[k]), k
