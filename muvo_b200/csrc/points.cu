@@ -700,6 +700,17 @@ k_scan_queue(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix,
 }
 
 // ---------------------------------------------------------------- K1: point pass
+// The tables live in global memory; explicit .global atomics keep the compiler from emitting generic-address atomics
+// (address-space test + a shared-memory CAS loop per atomic) once a pointer has been through an opaque asm.
+__device__ __forceinline__ u64 atom_max_global(u64* p, u64 v) {
+  u64 old;
+  asm volatile("atom.global.max.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void red_or_global(uint32_t* p, uint32_t v) {
+  asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Scan-ordered clouds put runs of consecutive points (= adjacent lanes) into one voxel.  A lane whose neighbour in
 // the same voxel holds a strictly better top-32 key class can never win the voxel: it skips its atomicMax.
 template <bool ONE_FRAME>
@@ -762,7 +773,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
       auto settle = [&](const Pending& d) {
         if (DO_VOX) {
           if (d.vold == 0ull)                                               // first claim of the voxel marks it occupied
-            atomicOr((FAST ? bitmap_f : bitmap + (size_t)d.fk * g.gw) + (d.bit >> 5), 1u << (d.bit & 31));
+            red_or_global((FAST ? bitmap_f : bitmap + (size_t)d.fk * g.gw) + (d.bit >> 5), 1u << (d.bit & 31));
           else if (d.vgo && word_top(d.vold) == d.vtop)                     // same top-32 class: exact protocol
             q[atomicAdd(qn, 1u)] = make_uint2(d.rel | kQVoxel, vox_word_idx1(d.packl, d.vold));
         }
@@ -806,14 +817,14 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
 #pragma unroll
         for (int k = 0; k < kKPL; ++k) {
           vold[k] = 1ull; pold[k] = 0ull;
-          if (DO_VOX && vbit[k] != 0xffffffffu) vold[k] = atomicMax(vtab_f + vbit[k], vword[k]);
-          if (DO_RANGE && ppix[k] != 0xffffffffu) pold[k] = atomicMax(pixtab_f + ppix[k], pword[k]);
+          if (DO_VOX && vbit[k] != 0xffffffffu) vold[k] = atom_max_global(vtab_f + vbit[k], vword[k]);
+          if (DO_RANGE && ppix[k] != 0xffffffffu) pold[k] = atom_max_global(pixtab_f + ppix[k], pword[k]);
         }
 #pragma unroll
         for (int k = 0; k < kKPL; ++k) {
           if (DO_VOX) {
             if (vold[k] == 0ull)                                            // first claim of the voxel marks it occupied
-              atomicOr(bitmap_f + (vbit[k] >> 5), 1u << (vbit[k] & 31));
+              red_or_global(bitmap_f + (vbit[k] >> 5), 1u << (vbit[k] & 31));
             else if (vbit[k] != 0xffffffffu && word_top(vold[k]) == word_top(vword[k]))   // same top-32 class: exact protocol
               q[atomicAdd(qn, 1u)] = make_uint2((rel_0 + k * kTileThreads) | kQVoxel, vox_word_idx1(PACKL_T, vold[k]));
           }
@@ -853,7 +864,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
           n_in += in ? 1u : 0u;
           cur.vgo = use_filter ? pair_filter<FAST>(in, cur.bit, fk, top) : in;
           cur.vtop = top;
-          if (cur.vgo) cur.vold = atomicMax((FAST ? vtab_f : vtab + (size_t)fk * g.G) + cur.bit, vox_word(packl, top, me1, lab));
+          if (cur.vgo) cur.vold = atom_max_global((FAST ? vtab_f : vtab + (size_t)fk * g.G) + cur.bit, vox_word(packl, top, me1, lab));
         }
         if (DO_RANGE && valid) {
           const PixFast pk = pix_fast(x, y, z, r);
@@ -863,7 +874,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
             cur.pgo = true;
             // s > 0: its bit pattern orders like the value, and like the depth sqrt(s)
             cur.ptop = key_top_inv((u64)__double_as_longlong(pk.s));
-            cur.pold = atomicMax((FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix, pack_word(cur.ptop, me1));
+            cur.pold = atom_max_global((FAST ? pixtab_f : pixtab + (size_t)fk * HW) + pk.pix, pack_word(cur.ptop, me1));
           }
         }
         if (k > 0) settle(prev);
