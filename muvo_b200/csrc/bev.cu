@@ -242,7 +242,7 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
 // (lane-strided partials + fixed xor tree -> deterministic).  Frames with more kept points than fit in shared
 // memory are processed in windows of whole cells.
 constexpr int kRowThreads = 1024;
-constexpr int kRowCap = 54 * 1024;   // floats of staging (216 KB)
+constexpr int kRowCap = 52 * 1024;   // floats of staging (208 KB)
 constexpr int kBigCell = 64;         // cells above this many points are summed by the whole warp
 template <typename T>
 __global__ void __launch_bounds__(kRowThreads, 1)
@@ -250,6 +250,8 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
             const uint32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted, int B, int64_t n_pts, int C,
             int n_cells, float* __restrict__ out) {
   extern __shared__ float buf[];
+  __shared__ int n_big;
+  uint16_t* big_list = reinterpret_cast<uint16_t*>(buf + kRowCap);   // [n_cells] cells of the current window with > kBigCell points
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x / C, c = blockIdx.x % C;
   const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
@@ -287,9 +289,12 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
         }
       }
       __syncthreads();
-      // Segment sums: one THREAD per cell for the common small cells (sequential, ascending point order), the
-      // warp cooperates (lane-strided partials + fixed xor tree) only on cells above kBigCell points.  A warp
-      // step covers 32 consecutive cells -> one coalesced 128-byte store.
+      // Segment sums: one THREAD per cell for the common small cells (sequential, ascending point order); cells above
+      // kBigCell points (they are neighbours: the cells next to the camera) are collected and then dealt round-robin to
+      // ALL warps of the CTA (lane-strided partials + fixed xor tree), instead of leaving them to the one warp that
+      // owns their index range.  A warp step of the first pass covers 32 consecutive cells -> one coalesced store.
+      if (tid == 0) n_big = 0;
+      __syncthreads();
       for (int cb = c0 + warp * 32; cb < c1; cb += (kRowThreads / 32) * 32) {
         const int cell = cb + lane;
         uint32_t s0 = 0, s1 = 0;
@@ -297,18 +302,18 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
         const bool big = (s1 - s0) > (uint32_t)kBigCell;
         float acc = 0.f;
         if (!big) for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
-        unsigned todo = __ballot_sync(0xffffffffu, big);
-        while (todo) {
-          const int src = __ffs(todo) - 1;
-          todo &= todo - 1;
-          const uint32_t b0 = __shfl_sync(0xffffffffu, s0, src), b1 = __shfl_sync(0xffffffffu, s1, src);
-          float part = 0.f;
-          for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
+        else big_list[atomicAdd(&n_big, 1)] = (uint16_t)(cell - c0);
+        if (cell < c1 && !big) o[cell] = acc;
+      }
+      __syncthreads();
+      for (int i = warp; i < n_big; i += kRowThreads / 32) {
+        const int cell = c0 + (int)big_list[i];
+        const uint32_t b0 = cs[cell] - w0, b1 = cs[cell + 1] - w0;
+        float part = 0.f;
+        for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
 #pragma unroll
-          for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
-          if (lane == src) acc = part;
-        }
-        if (cell < c1) o[cell] = acc;
+        for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+        if (lane == 0) o[cell] = part;
       }
       __syncthreads();
     } else {
@@ -715,7 +720,8 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
                                                              w.chunk_kept, w.kp, w.dest);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
   if (sp == 1) {
-    const size_t rsmem = (size_t)kRowCap * sizeof(float);
+    const size_t rsmem = (size_t)kRowCap * sizeof(float) + (size_t)n_cells * 2 + 16;
+    if (n_cells > 65535 || rsmem > 227 * 1024) return MUVO_E_SHAPE;
     cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
     if (e != cudaSuccess) return (int)e;
     k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.kp, w.dest, w.cell_start, w.sorted, B, n_pts,
