@@ -380,6 +380,19 @@ def other_stages(device, rank, world, hbm_peak, args):
     res["ssc_counts"] = {"ms": ms_d, "algorithmic_GBps": bytes_d / ms_d / 1e6, "frac": bytes_d / ms_d / 1e6 / hbm_peak,
                          "voxels_per_s": tp.numel() * world / (ms_d * 1e-3), "frames_per_rank": 16,
                          "allreduce": "nccl int64[9]" if world > 1 else "none (1 rank)"}
+    # N4: SemScalLoss + GeoScalLoss on the voxel logits of the same 16 frames (C = 2, fp32), forward and backward
+    from muvo_b200.losses import scal_losses
+    gen = torch.Generator(device=device).manual_seed(4100 + rank)
+    logits = torch.randn((1, 16, 2, 192, 192, 64), generator=gen, device=device).requires_grad_(True)
+    tl = tt.view(1, 16, 192, 192, 64)
+    ms_sf = timed(lambda: scal_losses(logits.detach(), tl), steps)
+    sem, geo = scal_losses(logits, tl)
+    ms_sb = timed(lambda: torch.autograd.grad(sem + geo, logits, retain_graph=True), steps)
+    bytes_sf = tl.numel() * (2 * 4 + 1)
+    bytes_sb = tl.numel() * (4 * 4 + 1)
+    res["scal_losses_fwd"] = {"ms": ms_sf, "algorithmic_GBps": bytes_sf / ms_sf / 1e6, "frac": bytes_sf / ms_sf / 1e6 / hbm_peak,
+                              "note": "N4: both losses from one pass over the logits (losses.py:191-287), includes the scalar epilogue"}
+    res["scal_losses_bwd"] = {"ms": ms_sb, "algorithmic_GBps": bytes_sb / ms_sb / 1e6, "frac": bytes_sb / ms_sb / 1e6 / hbm_peak}
     return res
 
 

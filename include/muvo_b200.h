@@ -229,6 +229,26 @@ MUVO_API int muvo_ssc_counts_from_logits(const void* logits, int32_t logits_dtyp
                                 int32_t n_classes, int64_t voxels_per_frame, int32_t ignore255,
                                 int64_t* counts_out, void* stream);
 
+/* ---- next row N4: SemScalLoss / GeoScalLoss reductions -------------------------------------
+ * Replaces the softmax + per-class masked reductions of SemScalLoss.forward / GeoScalLoss.forward,
+ * muvo/losses.py:199-251 and :259-287 (called from trainer.py:375-382).  Both losses are functions of
+ *   sums_out[3C+1] float64 = sum_p[C] (sum of softmax prob. of class i over valid voxels),
+ *                            nom[C]   (same, restricted to target == i), cnt[C] (#valid voxels with target == i), n_valid
+ * where valid = target != ignore_index (pass -1 for "no ignore").  logits [F, C, S] f32/f16/bf16 contiguous (softmax in
+ * fp32 as under autocast), target [F, S] uint8, n_classes <= 32.  sums_out is OVERWRITTEN; the result is deterministic.
+ * losses_out[2 + 4C] float64 (or NULL) additionally receives SemScalLoss, GeoScalLoss and their derivatives
+ * d SemScal / d(sum_p[C], nom[C]), d GeoScal / d(sum_p[C], nom[C]), evaluated with the reference's conditions
+ * (class skipped when absent, term skipped when outside [0,1], log clamped at -100; NaN where the reference raises).
+ * muvo_scal_sums_bwd writes grad_logits [F, C, S] (logits' dtype, fully written) from grad_sums[2C] float32 =
+ * d loss / d sum_p[C], d loss / d nom[C] (device pointer; the scalar algebra between the two calls is the caller's).   */
+MUVO_API int muvo_scal_workspace_bytes(int32_t n_classes, size_t* bytes_out_h);
+MUVO_API int muvo_scal_sums_fwd(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames,
+                                int32_t n_classes, int64_t voxels_per_frame, int32_t ignore_index, double* sums_out,
+                                double* losses_out, void* ws, size_t ws_bytes, void* stream);
+MUVO_API int muvo_scal_sums_bwd(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames,
+                                int32_t n_classes, int64_t voxels_per_frame, int32_t ignore_index, const float* grad_sums,
+                                void* grad_logits, void* stream);
+
 /* ---- test / tuning hooks (not part of the drop-in surface) ------------------------------
  * muvo_debug_pixel_check: runs the f32 pixel path of the range projection next to the float64 formula of
  * geometry_utils.py:180-200 on n_points float32 ego-frame points and ACCUMULATES into counts_out[4] (device, int64):

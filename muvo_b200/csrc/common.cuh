@@ -47,19 +47,19 @@ __host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { ret
 // first-to-evict in L2 so that the small L2-resident tables survive next to them.
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* p) {
   uint32_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void st_stream_u4(uint4* p, uint4 v) {

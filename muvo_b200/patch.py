@@ -51,6 +51,13 @@ def patch(verbose: bool = False) -> int:
     m = sys.modules.get("muvo.trainer")
     if m is not None:
         _swap(m, "SSCMetrics", metrics.SSCMetrics)
+    from . import losses                                          # N4: SemScalLoss / GeoScalLoss reductions
+    for mod in ("muvo.losses", "muvo.trainer"):
+        m = sys.modules.get(mod)
+        if m is not None:
+            for name in ("SemScalLoss", "GeoScalLoss"):
+                if hasattr(m, name):
+                    _swap(m, name, getattr(losses, name))
     if verbose:
         for obj, name, _ in _saved[n0:]:
             print(f"muvo_b200.patch: {getattr(obj, '__name__', obj)}.{name}")

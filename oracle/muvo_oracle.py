@@ -29,7 +29,7 @@ __all__ = [
     "bev_intrinsics", "gen_dx_bx", "frustum_grid", "frustum_geometry", "bev_cell_ids",
     "cumsum_trick", "quick_cumsum_backward", "voxel_pooling_cumsum", "voxel_pooling_exact",
     "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "label_pyramids", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
-    "ssc_stats_from_counts",
+    "ssc_stats_from_counts", "sem_scal_loss", "geo_scal_loss", "scal_sums",
 ]
 
 
@@ -497,6 +497,84 @@ def ssc_stats_from_counts(counts, n_classes):
     iou_ssc = tps / (tps + fps + fns + 1e-5)
     return {"precision": precision, "recall": recall, "iou": iou, "iou_ssc": iou_ssc,
             "iou_ssc_mean": torch.mean(iou_ssc[1:])}
+
+
+# ---------------------------------------------------------------------------------------------
+# N4: SemScalLoss / GeoScalLoss (muvo/losses.py:191-287), float64 restatement
+# ---------------------------------------------------------------------------------------------
+def _softmax64(prediction):
+    """F.softmax(prediction, dim=1) (losses.py:205, :268) of float32 logits, evaluated in float64."""
+    x = np.asarray(prediction, dtype=np.float64)
+    x = x - x.max(axis=1, keepdims=True)
+    e = np.exp(x)
+    return e / e.sum(axis=1, keepdims=True)
+
+
+def _bce_to_one(x):
+    """F.binary_cross_entropy(x, ones) (losses.py:230-249, :284-286): -log(x) with the log clamped at -100."""
+    with np.errstate(divide="ignore"):
+        return -max(np.log(x), -100.0)
+
+
+def sem_scal_loss(prediction, target, ignore_index=255):
+    """SemScalLoss.forward, losses.py:199-251.  prediction (b,s,c,x,y,z) logits, target (b,s,x,y,z) labels."""
+    b, s, c = prediction.shape[:3]
+    p_all = _softmax64(np.asarray(prediction).reshape((b * s, c) + tuple(prediction.shape[3:])))
+    tgt = np.asarray(target).reshape((b * s,) + tuple(prediction.shape[3:]))
+    mask = tgt != ignore_index                                            # :208
+    loss, count = 0.0, 0.0
+    for i in range(c):                                                    # :210
+        p = p_all[:, i][mask]                                             # :213-217
+        t = (tgt[mask] == i).astype(np.float64)                           # :220-221
+        if t.sum() > 0:                                                   # :224
+            count += 1.0
+            nominator = (p * t).sum()
+            loss_class = 0.0
+            if p.sum() > 0:                                               # :229
+                precision = nominator / p.sum()
+                if 0 <= precision <= 1:
+                    loss_class += _bce_to_one(precision)
+            recall = nominator / t.sum()                                  # :236-237
+            if 0 <= recall <= 1:
+                loss_class += _bce_to_one(recall)
+            if (1 - t).sum() > 0:                                         # :243
+                specificity = ((1 - p) * (1 - t)).sum() / (1 - t).sum()
+                if 0 <= specificity <= 1:
+                    loss_class += _bce_to_one(specificity)
+            loss += loss_class
+    return loss / count                                                   # :251 (ZeroDivisionError when no class is present)
+
+
+def geo_scal_loss(prediction, target, ignore_index=255):
+    """GeoScalLoss.forward, losses.py:259-287."""
+    b, s, c = prediction.shape[:3]
+    p_all = _softmax64(np.asarray(prediction).reshape((b * s, c) + tuple(prediction.shape[3:])))
+    tgt = np.asarray(target).reshape((b * s,) + tuple(prediction.shape[3:]))
+    mask = tgt != ignore_index                                            # :275
+    empty = p_all[:, 0][mask]                                             # :271, :279
+    nonempty = 1.0 - empty
+    nt = (tgt != 0)[mask].astype(np.float64)                              # :276-277
+    inter = (nt * nonempty).sum()                                         # :281
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = inter / nonempty.sum()
+        recall = inter / nt.sum()
+        spec = ((1 - nt) * empty).sum() / (1 - nt).sum()
+    return _bce_to_one(precision) + _bce_to_one(recall) + _bce_to_one(spec)
+
+
+def scal_sums(prediction, target, ignore_index=255):
+    """The 3C+1 scalars both losses are functions of: sum_p[C], nom[C], cnt[C], n_valid (float64)."""
+    b, s, c = prediction.shape[:3]
+    p_all = _softmax64(np.asarray(prediction).reshape((b * s, c) + tuple(prediction.shape[3:])))
+    tgt = np.asarray(target).reshape((b * s,) + tuple(prediction.shape[3:]))
+    mask = tgt != ignore_index
+    out = np.zeros(3 * c + 1)
+    for i in range(c):
+        p = p_all[:, i][mask]
+        hit = tgt[mask] == i
+        out[i], out[c + i], out[2 * c + i] = p.sum(), p[hit].sum(), hit.sum()
+    out[3 * c] = mask.sum()
+    return out
 
 
 def _self_check():  # pragma: no cover - quick sanity when run directly

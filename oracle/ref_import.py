@@ -38,6 +38,7 @@ def load() -> types.SimpleNamespace:
     from muvo.models import frustum_pooling  # type: ignore
     from muvo.layers import layers  # type: ignore
     from muvo import metrics  # type: ignore
+    from muvo import losses  # type: ignore
     return types.SimpleNamespace(
         data_preprocessing=data_preprocessing,
         geometry_utils=geometry_utils,
@@ -55,4 +56,7 @@ def load() -> types.SimpleNamespace:
         cumsum_trick=frustum_pooling.cumsum_trick,
         VoxelsSumming=layers.VoxelsSumming,
         SSCMetrics=metrics.SSCMetrics,
+        losses=losses,
+        SemScalLoss=losses.SemScalLoss,
+        GeoScalLoss=losses.GeoScalLoss,
     )

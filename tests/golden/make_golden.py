@@ -171,6 +171,41 @@ def golden_merge(R):
     save("merge.npz", img=img, lidar_xyz=lid, lidar_sem=sem, pcd=pcd, sem=s, pcd_nomask=pcd2, sem_nomask=s2, vox=vox, lab=lab)
 
 
+def scal_inputs(C, seed, shape=(1, 3, 12, 10, 8), ignore_frac=0.02):
+    """Seeded logits (b,s,C,x,y,z) f32 and uint8 targets with a few 255s -- stored in the fixture, not regenerated."""
+    g = torch.Generator().manual_seed(seed)
+    b, s = shape[:2]
+    pred = torch.randn((b, s, C) + tuple(shape[2:]), generator=g) * 2.0
+    tgt = torch.randint(0, C, (b, s) + tuple(shape[2:]), generator=g).to(torch.uint8)
+    tgt[torch.rand(tgt.shape, generator=g) < 0.6] = 0                      # mostly empty, like occupancy grids
+    tgt[torch.rand(tgt.shape, generator=g) < ignore_frac] = 255
+    return pred, tgt
+
+
+def golden_scal(R):
+    """N4: SemScalLoss / GeoScalLoss of the reference (fp32, CPU) with their gradients w.r.t. the logits."""
+    out = {}
+    warnings.filterwarnings("ignore", category=FutureWarning)
+    for C in (2, 5, 9):
+        pred, tgt = scal_inputs(C, 7000 + C)
+        for name, cls in (("sem", R.SemScalLoss), ("geo", R.GeoScalLoss)):
+            p = pred.clone().requires_grad_(True)
+            loss = cls()(p, tgt)
+            loss.backward()
+            out[f"c{C}_{name}_loss"] = np.float64(loss.item())
+            out[f"c{C}_{name}_grad"] = p.grad.numpy()
+        out[f"c{C}_pred"] = pred.numpy()
+        out[f"c{C}_target"] = tgt.numpy()
+    # class 1 absent from the targets: SemScalLoss skips it (count), and no ignore voxels at all
+    pred, tgt = scal_inputs(3, 7100, ignore_frac=0.0)
+    tgt[tgt == 1] = 0
+    p = pred.clone().requires_grad_(True)
+    loss = R.SemScalLoss()(p, tgt)
+    loss.backward()
+    out.update(absent_pred=pred.numpy(), absent_target=tgt.numpy(), absent_sem_loss=np.float64(loss.item()), absent_sem_grad=p.grad.numpy())
+    save("scal.npz", **out)
+
+
 def main():
     R = ref_import.load()
     golden_merge(R)
@@ -178,6 +213,7 @@ def main():
     golden_range(R)
     golden_bev(R)
     golden_ssc(R)
+    golden_scal(R)
 
 
 if __name__ == "__main__":

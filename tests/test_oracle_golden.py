@@ -155,3 +155,15 @@ def test_label_pyramids_oracle_matches_torch_nearest():
         v1 = torch.from_numpy(vox)[:, None]
         v2 = Fn.interpolate(v1, (X // 2, Y // 2, Z // 2), mode="nearest"); v4 = Fn.interpolate(v2, (X // 4, Y // 4, Z // 4), mode="nearest")
         assert np.array_equal(got["voxel_label_2"], v2[:, 0].numpy()) and np.array_equal(got["voxel_label_4"], v4[:, 0].numpy())
+
+
+def test_scal_losses_golden(golden):
+    """N4: float64 restatement vs the reference's fp32 SemScalLoss / GeoScalLoss (losses.py:191-287)."""
+    g = golden("scal.npz")
+    for C in (2, 5, 9):
+        pred, tgt = g[f"c{C}_pred"], g[f"c{C}_target"]
+        assert abs(O.sem_scal_loss(pred, tgt) - float(g[f"c{C}_sem_loss"])) <= 1e-6 * float(g[f"c{C}_sem_loss"])
+        assert abs(O.geo_scal_loss(pred, tgt) - float(g[f"c{C}_geo_loss"])) <= 1e-6 * float(g[f"c{C}_geo_loss"])
+        s = O.scal_sums(pred, tgt)
+        assert s[3 * C] == (tgt != 255).sum() and abs(s[:C].sum() - s[3 * C]) < 1e-6
+    assert abs(O.sem_scal_loss(g["absent_pred"], g["absent_target"]) - float(g["absent_sem_loss"])) <= 1e-6 * float(g["absent_sem_loss"])

@@ -29,7 +29,13 @@ def show(tag, fn, reps=5):
         m = sum(v) / len(v)
         tot += m
         print(f"{tag:10s} {k:28s} {1e3 * m:9.1f} us")
-    print(f"{tag:10s} {'TOTAL':28s} {1e3 * tot:9.1f} us")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{tag:10s} {'TOTAL':28s} {1e3 * tot:9.1f} us   (events around the call: {1e3 * e0.elapsed_time(e1) / reps:9.1f} us)")
 
 
 B, C = 6, 384
@@ -55,3 +61,14 @@ for Cn in (2, 9, 23):
     yp, yt = synth.occupancy_pair(16, min(Cn, 23), 4000)
     tp, tt = torch.from_numpy(yp).to(dev), torch.from_numpy(yt).to(dev)
     show(f"ssc_C{Cn}", lambda: ssc_counts(tp, tt, Cn, ignore255=True))
+del x, xc, out, g, fl, dl, ol
+torch.cuda.empty_cache()
+from muvo_b200.losses import scal_losses  # noqa: E402
+for Cn, dt in ((2, torch.float32), (9, torch.float32), (2, torch.bfloat16), (5, torch.float32)):
+    yp, yt = synth.occupancy_pair(16, min(Cn, 9), 4000)
+    tl = torch.from_numpy(yt).to(dev).view(1, 16, 192, 192, 64)
+    lg = torch.randn((1, 16, Cn, 192, 192, 64), device=dev).to(dt).requires_grad_(True)
+    show(f"scal_C{Cn}_{str(dt)[6:]}", lambda: scal_losses(lg.detach(), tl))
+    sem, geo = scal_losses(lg, tl)
+    show(f"scalb_C{Cn}_{str(dt)[6:]}", lambda: torch.autograd.grad(sem + geo, lg, retain_graph=True))
+    del lg, sem, geo
