@@ -688,12 +688,21 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
   }
 }
 
+// Programmatic dependent launch: the kernels of one call are chained with cudaLaunchAttributeProgrammaticStreamSerialization.
+// `pdl_wait` returns once the previous kernel of the stream has completed and its writes are visible (a no-op for a kernel
+// launched without the attribute); `pdl_launch` lets the next kernel's CTAs be scheduled as soon as every CTA of this grid
+// has called it or exited, so that launch latency and prologue overlap this grid's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // K2: grid = n_scan_frames * 8 scan CTAs (only when the sorted sparse list is wanted), then the queue CTAs (padded to a
 // multiple of the cluster size)
 template <typename T>
 __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThreads)
 k_scan_queue(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw, int n_scan_frames,
              int64_t* __restrict__ n_occ_out, QueueArgs<T> qa, GridDev g, RangeDev r) {
+  pdl_wait();
+  pdl_launch();
   const int scan_ctas = n_scan_frames * kScanCluster;
   if ((int)blockIdx.x < scan_ctas) scan_role(bitmap, prefix, gw, n_occ_out);
   else queue_role<T>((int)blockIdx.x - scan_ctas, qa, g, r);
@@ -889,6 +898,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
     }
     __syncthreads();                         // tile buffer free for the copy issued by the next next()
   }
+  pdl_launch();
   if (tid == 0) { qcount[2 * blockIdx.x] = *qn; qcount[2 * blockIdx.x + 1] = (uint32_t)f_first; }
   if (diag) {
     if (DO_RANGE) diag_add(diag, MUVO_DIAG_DROPPED_NONFINITE, n_drop);
@@ -947,6 +957,8 @@ __device__ __forceinline__ uint32_t tile_swz(uint32_t pos) { return pos ^ ((pos 
 struct EmitDenseArgs {
   uint32_t* bitmap; u64* vtab; const int64_t* off; const uint8_t* sem; const uint8_t* remap; uint8_t* dense; int64_t* n_occ;
   int f_lo;   // first frame of this launch (grid.y counts frames from here)
+  int wait_prev;   // 0 when the previous kernel of the stream is k_emit_range: that one triggers this launch only after its own
+                   // pdl_wait (= K1 and K2 complete) and touches none of this kernel's buffers, so the two may overlap
 };
 // CTA `bx` of frame `f`
 __device__ __forceinline__ void emit_dense_body(int bx, int f, EmitSmem& sm, const EmitDenseArgs& a, const GridDev& g) {
@@ -1056,6 +1068,7 @@ __device__ __forceinline__ void emit_dense_body(int bx, int f, EmitSmem& sm, con
 __global__ void __launch_bounds__(kBlock)
 k_emit_dense(EmitDenseArgs a, GridDev g) {
   extern __shared__ __align__(16) unsigned char emit_raw[];
+  if (a.wait_prev) pdl_wait();
   emit_dense_body((int)blockIdx.x, a.f_lo + (int)blockIdx.y, *reinterpret_cast<EmitSmem*>(emit_raw), a, g);
 }
 
@@ -1254,7 +1267,11 @@ __device__ __forceinline__ void emit_range_body(int64_t vblock, const EmitRangeA
 #endif
 template <typename T, int NP, int LAYOUT>
 __global__ void __launch_bounds__(kBlock, MUVO_ER_MINB)
-k_emit_range(EmitRangeArgs<T> a, RangeDev r) { emit_range_body<T, NP, LAYOUT>((int64_t)blockIdx.x, a, r); }
+k_emit_range(EmitRangeArgs<T> a, RangeDev r) {
+  pdl_wait();
+  pdl_launch();
+  emit_range_body<T, NP, LAYOUT>((int64_t)blockIdx.x, a, r);
+}
 
 // ---------------------------------------------------------------- test hook: f32 pixel path vs float64 formula
 __global__ void __launch_bounds__(kBlock)
@@ -1388,6 +1405,17 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     if (e != cudaSuccess) return (int)e;
   }
 
+  // launch with the programmatic-dependent-launch attribute (see pdl_wait)
+  auto launch_pdl = [](auto kern, dim3 grid, dim3 block, size_t smem, cudaStream_t cs, auto... args) -> cudaError_t {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = cs;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+  };
+
   // One chunk = frames [f0, f1) = points [p0, p1): point pass, rare-path queues, emits, all on stream `cs`.
   int chunk_ctas[kMaxChunks] = {0};
   auto run_pass = [&](int chunk, int f0, int f1, int64_t p0, int64_t p1, cudaStream_t cs) -> int {
@@ -1420,19 +1448,21 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       const unsigned sgrid = (unsigned)(scan_frames * kScanCluster + queue_ctas);
       if (sgrid > 0) {
         QueueArgs<T> qa{xyz, sem, off, F, p0, p1, w.pixtab, w.vtab, w.queue, qcount, queue_ctas ? n_tile_ctas : 0, diag};
-        k_scan_queue<T><<<sgrid, kScanThreads, 0, cs>>>(w.bitmap, w.prefix, g.gw, scan_frames, n_occ, qa, g, r);
+        launch_pdl(k_scan_queue<T>, dim3(sgrid), dim3(kScanThreads), 0, cs, (const uint32_t*)w.bitmap, w.prefix, g.gw, scan_frames, n_occ, qa, g, r);
         MUVO_AFTER_LAUNCH("k_scan_queue", cs);
       }
     }
+    bool emitted_range = false;
     if (do_range) {              // right after its producers: the pixel words are still L2 resident
+      emitted_range = true;
       EmitRangeArgs<T> era{w.pixtab, xyz, sem, off, f0, f1, depth_out, xyz_out, sem_out};
       const int64_t npix = (int64_t)(f1 - f0) * HWr;
       if (range_vec4) {
-        if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix / 4), kBlock, 0, cs>>>(era, r);
-        else                                 k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix / 4), kBlock, 0, cs>>>(era, r);
+        if (layout == MUVO_RANGE_LAYOUT_HWC) launch_pdl(k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC>, dim3(blocks_for(npix / 4)), dim3(kBlock), 0, cs, era, r);
+        else                                 launch_pdl(k_emit_range<T, 4, MUVO_RANGE_LAYOUT_XYZD>, dim3(blocks_for(npix / 4)), dim3(kBlock), 0, cs, era, r);
       } else {
-        if (layout == MUVO_RANGE_LAYOUT_HWC) k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC><<<blocks_for(npix), kBlock, 0, cs>>>(era, r);
-        else                                 k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD><<<blocks_for(npix), kBlock, 0, cs>>>(era, r);
+        if (layout == MUVO_RANGE_LAYOUT_HWC) launch_pdl(k_emit_range<T, 1, MUVO_RANGE_LAYOUT_HWC>, dim3(blocks_for(npix)), dim3(kBlock), 0, cs, era, r);
+        else                                 launch_pdl(k_emit_range<T, 1, MUVO_RANGE_LAYOUT_XYZD>, dim3(blocks_for(npix)), dim3(kBlock), 0, cs, era, r);
       }
       MUVO_AFTER_LAUNCH("k_emit_range", cs);
     }
@@ -1440,8 +1470,8 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       // K5 (the last consumer of the tables clears them)
       if (dense_fast) {
         const int bpf = (int)ceil_div64(g.gw, kBlock * kEmitWords);
-        EmitDenseArgs eda{w.bitmap, w.vtab, off, sem, remap, dense, n_occ_emit, f0};
-        k_emit_dense<<<dim3((unsigned)bpf, (unsigned)(f1 - f0)), kBlock, sizeof(EmitSmem), cs>>>(eda, g);
+        EmitDenseArgs eda{w.bitmap, w.vtab, off, sem, remap, dense, n_occ_emit, f0, (do_range && emitted_range) ? 0 : 1};
+        launch_pdl(k_emit_dense, dim3((unsigned)bpf, (unsigned)(f1 - f0)), dim3(kBlock), sizeof(EmitSmem), cs, eda, g);
         MUVO_AFTER_LAUNCH("k_emit_dense", cs);
       } else {
         const int64_t words = (int64_t)F * g.gw;

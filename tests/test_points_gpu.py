@@ -258,6 +258,29 @@ def test_full_size_batch_properties(lib):
         assert np.array_equal(rsem[f].cpu().numpy(), s0)
 
 
+def test_cfg5_million_point_frames_vs_oracle(lib):
+    """cfg5 frame size (64 beams x 15 625 azimuths = 1 M points per frame): three ragged frames, full oracle parity on
+    every output (dense + sorted sparse voxels, range view) -- many points per voxel / pixel, long atomic chains."""
+    sizes = [1_000_000, 999_999, 1_000_000]
+    frames = [synth.carla_lidar_frame(n, 5000 + i) for i, n in enumerate(sizes)]
+    pts = np.concatenate([f[0] for f in frames]); sem = np.concatenate([f[1] for f in frames])
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    r = sensor_to_grid(torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev()), off, grid=GridSpec(),
+                       range_spec=RangeSpec(lidar_position=tuple(LIDAR)), dense=True, sparse=True, layout="xyzd")
+    torch.cuda.synchronize()
+    for f, (p, sm) in enumerate(frames):
+        v0, l0 = O.voxel_filter_fast(p, sm, *GRID)
+        n = int(r["n_occ"][f])
+        assert n == len(v0)
+        rows = r["voxel_sparse"][off[f]:off[f] + n].cpu().numpy().view(np.uint16)
+        assert np.array_equal(rows[:, :3], v0) and np.array_equal(rows[:, 3], l0.astype(np.uint16))
+        want = O.densify_voxels(np.concatenate([v0, l0[:, None].astype(np.uint16)], 1), (192, 192, 64))
+        assert np.array_equal(r["voxel"][f].cpu().numpy(), want)
+        d0, x0, s0 = O.range_projection(p, sm, lidar_position=LIDAR)
+        assert np.array_equal(r["range_xyzd"][f].cpu().numpy(), O.pack_range_view(d0, x0))
+        assert np.array_equal(r["range_sem"][f].cpu().numpy(), s0)
+
+
 # ------------------------------------------------------------------ near-ties: the packed atomicMax + exact tie protocol
 def test_voxel_near_ties_resolve_exactly(lib):
     """Thousands of points whose |p mod res|^2 agree in the top 32 key bits (and many exact ties) in a handful
