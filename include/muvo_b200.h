@@ -255,7 +255,8 @@ MUVO_API int muvo_scal_sums_bwd(const void* logits, int32_t logits_dtype, const 
  * [0] points decided by the f32 path, [1] points deferred to the float64 formula (near a bin edge),
  * [2] f32-decided points whose pixel differs from the float64 one (must stay 0), [3] dropped (non-finite / at the sensor).
  * muvo_debug_set_tuning: process-wide launch knobs for benchmarking sweeps; key 0 = CTAs per SM of the persistent
- * point pass (0 = as many as fit), key 1 bit 0 = disable the neighbour filter in front of the voxel atomicMax.                                              */
+ * point pass (0 = as many as fit), key 1 bit 0 = disable the neighbour filter in front of the voxel atomicMax,
+ * key 2 = 1 forces the per-point gather kernel of the BEV pool forward (default: streamed rows).                                              */
 MUVO_API int muvo_debug_pixel_check(const float* xyz, int64_t n_points, const MuvoRangeCfg* cfg_h, int64_t* counts_out,
                                     void* stream);
 MUVO_API int muvo_debug_set_tuning(int32_t key, int32_t value);

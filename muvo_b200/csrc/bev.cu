@@ -31,6 +31,10 @@ template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float ldf<__half>(const __half* p) { return __half2float(__ldg(p)); }
 template <> __device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+template <typename T> __device__ __forceinline__ float ldf_reg(T v);
+template <> __device__ __forceinline__ float ldf_reg<float>(float v) { return v; }
+template <> __device__ __forceinline__ float ldf_reg<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float ldf_reg<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 template <typename T> __device__ __forceinline__ T cvt(float v);
 template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half cvt<__half>(float v) { return __float2half_rn(v); }
@@ -43,6 +47,7 @@ struct BevWs {
   int32_t* sorted = nullptr;        // [B, n_pts]  point ids grouped by cell, ascending inside a cell
   int32_t* kp = nullptr;            // [B, n_pts]  kept points in ascending point order ...
   int32_t* dest = nullptr;          // [B, n_pts]  ... and their position in `sorted`
+  uint16_t* dest16 = nullptr;       // [B, n_pts]  `dest` as uint16 (saturated; read only for frames with <= 32768 kept points)
   uint32_t* chunk_kept = nullptr;   // [B, n_wc]   kept points per warp-chunk, scanned in place by S3
   int n_wc = 0;
   size_t bytes = 0;
@@ -59,6 +64,7 @@ static BevWs carve_bev(void* base, int B, int64_t n_pts, int n_cells) {
   w.sorted = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
   w.kp = (int32_t*)(b + o);          o = align_up(o + (size_t)B * n_pts * 4, 256);
   w.dest = (int32_t*)(b + o);        o = align_up(o + (size_t)B * n_pts * 4, 256);
+  w.dest16 = (uint16_t*)(b + o);     o = align_up(o + (size_t)B * n_pts * 2, 256);
   w.chunk_kept = (uint32_t*)(b + o); o = align_up(o + (size_t)B * w.n_wc * 4, 256);
   w.bytes = o;
   return w;
@@ -184,7 +190,8 @@ k_cell_starts(const uint32_t* __restrict__ cell_total, uint32_t* __restrict__ ce
 __global__ void __launch_bounds__(kSortWarps * 32)
 k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells, int n_wc,
              const uint32_t* __restrict__ chunk_base, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ sorted,
-             const uint32_t* __restrict__ chunk_kept, int32_t* __restrict__ kp, int32_t* __restrict__ dest) {
+             const uint32_t* __restrict__ chunk_kept, int32_t* __restrict__ kp, int32_t* __restrict__ dest,
+             uint16_t* __restrict__ dest16) {
   extern __shared__ uint32_t sm[];                 // running count per cell inside this warp-chunk
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t wc_global = (int64_t)blockIdx.x * kSortWarps + warp;
@@ -199,6 +206,7 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
   int32_t* out = sorted + (size_t)b * n_pts;
   int32_t* kpo = kp + (size_t)b * n_pts;
   int32_t* dso = dest + (size_t)b * n_pts;
+  uint16_t* d16 = dest16 + (size_t)b * n_pts;
   uint32_t krun = chunk_kept[(size_t)b * n_wc + wc];   // kept points before this chunk (frame-relative)
   const int64_t p0 = (int64_t)wc * kWarpChunk;
   for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
@@ -224,6 +232,7 @@ k_cell_place(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells
         out[pos] = (int32_t)pp;
         kpo[kr] = (int32_t)pp;
         dso[kr] = (int32_t)pos;
+        d16[kr] = (uint16_t)(pos < 65535u ? pos : 65535u);
       }
       krun += __popc(vb);
       __syncwarp();
@@ -300,9 +309,15 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
         uint32_t s0 = 0, s1 = 0;
         if (cell < c1) { s0 = cs[cell] - w0; s1 = cs[cell + 1] - w0; }
         const bool big = (s1 - s0) > (uint32_t)kBigCell;
+        const unsigned bm = __ballot_sync(0xffffffffu, big);    // one shared-memory atomic per warp step, not per big cell
+        if (bm) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&n_big, __popc(bm));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (big) big_list[base + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)(cell - c0);
+        }
         float acc = 0.f;
         if (!big) for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
-        else big_list[atomicAdd(&n_big, 1)] = (uint16_t)(cell - c0);
         if (cell < c1 && !big) o[cell] = acc;
       }
       __syncthreads();
@@ -328,6 +343,237 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
       }
     }
     c0 = c1;
+  }
+}
+
+// (Streaming the row with coalesced 16-byte loads next to a dense int32 position map was also measured: 584 us.  The map
+// doubles the L2 -> SM traffic, 4.4 GB per forward, and that fabric tops out near 7.5 TB/s.)
+//
+// Persistent rows (the default): one CTA per SM walks ~16 consecutive (frame, channel) rows.  A thread owns up to
+// kPipeItems kept points of a row (address-ordered pairs, one 8-byte index load per pair), issues all its gathers at once
+// and does so for row r+1 BEFORE the segment sums of row r; the frame's cell starts and its list of big cells are staged
+// in shared memory once per frame; the positions of a thread's pairs arrive in one batch of 32-bit loads (uint16 copy of
+// `dest`).  Rows of frames with > 32768 kept points take the windowed code of k_pool_rows via pool_row_windowed.
+//
+// Measured at cfg3 (6 frames, C = 384, 30 k kept points per row; forward incl. the 62 us index sort):
+//   k_pool_rows, one CTA per row, 8 gathers in flight per thread                                   427 us  (16 in flight: 540 us)
+//   this kernel                                                                                    402 us
+//   ... without the scatter into the row buffer: -24 us; without the segment sums: -94 us; without both: 299 us
+//   gathering in cell-sorted order (coalesced stores, no position list)                           1038 us
+//   streaming the row with 16-byte loads next to a dense int32 position map                         644 us
+//   warp-specialised (8 producer warps gather half a row, 8 consumer warps sum the other half)      771 us
+// ncu (profiles/r1_bev_pool_rows_ncu.txt): DRAM 36 % of peak, no unit above 50 %, long-scoreboard stalls.  The gather rate
+// follows the number of WARPS that issue loads (8 warps: half the rate of 16 or 32), not the loads each thread has in
+// flight, so the shared-memory phases cannot be hidden behind the gathers by the same warps and taking warps away from
+// the gathers costs more than the overlap returns.  The fused lift-splat (N2) avoids the problem: it never reads `x`.
+constexpr int kPipeThreads = 512;                      // 128 registers per thread: 64 of them hold the row in flight
+constexpr int kPipeItems = 64;                         // kept points per thread: kPipeItems * kPipeThreads = 32768 per row
+
+// segment sums of the cells [c0, c1) whose values sit in buf[cs[cell] - w0 ...): see k_pool_rows
+__device__ __forceinline__ void pool_segments(const float* buf, uint16_t* big_list, int* n_big, const uint32_t* __restrict__ cs,
+                                              int c0, int c1, uint32_t w0, float* __restrict__ o) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int cb = c0 + warp * 32; cb < c1; cb += (kPipeThreads / 32) * 32) {
+    const int cell = cb + lane;
+    uint32_t s0 = 0, s1 = 0;
+    if (cell < c1) { s0 = cs[cell] - w0; s1 = cs[cell + 1] - w0; }
+    const bool big = (s1 - s0) > (uint32_t)kBigCell;
+    const unsigned bm = __ballot_sync(0xffffffffu, big);        // one shared-memory atomic per warp step, not per big cell
+    if (bm) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(n_big, __popc(bm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (big) big_list[base + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)(cell - c0);
+    }
+    float acc = 0.f;
+    if (!big) for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
+    if (cell < c1 && !big) o[cell] = acc;
+  }
+  __syncthreads();
+  const int nb = *n_big;
+  for (int i = warp; i < nb; i += kPipeThreads / 32) {
+    const int cell = c0 + (int)big_list[i];
+    const uint32_t b0 = cs[cell] - w0, b1 = cs[cell + 1] - w0;
+    float part = 0.f;
+    for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+    if (lane == 0) o[cell] = part;
+  }
+}
+
+// The same sums with the big-cell list of the frame built once (pool_big_list) and reused by every channel row: no atomics,
+// no barrier between the two parts.
+__device__ __forceinline__ void pool_big_list(uint16_t* big_list, int* n_big, const uint32_t* cs, int n_cells) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *n_big = 0;
+  __syncthreads();
+  for (int cb = warp * 32; cb < n_cells; cb += (kPipeThreads / 32) * 32) {
+    const int cell = cb + lane;
+    const bool big = cell < n_cells && (cs[cell + 1] - cs[cell]) > (uint32_t)kBigCell;
+    const unsigned bm = __ballot_sync(0xffffffffu, big);
+    if (bm) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(n_big, __popc(bm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (big) big_list[base + __popc(bm & ((1u << lane) - 1u))] = (uint16_t)cell;
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ void pool_segments_pre(const float* buf, const uint16_t* big_list, int nb, const uint32_t* cs, int n_cells,
+                                                  float* __restrict__ o) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = warp; i < nb; i += kPipeThreads / 32) {        // big cells first: they are the long poles
+    const int cell = (int)big_list[i];
+    const uint32_t b0 = cs[cell], b1 = cs[cell + 1];
+    float part = 0.f;
+    for (uint32_t j = b0 + lane; j < b1; j += 32) part += buf[j];
+#pragma unroll
+    for (int dd = 16; dd; dd >>= 1) part += __shfl_xor_sync(0xffffffffu, part, dd);
+    if (lane == 0) o[cell] = part;
+  }
+  for (int cell = tid; cell < n_cells; cell += kPipeThreads) {
+    const uint32_t s0 = cs[cell], s1 = cs[cell + 1];
+    if (s1 - s0 > (uint32_t)kBigCell) continue;
+    float acc = 0.f;
+    for (uint32_t j = s0; j < s1; ++j) acc += buf[j];
+    o[cell] = acc;
+  }
+}
+
+// one row with the windowed gather code (any number of kept points); all threads of the CTA
+template <typename T>
+__device__ __noinline__ void pool_row_windowed(const T* __restrict__ xr, const int32_t* __restrict__ kp, const int32_t* __restrict__ ds,
+                                  const uint32_t* __restrict__ cs, const int32_t* __restrict__ list, int n_cells, float* buf,
+                                  uint16_t* big_list, int* n_big, float* __restrict__ o) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_kept = (int)cs[n_cells];
+  int c0 = 0;
+  while (c0 < n_cells) {
+    const uint32_t w0 = cs[c0];
+    int lo = c0 + 1, hi = n_cells;
+    while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (cs[mid] - w0 <= (uint32_t)kRowCap) lo = mid; else hi = mid - 1; }
+    const int c1 = lo;
+    const uint32_t w1 = cs[c1];
+    if (w1 - w0 <= (uint32_t)kRowCap) {
+      const int iw0 = (int)w0, iw1 = (int)w1;
+      for (int j0 = 0; j0 < n_kept && w1 > w0; j0 += kPipeThreads * 8) {
+        int d[8], pp[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int j = j0 + u * kPipeThreads + tid;
+          bool in = j < n_kept;
+          d[u] = in ? __ldg(ds + j) : -1;
+          pp[u] = in ? __ldg(kp + j) : 0;
+        }
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (d[u] >= iw0 && d[u] < iw1) ? ldf<T>(xr + pp[u]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (d[u] >= iw0 && d[u] < iw1) buf[d[u] - iw0] = v[u];
+      }
+      if (tid == 0) *n_big = 0;
+      __syncthreads();
+      pool_segments(buf, big_list, n_big, cs, c0, c1, w0, o);
+      __syncthreads();
+    } else {
+      if (warp == 0) {
+        float acc = 0.f;
+        for (uint32_t j = w0 + lane; j < w1; j += 32) acc += ldf<T>(xr + list[j]);
+#pragma unroll
+        for (int dd = 16; dd; dd >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, dd);
+        if (lane == 0) o[c0] = acc;
+      }
+    }
+    c0 = c1;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+k_pool_rows_pipe(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __restrict__ kp_all,
+                 const int32_t* __restrict__ dest_all, const uint16_t* __restrict__ dest16_all,
+                 const uint32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted_all, int B, int64_t n_pts, int C,
+                 int n_cells, float* __restrict__ out) {
+  extern __shared__ float buf[];
+  __shared__ int n_big;
+  uint16_t* big_list = reinterpret_cast<uint16_t*>(buf + kRowCap);
+  uint32_t* cs_s = reinterpret_cast<uint32_t*>(buf + kRowCap) + (n_cells + 1) / 2 + 1;   // [n_cells + 1] cell starts of the current frame
+  const int tid = threadIdx.x;
+  const int n_rows = B * C;
+  // contiguous rows per CTA: ~n_rows / gridDim.x consecutive channels of (mostly) one frame
+  const int r_lo = (int)((int64_t)n_rows * blockIdx.x / gridDim.x), r_hi = (int)((int64_t)n_rows * (blockIdx.x + 1) / gridDim.x);
+  if (r_lo >= r_hi) return;
+  constexpr int kPairs = kPipeItems / 2;
+  T v[kPipeItems];                                       // raw elements: converting here would wait for every load
+  // All gathers of row `row` into v[], in ADDRESS order (kept list): thread t owns the pairs t, t + 512, ...; v[2i], v[2i+1]
+  // = items 2 (i * 512 + t) and the next one, fetched with one 8-byte index load.  Asynchronous: nothing here waits for
+  // the values.  (Gathering in cell-sorted order instead -- no position list, coalesced stores -- was 2.5x slower: neighbours
+  // in a sector belong to different cells, so every sector is requested again and again.)
+  auto issue = [&](int row, int n_kept) {
+    const int b = row / C, c = row - b * C;
+    const int2* kp2 = reinterpret_cast<const int2*>(kp_all + (size_t)b * n_pts);
+    const T* xr = x + (size_t)b * sb + (size_t)c * sc;
+    int2 pp[kPairs];
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      const int k = i * kPipeThreads + tid;
+      pp[i] = 2 * k < n_kept ? __ldg(kp2 + k) : make_int2(-1, -1);
+      if (2 * k + 1 >= n_kept) pp[i].y = -1;
+    }
+#pragma unroll
+    for (int i = 0; i < kPairs; ++i) {
+      v[2 * i] = pp[i].x >= 0 ? __ldg(xr + pp[i].x) : cvt<T>(0.f);
+      v[2 * i + 1] = pp[i].y >= 0 ? __ldg(xr + pp[i].y) : cvt<T>(0.f);
+    }
+  };
+  auto kept_of = [&](int row) { return (int)__ldg(cell_start + (size_t)(row / C) * (n_cells + 1) + n_cells); };
+
+  int row = r_lo;
+  int n_kept = kept_of(row);
+  bool piped = n_kept <= kPipeItems * kPipeThreads;
+  if (piped) issue(row, n_kept);
+  int b_staged = -1;
+  while (row < r_hi) {
+    const int b = row / C, c = row - b * C;
+    if (b != b_staged) {                                  // (the previous row's segment sums ended with a barrier)
+      const uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+      for (int i = tid; i <= n_cells; i += kPipeThreads) cs_s[i] = __ldg(cs + i);
+      __syncthreads();
+      pool_big_list(big_list, &n_big, cs_s, n_cells);      // once per frame, shared by its channel rows
+      b_staged = b;
+    }
+    float* o = out + ((size_t)b * C + c) * n_cells;
+    const int next = row + 1;
+    const int next_kept = next < r_hi ? (next / C == b ? n_kept : kept_of(next)) : 0;
+    const bool next_piped = next < r_hi && next_kept <= kPipeItems * kPipeThreads;
+    if (piped) {
+      // positions of this thread's pairs: ALL loads first (one L2 round trip, the gathers are still in flight), then the
+      // scatter into the row buffer
+      const uint32_t* d2 = reinterpret_cast<const uint32_t*>(dest16_all + (size_t)b * n_pts);
+      uint32_t d[kPairs];
+#pragma unroll
+      for (int i = 0; i < kPairs; ++i) { const int k = i * kPipeThreads + tid; d[i] = 2 * k < n_kept ? __ldg(d2 + k) : 0u; }
+#pragma unroll
+      for (int i = 0; i < kPairs; ++i) {
+        const int k = i * kPipeThreads + tid;
+        if (2 * k < n_kept) buf[d[i] & 0xffffu] = ldf_reg<T>(v[2 * i]);
+        if (2 * k + 1 < n_kept) buf[d[i] >> 16] = ldf_reg<T>(v[2 * i + 1]);
+      }
+      __syncthreads();
+      if (next_piped) issue(next, next_kept);             // next row's DRAM round trips run under this row's segment sums
+      pool_segments_pre(buf, big_list, n_big, cs_s, n_cells, o);
+      __syncthreads();
+    } else {
+      __syncthreads();
+      b_staged = -1;                                      // the windowed code rebuilds the big-cell list per window
+      pool_row_windowed<T>(x + (size_t)b * sb + (size_t)c * sc, kp_all + (size_t)b * n_pts, dest_all + (size_t)b * n_pts, cs_s,
+                           sorted_all + (size_t)b * n_pts, n_cells, buf, big_list, &n_big, o);
+      if (next_piped) issue(next, next_kept);
+    }
+    row = next; n_kept = next_kept; piped = next_piped;
   }
 }
 
@@ -717,15 +963,27 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_starts", st);
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
-                                                             w.chunk_kept, w.kp, w.dest);
+                                                             w.chunk_kept, w.kp, w.dest, w.dest16);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
   if (sp == 1) {
     const size_t rsmem = (size_t)kRowCap * sizeof(float) + (size_t)n_cells * 2 + 16;
     if (n_cells > 65535 || rsmem > 227 * 1024) return MUVO_E_SHAPE;
-    cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-    if (e != cudaSuccess) return (int)e;
-    k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.kp, w.dest, w.cell_start, w.sorted, B, n_pts,
-                                                                         C, n_cells, out);
+    if (g_tuning[2] == 1 || n_pts % 2 != 0) {        // tuning key 2 = 1: the one-CTA-per-row gather kernel (also: odd row stride)
+      cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
+      if (e != cudaSuccess) return (int)e;
+      k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.kp, w.dest, w.cell_start, w.sorted, B, n_pts,
+                                                                           C, n_cells, out);
+    } else {
+      const size_t psmem = (size_t)kRowCap * sizeof(float) + (size_t)((n_cells + 1) / 2 + 1) * 4 + (size_t)(n_cells + 1) * 4;
+      if (psmem > 227 * 1024) return MUVO_E_SHAPE;
+      cudaError_t e = cudaFuncSetAttribute(k_pool_rows_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
+      if (e != cudaSuccess) return (int)e;
+      int sms = kNumSMsB200;
+      { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+      const int64_t rows = (int64_t)B * C;
+      k_pool_rows_pipe<T><<<(unsigned)(rows < sms ? rows : sms), kPipeThreads, psmem, st>>>(x, sb, sc, w.kp, w.dest, w.dest16, w.cell_start,
+                                                                                        w.sorted, B, n_pts, C, n_cells, out);
+    }
   } else {
     k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,
                                                                              C, n_cells, out);
@@ -841,7 +1099,7 @@ int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t*
   k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_starts", st);
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
-                                                             w.chunk_kept, w.kp, w.dest);
+                                                             w.chunk_kept, w.kp, w.dest, w.dest16);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
   const int groups = (n_cells + kLsCells - 1) / kLsCells;
   if (C % 4 == 0 && C / 4 <= kLsThreads && (reinterpret_cast<uintptr_t>(feat_cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {

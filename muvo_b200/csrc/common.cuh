@@ -19,6 +19,7 @@
 namespace muvo {
 
 constexpr int kNumSMsB200 = 148;
+extern int g_tuning[8];   // muvo_debug_set_tuning (points.cu)
 
 // Optional per-kernel timing (muvo_profile_begin/end): when active on this host thread, every launch site
 // records a CUDA event on the launching stream right after its kernel.  Inactive -> a single branch.

@@ -16,7 +16,12 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--stage", default="points")
 ap.add_argument("--nmin", type=int, default=60000)
 ap.add_argument("--nmax", type=int, default=100000)
+ap.add_argument("--tune", action="append", default=[], help="k=v for muvo_debug_set_tuning")
 a = ap.parse_args()
+for kv in a.tune:
+    from muvo_b200 import _lib
+    k, v = kv.split("=")
+    _lib.check(_lib.load().muvo_debug_set_tuning(int(k), int(v)), "set_tuning")
 dev = torch.device("cuda", 0)
 if a.stage == "points":
     pts, sem, off = synth.lidar_batch(a.frames, a.nmin, a.nmax, 2000)
