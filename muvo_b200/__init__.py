@@ -17,6 +17,7 @@ from .metrics import SSCMetrics, ssc_counts, ssc_counts_from_logits, all_reduce_
 from .frustum_pooling import (FrustumPooling, QuickCumsum, VoxelsSumming, cumsum_trick, quick_cumsum, gen_dx_bx,  # noqa: F401
                               bev_pool, lift_splat, bev_params_to_intrinsics, intrinsics_inverse)
 from .losses import SemScalLoss, GeoScalLoss, scal_losses, scal_sums  # noqa: F401
+from .pillars import scatter_mean, scatter_max, pillar_grid_locations, pillar_decorate, pillar_scatter_points  # noqa: F401
 from .patch import patch, unpatch  # noqa: F401
 from .distributed import shard_frames, init_distributed  # noqa: F401
 

@@ -22,7 +22,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 # points.cu reproduces numpy's float64 arithmetic: no FMA contraction allowed there.
 PER_FILE = {"points.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split(),
             "merge.cu": ["-fmad=false"]}   # MUVO_NVCC_EXTRA: tuning builds only
-SOURCES = ["api.cu", "points.cu", "ssc.cu", "bev.cu", "merge.cu", "pyramid.cu", "scal.cu"]
+SOURCES = ["api.cu", "points.cu", "ssc.cu", "bev.cu", "merge.cu", "pyramid.cu", "scal.cu", "pillar.cu"]
 
 
 def _nvcc() -> str:

@@ -58,6 +58,11 @@ def patch(verbose: bool = False) -> int:
             for name in ("SemScalLoss", "GeoScalLoss"):
                 if hasattr(m, name):
                     _swap(m, name, getattr(losses, name))
+    from . import pillars                                         # N4: torch_scatter calls of the PointPillar encoder
+    m = sys.modules.get("muvo.models.common")
+    if m is not None:
+        _swap(m, "scatter_mean", pillars.scatter_mean)
+        _swap(m, "scatter_max", pillars.scatter_max)
     if verbose:
         for obj, name, _ in _saved[n0:]:
             print(f"muvo_b200.patch: {getattr(obj, '__name__', obj)}.{name}")

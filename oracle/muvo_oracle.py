@@ -29,7 +29,7 @@ __all__ = [
     "bev_intrinsics", "gen_dx_bx", "frustum_grid", "frustum_geometry", "bev_cell_ids",
     "cumsum_trick", "quick_cumsum_backward", "voxel_pooling_cumsum", "voxel_pooling_exact",
     "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "label_pyramids", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
-    "ssc_stats_from_counts", "sem_scal_loss", "geo_scal_loss", "scal_sums",
+    "ssc_stats_from_counts", "sem_scal_loss", "geo_scal_loss", "scal_sums", "scatter_mean", "scatter_max",
 ]
 
 
@@ -575,6 +575,43 @@ def scal_sums(prediction, target, ignore_index=255):
         out[i], out[c + i], out[2 * c + i] = p.sum(), p[hit].sum(), hit.sum()
     out[3 * c] = mask.sum()
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# N4: torch_scatter reductions used by the PointPillar encoder (muvo/models/common.py:703, :731)
+# torch_scatter is a third-party dependency of the reference (not vendored, no pinned version in requirements.txt);
+# these restate its documented semantics for dim=0.  PARITY UNPINNED: the package is not installable here.
+# ---------------------------------------------------------------------------------------------
+def scatter_mean(src, index, dim_size=None):
+    """out[m] = mean of src rows with index == m (float64 accumulation); rows that receive nothing are 0."""
+    src = np.asarray(src, dtype=np.float64)
+    index = np.asarray(index).reshape(-1)
+    M = int(dim_size) if dim_size is not None else (int(index.max()) + 1 if index.size else 0)
+    out = np.zeros((M, src.shape[1]))
+    np.add.at(out, index, src)
+    cnt = np.bincount(index, minlength=M).astype(np.float64)
+    return out / np.maximum(cnt, 1.0)[:, None]
+
+
+def scatter_max(src, index, dim_size=None):
+    """(max, arg): per output row and feature the maximum over the source rows with index == m and the LOWEST source row
+    attaining it; rows that receive nothing are 0 with arg = N."""
+    src = np.asarray(src)
+    index = np.asarray(index).reshape(-1)
+    N, F = src.shape
+    M = int(dim_size) if dim_size is not None else (int(index.max()) + 1 if index.size else 0)
+    out = np.zeros((M, F), dtype=src.dtype)
+    arg = np.full((M, F), N, dtype=np.int64)
+    seen = np.zeros(M, dtype=bool)
+    for n in range(N):                                   # small inputs only
+        m = index[n]
+        if not seen[m]:
+            out[m], arg[m], seen[m] = src[n], n, True
+        else:
+            better = src[n] > out[m]
+            out[m] = np.where(better, src[n], out[m])
+            arg[m] = np.where(better, n, arg[m])
+    return out, arg
 
 
 def _self_check():  # pragma: no cover - quick sanity when run directly

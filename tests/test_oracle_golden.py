@@ -167,3 +167,14 @@ def test_scal_losses_golden(golden):
         s = O.scal_sums(pred, tgt)
         assert s[3 * C] == (tgt != 255).sum() and abs(s[:C].sum() - s[3 * C]) < 1e-6
     assert abs(O.sem_scal_loss(g["absent_pred"], g["absent_target"]) - float(g["absent_sem_loss"])) <= 1e-6 * float(g["absent_sem_loss"])
+
+
+def test_scatter_oracle_known_answers():
+    """N4 (PointPillar): restated torch_scatter semantics on a hand-checked case; torch.scatter_reduce as a second opinion."""
+    src = np.array([[1., 2], [3, 1], [3, 5], [0, 0]], dtype=np.float32)
+    idx = np.array([0, 2, 2, 0])
+    assert O.scatter_mean(src, idx, 4).tolist() == [[0.5, 1.0], [0, 0], [3.0, 3.0], [0, 0]]
+    mx, arg = O.scatter_max(src, idx, 4)
+    assert mx.tolist() == [[1, 2], [0, 0], [3, 5], [0, 0]] and arg.tolist() == [[0, 0], [4, 4], [1, 2], [4, 4]]
+    t = torch.zeros((4, 2)).scatter_reduce(0, torch.from_numpy(idx)[:, None].expand(-1, 2), torch.from_numpy(src), "amax", include_self=False)
+    assert np.array_equal(t.numpy(), mx)
