@@ -114,7 +114,14 @@ __global__ void k_cell_scan(uint32_t* __restrict__ chunk_base, uint32_t* __restr
   uint32_t* col = chunk_base + (size_t)b * n_wc * n_cells + c;
   uint32_t run = 0;
   int k = 0;
-  for (; k + 8 <= n_wc; k += 8) {           // 8 independent loads, then the dependent stores
+  for (; k + 32 <= n_wc; k += 32) {         // 32 independent loads, then the dependent stores (latency bound: few threads)
+    uint32_t v[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) v[u] = col[(size_t)(k + u) * n_cells];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) { col[(size_t)(k + u) * n_cells] = run; run += v[u]; }
+  }
+  for (; k + 8 <= n_wc; k += 8) {
     uint32_t v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = col[(size_t)(k + u) * n_cells];
@@ -958,7 +965,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   prof_mark("<bev_fwd>", st);
   k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.chunk_kept);
   MUVO_AFTER_LAUNCH("k_cell_hist", st);
-  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
+  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 64), 64, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_scan", st);
   k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_starts", st);
@@ -1094,7 +1101,7 @@ int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t*
   prof_mark("<lift_splat_fwd>", st);
   k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.chunk_kept);
   MUVO_AFTER_LAUNCH("k_cell_hist", st);
-  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 256), 256, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
+  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 64), 64, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_scan", st);
   k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
   MUVO_AFTER_LAUNCH("k_cell_starts", st);
