@@ -56,7 +56,11 @@ class HostPipeline:
         self.queue = []
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self.host_threads = int(host_threads)   # 0 = one per core (capped at 16)
+        if int(host_threads) <= 0:              # default: the cores of this box shared by the ranks running on it, capped at 16
+            import os
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+            host_threads = max(1, min(16, (os.cpu_count() or 1) // max(local, 1)))
+        self.host_threads = int(host_threads)
         self.row_cap = None                     # sparse rows read back per batch: 1.25 x the largest total seen so far
 
     def _ensure(self, slot: _Slot, n_pts: int, n_frames: int):
