@@ -241,29 +241,40 @@ def run_ours(args):
     # end to end through the host-buffer API: pinned staging, H2D, kernels, D2H of the reference-facing results
     pipe = HostPipeline(device, grid=grid, range_spec=rspec, dense=False, sparse=True, layout="hwc", depth=3)
     pipe.warmup(pts, sem, off)                 # every slot's pinned / device buffers allocated
-    for _ in range(3):
-        pipe.submit(pts, sem, off)
-        pipe.result()
-    barrier()
+    # the step's inputs in pinned host memory (filled once, outside the timed region), as the bench contract words it; the
+    # same loop from ordinary pageable numpy arrays (one more staging copy per step) is reported next to it
+    pin_pts, pin_sem, pin_off = HostPipeline.pinned_inputs(P, n_frames)
+    pin_pts.numpy()[...] = pts; pin_sem.numpy()[...] = sem; pin_off.numpy()[...] = off
     e2e_steps = max(args.steps, 4)
-    t0 = time.perf_counter()
-    submitted = done = 0
-    while done < e2e_steps:
-        while submitted < e2e_steps and submitted - done < len(pipe.slots):   # keep every slot busy
-            pipe.submit(pts, sem, off)
-            submitted += 1
-        res = pipe.result()
-        done += 1
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+
+    def e2e_loop(a_pts, a_sem, a_off):
+        for _ in range(3):
+            pipe.submit(a_pts, a_sem, a_off)
+            pipe.result()
+        barrier()
+        t0 = time.perf_counter()
+        submitted = done = 0
+        while done < e2e_steps:
+            while submitted < e2e_steps and submitted - done < len(pipe.slots):   # keep every slot busy
+                pipe.submit(a_pts, a_sem, a_off)
+                submitted += 1
+            pipe.result()
+            done += 1
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.item())
+
+    e2e_pageable_s = e2e_loop(pts, sem, off)
+    e2e_s = e2e_loop(pin_pts, pin_sem, pin_off)
     clocks = sampler.stop()                     # sampled across the device-timed and the end-to-end timed regions
-    e2e = {"value": total_pts * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes),
-           "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
-           "api": "muvo_b200.pipeline.HostPipeline.submit/result (numpy in, pinned host out: sparse voxel lists + "
-                  "HWC range images = the returns of voxel_filter / do_range_projection)"}
+    e2e = {"value": total_pts * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(pipe.h2d_bytes),
+           "d2h_bytes_per_step": int(pipe.d2h_bytes), "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "from_pageable_numpy": {"value": total_pts * e2e_steps / e2e_pageable_s, "ms_per_step": 1e3 * e2e_pageable_s / e2e_steps,
+                                   "note": "same loop with ordinary numpy inputs: one more 98.6 MB staging copy per step on host threads"},
+           "api": "muvo_b200.pipeline.HostPipeline.submit/result (inputs in pinned host memory, pinned host out: sparse voxel "
+                  "lists + HWC range images = the returns of voxel_filter / do_range_projection)"}
 
     stages = {}
     if not args.no_stages:

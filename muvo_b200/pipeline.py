@@ -1,7 +1,8 @@
 """Host-buffer front end for stages (a)+(b): the call a data-loading process makes.
 
 ``HostPipeline.submit(points_np, sem_np, frame_offsets_np)`` stages the ragged batch through pinned host
-memory, runs the fused point kernels and copies the reference-facing results back into pinned host
+memory (on a worker thread: ``submit`` returns at once, so the caller's thread is free while the 100 MB staging copy
+runs), runs the fused point kernels and copies the reference-facing results back into pinned host
 buffers: the sparse ``(n,4) uint16`` voxel lists (what ``voxel_filter`` returns) and/or the dense grids,
 and the range images (what ``do_range_projection`` returns).  Two slots are double-buffered over three
 streams (H2D / kernels / D2H), so the copies of batch i+1 overlap the kernels of batch i and the
@@ -13,6 +14,7 @@ read-back moves only about as many rows as there are occupied voxels instead of 
 """
 from __future__ import annotations
 
+from concurrent.futures import ThreadPoolExecutor
 from typing import Optional
 
 import numpy as np
@@ -20,6 +22,13 @@ import torch
 
 from . import _lib
 from .points import GridSpec, RangeSpec, sensor_to_grid
+
+
+def _pinned_view(a, dtype):
+    """``a`` itself when it is a contiguous pinned CPU tensor of ``dtype`` (usable as a DMA source), else None."""
+    if isinstance(a, torch.Tensor) and a.device.type == "cpu" and a.dtype == dtype and a.is_contiguous() and a.is_pinned():
+        return a
+    return None
 
 
 class _Slot:
@@ -33,6 +42,7 @@ class _Slot:
         self.done = None
         self.busy = False
         self.meta = None
+        self.future = None
 
 
 class HostPipeline:
@@ -54,6 +64,7 @@ class HostPipeline:
         self.s_out = torch.cuda.Stream(self.device)
         self.slots = [_Slot() for _ in range(depth)]
         self.queue = []
+        self._worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="muvo_b200_stage")   # keeps batches in order
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         if int(host_threads) <= 0:              # default: the cores of this box shared by the ranks running on it, capped at 16
@@ -84,25 +95,43 @@ class HostPipeline:
             slot.host_out = {k: v for k, v in slot.host_out.items() if k == "voxel_sparse"}
 
     def submit(self, points: np.ndarray, semantics: np.ndarray, frame_offsets: np.ndarray):
-        """Enqueue one ragged batch (host arrays).  Returns immediately; see :meth:`result`."""
+        """Enqueue one ragged batch (host arrays).  Returns immediately; see :meth:`result`.
+
+        The staging copy and the CUDA enqueues run on the pipeline's worker thread, in submission order; the input arrays
+        must stay unchanged until ``result()`` of this batch has returned."""
         slot = next((s for s in self.slots if not s.busy), None)
         if slot is None:
             raise RuntimeError("all pipeline slots are in flight; call result() first")
+        fo = frame_offsets.numpy() if isinstance(frame_offsets, torch.Tensor) else np.asarray(frame_offsets)
+        if fo.ndim != 1 or len(fo) < 1 or int(fo[0]) != 0 or int(fo[-1]) != int(points.shape[0]) or np.any(np.diff(fo) < 0):
+            raise ValueError("frame_offsets must be non-decreasing, start at 0 and end at the number of points")
+        slot.busy = True
+        slot.future = self._worker.submit(self._stage_and_launch, slot, points, semantics, frame_offsets)
+        self.queue.append(slot)
+
+    def _stage_and_launch(self, slot: _Slot, points: np.ndarray, semantics: np.ndarray, frame_offsets: np.ndarray):
+        torch.cuda.set_device(self.device)       # the worker thread starts on device 0 (pinned allocations follow the current device)
         n_pts, n_frames = int(points.shape[0]), int(len(frame_offsets) - 1)
         self._ensure(slot, n_pts, n_frames)
-        # host -> pinned staging (the application's arrays are ordinary pageable memory)
+        # host -> pinned staging for ordinary pageable arrays; inputs that already live in pinned memory
+        # (torch CPU tensors with is_pinned(), e.g. from pinned_inputs()) are the DMA source themselves
         lib = _lib.load()
-        pts_c = np.ascontiguousarray(points, dtype=np.float32)
-        sem_c = np.ascontiguousarray(semantics.reshape(-1), dtype=np.uint8)
-        _lib.check(lib.muvo_host_copy(slot.h_pts.data_ptr(), pts_c.ctypes.data, pts_c.nbytes, self.host_threads), "muvo_host_copy")
-        _lib.check(lib.muvo_host_copy(slot.h_sem.data_ptr(), sem_c.ctypes.data, sem_c.nbytes, self.host_threads), "muvo_host_copy")
-        slot.h_off[:n_frames + 1].numpy()[...] = frame_offsets
+        src_pts, src_sem = _pinned_view(points, torch.float32), _pinned_view(semantics, torch.uint8)
+        if src_pts is None:
+            pts_c = np.ascontiguousarray(points.numpy() if isinstance(points, torch.Tensor) else points, dtype=np.float32)
+            _lib.check(lib.muvo_host_copy(slot.h_pts.data_ptr(), pts_c.ctypes.data, pts_c.nbytes, self.host_threads), "muvo_host_copy")
+            src_pts = slot.h_pts[:n_pts]
+        if src_sem is None:
+            sem_c = np.ascontiguousarray((semantics.numpy() if isinstance(semantics, torch.Tensor) else semantics).reshape(-1), dtype=np.uint8)
+            _lib.check(lib.muvo_host_copy(slot.h_sem.data_ptr(), sem_c.ctypes.data, sem_c.nbytes, self.host_threads), "muvo_host_copy")
+            src_sem = slot.h_sem[:n_pts]
+        slot.h_off[:n_frames + 1].numpy()[...] = frame_offsets.numpy() if isinstance(frame_offsets, torch.Tensor) else frame_offsets
         with torch.cuda.device(self.device):
             if slot.done is not None:
                 self.s_in.wait_event(slot.done)           # previous read-back of this slot finished
             with torch.cuda.stream(self.s_in):
-                slot.d_pts[:n_pts].copy_(slot.h_pts[:n_pts], non_blocking=True)
-                slot.d_sem[:n_pts].copy_(slot.h_sem[:n_pts], non_blocking=True)
+                slot.d_pts[:n_pts].copy_(src_pts.view(n_pts, 3), non_blocking=True)
+                slot.d_sem[:n_pts].copy_(src_sem.view(n_pts), non_blocking=True)
                 slot.d_off[:n_frames + 1].copy_(slot.h_off[:n_frames + 1], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_in)
@@ -136,9 +165,7 @@ class HostPipeline:
                 slot.done = torch.cuda.Event()
                 slot.done.record(self.s_out)
             self.d2h_bytes = nbytes
-        slot.busy = True
         slot.meta = (n_pts, n_frames, rows)
-        self.queue.append(slot)
 
     def result(self) -> dict:
         """Blocks until the oldest submitted batch is back in host memory; returns its pinned host tensors.
@@ -147,6 +174,11 @@ class HostPipeline:
         view as uint16).  The buffers are reused by the next ``submit`` on the same slot.
         """
         slot = self.queue.pop(0)
+        try:
+            slot.future.result()                 # staging + enqueue finished (re-raises what the worker raised)
+        except BaseException:
+            slot.busy = False
+            raise
         slot.done.synchronize()
         if self.sparse and "sparse_start" in slot.host_out:
             n_pts, n_frames, rows = slot.meta
@@ -159,6 +191,13 @@ class HostPipeline:
             self.row_cap = cap if self.row_cap is None else max(self.row_cap, cap)
         slot.busy = False
         return dict(slot.host_out)
+
+    @staticmethod
+    def pinned_inputs(n_points: int, n_frames: int):
+        """Pinned host tensors ``(points (n,3) f32, semantics (n,) u8, frame_offsets (F+1,) i64)`` for the caller to fill
+        (``.numpy()`` gives writable views): batches submitted from them skip the staging copy."""
+        return (torch.empty((n_points, 3), dtype=torch.float32).pin_memory(), torch.empty((n_points,), dtype=torch.uint8).pin_memory(),
+                torch.empty((n_frames + 1,), dtype=torch.int64).pin_memory())
 
     def warmup(self, points: np.ndarray, semantics: np.ndarray, frame_offsets: np.ndarray):
         """Run one batch through EVERY slot so that all pinned / device buffers exist before timing-sensitive use

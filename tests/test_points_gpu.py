@@ -420,6 +420,36 @@ def test_host_pipeline_packed_sparse_and_range(lib):
             assert np.array_equal(r["range_sem"][f].numpy(), s0)
 
 
+def test_host_pipeline_pinned_inputs_skip_staging_and_errors_surface(lib):
+    """Inputs that already live in pinned memory are the DMA source themselves; same results as from numpy.  Inconsistent
+    frame_offsets are rejected by submit(); a failure on the worker thread is re-raised by result()."""
+    from muvo_b200.pipeline import HostPipeline
+    pipe = HostPipeline(dev(), grid=GridSpec(), range_spec=RangeSpec(lidar_position=tuple(LIDAR)), dense=False, sparse=True, layout="hwc")
+    pts, sem, off = _batch(3, 2000, 3000, 2500)
+    ppts, psem, poff = HostPipeline.pinned_inputs(len(pts), len(off) - 1)
+    ppts.numpy()[...] = pts; psem.numpy()[...] = sem; poff.numpy()[...] = off
+    assert ppts.is_pinned()
+    pipe.submit(pts, sem, off)
+    a = {k: v.clone() for k, v in pipe.result().items()}
+    pipe.submit(ppts, psem, poff)
+    b = {k: v.clone() for k, v in pipe.result().items()}
+    assert a.keys() == b.keys()
+    n = int(a["sparse_start"][-1])
+    assert torch.equal(a["voxel_sparse"][:n], b["voxel_sparse"][:n])
+    for k in a:
+        if k != "voxel_sparse":
+            assert torch.equal(a[k], b[k]), k
+    bad = off.copy(); bad[-1] += 5
+    with pytest.raises(ValueError):
+        pipe.submit(pts, sem, bad)                                       # checked on the caller's thread
+    pipe.submit(pts, np.array(["x"] * len(sem)), off)                    # fails on the worker thread (not convertible to uint8)
+    with pytest.raises(Exception):
+        pipe.result()
+    pipe.submit(pts, sem, off)                                           # the pipeline is usable afterwards
+    c = pipe.result()
+    assert torch.equal(c["n_occ"], a["n_occ"])
+
+
 # ------------------------------------------------------------------ N1: camera + LiDAR cloud in front of (a)
 def test_merge_pcd_golden_and_full_size_vs_oracle(golden, lib):
     g = golden("merge.npz")
