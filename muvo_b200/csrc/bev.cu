@@ -85,16 +85,16 @@ k_cell_hist(const int32_t* __restrict__ cell, int B, int64_t n_pts, int n_cells,
   const int32_t* cp = cell + (size_t)b * n_pts;
   const int64_t p0 = (int64_t)wc * kWarpChunk;
   uint32_t kept = 0;
-  for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 8) {
-    int cc[8];
+  for (int r0 = 0; r0 < kWarpChunk / 32; r0 += 16) {
+    int cc[16];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {           // 8 independent loads in flight
+    for (int u = 0; u < 16; ++u) {          // 16 independent loads in flight (the kernel is latency bound: ~6 warps per SM)
       int64_t p = p0 + (r0 + u) * 32 + lane;
       int c = (p < n_pts) ? __ldg(cp + p) : -1;
       cc[u] = (c >= n_cells) ? -1 : c;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 16; ++u) {
       unsigned m = __match_any_sync(0xffffffffu, cc[u]);
       kept += __popc(__ballot_sync(0xffffffffu, cc[u] >= 0));
       if (cc[u] >= 0 && lane == (__ffs(m) - 1)) h[cc[u]] += __popc(m);
