@@ -369,10 +369,13 @@ k_pool_rows(const T* __restrict__ x, int64_t sb, int64_t sc, const int32_t* __re
 //   gathering in cell-sorted order (coalesced stores, no position list)                           1038 us
 //   streaming the row with 16-byte loads next to a dense int32 position map                         644 us
 //   warp-specialised (8 producer warps gather half a row, 8 consumer warps sum the other half)      771 us
+//   one CTA per (row, half of the cells), 64 KB staging, three CTAs per SM                          513 us
 // ncu (profiles/r1_bev_pool_rows_ncu.txt): DRAM 36 % of peak, no unit above 50 %, long-scoreboard stalls.  The gather rate
 // follows the number of WARPS that issue loads (8 warps: half the rate of 16 or 32), not the loads each thread has in
 // flight, so the shared-memory phases cannot be hidden behind the gathers by the same warps and taking warps away from
-// the gathers costs more than the overlap returns.  The fused lift-splat (N2) avoids the problem: it never reads `x`.
+// the gathers costs more than the overlap returns; splitting a row by cells so that several small CTAs share an SM makes
+// every half fetch the sectors it shares with the other one (neighbouring points fall into different cells).  The
+// fused lift-splat (N2) avoids the problem: it never reads `x`.
 constexpr int kPipeThreads = 512;                      // 128 registers per thread: 64 of them hold the row in flight
 constexpr int kPipeItems = 64;                         // kept points per thread: kPipeItems * kPipeThreads = 32768 per row
 
