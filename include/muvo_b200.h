@@ -239,15 +239,16 @@ MUVO_API int muvo_ssc_counts_from_logits(const void* logits, int32_t logits_dtyp
  * losses_out[2 + 4C] float64 (or NULL) additionally receives SemScalLoss, GeoScalLoss and their derivatives
  * d SemScal / d(sum_p[C], nom[C]), d GeoScal / d(sum_p[C], nom[C]), evaluated with the reference's conditions
  * (class skipped when absent, term skipped when outside [0,1], log clamped at -100; NaN where the reference raises).
- * muvo_scal_sums_bwd writes grad_logits [F, C, S] (logits' dtype, fully written) from grad_sums[2C] float32 =
- * d loss / d sum_p[C], d loss / d nom[C] (device pointer; the scalar algebra between the two calls is the caller's).   */
+ * muvo_scal_sums_bwd writes grad_logits [F, C, S] (logits' dtype, fully written) = g_sem * d SemScal / d logits +
+ * g_geo * d GeoScal / d logits, from dloss = losses_out + 2 (the [2, 2C] derivative block of the forward call) and the two
+ * upstream gradients g_sem, g_geo (device float32 scalars; NULL = 0).                                                    */
 MUVO_API int muvo_scal_workspace_bytes(int32_t n_classes, size_t* bytes_out_h);
 MUVO_API int muvo_scal_sums_fwd(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames,
                                 int32_t n_classes, int64_t voxels_per_frame, int32_t ignore_index, double* sums_out,
                                 double* losses_out, void* ws, size_t ws_bytes, void* stream);
 MUVO_API int muvo_scal_sums_bwd(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames,
-                                int32_t n_classes, int64_t voxels_per_frame, int32_t ignore_index, const float* grad_sums,
-                                void* grad_logits, void* stream);
+                                int32_t n_classes, int64_t voxels_per_frame, int32_t ignore_index, const double* dloss,
+                                const float* g_sem, const float* g_geo, void* grad_logits, void* stream);
 
 /* ---- next row N4: the torch_scatter reductions of the PointPillar encoder ---------------------
  * Replaces scatter_mean(xyz, inverse_indices, dim=0) and scatter_max(feat, inverse_indices, dim=0)

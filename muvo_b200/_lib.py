@@ -66,7 +66,7 @@ SIGNATURES = {
     "muvo_ssc_counts_from_logits": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _I32, _P, _P]),
     "muvo_scal_workspace_bytes": (C.c_int, [_I32, C.POINTER(_SZ)]),
     "muvo_scal_sums_fwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _I32, _P, _P, _P, _SZ, _P]),
-    "muvo_scal_sums_bwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _I32, _P, _P, _P]),
+    "muvo_scal_sums_bwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _I32, _P, _P, _P, _P, _P]),
     "muvo_pillar_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(_SZ)]),
     "muvo_pillar_scatter_mean": (C.c_int, [_P, _P, _I32, _I64, _I32, _I64, _P, _P, _P, _SZ, _P, _P]),
     "muvo_pillar_scatter_mean_bwd": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),

@@ -273,10 +273,15 @@ __global__ void k_scal_finish(const double* __restrict__ partial, int n_cta, int
 template <typename LT, int CT, int VEC>
 __global__ void __launch_bounds__(kScalThreads)
 k_scal_bwd(const LT* __restrict__ logits, const uint8_t* __restrict__ target, int F, int64_t S, int ignore,
-           const float* __restrict__ gs, LT* __restrict__ grad) {
+           const double* __restrict__ dl, const float* __restrict__ g_sem, const float* __restrict__ g_geo, LT* __restrict__ grad) {
+  // d loss / d(sum_p, nom) = g_sem * dSemScal + g_geo * dGeoScal (dl = the [2, 2C] block k_scal_finish wrote)
+  const double gs = g_sem ? (double)__ldg(g_sem) : 0.0, gg = g_geo ? (double)__ldg(g_geo) : 0.0;
   float ga[CT], gb[CT];
 #pragma unroll
-  for (int k = 0; k < CT; ++k) { ga[k] = __ldg(gs + k); gb[k] = __ldg(gs + CT + k); }
+  for (int k = 0; k < CT; ++k) {
+    ga[k] = (float)(gs * dl[k] + gg * dl[2 * CT + k]);
+    gb[k] = (float)(gs * dl[CT + k] + gg * dl[3 * CT + k]);
+  }
   const int64_t groups = S / VEC;
   for (int f = blockIdx.y; f < F; f += gridDim.y) {
     const size_t fo = (size_t)f * CT * S;
@@ -309,9 +314,12 @@ k_scal_bwd(const LT* __restrict__ logits, const uint8_t* __restrict__ target, in
 template <typename LT>
 __global__ void __launch_bounds__(kScalThreads)
 k_scal_bwd_any(const LT* __restrict__ logits, const uint8_t* __restrict__ target, int F, int C, int64_t S, int ignore,
-               const float* __restrict__ gs, LT* __restrict__ grad) {
+               const double* __restrict__ dl, const float* __restrict__ g_sem, const float* __restrict__ g_geo, LT* __restrict__ grad) {
   __shared__ float g_s[2 * kScalMaxC];
-  if (threadIdx.x < 2 * C) g_s[threadIdx.x] = gs[threadIdx.x];
+  if (threadIdx.x < 2 * C) {
+    const double gs = g_sem ? (double)__ldg(g_sem) : 0.0, gg = g_geo ? (double)__ldg(g_geo) : 0.0;
+    g_s[threadIdx.x] = (float)(gs * dl[threadIdx.x] + gg * dl[2 * C + threadIdx.x]);
+  }
   __syncthreads();
   for (int f = blockIdx.y; f < F; f += gridDim.y)
     for (int64_t s = (int64_t)blockIdx.x * kScalThreads + threadIdx.x; s < S; s += (int64_t)gridDim.x * kScalThreads) {
@@ -385,17 +393,17 @@ static int launch_scal_fwd(const void* logits, const uint8_t* target, int F, int
 }
 
 template <typename LT>
-static int launch_scal_bwd(const void* logits, const uint8_t* target, int F, int C, int64_t S, int ignore, const float* gs,
-                           void* grad, cudaStream_t st) {
+static int launch_scal_bwd(const void* logits, const uint8_t* target, int F, int C, int64_t S, int ignore, const double* dl,
+                           const float* g_sem, const float* g_geo, void* grad, cudaStream_t st) {
   const LT* lg = (const LT*)logits;
   LT* gr = (LT*)grad;
   const bool v4 = vec4_ok(logits, grad, target, S, sizeof(LT));
   prof_mark("<scal>", st);
   if (C == 2 || C == 9) {
     auto kern = C == 2 ? (v4 ? k_scal_bwd<LT, 2, 4> : k_scal_bwd<LT, 2, 1>) : (v4 ? k_scal_bwd<LT, 9, 4> : k_scal_bwd<LT, 9, 1>);
-    kern<<<scal_grid(kern, 0, F, v4 ? S / 4 : S), kScalThreads, 0, st>>>(lg, target, F, S, ignore, gs, gr);
+    kern<<<scal_grid(kern, 0, F, v4 ? S / 4 : S), kScalThreads, 0, st>>>(lg, target, F, S, ignore, dl, g_sem, g_geo, gr);
   } else {
-    k_scal_bwd_any<LT><<<scal_grid(k_scal_bwd_any<LT>, 0, F, S), kScalThreads, 0, st>>>(lg, target, F, C, S, ignore, gs, gr);
+    k_scal_bwd_any<LT><<<scal_grid(k_scal_bwd_any<LT>, 0, F, S), kScalThreads, 0, st>>>(lg, target, F, C, S, ignore, dl, g_sem, g_geo, gr);
   }
   MUVO_AFTER_LAUNCH("k_scal_bwd", st);
   return MUVO_OK;
@@ -438,16 +446,16 @@ int muvo_scal_sums_fwd(const void* logits, int32_t logits_dtype, const uint8_t* 
 }
 
 int muvo_scal_sums_bwd(const void* logits, int32_t logits_dtype, const uint8_t* target, int32_t n_frames, int32_t n_classes,
-                       int64_t voxels_per_frame, int32_t ignore_index, const float* grad_sums, void* grad_logits,
-                       void* stream) {
+                       int64_t voxels_per_frame, int32_t ignore_index, const double* dloss, const float* g_sem, const float* g_geo,
+                       void* grad_logits, void* stream) {
   if (n_frames < 0 || n_classes <= 0 || n_classes > kScalMaxC || voxels_per_frame < 0) return MUVO_E_ARG;
   if (n_frames == 0 || voxels_per_frame == 0) return MUVO_OK;
-  if (!logits || !target || !grad_sums || !grad_logits) return MUVO_E_NULL;
+  if (!logits || !target || !dloss || !grad_logits) return MUVO_E_NULL;
   cudaStream_t st = (cudaStream_t)stream;
   switch (logits_dtype) {
-    case MUVO_F32:  return launch_scal_bwd<float>(logits, target, n_frames, n_classes, voxels_per_frame, ignore_index, grad_sums, grad_logits, st);
-    case MUVO_F16:  return launch_scal_bwd<__half>(logits, target, n_frames, n_classes, voxels_per_frame, ignore_index, grad_sums, grad_logits, st);
-    case MUVO_BF16: return launch_scal_bwd<__nv_bfloat16>(logits, target, n_frames, n_classes, voxels_per_frame, ignore_index, grad_sums, grad_logits, st);
+    case MUVO_F32:  return launch_scal_bwd<float>(logits, target, n_frames, n_classes, voxels_per_frame, ignore_index, dloss, g_sem, g_geo, grad_logits, st);
+    case MUVO_F16:  return launch_scal_bwd<__half>(logits, target, n_frames, n_classes, voxels_per_frame, ignore_index, dloss, g_sem, g_geo, grad_logits, st);
+    case MUVO_BF16: return launch_scal_bwd<__nv_bfloat16>(logits, target, n_frames, n_classes, voxels_per_frame, ignore_index, dloss, g_sem, g_geo, grad_logits, st);
     default: return MUVO_E_ARG;
   }
 }

@@ -75,12 +75,13 @@ class _ScalLosses(torch.autograd.Function):
         logits, target, losses = ctx.saved_tensors
         F, n_cls, S = (int(v) for v in logits.shape)
         dev = logits.device
-        d = losses[2:].view(2, 2 * n_cls)
-        gs = (g_sem.double() * d[0] + g_geo.double() * d[1]).float().contiguous()
         grad = torch.empty_like(logits)
+        g_sem = g_sem.detach().float().contiguous() if g_sem is not None else None
+        g_geo = g_geo.detach().float().contiguous() if g_geo is not None else None
         with torch.cuda.device(dev):
             rc = _lib.load().muvo_scal_sums_bwd(_lib.ptr(logits), _LOGIT_DTYPES[logits.dtype], _lib.ptr(target), F, n_cls, S,
-                                                ctx.ignore_index, gs.data_ptr(), grad.data_ptr(), _lib.current_stream(dev))
+                                                ctx.ignore_index, losses.data_ptr() + 16, _lib.ptr(g_sem), _lib.ptr(g_geo),
+                                                grad.data_ptr(), _lib.current_stream(dev))
         _lib.check(rc, "muvo_scal_sums_bwd")
         return grad, None, None
 

@@ -43,6 +43,24 @@ elif a.stage == "bev":
     for _ in range(a.steps):
         out = bev_pool(x, cell, 2304)
         torch.autograd.grad(out, x, torch.ones_like(out))
+elif a.stage == "other":        # (d) counts, N4 scal losses fwd + bwd, N2 fused lift-splat fwd + bwd at the bench shapes
+    from muvo_b200.frustum_pooling import lift_splat
+    from muvo_b200.losses import scal_losses
+    from muvo_b200.metrics import ssc_counts
+    yp, yt = synth.occupancy_pair(16, 2, 4000)
+    tp, tt = torch.from_numpy(yp).to(dev), torch.from_numpy(yt).to(dev)
+    logits = torch.randn((1, 16, 2, 192, 192, 64), device=dev).requires_grad_(True)
+    feat, depth, mask, K, E = synth.bev_inputs(6, 384, 3000, device=dev)
+    fp = muvo_b200.FrustumPooling(**synth.BEV_POOL_ARGS).to(dev)
+    fp.initialize_frustum(synth.lift(feat[:1], depth[:1]))
+    cell = fp.cell_ids(fp.get_geometry(E[:, None, :3, :3], E[:, None, :3, 3:], K[:, None]), mask)
+    fl, dl = feat.detach().requires_grad_(True), depth.detach().requires_grad_(True)
+    for _ in range(a.steps):
+        ssc_counts(tp, tt, 2, ignore255=True)
+        sem, geo = scal_losses(logits, tt.view(1, 16, 192, 192, 64))
+        torch.autograd.grad(sem + geo, logits)
+        ol = lift_splat(fl, dl, cell, 2304)
+        torch.autograd.grad(ol, (fl, dl), torch.ones_like(ol))
 else:
     from muvo_b200.metrics import ssc_counts
     yp, yt = synth.occupancy_pair(16, 2, 4000)
