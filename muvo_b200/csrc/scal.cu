@@ -17,6 +17,9 @@
 namespace muvo {
 namespace {
 
+#ifndef MUVO_SCAL_UNR
+#define MUVO_SCAL_UNR 1
+#endif
 constexpr int kScalThreads = 256;
 constexpr int kScalMaxC = 32;
 constexpr int kScalMaxCtas = kNumSMsB200 * 8;
@@ -80,6 +83,12 @@ __device__ __forceinline__ float rcp_fast(float v) {      // den is in [1, C]: M
   return r;
 }
 
+__device__ __forceinline__ float exp_nonpos(float v) {    // exp of v <= 0: ex2.approx on v * log2(e), no range fix-up needed
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v * 1.4426950408889634f));
+  return r;
+}
+
 // softmax over the CT register-resident classes of voxel j (F.softmax in fp32): p[k] = exp(x_k - max) / sum.
 // ex2.approx + one reciprocal: a few ulp from torch's expf / divide, far inside the 1e-5 bar, and a third of the
 // issue slots (the kernels are issue bound at C = 2 otherwise).
@@ -90,7 +99,7 @@ __device__ __forceinline__ void softmax_probs(const float (&x)[CT][VEC], int j, 
   for (int k = 1; k < CT; ++k) m = fmaxf(m, x[k][j]);
   float den = 0.f;
 #pragma unroll
-  for (int k = 0; k < CT; ++k) { p[k] = __expf(x[k][j] - m); den += p[k]; }
+  for (int k = 0; k < CT; ++k) { p[k] = exp_nonpos(x[k][j] - m); den += p[k]; }
   const float inv = rcp_fast(den);
 #pragma unroll
   for (int k = 0; k < CT; ++k) p[k] *= inv;
@@ -131,15 +140,15 @@ k_scal_fwd(const LT* __restrict__ logits, const uint8_t* __restrict__ target, in
 #pragma unroll
         for (int k = 0; k < CT; ++k) { gs[k] = 0.f; gn[k] = 0.f; }
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-          if (t[u][j] == ignore) continue;                 // mask = target != ignore_index (:208, :273)
+        for (int j = 0; j < VEC; ++j) {                     // branch free: selects keep gs / gn / cn in registers
+          const bool valid = t[u][j] != ignore;             // mask = target != ignore_index (:208, :273)
           float p[CT];
           softmax_probs<CT, VEC>(x[u], j, p);
-          ++nv;
+          nv += valid ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < CT; ++k) {                    // selects, not branches: keeps gn / cn in registers
-            const bool hit = t[u][j] == k;
-            gs[k] += p[k];
+          for (int k = 0; k < CT; ++k) {
+            const bool hit = valid && t[u][j] == k;
+            gs[k] += valid ? p[k] : 0.f;
             gn[k] += hit ? p[k] : 0.f;
             cn[k] += hit ? 1u : 0u;
           }
@@ -376,7 +385,7 @@ static int launch_scal_fwd(const void* logits, const uint8_t* target, int F, int
   dim3 grid;
   prof_mark("<scal>", st);
   if (C == 2 || C == 9) {
-    auto kern = C == 2 ? (v4 ? k_scal_fwd<LT, 2, 4, 2> : k_scal_fwd<LT, 2, 1, 2>) : (v4 ? k_scal_fwd<LT, 9, 4, 1> : k_scal_fwd<LT, 9, 1, 1>);
+    auto kern = C == 2 ? (v4 ? k_scal_fwd<LT, 2, 4, MUVO_SCAL_UNR> : k_scal_fwd<LT, 2, 1, MUVO_SCAL_UNR>) : (v4 ? k_scal_fwd<LT, 9, 4, 1> : k_scal_fwd<LT, 9, 1, 1>);
     grid = scal_grid(kern, 0, F, v4 ? S / 4 : S);
     kern<<<grid, kScalThreads, 0, st>>>(lg, target, F, S, ignore, partial);
   } else {
