@@ -450,6 +450,45 @@ def test_host_pipeline_pinned_inputs_skip_staging_and_errors_surface(lib):
     assert torch.equal(c["n_occ"], a["n_occ"])
 
 
+def test_cuda_graph_replay_of_the_point_kernels(lib):
+    """The four kernels are chained by programmatic dependent launch; capturing the call in a CUDA graph and replaying it on
+    new input values (same buffers) must still give the oracle's result, twice in a row (workspace self-cleaning)."""
+    pts, sem, off = _batch(4, 3000, 5000, 2600)
+    pts2, sem2, _ = _batch(4, 3000, 5000, 2700)
+    n = min(len(pts), len(pts2))
+    off = np.array([0, n // 4, n // 2, 3 * n // 4, n], dtype=np.int64)
+    tp, ts, to = torch.from_numpy(pts[:n].copy()).to(dev()), torch.from_numpy(sem[:n].copy()).to(dev()), torch.from_numpy(off).to(dev())
+    out = {}
+
+    def step():
+        r = sensor_to_grid(tp, ts, to, grid=GridSpec(), range_spec=RangeSpec(lidar_position=tuple(LIDAR)), layout="xyzd", out=out)
+        out.update({k: r[k] for k in ("voxel", "n_occ", "range_xyzd", "range_sem")})
+        return r
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        step()
+    for src_p, src_s in ((pts2[:n], sem2[:n]), (pts[:n], sem[:n])):
+        tp.copy_(torch.from_numpy(src_p.copy())); ts.copy_(torch.from_numpy(src_s.copy()))
+        g.replay()
+        torch.cuda.synchronize()
+        for f in range(4):
+            p, s_ = src_p[off[f]:off[f + 1]], src_s[off[f]:off[f + 1]]
+            v0, l0 = O.voxel_filter_fast(p, s_, *GRID)
+            want = O.densify_voxels(np.concatenate([v0, l0[:, None].astype(np.uint16)], 1), (192, 192, 64))
+            assert np.array_equal(out["voxel"][f].cpu().numpy(), want)
+            d0, x0, s0 = O.range_projection(p, s_, lidar_position=LIDAR)
+            assert np.array_equal(out["range_xyzd"][f].cpu().numpy(), O.pack_range_view(d0, x0))
+            assert np.array_equal(out["range_sem"][f].cpu().numpy(), s0)
+
+
 # ------------------------------------------------------------------ N1: camera + LiDAR cloud in front of (a)
 def test_merge_pcd_golden_and_full_size_vs_oracle(golden, lib):
     g = golden("merge.npz")
