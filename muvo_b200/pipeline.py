@@ -210,3 +210,15 @@ class HostPipeline:
     def drain(self):
         while self.queue:
             self.result()
+
+    def close(self):
+        """Finish what is in flight and stop the worker thread."""
+        self.drain()
+        self._worker.shutdown(wait=True)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
