@@ -280,10 +280,15 @@ MUVO_API int muvo_pillar_scatter_max_bwd(const float* grad_out, const void* inde
  * [2] f32-decided points whose pixel differs from the float64 one (must stay 0), [3] dropped (non-finite / at the sensor).
  * muvo_debug_set_tuning: process-wide launch knobs for benchmarking sweeps; key 0 = CTAs per SM of the persistent
  * point pass (0 = as many as fit), key 1 bit 0 = disable the neighbour filter in front of the voxel atomicMax,
- * key 2 = 1 forces the per-point gather kernel of the BEV pool forward (default: streamed rows).                                              */
+ * key 2 = 1 forces the per-point gather kernel of the BEV pool forward (default: streamed rows); key 3 = 1 forces the
+ * multi-launch point path where the single-launch dataflow kernel would be eligible.                                   */
 MUVO_API int muvo_debug_pixel_check(const float* xyz, int64_t n_points, const MuvoRangeCfg* cfg_h, int64_t* counts_out,
                                     void* stream);
 MUVO_API int muvo_debug_set_tuning(int32_t key, int32_t value);
+/* muvo_debug_mega_stats: synchronises the device and copies the per-CTA cycle counters of the dataflow point kernel
+ * (points_mega.cu: 12 uint64 per CTA -- waiting / P / ER / ED / queue / producer waits / unit counts / total) of the first
+ * n_ctas CTAs into out_h (host, may be NULL); reset != 0 zeroes them afterwards.  Counters accumulate over calls.        */
+MUVO_API int muvo_debug_mega_stats(unsigned long long* out_h, int32_t n_ctas, int32_t reset);
 
 #ifdef __cplusplus
 }

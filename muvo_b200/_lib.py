@@ -74,6 +74,7 @@ SIGNATURES = {
     "muvo_pillar_scatter_max_bwd": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
     "muvo_debug_pixel_check": (C.c_int, [_P, _I64, C.POINTER(MuvoRangeCfg), _P, _P]),
     "muvo_debug_set_tuning": (C.c_int, [_I32, _I32]),
+    "muvo_debug_mega_stats": (C.c_int, [_P, _I32, _I32]),
 }
 
 _lib = None

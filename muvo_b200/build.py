@@ -21,8 +21,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 # points.cu reproduces numpy's float64 arithmetic: no FMA contraction allowed there.
 PER_FILE = {"points.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split(),
+            "points_mega.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split(),
             "merge.cu": ["-fmad=false"]}   # MUVO_NVCC_EXTRA: tuning builds only
-SOURCES = ["api.cu", "points.cu", "ssc.cu", "bev.cu", "merge.cu", "pyramid.cu", "scal.cu", "pillar.cu"]
+SOURCES = ["api.cu", "points.cu", "points_mega.cu", "ssc.cu", "bev.cu", "merge.cu", "pyramid.cu", "scal.cu", "pillar.cu"]
 
 
 def _nvcc() -> str:
@@ -42,7 +43,7 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(INCLUDE, "muvo_b200.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "points_dev.cuh"), os.path.join(INCLUDE, "muvo_b200.h")]
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
