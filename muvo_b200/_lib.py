@@ -99,6 +99,10 @@ def load() -> C.CDLL:
             fn.argtypes = args
         if lib.muvo_abi_version() != ABI_VERSION:
             raise MuvoError(f"libmuvo_b200.so ABI {lib.muvo_abi_version()} != expected {ABI_VERSION}; rebuild")
+        # MUVO_TUNING="key=value,..." : debug / benchmarking knobs of muvo_debug_set_tuning, applied once at load
+        for kv in filter(None, os.environ.get("MUVO_TUNING", "").replace(" ", ",").split(",")):
+            k, v = kv.split("=")
+            lib.muvo_debug_set_tuning(int(k), int(v))
         _lib = lib
     return _lib
 

@@ -53,7 +53,7 @@ struct PointsWs {
   u64* pixtab = nullptr;        // [F, H*W]   packed winner per pixel (0 = empty)
   uint32_t* qcount = nullptr;   // [kMaxChunks, kMaxTileCtas, 2] (length, frame of the CTA's first point): rare-path queue length per tile CTA (rewritten by every call)
   uint2* queue = nullptr;       // [2P]       rare-path queue, CTA b's segment starts at 2 * (its first point)
-  uint32_t* sync = nullptr;     // [16 + 5F + 80] ticket counter, per-frame completion counters and the ticket schedule of points_mega.cu
+  uint32_t* sync = nullptr;     // [6F] per-frame claim / completion counters of points_mega.cu
   double* edges = nullptr;      // [2 (W + 1) + H + 1] range-image bin edges (points_mega.cu)
   size_t bytes = 0;
 };
@@ -86,7 +86,7 @@ static PointsWs carve(void* base, int64_t P, int F, const MuvoGrid* g, const Muv
     w.pixtab = (u64*)(b + o); o = align_up(o + (size_t)F * r->H * r->W * 8, 256);
   }
   w.qcount = (uint32_t*)(b + o); o = align_up(o + (size_t)kMaxChunks * kMaxTileCtas * 8, 256);
-  w.sync = (uint32_t*)(b + o); o = align_up(o + ((size_t)5 * F + 96) * 4, 256);
+  w.sync = (uint32_t*)(b + o); o = align_up(o + ((size_t)6 * F + 64) * 4, 256);
   if (r) { w.edges = (double*)(b + o); o = align_up(o + ((size_t)2 * (r->W + 1) + r->H + 1) * 8, 256); }
   w.queue = (uint2*)(b + o); o = align_up(o + (size_t)(P > 0 ? P : 1) * 16, 256);
   w.bytes = o;

@@ -33,7 +33,7 @@ constexpr int kConsumerWarps = 7;
 constexpr int kConsumers = kConsumerWarps * 32;            // 224
 constexpr int kPPT = 8;                                    // points per consumer thread per P unit
 #ifndef MUVO_MEGA_BATCH
-#define MUVO_MEGA_BATCH 4
+#define MUVO_MEGA_BATCH 2
 #endif
 constexpr int kBatch = MUVO_MEGA_BATCH;                    // points per thread whose claims are in flight together
 #ifndef MUVO_MEGA_MINB
@@ -47,7 +47,7 @@ constexpr int kStageBytes = (kTileXyzBytes + kTileSemBytes + 127) / 128 * 128;
 constexpr int kPixUnit = kConsumers * 8;                   // pixels per ER unit (two groups of 4 per thread)
 constexpr int kEdWordsPerBlock = kConsumerWarps * 32 * kEmitWords;   // bitmap words per dense block (448 -> 14 KiB of output)
 constexpr int kEdBlocksPerUnit = 4;
-constexpr int kMaxRing = 64, kDefaultRing = 32;
+constexpr int kMaxRing = 64, kDefaultRing = 16;
 
 enum UnitType { U_POINTS = 0, U_RANGE = 1, U_DENSE = 2, U_DONE = 3 };
 
@@ -68,25 +68,25 @@ struct GridF {
   float inv_res, inv_res2_cls;     // 1/res ; class scale relative to res^2 (see vox_cls_exact)
   float offq[3];
   uint32_t dimu[3];
-  uint32_t tiny_m1;                // bits(tiny) - 1: coordinates in (-tiny, 0) take the float64 path
+  uint32_t tiny_m1[3];             // bits(tiny_k) - 1: a coordinate in (-tiny_k, 0) takes the float64 path
   uint32_t sx, sy;                 // bit = ix*sx + iy*sy + iz
   int road;
 };
 
 struct SyncWs {
-  uint32_t* ticket;    // [1]
-  uint32_t* p_done;    // [F]
-  uint32_t* ready;     // [F]
-  uint32_t* e_done;    // [F]
+  uint32_t* p_claim;   // [F]   P units of the frame handed out so far
+  uint32_t* e_claim;   // [F]   E units handed out so far
+  uint32_t* p_done;    // [F]   warps that finished their share of a P unit
+  uint32_t* ready;     // [F]   1 = all points are in the tables and the queue is settled
+  uint32_t* e_done;    // [F]   warps that finished their share of an E unit
   uint32_t* qn;        // [F]   rare-path queue length of the frame
-  int32_t* base;       // [F + kMaxRing + 1] first ticket of every block
 };
 
 struct MegaArgs {
   const float* xyz; const uint8_t* sem; const int64_t* off; int F; int64_t P;
   GridDev g; GridF gf; RangeDev r; int64_t HW;
   int do_vox, do_range, layout, filter;
-  int R, L, NB, nER, nED;
+  int R, nER, nED;
   uint32_t* bitmap; u64* vtab; u64* pixtab; uint2* queue;
   SyncWs s;
   const uint8_t* remap; uint8_t* dense; int64_t* n_occ;
@@ -96,8 +96,7 @@ struct MegaArgs {
 };
 
 constexpr float kVoxClsScale = 262144.0f;      // 2^18 classes per res^2: f32 key error (< 0.2 class) keeps exact order within +-1 class
-constexpr int kPixClsShift = 5;                // f32 squared range, 18 mantissa bits per class (relative error 3e-7 << 2^-19)
-constexpr uint32_t kVoxTopMax = 0x003fffffu, kPixTopMax = 0x07ffffffu;
+constexpr uint32_t kVoxTopMax = 0x003fffffu;
 constexpr uint32_t kQSlow = 0xffffffffu;       // queue entry .y: the float64 formula decides the cell (else: 1-based index of the in-band holder met)
 constexpr uint32_t kQVoxel = 0x80000000u;      // queue entry .x: frame-relative point index, this bit set for a voxel event
 
@@ -220,7 +219,7 @@ __device__ __forceinline__ VoxF vox_fast32(float x, float y, float z, uint32_t l
   v.top = vox_top_from_cls(cls, (int)lab != g.road);
   v.bit = ix * g.sx + iy * g.sy + iz;
   const uint32_t ux = __float_as_uint(x) - 0x80000001u, uy = __float_as_uint(y) - 0x80000001u, uz = __float_as_uint(z) - 0x80000001u;
-  v.slow = min(ux, min(uy, uz)) < g.tiny_m1;
+  v.slow = (ux < g.tiny_m1[0]) | (uy < g.tiny_m1[1]) | (uz < g.tiny_m1[2]);
   return v;
 }
 // class of an exactly computed |p mod res|^2 (float64 path): same scale as vox_fast32
@@ -229,15 +228,23 @@ __device__ __forceinline__ uint32_t vox_cls_exact(double dis, const GridF& g) {
   return c < 4194303.0 ? (uint32_t)c : 4194303u;
 }
 
-struct PixF { uint32_t pix, top; bool slow; };
-__device__ __forceinline__ uint32_t pix_top_from_s(float s) { return kPixTopMax - (__float_as_uint(s) >> kPixClsShift); }
-// f32 squared range as the hot loop computes it (also re-derived for a competitor by the queue code)
+// Pixel words: [inverted top bits of the float64 squared range | inverted 1-based index], 40 | 24 bits for frames with
+// fewer than 2^24 - 1 points (`packl`), else 32 | 32.  The class is an exact truncation of the reference's key (the depth
+// orders like its square), so two words only need the exact protocol when their class bits are EQUAL.
+struct PixF { uint32_t pix; u64 word; bool slow; };
+__device__ __forceinline__ u64 pix_word(double s64, uint32_t me1, bool packl) {
+  const u64 inv = ~(u64)__double_as_longlong(s64);
+  return packl ? ((inv & ~0xffffffull) | (u64)((~me1) & 0xffffffu)) : ((inv & ~0xffffffffull) | (u64)(uint32_t)(~me1));
+}
+__device__ __forceinline__ u64 pix_cls(u64 w, bool packl) { return packl ? (w >> 24) : (w >> 32); }
+__device__ __forceinline__ uint32_t pix_idx1(u64 w, bool packl) { return packl ? ((~(uint32_t)w) & 0xffffffu) : ~(uint32_t)w; }
+// f32 squared range as the hot loop computes it (magnitude test only)
 __device__ __forceinline__ float range_s32(float x, float y, float z, const RangeDev& r, float* xf_o, float* yf_o, float* zf_o) {
   const float xf = x - r.Lf[0], yf = -((-y) - r.Lf[1]), zf = z - r.Lf[2];   // same zero signs as geometry_utils.py:177-183
   *xf_o = xf; *yf_o = yf; *zf_o = zf;
   return __fmaf_rn(zf, zf, __fmaf_rn(xf, xf, __fmul_rn(yf, yf)));
 }
-__device__ __forceinline__ PixF pix_fast32(float x, float y, float z, const RangeDev& r) {
+__device__ __forceinline__ PixF pix_fast32(float x, float y, float z, uint32_t me1, bool packl, const RangeDev& r) {
   PixF k;
   float xf, yf, zf;
   const float s = range_s32(x, y, z, r, &xf, &yf, &zf);
@@ -245,13 +252,14 @@ __device__ __forceinline__ PixF pix_fast32(float x, float y, float z, const Rang
   pix_coords_f32(xf, yf, zf, r, &pw, &ph);
   const float fw = floorf(pw), fh = floorf(ph);
   const bool safe_w = fabsf((pw - fw) - 0.5f) < r.safe_w, safe_h = fabsf((ph - fh) - 0.5f) < r.safe_h;
-  // 1e-12 < s < 1e12 (metres^2): inside, no f32 square over/underflows in a way that could move a pixel or a class
+  // 1e-12 < s < 1e12 (metres^2): inside, no f32 square over/underflows in a way that could move a pixel
   const bool mag_ok = (__float_as_uint(s) - 0x2b8cbcccu) < (0x5368d4a5u - 0x2b8cbcccu);
   k.slow = !(safe_w & safe_h & mag_ok);     // NaN compares false -> slow
   const int iw = (int)fminf(fmaxf(fw, 0.0f), r.w_max);
   const int ih = (int)fminf(fmaxf(fh, 0.0f), r.h_max);
   k.pix = (uint32_t)(ih * r.W + iw);
-  k.top = pix_top_from_s(s);
+  double xc, yc, zc;
+  k.word = pix_word(range_sq_of(x, y, z, r, &xc, &yc, &zc), me1, packl);      // float64, numpy's order (geometry_utils.py:177-180)
   return k;
 }
 
@@ -343,13 +351,14 @@ __device__ __forceinline__ void unit_points(const MegaArgs& a, const UnitDesc& d
   const uint64_t pol = l2_evict_last_policy();
 #pragma unroll
   for (int h = 0; h < kPPT / kBatch; ++h) {
-    uint32_t vcell[kBatch], vtop[kBatch], pcell[kBatch], ptop[kBatch];
+    uint32_t vcell[kBatch], vtop[kBatch], pcell[kBatch];
+    u64 pword[kBatch];
     bool undecided = false;
 #pragma unroll
     for (int k = 0; k < kBatch; ++k) {
       const int kk = h * kBatch + k;
       const float x = sx[3 * kk * kConsumers], y = sx[3 * kk * kConsumers + 1], z = sx[3 * kk * kConsumers + 2];
-      vcell[k] = kCellNone; pcell[k] = kCellNone; vtop[k] = 0u; ptop[k] = 0u;
+      vcell[k] = kCellNone; pcell[k] = kCellNone; vtop[k] = 0u; pword[k] = 0ull;
       if (DO_VOX) {
         const VoxF v = vox_fast32(x, y, z, ss[kk * kConsumers], a.gf);
         vtop[k] = v.top;
@@ -357,8 +366,8 @@ __device__ __forceinline__ void unit_points(const MegaArgs& a, const UnitDesc& d
         if (v.slow) vcell[k] = kCellSlow;
       }
       if (DO_RANGE) {
-        const PixF p = pix_fast32(x, y, z, a.r);
-        ptop[k] = p.top;
+        const PixF p = pix_fast32(x, y, z, rel0 + kk * kConsumers + 1u, packl, a.r);
+        pword[k] = p.word;
         pcell[k] = p.slow ? kCellSlow : p.pix;
       }
       if (!FULL && !(ct + kk * kConsumers < d.n)) { vcell[k] = kCellNone; pcell[k] = kCellNone; }   // the frame's last, partial unit
@@ -385,7 +394,7 @@ __device__ __forceinline__ void unit_points(const MegaArgs& a, const UnitDesc& d
         const uint32_t lo = packl ? nme * 256u + ss[(h * kBatch + k) * kConsumers] : nme;
         vold[k] = atom_max_if(vtab_s, vcell[k], ((u64)vtop[k] << 32) | lo, ~0ull, pol);
       }
-      if (DO_RANGE) pold[k] = atom_max_if(pixtab_s, pcell[k], ((u64)ptop[k] << 32) | nme, ~0ull, pol);
+      if (DO_RANGE) pold[k] = atom_max_if(pixtab_s, pcell[k], pword[k], ~0ull, pol);
     }
     bool band = false;
 #pragma unroll
@@ -394,14 +403,14 @@ __device__ __forceinline__ void unit_points(const MegaArgs& a, const UnitDesc& d
         red_or_if(bitmap_s, vcell[k], word_top(vold[k]) == 0u, pol);    // first claim marks the voxel occupied
         band |= in_band(word_top(vold[k]), vtop[k]);
       }
-      if (DO_RANGE) band |= in_band(word_top(pold[k]), ptop[k]);
+      if (DO_RANGE) band |= pix_cls(pold[k] ^ pword[k], packl) == 0ull;
     }
     if (band) {
 #pragma unroll
       for (int k = 0; k < kBatch; ++k) {
         const uint32_t rel = rel0 + (h * kBatch + k) * kConsumers;
         if (DO_VOX && in_band(word_top(vold[k]), vtop[k])) queue_push_cold(q, qn, rel | kQVoxel, vox_word_idx1(packl, vold[k]));
-        if (DO_RANGE && in_band(word_top(pold[k]), ptop[k])) queue_push_cold(q, qn, rel, word_idx1(pold[k]));
+        if (DO_RANGE && pix_cls(pold[k] ^ pword[k], packl) == 0ull) queue_push_cold(q, qn, rel, pix_idx1(pold[k], packl));
       }
     }
   }
@@ -412,8 +421,9 @@ __device__ __forceinline__ void unit_points(const MegaArgs& a, const UnitDesc& d
 // the slot ends up holding a point that is exactly <= cand, or one whose class is better by 2 or more (which is then
 // exactly better as well).  Every point that displaced, or failed to displace, an in-band holder runs this, so the final
 // holder is the exact arg-min with the lowest index among equal keys.
-template <typename KeyFn, typename PackFn, typename IdxFn>
-__device__ __noinline__ void band_protocol(u64* slot, uint32_t me1, uint32_t partner1, KeyFn key_of, PackFn pack_of, IdxFn idx_of) {
+template <typename KeyFn, typename PackFn, typename IdxFn, typename ClsFn>
+__device__ __noinline__ void band_protocol(u64* slot, uint32_t me1, uint32_t partner1, KeyFn key_of, PackFn pack_of, IdxFn idx_of,
+                                           ClsFn cls_of, u64 margin) {
   uint32_t cand1 = me1;
   u64 ck = key_of(me1);
   {
@@ -423,7 +433,7 @@ __device__ __noinline__ void band_protocol(u64* slot, uint32_t me1, uint32_t par
   const u64 cw = pack_of(cand1);
   u64 cur = ld_cg_u64(slot);
   for (;;) {
-    if (word_top(cur) >= word_top(cw) + 2u) break;
+    if (cls_of(cur) >= cls_of(cw) + margin) break;        // a class that is certainly better holds the slot
     const uint32_t h1 = idx_of(cur);
     if (h1 == cand1) break;
     const u64 hk = key_of(h1);
@@ -484,10 +494,9 @@ __device__ __noinline__ void drain_queue(const MegaArgs& a, const UnitDesc& d) {
       if (flags & 4) { ++n_drop; }
       else {
         n_nw += (flags & 1) ? 1u : 0u; n_nh += (flags & 2) ? 1u : 0u;
-        float xf, yf, zf;
-        const uint32_t top = pix_top_from_s(range_s32(x, y, z, r, &xf, &yf, &zf));
-        const u64 old = atom_max_global(pixtab_s + (ih * r.W + iw), pack_word(top, me1));
-        if (old != 0ull && in_band(word_top(old), top)) partner = word_idx1(old);
+        const u64 mine = pix_word(s, me1, packl);
+        const u64 old = atom_max_global(pixtab_s + (ih * r.W + iw), mine);
+        if (old != 0ull && pix_cls(old ^ mine, packl) == 0ull) partner = pix_idx1(old, packl);
       }
     }
     q[e] = make_uint2(ent.x, partner);      // 0 = settled
@@ -520,10 +529,11 @@ __device__ __noinline__ void drain_queue(const MegaArgs& a, const UnitDesc& d) {
         return vox_word(packl, vox_top_of(q1, o), q1, packl ? (uint32_t)__ldg(fs + (q1 - 1u)) : 0u);
       };
       auto idx_of = [&](u64 wv) -> uint32_t { return vox_word_idx1(packl, wv); };
-      band_protocol(vtab_s + v.bit, me1, ent.y, key_of, pack_of, idx_of);
+      auto cls_of = [](u64 wv) -> u64 { return wv >> 32; };
+      band_protocol(vtab_s + v.bit, me1, ent.y, key_of, pack_of, idx_of, cls_of, 2ull);
     } else {
       // the pixel: f32 path unless this point itself was decided by the float64 formula (then it is recomputed exactly)
-      const PixF pf = pix_fast32(x, y, z, r);
+      const PixF pf = pix_fast32(x, y, z, me1, packl, r);
       uint32_t pix = pf.pix;
       if (pf.slow && (pix = pix_refine(x, y, z, r, a.edges)) == kCellSlow) {
         double xc, yc, zc;
@@ -540,11 +550,12 @@ __device__ __noinline__ void drain_queue(const MegaArgs& a, const UnitDesc& d) {
       };
       auto pack_of = [&](uint32_t q1) -> u64 {
         const float* p = fx + 3 * (int64_t)(q1 - 1u);
-        float xf, yf, zf;
-        return pack_word(pix_top_from_s(range_s32(__ldg(p), __ldg(p + 1), __ldg(p + 2), r, &xf, &yf, &zf)), q1);
+        double aa, bb, cc;
+        return pix_word(range_sq_of(__ldg(p), __ldg(p + 1), __ldg(p + 2), r, &aa, &bb, &cc), q1, packl);
       };
-      auto idx_of = [](u64 wv) -> uint32_t { return word_idx1(wv); };
-      band_protocol(pixtab_s + pix, me1, ent.y, key_of, pack_of, idx_of);
+      auto idx_of = [&](u64 wv) -> uint32_t { return pix_idx1(wv, packl); };
+      auto cls_of = [&](u64 wv) -> u64 { return pix_cls(wv, packl); };
+      band_protocol(pixtab_s + pix, me1, ent.y, key_of, pack_of, idx_of, cls_of, 1ull);
     }
   }
   if (ct == 0) stat_add(18, clock64() - td0);
@@ -566,6 +577,7 @@ __device__ __forceinline__ void unit_emit_range(const MegaArgs& a, const UnitDes
   const float* fx = a.xyz + 3 * d.fbeg;
   const uint8_t* fs = a.sem + d.fbeg;
   const uint64_t pol = l2_evict_last_policy();
+  const bool packl = d.packl != 0;
   u64 wv[2][4];
   int64_t pin[2];
 #pragma unroll
@@ -588,7 +600,7 @@ __device__ __forceinline__ void unit_emit_range(const MegaArgs& a, const UnitDes
     for (int k = 0; k < 4; ++k) {
       px[k] = py[k] = pz[k] = 0.f; pd[k] = -1.f;                 // geometry_utils.py:210-212 initial values
       if (wv[gq][k]) {
-        const int64_t qi = (int64_t)(word_idx1(wv[gq][k]) - 1u);
+        const int64_t qi = (int64_t)(pix_idx1(wv[gq][k], packl) - 1u);
         const float x = __ldg(fx + 3 * qi), y = __ldg(fx + 3 * qi + 1), z = __ldg(fx + 3 * qi + 2);
         double aa, bb, cc;
         pd[k] = (float)range_depth_of(x, y, z, r, &aa, &bb, &cc);   // :217 float32(depth64)
@@ -714,15 +726,11 @@ __device__ __forceinline__ void unit_emit_dense(const MegaArgs& a, const UnitDes
   if (a.n_occ && occ && lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.n_occ + d.f), (unsigned long long)occ);
 }
 
-// ---------------------------------------------------------------- schedule (one CTA)
-// Block b of the ticket sequence = [E units of frame b - L] [P units of frame b]; base[b] = its first ticket.
+// ---------------------------------------------------------------- per-call initialisation (one CTA)
 __global__ void __launch_bounds__(1024)
-k_mega_schedule(const int64_t* __restrict__ off, int F, int L, int NB, int nE, SyncWs s, int64_t* __restrict__ n_occ,
-                double* __restrict__ edges, int H, int W, double fda, double fov) {
-  __shared__ uint32_t wsum[32];
-  __shared__ uint32_t carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { carry_s = 0u; *s.ticket = 0u; }
+k_mega_init(const int64_t* __restrict__ off, int F, SyncWs s, int64_t* __restrict__ n_occ, double* __restrict__ edges, int H, int W,
+            double fda, double fov) {
+  const int tid = threadIdx.x;
   if (edges) {                                                    // bin edges of the range image (pix_refine)
     for (int e = tid; e <= W; e += 1024) {
       const double th = kPi * (1.0 - 2.0 * (double)e / (double)W);
@@ -731,30 +739,9 @@ k_mega_schedule(const int64_t* __restrict__ off, int F, int L, int NB, int nE, S
     for (int e = tid; e <= H; e += 1024) edges[2 * (W + 1) + e] = sin(fov * (1.0 - (double)e / (double)H) - fda);
   }
   for (int f = tid; f < F; f += 1024) {
-    s.p_done[f] = 0u; s.e_done[f] = 0u; s.qn[f] = 0u;
+    s.p_claim[f] = 0u; s.e_claim[f] = 0u; s.p_done[f] = 0u; s.e_done[f] = 0u; s.qn[f] = 0u;
     s.ready[f] = (off[f + 1] - off[f]) > 0 ? 0u : 1u;             // a frame without points has nothing to wait for
     if (n_occ) n_occ[f] = 0;
-  }
-  __syncthreads();
-  for (int b0 = 0; b0 <= NB; b0 += 1024) {
-    const int b = b0 + tid;
-    uint32_t v = 0;
-    if (b < NB) {
-      if (b < F) { const int64_t n = off[b + 1] - off[b]; v += n > 0 ? (uint32_t)((n + kUnit - 1) / kUnit) : 0u; }
-      if (b - L >= 0 && b - L < F) v += (uint32_t)nE;
-    }
-    uint32_t incl = v;
-#pragma unroll
-    for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, dd); if (lane >= dd) incl += t; }
-    if (lane == 31) wsum[warp] = incl;
-    __syncthreads();
-    const uint32_t carry = carry_s;
-    uint32_t wbase = 0;
-    for (int w = 0; w < warp; ++w) wbase += wsum[w];
-    __syncthreads();
-    if (b <= NB) s.base[b] = (int32_t)(carry + wbase + incl - v);
-    if (tid == 1023) carry_s = carry + wbase + incl;
-    __syncthreads();
   }
 }
 
@@ -769,59 +756,75 @@ __device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t need) {
   while (ld_acquire_u32(p) < need) __nanosleep(64);
 }
 
-// Producer warp: draws tickets, waits for what the unit depends on, stages point tiles.
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Producer warp.  Work is claimed per frame and only once it can run: an emit unit of the oldest frame whose points are
+// all in (emits free table slots, so they go first), else a P unit of the oldest frame whose table slot has been emitted
+// and cleared (frame f uses slot f % R, i.e. waits for the emits of frame f - R).  Nothing is ever held while it waits for
+// somebody else, so the scheme cannot deadlock, and at most R frames are in flight.
 __device__ __forceinline__ void producer_loop(const MegaArgs& a, unsigned char* smem) {
   UnitDesc* desc = reinterpret_cast<UnitDesc*>(smem + kSmemDesc);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   uint64_t* empty = full + kStages;
   const unsigned lane = lane_id();
-  const int nE = a.nER + a.nED;
-  const uint32_t total = (uint32_t)__ldg(a.s.base + a.NB);
-  int b = 0;
+  const uint32_t nE = (uint32_t)(a.nER + a.nED);
+  int fe = 0, fp = 0;                                            // first frame that may still have E / P units to hand out
   for (uint32_t it = 0;; ++it) {
     const int s = (int)(it & 1u);
     long long tp0 = clock64();
     if (it >= (uint32_t)kStages) mbar_wait(empty + s, ((it >> 1) - 1u) & 1u);
     if (lane == 0) stat_add(5, clock64() - tp0);
-    uint32_t T = 0;
-    if (lane == 0) T = atomicAdd(a.s.ticket, 1u);
-    T = __shfl_sync(0xffffffffu, T, 0);
+    // ---- lane 0 claims a unit: type (U_DONE = everything has been handed out), frame, index
+    int type = U_DONE, uf = 0, uj = 0;
+    if (lane == 0) {
+      tp0 = clock64();
+      for (;;) {
+        bool got = false;
+        for (int f = fe; f < a.F; ++f) {                         // emits, oldest frame first
+          if (ld_relaxed_u32(a.s.e_claim + f) >= nE) { if (f == fe) ++fe; continue; }
+          if (ld_acquire_u32(a.s.ready + f) == 0u) break;
+          const uint32_t t = atomicAdd(a.s.e_claim + f, 1u);
+          if (t < nE) { type = t < (uint32_t)a.nER ? U_RANGE : U_DENSE; uf = f; uj = (int)(t < (uint32_t)a.nER ? t : t - a.nER); got = true; break; }
+        }
+        if (got) break;
+        if (fe >= a.F) break;                                    // all emits handed out: done
+        for (int f = fp; f < a.F && f < fe + a.R; ++f) {         // points, oldest frame first; its slot must be free
+          const int64_t n = __ldg(a.off + f + 1) - __ldg(a.off + f);
+          const uint32_t nP = n > 0 ? (uint32_t)((n + kUnit - 1) / kUnit) : 0u;
+          if (ld_relaxed_u32(a.s.p_claim + f) >= nP) { if (f == fp) ++fp; continue; }
+          if (f >= a.R && ld_acquire_u32(a.s.e_done + (f - a.R)) < nE * kConsumerWarps) break;
+          const uint32_t t = atomicAdd(a.s.p_claim + f, 1u);
+          if (t < nP) { type = U_POINTS; uf = f; uj = (int)t; got = true; break; }
+        }
+        if (got) break;
+        __nanosleep(200);
+      }
+      stat_add(6, clock64() - tp0);
+    }
+    type = __shfl_sync(0xffffffffu, type, 0); uf = __shfl_sync(0xffffffffu, uf, 0); uj = __shfl_sync(0xffffffffu, uj, 0);
     UnitDesc& d = *reinterpret_cast<UnitDesc*>(reinterpret_cast<unsigned char*>(desc) + s * 64);
-    if (T >= total) {
+    if (type == U_DONE) {
       if (lane == 0) { d.type = U_DONE; mbar_arrive(full + s); }
       break;
     }
-    while ((uint32_t)__ldg(a.s.base + b + 1) <= T) ++b;
-    const int local = (int)(T - (uint32_t)__ldg(a.s.base + b));
-    const int fE = b - a.L;
-    const int nE_b = (fE >= 0 && fE < a.F) ? nE : 0;
     unsigned char* tile = smem + s * kStageBytes;
-    if (local < nE_b) {                                          // an emit unit of frame fE
-      const int64_t fbeg = __ldg(a.off + fE), fend = __ldg(a.off + fE + 1);
+    const int64_t fbeg = __ldg(a.off + uf), fend = __ldg(a.off + uf + 1);
+    if (type != U_POINTS) {
       if (lane == 0) {
-        tp0 = clock64();
-        spin_until(a.s.ready + fE, 1u);                          // all points of the frame are in the tables, queue settled
-        stat_add(6, clock64() - tp0);
-        d.type = local < a.nER ? U_RANGE : U_DENSE;
-        d.j = local < a.nER ? local : local - a.nER;
-        d.f = fE; d.slot = fE % a.R; d.fbeg = fbeg; d.packl = (fend - fbeg) < kPackLimit ? 1 : 0;
+        d.type = type; d.j = uj; d.f = uf; d.slot = uf % a.R; d.fbeg = fbeg; d.packl = (fend - fbeg) < kPackLimit ? 1 : 0;
         d.n = 0; d.lead = 0; d.a = fbeg; d.n_units = 0;
         mbar_arrive(full + s);
       }
-    } else {                                                     // a P unit of frame b
-      const int f = b, j = local - nE_b;
-      const int64_t fbeg = __ldg(a.off + f), fend = __ldg(a.off + f + 1);
-      const int64_t pa = fbeg + (int64_t)j * kUnit;
+    } else {
+      const int64_t pa = fbeg + (int64_t)uj * kUnit;
       const int64_t pb = pa + kUnit < fend ? pa + kUnit : fend;
       const int64_t a0 = pa & ~(int64_t)15;                      // the bulk copies start and end on multiples of 16 points
       const int64_t body_end = (pb & ~(int64_t)15) > a0 ? (pb & ~(int64_t)15) : a0;
       const uint32_t nb = (uint32_t)(body_end - a0);
-      if (lane == 0 && f >= a.R) {
-        tp0 = clock64();
-        spin_until(a.s.e_done + (f - a.R), (uint32_t)nE * kConsumerWarps);   // the table slot has been emitted and cleared
-        stat_add(7, clock64() - tp0);
-      }
-      __syncwarp();
       // the last (< 16) points of the unit, which a 16-byte granular copy cannot fetch without reading past the frame
       const int64_t tp = body_end + lane;
       if (tp < pb) {
@@ -831,7 +834,7 @@ __device__ __forceinline__ void producer_loop(const MegaArgs& a, unsigned char* 
       }
       __syncwarp();
       if (lane == 0) {
-        d.type = U_POINTS; d.f = f; d.j = j; d.slot = f % a.R; d.fbeg = fbeg; d.a = pa;
+        d.type = U_POINTS; d.f = uf; d.j = uj; d.slot = uf % a.R; d.fbeg = fbeg; d.a = pa;
         d.n = (int)(pb - pa); d.lead = (int)(pa - a0); d.packl = (fend - fbeg) < kPackLimit ? 1 : 0;
         d.n_units = (int)((fend - fbeg + kUnit - 1) / kUnit);
         if (nb) {
@@ -966,30 +969,31 @@ int points_mega_f32(const float* xyz, const uint8_t* sem, const int64_t* off, in
     a.g = *g;
     a.gf.inv_res = (float)g->inv_res;
     a.gf.inv_res2_cls = (float)(g->inv_res * g->inv_res * (double)kVoxClsScale);
-    double omax = 0.0;
-    for (int k = 0; k < 3; ++k) { a.gf.offq[k] = (float)(g->off[k] * g->inv_res); if (fabs(g->off[k]) > omax) omax = fabs(g->off[k]); }
+    for (int k = 0; k < 3; ++k) {
+      a.gf.offq[k] = (float)(g->off[k] * g->inv_res);
+      // p + off is exact in float64 when the lowest bit of p (>= |p| 2^-23) is no more than 52 binary places below the top bit
+      // of the sum: |p| >= 2^(e_off - 28) for an offset with at most 22 significant bits; x2 margin; denormals always slow
+      int e = 0;
+      frexp(fabs(g->off[k]), &e);                                  // |off| in [2^(e-1), 2^e)
+      float tiny = g->off[k] != 0.0 ? (float)ldexp(1.0, e - 1 - 28 + 1) : 0.f;
+      if (!(tiny > 1e-30f)) tiny = 1e-30f;
+      uint32_t tb; memcpy(&tb, &tiny, 4);
+      a.gf.tiny_m1[k] = tb - 1u;
+    }
     a.gf.dimu[0] = (uint32_t)g->dx; a.gf.dimu[1] = (uint32_t)g->dy; a.gf.dimu[2] = (uint32_t)g->dz;
-    // p + offset is exact in float64 for |p| >= |offset| * 2^-26 (see the kernel header); denormals always take the slow path
-    float tiny = (float)(omax * 1.4901161193847656e-08 * 1.0000002);
-    if (!(tiny > 1e-30f)) tiny = 1e-30f;
-    uint32_t tb; memcpy(&tb, &tiny, 4);
-    a.gf.tiny_m1 = tb - 1u;
     a.gf.sx = g->sx; a.gf.sy = g->sy;
     a.gf.road = g->road;
   }
   if (r) { a.r = *r; a.HW = (int64_t)r->H * r->W; }
-  // ring of table slots and lag (in frames) between a frame's points and its emits; tuning keys 4 / 5 override
+  // ring of table slots = frames in flight; tuning key 4 overrides
   int ring = g_tuning[4] > 0 ? g_tuning[4] : kDefaultRing;
   if (ring > kMaxRing) ring = kMaxRing;
   a.R = F < ring ? F : ring;
-  a.L = a.R / 2 > 1 ? a.R / 2 : 1;
-  if (g_tuning[5] > 0 && g_tuning[5] < a.R) a.L = g_tuning[5];
-  a.NB = F + a.L;
   a.nER = r ? (int)ceil_div64(a.HW, kPixUnit) : 0;
   a.nED = g ? (int)ceil_div64(ceil_div64(g->gw, kEdWordsPerBlock), kEdBlocksPerUnit) : 0;
   a.bitmap = w.bitmap; a.vtab = w.vtab; a.pixtab = w.pixtab; a.queue = w.queue;
-  a.s.ticket = w.sync; a.s.p_done = w.sync + 16; a.s.ready = a.s.p_done + F; a.s.e_done = a.s.ready + F; a.s.qn = a.s.e_done + F;
-  a.s.base = reinterpret_cast<int32_t*>(a.s.qn + F);
+  a.s.p_claim = w.sync; a.s.e_claim = a.s.p_claim + F; a.s.p_done = a.s.e_claim + F; a.s.ready = a.s.p_done + F;
+  a.s.e_done = a.s.ready + F; a.s.qn = a.s.e_done + F;
   a.remap = remap; a.dense = dense; a.n_occ = n_occ; a.depth_out = depth_out; a.xyz_out = xyz_out; a.sem_out = sem_out;
   a.diag = diag; a.edges = w.edges;
 
@@ -1012,9 +1016,25 @@ int points_mega_f32(const float* xyz, const uint8_t* sem, const int64_t* off, in
   if (grid > max_units) grid = max_units;
   if (grid < 1) grid = 1;
 
-  k_mega_schedule<<<1, 1024, 0, st>>>(off, F, a.L, a.NB, a.nER + a.nED, a.s, n_occ, w.edges, r ? r->H : 0, r ? r->W : 0,
-                                      r ? r->fda : 0.0, r ? r->fov : 1.0);
-  MUVO_AFTER_LAUNCH("k_mega_schedule", st);
+  // The evict_last hints on the table accesses only pin lines inside the persisting-L2 carve-out: reserve it once per device
+  // (tuning key 7 = MB, default 48, negative = leave the device setting alone).
+  {
+    static int done_for_device[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 && done_for_device[dev] != g_tuning[7] + 1) {
+      done_for_device[dev] = g_tuning[7] + 1;
+      if (g_tuning[7] >= 0) {
+        int max_persist = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        size_t want = (size_t)(g_tuning[7] > 0 ? g_tuning[7] : 48) << 20;
+        if (want > (size_t)max_persist) want = (size_t)max_persist;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+        cudaGetLastError();
+      }
+    }
+  }
+  k_mega_init<<<1, 1024, 0, st>>>(off, F, a.s, n_occ, w.edges, r ? r->H : 0, r ? r->W : 0, r ? r->fda : 0.0, r ? r->fov : 1.0);
+  MUVO_AFTER_LAUNCH("k_mega_init", st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = kMegaSmemBytes; cfg.stream = st;
   cudaLaunchAttribute attr[1];

@@ -71,9 +71,9 @@ def test_workspace_size_and_argument_errors(lib):
     assert lib.muvo_points_workspace_bytes(100000, 1, C.byref(g), C.byref(r), C.byref(n)) == 0
     # bitmap (G/8) + chunk prefix (G/32) + voxel winner table (8 B/voxel) + pixel table (8 B/px)
     # + queue length / first-frame slots (32 KiB) + rare-path queue (16 B/pt)
-    # + dataflow kernel: ticket schedule / completion counters ((5 F + 96) * 4 B) and range-image bin edges ((2 (W + 1) + H + 1) * 8 B)
+    # + dataflow kernel: per-frame claim / completion counters ((6 F + 64) * 4 B) and range-image bin edges ((2 (W + 1) + H + 1) * 8 B)
     G = 192 * 192 * 64
-    need = G // 8 + G // 32 + 8 * G + 8 * 64 * 1024 + 32768 + 16 * 100000 + (5 + 96) * 4 + (2 * 1025 + 65) * 8
+    need = G // 8 + G // 32 + 8 * G + 8 * 64 * 1024 + 32768 + 16 * 100000 + (6 + 64) * 4 + (2 * 1025 + 65) * 8
     assert need <= n.value < need + 4096
     assert lib.muvo_points_workspace_bytes(-1, 1, C.byref(g), C.byref(r), C.byref(n)) == -2
     assert lib.muvo_points_workspace_bytes(10, 1, C.byref(g), C.byref(r), None) == -1

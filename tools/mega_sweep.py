@@ -20,7 +20,6 @@ def step():
 for cfg in sys.argv[1:] or [""]:
     for k in range(8):
         lib.muvo_debug_set_tuning(k, 0)
-    lib.muvo_debug_set_tuning(3, 2)
     for kv in cfg.split():
         k, v = kv.split("=")
         lib.muvo_debug_set_tuning(int(k), int(v))
