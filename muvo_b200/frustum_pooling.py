@@ -244,10 +244,9 @@ def quick_cumsum(x, geom_feats, ranks):
 
 
 def cumsum_trick(x, geom_feats, ranks):
-    """Eval-mode twin (frustum_pooling.py:23-31): identical values, no autograd bookkeeping needed."""
-    with torch.no_grad():
-        xs, gs = QuickCumsum.apply(x, geom_feats, ranks)
-    return xs, gs
+    """``cumsum_trick`` (frustum_pooling.py:23-31): same values as ``QuickCumsum`` and, like the reference's plain-torch
+    version (used in training when ``use_quickcumsum=False``, :176-178), differentiable in ``x``."""
+    return QuickCumsum.apply(x, geom_feats, ranks)
 
 
 # --------------------------------------------------------------------------- the module

@@ -10,31 +10,80 @@ _saved: list = []
 
 
 def _swap(obj, name, new):
-    if hasattr(obj, name):
+    if hasattr(obj, name) and getattr(obj, name) is not new:
         _saved.append((obj, name, getattr(obj, name)))
         setattr(obj, name, new)
 
 
-def patch(verbose: bool = False) -> int:
+def _in_worker_or_bad_fork() -> bool:
+    """True inside a DataLoader worker, or in a forked child of a process that had already initialised CUDA
+    (where any CUDA call raises "Cannot re-initialize CUDA in forked subprocess")."""
+    import torch
+    try:
+        if torch.utils.data.get_worker_info() is not None:
+            return True
+    except Exception:
+        pass
+    bad_fork = getattr(torch.cuda, "_is_in_bad_fork", None)
+    return bool(bad_fork()) if callable(bad_fork) else False
+
+
+def _range_projection_dispatch(original):
+    """``PointCloud.do_range_projection`` replacement that is safe at the reference's own call site.
+
+    The reference calls it per sample from ``Dataset.__getitem__`` (muvo/data/dataset.py:300), i.e. inside forked
+    DataLoader workers (``N_WORKERS`` > 0), where CUDA cannot be used: there the reference's own NumPy method runs
+    unchanged.  In the main process (``num_workers=0``, offline tools, tests) the B200 kernel runs.  The batched
+    GPU path for training is ``muvo_b200.sensor_to_grid`` / ``HostPipeline`` in the main process."""
+    from . import points
+
+    def do_range_projection(self, pts, semantics):
+        if _in_worker_or_bad_fork():
+            return original(self, pts, semantics)
+        return points.do_range_projection(self, pts, semantics)
+
+    do_range_projection.__wrapped__ = original
+    return do_range_projection
+
+
+def patch(verbose: bool = False, range_projection: str = "auto") -> int:
     """Patch every already-imported reference module; returns the number of symbols replaced.
 
-    ``data/generate_voxels.py`` does ``from data_preprocessing import *``; import it AFTER calling
-    ``patch()`` (or call ``patch()`` again) so that its namespace picks up the replacement too.
+    ``data/generate_voxels.py`` does ``from data_preprocessing import *`` (``generate_voxels.py:16``), so the star-imported
+    names live in its own namespace: every namespace that holds a copy (``data_preprocessing``, ``data.data_preprocessing``,
+    ``generate_voxels``, ``data.generate_voxels`` and ``__main__`` when the script itself is running) is patched.
+    Call ``patch()`` after the reference modules are imported (or again later: it is idempotent per symbol).
+
+    ``range_projection``: "auto" (default) = GPU kernel in the main process, the reference's NumPy method inside
+    DataLoader workers / forked children; "always" = GPU kernel everywhere (needs ``num_workers=0`` or the spawn start
+    method); "never" = leave ``PointCloud.do_range_projection`` alone.
     """
     from . import frustum_pooling as fp, metrics, points
+    if range_projection not in ("auto", "always", "never"):
+        raise ValueError("range_projection must be 'auto', 'always' or 'never'")
     n0 = len(_saved)
-    m = sys.modules.get("data_preprocessing")
-    if m is not None:
-        _swap(m, "voxel_filter", points.voxel_filter)
-        _swap(m, "merge_pcd", points.merge_pcd)                   # N1: camera + LiDAR cloud on the device
-    m = sys.modules.get("generate_voxels")
-    if m is not None:
-        _swap(m, "voxel_filter", points.voxel_filter)
-        _swap(m, "merge_pcd", points.merge_pcd)
-        _swap(m, "voxelize_one", points.voxelize_one)             # merge + voxelise without a host round trip
+    mains = [sys.modules.get("__main__")]
+    for name in ("data_preprocessing", "data.data_preprocessing"):
+        m = sys.modules.get(name)
+        if m is not None:
+            for name, new in (("voxel_filter", points.voxel_filter), ("merge_pcd", points.merge_pcd)):   # N1: merge on the device
+                if hasattr(m, name) and not getattr(getattr(m, name), "__module__", "").startswith("muvo_b200"):
+                    _swap(m, name, new)
+    for m in [sys.modules.get("generate_voxels"), sys.modules.get("data.generate_voxels")] + mains:
+        if m is None or getattr(m, "__name__", "").startswith("muvo_b200"):
+            continue
+        if m in mains and not all(hasattr(m, k) for k in ("voxelize_one", "voxel_filter", "merge_pcd")):
+            continue                                              # __main__ only when it is the reference script itself
+        for name, new in (("voxel_filter", points.voxel_filter), ("merge_pcd", points.merge_pcd),
+                          ("voxelize_one", points.voxelize_one)):   # voxelize_one: merge + voxelise without a host round trip
+            if hasattr(m, name) and not getattr(getattr(m, name), "__module__", "").startswith("muvo_b200"):
+                _swap(m, name, new)
     m = sys.modules.get("muvo.utils.geometry_utils")
-    if m is not None and hasattr(m, "PointCloud"):
-        _swap(m.PointCloud, "do_range_projection", points.do_range_projection)
+    if m is not None and hasattr(m, "PointCloud") and range_projection != "never":
+        cur = m.PointCloud.do_range_projection
+        if not hasattr(cur, "__wrapped__") and getattr(cur, "__module__", "") != points.__name__:
+            _swap(m.PointCloud, "do_range_projection",
+                  points.do_range_projection if range_projection == "always" else _range_projection_dispatch(cur))
     m = sys.modules.get("muvo.models.frustum_pooling")
     if m is not None:
         for name in ("FrustumPooling", "QuickCumsum", "cumsum_trick", "quick_cumsum"):

@@ -100,6 +100,11 @@ def test_shard_frames():
 def test_patch_and_unpatch_swap_reference_symbols():
     fake_dp = types.ModuleType("data_preprocessing")
     fake_dp.voxel_filter = lambda *a: "ref"
+    fake_dp2 = types.ModuleType("data.data_preprocessing")      # the name muvo/data/dataset.py:16 imports it under
+    fake_dp2.voxel_filter = fake_dp.voxel_filter
+    fake_gv = types.ModuleType("data.generate_voxels")          # star-import copy of generate_voxels.py:16
+    fake_gv.voxel_filter = fake_dp.voxel_filter
+    fake_gv.voxelize_one = lambda *a: "ref"
     fake_m = types.ModuleType("muvo.metrics")
     fake_m.SSCMetrics = object
     fake_g = types.ModuleType("muvo.utils.geometry_utils")
@@ -108,19 +113,72 @@ def test_patch_and_unpatch_swap_reference_symbols():
         def do_range_projection(self, p, s):
             return "ref"
     fake_g.PointCloud = RefPC
-    sys.modules.update({"data_preprocessing": fake_dp, "muvo.metrics": fake_m, "muvo.utils.geometry_utils": fake_g})
+    names = {"data_preprocessing": fake_dp, "data.data_preprocessing": fake_dp2, "data.generate_voxels": fake_gv,
+             "muvo.metrics": fake_m, "muvo.utils.geometry_utils": fake_g}
+    sys.modules.update(names)
     try:
         n = muvo_b200.patch()
-        assert n == 3
-        assert fake_dp.voxel_filter is muvo_b200.voxel_filter
+        assert n == 6
+        assert muvo_b200.patch() == 0                            # idempotent
+        assert fake_dp.voxel_filter is muvo_b200.voxel_filter and fake_dp2.voxel_filter is muvo_b200.voxel_filter
+        assert fake_gv.voxel_filter is muvo_b200.voxel_filter and fake_gv.voxelize_one is muvo_b200.points.voxelize_one
         assert fake_m.SSCMetrics is muvo_b200.SSCMetrics
-        assert RefPC.do_range_projection is muvo_b200.points.do_range_projection
+        # "auto": a dispatcher that keeps the reference's NumPy method for DataLoader workers / forked children
+        disp = RefPC.do_range_projection
+        assert disp is not muvo_b200.points.do_range_projection and disp.__wrapped__(RefPC(), 0, 0) == "ref"
+        P = sys.modules["muvo_b200.patch"]
+        saved = P._in_worker_or_bad_fork
+        P._in_worker_or_bad_fork = lambda: True
+        try:
+            assert RefPC().do_range_projection(0, 0) == "ref"
+        finally:
+            P._in_worker_or_bad_fork = saved
         muvo_b200.unpatch()
         assert fake_dp.voxel_filter() == "ref" and fake_m.SSCMetrics is object and RefPC().do_range_projection(0, 0) == "ref"
+        assert muvo_b200.patch(range_projection="always") == 6
+        assert RefPC.do_range_projection is muvo_b200.points.do_range_projection
+        muvo_b200.unpatch()
+        assert muvo_b200.patch(range_projection="never") == 5 and RefPC().do_range_projection(0, 0) == "ref"
     finally:
         muvo_b200.unpatch()
-        for k in ("data_preprocessing", "muvo.metrics", "muvo.utils.geometry_utils"):
+        for k in names:
             sys.modules.pop(k, None)
+
+
+class _RangeDataset(torch.utils.data.Dataset):
+    """Calls do_range_projection per sample, like muvo/data/dataset.py:300."""
+
+    def __init__(self, pc):
+        self.pc = pc
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        pts, sem = synth.carla_lidar_frame(2000, 7000 + i)
+        d, x, s = self.pc.do_range_projection(pts, sem)
+        return torch.from_numpy(d), torch.from_numpy(s)
+
+
+def test_patched_range_projection_in_dataloader_workers():
+    """the reference runs do_range_projection in forked DataLoader workers (N_WORKERS > 0), where CUDA cannot
+    be used; the default patch must keep working there (reference NumPy method), not crash."""
+    ref_import = pytest.importorskip("oracle.ref_import")
+    if not ref_import.available():
+        pytest.skip("reference checkout not mounted")
+    gu = ref_import.load().geometry_utils
+    pc = gu.PointCloud(64, 1024, -30, 10, [1.0, 0.0, 2.0])
+    want = [_RangeDataset(pc)[i] for i in range(4)]
+    sys.modules.setdefault("muvo.utils.geometry_utils", gu)
+    try:
+        muvo_b200.patch()
+        assert hasattr(gu.PointCloud.do_range_projection, "__wrapped__")
+        dl = torch.utils.data.DataLoader(_RangeDataset(pc), batch_size=1, num_workers=2, shuffle=False)
+        got = [(d[0], s[0]) for d, s in dl]
+        for (d0, s0), (d1, s1) in zip(want, got):
+            assert torch.equal(d0, d1) and torch.equal(s0, s1)
+    finally:
+        muvo_b200.unpatch()
 
 
 def test_synth_generators_are_deterministic_and_in_contract():
