@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MUVO_B200_ABI_VERSION 2
+#define MUVO_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MUVO_API __attribute__((visibility("default")))
@@ -255,23 +255,23 @@ MUVO_API int muvo_scal_sums_bwd(const void* logits, int32_t logits_dtype, const 
  * (muvo/models/common.py:731 and :703; torch_scatter is a third-party dependency of the reference, not vendored).
  *   src [n_src, n_feat] float32 row-major, index [n_src] int64 or int32 (index_dtype), values in [0, n_out)
  *   out [n_out, n_feat] float32, fully written: mean / max over the rows with index == m, 0 for rows that receive none
- *   scatter_mean: count_out [n_out] int32 (rows per output, kept for the backward); sums use float atomics (order dependent
- *                 in the last bits, like torch_scatter)
+ *   scatter_mean: count_out [n_out] int32 (rows per output, kept for the backward); deterministic: 64-bit fixed-point sums
+ *                 (integer atomics), rounded to float32 once; ws = muvo_pillar_workspace_bytes(n_out, n_feat), 8-byte aligned
  *   scatter_max : arg_out [n_out, n_feat] int64 or NULL: the LOWEST source row attaining the maximum, n_src for empty
  *                 rows; deterministic; ws = muvo_pillar_workspace_bytes(n_out, n_feat), 8-byte aligned
  *   bad_index_flag [1] int32 device: set to 1 when an index is out of range (that row is skipped); caller zeroes it
- *   *_bwd: grad_src [n_src, n_feat] fully written from grad_out [n_out, n_feat].                                   */
+ *   *_bwd: grad_src [n_src, n_feat] fully written from grad_out [n_out, n_feat] (0 for rows whose index is out of range). */
 MUVO_API int muvo_pillar_workspace_bytes(int64_t n_out, int32_t n_feat, size_t* bytes_out_h);
 MUVO_API int muvo_pillar_scatter_mean(const float* src, const void* index, int32_t index_dtype, int64_t n_src, int32_t n_feat,
                                       int64_t n_out, float* out, int32_t* count_out, void* ws, size_t ws_bytes,
                                       int32_t* bad_index_flag, void* stream);
 MUVO_API int muvo_pillar_scatter_mean_bwd(const float* grad_out, const void* index, int32_t index_dtype, const int32_t* count,
-                                          int64_t n_src, int32_t n_feat, float* grad_src, void* stream);
+                                          int64_t n_src, int32_t n_feat, int64_t n_out, float* grad_src, void* stream);
 MUVO_API int muvo_pillar_scatter_max(const float* src, const void* index, int32_t index_dtype, int64_t n_src, int32_t n_feat,
                                      int64_t n_out, float* out, int64_t* arg_out, void* ws, size_t ws_bytes,
                                      int32_t* bad_index_flag, void* stream);
 MUVO_API int muvo_pillar_scatter_max_bwd(const float* grad_out, const void* index, int32_t index_dtype, const int64_t* arg,
-                                         int64_t n_src, int32_t n_feat, float* grad_src, void* stream);
+                                         int64_t n_src, int32_t n_feat, int64_t n_out, float* grad_src, void* stream);
 
 /* ---- test / tuning hooks (not part of the drop-in surface) ------------------------------
  * muvo_debug_pixel_check: runs the f32 pixel path of the range projection next to the float64 formula of

@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmuvo_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 # dtype codes (include/muvo_b200.h)
 F32, F64, F16, BF16 = 0, 1, 2, 3
 I64, I32, U8, I16 = 0, 1, 2, 3
@@ -69,9 +69,9 @@ SIGNATURES = {
     "muvo_scal_sums_bwd": (C.c_int, [_P, _I32, _P, _I32, _I32, _I64, _I32, _P, _P, _P, _P, _P]),
     "muvo_pillar_workspace_bytes": (C.c_int, [_I64, _I32, C.POINTER(_SZ)]),
     "muvo_pillar_scatter_mean": (C.c_int, [_P, _P, _I32, _I64, _I32, _I64, _P, _P, _P, _SZ, _P, _P]),
-    "muvo_pillar_scatter_mean_bwd": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
+    "muvo_pillar_scatter_mean_bwd": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I64, _P, _P]),
     "muvo_pillar_scatter_max": (C.c_int, [_P, _P, _I32, _I64, _I32, _I64, _P, _P, _P, _SZ, _P, _P]),
-    "muvo_pillar_scatter_max_bwd": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _P, _P]),
+    "muvo_pillar_scatter_max_bwd": (C.c_int, [_P, _P, _I32, _P, _I64, _I32, _I64, _P, _P]),
     "muvo_debug_pixel_check": (C.c_int, [_P, _I64, C.POINTER(MuvoRangeCfg), _P, _P]),
     "muvo_debug_set_tuning": (C.c_int, [_I32, _I32]),
     "muvo_debug_mega_stats": (C.c_int, [_P, _I32, _I32]),

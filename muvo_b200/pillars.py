@@ -5,7 +5,9 @@ as ``muvo/models/common.py`` uses them (``DynamicPointNet.forward`` :703, ``Poin
 ``PointPillarNet``'s geometric helpers (``grid_locations`` :735-745, ``decorate`` :721-733, ``scatter_points`` :756-761)
 as functions.  ``torch_scatter`` is a third-party dependency of the reference that is neither vendored nor installed in
 this image, so parity is against its documented semantics (restated in ``oracle/``) and ``torch.scatter_reduce``.
-Only ``dim=0`` on 2-D float32 ``src`` is supported -- what the reference calls.  No CPU fallback.
+Only ``dim=0`` on 2-D floating ``src`` is supported -- what the reference calls; float16 / bfloat16 inputs (the
+reference's default ``PRECISION='16-mixed'`` feeds ``scatter_max`` half tensors, common.py:702-703) are reduced in
+float32 and returned, with their gradients, in the input dtype.  Both reductions are deterministic.  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -31,8 +33,8 @@ def _prep(src: torch.Tensor, index: torch.Tensor, dim: int, dim_size: Optional[i
     _lib.require_cuda(src, index)
     if dim not in (0, -src.dim()):
         raise NotImplementedError("muvo_b200 scatter ops support dim=0 only (the PointPillar call sites)")
-    if src.dim() != 2 or src.dtype != torch.float32:
-        raise TypeError("src must be a 2-D float32 tensor")
+    if src.dim() != 2 or src.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+        raise TypeError("src must be a 2-D float32 / float16 / bfloat16 tensor")
     if index.dtype not in _IDX:
         raise TypeError("index must be int64 or int32")
     if index.dim() == 2:                       # torch_scatter broadcasts an index of src's shape; the reference passes 1-D
@@ -41,6 +43,12 @@ def _prep(src: torch.Tensor, index: torch.Tensor, dim: int, dim_size: Optional[i
         raise ValueError("index must have one entry per source row")
     M = int(dim_size) if dim_size is not None else (int(index.max().item()) + 1 if index.numel() else 0)
     return src.contiguous(), index.contiguous(), M
+
+
+def _workspace(lib, M: int, F: int, dev) -> torch.Tensor:
+    need = C.c_size_t(0)
+    _lib.check(lib.muvo_pillar_workspace_bytes(M, F, C.byref(need)), "muvo_pillar_workspace_bytes")
+    return torch.empty(int(need.value), dtype=torch.uint8, device=dev)
 
 
 def check_indices(device=None) -> None:
@@ -57,28 +65,33 @@ class _ScatterMean(torch.autograd.Function):
     def forward(ctx, src, index, M):
         N, F = int(src.shape[0]), int(src.shape[1])
         dev = src.device
+        in_dtype = src.dtype
+        src = src.float()                                          # the reduction runs in float32 (as under autocast)
         out = torch.empty((M, F), dtype=torch.float32, device=dev)
         count = torch.empty((M,), dtype=torch.int32, device=dev)
+        lib = _lib.load()
         with torch.cuda.device(dev):
-            rc = _lib.load().muvo_pillar_scatter_mean(_lib.ptr(src), _lib.ptr(index), _IDX[index.dtype], N, F, M, _lib.ptr(out),
-                                                      _lib.ptr(count), None, 0, _flag(dev).data_ptr(), _lib.current_stream(dev))
+            ws = _workspace(lib, M, F, dev)
+            rc = lib.muvo_pillar_scatter_mean(_lib.ptr(src), _lib.ptr(index), _IDX[index.dtype], N, F, M, _lib.ptr(out),
+                                              _lib.ptr(count), ws.data_ptr(), ws.numel(), _flag(dev).data_ptr(),
+                                              _lib.current_stream(dev))
         _lib.check(rc, "muvo_pillar_scatter_mean")
         ctx.save_for_backward(index, count)
-        ctx.shape = (N, F)
-        return out
+        ctx.shape = (N, F, M, in_dtype)
+        return out.to(in_dtype)
 
     @staticmethod
     def backward(ctx, g):
         index, count = ctx.saved_tensors
-        N, F = ctx.shape
+        N, F, M, in_dtype = ctx.shape
         dev = g.device
         gs = torch.empty((N, F), dtype=torch.float32, device=dev)
         g = g.contiguous().float()
         with torch.cuda.device(dev):
-            rc = _lib.load().muvo_pillar_scatter_mean_bwd(_lib.ptr(g), _lib.ptr(index), _IDX[index.dtype], _lib.ptr(count), N, F,
+            rc = _lib.load().muvo_pillar_scatter_mean_bwd(_lib.ptr(g), _lib.ptr(index), _IDX[index.dtype], _lib.ptr(count), N, F, M,
                                                           _lib.ptr(gs), _lib.current_stream(dev))
         _lib.check(rc, "muvo_pillar_scatter_mean_bwd")
-        return gs, None, None
+        return gs.to(in_dtype), None, None
 
 
 class _ScatterMax(torch.autograd.Function):
@@ -86,33 +99,33 @@ class _ScatterMax(torch.autograd.Function):
     def forward(ctx, src, index, M):
         N, F = int(src.shape[0]), int(src.shape[1])
         dev = src.device
+        in_dtype = src.dtype
+        src = src.float()                                          # exact for float16 / bfloat16 values: the max is unchanged
         out = torch.empty((M, F), dtype=torch.float32, device=dev)
         arg = torch.empty((M, F), dtype=torch.int64, device=dev)
-        need = C.c_size_t(0)
         lib = _lib.load()
-        _lib.check(lib.muvo_pillar_workspace_bytes(M, F, C.byref(need)), "muvo_pillar_workspace_bytes")
-        ws = torch.empty(int(need.value), dtype=torch.uint8, device=dev)
+        ws = _workspace(lib, M, F, dev)
         with torch.cuda.device(dev):
             rc = lib.muvo_pillar_scatter_max(_lib.ptr(src), _lib.ptr(index), _IDX[index.dtype], N, F, M, _lib.ptr(out), _lib.ptr(arg),
                                              ws.data_ptr(), ws.numel(), _flag(dev).data_ptr(), _lib.current_stream(dev))
         _lib.check(rc, "muvo_pillar_scatter_max")
         ctx.save_for_backward(index, arg)
-        ctx.shape = (N, F)
+        ctx.shape = (N, F, M, in_dtype)
         ctx.mark_non_differentiable(arg)
-        return out, arg
+        return out.to(in_dtype), arg
 
     @staticmethod
     def backward(ctx, g, _g_arg):
         index, arg = ctx.saved_tensors
-        N, F = ctx.shape
+        N, F, M, in_dtype = ctx.shape
         dev = g.device
         gs = torch.empty((N, F), dtype=torch.float32, device=dev)
         g = g.contiguous().float()
         with torch.cuda.device(dev):
-            rc = _lib.load().muvo_pillar_scatter_max_bwd(_lib.ptr(g), _lib.ptr(index), _IDX[index.dtype], _lib.ptr(arg), N, F,
+            rc = _lib.load().muvo_pillar_scatter_max_bwd(_lib.ptr(g), _lib.ptr(index), _IDX[index.dtype], _lib.ptr(arg), N, F, M,
                                                          _lib.ptr(gs), _lib.current_stream(dev))
         _lib.check(rc, "muvo_pillar_scatter_max_bwd")
-        return gs, None, None
+        return gs.to(in_dtype), None, None
 
 
 def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = 0, out=None, dim_size: Optional[int] = None) -> torch.Tensor:

@@ -1,8 +1,9 @@
 """GPU parity for the PointPillar scatter reductions ("next" row N4; muvo/models/common.py:703, :731).
 
 torch_scatter is not installable here, so the checks are the oracle's restatement of its documented semantics and
-``torch.Tensor.scatter_reduce`` as an independent implementation.  scatter_max is exact; scatter_mean is a float
-atomic sum (like torch_scatter's), bar 1e-6 relative to the largest magnitude in the row."""
+``torch.Tensor.scatter_reduce`` as an independent implementation.  scatter_max is exact; scatter_mean is a 64-bit
+fixed-point sum (deterministic: bit-identical under any permutation of the rows), bar 1e-6 relative to the largest
+magnitude against the float64 oracle."""
 import numpy as np
 import pytest
 import torch
@@ -90,3 +91,58 @@ def test_decorate_and_canvas_match_a_torch_restatement(lib):
     fmax, _ = pillars.scatter_max(feat, inv, dim_size=uniq.shape[0])
     canvas = pillars.pillar_scatter_points(fmax, uniq, 1, 320, 320)
     assert canvas.shape == (1, 16, 320, 320) and int((canvas.abs().sum(1) > 0).sum()) == uniq.shape[0]
+
+
+def test_scatter_mean_is_deterministic_and_order_independent(lib):
+    """north_star: no float atomics.  The fixed-point accumulation makes the result a function of the multiset of rows."""
+    src, idx = _case(60000, 3, 9000, 11)
+    src = src * 50.0                                                     # metres, like the xyz the reference averages (:731)
+    a = pillars.scatter_mean(src.cuda(), idx.cuda(), dim_size=9000)
+    b = pillars.scatter_mean(src.cuda(), idx.cuda(), dim_size=9000)
+    perm = torch.randperm(src.shape[0], generator=torch.Generator().manual_seed(3))
+    c = pillars.scatter_mean(src[perm].cuda(), idx[perm].cuda(), dim_size=9000)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    want = O.scatter_mean(src.numpy().astype(np.float64), idx.numpy(), 9000)
+    got = a.cpu().numpy().astype(np.float64)
+    assert np.abs(got - want).max() <= 6e-8 * np.abs(want).max() + 1e-30   # half a float32 ulp of the largest mean
+
+
+def test_scatter_half_precision_and_special_values(lib):
+    """under PRECISION='16-mixed' DynamicPointNet.forward feeds scatter_max float16 (common.py:702-703)."""
+    src, idx = _case(2000, 16, 150, 21)
+    for dt in (torch.float16, torch.bfloat16):
+        s = src.to(dt).cuda().requires_grad_(True)
+        mx, arg = pillars.scatter_max(s, idx.cuda(), dim_size=150)
+        assert mx.dtype == dt
+        wmx, warg = O.scatter_max(src.to(dt).float().numpy(), idx.numpy(), 150)
+        assert np.array_equal(mx.float().cpu().numpy(), wmx) and np.array_equal(arg.cpu().numpy(), warg)
+        mx.float().sum().backward()
+        assert s.grad.dtype == dt and float(s.grad.float().sum()) == float((warg < 2000).sum())
+        mean = pillars.scatter_mean(src.to(dt).cuda(), idx.cuda(), dim_size=150)
+        assert mean.dtype == dt
+    with torch.autocast("cuda", dtype=torch.float16):
+        h = torch.nn.functional.relu(torch.nn.Linear(16, 8).cuda()(src.cuda()))   # float16 under autocast
+        out, _ = pillars.scatter_max(h, idx.cuda(), dim_size=150)
+    assert h.dtype == torch.float16 and out.dtype == torch.float16
+    # NaN / Inf propagate per output element; everything else is untouched
+    s2 = src.clone()
+    s2[0, 0], s2[1, 1], s2[2, 2], s2[3, 2] = float("nan"), float("inf"), float("inf"), float("-inf")
+    idx2 = idx.clone(); idx2[2] = idx2[3]
+    got = pillars.scatter_mean(s2.cuda(), idx2.cuda(), dim_size=150).cpu()
+    assert torch.isnan(got[idx2[0], 0]) and got[idx2[1], 1] == float("inf") and torch.isnan(got[idx2[2], 2])
+    clean = torch.ones_like(got, dtype=torch.bool)
+    clean[idx2[0], 0] = clean[idx2[1], 1] = clean[idx2[2], 2] = False
+    want = torch.from_numpy(O.scatter_mean(src.numpy(), idx2.numpy(), 150))
+    assert torch.allclose(got[clean], want[clean], rtol=0, atol=1e-6 * float(src.abs().max()))
+
+
+def test_out_of_range_index_is_flagged_and_backward_is_safe(lib):
+    src, idx = _case(500, 4, 50, 5)
+    idx[7], idx[9] = 50, -1                                              # one past the end, negative
+    s = src.cuda().requires_grad_(True)
+    mean = pillars.scatter_mean(s, idx.cuda(), dim_size=50)
+    mx, _ = pillars.scatter_max(s, idx.cuda(), dim_size=50)
+    (mean.sum() + mx.sum()).backward()                                   # must not read out of bounds
+    assert torch.all(s.grad[7] == 0) and torch.all(s.grad[9] == 0) and torch.isfinite(s.grad).all()
+    with pytest.raises(IndexError):
+        pillars.check_indices()
