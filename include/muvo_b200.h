@@ -176,6 +176,12 @@ MUVO_API int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64
  *   out      [B, C*nz, ny, nx] float32, fully written (empty cells = 0, :180-185)
  * The sum over a cell's points is taken in ascending point order (deterministic).   */
 MUVO_API int muvo_bev_pool_workspace_bytes(int32_t B, int64_t n_pts, int32_t n_cells, size_t* bytes_out_h);
+/* Largest n_cells the forward kernels accept (one histogram per warp in shared memory: 12800 cells, e.g. up to a 113 x 113
+ * BEV with nz = 1; MUVO's muvo.yml uses 48 x 48 = 2304).  Larger grids return MUVO_E_SHAPE.                              */
+MUVO_API int muvo_bev_pool_max_cells(void);
+/* cell_out[i] = mask[i] ? cell0[i] : -1 for i < n: the top-k depth mask of mile.py:512-514 (frustum_pooling.py:153-156)
+ * applied to mask-independent cell ids, which the host caches per (intrinsics, extrinsics, frustum shape).              */
+MUVO_API int muvo_bev_fold_mask(const int32_t* cell0, const uint8_t* mask, int64_t n, int32_t* cell_out, void* stream);
 MUVO_API int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
                       const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells, float* out,
                       void* ws, size_t ws_bytes, void* stream);

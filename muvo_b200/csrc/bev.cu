@@ -1073,6 +1073,21 @@ static int run_pool_bwd(const float* gout, const int32_t* cell, int B, int64_t n
   return MUVO_OK;
 }
 
+// cell[i] = mask[i] ? cell0[i] : -1  (frustum_pooling.py:153-156 applied to the cached, mask-independent cell ids)
+__global__ void __launch_bounds__(256)
+k_fold_mask(const int32_t* __restrict__ cell0, const uint8_t* __restrict__ mask, int64_t n4, int64_t n, int32_t* __restrict__ cell) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t < n4) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(cell0) + t);
+    const uint32_t m = __ldg(reinterpret_cast<const uint32_t*>(mask) + t);
+    int4 o;
+    o.x = (m & 0x000000ffu) ? c.x : -1; o.y = (m & 0x0000ff00u) ? c.y : -1;
+    o.z = (m & 0x00ff0000u) ? c.z : -1; o.w = (m & 0xff000000u) ? c.w : -1;
+    reinterpret_cast<int4*>(cell)[t] = o;
+  }
+  if (t == 0) for (int64_t i = n4 * 4; i < n; ++i) cell[i] = mask[i] ? cell0[i] : -1;
+}
+
 struct SegWs { uint32_t* block_cnt; size_t bytes; int nblocks; };
 static SegWs carve_seg(void* base, int64_t n) {
   SegWs w;
@@ -1093,6 +1108,20 @@ int muvo_bev_pool_workspace_bytes(int32_t B, int64_t n_pts, int32_t n_cells, siz
   if (!bytes_out_h) return MUVO_E_NULL;
   if (B < 0 || n_pts < 0 || n_cells <= 0) return MUVO_E_ARG;
   *bytes_out_h = carve_bev(nullptr, B, n_pts, n_cells).bytes + 256;
+  return MUVO_OK;
+}
+
+int muvo_bev_pool_max_cells(void) { return (200 * 1024) / (kSortWarps * 4); }
+
+int muvo_bev_fold_mask(const int32_t* cell0, const uint8_t* mask, int64_t n, int32_t* cell_out, void* stream) {
+  if (n < 0) return MUVO_E_ARG;
+  if (n == 0) return MUVO_OK;
+  if (!cell0 || !mask || !cell_out) return MUVO_E_NULL;
+  const bool vec = ((reinterpret_cast<uintptr_t>(cell0) | reinterpret_cast<uintptr_t>(cell_out)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(mask) & 3) == 0;
+  const int64_t n4 = vec ? n / 4 : 0;
+  k_fold_mask<<<(unsigned)ceil_div64(n4 > 0 ? n4 : 1, 256), 256, 0, (cudaStream_t)stream>>>(cell0, mask, n4, n, cell_out);
+  MUVO_AFTER_LAUNCH("k_fold_mask", (cudaStream_t)stream);
   return MUVO_OK;
 }
 

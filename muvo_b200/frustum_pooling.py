@@ -135,7 +135,27 @@ def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
 
 def bev_pool(x: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
     """``x (B,N,D,H,W,C)`` any strides, ``cell (B, N*D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
+    limit = _lib.load().muvo_bev_pool_max_cells()
+    if int(n_cells) > limit:
+        raise ValueError(f"muvo_b200 BEV pooling supports at most {limit} BEV cells (nx*ny*nz), got {n_cells}: the index sort "
+                         "keeps one histogram per warp in shared memory.  MUVO's shipped configs use 48*48*1 = 2304; see "
+                         "INTEGRATION.md (limits).")
     return _BevPool.apply(x, cell, int(n_cells))
+
+
+def fold_mask(cell0: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """``cell0`` int32 with ``mask`` (bool / uint8, same number of elements) applied: dropped points become -1."""
+    _lib.require_cuda(cell0, mask)
+    m = mask.reshape(-1)
+    m = (m if m.dtype in (torch.bool, torch.uint8) else m.bool()).contiguous().view(torch.uint8)
+    c0 = cell0.contiguous()
+    if m.numel() != c0.numel():
+        raise ValueError("mask and cell ids differ in size")
+    out = torch.empty_like(c0)
+    with torch.cuda.device(c0.device):
+        rc = _lib.load().muvo_bev_fold_mask(_lib.ptr(c0), _lib.ptr(m), c0.numel(), _lib.ptr(out), _lib.current_stream(c0.device))
+    _lib.check(rc, "muvo_bev_fold_mask")
+    return out
 
 
 class _LiftSplat(torch.autograd.Function):
@@ -267,6 +287,7 @@ class FrustumPooling(nn.Module):
         self.register_buffer('ds', ds, persistent=False)
         self.downsample = downsample
         self.register_buffer('frustum', torch.zeros(0, ), persistent=False)
+        self._geom_cache = None          # (intrinsics, pose, frustum shape) -> mask-independent cell ids; not part of state_dict
 
     def initialize_frustum(self, image):
         """frustum_pooling.py:97-109."""
@@ -316,24 +337,51 @@ class FrustumPooling(nn.Module):
             return out.view(B, Cc, ny, nx)
         return out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
 
+    def cached_cell_ids(self, intrinsics, pose, frustum_like):
+        """Mask-independent cell id of every frustum point, cached.
+
+        The geometry (frustum_pooling.py:111-129) and the integer cell of a frustum point (:139-163 without the mask)
+        depend only on the intrinsics, the extrinsics and the frustum shape -- constant for a fixed camera rig -- so they
+        are computed once with the reference's own torch ops (bit-identical cell ids) and reused; per call only the top-k
+        mask is folded in (one small kernel).  Cache hit = the same tensor objects (unchanged in place), or equal values
+        (``torch.equal``: two tiny kernels and one sync, still far below the ~25 eager launches + batched gemv it replaces;
+        the reference's own ``x[kept]`` indexing synchronises every call as well)."""
+        self.initialize_frustum(frustum_like)
+        c = self._geom_cache
+        key = (tuple(intrinsics.shape), tuple(pose.shape), tuple(self.frustum.shape), intrinsics.device, intrinsics.dtype)
+        if c is not None and c["key"] == key:
+            same_obj = (c["K_id"] == (id(intrinsics), intrinsics._version) and c["E_id"] == (id(pose), pose._version))
+            if same_obj or (torch.equal(intrinsics, c["K"]) and torch.equal(pose, c["E"])):
+                c["K_id"], c["E_id"] = (id(intrinsics), intrinsics._version), (id(pose), pose._version)
+                c["hits"] += 1
+                return c["cell0"]
+        with torch.no_grad():
+            geom = self.get_geometry(pose[..., :3, :3], pose[..., :3, 3:], intrinsics)
+            cell0 = self.cell_ids(geom, torch.zeros(0))
+        self._geom_cache = {"key": key, "K": intrinsics.detach().clone(), "E": pose.detach().clone(), "cell0": cell0, "hits": 0,
+                            "K_id": (id(intrinsics), intrinsics._version), "E_id": (id(pose), pose._version)}
+        return cell0
+
+    def _pool_cells(self, x, cell0, mask):
+        B, N, D, H, W, Cc = x.shape
+        nx, ny, nz = self.nx_constant
+        cell = fold_mask(cell0, mask) if len(mask) > 0 else cell0
+        out = bev_pool(x, cell, nx * ny * nz).view(B, Cc, nz, ny, nx)
+        return out.view(B, Cc, ny, nx) if nz == 1 else out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
+
     def forward(self, x, intrinsics, pose, mask=torch.zeros(0)):
-        """frustum_pooling.py:189-209."""
-        self.initialize_frustum(x)
-        rots = pose[..., :3, :3]
-        trans = pose[..., :3, 3:]
-        geom = self.get_geometry(rots, trans, intrinsics)
-        x = self.voxel_pooling(geom, x, mask).type_as(x)
-        return x
+        """frustum_pooling.py:189-209 (geometry + cell ids cached per camera, see :meth:`cached_cell_ids`)."""
+        cell0 = self.cached_cell_ids(intrinsics, pose, x)
+        return self._pool_cells(x, cell0, mask).type_as(x)
 
     def lift_splat(self, feat, depth, intrinsics, pose, mask=torch.zeros(0)):
         """Opt-in fused replacement of ``forward((depth[:,None] * feat[:,:,None])[:,None].permute(0,1,3,4,5,2), ...)``
         (muvo/models/mile.py:517-523): same output, the (B,C,D,H,W) outer product is never materialised and the
         gradients go straight to ``feat`` and ``depth``.  ``feat (B,C,fH,fW)``, ``depth (B,D,fH,fW)``, one camera."""
         B, Cc, H, W = feat.shape
-        self.initialize_frustum(feat.new_zeros((1, 1, 1, H, W, 1)))
-        geom = self.get_geometry(pose[..., :3, :3], pose[..., :3, 3:], intrinsics)
+        cell0 = self.cached_cell_ids(intrinsics, pose, feat.new_zeros((1, 1, 1, H, W, 1)))
         nx, ny, nz = self.nx_constant
-        cell = self.cell_ids(geom, mask)
+        cell = fold_mask(cell0, mask) if len(mask) > 0 else cell0
         out = lift_splat(feat, depth, cell, nx * ny * nz).view(B, Cc, nz, ny, nx)
         out = out.view(B, Cc, ny, nx) if nz == 1 else out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
         return out.type_as(feat)
