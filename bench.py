@@ -89,17 +89,46 @@ def make_batch(rank: int, n_frames: int = F_BATCH * F_SEQ, n_min: int = N_MIN, n
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+_REF = {"tried": False, "ns": None}
+
+
+def ref_namespace():
+    """The UNMODIFIED reference functions (oracle/ref_import.py: $MUVO_REFERENCE_ROOT, /root/reference or baseline/_ref),
+    or None -- then the oracle's restatement ("port") is timed instead."""
+    if not _REF["tried"]:
+        _REF["tried"] = True
+        try:
+            import warnings
+            warnings.filterwarnings("ignore")
+            import oracle.ref_import as R
+            _REF["ns"] = R.load() if R.available() else None
+        except Exception as e:                                  # a missing optional import of the reference, ...
+            print(f"bench: reference not importable ({e}); timing the oracle port", file=sys.stderr)
+            _REF["ns"] = None
+    return _REF["ns"]
+
+
+def cpu_kind():
+    return "reference" if ref_namespace() is not None else "port"
+
+
 def _cpu_frame(args):
+    """(a) voxel_filter + densify and (b) do_range_projection + pack for one frame, on one core."""
     import warnings
     warnings.filterwarnings("ignore")
     import oracle as O
-    p, s = args
-    v, l = O.voxel_filter_loop(p, s, 0.5, [192, 192, 64], [0.0, 0, -10.0])           # (a) data_preprocessing.py:172-228
-    data = np.concatenate([v, l[:, None].astype(np.uint16)], 1)
     from muvo_b200 import synth
-    grid = O.densify_voxels(data, (192, 192, 64), synth.label_remap256())             # dataset.py:317-327
-    d, x, sm = O.range_projection(p, s, lidar_position=list(LIDAR))                    # (b) geometry_utils.py:175-220
-    O.pack_range_view(d, x)
+    p, s = args
+    ns = ref_namespace()
+    if ns is not None:
+        v, l = ns.voxel_filter(p, s, 0.5, [192, 192, 64], [0.0, 0, -10.0])           # data/data_preprocessing.py:172-228, unmodified
+        d, x, sm = ns.PointCloud(64, 1024, -30, 10, list(LIDAR)).do_range_projection(p, s)   # geometry_utils.py:175-220, unmodified
+    else:
+        v, l = O.voxel_filter_loop(p, s, 0.5, [192, 192, 64], [0.0, 0, -10.0])
+        d, x, sm = O.range_projection(p, s, lidar_position=list(LIDAR))
+    data = np.concatenate([v, l[:, None].astype(np.uint16)], 1)
+    grid = O.densify_voxels(data, (192, 192, 64), synth.label_remap256())             # dataset.py:317-327 (glue; muvo.data.dataset needs lightning)
+    O.pack_range_view(d, x)                                                            # dataset.py:301-303
     return int(grid.sum()) + int(sm.sum())
 
 
@@ -111,7 +140,10 @@ def cpu_reference(frames, pool, cores):
     return sum(len(p) for p, _ in frames), dt
 
 
-def cpu_sample_frames(n_frames):
+def cpu_sample_frames(n_frames, cfg="cfg2"):
+    if cfg == "cfg5":
+        from muvo_b200 import synth
+        return [synth.carla_lidar_frame(1_000_000, 5000 + i) for i in range(n_frames)]
     pts, sem, off = make_batch(0, n_frames)
     return [(pts[off[f]:off[f + 1]].copy(), sem[off[f]:off[f + 1]].copy()) for f in range(n_frames)]
 
@@ -122,27 +154,37 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_frames = max(cores, 8)                      # one frame per worker per step: ~0.3-0.6 s of CPU work per frame
-    frames = cpu_sample_frames(n_frames)
+    ref_namespace()                                   # import once in the parent: forked workers inherit it
+    if args.config == "cfg5":
+        n_frames = 16                                 # the stated 16-frame subset of SURVEY.md 8(d) item 5 (a full pass is ~7700 core-seconds)
+    else:
+        n_frames = max(cores, 8)                      # one frame per worker per step: ~0.3-0.6 s of CPU work per frame
+    frames = cpu_sample_frames(n_frames, args.config)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        for _ in range(max(args.warmup, 1) if args.warmup else 0):
-            cpu_reference(frames[:cores], pool, cores)
+    steps = args.steps if args.config != "cfg5" else max(1, min(args.steps, 2))
+    with ctx.Pool(min(cores, n_frames)) as pool:
+        for _ in range(1 if args.warmup else 0):
+            cpu_reference(frames[:min(cores, n_frames)], pool, cores)
         tot_pts, tot_s = 0, 0.0
-        for _ in range(args.steps):
+        for _ in range(steps):
             n, dt = cpu_reference(frames, pool, cores)
             tot_pts += n
             tot_s += dt
     value = tot_pts / tot_s
-    sample = (f"{n_frames} frames/step of the cfg2 generator ({tot_pts // max(args.steps, 1)} points/step), "
-              f"multiprocessing.Pool({cores}) over frames like data/generate_voxels.py:134; oracle *_loop port "
-              f"(voxel_filter + densify + do_range_projection), numpy {np.__version__}")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / max(args.steps, 1), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg2: range-view projection + occupancy voxelisation (CPU oracle port, bounded sample)",
-                       "frames_per_step": n_frames, "points_per_frame": f"{N_MIN}-{N_MAX}"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    kind = cpu_kind()
+    what = ("unmodified voxel_filter + PointCloud.do_range_projection of the reference" if kind == "reference"
+            else "oracle *_loop port of voxel_filter + do_range_projection") + " (+ densify / pack glue)"
+    workload, metric = ("cfg2", METRIC) if args.config != "cfg5" else ("cfg5", METRIC)
+    sample = (f"{n_frames} frames/step of the {workload} generator ({tot_pts // max(steps, 1)} points/step), "
+              f"multiprocessing.Pool({min(cores, n_frames)}) over frames like data/generate_voxels.py:134; {what}, numpy {np.__version__}")
+    cfg = ({"workload": "cfg2: range-view projection + occupancy voxelisation (CPU reference, bounded sample)",
+            "frames_per_step": n_frames, "points_per_frame": f"{N_MIN}-{N_MAX}"} if args.config != "cfg5" else
+           {"workload": "cfg5: 1M-point frames, voxelise + project (CPU reference on a 16-frame subset; 768 frames extrapolate linearly: "
+                        f"{768 * 1e6 / value:.0f} s on this box)", "frames_per_step": n_frames, "points_per_frame": 1_000_000})
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1 if args.warmup else 0, "ms_per_step": 1e3 * tot_s / max(steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, n_frames), "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit_line(line)
@@ -301,22 +343,29 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline_leg():
+def cpu_baseline_leg(cfg="cfg2"):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_frames = max(cores, 8)
-    frames = cpu_sample_frames(n_frames)
+    ref_namespace()
+    n_frames = max(cores, 8) if cfg != "cfg5" else 16
+    frames = cpu_sample_frames(n_frames, cfg)
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        cpu_reference(frames[:cores], pool, cores)
+    with ctx.Pool(min(cores, n_frames)) as pool:
+        if cfg != "cfg5":
+            cpu_reference(frames[:cores], pool, cores)
         n, dt = cpu_reference(frames, pool, cores)
     t0 = time.perf_counter()
     _cpu_frame(frames[0])
     one = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_frames} cfg2 frames ({n} points) through the oracle *_loop port with multiprocessing.Pool({cores}); "
-                      f"single core: {len(frames[0][0]) / one:.3g} points/s",
-            "single_core_value": len(frames[0][0]) / one}
+    kind = cpu_kind()
+    what = "the reference's unmodified voxel_filter + do_range_projection" if kind == "reference" else "the oracle *_loop port"
+    out = {"value": n / dt, "unit": UNIT, "cores": min(cores, n_frames), "kind": kind,
+           "sample": f"{n_frames} {cfg} frames ({n} points) through {what} with multiprocessing.Pool({min(cores, n_frames)}); "
+                     f"single core: {len(frames[0][0]) / one:.3g} points/s",
+           "single_core_value": len(frames[0][0]) / one}
+    if cfg == "cfg5":
+        out["extrapolated_768_frames_s"] = 768 * 1e6 / (n / dt)
+    return out
 
 
 def other_stages(device, rank, world, hbm_peak, args):
@@ -364,6 +413,50 @@ def other_stages(device, rank, world, hbm_peak, args):
                            "dense_read_GBps": bytes_f_sector / ms_f / 1e6, "frames": B, "C": C, "n_kept": n_kept,
                            "note": "kernel only (cell ids precomputed); dense_read = whole lifted tensor, the sector-granular bound for a random top-k mask"}
     res["bev_pool_bwd"] = {"ms": ms_b, "algorithmic_GBps": bytes_b / ms_b / 1e6, "frac": bytes_b / ms_b / 1e6 / hbm_peak}
+    # the drop-in boundary itself: FrustumPooling.forward(x, intrinsics, pose, mask) (frustum_pooling.py:189-209); geometry and
+    # cell ids come from the per-camera cache, the mask is folded in per call
+    Kc, Ec = K[:, None].contiguous(), E[:, None].contiguous()
+    fp(x, Kc, Ec, mask)
+    ms_m = timed(lambda: fp(x, Kc, Ec, mask), steps)
+    res["bev_module_fwd"] = {"ms": ms_m, "algorithmic_GBps": bytes_f / ms_m / 1e6, "frac": bytes_f / ms_m / 1e6 / hbm_peak,
+                             "dense_read_GBps": bytes_f_sector / ms_m / 1e6, "dense_read_frac": bytes_f_sector / ms_m / 1e6 / hbm_peak,
+                             "cache_hits": int(fp._geom_cache["hits"]),
+                             "note": "muvo_b200.FrustumPooling.forward(x, K, E, mask): cached cell ids + mask fold + index sort + pool kernel"}
+    xm = x.detach().requires_grad_(True)
+    om = fp(xm, Kc, Ec, mask)
+    ms_mb = timed(lambda: torch.autograd.grad(om, xm, gout.view(om.shape), retain_graph=True), steps)
+    res["bev_module_bwd"] = {"ms": ms_mb, "algorithmic_GBps": bytes_b / ms_mb / 1e6, "frac": bytes_b / ms_mb / 1e6 / hbm_peak}
+    del xm, om
+    # the reference's own FrustumPooling on the same inputs: stock PyTorch on this B200, and on the host cores (rank 0)
+    ns = ref_namespace()
+    if ns is not None and rank == 0:
+        try:
+            rfp = ns.FrustumPooling(**synth.BEV_POOL_ARGS).to(device)
+            xr = x.detach().clone().requires_grad_(True)
+            outr = rfp(xr, Kc, Ec, mask)
+            err = float((outr.detach() - fp(x, Kc, Ec, mask)).abs().max() / outr.detach().abs().max())
+            ms_rf = timed(lambda: rfp(x, Kc, Ec, mask), max(2, steps // 2))
+            ms_rb = timed(lambda: torch.autograd.grad(rfp(xr, Kc, Ec, mask), xr, gout.view(outr.shape)), max(2, steps // 2)) - ms_rf
+            res["bev_reference_gpu"] = {"fwd_ms": ms_rf, "bwd_ms": ms_rb, "kind": "reference",
+                                        "what": "unmodified muvo.models.frustum_pooling.FrustumPooling, CUDA tensors, same B200 (stock PyTorch)",
+                                        "max_rel_diff_vs_ours": err,
+                                        "vs_reference": {"fwd": ms_rf / ms_m, "bwd": ms_rb / ms_mb}}
+            del rfp, xr, outr
+            torch.cuda.empty_cache()
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            rfc = ns.FrustumPooling(**synth.BEV_POOL_ARGS)
+            xc = x.detach().cpu().requires_grad_(True)
+            Kh, Eh, mh, gh = Kc.cpu(), Ec.cpu(), mask.cpu(), gout.cpu()
+            rfc(xc.detach(), Kh, Eh, mh)
+            t0 = time.perf_counter(); oc = rfc(xc, Kh, Eh, mh); t1 = time.perf_counter()
+            torch.autograd.grad(oc, xc, gh.view(oc.shape)); t2 = time.perf_counter()
+            res["bev_reference_cpu"] = {"fwd_ms": 1e3 * (t1 - t0), "bwd_ms": 1e3 * (t2 - t1), "cores": cores, "kind": "reference",
+                                        "sample": f"one forward + backward of the unmodified FrustumPooling at cfg3 shapes on {cores} torch threads",
+                                        "vs_reference": {"fwd": 1e3 * (t1 - t0) / ms_m, "bwd": 1e3 * (t2 - t1) / ms_mb}}
+            del rfc, xc, oc
+        except Exception as e:                                    # never lose the bench line to a baseline
+            res["bev_reference_error"] = repr(e)[:200]
     # N2: fused lift-splat on the same inputs (feat, depth -> BEV), forward and backward to feat / depth
     from muvo_b200.frustum_pooling import lift_splat
     fl, dl = feat.detach().requires_grad_(True), depth.detach().requires_grad_(True)
@@ -374,23 +467,93 @@ def other_stages(device, rank, world, hbm_peak, args):
     res["lift_splat_fused_fwd"] = {"ms": ms_lf, "algorithmic_GBps": bytes_l / ms_lf / 1e6, "frac": bytes_l / ms_lf / 1e6 / hbm_peak,
                                    "note": "N2: same output as lift (mile.py:517-521) + bev_pool_fwd, outer product never materialised; "
                                            "includes the channels-last copy of feat and the cell sort"}
-    res["lift_splat_fused_bwd"] = {"ms": ms_lb, "note": "grad_feat + grad_depth, includes the [B,cells,C] copy of grad_out"}
+    bytes_lb = B * (2 * C * H * W * 4 + n_pts * (4 + 4 + 4) + C * 2304 * 4)      # gout + feat in, grad_feat out, depth + cell in, grad_depth out
+    res["lift_splat_fused_bwd"] = {"ms": ms_lb, "algorithmic_GBps": bytes_lb / ms_lb / 1e6, "frac": bytes_lb / ms_lb / 1e6 / hbm_peak,
+                                   "note": "grad_feat + grad_depth, includes the [B,cells,C] copy of grad_out"}
     del x, xg, out, gout, feat, depth, fl, dl, ol
     torch.cuda.empty_cache()
-    # (d) cfg4: 16 frames per rank, C = 2, counts all-reduced
+    # (d) cfg4: 16 frames per rank, C = 2 and C = 9, counts all-reduced over the ranks and checked against the single-process
+    # oracle over ALL ranks' frames (every rank's inputs are seeded, so rank 0 regenerates them)
+    for Cn in (2, 9):
+        yp, yt = synth.occupancy_pair(16, Cn, 4000 + rank + 100 * (Cn != 2))
+        tp, tt = torch.from_numpy(yp).to(device), torch.from_numpy(yt).to(device)
+        acc = torch.zeros(3 + 3 * Cn, dtype=torch.int64, device=device)
+
+        def ssc():
+            acc.zero_()
+            ssc_counts(tp, tt, Cn, ignore255=True, out=acc)
+            all_reduce_counts(acc)
+        ms_d = timed(ssc, steps)
+        acc.zero_()
+        ssc_counts(tp, tt, Cn, ignore255=True, out=acc)
+        ms_k = timed(lambda: ssc_counts(tp, tt, Cn, ignore255=True, out=acc), steps)      # kernel alone, no collective
+        ssc()
+        got = acc.cpu().numpy()
+        bytes_d = tp.numel() * 9
+        key = "ssc_counts" if Cn == 2 else "ssc_counts_c9"
+        res[key] = {"ms": ms_d, "kernel_only_ms": ms_k, "algorithmic_GBps": bytes_d / ms_d / 1e6, "frac": bytes_d / ms_d / 1e6 / hbm_peak,
+                    "kernel_only_frac": bytes_d / ms_k / 1e6 / hbm_peak, "n_classes": Cn,
+                    "voxels_per_s": tp.numel() * world / (ms_d * 1e-3), "frames_per_rank": 16,
+                    "allreduce": f"nccl int64[{3 + 3 * Cn}]" if world > 1 else "none (1 rank)"}
+        if rank == 0:
+            import oracle as O                                     # the checker, not the thing measured
+            want = np.zeros(3 + 3 * Cn, dtype=np.int64)
+            for r in range(world):
+                ypr, ytr = (yp, yt) if r == 0 else synth.occupancy_pair(16, Cn, 4000 + r + 100 * (Cn != 2))
+                want += O.ssc_add_batch_counts(ypr, ytr, Cn)
+            res[key]["allreduced_counts_equal_oracle"] = bool(np.array_equal(got, want))
+            res[key]["frames_checked"] = 16 * world
+            assert np.array_equal(got, want), f"cfg4 C={Cn}: all-reduced counts differ from the oracle over {16 * world} frames"
+            ns = ref_namespace()
+            if ns is not None:
+                try:
+                    m = ns.SSCMetrics(Cn)
+                    m.add_batch(tp[:2], tt[:2])                      # warm
+                    m.reset()
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    m.add_batch(tp, tt)
+                    torch.cuda.synchronize(); t_gpu = time.perf_counter() - t0
+                    cores = os.cpu_count() or 1
+                    torch.set_num_threads(cores)
+                    mc = ns.SSCMetrics(Cn)
+                    t0 = time.perf_counter()
+                    mc.add_batch(torch.from_numpy(yp), torch.from_numpy(yt))
+                    t_cpu = time.perf_counter() - t0
+                    ref_counts = np.r_[mc.completion_tp, mc.completion_fp, mc.completion_fn, mc.tps.numpy(), mc.fps.numpy(), mc.fns.numpy()]
+                    mine = O.ssc_add_batch_counts(yp, yt, Cn)
+                    res[key]["reference"] = {"kind": "reference", "what": "unmodified muvo.metrics.SSCMetrics.add_batch, 16 frames",
+                                             "gpu_ms": 1e3 * t_gpu, "cpu_ms": 1e3 * t_cpu, "cores": cores,
+                                             "counts_equal": bool(np.array_equal(ref_counts.astype(np.int64), mine)),
+                                             "vs_reference": {"gpu": 1e3 * t_gpu / ms_k, "cpu": 1e3 * t_cpu / ms_k}}
+                except Exception as e:
+                    res[key]["reference_error"] = repr(e)[:200]
     yp, yt = synth.occupancy_pair(16, 2, 4000 + rank)
     tp, tt = torch.from_numpy(yp).to(device), torch.from_numpy(yt).to(device)
-    acc = torch.zeros(9, dtype=torch.int64, device=device)
-
-    def ssc():
-        acc.zero_()
-        ssc_counts(tp, tt, 2, ignore255=True, out=acc)
-        all_reduce_counts(acc)
-    ms_d = timed(ssc, steps)
-    bytes_d = tp.numel() * 9
-    res["ssc_counts"] = {"ms": ms_d, "algorithmic_GBps": bytes_d / ms_d / 1e6, "frac": bytes_d / ms_d / 1e6 / hbm_peak,
-                         "voxels_per_s": tp.numel() * world / (ms_d * 1e-3), "frames_per_rank": 16,
-                         "allreduce": "nccl int64[9]" if world > 1 else "none (1 rank)"}
+    # cfg1 (BASELINE.json configs[0]): ONE 100 k-point frame, voxel_filter on one CPU core vs the kernel behind the same signature
+    if rank == 0:
+        p1, s1 = synth.carla_lidar_frame(100_000, 1000)
+        grid1 = (0.5, [192, 192, 64], [0.0, 0, -10.0])
+        muvo_b200.voxel_filter(p1, s1, *grid1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            v1, l1 = muvo_b200.voxel_filter(p1, s1, *grid1)
+        t_ours = (time.perf_counter() - t0) / 5
+        from muvo_b200.points import GridSpec as _G, sensor_to_grid as _s2g
+        dp1, ds1 = torch.from_numpy(p1).to(device), torch.from_numpy(s1).to(device)
+        ms_k1 = timed(lambda: _s2g(dp1, ds1, None, grid=_G(), dense=False, sparse=True), steps)
+        ns = ref_namespace()
+        import oracle as O
+        t0 = time.perf_counter()
+        v0, l0 = (ns.voxel_filter if ns is not None else O.voxel_filter_loop)(p1, s1, *grid1)
+        t_ref = time.perf_counter() - t0
+        res["cfg1_voxel_filter"] = {"points": 100_000, "kernel_ms": ms_k1, "numpy_in_numpy_out_ms": 1e3 * t_ours,
+                                    "cpu_ms": 1e3 * t_ref, "cpu_kind": cpu_kind(), "cores": 1,
+                                    "equal": bool(np.array_equal(v1, v0) and np.array_equal(l1, l0)),
+                                    "points_per_s": {"kernel": 1e5 / (ms_k1 * 1e-3), "drop_in_call": 1e5 / t_ours, "cpu": 1e5 / t_ref},
+                                    "vs_reference": {"drop_in_call": t_ref / t_ours, "kernel": 1e3 * t_ref / ms_k1},
+                                    "note": "data/generate_voxels.py voxelisation of one CARLA-style frame: voxel_filter(pcd, sem, 0.5, "
+                                            "[192,192,64], [0,0,-10]) NumPy in / NumPy out (H2D + kernels + D2H) vs one CPU core"}
+        del dp1, ds1
     # N4: SemScalLoss + GeoScalLoss on the voxel logits of the same 16 frames (C = 2, fp32), forward and backward
     from muvo_b200.losses import scal_losses
     gen = torch.Generator(device=device).manual_seed(4100 + rank)
@@ -432,6 +595,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-stages", action="store_true", help="skip the BEV-pool / IoU stage numbers")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg5"],
+                    help="cfg2 = BASELINE.json configs[1] (the headline); cfg5 = configs[4], the 1M-point-frame scaling sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1,9 +1,11 @@
-"""Import the UNMODIFIED reference functions (build container only).
+"""Import the UNMODIFIED reference functions.
 
-TEST INFRASTRUCTURE ONLY.  ``/root/reference`` does not exist on the GPU box, so
-nothing that runs there (``-m gpu`` tests, ``smoke()``, ``bench.py``) may call this.
-It is used by ``tests/golden/make_golden.py`` (to freeze golden vectors) and by
-``tests/test_oracle_vs_reference.py`` (skipped when the checkout is absent).
+TEST / BASELINE INFRASTRUCTURE ONLY -- the product (``muvo_b200/``) never imports this.
+Resolution order: ``$MUVO_REFERENCE_ROOT``, ``/root/reference`` (the build container), ``baseline/_ref`` (the unmodified
+copy that ``tools/install_reference.py`` / ``__graft_entry__.build()`` leave next to the repo; git-ignored, but it travels
+to the GPU box, where ``/root/reference`` does not exist).  Used by ``tests/golden/make_golden.py`` (golden vectors),
+``tests/test_oracle_vs_reference.py`` / ``tests/test_reference_integration.py`` (skipped when nothing resolves) and by
+``bench.py``'s reference arm and ``cpu_baseline`` / stage baselines (falling back to the oracle port otherwise).
 
 Optional third-party imports of the reference that are not installed here
 (open3d, carla, chamferdist, timm, torch_scatter) are replaced by ``MagicMock``
@@ -16,7 +18,18 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("MUVO_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _resolve() -> str:
+    cands = [os.environ.get("MUVO_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "muvo", "metrics.py")):
+            return c
+    return cands[1]
+
+
+REFERENCE_ROOT = _resolve()
 _STUBS = ["open3d", "carla", "chamferdist", "timm", "timm.models", "timm.models.resnet", "torch_scatter"]
 
 
