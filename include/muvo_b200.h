@@ -185,6 +185,14 @@ MUVO_API int muvo_bev_fold_mask(const int32_t* cell0, const uint8_t* mask, int64
 MUVO_API int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
                       const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells, float* out,
                       void* ws, size_t ws_bytes, void* stream);
+/* FrustumPooling.forward as the module calls it (frustum_pooling.py:189-209 with the mask of mile.py:512-514): cell0 = the
+ * cached mask-independent cell ids, mask = the top-k depth mask as uint8 [B, n_pts] (nullptr = no mask), cell_out [B, n_pts]
+ * receives cell0 with the mask folded in (what muvo_bev_pool_bwd needs).  When x is (B, C, D, H, W) memory (x_stride_p == 1,
+ * 16-byte aligned rows) the tensor is streamed through shared memory with TMA bulk copies instead of gathered
+ * (bev_stream.cu); otherwise this is muvo_bev_fold_mask + muvo_bev_pool_fwd.  Same output contract as muvo_bev_pool_fwd. */
+MUVO_API int muvo_bev_pool_fwd_masked(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
+                      const int32_t* cell0, const uint8_t* mask, int32_t* cell_out, int32_t B, int64_t n_pts, int32_t C,
+                      int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream);
 /* grad_x[b,p,c] = cell[b,p] >= 0 ? grad_out[b,c,cell[b,p]] : 0  (frustum_pooling.py:52-60 + index bwd);
  * grad_x is written with the given element strides (every element written).         */
 MUVO_API int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C,

@@ -23,7 +23,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
 PER_FILE = {"points.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split(),
             "points_mega.cu": ["-fmad=false"] + os.environ.get("MUVO_NVCC_EXTRA", "").split(),
             "merge.cu": ["-fmad=false"]}   # MUVO_NVCC_EXTRA: tuning builds only
-SOURCES = ["api.cu", "points.cu", "points_mega.cu", "ssc.cu", "bev.cu", "merge.cu", "pyramid.cu", "scal.cu", "pillar.cu"]
+SOURCES = ["api.cu", "points.cu", "points_mega.cu", "ssc.cu", "bev.cu", "bev_stream.cu", "merge.cu", "pyramid.cu", "scal.cu", "pillar.cu"]
 
 
 def _nvcc() -> str:
@@ -43,14 +43,14 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "points_dev.cuh"), os.path.join(INCLUDE, "muvo_b200.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "points_dev.cuh"), os.path.join(CSRC, "tma.cuh"), os.path.join(CSRC, "bev_stream.cuh"), os.path.join(INCLUDE, "muvo_b200.h")]
     objs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(src, []), "-I", INCLUDE, "-c", s, "-o", o]
+            cmd = [nvcc, *ARCH, *COMMON, *PER_FILE.get(src, []), *os.environ.get("MUVO_NVCC_ALL", "").split(), "-I", INCLUDE, "-c", s, "-o", o]
             if verbose:
                 cmd[1:1] = ["-Xptxas", "-v"]
                 print(" ".join(cmd), flush=True)

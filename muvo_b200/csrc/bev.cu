@@ -19,7 +19,9 @@
 // Backward: pure gather, every grad_x element written once, in the producer's memory format.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "common.cuh"
+#include "bev_stream.cuh"
 
 namespace muvo {
 namespace {
@@ -49,6 +51,8 @@ struct BevWs {
   int32_t* dest = nullptr;          // [B, n_pts]  ... and their position in `sorted`
   uint16_t* dest16 = nullptr;       // [B, n_pts]  `dest` as uint16 (saturated; read only for frames with <= 32768 kept points)
   uint32_t* chunk_kept = nullptr;   // [B, n_wc]   kept points per warp-chunk, scanned in place by S3
+  uint32_t* lists = nullptr;        // [B, n_chunks, 2048]  streamed pool: per-chunk sorted (cell, position) lists, lane-interleaved
+  uint32_t* steps = nullptr;        // [B, n_chunks]        ... and their length in warp steps
   int n_wc = 0;
   size_t bytes = 0;
 };
@@ -66,6 +70,8 @@ static BevWs carve_bev(void* base, int B, int64_t n_pts, int n_cells) {
   w.dest = (int32_t*)(b + o);        o = align_up(o + (size_t)B * n_pts * 4, 256);
   w.dest16 = (uint16_t*)(b + o);     o = align_up(o + (size_t)B * n_pts * 2, 256);
   w.chunk_kept = (uint32_t*)(b + o); o = align_up(o + (size_t)B * w.n_wc * 4, 256);
+  w.lists = (uint32_t*)(b + o);      o = align_up(o + stream_lists_bytes(B, n_pts), 256);
+  w.steps = (uint32_t*)(b + o);      o = align_up(o + stream_steps_bytes(B, n_pts), 256);
   w.bytes = o;
   return w;
 }
@@ -1004,6 +1010,11 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
                         int n_cells, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
   BevWs w = carve_bev(ws, B, n_pts, n_cells);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+  if (pool_stream_eligible((int)sizeof(T), x, sb, sp, sc, B, n_pts, C, n_cells)) {     // (B, C, D, H, W) memory: stream it (bev_stream.cu)
+    prof_mark("<bev_fwd>", st);
+    return pool_stream_fwd(x, sizeof(T) == 4 ? MUVO_F32 : (std::is_same<T, __half>::value ? MUVO_F16 : MUVO_BF16), sb, sc, cell, nullptr,
+                           nullptr, B, n_pts, C, n_cells, out, w.lists, w.steps, st);
+  }
   const size_t smem = (size_t)kSortWarps * n_cells * 4;
   if (smem > 200 * 1024) return MUVO_E_SHAPE;
   if (smem > 48 * 1024) {
@@ -1141,6 +1152,36 @@ int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_
     case MUVO_BF16: return run_pool_fwd<__nv_bfloat16>((const __nv_bfloat16*)x, x_stride_b, x_stride_p, x_stride_c, cell, B, n_pts, C, n_cells, out, ws, ws_bytes, st);
     default: return MUVO_E_ARG;
   }
+}
+
+int muvo_bev_pool_fwd_masked(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
+                             const int32_t* cell0, const uint8_t* mask, int32_t* cell_out, int32_t B, int64_t n_pts, int32_t C,
+                             int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream) {
+  if (B < 0 || n_pts < 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || C == 0) return MUVO_OK;
+  if (!out || !ws || !cell_out) return MUVO_E_NULL;
+  if (n_pts > 0 && (!x || !cell0)) return MUVO_E_NULL;
+  if (x_dtype != MUVO_F32 && x_dtype != MUVO_F16 && x_dtype != MUVO_BF16) return MUVO_E_ARG;
+  if (n_pts >= ((int64_t)1 << 31) || (int64_t)B * n_cells >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
+  if (reinterpret_cast<uintptr_t>(ws) & 255) return MUVO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int eb = x_dtype == MUVO_F32 ? 4 : 2;
+  if (pool_stream_eligible(eb, x, x_stride_b, x_stride_p, x_stride_c, B, n_pts, C, n_cells)) {
+    BevWs w = carve_bev(ws, B, n_pts, n_cells);
+    if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
+    prof_mark("<bev_fwd>", st);
+    return pool_stream_fwd(x, x_dtype, x_stride_b, x_stride_c, cell0, mask, cell_out, B, n_pts, C, n_cells, out, w.lists, w.steps, st);
+  }
+  // gather path: fold the mask first (frustum_pooling.py:153-156), then the index sort + row kernels
+  const int64_t n = (int64_t)B * n_pts;
+  if (mask) {
+    int rc = muvo_bev_fold_mask(cell0, mask, n, cell_out, stream);
+    if (rc != MUVO_OK) return rc;
+  } else if (n > 0) {
+    cudaError_t e = cudaMemcpyAsync(cell_out, cell0, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return muvo_bev_pool_fwd(x, x_dtype, x_stride_b, x_stride_p, x_stride_c, cell_out, B, n_pts, C, n_cells, out, ws, ws_bytes, stream);
 }
 
 int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells,

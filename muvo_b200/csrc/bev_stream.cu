@@ -1,0 +1,307 @@
+// Stage (c), streamed forward: out[b, c, cell] = sum of x[b, p, c] over the kept frustum points p of the cell
+// (FrustumPooling.voxel_pooling, muvo/models/frustum_pooling.py:131-187, for the lifted tensor of mile.py:517-521 whose
+// memory is (B, C, D, H, W): every channel row is contiguous in the point index).
+//
+// The gather kernels of bev.cu read only the kept elements, but a top-k depth mask leaves ~92 % of the 32-byte sectors of
+// the tensor touched, so they move the whole tensor anyway, one scattered sector at a time (3.6x the algorithmic bytes,
+// 36 % of the HBM rate).  Here the tensor is STREAMED: a producer warp moves [8 channels x 2048 points] tiles into a
+// shared-memory ring with cp.async.bulk (TMA) + mbarriers, and the segment sums are formed from shared memory:
+//
+//   L  k_chunk_lists : per (frame, chunk of 2048 points): keys (cell << 11 | position) of the kept points, mask folded in,
+//                      bitonic-sorted in shared memory (= stable by cell, ascending point order inside a cell) and written
+//                      lane-interleaved: lane l of a warp owns the contiguous run [l*m, (l+1)*m) of the sorted list.
+//   P  k_pool_stream : one CTA per (frame, 8 channels), walking the chunks in order; consumer warp w owns channel w, so its
+//                      accumulators (n_cells floats in shared memory) are private: no atomics, no CTA-wide barrier.  A lane
+//                      sums its run sequentially; the segment that a run shares with the previous lanes (its first cell)
+//                      is combined by a fixed shuffle tree.  The summation order is a function of (geometry, mask) only:
+//                      deterministic, and within the fp32 tolerance of the reference's cumsum differencing.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "bev_stream.cuh"
+#include "tma.cuh"
+
+namespace muvo {
+namespace {
+
+constexpr int kSCh = 8;                            // channels per CTA = consumer warps
+constexpr int kSThreads = (kSCh + 1) * 32;         // + one producer warp
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr uint32_t kPosMask = (1u << kStreamPosBits) - 1u;
+constexpr int kListThreads = kStreamChunk / 2;
+constexpr int kSVirt = kSCh * 32;                  // consumer threads = virtual lanes of a chunk list
+__host__ __device__ constexpr size_t align_up16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---------------------------------------------------------------- L: per-chunk sorted lists
+// lists[b][k][i * 256 + v] = sorted[v * m + i]: "virtual lane" v (= thread of the pool kernel's 8 consumer warps) owns the
+// contiguous run [v*m, (v+1)*m) of the chunk's sorted key list, m = ceil(n / 256) = steps[b][k].
+__global__ void __launch_bounds__(kListThreads)
+k_chunk_lists(const int32_t* __restrict__ cell0, const uint8_t* __restrict__ mask, int32_t* __restrict__ cell_out, int64_t n_pts,
+              int n_cells, int n_chunks, uint32_t* __restrict__ lists, uint32_t* __restrict__ steps) {
+  __shared__ uint32_t s[kStreamChunk];
+  __shared__ int n_s;
+  const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+  const int64_t base = (int64_t)k * kStreamChunk;
+  if (tid == 0) n_s = 0;
+#pragma unroll
+  for (int r = 0; r < kStreamChunk / kListThreads; ++r) {
+    const int i = tid + r * kListThreads;
+    const int64_t p = base + i;
+    uint32_t key = kNone;
+    if (p < n_pts) {
+      int32_t c = __ldg(cell0 + (int64_t)b * n_pts + p);
+      if (mask && !__ldg(mask + (int64_t)b * n_pts + p)) c = -1;
+      if (cell_out) cell_out[(int64_t)b * n_pts + p] = c;
+      if (c >= 0 && c < n_cells) key = ((uint32_t)c << kStreamPosBits) | (uint32_t)i;
+    }
+    s[i] = key;
+  }
+  __syncthreads();
+  // bitonic sort, ascending (dropped points = 0xffffffff end up last)
+  for (int kk = 2; kk <= kStreamChunk; kk <<= 1) {
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      const int t = tid;
+      const int i = 2 * t - (t & (j - 1));             // lower element of the pair (bit j clear)
+      const uint32_t a = s[i], c = s[i + j];
+      const bool up = (i & kk) == 0;
+      if ((a > c) == up) { s[i] = c; s[i + j] = a; }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kStreamChunk / kListThreads; ++r) {
+    const int i = tid + r * kListThreads;
+    if (s[i] != kNone && (i == kStreamChunk - 1 || s[i + 1] == kNone)) n_s = i + 1;
+  }
+  __syncthreads();
+  const int n = n_s, m = (n + kSVirt - 1) / kSVirt;
+  uint32_t* out = lists + ((size_t)b * n_chunks + k) * kStreamChunk;
+  for (int idx = tid; idx < m * kSVirt; idx += kListThreads) {
+    const int src = (idx % kSVirt) * m + (idx / kSVirt);
+    out[idx] = src < n ? s[src] : kNone;
+  }
+  if (tid == 0) steps[(size_t)b * n_chunks + k] = (uint32_t)m;
+}
+
+// ---------------------------------------------------------------- P: streamed pool
+__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kSVirt) : "memory"); }
+
+template <typename T, int NS>
+__global__ void __launch_bounds__(kSThreads, 1)
+k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* __restrict__ lists, const uint32_t* __restrict__ steps,
+              int B, int64_t n_pts, int C, int n_cells, int n_chunks, float* __restrict__ out, int flags) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr size_t kChanBytes = (size_t)kStreamChunk * sizeof(T);
+  constexpr size_t kTileBytes = kChanBytes * kSCh;
+  constexpr size_t kListBytes = (size_t)kStreamChunk * 4;
+  constexpr size_t kStageBytes = kTileBytes + kListBytes;
+  // [NS stages: 8 channel tiles + the chunk's list] [acc: 8 x n_cells floats] [carry: 8 warps x 8 floats, 8 cells] [m per stage] [barriers]
+  float* acc = reinterpret_cast<float*>(smem + NS * kStageBytes);
+  const size_t acc_bytes = align_up16((size_t)kSCh * n_cells * 4);
+  float* carry = reinterpret_cast<float*>(smem + NS * kStageBytes + acc_bytes);
+  uint32_t* carry_cell = reinterpret_cast<uint32_t*>(carry + kSCh * kSCh);
+  int* mstep = reinterpret_cast<int*>(carry_cell + kSCh);
+  uint64_t* full = reinterpret_cast<uint64_t*>(mstep + 8);
+  uint64_t* empty = full + NS;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned lane = lane_id();
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, kSCh); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int n_cg = (C + kSCh - 1) / kSCh;
+  const int items = B * n_cg;
+  if (warp == kSCh) {
+    // ---- producer: one elected lane issues every bulk copy of this CTA
+    if (lane == 0) {
+      const uint64_t pol = l2_evict_first_policy();
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int b = item / n_cg, c0 = (item % n_cg) * kSCh;
+        const int nc = C - c0 < kSCh ? C - c0 : kSCh;
+        const T* xb = x + (int64_t)b * sb + (int64_t)c0 * sc;
+        const uint32_t* mb = steps + (size_t)b * n_chunks;
+        uint32_t m_next = __ldg(mb);
+        for (int k = 0; k < n_chunks; ++k, ++it) {
+          const int s = it % NS;
+          const uint32_t use = it / NS;
+          const uint32_t m = m_next;
+          if (k + 1 < n_chunks) m_next = __ldg(mb + k + 1);
+          if (use > 0) mbar_wait(empty + s, (use - 1) & 1u);
+          unsigned char* sbase = smem + s * kStageBytes;
+          const int64_t p0 = (int64_t)k * kStreamChunk;
+          const uint32_t bytes = (uint32_t)((n_pts - p0 < kStreamChunk ? n_pts - p0 : kStreamChunk) * sizeof(T));
+          mstep[s] = (int)m;                                           // ordered before the copies' completion by the barrier
+          mbar_expect_tx(full + s, bytes * nc + m * kSVirt * 4);
+          if (m) bulk_g2s(sbase + kTileBytes, lists + ((size_t)b * n_chunks + k) * kStreamChunk, m * kSVirt * 4, full + s, l2_default_policy());
+          for (int c = 0; c < nc; ++c) bulk_g2s(sbase + c * kChanBytes, xb + (int64_t)c * sc + p0, bytes, full + s, pol);
+        }
+      }
+    }
+    return;
+  }
+  // ---- consumers: thread v = virtual lane v of every chunk list, all 8 channels
+  uint32_t it = 0;
+  for (int i = tid; i < kSCh * n_cells; i += kSVirt) acc[i] = 0.f;
+  bar_consumers();
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / n_cg, c0 = (item % n_cg) * kSCh;
+    const int nc = C - c0 < kSCh ? C - c0 : kSCh;
+    for (int k = 0; k < n_chunks; ++k, ++it) {
+      const int s = it % NS;
+      mbar_wait(full + s, (it / NS) & 1u);
+      const unsigned char* sbase = smem + s * kStageBytes;
+      const T* st = reinterpret_cast<const T*>(sbase);
+      const uint32_t* L = reinterpret_cast<const uint32_t*>(sbase + kTileBytes);
+      const int m = (flags & 1) ? 0 : mstep[s];
+      uint32_t cur = kNone, fcell = kNone;
+      float run[kSCh], fp[kSCh];
+#pragma unroll
+      for (int c = 0; c < kSCh; ++c) { run[c] = 0.f; fp[c] = 0.f; }
+      bool first = true;
+      auto close = [&]() {          // the run of `cur` ends: the thread's first cell goes through the shuffle tree / carries, the
+        if (cur != kNone) {         // others are cells that START inside this thread's run -> nobody else adds to them directly
+          if (first) {
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) fp[c] = run[c];
+            fcell = cur; first = false;
+          } else {
+            float a[kSCh];
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) a[c] = acc[c * n_cells + cur];
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) acc[c * n_cells + cur] = a[c] + run[c];
+          }
+        }
+      };
+      for (int i = 0; i < m; ++i) {
+        const uint32_t e = L[i * kSVirt + tid];
+        if (e != kNone) {
+          const uint32_t cell = e >> kStreamPosBits, pos = e & kPosMask;
+          float v[kSCh];
+#pragma unroll
+          for (int c = 0; c < kSCh; ++c) v[c] = to_f32<T>(st[c * kStreamChunk + pos]);
+          if (cell != cur) {
+            close();
+            cur = cell;
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) run[c] = 0.f;
+          }
+#pragma unroll
+          for (int c = 0; c < kSCh; ++c) run[c] += v[c];
+        }
+      }
+      close();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);                             // the tile is consumed: the producer may refill the stage
+      // first cells: threads with entries form a prefix and their first cells are non-decreasing; segmented inclusive scan
+      // inside the warp (fixed tree), the run that reaches lane 0 may continue the previous warp's: it goes to `carry`
+      if (m > 0) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t cu = __shfl_up_sync(0xffffffffu, fcell, off);
+          const bool add = lane >= (unsigned)off && cu == fcell;
+#pragma unroll
+          for (int c = 0; c < kSCh; ++c) {
+            const float t = __shfl_up_sync(0xffffffffu, fp[c], off);
+            if (add) fp[c] += t;
+          }
+        }
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, fcell, 1);
+        const uint32_t head = __shfl_sync(0xffffffffu, fcell, 0);
+        if (lane == 0 && head == kNone) carry_cell[warp] = kNone;
+        if (fcell != kNone && (lane == 31u || nxt != fcell)) {
+          if (warp > 0 && fcell == head) {
+            carry_cell[warp] = fcell;
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) carry[warp * kSCh + c] = fp[c];
+          } else {
+            float a[kSCh];
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) a[c] = acc[c * n_cells + fcell];
+#pragma unroll
+            for (int c = 0; c < kSCh; ++c) acc[c * n_cells + fcell] = a[c] + fp[c];
+          }
+        }
+        bar_consumers();
+        if (tid < kSCh) {                                                  // thread c folds channel c's carries in warp order
+#pragma unroll
+          for (int w = 1; w < kSCh; ++w) {
+            const uint32_t cc = carry_cell[w];
+            if (cc != kNone) acc[tid * n_cells + cc] += carry[w * kSCh + tid];
+          }
+        }
+        bar_consumers();
+      }
+    }
+    // the item's 8 x n_cells sums -> out (contiguous: channels c0 .. c0 + nc - 1 of frame b), accumulators back to zero
+    float* o = out + ((size_t)b * C + c0) * n_cells;
+    const int n_out = nc * n_cells;
+    for (int i = tid; i < kSCh * n_cells; i += kSVirt) {
+      if (i < n_out) o[i] = acc[i];
+      acc[i] = 0.f;
+    }
+    bar_consumers();
+  }
+}
+
+template <typename T> constexpr int stages_for() { return (128 * 1024) / (kSCh * kStreamChunk * (int)sizeof(T)); }   // 128 KiB of tiles in the ring
+
+template <typename T>
+size_t stream_smem_bytes(int n_cells) {
+  return (size_t)stages_for<T>() * ((size_t)kSCh * kStreamChunk * sizeof(T) + (size_t)kStreamChunk * 4) + align_up16((size_t)kSCh * n_cells * 4) +
+         (size_t)kSCh * kSCh * 4 + kSCh * 4 + 32 + 2 * stages_for<T>() * 8;
+}
+
+template <typename T>
+int launch_stream(const T* x, int64_t sb, int64_t sc, const uint32_t* lists, const uint32_t* steps, int B, int64_t n_pts, int C,
+                  int n_cells, int n_chunks, float* out, cudaStream_t st) {
+  constexpr int NS = stages_for<T>();
+  const size_t smem = stream_smem_bytes<T>(n_cells);
+  cudaError_t e = cudaFuncSetAttribute(k_pool_stream<T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int sms = kNumSMsB200;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int items = B * ((C + kSCh - 1) / kSCh);
+  k_pool_stream<T, NS><<<(unsigned)(items < sms ? items : sms), kSThreads, smem, st>>>(x, sb, sc, lists, steps, B, n_pts, C, n_cells,
+                                                                                      n_chunks, out, g_tuning[3]);
+  MUVO_AFTER_LAUNCH("k_pool_stream", st);
+  return MUVO_OK;
+}
+
+}  // namespace
+
+size_t stream_lists_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * kStreamChunk * 4; }
+size_t stream_steps_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * 4; }
+
+bool pool_stream_eligible(int elem_bytes, const void* x, int64_t sb, int64_t sp, int64_t sc, int B, int64_t n_pts, int C, int n_cells) {
+  if (g_tuning[2] == 1 || g_tuning[2] == 2) return false;     // tuning key 2: 1 / 2 = the gather kernels of bev.cu, 3 = always stream
+  if (sp != 1 || n_pts <= 0 || B <= 0 || C <= 0) return false;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (sb * elem_bytes) % 16 || (sc * elem_bytes) % 16 || (n_pts * elem_bytes) % 16) return false;
+  if (n_cells >= (1 << (32 - kStreamPosBits)) - 1) return false;
+  const size_t smem = elem_bytes == 4 ? stream_smem_bytes<float>(n_cells) : stream_smem_bytes<__half>(n_cells);
+  if (smem > 227 * 1024) return false;
+  // one CTA per (frame, 8 channels): with fewer items than ~half the SMs the row kernels (one CTA per channel row) are faster
+  return g_tuning[2] == 3 || (int64_t)B * ((C + kSCh - 1) / kSCh) >= 64;
+}
+
+int pool_stream_fwd(const void* x, int32_t x_dtype, int64_t sb, int64_t sc, const int32_t* cell0, const uint8_t* mask,
+                    int32_t* cell_out, int B, int64_t n_pts, int C, int n_cells, float* out, uint32_t* lists, uint32_t* steps,
+                    cudaStream_t st) {
+  const int n_chunks = (int)ceil_div64(n_pts, kStreamChunk);
+  k_chunk_lists<<<dim3((unsigned)n_chunks, (unsigned)B), kListThreads, 0, st>>>(cell0, mask, cell_out, n_pts, n_cells, n_chunks, lists, steps);
+  MUVO_AFTER_LAUNCH("k_chunk_lists", st);
+  switch (x_dtype) {
+    case MUVO_F32:  return launch_stream<float>((const float*)x, sb, sc, lists, steps, B, n_pts, C, n_cells, n_chunks, out, st);
+    case MUVO_F16:  return launch_stream<__half>((const __half*)x, sb, sc, lists, steps, B, n_pts, C, n_cells, n_chunks, out, st);
+    case MUVO_BF16: return launch_stream<__nv_bfloat16>((const __nv_bfloat16*)x, sb, sc, lists, steps, B, n_pts, C, n_cells, n_chunks, out, st);
+    default: return MUVO_E_ARG;
+  }
+}
+
+}  // namespace muvo

@@ -4,6 +4,7 @@
 #pragma once
 #include <math.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace muvo {
 
@@ -327,37 +328,6 @@ __device__ __forceinline__ int find_frame(const int64_t* __restrict__ off, int F
 __device__ __forceinline__ void diag_add(int64_t* diag, int slot, unsigned v) {
   unsigned tot = __reduce_add_sync(0xffffffffu, v);
   if (tot && lane_id() == 0) atomicAdd(reinterpret_cast<unsigned long long*>(diag + slot), (unsigned long long)tot);
-}
-
-// ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+ PTX)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// read-once stream: evict-first in L2 so that the L2-resident tables (bitmap, pixel words, slots) survive next to it
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "MUVO_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra MUVO_DONE;\n"
-      "bra MUVO_WAIT;\n"
-      "MUVO_DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
 // ---------------------------------------------------------------- exact tie protocol (rare path)

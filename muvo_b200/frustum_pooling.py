@@ -110,6 +110,48 @@ class _BevPool(torch.autograd.Function):
         return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None
 
 
+class _BevPoolMasked(torch.autograd.Function):
+    """``bev_pool(x, fold_mask(cell0, mask))`` as ONE library call (``muvo_bev_pool_fwd_masked``): the mask is folded in by
+    the kernel that builds the per-chunk cell lists, and (B, C, D, H, W) memory is streamed instead of gathered."""
+
+    @staticmethod
+    def forward(ctx, x, cell0, mask, n_cells):
+        _lib.require_cuda(x, cell0)
+        if x.dtype not in _FLOAT_DTYPES:
+            raise TypeError(f"unsupported feature dtype {x.dtype}")
+        lib = _lib.load()
+        xv, sb, sp, sc, n_pts = _strides_bpc(x)
+        B, Cc = x.shape[0], x.shape[5]
+        dev = x.device
+        cell0 = cell0.reshape(B, n_pts).contiguous()
+        m = None
+        if mask is not None and mask.numel() > 0:
+            m = mask.reshape(-1)
+            m = (m if m.dtype in (torch.bool, torch.uint8) else m.bool()).contiguous().view(torch.uint8)
+            if m.numel() != cell0.numel():
+                raise ValueError("mask and cell ids differ in size")
+        cell = torch.empty_like(cell0)
+        out = torch.empty((B, Cc, n_cells), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            stream = _lib.current_stream(dev)
+            nb = C.c_size_t(0)
+            _lib.check(lib.muvo_bev_pool_workspace_bytes(B, n_pts, n_cells, C.byref(nb)), "muvo_bev_pool_workspace_bytes")
+            ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+            rc = lib.muvo_bev_pool_fwd_masked(_lib.ptr(xv), _FLOAT_DTYPES[xv.dtype], sb, sp, sc, _lib.ptr(cell0),
+                                              _lib.ptr(m) if m is not None else None, _lib.ptr(cell), B, n_pts, Cc, n_cells,
+                                              out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "muvo_bev_pool_fwd_masked")
+        ctx.save_for_backward(cell)
+        ctx.meta = (tuple(x.shape), x.dtype, n_cells, x.stride())
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (cell,) = ctx.saved_tensors
+        shape, dtype, n_cells, xstride = ctx.meta
+        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None, None
+
+
 def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
     """``grad_x[b,p,c] = cell[b,p] >= 0 ? grad_out[b,c,cell[b,p]] : 0`` (frustum_pooling.py:52-60 + index backward).
 
@@ -135,12 +177,23 @@ def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
 
 def bev_pool(x: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
     """``x (B,N,D,H,W,C)`` any strides, ``cell (B, N*D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
+    _check_cells(n_cells)
+    return _BevPool.apply(x, cell, int(n_cells))
+
+
+def _check_cells(n_cells):
     limit = _lib.load().muvo_bev_pool_max_cells()
     if int(n_cells) > limit:
         raise ValueError(f"muvo_b200 BEV pooling supports at most {limit} BEV cells (nx*ny*nz), got {n_cells}: the index sort "
                          "keeps one histogram per warp in shared memory.  MUVO's shipped configs use 48*48*1 = 2304; see "
                          "INTEGRATION.md (limits).")
-    return _BevPool.apply(x, cell, int(n_cells))
+
+
+def bev_pool_masked(x: torch.Tensor, cell0: torch.Tensor, mask, n_cells: int) -> torch.Tensor:
+    """``x (B,N,D,H,W,C)``, mask-independent ``cell0 (B, n_pts) int32``, ``mask`` bool/uint8 with n_pts entries per frame (or
+    empty / None) -> ``(B, C, n_cells)`` fp32: what ``bev_pool(x, fold_mask(cell0, mask), n_cells)`` returns."""
+    _check_cells(n_cells)
+    return _BevPoolMasked.apply(x, cell0, mask, int(n_cells))
 
 
 def fold_mask(cell0: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -365,8 +418,7 @@ class FrustumPooling(nn.Module):
     def _pool_cells(self, x, cell0, mask):
         B, N, D, H, W, Cc = x.shape
         nx, ny, nz = self.nx_constant
-        cell = fold_mask(cell0, mask) if len(mask) > 0 else cell0
-        out = bev_pool(x, cell, nx * ny * nz).view(B, Cc, nz, ny, nx)
+        out = bev_pool_masked(x, cell0, mask if len(mask) > 0 else None, nx * ny * nz).view(B, Cc, nz, ny, nx)
         return out.view(B, Cc, ny, nx) if nz == 1 else out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
 
     def forward(self, x, intrinsics, pose, mask=torch.zeros(0)):
