@@ -191,8 +191,16 @@ MUVO_API int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_
  * 16-byte aligned rows) the tensor is streamed through shared memory with TMA bulk copies instead of gathered
  * (bev_stream.cu); otherwise this is muvo_bev_fold_mask + muvo_bev_pool_fwd.  Same output contract as muvo_bev_pool_fwd. */
 MUVO_API int muvo_bev_pool_fwd_masked(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
-                      const int32_t* cell0, const uint8_t* mask, int32_t* cell_out, int32_t B, int64_t n_pts, int32_t C,
-                      int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream);
+                      const int32_t* cell0, const uint8_t* mask, int32_t* cell_out, const void* plan, int32_t B, int64_t n_pts,
+                      int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream);
+/* The mask-independent half of the streamed forward, cached by the host next to cell0 (per intrinsics / extrinsics / frustum
+ * shape, frustum_pooling.py:111-163): per chunk of 2048 frustum points the kept points' (cell, position) keys in cell-sorted
+ * order.  `plan` (muvo_bev_plan_bytes bytes, 256-byte aligned, caller-owned) may be passed to muvo_bev_pool_fwd_masked
+ * together with the SAME cell0: per call only a stable compaction by the mask remains (no sort).  plan = nullptr: the lists
+ * are sorted per call.                                                                                                     */
+MUVO_API int muvo_bev_plan_bytes(int32_t B, int64_t n_pts, size_t* bytes_out_h);
+MUVO_API int muvo_bev_plan_build(const int32_t* cell0, int32_t B, int64_t n_pts, int32_t n_cells, void* plan, size_t plan_bytes,
+                      void* stream);
 /* grad_x[b,p,c] = cell[b,p] >= 0 ? grad_out[b,c,cell[b,p]] : 0  (frustum_pooling.py:52-60 + index bwd);
  * grad_x is written with the given element strides (every element written).         */
 MUVO_API int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C,

@@ -1013,7 +1013,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   if (pool_stream_eligible((int)sizeof(T), x, sb, sp, sc, B, n_pts, C, n_cells)) {     // (B, C, D, H, W) memory: stream it (bev_stream.cu)
     prof_mark("<bev_fwd>", st);
     return pool_stream_fwd(x, sizeof(T) == 4 ? MUVO_F32 : (std::is_same<T, __half>::value ? MUVO_F16 : MUVO_BF16), sb, sc, cell, nullptr,
-                           nullptr, B, n_pts, C, n_cells, out, w.lists, w.steps, st);
+                           nullptr, nullptr, nullptr, B, n_pts, C, n_cells, out, w.lists, w.steps, st);
   }
   const size_t smem = (size_t)kSortWarps * n_cells * 4;
   if (smem > 200 * 1024) return MUVO_E_SHAPE;
@@ -1154,9 +1154,30 @@ int muvo_bev_pool_fwd(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_
   }
 }
 
+int muvo_bev_plan_bytes(int32_t B, int64_t n_pts, size_t* bytes_out_h) {
+  if (!bytes_out_h) return MUVO_E_NULL;
+  if (B < 0 || n_pts < 0) return MUVO_E_ARG;
+  *bytes_out_h = align_up(stream_lists_bytes(B, n_pts), 256) + align_up(stream_steps_bytes(B, n_pts), 256) + 256;
+  return MUVO_OK;
+}
+
+int muvo_bev_plan_build(const int32_t* cell0, int32_t B, int64_t n_pts, int32_t n_cells, void* plan, size_t plan_bytes, void* stream) {
+  if (B < 0 || n_pts < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || n_pts == 0) return MUVO_OK;
+  if (!cell0 || !plan) return MUVO_E_NULL;
+  if (reinterpret_cast<uintptr_t>(plan) & 255) return MUVO_E_ALIGN;
+  if (n_cells >= (1 << (32 - kStreamPosBits)) - 1) return MUVO_E_SHAPE;
+  size_t need = 0;
+  muvo_bev_plan_bytes(B, n_pts, &need);
+  if (plan_bytes < need - 256) return MUVO_E_WORKSPACE;
+  uint32_t* keys = (uint32_t*)plan;
+  uint32_t* cnt = (uint32_t*)((char*)plan + align_up(stream_lists_bytes(B, n_pts), 256));
+  return pool_stream_plan(cell0, B, n_pts, n_cells, keys, cnt, (cudaStream_t)stream);
+}
+
 int muvo_bev_pool_fwd_masked(const void* x, int32_t x_dtype, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
-                             const int32_t* cell0, const uint8_t* mask, int32_t* cell_out, int32_t B, int64_t n_pts, int32_t C,
-                             int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream) {
+                             const int32_t* cell0, const uint8_t* mask, int32_t* cell_out, const void* plan, int32_t B,
+                             int64_t n_pts, int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream) {
   if (B < 0 || n_pts < 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
   if (B == 0 || C == 0) return MUVO_OK;
   if (!out || !ws || !cell_out) return MUVO_E_NULL;
@@ -1170,7 +1191,10 @@ int muvo_bev_pool_fwd_masked(const void* x, int32_t x_dtype, int64_t x_stride_b,
     BevWs w = carve_bev(ws, B, n_pts, n_cells);
     if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
     prof_mark("<bev_fwd>", st);
-    return pool_stream_fwd(x, x_dtype, x_stride_b, x_stride_c, cell0, mask, cell_out, B, n_pts, C, n_cells, out, w.lists, w.steps, st);
+    const uint32_t* keys = (const uint32_t*)plan;
+    const uint32_t* cnt = plan ? (const uint32_t*)((const char*)plan + align_up(stream_lists_bytes(B, n_pts), 256)) : nullptr;
+    return pool_stream_fwd(x, x_dtype, x_stride_b, x_stride_c, cell0, mask, cell_out, keys, cnt, B, n_pts, C, n_cells, out, w.lists,
+                           w.steps, st);
   }
   // gather path: fold the mask first (frustum_pooling.py:153-156), then the index sort + row kernels
   const int64_t n = (int64_t)B * n_pts;

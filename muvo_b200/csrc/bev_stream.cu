@@ -41,7 +41,7 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 // contiguous run [v*m, (v+1)*m) of the chunk's sorted key list, m = ceil(n / 256) = steps[b][k].
 __global__ void __launch_bounds__(kListThreads)
 k_chunk_lists(const int32_t* __restrict__ cell0, const uint8_t* __restrict__ mask, int32_t* __restrict__ cell_out, int64_t n_pts,
-              int n_cells, int n_chunks, uint32_t* __restrict__ lists, uint32_t* __restrict__ steps) {
+              int n_cells, int n_chunks, uint32_t* __restrict__ lists, uint32_t* __restrict__ steps, int plan_mode) {
   __shared__ uint32_t s[kStreamChunk];
   __shared__ int n_s;
   const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
@@ -80,11 +80,71 @@ k_chunk_lists(const int32_t* __restrict__ cell0, const uint8_t* __restrict__ mas
   __syncthreads();
   const int n = n_s, m = (n + kSVirt - 1) / kSVirt;
   uint32_t* out = lists + ((size_t)b * n_chunks + k) * kStreamChunk;
+  if (plan_mode) {                // the mask-independent plan: the sorted keys as they are + their count (k_chunk_compact's input)
+    for (int idx = tid; idx < kStreamChunk; idx += kListThreads) out[idx] = s[idx];
+    if (tid == 0) steps[(size_t)b * n_chunks + k] = (uint32_t)n;
+    return;
+  }
   for (int idx = tid; idx < m * kSVirt; idx += kListThreads) {
     const int src = (idx % kSVirt) * m + (idx / kSVirt);
     out[idx] = src < n ? s[src] : kNone;
   }
   if (tid == 0) steps[(size_t)b * n_chunks + k] = (uint32_t)m;
+}
+
+// Per call, with a cached plan: keep the plan entries whose mask byte is set (a stable compaction: the order by cell, then
+// by point, survives), write them lane-interleaved like k_chunk_lists, and write the folded cell ids the backward needs.
+constexpr int kCompactThreads = 256;
+constexpr int kCompactPer = kStreamChunk / kCompactThreads;
+__global__ void __launch_bounds__(kCompactThreads)
+k_chunk_compact(const uint32_t* __restrict__ plan, const uint32_t* __restrict__ plan_n, const int32_t* __restrict__ cell0,
+                const uint8_t* __restrict__ mask, int32_t* __restrict__ cell_out, int64_t n_pts, int n_chunks,
+                uint32_t* __restrict__ lists, uint32_t* __restrict__ steps) {
+  __shared__ __align__(16) uint8_t ms[kStreamChunk];
+  __shared__ uint32_t cs[kStreamChunk];
+  __shared__ uint32_t wsum[kCompactThreads / 32];
+  const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+  const unsigned lane = lane_id();
+  const int64_t base = (int64_t)b * n_pts + (int64_t)k * kStreamChunk;
+  const int64_t left = n_pts - (int64_t)k * kStreamChunk;
+  const int npt = left < kStreamChunk ? (int)left : kStreamChunk;
+  for (int i = tid; i < npt; i += kCompactThreads) {
+    const uint8_t mk = mask ? __ldg(mask + base + i) : (uint8_t)1;
+    ms[i] = mk;
+    if (cell_out) cell_out[base + i] = mk ? __ldg(cell0 + base + i) : -1;
+  }
+  __syncthreads();
+  const size_t slot = (size_t)b * n_chunks + k;
+  const int n0 = (int)__ldg(plan_n + slot);
+  const uint32_t* pl = plan + slot * kStreamChunk;
+  uint32_t e[kCompactPer];
+  uint32_t keep = 0;
+#pragma unroll
+  for (int u = 0; u < kCompactPer; ++u) {
+    const int idx = tid * kCompactPer + u;
+    e[u] = idx < n0 ? __ldg(pl + idx) : kNone;
+    if (e[u] != kNone && ms[e[u] & kPosMask]) keep |= 1u << u;
+  }
+  const uint32_t cnt = __popc(keep);
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += t; }
+  if (lane == 31) wsum[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t wbase = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kCompactThreads / 32; ++w) { const uint32_t t = wsum[w]; if (w < (tid >> 5)) wbase += t; total += t; }
+  uint32_t o = wbase + incl - cnt;
+#pragma unroll
+  for (int u = 0; u < kCompactPer; ++u) if (keep & (1u << u)) cs[o++] = e[u];
+  __syncthreads();
+  const int n = (int)total, m = (n + kSVirt - 1) / kSVirt;
+  uint32_t* out = lists + slot * kStreamChunk;
+  for (int idx = tid; idx < m * kSVirt; idx += kCompactThreads) {
+    const int src = (idx % kSVirt) * m + (idx / kSVirt);
+    out[idx] = src < n ? cs[src] : kNone;
+  }
+  if (tid == 0) steps[slot] = (uint32_t)m;
 }
 
 // ---------------------------------------------------------------- P: streamed pool
@@ -290,12 +350,24 @@ bool pool_stream_eligible(int elem_bytes, const void* x, int64_t sb, int64_t sp,
   return g_tuning[2] == 3 || (int64_t)B * ((C + kSCh - 1) / kSCh) >= 64;
 }
 
-int pool_stream_fwd(const void* x, int32_t x_dtype, int64_t sb, int64_t sc, const int32_t* cell0, const uint8_t* mask,
-                    int32_t* cell_out, int B, int64_t n_pts, int C, int n_cells, float* out, uint32_t* lists, uint32_t* steps,
-                    cudaStream_t st) {
+int pool_stream_plan(const int32_t* cell0, int B, int64_t n_pts, int n_cells, uint32_t* plan, uint32_t* plan_n, cudaStream_t st) {
   const int n_chunks = (int)ceil_div64(n_pts, kStreamChunk);
-  k_chunk_lists<<<dim3((unsigned)n_chunks, (unsigned)B), kListThreads, 0, st>>>(cell0, mask, cell_out, n_pts, n_cells, n_chunks, lists, steps);
+  k_chunk_lists<<<dim3((unsigned)n_chunks, (unsigned)B), kListThreads, 0, st>>>(cell0, nullptr, nullptr, n_pts, n_cells, n_chunks, plan, plan_n, 1);
   MUVO_AFTER_LAUNCH("k_chunk_lists", st);
+  return MUVO_OK;
+}
+
+int pool_stream_fwd(const void* x, int32_t x_dtype, int64_t sb, int64_t sc, const int32_t* cell0, const uint8_t* mask,
+                    int32_t* cell_out, const uint32_t* plan, const uint32_t* plan_n, int B, int64_t n_pts, int C, int n_cells,
+                    float* out, uint32_t* lists, uint32_t* steps, cudaStream_t st) {
+  const int n_chunks = (int)ceil_div64(n_pts, kStreamChunk);
+  if (plan && plan_n) {
+    k_chunk_compact<<<dim3((unsigned)n_chunks, (unsigned)B), kCompactThreads, 0, st>>>(plan, plan_n, cell0, mask, cell_out, n_pts, n_chunks, lists, steps);
+    MUVO_AFTER_LAUNCH("k_chunk_compact", st);
+  } else {
+    k_chunk_lists<<<dim3((unsigned)n_chunks, (unsigned)B), kListThreads, 0, st>>>(cell0, mask, cell_out, n_pts, n_cells, n_chunks, lists, steps, 0);
+    MUVO_AFTER_LAUNCH("k_chunk_lists", st);
+  }
   switch (x_dtype) {
     case MUVO_F32:  return launch_stream<float>((const float*)x, sb, sc, lists, steps, B, n_pts, C, n_cells, n_chunks, out, st);
     case MUVO_F16:  return launch_stream<__half>((const __half*)x, sb, sc, lists, steps, B, n_pts, C, n_cells, n_chunks, out, st);

@@ -115,7 +115,7 @@ class _BevPoolMasked(torch.autograd.Function):
     the kernel that builds the per-chunk cell lists, and (B, C, D, H, W) memory is streamed instead of gathered."""
 
     @staticmethod
-    def forward(ctx, x, cell0, mask, n_cells):
+    def forward(ctx, x, cell0, mask, n_cells, plan=None):
         _lib.require_cuda(x, cell0)
         if x.dtype not in _FLOAT_DTYPES:
             raise TypeError(f"unsupported feature dtype {x.dtype}")
@@ -138,7 +138,8 @@ class _BevPoolMasked(torch.autograd.Function):
             _lib.check(lib.muvo_bev_pool_workspace_bytes(B, n_pts, n_cells, C.byref(nb)), "muvo_bev_pool_workspace_bytes")
             ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
             rc = lib.muvo_bev_pool_fwd_masked(_lib.ptr(xv), _FLOAT_DTYPES[xv.dtype], sb, sp, sc, _lib.ptr(cell0),
-                                              _lib.ptr(m) if m is not None else None, _lib.ptr(cell), B, n_pts, Cc, n_cells,
+                                              _lib.ptr(m) if m is not None else None, _lib.ptr(cell),
+                                              plan.data_ptr() if plan is not None else None, B, n_pts, Cc, n_cells,
                                               out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "muvo_bev_pool_fwd_masked")
         ctx.save_for_backward(cell)
@@ -149,7 +150,23 @@ class _BevPoolMasked(torch.autograd.Function):
     def backward(ctx, grad_out):
         (cell,) = ctx.saved_tensors
         shape, dtype, n_cells, xstride = ctx.meta
-        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None, None
+        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None, None, None
+
+
+def build_plan(cell0: torch.Tensor, n_cells: int) -> torch.Tensor:
+    """Mask-independent per-chunk sorted cell lists for ``bev_pool_masked(..., plan=)`` (``muvo_bev_plan_build``); valid for
+    this exact ``cell0 (B, n_pts) int32`` only."""
+    _lib.require_cuda(cell0)
+    lib = _lib.load()
+    B, n_pts = cell0.shape
+    nb = C.c_size_t(0)
+    _lib.check(lib.muvo_bev_plan_bytes(B, n_pts, C.byref(nb)), "muvo_bev_plan_bytes")
+    plan = torch.empty(nb.value, dtype=torch.uint8, device=cell0.device)
+    c0 = cell0.contiguous()
+    with torch.cuda.device(cell0.device):
+        rc = lib.muvo_bev_plan_build(_lib.ptr(c0), B, n_pts, int(n_cells), plan.data_ptr(), plan.numel(), _lib.current_stream(cell0.device))
+    _lib.check(rc, "muvo_bev_plan_build")
+    return plan
 
 
 def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
@@ -189,11 +206,12 @@ def _check_cells(n_cells):
                          "INTEGRATION.md (limits).")
 
 
-def bev_pool_masked(x: torch.Tensor, cell0: torch.Tensor, mask, n_cells: int) -> torch.Tensor:
+def bev_pool_masked(x: torch.Tensor, cell0: torch.Tensor, mask, n_cells: int, plan=None) -> torch.Tensor:
     """``x (B,N,D,H,W,C)``, mask-independent ``cell0 (B, n_pts) int32``, ``mask`` bool/uint8 with n_pts entries per frame (or
-    empty / None) -> ``(B, C, n_cells)`` fp32: what ``bev_pool(x, fold_mask(cell0, mask), n_cells)`` returns."""
+    empty / None) -> ``(B, C, n_cells)`` fp32: what ``bev_pool(x, fold_mask(cell0, mask), n_cells)`` returns.  ``plan`` =
+    ``build_plan(cell0, n_cells)`` (optional, cached by the caller) removes the per-call sort."""
     _check_cells(n_cells)
-    return _BevPoolMasked.apply(x, cell0, mask, int(n_cells))
+    return _BevPoolMasked.apply(x, cell0, mask, int(n_cells), plan)
 
 
 def fold_mask(cell0: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -418,7 +436,13 @@ class FrustumPooling(nn.Module):
     def _pool_cells(self, x, cell0, mask):
         B, N, D, H, W, Cc = x.shape
         nx, ny, nz = self.nx_constant
-        out = bev_pool_masked(x, cell0, mask if len(mask) > 0 else None, nx * ny * nz).view(B, Cc, nz, ny, nx)
+        c = self._geom_cache
+        plan = None
+        if c is not None and c["cell0"] is cell0 and cell0.shape[0] == B:
+            if c.get("plan") is None:
+                c["plan"] = build_plan(cell0, nx * ny * nz)
+            plan = c["plan"]
+        out = bev_pool_masked(x, cell0, mask if len(mask) > 0 else None, nx * ny * nz, plan).view(B, Cc, nz, ny, nx)
         return out.view(B, Cc, ny, nx) if nz == 1 else out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
 
     def forward(self, x, intrinsics, pose, mask=torch.zeros(0)):

@@ -319,6 +319,14 @@ def test_streamed_pool_matches_float64_sums(shape, dtype, lib):
             assert torch.equal(gx.reshape(B, -1, C).cpu(), exp.to(dtype))
             # the plain entry point (mask already folded) takes the same path
             assert torch.equal(bev_pool(x, cell, n_cells), out)
+            # cached plan (sorted once, compacted by the mask per call): the same lists, hence the same bits
+            if m is not None:
+                from muvo_b200.frustum_pooling import build_plan
+                xp = x.detach().requires_grad_(True)
+                outp = bev_pool_masked(xp, cell0, m, n_cells, build_plan(cell0, n_cells))
+                assert torch.equal(outp, out)
+                (gxp,) = torch.autograd.grad(outp, xp, gout)
+                assert torch.equal(gxp, gx)
     finally:
         _set_pool_path(lib, 0)
 
