@@ -99,18 +99,33 @@ def all_reduce_counts(counts: torch.Tensor, group=None) -> torch.Tensor:
 
 
 class SSCMetrics:
-    """Same interface as the reference class; ``sync_dist=True`` all-reduces counts across ranks."""
+    """Same interface as the reference class (muvo/metrics.py:47-216).
 
-    def __init__(self, n_classes, sync_dist: bool = False, process_group=None):
+    ``sync_dist=True`` all-reduces the counts of every ``add_batch`` across ranks (NCCL), so that each rank's running
+    statistics are the global ones after every batch, exactly as if one process had seen all frames.
+    ``sync_dist="epoch"`` keeps the collective and the device->host copy off the per-batch path: counts accumulate in an
+    int64 vector ON THE DEVICE (``add_batch`` neither synchronises nor communicates), and the first ``get_stats()`` /
+    ``compute()`` afterwards does ONE all-reduce and ONE read-back -- the reference only looks at the statistics in
+    ``on_validation_epoch_end`` (muvo/trainer.py:515-567).  In that mode the statistics come from the exact int64 totals
+    (the reference's float32 running sums round once a count passes 2^24; ``counts_exact`` holds the integers).
+    """
+
+    def __init__(self, n_classes, sync_dist=False, process_group=None):
         self.n_classes = n_classes
         self.sync_dist = sync_dist
         self.process_group = process_group
+        self._dev_acc = None            # "epoch" mode: per-rank int64[3+3C] on the device
+        self._pending = False
         self.reset()
+
+    @property
+    def deferred(self) -> bool:
+        return self.sync_dist == "epoch"
 
     # -- kernels -----------------------------------------------------------------
     def _counts(self, predict, target, nonempty, nonsurface, ignore255):
         c = ssc_counts(predict, target, self.n_classes, nonempty, nonsurface, ignore255)
-        if self.sync_dist:
+        if self.sync_dist and not self.deferred:
             all_reduce_counts(c, self.process_group)
         return c.cpu()          # the single device->host copy of this call
 
@@ -129,12 +144,44 @@ class SSCMetrics:
     def add_batch(self, y_pred, y_true, nonempty=None, nonsurface=None):
         """muvo/metrics.py:77-100, one launch: completion uses nonempty & nonsurface, classes nonempty only."""
         self.count += 1
+        if self.deferred:
+            self._dev_acc = self._acc_on(y_pred.device)
+            ssc_counts(y_pred, y_true, self.n_classes, nonempty, nonsurface, True, out=self._dev_acc)   # adds into out
+            self._pending = True
+            return
         c = self._counts(y_pred, y_true, nonempty, nonsurface, True)
         self._accumulate(c)
+
+    def _acc_on(self, dev):
+        if self._dev_acc is None or self._dev_acc.device != dev:
+            self._dev_acc = torch.zeros(3 + 3 * self.n_classes, dtype=torch.int64, device=dev)
+        return self._dev_acc
+
+    def _flush(self):
+        """"epoch" mode: one all-reduce + one read-back of everything accumulated since the last flush / reset."""
+        if not self._pending:
+            return
+        c = self._dev_acc.clone()
+        self._dev_acc.zero_()
+        self._pending = False
+        all_reduce_counts(c, self.process_group)
+        c = c.cpu()
+        C = self.n_classes
+        self.counts_exact += c
+        t = self.counts_exact
+        self.completion_tp, self.completion_fp, self.completion_fn = int(t[0]), int(t[1]), int(t[2])
+        self.tps = t[3:3 + C].to(torch.float32)
+        self.fps = t[3 + C:3 + 2 * C].to(torch.float32)
+        self.fns = t[3 + 2 * C:3 + 3 * C].to(torch.float32)
 
     def add_batch_from_logits(self, logits, y_true):
         """``add_batch(argmax(logits, 1), y_true)`` without materialising the prediction (trainer.py:483-490)."""
         self.count += 1
+        if self.deferred:
+            self._dev_acc = self._acc_on(logits.device)
+            ssc_counts_from_logits(logits, y_true, True, out=self._dev_acc)
+            self._pending = True
+            return
         c = ssc_counts_from_logits(logits, y_true, True)
         if self.sync_dist:
             all_reduce_counts(c, self.process_group)
@@ -152,6 +199,8 @@ class SSCMetrics:
         self.compute()
 
     def compute(self):
+        if self.deferred:
+            self._flush()
         if self.completion_tp != 0:
             self.precision = self.completion_tp / (self.completion_tp + self.completion_fp)
             self.recall = self.completion_tp / (self.completion_tp + self.completion_fn)
@@ -161,6 +210,8 @@ class SSCMetrics:
         self.iou_ssc = self.tps / (self.tps + self.fps + self.fns + 1e-5)
 
     def get_stats(self):
+        if self.deferred and self._pending:
+            self.compute()
         return {
             "precision": self.precision,
             "recall": self.recall,
@@ -170,6 +221,9 @@ class SSCMetrics:
         }
 
     def reset(self):
+        if self._dev_acc is not None:
+            self._dev_acc.zero_()
+        self._pending = False
         self.completion_tp = 0
         self.completion_fp = 0
         self.completion_fn = 0

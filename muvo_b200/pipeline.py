@@ -48,7 +48,10 @@ class _Slot:
 class HostPipeline:
     def __init__(self, device=None, grid: Optional[GridSpec] = GridSpec(), range_spec: Optional[RangeSpec] = RangeSpec(),
                  dense: bool = False, sparse: bool = True, layout: str = "hwc", remap: Optional[np.ndarray] = None,
-                 depth: int = 2, host_threads: int = 0):
+                 depth: int = 2, host_threads: int = 0, device_out: bool = False):
+        """``device_out=True``: the results stay on the device (a training step consumes them there, as MUVO's batches end
+        up on the GPU anyway); ``result()`` then returns device tensors that are valid until the slot's next ``submit``,
+        and only the per-frame counts (``n_occ`` / ``sparse_start``) are read back."""
         if not torch.cuda.is_available():
             raise _lib.MuvoError("muvo_b200 kernels need a CUDA device (sm_100a); no CPU fallback exists")
         if device is None:
@@ -58,6 +61,7 @@ class HostPipeline:
             raise _lib.MuvoError("HostPipeline needs a CUDA device")
         self.grid, self.range_spec = grid, range_spec
         self.dense, self.sparse, self.layout = dense, sparse, layout
+        self.device_out = bool(device_out)
         self.remap = torch.from_numpy(np.ascontiguousarray(remap)).to(self.device) if remap is not None else None
         self.s_in = torch.cuda.Stream(self.device)
         self.s_run = torch.cuda.Stream(self.device)
@@ -135,10 +139,13 @@ class HostPipeline:
                 slot.d_off[:n_frames + 1].copy_(slot.h_off[:n_frames + 1], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_in)
-            self.h2d_bytes = n_pts * 13 + (n_frames + 1) * 8
+            h2d_bytes = n_pts * 13 + (n_frames + 1) * 8
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ev_in)
-                out = {k: v for k, v in slot.dev_out.items() if v.shape[0] in (n_frames, slot.cap_pts)}
+                # reuse the slot's output tensors whose leading dimension still fits: per-point rows for the sparse list,
+                # F + 1 rows for the packed starts, F rows for everything else
+                want_rows = {"voxel_sparse": slot.cap_pts, "sparse_start": n_frames + 1}
+                out = {k: v for k, v in slot.dev_out.items() if v.shape[0] == want_rows.get(k, n_frames)}
                 res = sensor_to_grid(slot.d_pts[:n_pts], slot.d_sem[:n_pts], slot.d_off[:n_frames + 1], grid=self.grid,
                                      range_spec=self.range_spec, dense=self.dense, sparse=self.sparse, remap=self.remap,
                                      layout=self.layout, out=out, packed_sparse=self.sparse)
@@ -152,6 +159,8 @@ class HostPipeline:
                 rows = n_pts if self.row_cap is None else min(n_pts, self.row_cap)
                 for k in keys:
                     t = res[k]
+                    if self.device_out and k not in ("n_occ", "sparse_start"):
+                        continue                          # stays on the device
                     h = slot.host_out.get(k)
                     if h is None or h.shape != t.shape:
                         h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
@@ -164,8 +173,7 @@ class HostPipeline:
                         nbytes += t.numel() * t.element_size()
                 slot.done = torch.cuda.Event()
                 slot.done.record(self.s_out)
-            self.d2h_bytes = nbytes
-        slot.meta = (n_pts, n_frames, rows)
+        slot.meta = (n_pts, n_frames, rows, h2d_bytes, nbytes)      # published by result() on the caller's thread
 
     def result(self) -> dict:
         """Blocks until the oldest submitted batch is back in host memory; returns its pinned host tensors.
@@ -180,15 +188,21 @@ class HostPipeline:
             slot.busy = False
             raise
         slot.done.synchronize()
+        n_pts, n_frames, rows, self.h2d_bytes, self.d2h_bytes = slot.meta
+        if self.device_out:
+            slot.busy = False
+            out = dict(slot.dev_out)
+            out.update(slot.host_out)                # n_occ / sparse_start: host copies
+            return out
         if self.sparse and "sparse_start" in slot.host_out:
-            n_pts, n_frames, rows = slot.meta
             total = int(slot.host_out["sparse_start"][n_frames].item())
             if total > rows:                         # more occupied voxels than the rows read back so far: top up
                 with torch.cuda.device(self.device), torch.cuda.stream(self.s_out):
                     slot.host_out["voxel_sparse"][rows:total].copy_(slot.dev_out["voxel_sparse"][rows:total], non_blocking=True)
                     self.s_out.synchronize()
+                self.d2h_bytes += (total - rows) * 8
             cap = max(1024, int(total * 1.25))
-            self.row_cap = cap if self.row_cap is None else max(self.row_cap, cap)
+            self.row_cap = cap if self.row_cap is None else max(self.row_cap, cap)       # (read by the worker: a stale value only costs a top-up)
         slot.busy = False
         return dict(slot.host_out)
 

@@ -132,7 +132,7 @@ def test_scatter_half_precision_and_special_values(lib):
     assert torch.isnan(got[idx2[0], 0]) and got[idx2[1], 1] == float("inf") and torch.isnan(got[idx2[2], 2])
     clean = torch.ones_like(got, dtype=torch.bool)
     clean[idx2[0], 0] = clean[idx2[1], 1] = clean[idx2[2], 2] = False
-    want = torch.from_numpy(O.scatter_mean(src.numpy(), idx2.numpy(), 150))
+    want = torch.from_numpy(O.scatter_mean(src.numpy(), idx2.numpy(), 150)).to(got.dtype)
     assert torch.allclose(got[clean], want[clean], rtol=0, atol=1e-6 * float(src.abs().max()))
 
 

@@ -102,3 +102,28 @@ def test_full_size_properties(lib):
     assert c[0] + c[2] == ((yt > 0) & valid).sum()                      # completion tp + fn = occupied ground truth
     assert np.array_equal(c, O.ssc_add_batch_counts(yp, yt, C))
     assert torch.equal(total, ssc_counts(tp, tt, C, ignore255=True))    # deterministic
+
+
+def test_epoch_sync_accumulates_on_device_and_matches_exact_totals(lib):
+    """``sync_dist="epoch"``: add_batch neither copies to the host nor communicates; get_stats() flushes once
+    (muvo/trainer.py:515-567 reads the statistics at epoch end only).  Totals = the oracle's over all batches."""
+    C = 9
+    m = muvo_b200.SSCMetrics(C, sync_dist="epoch")
+    want = np.zeros(3 + 3 * C, dtype=np.int64)
+    for k in range(3):
+        yp, yt = synth.occupancy_pair(2, C, 4200 + k, size=(48, 48, 16))
+        m.add_batch(cu(yp), cu(yt))
+        want += O.ssc_add_batch_counts(yp, yt, C)
+    assert m._pending and int(m.counts_exact.sum()) == 0            # nothing has left the device yet
+    st = m.get_stats()
+    assert np.array_equal(m.counts_exact.numpy(), want)
+    tp, fp, fn = want[0], want[1], want[2]
+    assert st["iou"] == tp / (tp + fp + fn) and st["precision"] == tp / (tp + fp) and st["recall"] == tp / (tp + fn)
+    tps, fps, fns = (torch.from_numpy(want[3 + i * C:3 + (i + 1) * C]).float() for i in range(3))
+    assert torch.equal(st["iou_ssc"], tps / (tps + fps + fns + 1e-5))
+    yp, yt = synth.occupancy_pair(1, C, 4300, size=(48, 48, 16))      # a later batch keeps accumulating after a flush
+    m.add_batch(cu(yp), cu(yt))
+    m.get_stats()
+    assert np.array_equal(m.counts_exact.numpy(), want + O.ssc_add_batch_counts(yp, yt, C))
+    m.reset()
+    assert int(m.counts_exact.sum()) == 0 and not m._pending
