@@ -78,6 +78,19 @@ typedef struct MuvoRangeCfg {
   double lidar_pos[3];  /* (:173,:178)                               */
 } MuvoRangeCfg;
 
+/* LiDAR-side prep in front of the range projection, muvo/data/dataset.py:275-290:
+ * convert_coor_lidar (data/data_preprocessing.py:119-122: p = float32(float64(p) + add), then y = -y), the ego-box drop
+ * (:286-290: points with box_lo < p < box_hi on all three axes are removed before the projection) and the LABEL_MAP
+ * remap of the point semantics (:281-283, applied to the winner's tag when the image is written).                       */
+typedef struct MuvoLidarPrep {
+  double add[3];            /* cfg.POINTS.LIDAR_POSITION                                   */
+  double box_lo[3];         /* (-x/2, -y/2, 0) of EGO_VEHICLE_DIMENSION                     */
+  double box_hi[3];         /* ( x/2,  y/2, z)                                              */
+  int32_t use_ego_box;      /* 0: keep every point                                          */
+  int32_t reserved;
+  const uint8_t* remap256;  /* DEVICE pointer to a 256-entry table, or NULL = tags as they are */
+} MuvoLidarPrep;
+
 /* diag[] slots written by the point kernels (int64 each) */
 enum { MUVO_DIAG_DROPPED_NONFINITE = 0, /* points with NaN/Inf coordinates or at the sensor origin (reference: IndexError) */
        MUVO_DIAG_NEAR_EDGE_W = 1,       /* |frac(proj_w)| within 1e-9 of a column edge (incl. exactly on it)               */
@@ -133,6 +146,15 @@ MUVO_API int muvo_label_pyramids(const float* range_xyzd, const uint8_t* range_s
                         int32_t W, int32_t X, int32_t Y, int32_t Z, float scale, float* rv1, float* rv2, float* rv4,
                         uint8_t* seg2, uint8_t* seg4, uint8_t* vox2, uint8_t* vox4, void* stream);
 
+/* Saved sparse voxels -> dense training grids: muvo/data/dataset.py:317-327 for F files at once.
+ *   rows [n_rows,4] uint16 (x, y, z, label) as data/generate_voxels.py:72-73 saves them, files back to back,
+ *   row_offsets [F+1] int64; label 255 -> 0 (:322), remap256[label] (:323, NULL = identity); the LAST row of a voxel wins
+ *   like numpy's fancy assignment (:325); rows outside the grid are skipped and counted in n_bad [1] int64 (numpy raises
+ *   IndexError there; may be NULL).  dense_out [F,Dx,Dy,Dz] uint8 fully written, 4-byte aligned; scratch_rows [n_rows] uint8. */
+MUVO_API int muvo_densify_sparse(const uint16_t* rows, const int64_t* row_offsets, int32_t n_frames, int64_t n_rows, int32_t dx,
+                        int32_t dy, int32_t dz, const uint8_t* remap256, uint8_t* dense_out, uint8_t* scratch_rows,
+                        int64_t* n_bad, void* stream);
+
 /* ---- (a) voxelisation ------------------------------------------------------------
  * Replaces voxel_filter(), data/data_preprocessing.py:172-228, batched over frames, and
  * (dense_out) the densify step of muvo/data/dataset.py:317-327.
@@ -158,6 +180,15 @@ MUVO_API int muvo_voxelize(const void* xyz, int32_t xyz_dtype, const uint8_t* se
 MUVO_API int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,
                        int64_t n_points_total, const MuvoRangeCfg* cfg_h, int32_t layout, float* depth_out,
                        float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, void* stream);
+
+/* (b) straight from the raw semantic-LiDAR sweep: what muvo/data/dataset.py:275-300 does per sample --
+ * convert_coor_lidar, LABEL_MAP remap, ego-box drop, do_range_projection -- as ONE pass of the same kernels (the prep is applied
+ * where a point is loaded; no intermediate cloud is written).  xyz_raw [P,3] float32 in the LiDAR frame, tag [P] uint8 raw
+ * CARLA tags; outputs as muvo_range_project (range_xyz holds the converted ego-frame points, range_sem the remapped tags). */
+MUVO_API int muvo_range_project_lidar(const float* xyz_raw, const uint8_t* tag, const int64_t* frame_offsets, int32_t n_frames,
+                       int64_t n_points_total, const MuvoRangeCfg* cfg_h, const MuvoLidarPrep* prep_h, int32_t layout,
+                       float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes,
+                       void* stream);
 
 /* ---- (a)+(b) fused: one read of the point stream feeds both stages ---------------- */
 MUVO_API int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets, int32_t n_frames,

@@ -34,6 +34,11 @@ class MuvoRangeCfg(C.Structure):
                 ("lidar_pos", C.c_double * 3)]
 
 
+class MuvoLidarPrep(C.Structure):
+    _fields_ = [("add", C.c_double * 3), ("box_lo", C.c_double * 3), ("box_hi", C.c_double * 3),
+                ("use_ego_box", C.c_int32), ("reserved", C.c_int32), ("remap256", C.c_void_p)]
+
+
 _P = C.c_void_p
 _I32, _I64, _SZ = C.c_int32, C.c_int64, C.c_size_t
 
@@ -51,6 +56,9 @@ SIGNATURES = {
     "muvo_label_pyramids": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "muvo_voxelize": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_range_project": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoRangeCfg), _I32, _P, _P, _P, _P, _P, _SZ, _P]),
+    "muvo_densify_sparse": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "muvo_range_project_lidar": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoRangeCfg), C.POINTER(MuvoLidarPrep), _I32, _P, _P, _P,
+                                           _P, _P, _SZ, _P]),
     "muvo_points_fused": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, C.POINTER(MuvoRangeCfg), _I32,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_host_copy": (C.c_int, [_P, _P, _SZ, _I32]),

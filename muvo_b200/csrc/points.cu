@@ -273,7 +273,8 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
   for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
     const uint2 ent = q[e];
     const int64_t i = blk_first + (int64_t)(ent.x & ~kQVoxel);
-    const T x = __ldg(a.xyz + 3 * i), y = __ldg(a.xyz + 3 * i + 1), z = __ldg(a.xyz + 3 * i + 2);
+    T x = __ldg(a.xyz + 3 * i), y = __ldg(a.xyz + 3 * i + 1), z = __ldg(a.xyz + 3 * i + 2);
+    if (r.prep) lidar_prep(x, y, z, r);
     int f = f_first;
     while (f + 1 < a.F && i >= __ldg(a.off + f + 1)) ++f;
     const int64_t fb = __ldg(a.off + f);
@@ -313,8 +314,10 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
     if (old_word != 0ull && word_top(old_word) == top) {
       auto key_of = [&](uint32_t q1) -> u64 {     // exact key: the float64 depth (geometry_utils.py:180)
         const T* qp = fx + 3 * (int64_t)(q1 - 1u);
+        T qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        if (r.prep) lidar_prep(qx, qy, qz, r);
         double aa, bb, cc;
-        return (u64)__double_as_longlong(sqrt(range_sq_of(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), r, &aa, &bb, &cc)));
+        return (u64)__double_as_longlong(sqrt(range_sq_of(qx, qy, qz, r, &aa, &bb, &cc)));
       };
       auto pack = [&](uint32_t q1) -> u64 { return pack_word(top, q1); };
       auto idx_of = [](u64 wv) -> uint32_t { return word_idx1(wv); };
@@ -360,7 +363,7 @@ __device__ __forceinline__ bool pair_filter(bool in, uint32_t bit /* 0xffffffff 
   return in && !beaten;
 }
 
-template <typename T, bool DO_VOX, bool DO_RANGE, bool REG>
+template <typename T, bool DO_VOX, bool DO_RANGE, bool REG, bool PREP = false>
 __global__ void __launch_bounds__(kTileThreads, MUVO_K1_MINB)
 k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const int64_t* __restrict__ off, int F, int64_t P0,
               int64_t P, int f_lo, int f_hi, bool vec_ok, GridDev g, RangeDev r, uint32_t* __restrict__ bitmap, u64* __restrict__ vtab, u64* __restrict__ pixtab,
@@ -422,10 +425,11 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
         u64 vword[kKPL], pword[kKPL];
 #pragma unroll
         for (int k = 0; k < kKPL; ++k) {
-          const T x = sx[3 * k * kTileThreads], y = sx[3 * k * kTileThreads + 1], z = sx[3 * k * kTileThreads + 2];
+          T x = sx[3 * k * kTileThreads], y = sx[3 * k * kTileThreads + 1], z = sx[3 * k * kTileThreads + 2];
           const uint32_t lab = ss[k * kTileThreads];
           const uint32_t me1 = idx1_0 + k * kTileThreads;
           vbit[k] = 0xffffffffu; ppix[k] = 0xffffffffu; vword[k] = 0ull; pword[k] = 0ull;
+          const bool keep = PREP ? lidar_prep(x, y, z, r) : true;                   // N1: raw LiDAR-frame points (range-only calls)
           if (DO_VOX) {
             bool in; double dis; uint32_t bit = 0xffffffffu;
             if (REG) { VoxFast v = vox_regular(x, y, z, g); in = v.in; dis = vox_regular_dis(v, g); if (in) bit = v.bit; }
@@ -435,7 +439,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
             const bool go = use_filter ? pair_filter<true>(in, bit, 0, top) : in;
             if (go) { vbit[k] = bit; vword[k] = vox_word(PACKL_T, top, me1, lab); }
           }
-          if (DO_RANGE) {
+          if (DO_RANGE && keep) {
             const PixFast pk = pix_fast(x, y, z, r);
             if (!pk.ok) ++n_drop;
             else if (pk.slow) q[atomicAdd(qn, 1u)] = make_uint2(rel_0 + k * kTileThreads, kQExact);
@@ -483,6 +487,7 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
           tl.frame_of(tl.base + k * kTileThreads + tid, &fk, &fb);
           packl = (__ldg(off + fk + 1) - fb) < kPackLimit;
         }
+        if (PREP && valid) valid = lidar_prep(x, y, z, r);
         const uint32_t me1 = FAST ? idx1_0 + k * kTileThreads : (uint32_t)(tl.base + k * kTileThreads + tid - fb) + 1u;
         Pending cur{1ull, 0ull, 0xffffffffu, 0u, 0u, rel_0 + k * kTileThreads, fk, false, false, packl};
         if (DO_VOX) {
@@ -793,12 +798,14 @@ template <typename T>
 struct EmitRangeArgs {
   u64* pixtab; const T* xyz; const uint8_t* sem; const int64_t* off; int f_lo, f_hi;   // frames [f_lo, f_hi) of this launch
   float* depth_out; float* xyz_out; uint8_t* sem_out;
+  const uint8_t* sem_remap;   // N1: 256-entry label remap applied to the winner's tag (dataset.py:281-283), or nullptr
 };
 template <typename T, int NP, int LAYOUT>
 __device__ __forceinline__ void emit_range_body(int64_t vblock, const EmitRangeArgs<T>& a, const RangeDev& r) {
   u64* __restrict__ pixtab = a.pixtab; const T* __restrict__ xyz = a.xyz; const uint8_t* __restrict__ sem = a.sem;
   const int64_t* __restrict__ off = a.off;
   float* __restrict__ depth_out = a.depth_out; float* __restrict__ xyz_out = a.xyz_out; uint8_t* __restrict__ sem_out = a.sem_out;
+  const uint8_t* __restrict__ sem_remap = a.sem_remap;
   constexpr bool clean = true;
   const int64_t HW = (int64_t)r.H * r.W;
   int64_t t = vblock * kBlock + threadIdx.x;
@@ -828,10 +835,13 @@ __device__ __forceinline__ void emit_range_body(int64_t vblock, const EmitRangeA
     if (wv[k]) {
       int64_t qi = fbeg + (int64_t)(word_idx1(wv[k]) - 1u);
       T x = __ldg(xyz + 3 * qi), y = __ldg(xyz + 3 * qi + 1), z = __ldg(xyz + 3 * qi + 2);
+      if (r.prep) lidar_prep(x, y, z, r);
       double a, b, c;
       pd[k] = (float)range_depth_of(x, y, z, r, &a, &b, &c);   // :217 float32(depth64)
       px[k] = (float)x; py[k] = (float)y; pz[k] = (float)z;    // :218 the ego-frame input point
-      ps |= (uint32_t)__ldg(sem + qi) << (8 * k);              // :219
+      uint32_t sv = __ldg(sem + qi);
+      if (sem_remap) sv = __ldg(sem_remap + sv);
+      ps |= sv << (8 * k);                                     // :219
     }
   }
   if (NP == 4) {
@@ -903,8 +913,10 @@ template <typename T>
 static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int F, int64_t P,
                       const MuvoGrid* grid_h, const uint8_t* remap, const MuvoRangeCfg* cfg_h, int layout, uint8_t* dense,
                       uint16_t* sparse, int64_t* n_occ, int64_t* sparse_start, float* depth_out, float* xyz_out,
-                      uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, cudaStream_t st) {
+                      uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes, cudaStream_t st,
+                      const MuvoLidarPrep* prep_h = nullptr) {
   const bool do_vox = grid_h != nullptr, do_range = cfg_h != nullptr;
+  if (prep_h && (do_vox || !do_range || !std::is_same<T, float>::value)) return MUVO_E_ARG;   // N1 prep: float32, range-only calls
   if (!do_vox && !do_range) return MUVO_E_ARG;
   if (F < 0 || P < 0) return MUVO_E_ARG;
   if (F == 0) return MUVO_OK;
@@ -922,6 +934,13 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   const int order = (sparse != nullptr) ? ORDER_LINEAR : ORDER_DENSE;   // bit index = output order of the list that is emitted
   if (do_vox && (rc = make_grid_dev(grid_h, order, &g)) != MUVO_OK) return rc;
   if (do_range && (rc = make_range_dev(cfg_h, &r)) != MUVO_OK) return rc;
+  if (prep_h) {
+    r.prep = 1; r.prep_box = prep_h->use_ego_box ? 1 : 0;
+    for (int k = 0; k < 3; ++k) {
+      if (!isfinite(prep_h->add[k])) return MUVO_E_ARG;
+      r.padd[k] = prep_h->add[k]; r.blo[k] = prep_h->box_lo[k]; r.bhi[k] = prep_h->box_hi[k];
+    }
+  }
   PointsWs w = carve(ws, P, F, grid_h, cfg_h);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
   const bool vec_ok = (reinterpret_cast<uintptr_t>(xyz) % 16 == 0) && (reinterpret_cast<uintptr_t>(sem) % 16 == 0);
@@ -945,6 +964,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   K1Fn k1;
   if (do_vox && do_range) k1 = reg ? k_points_tile<T, true, true, true> : k_points_tile<T, true, true, false>;
   else if (do_vox)        k1 = reg ? k_points_tile<T, true, false, true> : k_points_tile<T, true, false, false>;
+  else if (prep_h)        k1 = k_points_tile<T, false, true, true, true>;
   else                    k1 = k_points_tile<T, false, true, true>;
   int k1_per_sm = 0;
   {
@@ -1009,7 +1029,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
     bool emitted_range = false;
     if (do_range) {              // right after its producers: the pixel words are still L2 resident
       emitted_range = true;
-      EmitRangeArgs<T> era{w.pixtab, xyz, sem, off, f0, f1, depth_out, xyz_out, sem_out};
+      EmitRangeArgs<T> era{w.pixtab, xyz, sem, off, f0, f1, depth_out, xyz_out, sem_out, prep_h ? prep_h->remap256 : nullptr};
       const int64_t npix = (int64_t)(f1 - f0) * HWr;
       if (range_vec4) {
         if (layout == MUVO_RANGE_LAYOUT_HWC) launch_pdl(k_emit_range<T, 4, MUVO_RANGE_LAYOUT_HWC>, dim3(blocks_for(npix / 4)), dim3(kBlock), 0, cs, era, r);
@@ -1046,7 +1066,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
 
   prof_mark("<points>", st);
   // float32 clouds -> dense grids / range images: the single-launch dataflow kernel (points_mega.cu)
-  if (std::is_same<T, float>::value && (!do_vox || dense_fast) &&
+  if (std::is_same<T, float>::value && !prep_h && (!do_vox || dense_fast) &&
       points_mega_eligible(do_vox ? &g : nullptr, do_range ? &r : nullptr, xyz, sem, dense, depth_out, xyz_out, sem_out, layout))
     return points_mega_f32(reinterpret_cast<const float*>(xyz), sem, off, F, P, do_vox ? &g : nullptr, remap, do_range ? &r : nullptr,
                            layout, dense, n_occ_emit, depth_out, xyz_out, sem_out, diag, w, st);
@@ -1121,6 +1141,16 @@ int muvo_range_project(const float* xyz, const uint8_t* sem, const int64_t* fram
   return run_points<float>(xyz, sem, frame_offsets, n_frames, n_points_total, nullptr, nullptr, cfg_h, layout,
                            nullptr, nullptr, nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes,
                            (cudaStream_t)stream);
+}
+
+int muvo_range_project_lidar(const float* xyz_raw, const uint8_t* tag, const int64_t* frame_offsets, int32_t n_frames,
+                             int64_t n_points_total, const MuvoRangeCfg* cfg_h, const MuvoLidarPrep* prep_h, int32_t layout,
+                             float* depth_out, float* xyz_out, uint8_t* sem_out, int64_t* diag, void* ws, size_t ws_bytes,
+                             void* stream) {
+  if (!cfg_h || !prep_h) return MUVO_E_NULL;
+  return run_points<float>(xyz_raw, tag, frame_offsets, n_frames, n_points_total, nullptr, nullptr, cfg_h, layout,
+                           nullptr, nullptr, nullptr, nullptr, depth_out, xyz_out, sem_out, diag, ws, ws_bytes,
+                           (cudaStream_t)stream, prep_h);
 }
 
 int muvo_points_fused(const float* xyz, const uint8_t* sem, const int64_t* frame_offsets,

@@ -43,6 +43,10 @@ struct RangeDev {
   float safe_w, safe_h;   // 0.5 - eps: |frac - 0.5| below this = provably inside the bin
   float Lf[3];            // sensor position in f32
   int lf_exact;           // ... and whether that is exact
+  // LiDAR-side prep in front of the projection (muvo/data/dataset.py:278-290), see lidar_prep(); prep = 0: points are taken as is
+  int prep, prep_box;
+  double padd[3];         // convert_coor_lidar: += lidar_pos (data/data_preprocessing.py:119-122)
+  double blo[3], bhi[3];  // ego box (dataset.py:286-288)
 };
 
 typedef unsigned long long u64;
@@ -248,6 +252,18 @@ __device__ __forceinline__ double range_sq_of(T x, T y, T z, const RangeDev& r, 
   return (xc * xc + yc * yc) + zc * zc;
 }
 
+// LiDAR-side prep (N1), fused into every kernel that loads a raw point: convert_coor_lidar (`pcd += lidar_pos` on a float32
+// array = float32(float64(p) + lidar_pos), then `pcd[:, 1] *= -1`, data/data_preprocessing.py:119-122) and the ego-box drop
+// (`(lo < p) & (p < hi)` in float64, muvo/data/dataset.py:286-290).  Returns false for a point inside the box (dropped
+// before the projection in the reference: the order of the survivors is unchanged, so ties resolve the same way).
+__device__ __forceinline__ bool lidar_prep(float& x, float& y, float& z, const RangeDev& r) {
+  x = (float)((double)x + r.padd[0]); y = -(float)((double)y + r.padd[1]); z = (float)((double)z + r.padd[2]);
+  if (!r.prep_box) return true;
+  const double dx = (double)x, dy = (double)y, dz = (double)z;
+  return !((r.blo[0] < dx) & (dx < r.bhi[0]) & (r.blo[1] < dy) & (dy < r.bhi[1]) & (r.blo[2] < dz) & (dz < r.bhi[2]));
+}
+__device__ __forceinline__ bool lidar_prep(double&, double&, double&, const RangeDev&) { return true; }   // (float32 clouds only)
+
 // ---- f32 fast path of the pixel computation
 // atan(t)/pi on [0,1] as t*Q(t^2), Q of degree 6 (tools/fit_atan.py: |error| < 1.2e-7 including the f32 Horner
 // rounding).  Together with the quotient (2 ulp), the f32 coordinates (0.5 ulp each) and the final scaling the
@@ -449,6 +465,7 @@ static int make_range_dev(const MuvoRangeCfg* c, RangeDev* o) {
   o->lf_exact = 1;
   for (int k = 0; k < 3; ++k) { o->Lf[k] = (float)c->lidar_pos[k]; if ((double)o->Lf[k] != c->lidar_pos[k]) o->lf_exact = 0; }
   for (int k = 0; k < 3; ++k) o->L[k] = c->lidar_pos[k];
+  o->prep = 0; o->prep_box = 0;
   return MUVO_OK;
 }
 

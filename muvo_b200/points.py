@@ -86,11 +86,39 @@ def _as_offsets(frame_offsets, n_points: int, device) -> torch.Tensor:
     return off.contiguous()
 
 
+@dataclass(frozen=True)
+class LidarPrep:
+    """LiDAR-side prep of ``muvo/data/dataset.py:275-290`` fused into the range projection (``sensor_to_grid(...,
+    lidar_prep=)``): ``convert_coor_lidar(points_xyz, lidar_position)``, ``remap[ObjTag]`` and the ego-box drop."""
+    lidar_position: Sequence[float] = (1.0, 0.0, 2.0)            # cfg.POINTS.LIDAR_POSITION (muvo/config.py:85)
+    ego_dimension: Optional[Sequence[float]] = (4.902, 2.128, 1.511)   # constants.py:8; None = keep every point
+    remap: Optional[np.ndarray] = None                            # 256-entry uint8 table (dataset.py:281-283) or None
+
+    def to_c(self, dev):
+        c = _lib.MuvoLidarPrep()
+        keep = None
+        for k in range(3):
+            c.add[k] = float(self.lidar_position[k])
+        if self.ego_dimension is not None:
+            x, y, z = (float(v) for v in self.ego_dimension)
+            lo, hi = np.array([[-x / 2, -y / 2, 0], [x / 2, y / 2, z]])          # dataset.py:287, evaluated by numpy
+            for k in range(3):
+                c.box_lo[k], c.box_hi[k] = float(lo[k]), float(hi[k])
+            c.use_ego_box = 1
+        if self.remap is not None:
+            tab = np.asarray(self.remap, dtype=np.uint8).reshape(-1)
+            if tab.size < 256:                                                   # remap tables cover the raw tags only
+                tab = np.concatenate([tab, np.full(256 - tab.size, tab.max() if tab.size else 0, np.uint8)])
+            keep = torch.from_numpy(np.ascontiguousarray(tab[:256])).to(dev)
+            c.remap256 = keep.data_ptr()
+        return c, keep
+
+
 def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=None, *,
                    grid: Optional[GridSpec] = None, range_spec: Optional[RangeSpec] = None,
                    dense: bool = True, sparse: bool = False, remap: Optional[torch.Tensor] = None,
                    layout: str = "xyzd", want_diag: bool = False, out: Optional[dict] = None,
-                   packed_sparse: bool = False) -> dict:
+                   packed_sparse: bool = False, lidar_prep: Optional[LidarPrep] = None) -> dict:
     """Batched (a)+(b) on the current CUDA stream.  Nothing synchronises.
 
     points ``(P,3)`` float32 (float64 allowed when only ``grid`` is given), semantics ``(P,)`` uint8,
@@ -101,10 +129,14 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
     ``out`` may carry preallocated tensors under the same keys.  Frame f's sparse rows start at row
     ``frame_offsets[f]``; with ``packed_sparse`` the frames' lists are stored back to back instead and
     ``sparse_start (F+1,) i64`` gives the first row of every frame (a read-back then moves only the rows used).
+    ``lidar_prep`` (range-only calls): ``points`` / ``semantics`` are the RAW sweep (LiDAR frame, CARLA tags) and the prep of
+    dataset.py:275-290 happens inside the kernels; ``range_xyz*`` then holds the converted points, ``range_sem`` the remapped tags.
     """
     _lib.require_cuda(points, semantics)
     if grid is None and range_spec is None:
         raise ValueError("nothing to do: pass grid and/or range_spec")
+    if lidar_prep is not None and (grid is not None or range_spec is None or points.dtype != torch.float32):
+        raise ValueError("lidar_prep belongs to range-only calls on float32 points (muvo/data/dataset.py:275-300)")
     lib = _lib.load()
     dev = points.device
     if points.dim() != 2 or points.shape[1] != 3:
@@ -185,6 +217,10 @@ def sensor_to_grid(points: torch.Tensor, semantics: torch.Tensor, frame_offsets=
             dt = _lib.F32 if points.dtype == torch.float32 else _lib.F64
             rc = lib.muvo_voxelize(p(points), dt, p(semantics), p(off), F, P, C.byref(g_c), p(remap), p(dense_t),
                                    p(sparse_t), p(nocc_t), p(start_t), p(diag), ws.data_ptr(), ws.numel(), stream)
+        elif lidar_prep is not None:
+            prep_c, _keep = lidar_prep.to_c(dev)
+            rc = lib.muvo_range_project_lidar(p(points), p(semantics), p(off), F, P, C.byref(r_c), C.byref(prep_c), lay, p(depth_t),
+                                              p(xyz_t), p(sem_t), p(diag), ws.data_ptr(), ws.numel(), stream)
         else:
             rc = lib.muvo_range_project(p(points), p(semantics), p(off), F, P, C.byref(r_c), lay, p(depth_t), p(xyz_t),
                                         p(sem_t), p(diag), ws.data_ptr(), ws.numel(), stream)
@@ -357,6 +393,63 @@ def voxelize_one(depth_file, lidar_file, cfg, save_name, pipe=None):
     if pipe is not None:
         pipe.send(['x'])
     return out
+
+
+def densify_voxels(voxel_data, voxel_size, remap=None, frame_offsets=None, device=None):
+    """Saved sparse voxels -> dense grid, ``muvo/data/dataset.py:317-327``: ``voxel_data (n,4)`` uint16 / int16 rows
+    ``[x, y, z, label]`` as ``voxelize_one`` saves them (NumPy array or device tensor; several files concatenated with
+    ``frame_offsets [F+1]``), label 255 -> 0 then ``remap[label]`` (dataset.py:322-323), written with the reference's
+    "last row wins" rule.  Returns a DEVICE tensor ``(F, Dx, Dy, Dz) uint8`` (``[0][None]`` is dataset.py:327's array)."""
+    lib = _lib.load()
+    dev = torch.device(device) if device is not None else (voxel_data.device if isinstance(voxel_data, torch.Tensor) and voxel_data.is_cuda
+                                                           else _default_device())
+    if isinstance(voxel_data, torch.Tensor):
+        vd = voxel_data.to(dev)
+        vd = vd.view(torch.int16) if vd.dtype in (torch.int16, torch.uint16) else vd.to(torch.int16)
+    else:
+        vd = torch.from_numpy(np.ascontiguousarray(np.asarray(voxel_data).astype(np.uint16, copy=False)).view(np.int16)).to(dev)
+    if vd.dim() != 2 or vd.shape[1] != 4:
+        raise ValueError("voxel_data must be (n, 4) rows [x, y, z, label]")
+    vd = vd.contiguous()
+    n = int(vd.shape[0])
+    off = _as_offsets(frame_offsets, n, dev)
+    F = off.numel() - 1
+    dx, dy, dz = (int(v) for v in voxel_size)
+    tab = None
+    if remap is not None:
+        t = np.asarray(remap, dtype=np.uint8).reshape(-1)
+        if t.size < 256:
+            t = np.concatenate([t, np.full(256 - t.size, t.max() if t.size else 0, np.uint8)])
+        tab = torch.from_numpy(np.ascontiguousarray(t[:256])).to(dev)
+    out = torch.empty((F, dx, dy, dz), dtype=torch.uint8, device=dev)
+    scratch = torch.empty((max(n, 1),), dtype=torch.uint8, device=dev)
+    n_bad = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.muvo_densify_sparse(_lib.ptr(vd), _lib.ptr(off), F, n, dx, dy, dz, _lib.ptr(tab), _lib.ptr(out), _lib.ptr(scratch),
+                                     _lib.ptr(n_bad), _lib.current_stream(dev))
+    _lib.check(rc, "muvo_densify_sparse")
+    out.n_bad = n_bad                    # rows outside the grid (numpy: IndexError); a device counter, read it if you care
+    return out
+
+
+def lidar_range_view(points_xyz, obj_tag, pc=None, lidar_position=(1.0, 0.0, 2.0), remap=None, frame_offsets=None,
+                     layout: str = "xyzd", device=None):
+    """``muvo/data/dataset.py:275-305`` for one or more raw semantic-LiDAR sweeps in ONE pass of the point kernels:
+    ``convert_coor_lidar`` + ``remap[ObjTag]`` + ego-box drop + ``do_range_projection`` (+ the ``(4,H,W)`` packing of
+    :301-303 with ``layout="xyzd"``).  ``points_xyz (P,3)`` float32 in the LiDAR frame and ``obj_tag (P,)`` uint8, NumPy or
+    device tensors (the inputs are not modified, unlike ``convert_coor_lidar``).  Returns :func:`sensor_to_grid`'s dict
+    of device tensors."""
+    dev = torch.device(device) if device is not None else (points_xyz.device if isinstance(points_xyz, torch.Tensor) and points_xyz.is_cuda
+                                                           else _default_device())
+    pts = points_xyz if isinstance(points_xyz, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(points_xyz, dtype=np.float32))
+    tag = obj_tag if isinstance(obj_tag, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(np.asarray(obj_tag).reshape(-1), dtype=np.uint8))
+    pts, tag = pts.to(dev, torch.float32), tag.to(dev, torch.uint8).reshape(-1)
+    if pc is None:
+        pc = PointCloud(lidar_position=lidar_position)
+    spec = pc.spec if isinstance(pc, PointCloud) else _RadianRangeSpec(pc.H, pc.W, float(pc.fov_down), float(pc.fov),
+                                                                      tuple(float(v) for v in np.asarray(pc.lidar_position, dtype=np.float64).reshape(-1)))
+    return sensor_to_grid(pts, tag, frame_offsets, range_spec=spec, layout=layout, want_diag=True,
+                          lidar_prep=LidarPrep(lidar_position=tuple(float(v) for v in lidar_position), remap=remap))
 
 
 def voxelize_one_array(pcd, sem, voxel_resolution, voxel_size, offset):

@@ -28,7 +28,7 @@ __all__ = [
     "label_remap_table", "range_projection", "range_projection_indices", "pack_range_view",
     "bev_intrinsics", "gen_dx_bx", "frustum_grid", "frustum_geometry", "bev_cell_ids",
     "cumsum_trick", "quick_cumsum_backward", "voxel_pooling_cumsum", "voxel_pooling_exact",
-    "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "label_pyramids", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
+    "frustum_pooling_forward", "decode_depth_image", "depth2pcd", "merge_pcd_arrays", "lidar_prep", "label_pyramids", "ssc_counts", "ssc_counts_loop", "ssc_add_batch_counts",
     "ssc_stats_from_counts", "sem_scal_loss", "geo_scal_loss", "scal_sums", "scatter_mean", "scatter_max",
 ]
 
@@ -134,6 +134,24 @@ def densify_voxels(voxel_data, voxel_size, remap=None):
 
 # --------------------------------------------------------------------------- N1: camera + LiDAR cloud in front of (a)
 EGO_VEHICLE_DIMENSION = [4.902, 2.128, 1.511]          # data/data_preprocessing.py:5
+
+
+def lidar_prep(points_xyz, obj_tag, lidar_position, remap=None, ego_dimension=EGO_VEHICLE_DIMENSION):
+    """The LiDAR-side prep in front of stage (b), muvo/data/dataset.py:278-290, on copies of the inputs:
+    ``convert_coor_lidar`` (data/data_preprocessing.py:119-122: in-place ``+=`` on the float32 array, ``y *= -1``),
+    ``remap[ObjTag]`` (:281-283) and the ego-box drop (:286-290).  Returns ``(points float32 (m,3), semantics uint8 (m,))``."""
+    pcd = np.array(points_xyz, dtype=np.float32, copy=True)
+    pcd += np.asarray(lidar_position)                               # data_preprocessing.py:120
+    pcd[:, 1] *= -1                                                 # :121
+    sem = np.asarray(obj_tag).reshape(-1)
+    if remap is not None:
+        sem = np.asarray(remap)[sem]                                # dataset.py:283
+    if ego_dimension is not None:
+        x, y, z = ego_dimension
+        ego_box = np.array([[-x / 2, -y / 2, 0], [x / 2, y / 2, z]])    # :287
+        ego_idx = ((ego_box[0] < pcd) & (pcd < ego_box[1])).all(axis=1)  # :288
+        sem, pcd = sem[~ego_idx], pcd[~ego_idx]                     # :289-290
+    return pcd, sem.astype(np.uint8)
 
 
 def decode_depth_image(img):

@@ -206,8 +206,52 @@ def golden_scal(R):
     save("scal.npz", **out)
 
 
+def golden_lidar(R):
+    """N1, LiDAR side: the reference's own ``convert_coor_lidar`` + the literal dataset.py:281-290 lines +
+    ``PointCloud.do_range_projection`` on a raw sweep (LiDAR frame, raw CARLA tags, some points inside the ego box); and the
+    sparse -> dense voxel glue of dataset.py:317-327 (``muvo.data.dataset`` itself needs lightning / the CARLA dataframes)."""
+    pts, sem = synth.carla_lidar_frame(12000, 6000)
+    raw = pts.copy()
+    raw[:, 1] *= -1
+    raw -= np.float32([1.0, 0.0, 2.0])                              # back to the LiDAR frame (float32, as CARLA stores it)
+    rng = np.random.default_rng(61)
+    raw[:400] = (rng.uniform([-3.4, -1.0, -2.0], [1.4, 1.0, -0.4], (400, 3))).astype(np.float32)   # in / around the ego box
+    tag = sem.copy()
+    tag[:400] = rng.integers(0, 23, 400)
+    lidar_position = [1.0, 0.0, 2.0]
+    LABEL_MAP = synth.LABEL_MAP
+    points = R.convert_coor_lidar(raw.copy(), lidar_position)                       # dataset.py:278
+    remap = np.full((max(LABEL_MAP.keys()) + 1), max(LABEL_MAP.values()), dtype=np.uint8)   # :281
+    remap[list(LABEL_MAP.keys())] = list(LABEL_MAP.values())                        # :282
+    semantics = remap[tag]                                                          # :283
+    x, y, z = [4.902, 2.128, 1.511]                                                 # constants.py:8
+    ego_box = np.array([[-x / 2, -y / 2, 0], [x / 2, y / 2, z]])                    # :287
+    ego_idx = ((ego_box[0] < points) & (points < ego_box[1])).all(axis=1)           # :288
+    semantics = semantics[~ego_idx]
+    points = points[~ego_idx]
+    pc = R.PointCloud(64, 1024, -30, 10, lidar_position)
+    d, xyz, sm = pc.do_range_projection(points, semantics)                          # :300
+    xyzd = np.concatenate([xyz, d[..., None]], axis=-1).transpose((2, 0, 1))        # :302-303
+    # sparse -> dense (:317-327) on a voxel_filter output with one 255 label and a duplicated row
+    v, l = R.voxel_filter(pts.copy(), sem, 0.5, [192, 192, 64], [0.0, 0, -10.0])
+    voxel_data = np.concatenate([v, l[:, None].astype(np.uint16)], axis=1)
+    voxel_data[5, 3] = 255
+    voxel_data = np.concatenate([voxel_data, voxel_data[10:12] * np.uint16([1, 1, 1, 0]) + np.uint16([0, 0, 0, 13]),
+                                 voxel_data[20:21]])       # (label 13 -> 0: the later row must win; an exact repeat)
+    voxel_points = voxel_data[:, :-1]
+    voxel_semantics = voxel_data[:, -1].copy()
+    voxel_semantics[voxel_semantics == 255] = 0                                     # :322
+    voxel_semantics = remap[voxel_semantics]                                        # :323
+    voxels = np.zeros([192, 192, 64], dtype=np.uint8)                               # :324
+    voxels[voxel_points[:, 0], voxel_points[:, 1], voxel_points[:, 2]] = voxel_semantics   # :325
+    save("lidar.npz", raw=raw, tag=tag, remap=remap, n_ego=np.int64(ego_idx.sum()), points=points, semantics=semantics,
+         depth=d, xyz=xyz, semimg=sm, xyzd=xyzd, voxel_data=voxel_data, voxels_packed=np.packbits(voxels > 0),
+         voxels_nz_idx=np.flatnonzero(voxels).astype(np.int32), voxels_nz_val=voxels.reshape(-1)[np.flatnonzero(voxels)])
+
+
 def main():
     R = ref_import.load()
+    golden_lidar(R)
     golden_merge(R)
     golden_voxel(R)
     golden_range(R)

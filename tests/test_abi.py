@@ -46,14 +46,16 @@ def test_header_compiles_as_plain_c(tmp_path):
 
 def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "s.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "muvo_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "muvo_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(MuvoGrid),offsetof(MuvoGrid,size),offsetof(MuvoGrid,roadline_id),sizeof(MuvoRangeCfg),'
-                   'offsetof(MuvoRangeCfg,fov),offsetof(MuvoRangeCfg,lidar_pos));return 0;}\n')
+                   'offsetof(MuvoRangeCfg,fov),offsetof(MuvoRangeCfg,lidar_pos),sizeof(MuvoLidarPrep),'
+                   'offsetof(MuvoLidarPrep,use_ego_box),offsetof(MuvoLidarPrep,remap256));return 0;}\n')
     exe = tmp_path / "s"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(_lib.MuvoGrid), _lib.MuvoGrid.size.offset, _lib.MuvoGrid.roadline_id.offset,
-            C.sizeof(_lib.MuvoRangeCfg), _lib.MuvoRangeCfg.fov.offset, _lib.MuvoRangeCfg.lidar_pos.offset]
+            C.sizeof(_lib.MuvoRangeCfg), _lib.MuvoRangeCfg.fov.offset, _lib.MuvoRangeCfg.lidar_pos.offset,
+            C.sizeof(_lib.MuvoLidarPrep), _lib.MuvoLidarPrep.use_ego_box.offset, _lib.MuvoLidarPrep.remap256.offset]
     assert got == want
 
 

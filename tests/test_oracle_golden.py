@@ -178,3 +178,17 @@ def test_scatter_oracle_known_answers():
     assert mx.tolist() == [[1, 2], [0, 0], [3, 5], [0, 0]] and arg.tolist() == [[0, 0], [4, 4], [1, 2], [4, 4]]
     t = torch.zeros((4, 2)).scatter_reduce(0, torch.from_numpy(idx)[:, None].expand(-1, 2), torch.from_numpy(src), "amax", include_self=False)
     assert np.array_equal(t.numpy(), mx)
+
+
+def test_lidar_prep_and_densify_match_reference_golden(golden):
+    """N1 (LiDAR side): the restatement of dataset.py:278-290 / :317-327 against the reference's own functions run on a raw
+    sweep (tests/golden/make_golden.py:golden_lidar)."""
+    g = golden("lidar.npz")
+    p, s = O.lidar_prep(g["raw"], g["tag"], [1.0, 0.0, 2.0], g["remap"])
+    assert p.dtype == np.float32 and np.array_equal(p, g["points"]) and np.array_equal(s, g["semantics"])
+    assert len(g["raw"]) - len(p) == int(g["n_ego"]) > 0
+    d, x, sm = O.range_projection(p, s, lidar_position=[1.0, 0.0, 2.0])
+    assert np.array_equal(d, g["depth"]) and np.array_equal(x, g["xyz"]) and np.array_equal(sm, g["semimg"])
+    assert np.array_equal(O.pack_range_view(d, x), g["xyzd"])
+    grid = O.densify_voxels(g["voxel_data"], (192, 192, 64), g["remap"])
+    assert np.array_equal(np.flatnonzero(grid), g["voxels_nz_idx"]) and np.array_equal(grid.reshape(-1)[g["voxels_nz_idx"]], g["voxels_nz_val"])

@@ -566,3 +566,75 @@ def test_label_pyramids_match_oracle(lib):
     want = O.label_pyramids(xyzd.cpu().numpy(), None, vox.cpu().numpy(), scale=50.0)
     for k in want:
         assert np.array_equal(got[k].cpu().numpy(), want[k]), k
+
+
+# ----------------------------------------------------------------------------- N1: LiDAR-side prep fused into (b), densify
+def test_lidar_range_view_fused_prep_matches_reference_golden(golden, lib):
+    """muvo/data/dataset.py:275-305 for a raw sweep in one pass of the point kernels (convert_coor_lidar + LABEL_MAP remap +
+    ego-box drop inside the kernels): bit-equal to the reference's own functions (tests/golden/lidar.npz), single frame and
+    a ragged batch of three, both layouts; the caller's arrays are not modified."""
+    from muvo_b200.points import lidar_range_view
+    g = golden("lidar.npz")
+    raw, tag = g["raw"].copy(), g["tag"].copy()
+    r = lidar_range_view(raw, tag, lidar_position=(1.0, 0.0, 2.0), remap=g["remap"], layout="hwc")
+    assert np.array_equal(raw, g["raw"]) and np.array_equal(tag, g["tag"])
+    assert np.array_equal(r["range_depth"][0].cpu().numpy(), g["depth"])
+    assert np.array_equal(r["range_xyz"][0].cpu().numpy(), g["xyz"])
+    assert np.array_equal(r["range_sem"][0].cpu().numpy(), g["semimg"])
+    n = len(raw)
+    cut = [0, 5000, 5000 + 3000, n]
+    rb = lidar_range_view(np.concatenate([raw[:5000], raw[:3000], raw]), np.concatenate([tag[:5000], tag[:3000], tag]),
+                          lidar_position=(1.0, 0.0, 2.0), remap=g["remap"], frame_offsets=np.array([0, 5000, 8000, 8000 + n]))
+    assert np.array_equal(rb["range_xyzd"][2].cpu().numpy(), g["xyzd"])
+    for f, m in ((0, 5000), (1, 3000)):
+        p, s = O.lidar_prep(raw[:m], tag[:m], [1.0, 0.0, 2.0], g["remap"])
+        d, x, sm = O.range_projection(p, s, lidar_position=[1.0, 0.0, 2.0])
+        assert np.array_equal(rb["range_xyzd"][f].cpu().numpy(), O.pack_range_view(d, x))
+        assert np.array_equal(rb["range_sem"][f].cpu().numpy(), sm)
+    # without the ego box / remap the fused path equals convert_coor_lidar + plain projection
+    from muvo_b200.points import LidarPrep, RangeSpec, sensor_to_grid
+    r2 = sensor_to_grid(torch.from_numpy(raw).cuda(), torch.from_numpy(tag).cuda(), None, range_spec=RangeSpec(lidar_position=(1.0, 0.0, 2.0)),
+                        layout="hwc", lidar_prep=LidarPrep(ego_dimension=None))
+    p, s = O.lidar_prep(raw, tag, [1.0, 0.0, 2.0], None, ego_dimension=None)
+    d, x, sm = O.range_projection(p, s, lidar_position=[1.0, 0.0, 2.0])
+    assert np.array_equal(r2["range_depth"][0].cpu().numpy(), d) and np.array_equal(r2["range_sem"][0].cpu().numpy(), sm)
+
+
+def test_densify_voxels_matches_reference_golden_and_last_row_wins(golden, lib):
+    """dataset.py:317-327 on the device: 255 -> 0, remap, duplicates resolved like numpy's fancy assignment, files batched."""
+    from muvo_b200.points import densify_voxels
+    g = golden("lidar.npz")
+    vd = g["voxel_data"]
+    want = np.zeros(192 * 192 * 64, np.uint8)
+    want[g["voxels_nz_idx"]] = g["voxels_nz_val"]
+    got = densify_voxels(vd, (192, 192, 64), g["remap"])
+    assert got.shape == (1, 192, 192, 64) and np.array_equal(got[0].cpu().numpy().reshape(-1), want)
+    rng = np.random.default_rng(9)
+    rows = np.stack([rng.integers(0, 12, 4000), rng.integers(0, 10, 4000), rng.integers(0, 6, 4000), rng.integers(0, 23, 4000)], 1).astype(np.uint16)
+    rows[rng.random(4000) < 0.05, 3] = 255                                    # 720 voxels, 4000 rows: heavy duplication
+    off = np.array([0, 1500, 1500, 4000])
+    gb = densify_voxels(rows, (12, 10, 6), None, frame_offsets=off)
+    for f in range(3):
+        assert np.array_equal(gb[f].cpu().numpy(), O.densify_voxels(rows[off[f]:off[f + 1]], (12, 10, 6), None))
+    assert int(gb.n_bad.item()) == 0
+    bad = rows.copy(); bad[7, 0] = 12
+    assert int(densify_voxels(bad, (12, 10, 6), None).n_bad.item()) == 1
+
+
+def test_voxelize_one_drop_in_matches_reference_golden(golden, lib, tmp_path):
+    """``muvo_b200.points.voxelize_one`` (the replacement of data/generate_voxels.py:64-77, files in / file out) against the
+    reference's merge_pcd + voxel_filter run on the same files (tests/golden/merge.npz)."""
+    import types
+    cv2 = pytest.importorskip("cv2")
+    from muvo_b200.points import voxelize_one
+    g = golden("merge.npz")
+    img, lx, ls = g["img"], g["lidar_xyz"], g["lidar_sem"]
+    depth_file, lidar_file = str(tmp_path / "d.png"), str(tmp_path / "l.npy")
+    assert cv2.imwrite(depth_file, img)
+    np.save(lidar_file, {"points_xyz": lx, "ObjTag": ls}, allow_pickle=True)
+    cfg = types.SimpleNamespace(camera_position=[1.0, 0.0, 2.0], lidar_position=[1.0, 0.0, 2.0], fov=110, bev_offset_forward=0,
+                                bev_resolution=0.2, offset_z=-20, voxel_resolution=0.5, voxel_size=[192, 192, 64])
+    out = voxelize_one(depth_file, lidar_file, cfg, str(tmp_path / "v.npy"))
+    want = np.concatenate([g["vox"], g["lab"][:, None].astype(np.uint16)], 1)      # the reference's merge_pcd + voxel_filter (:64-73)
+    assert out.dtype == np.uint16 and np.array_equal(out, want)
+    assert np.array_equal(np.load(str(tmp_path / "v.npy")), want)
