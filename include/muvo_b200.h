@@ -136,6 +136,14 @@ MUVO_API int muvo_merge_pcd(const uint8_t* img_bgra, int32_t H, int32_t W, doubl
                    const double* camera_pos_h, const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar,
                    const double* lidar_pos_h, const double* ego_box_h, double* xyz_out, uint8_t* sem_out,
                    int64_t* n_out, void* ws, size_t ws_bytes, void* stream);
+/* The same for frame `frame` of a batch: the merged cloud is written at row row_offsets[frame] of xyz_out / sem_out (device
+ * int64 array, row_offsets[0] set by the caller, normally 0) and row_offsets[frame + 1] = row_offsets[frame] + n is written by
+ * the call, so that N frames are packed back to back by N stream-ordered calls without a host synchronisation; the array is
+ * then the frame_offsets of muvo_voxelize.  Rows at or beyond capacity_rows are not written (check row_offsets afterwards). */
+MUVO_API int muvo_merge_pcd_at(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, double range, const double* camera_pos_h,
+                      const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar, const double* lidar_pos_h,
+                      const double* ego_box_h, double* xyz_out, uint8_t* sem_out, int64_t capacity_rows, int64_t* row_offsets,
+                      int32_t frame, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- N1: label pyramids behind (a)/(b) --------------------------------------------
  * Replaces the LIDAR_RE / LIDAR_SEG / VOXEL_SEG blocks of PreProcess.forward, muvo/models/preprocess.py:151-186:

@@ -53,6 +53,8 @@ SIGNATURES = {
     "muvo_merge_pcd_workspace_bytes": (C.c_int, [_I32, _I32, _I64, C.POINTER(_SZ)]),
     "muvo_merge_pcd": (C.c_int, [_P, _I32, _I32, C.c_double, C.c_double, C.POINTER(C.c_double), _P, _P, _I64, C.POINTER(C.c_double),
                                  C.POINTER(C.c_double), _P, _P, _P, _P, _SZ, _P]),
+    "muvo_merge_pcd_at": (C.c_int, [_P, _I32, _I32, C.c_double, C.c_double, C.POINTER(C.c_double), _P, _P, _I64, C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), _P, _P, _I64, _P, _I32, _P, _SZ, _P]),
     "muvo_label_pyramids": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, C.c_float, _P, _P, _P, _P, _P, _P, _P, _P]),
     "muvo_voxelize": (C.c_int, [_P, _I32, _P, _P, _I32, _I64, C.POINTER(MuvoGrid), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "muvo_range_project": (C.c_int, [_P, _P, _P, _I32, _I64, C.POINTER(MuvoRangeCfg), _I32, _P, _P, _P, _P, _P, _SZ, _P]),

@@ -73,7 +73,7 @@ k_merge_count(MergeDev m, const uint8_t* __restrict__ img, const float* __restri
 }
 
 __global__ void __launch_bounds__(1024)
-k_merge_scan(uint32_t* __restrict__ block_cnt, int nblocks, int64_t* __restrict__ n_out) {
+k_merge_scan(uint32_t* __restrict__ block_cnt, int nblocks, int64_t* __restrict__ n_out, int64_t* __restrict__ row_offsets, int frame) {
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -95,12 +95,16 @@ k_merge_scan(uint32_t* __restrict__ block_cnt, int nblocks, int64_t* __restrict_
     if (threadIdx.x == 1023) carry_s = carry + wbase + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *n_out = (int64_t)carry_s;
+  if (threadIdx.x == 0) {
+    if (n_out) *n_out = (int64_t)carry_s;
+    if (row_offsets) row_offsets[frame + 1] = row_offsets[frame] + (int64_t)carry_s;    // batched: frames packed back to back
+  }
 }
 
 __global__ void __launch_bounds__(kMergeBlock)
 k_merge_write(MergeDev m, const uint8_t* __restrict__ img, const float* __restrict__ lxyz, const uint8_t* __restrict__ lsem,
-              const uint32_t* __restrict__ block_off, double* __restrict__ xyz_out, uint8_t* __restrict__ sem_out) {
+              const uint32_t* __restrict__ block_off, double* __restrict__ xyz_out, uint8_t* __restrict__ sem_out,
+              const int64_t* __restrict__ row_offsets, int frame, int64_t capacity) {
   __shared__ uint32_t ws[kMergeBlock / 32];
   const int64_t e = (int64_t)blockIdx.x * kMergeBlock + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -113,7 +117,8 @@ k_merge_write(MergeDev m, const uint8_t* __restrict__ img, const float* __restri
 #pragma unroll
   for (int k = 0; k < kMergeBlock / 32; ++k) if (k < warp) wbase += ws[k];
   if (keep) {
-    const int64_t r = (int64_t)block_off[blockIdx.x] + wbase + __popc(bal & ((1u << lane) - 1u));
+    const int64_t r = (row_offsets ? row_offsets[frame] : 0) + (int64_t)block_off[blockIdx.x] + wbase + __popc(bal & ((1u << lane) - 1u));
+    if (capacity >= 0 && r >= capacity) return;                        // (batched output buffer too small: the host checks the offsets)
     xyz_out[3 * r] = X; xyz_out[3 * r + 1] = Y; xyz_out[3 * r + 2] = Z;
     sem_out[r] = lab;
   }
@@ -134,12 +139,12 @@ int muvo_merge_pcd_workspace_bytes(int32_t H, int32_t W, int64_t n_lidar, size_t
   return MUVO_OK;
 }
 
-int muvo_merge_pcd(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, double range, const double* camera_pos_h,
-                   const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar, const double* lidar_pos_h,
-                   const double* ego_box_h, double* xyz_out, uint8_t* sem_out, int64_t* n_out, void* ws, size_t ws_bytes,
-                   void* stream) {
+static int run_merge(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, double range, const double* camera_pos_h,
+                     const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar, const double* lidar_pos_h,
+                     const double* ego_box_h, double* xyz_out, uint8_t* sem_out, int64_t* n_out, int64_t* row_offsets, int frame,
+                     int64_t capacity, void* ws, size_t ws_bytes, void* stream) {
   if (H < 0 || W < 0 || n_lidar < 0 || ((int64_t)H * W > 0 && !(focal > 0.0))) return MUVO_E_ARG;
-  if (!camera_pos_h || !lidar_pos_h || !n_out || !ws) return MUVO_E_NULL;
+  if (!camera_pos_h || !lidar_pos_h || (!n_out && !row_offsets) || !ws) return MUVO_E_NULL;
   const int64_t n_img = (int64_t)H * W, n = n_img + n_lidar;
   if ((n_img > 0 && !img_bgra) || (n_lidar > 0 && (!lidar_xyz || !lidar_sem)) || (n > 0 && (!xyz_out || !sem_out))) return MUVO_E_NULL;
   if (n >= ((int64_t)1 << 31) * kMergeBlock) return MUVO_E_SHAPE;
@@ -157,11 +162,31 @@ int muvo_merge_pcd(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, 
   prof_mark("<merge_pcd>", st);
   k_merge_count<<<(unsigned)nblocks, kMergeBlock, 0, st>>>(m, img_bgra, lidar_xyz, lidar_sem, block_cnt);
   MUVO_AFTER_LAUNCH("k_merge_count", st);
-  k_merge_scan<<<1, 1024, 0, st>>>(block_cnt, (int)nblocks, n_out);
+  k_merge_scan<<<1, 1024, 0, st>>>(block_cnt, (int)nblocks, n_out, row_offsets, frame);
   MUVO_AFTER_LAUNCH("k_merge_scan", st);
-  k_merge_write<<<(unsigned)nblocks, kMergeBlock, 0, st>>>(m, img_bgra, lidar_xyz, lidar_sem, block_cnt, xyz_out, sem_out);
+  k_merge_write<<<(unsigned)nblocks, kMergeBlock, 0, st>>>(m, img_bgra, lidar_xyz, lidar_sem, block_cnt, xyz_out, sem_out, row_offsets,
+                                                            frame, capacity);
   MUVO_AFTER_LAUNCH("k_merge_write", st);
   return MUVO_OK;
+}
+
+int muvo_merge_pcd(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, double range, const double* camera_pos_h,
+                   const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar, const double* lidar_pos_h,
+                   const double* ego_box_h, double* xyz_out, uint8_t* sem_out, int64_t* n_out, void* ws, size_t ws_bytes,
+                   void* stream) {
+  if (!n_out) return MUVO_E_NULL;
+  return run_merge(img_bgra, H, W, focal, range, camera_pos_h, lidar_xyz, lidar_sem, n_lidar, lidar_pos_h, ego_box_h, xyz_out, sem_out,
+                   n_out, nullptr, 0, -1, ws, ws_bytes, stream);
+}
+
+int muvo_merge_pcd_at(const uint8_t* img_bgra, int32_t H, int32_t W, double focal, double range, const double* camera_pos_h,
+                      const float* lidar_xyz, const uint8_t* lidar_sem, int64_t n_lidar, const double* lidar_pos_h,
+                      const double* ego_box_h, double* xyz_out, uint8_t* sem_out, int64_t capacity_rows, int64_t* row_offsets,
+                      int32_t frame, void* ws, size_t ws_bytes, void* stream) {
+  if (!row_offsets) return MUVO_E_NULL;
+  if (frame < 0 || capacity_rows < 0) return MUVO_E_ARG;
+  return run_merge(img_bgra, H, W, focal, range, camera_pos_h, lidar_xyz, lidar_sem, n_lidar, lidar_pos_h, ego_box_h, xyz_out, sem_out,
+                   nullptr, row_offsets, frame, capacity_rows, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

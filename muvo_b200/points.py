@@ -362,6 +362,49 @@ def merge_pcd_device(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, 
     return xyz[:n], sem[:n]
 
 
+def merge_pcd_batch(frames, camera_pos, lidar_pos, fov=110, mask_ego=True, device=None):
+    """``merge_pcd`` for a list of decoded frames ``[(img, lidar_xyz, lidar_sem), ...]`` packed back to back on the device
+    with NO host synchronisation in between (``muvo_merge_pcd_at`` chains the row offsets on the device).  Returns
+    ``(xyz float64 (cap,3), sem uint8 (cap,), row_offsets int64 (N+1,))`` device tensors; ``row_offsets`` is the
+    ``frame_offsets`` of :func:`sensor_to_grid` (read it once to learn the total)."""
+    if not torch.cuda.is_available():
+        raise _lib.MuvoError("muvo_b200 kernels need a CUDA device (sm_100a); no CPU fallback exists")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    lib = _lib.load()
+    N = len(frames)
+    cam = (C.c_double * 3)(*[float(np.float32(v)) for v in camera_pos])
+    lid = (C.c_double * 3)(*[float(v) for v in lidar_pos])
+    box = None
+    if mask_ego:
+        x, y, z = EGO_VEHICLE_DIMENSION
+        box = (C.c_double * 6)(-x / 2, -y / 2, 0.0, x / 2, y / 2, z)
+    staged, cap, ws_need = [], 0, 0
+    for img, lxyz, lsem in frames:
+        img_t = torch.as_tensor(np.ascontiguousarray(img, dtype=np.uint8))
+        if img_t.dim() != 3 or img_t.shape[2] != 4:
+            raise ValueError("img must be uint8 (H, W, 4) as cv2.imread(file, -1) returns it")
+        lx = torch.as_tensor(np.ascontiguousarray(lxyz, dtype=np.float32))
+        ls = torch.as_tensor(np.ascontiguousarray(np.asarray(lsem).reshape(-1), dtype=np.uint8))
+        H, W, n = int(img_t.shape[0]), int(img_t.shape[1]), int(lx.shape[0])
+        nb = C.c_size_t(0)
+        _lib.check(lib.muvo_merge_pcd_workspace_bytes(H, W, n, C.byref(nb)), "muvo_merge_pcd_workspace_bytes")
+        ws_need = max(ws_need, nb.value)
+        cap += H * W + n
+        staged.append((img_t.to(dev, non_blocking=True), lx.to(dev, non_blocking=True), ls.to(dev, non_blocking=True), H, W, n))
+    xyz = torch.empty((max(cap, 1), 3), dtype=torch.float64, device=dev)
+    sem = torch.empty((max(cap, 1),), dtype=torch.uint8, device=dev)
+    offs = torch.zeros((N + 1,), dtype=torch.int64, device=dev)
+    ws = torch.empty(max(ws_need, 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = _lib.current_stream(dev)
+        for f, (img_t, lx, ls, H, W, n) in enumerate(staged):
+            focal = float(W / (2.0 * np.tan(fov * np.pi / 360.0)))
+            rc = lib.muvo_merge_pcd_at(_lib.ptr(img_t), H, W, focal, 100.0, cam, _lib.ptr(lx), _lib.ptr(ls), n, lid, box, xyz.data_ptr(),
+                                       sem.data_ptr(), cap, offs.data_ptr(), f, ws.data_ptr(), ws.numel(), stream)
+            _lib.check(rc, "muvo_merge_pcd_at")
+    return xyz, sem, offs
+
+
 def merge_pcd_arrays(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov=110, mask_ego=True):
     """``merge_pcd`` on arrays, NumPy in / NumPy out: ``(pcd float64 (n,3), semantic uint8 (n,1))``."""
     xyz, sem = merge_pcd_device(img, lidar_xyz, lidar_sem, camera_pos, lidar_pos, fov, mask_ego)

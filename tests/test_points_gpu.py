@@ -638,3 +638,22 @@ def test_voxelize_one_drop_in_matches_reference_golden(golden, lib, tmp_path):
     want = np.concatenate([g["vox"], g["lab"][:, None].astype(np.uint16)], 1)      # the reference's merge_pcd + voxel_filter (:64-73)
     assert out.dtype == np.uint16 and np.array_equal(out, want)
     assert np.array_equal(np.load(str(tmp_path / "v.npy")), want)
+
+
+def test_batched_voxelisation_equals_frame_by_frame(lib):
+    """generate_voxels.voxelize_frames: N merges packed on the device (muvo_merge_pcd_at), one launch of the point kernels
+    over the ragged batch, two host syncs -- the same (n,4) arrays as one frame at a time, for frames of different sizes."""
+    from muvo_b200.generate_voxels import load_config, voxelize_frame, voxelize_frames
+    cfg = load_config()
+    frames = []
+    for k, (h, w, n) in enumerate([(150, 240, 8000), (100, 160, 3000), (150, 240, 0), (60, 80, 12000)]):
+        img = synth.carla_depth_image(7400 + k, h=h, w=w)
+        pts, sem = synth.carla_lidar_frame(max(n, 1), 7410 + k)
+        lid = pts.copy(); lid[:, 1] *= -1; lid -= np.float32([1, 0, 2])
+        frames.append((img, lid[:n], sem[:n]))
+    got = voxelize_frames(frames, cfg)
+    assert len(got) == len(frames)
+    for f, g in zip(frames, got):
+        want = voxelize_frame(*f, cfg)
+        assert g.dtype == np.uint16 and np.array_equal(g, want)
+    assert voxelize_frames([], cfg) == []
