@@ -299,11 +299,15 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
     const double s = range_sq_of(x, y, z, r, &xc, &yc, &zc);
     int pix;
     if (ent.y == kQExact) {
-      int iw, ih, flags;
-      pix_exact(xc, yc, zc, s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
-      if (flags & 4) { ++n_drop; continue; }
-      n_nw += (flags & 1) ? 1u : 0u; n_nh += (flags & 2) ? 1u : 0u;
-      pix = ih * r.W + iw;
+      const uint32_t pr = pix_refine(x, y, z, r);               // the side of the nearest edge decides (no atan2 / asin) ...
+      if (pr != kPixUndecided) pix = (int)pr;
+      else {                                                    // ... unless the point is within 1e-9 of it: the reference formula
+        int iw, ih, flags;
+        pix_exact(xc, yc, zc, s, r.H, r.W, r.fda, r.fov, &iw, &ih, &flags);
+        if (flags & 4) { ++n_drop; continue; }
+        n_nw += (flags & 1) ? 1u : 0u; n_nh += (flags & 2) ? 1u : 0u;
+        pix = ih * r.W + iw;
+      }
     } else {
       pix = pix_fast(x, y, z, r).pix;
     }

@@ -43,6 +43,33 @@ elif a.stage == "bev":
     for _ in range(a.steps):
         out = bev_pool(x, cell, 2304)
         torch.autograd.grad(out, x, torch.ones_like(out))
+elif a.stage == "misc":         # every kernel that ships without a dedicated profile: sparse emit, merge, pyramids, densify, pillar scatter,
+    # LiDAR-prep range path, streamed BEV pool (module call) -- one call each at bench-like sizes
+    from muvo_b200 import pillars
+    from muvo_b200.points import densify_voxels, label_pyramids, lidar_range_view, merge_pcd_batch
+    pts, sem, off = synth.lidar_batch(24, a.nmin, a.nmax, 2000)
+    tp, ts, to = torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev), torch.from_numpy(off).to(dev)
+    frames = []
+    for k in range(4):
+        img = synth.carla_depth_image(5100 + k)
+        p1, s1 = synth.carla_lidar_frame(60000, 5200 + k)
+        lid = p1.copy(); lid[:, 1] *= -1; lid -= torch.tensor([1.0, 0.0, 2.0]).numpy()
+        frames.append((img, lid, s1))
+    feat, depth, mask, K, E = synth.bev_inputs(6, 384, 3000, device=dev)
+    fp = muvo_b200.FrustumPooling(**synth.BEV_POOL_ARGS).to(dev)
+    x = synth.lift(feat, depth).detach()
+    src = torch.randn(200_000, 64, device=dev)
+    idx = torch.randint(0, 12000, (200_000,), device=dev)
+    for _ in range(a.steps):
+        r = sensor_to_grid(tp, ts, to, grid=GridSpec(), dense=False, sparse=True, packed_sparse=True)                 # k_emit_sparse, k_frame_prefix, scan role
+        rows = r["voxel_sparse"].view(torch.int16)
+        dense = densify_voxels(r["voxel_sparse"][:int(r["sparse_start"][-1])], (192, 192, 64), synth.label_remap256(),
+                               frame_offsets=r["sparse_start"])                                                         # k_densify_*
+        rv = lidar_range_view(tp, ts, frame_offsets=to, remap=synth.label_remap256())                                    # prep variant of the point pass
+        label_pyramids(rv["range_xyzd"], rv["range_sem"], dense)                                                        # k_range_pyramid, k_voxel_pyramid
+        merge_pcd_batch(frames, [1.0, 0.0, 2.0], [1.0, 0.0, 2.0])                                                       # k_merge_*
+        pillars.scatter_mean(src, idx, dim_size=12000); pillars.scatter_max(src, idx, dim_size=12000)                   # k_pillar_*
+        fp(x, K[:, None], E[:, None], mask)                                                                             # k_chunk_compact + k_pool_stream
 elif a.stage == "other":        # (d) counts, N4 scal losses fwd + bwd, N2 fused lift-splat fwd + bwd at the bench shapes
     from muvo_b200.frustum_pooling import lift_splat
     from muvo_b200.losses import scal_losses
