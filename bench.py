@@ -698,14 +698,14 @@ def other_stages(device, rank, world, hbm_peak, args):
         ssc()
         got = acc.cpu().numpy()
         # the collective taken off the per-batch path: SSCMetrics(sync_dist="epoch") accumulates on the device and reduces
-        # once (trainer.py:515-567 reads the statistics at epoch end only); 8 batches + the flush, per batch
+        # once (trainer.py:515-567 reads the statistics at epoch end only); 32 batches + the flush, per batch
         md = muvo_b200.SSCMetrics(Cn, sync_dist="epoch")
 
         def ssc_epoch():
-            for _ in range(8):
+            for _ in range(32):
                 md.add_batch(tp, tt)
             md.get_stats()
-        ms_e = timed(ssc_epoch, max(2, steps // 2)) / 8
+        ms_e = timed(ssc_epoch, max(2, steps // 2)) / 32
         bytes_d = tp.numel() * 9
         key = "ssc_counts" if Cn == 2 else "ssc_counts_c9"
         res[key] = {"ms": ms_d, "kernel_only_ms": ms_k, "algorithmic_GBps": bytes_d / ms_d / 1e6, "frac": bytes_d / ms_d / 1e6 / hbm_peak,
