@@ -298,7 +298,7 @@ def run_ours(args):
     top = max(kern, key=kern.get)
     achieved = alg_kernel.get(top, 0) / (kern[top] * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")      # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tp):
         tj = json.load(open(tp))
         if top in tj.get("kernels", {}):

@@ -9,12 +9,14 @@
 //
 //   L  k_chunk_lists : per (frame, chunk of 2048 points): keys (cell << 11 | position) of the kept points, mask folded in,
 //                      bitonic-sorted in shared memory (= stable by cell, ascending point order inside a cell) and written
-//                      lane-interleaved: lane l of a warp owns the contiguous run [l*m, (l+1)*m) of the sorted list.
-//   P  k_pool_stream : one CTA per (frame, 8 channels), walking the chunks in order; consumer warp w owns channel w, so its
-//                      accumulators (n_cells floats in shared memory) are private: no atomics, no CTA-wide barrier.  A lane
-//                      sums its run sequentially; the segment that a run shares with the previous lanes (its first cell)
-//                      is combined by a fixed shuffle tree.  The summation order is a function of (geometry, mask) only:
-//                      deterministic, and within the fp32 tolerance of the reference's cumsum differencing.
+//                      row-interleaved per warp portion (write_rows).  k_chunk_compact: the same from a cached,
+//                      mask-independent sorted plan by a stable compaction (no sort per call).
+//   P  k_pool_stream : one CTA per (frame, 8 channels), walking the chunks in order; a chunk's list is cut into 8 warp
+//                      portions at cell boundaries, every lane owns a contiguous run of its warp's portion and sums it for
+//                      all 8 channels at once (accumulators: 8 x n_cells floats in shared memory, no atomics); the segment a
+//                      run shares with the previous lanes (its first cell) is combined by a fixed shuffle tree; one named
+//                      barrier per chunk.  The summation order is a function of (geometry, mask) only: deterministic, and
+//                      within the fp32 tolerance of the reference's cumsum differencing.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include "bev_stream.cuh"
@@ -37,12 +39,55 @@ template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return _
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ---------------------------------------------------------------- L: per-chunk sorted lists
-// lists[b][k][i * 256 + v] = sorted[v * m + i]: "virtual lane" v (= thread of the pool kernel's 8 consumer warps) owns the
-// contiguous run [v*m, (v+1)*m) of the chunk's sorted key list, m = ceil(n / 256) = steps[b][k].
+// Layout of one chunk's list (kListStride u32 = 74 rows of 32): row 0 is a header, word w < 8 = (first row << 16 | rows) of
+// consumer warp w, word 8 = total rows; the data rows follow.  The chunk's sorted keys [0, n) are cut into 8 warp portions
+// AT CELL BOUNDARIES (the first cell start at or after w * n / 8), so no cell is shared between two warps of the pool kernel
+// (no cross-warp ordering, no barrier); inside a portion of length L, lane l owns the contiguous run [l*m, (l+1)*m),
+// m = ceil(L / 32), stored row-interleaved: row i holds entry l*m + i of every lane.  Rows <= n/32 + 8 <= 72.
+// steps[b][k] = 1 + data rows = rows the pool kernel's producer copies.
+constexpr int kListRows = kStreamChunk / 32 + kSCh + 2;          // header + data rows (+1 spare): 74
+constexpr int kListStride = kListRows * 32;                      // u32 per chunk
+
+// `keys` = the chunk's n sorted keys in shared memory (visible to the block); called by every thread of a block of >= 256 threads
+__device__ __forceinline__ void write_rows(const uint32_t* keys, int n, uint32_t* __restrict__ out, uint32_t* __restrict__ steps_slot,
+                                           uint32_t* hdr_s /* [kSCh + 1] shared scratch */) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned lane = lane_id();
+  if (warp < kSCh) {                                             // warp w: portion start b_w = first cell start >= w * n / 8
+    int bnd = (int)(((int64_t)warp * n) / kSCh);
+    if (warp > 0 && bnd > 0) {
+      for (;;) {                                                 // 32 candidates per round
+        const int p = bnd + (int)lane;
+        const bool hit = p >= n || (keys[p] >> kStreamPosBits) != (keys[p - 1] >> kStreamPosBits);
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (bal) { bnd += __ffs(bal) - 1; break; }
+        bnd += 32;
+      }
+      if (bnd > n) bnd = n;
+    }
+    if (lane == 0) hdr_s[warp] = (uint32_t)bnd;
+  }
+  if (tid == 0) hdr_s[kSCh] = (uint32_t)n;
+  __syncthreads();
+  uint32_t row = 1, my_hdr = 0;                                  // every thread derives the 8 (first row, rows) pairs itself
+  for (int w = 0; w < kSCh; ++w) {
+    const uint32_t b0 = hdr_s[w], b1 = hdr_s[w + 1], m = (b1 - b0 + 31u) >> 5;
+    if (tid == w) my_hdr = (row << 16) | m;
+    for (int idx = tid; idx < (int)m * 32; idx += blockDim.x) {
+      const uint32_t src = b0 + (uint32_t)(idx & 31) * m + (uint32_t)(idx >> 5);
+      out[(row + (idx >> 5)) * 32 + (idx & 31)] = src < b1 ? keys[src] : kNone;
+    }
+    row += m;
+  }
+  if (tid < 32) out[tid] = tid < kSCh ? my_hdr : (tid == kSCh ? row : 0u);
+  if (tid == 0) *steps_slot = row;                               // header row + data rows
+}
+
 __global__ void __launch_bounds__(kListThreads)
 k_chunk_lists(const int32_t* __restrict__ cell0, const uint8_t* __restrict__ mask, int32_t* __restrict__ cell_out, int64_t n_pts,
               int n_cells, int n_chunks, uint32_t* __restrict__ lists, uint32_t* __restrict__ steps, int plan_mode) {
   __shared__ uint32_t s[kStreamChunk];
+  __shared__ uint32_t hdr_s[kSCh + 1];
   __shared__ int n_s;
   const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
   const int64_t base = (int64_t)k * kStreamChunk;
@@ -78,18 +123,14 @@ k_chunk_lists(const int32_t* __restrict__ cell0, const uint8_t* __restrict__ mas
     if (s[i] != kNone && (i == kStreamChunk - 1 || s[i + 1] == kNone)) n_s = i + 1;
   }
   __syncthreads();
-  const int n = n_s, m = (n + kSVirt - 1) / kSVirt;
-  uint32_t* out = lists + ((size_t)b * n_chunks + k) * kStreamChunk;
+  const int n = n_s;
   if (plan_mode) {                // the mask-independent plan: the sorted keys as they are + their count (k_chunk_compact's input)
+    uint32_t* out = lists + ((size_t)b * n_chunks + k) * kStreamChunk;
     for (int idx = tid; idx < kStreamChunk; idx += kListThreads) out[idx] = s[idx];
     if (tid == 0) steps[(size_t)b * n_chunks + k] = (uint32_t)n;
     return;
   }
-  for (int idx = tid; idx < m * kSVirt; idx += kListThreads) {
-    const int src = (idx % kSVirt) * m + (idx / kSVirt);
-    out[idx] = src < n ? s[src] : kNone;
-  }
-  if (tid == 0) steps[(size_t)b * n_chunks + k] = (uint32_t)m;
+  write_rows(s, n, lists + ((size_t)b * n_chunks + k) * kListStride, steps + (size_t)b * n_chunks + k, hdr_s);
 }
 
 // Per call, with a cached plan: keep the plan entries whose mask byte is set (a stable compaction: the order by cell, then
@@ -103,6 +144,7 @@ k_chunk_compact(const uint32_t* __restrict__ plan, const uint32_t* __restrict__ 
   __shared__ __align__(16) uint8_t ms[kStreamChunk];
   __shared__ uint32_t cs[kStreamChunk];
   __shared__ uint32_t wsum[kCompactThreads / 32];
+  __shared__ uint32_t hdr_s[kSCh + 1];
   const int b = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
   const unsigned lane = lane_id();
   const int64_t base = (int64_t)b * n_pts + (int64_t)k * kStreamChunk;
@@ -138,18 +180,10 @@ k_chunk_compact(const uint32_t* __restrict__ plan, const uint32_t* __restrict__ 
 #pragma unroll
   for (int u = 0; u < kCompactPer; ++u) if (keep & (1u << u)) cs[o++] = e[u];
   __syncthreads();
-  const int n = (int)total, m = (n + kSVirt - 1) / kSVirt;
-  uint32_t* out = lists + slot * kStreamChunk;
-  for (int idx = tid; idx < m * kSVirt; idx += kCompactThreads) {
-    const int src = (idx % kSVirt) * m + (idx / kSVirt);
-    out[idx] = src < n ? cs[src] : kNone;
-  }
-  if (tid == 0) steps[slot] = (uint32_t)m;
+  write_rows(cs, (int)total, lists + slot * kListStride, steps + slot, hdr_s);
 }
 
 // ---------------------------------------------------------------- P: streamed pool
-__device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kSVirt) : "memory"); }
-
 template <typename T, int NS>
 __global__ void __launch_bounds__(kSThreads, 1)
 k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* __restrict__ lists, const uint32_t* __restrict__ steps,
@@ -157,15 +191,12 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr size_t kChanBytes = (size_t)kStreamChunk * sizeof(T);
   constexpr size_t kTileBytes = kChanBytes * kSCh;
-  constexpr size_t kListBytes = (size_t)kStreamChunk * 4;
+  constexpr size_t kListBytes = (size_t)kListStride * 4;
   constexpr size_t kStageBytes = kTileBytes + kListBytes;
-  // [NS stages: 8 channel tiles + the chunk's list] [acc: 8 x n_cells floats] [carry: 8 warps x 8 floats, 8 cells] [m per stage] [barriers]
+  // [NS stages: 8 channel tiles + the chunk's list] [acc: 8 x n_cells floats] [barriers]
   float* acc = reinterpret_cast<float*>(smem + NS * kStageBytes);
   const size_t acc_bytes = align_up16((size_t)kSCh * n_cells * 4);
-  float* carry = reinterpret_cast<float*>(smem + NS * kStageBytes + acc_bytes);
-  uint32_t* carry_cell = reinterpret_cast<uint32_t*>(carry + kSCh * kSCh);
-  int* mstep = reinterpret_cast<int*>(carry_cell + kSCh);
-  uint64_t* full = reinterpret_cast<uint64_t*>(mstep + 8);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * kStageBytes + acc_bytes);
   uint64_t* empty = full + NS;
   const int tid = threadIdx.x, warp = tid >> 5;
   const unsigned lane = lane_id();
@@ -179,36 +210,39 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
   if (warp == kSCh) {
     // ---- producer: one elected lane issues every bulk copy of this CTA
     if (lane == 0) {
-      const uint64_t pol = l2_evict_first_policy();
+      const uint64_t pol = l2_evict_first_policy(), pol_keep = l2_default_policy();
       uint32_t it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int b = item / n_cg, c0 = (item % n_cg) * kSCh;
         const int nc = C - c0 < kSCh ? C - c0 : kSCh;
         const T* xb = x + (int64_t)b * sb + (int64_t)c0 * sc;
         const uint32_t* mb = steps + (size_t)b * n_chunks;
-        uint32_t m_next = __ldg(mb);
+        uint32_t rows_next = __ldg(mb);
         for (int k = 0; k < n_chunks; ++k, ++it) {
           const int s = it % NS;
           const uint32_t use = it / NS;
-          const uint32_t m = m_next;
-          if (k + 1 < n_chunks) m_next = __ldg(mb + k + 1);
+          const uint32_t rows = rows_next;                               // header row + data rows of this chunk's list
+          if (k + 1 < n_chunks) rows_next = __ldg(mb + k + 1);
           if (use > 0) mbar_wait(empty + s, (use - 1) & 1u);
           unsigned char* sbase = smem + s * kStageBytes;
           const int64_t p0 = (int64_t)k * kStreamChunk;
           const uint32_t bytes = (uint32_t)((n_pts - p0 < kStreamChunk ? n_pts - p0 : kStreamChunk) * sizeof(T));
-          mstep[s] = (int)m;                                           // ordered before the copies' completion by the barrier
-          mbar_expect_tx(full + s, bytes * nc + m * kSVirt * 4);
-          if (m) bulk_g2s(sbase + kTileBytes, lists + ((size_t)b * n_chunks + k) * kStreamChunk, m * kSVirt * 4, full + s, l2_default_policy());
+          mbar_expect_tx(full + s, bytes * nc + rows * 128u);
+          bulk_g2s(sbase + kTileBytes, lists + ((size_t)b * n_chunks + k) * kListStride, rows * 128u, full + s, pol_keep);
           for (int c = 0; c < nc; ++c) bulk_g2s(sbase + c * kChanBytes, xb + (int64_t)c * sc + p0, bytes, full + s, pol);
         }
       }
     }
     return;
   }
-  // ---- consumers: thread v = virtual lane v of every chunk list, all 8 channels
+  // ---- consumers.  Warp w walks ITS portion of every chunk list (portions start at cell boundaries: the cells of two warps
+  // are disjoint within a chunk, so the warps never synchronise with each other); lane l owns a contiguous run of the
+  // portion and sums it for all 8 channels at once.  A run's segments that START inside the run are added to the
+  // accumulators directly (nobody else holds points of those cells in this chunk); the run's first segment may continue the
+  // previous lane's last one: those go through a segmented shuffle scan over the lanes (fixed tree) and are added once.
   uint32_t it = 0;
   for (int i = tid; i < kSCh * n_cells; i += kSVirt) acc[i] = 0.f;
-  bar_consumers();
+  asm volatile("bar.sync 1, %0;" ::"n"(kSVirt) : "memory");
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / n_cg, c0 = (item % n_cg) * kSCh;
     const int nc = C - c0 < kSCh ? C - c0 : kSCh;
@@ -218,14 +252,16 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
       const unsigned char* sbase = smem + s * kStageBytes;
       const T* st = reinterpret_cast<const T*>(sbase);
       const uint32_t* L = reinterpret_cast<const uint32_t*>(sbase + kTileBytes);
-      const int m = (flags & 1) ? 0 : mstep[s];
+      const uint32_t h = L[warp];
+      const int m = (flags & 1) ? 0 : (int)(h & 0xffffu);
+      const uint32_t* Lw = L + (h >> 16) * 32 + lane;
       uint32_t cur = kNone, fcell = kNone;
       float run[kSCh], fp[kSCh];
 #pragma unroll
       for (int c = 0; c < kSCh; ++c) { run[c] = 0.f; fp[c] = 0.f; }
       bool first = true;
-      auto close = [&]() {          // the run of `cur` ends: the thread's first cell goes through the shuffle tree / carries, the
-        if (cur != kNone) {         // others are cells that START inside this thread's run -> nobody else adds to them directly
+      auto close = [&]() {
+        if (cur != kNone) {
           if (first) {
 #pragma unroll
             for (int c = 0; c < kSCh; ++c) fp[c] = run[c];
@@ -240,7 +276,7 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
         }
       };
       for (int i = 0; i < m; ++i) {
-        const uint32_t e = L[i * kSVirt + tid];
+        const uint32_t e = Lw[i * 32];
         if (e != kNone) {
           const uint32_t cell = e >> kStreamPosBits, pos = e & kPosMask;
           float v[kSCh];
@@ -259,13 +295,14 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
       close();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty + s);                             // the tile is consumed: the producer may refill the stage
-      // first cells: threads with entries form a prefix and their first cells are non-decreasing; segmented inclusive scan
-      // inside the warp (fixed tree), the run that reaches lane 0 may continue the previous warp's: it goes to `carry`
       if (m > 0) {
+        // first cells of the lanes: a non-decreasing sequence over the lanes that hold entries (a prefix); inclusive
+        // segmented scan, stopped as soon as no lane has an equal first cell 2^r lanes below
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
           const uint32_t cu = __shfl_up_sync(0xffffffffu, fcell, off);
-          const bool add = lane >= (unsigned)off && cu == fcell;
+          const bool add = lane >= (unsigned)off && cu == fcell && fcell != kNone;
+          if (!__any_sync(0xffffffffu, add)) break;
 #pragma unroll
           for (int c = 0; c < kSCh; ++c) {
             const float t = __shfl_up_sync(0xffffffffu, fp[c], off);
@@ -273,31 +310,17 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
           }
         }
         const uint32_t nxt = __shfl_down_sync(0xffffffffu, fcell, 1);
-        const uint32_t head = __shfl_sync(0xffffffffu, fcell, 0);
-        if (lane == 0 && head == kNone) carry_cell[warp] = kNone;
         if (fcell != kNone && (lane == 31u || nxt != fcell)) {
-          if (warp > 0 && fcell == head) {
-            carry_cell[warp] = fcell;
+          float a[kSCh];
 #pragma unroll
-            for (int c = 0; c < kSCh; ++c) carry[warp * kSCh + c] = fp[c];
-          } else {
-            float a[kSCh];
+          for (int c = 0; c < kSCh; ++c) a[c] = acc[c * n_cells + fcell];
 #pragma unroll
-            for (int c = 0; c < kSCh; ++c) a[c] = acc[c * n_cells + fcell];
-#pragma unroll
-            for (int c = 0; c < kSCh; ++c) acc[c * n_cells + fcell] = a[c] + fp[c];
-          }
+          for (int c = 0; c < kSCh; ++c) acc[c * n_cells + fcell] = a[c] + fp[c];
         }
-        bar_consumers();
-        if (tid < kSCh) {                                                  // thread c folds channel c's carries in warp order
-#pragma unroll
-          for (int w = 1; w < kSCh; ++w) {
-            const uint32_t cc = carry_cell[w];
-            if (cc != kNone) acc[tid * n_cells + cc] += carry[w * kSCh + tid];
-          }
-        }
-        bar_consumers();
       }
+      // the portions are re-cut for every chunk, so a cell may change hands between chunks: every warp's additions of this
+      // chunk must have landed before anyone starts the next one (the only cross-warp synchronisation of the loop)
+      asm volatile("bar.sync 1, %0;" ::"n"(kSVirt) : "memory");
     }
     // the item's 8 x n_cells sums -> out (contiguous: channels c0 .. c0 + nc - 1 of frame b), accumulators back to zero
     float* o = out + ((size_t)b * C + c0) * n_cells;
@@ -306,16 +329,17 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
       if (i < n_out) o[i] = acc[i];
       acc[i] = 0.f;
     }
-    bar_consumers();
+    asm volatile("bar.sync 1, %0;" ::"n"(kSVirt) : "memory");
   }
 }
 
-template <typename T> constexpr int stages_for() { return (128 * 1024) / (kSCh * kStreamChunk * (int)sizeof(T)); }   // 128 KiB of tiles in the ring
+// ring depth: 2 x 64 KiB tiles for float32, 3 x 32 KiB for 16-bit inputs (leaves room for 8 x 2304 accumulators either way)
+template <typename T> constexpr int stages_for() { return sizeof(T) == 4 ? 2 : 3; }
 
 template <typename T>
 size_t stream_smem_bytes(int n_cells) {
-  return (size_t)stages_for<T>() * ((size_t)kSCh * kStreamChunk * sizeof(T) + (size_t)kStreamChunk * 4) + align_up16((size_t)kSCh * n_cells * 4) +
-         (size_t)kSCh * kSCh * 4 + kSCh * 4 + 32 + 2 * stages_for<T>() * 8;
+  return (size_t)stages_for<T>() * ((size_t)kSCh * kStreamChunk * sizeof(T) + (size_t)kListStride * 4) + align_up16((size_t)kSCh * n_cells * 4) +
+         2 * stages_for<T>() * 8;
 }
 
 template <typename T>
@@ -336,7 +360,7 @@ int launch_stream(const T* x, int64_t sb, int64_t sc, const uint32_t* lists, con
 
 }  // namespace
 
-size_t stream_lists_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * kStreamChunk * 4; }
+size_t stream_lists_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * kListStride * 4; }   // (the plan uses the first 2048 of every 2368)
 size_t stream_steps_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * 4; }
 
 bool pool_stream_eligible(int elem_bytes, const void* x, int64_t sb, int64_t sp, int64_t sc, int B, int64_t n_pts, int C, int n_cells) {

@@ -295,6 +295,10 @@ def test_streamed_pool_matches_float64_sums(shape, dtype, lib):
     mask = (torch.rand(B, n_pts, generator=g) < 0.27).cuda()
     _set_pool_path(lib, 3)
     try:
+        from muvo_b200 import _lib
+        with _lib.profile(_lib.current_stream(x.device)) as prof:
+            bev_pool_masked(x.detach(), cell0, mask, n_cells)
+        assert "k_pool_stream" in [k for k, _ in prof.kernels], prof.kernels     # the streamed kernel really is the one running
         for m in (mask, None):
             out = bev_pool_masked(x, cell0, m, n_cells)
             out2 = bev_pool_masked(x, cell0, m, n_cells)
