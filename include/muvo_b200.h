@@ -245,6 +245,16 @@ MUVO_API int muvo_bev_plan_build(const int32_t* cell0, int32_t B, int64_t n_pts,
 MUVO_API int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C,
                       int32_t n_cells, void* grad_x, int32_t gx_dtype, int64_t gx_stride_b, int64_t gx_stride_p,
                       int64_t gx_stride_c, void* stream);
+/* 1 when muvo_bev_pool_fwd / _fwd_masked stream a tensor of this layout (bev_stream.cu), 0 when they gather. */
+MUVO_API int muvo_bev_pool_is_streamed(int32_t elem_bytes, const void* x, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c,
+                      int32_t B, int64_t n_pts, int32_t C, int32_t n_cells);
+/* muvo_bev_pool_bwd for a gradient tensor in (B, C, D, H, W) memory: 8-channel tiles are assembled in shared memory (zeros +
+ * the kept points, found through the chunk lists the STREAMED forward left in its workspace) and written with TMA bulk stores.
+ * fwd_ws = the workspace of the matching forward call, untouched since, and only if muvo_bev_pool_is_streamed() held for that
+ * forward's x; pass NULL (or an ineligible grad_x layout) and this is muvo_bev_pool_bwd.                                 */
+MUVO_API int muvo_bev_pool_bwd_streamed(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C,
+                      int32_t n_cells, void* grad_x, int32_t gx_dtype, int64_t gx_stride_b, int64_t gx_stride_p,
+                      int64_t gx_stride_c, const void* fwd_ws, size_t fwd_ws_bytes, void* stream);
 
 /* Fused lift-splat (opt-in replacement of the two steps at muvo/models/mile.py:517-523):
  * out[b,c,cell] = sum over the kept frustum points p = (d, hw) of the cell, ascending p, of depth[b,d,hw] * feat[b,hw,c]

@@ -71,6 +71,8 @@ SIGNATURES = {
     "muvo_bev_pool_fwd_masked": (C.c_int, [_P, _I32, _I64, _I64, _I64, _P, _P, _P, _P, _I32, _I64, _I32, _I32, _P, _P, _SZ, _P]),
     "muvo_bev_plan_bytes": (C.c_int, [_I32, _I64, C.POINTER(_SZ)]),
     "muvo_bev_plan_build": (C.c_int, [_P, _I32, _I64, _I32, _P, _SZ, _P]),
+    "muvo_bev_pool_is_streamed": (C.c_int, [_I32, _P, _I64, _I64, _I64, _I32, _I64, _I32, _I32]),
+    "muvo_bev_pool_bwd_streamed": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _I32, _I64, _I64, _I64, _P, _SZ, _P]),
     "muvo_bev_pool_bwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _I32, _I64, _I64, _I64, _P]),
     "muvo_lift_splat_fwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _SZ, _P]),
     "muvo_lift_splat_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),

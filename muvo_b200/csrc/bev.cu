@@ -1223,6 +1223,28 @@ int muvo_bev_pool_bwd(const float* grad_out, const int32_t* cell, int32_t B, int
   }
 }
 
+int muvo_bev_pool_is_streamed(int32_t elem_bytes, const void* x, int64_t x_stride_b, int64_t x_stride_p, int64_t x_stride_c, int32_t B,
+                              int64_t n_pts, int32_t C, int32_t n_cells) {
+  return pool_stream_eligible(elem_bytes, x, x_stride_b, x_stride_p, x_stride_c, B, n_pts, C, n_cells) ? 1 : 0;
+}
+
+int muvo_bev_pool_bwd_streamed(const float* grad_out, const int32_t* cell, int32_t B, int64_t n_pts, int32_t C, int32_t n_cells,
+                               void* grad_x, int32_t gx_dtype, int64_t gx_stride_b, int64_t gx_stride_p, int64_t gx_stride_c,
+                               const void* fwd_ws, size_t fwd_ws_bytes, void* stream) {
+  if (B < 0 || n_pts < 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || C == 0 || n_pts == 0) return MUVO_OK;
+  if (!grad_out || !cell || !grad_x) return MUVO_E_NULL;
+  const int eb = gx_dtype == MUVO_F32 ? 4 : 2;
+  if (fwd_ws && (gx_dtype == MUVO_F32 || gx_dtype == MUVO_F16 || gx_dtype == MUVO_BF16) &&
+      pool_bwd_stream_eligible(eb, grad_x, gx_stride_b, gx_stride_p, gx_stride_c, B, n_pts, C, n_cells)) {
+    BevWs w = carve_bev(const_cast<void*>(fwd_ws), B, n_pts, n_cells);
+    if (w.bytes > fwd_ws_bytes) return MUVO_E_WORKSPACE;
+    prof_mark("<bev_bwd>", (cudaStream_t)stream);
+    return pool_stream_bwd(grad_out, w.lists, w.steps, B, n_pts, C, n_cells, grad_x, gx_dtype, gx_stride_b, gx_stride_c, (cudaStream_t)stream);
+  }
+  return muvo_bev_pool_bwd(grad_out, cell, B, n_pts, C, n_cells, grad_x, gx_dtype, gx_stride_b, gx_stride_p, gx_stride_c, stream);
+}
+
 int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t* cell, int32_t B, int32_t D, int32_t HW,
                         int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream) {
   if (B < 0 || D <= 0 || HW <= 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;

@@ -37,6 +37,10 @@ template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // ---------------------------------------------------------------- L: per-chunk sorted lists
 // Layout of one chunk's list (kListStride u32 = 74 rows of 32): row 0 is a header, word w < 8 = (first row << 16 | rows) of
@@ -333,6 +337,84 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
   }
 }
 
+// ---------------------------------------------------------------- B: streamed backward
+// grad_x[b, p, c] = kept(p) ? grad_out[b, c, cell(p)] : 0 for (B, C, D, H, W) gradient memory: every element is written
+// once, 79 % of them zeros.  The gather kernel of bev.cu spends 176 M warp instructions on address arithmetic and predicated
+// loads for 1.42 GB of stores (ncu round 1: 288 us, issue-active 55 %).  Here one CTA per (frame, 8 channels) keeps its 8
+// grad_out rows in shared memory, builds [8 channels x 2048 points] tiles there -- zero fill with 128-bit stores, then the
+// kept points scattered from the forward pass's chunk lists -- and hands every tile to the TMA (cp.async.bulk shared ->
+// global, 8 KiB per channel row); two tiles alternate, a tile is reused once its bulk group has finished reading it.
+constexpr int kBThreads = 256;
+template <typename T>
+__global__ void __launch_bounds__(kBThreads, 1)
+k_pool_bwd_stream(const float* __restrict__ gout, const uint32_t* __restrict__ lists, const uint32_t* __restrict__ steps, int B,
+                  int64_t n_pts, int C, int n_cells, int n_chunks, T* __restrict__ gx, int64_t sb, int64_t sc) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr size_t kChanBytes = (size_t)kStreamChunk * sizeof(T);
+  constexpr size_t kTileBytes = kChanBytes * kSCh;
+  constexpr size_t kListBytes = (size_t)kListStride * 4;
+  // [2 tiles] [2 list buffers] [grad_out rows: 8 x n_cells floats] [2 mbarriers]
+  unsigned char* tiles = smem;
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(smem + 2 * kTileBytes);
+  float* g_s = reinterpret_cast<float*>(smem + 2 * kTileBytes + 2 * kListBytes);
+  uint64_t* lfull = reinterpret_cast<uint64_t*>(smem + 2 * kTileBytes + 2 * kListBytes + align_up16((size_t)kSCh * n_cells * 4));
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(lfull, 1); mbar_init(lfull + 1, 1); mbar_fence_init(); }
+  __syncthreads();
+  const int n_cg = (C + kSCh - 1) / kSCh;
+  const int items = B * n_cg;
+  const uint64_t pol_keep = l2_default_policy(), pol_stream = l2_evict_first_policy();
+  uint32_t it = 0;                                               // chunks processed by this CTA so far (list barrier phases)
+  auto request_list = [&](int b, int k, int buf) {               // thread 0 only
+    const uint32_t rows = __ldg(steps + (size_t)b * n_chunks + k);
+    mbar_expect_tx(lfull + buf, rows * 128u);
+    bulk_g2s(lbuf + (size_t)buf * kListStride, lists + ((size_t)b * n_chunks + k) * kListStride, rows * 128u, lfull + buf, pol_keep);
+  };
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / n_cg, c0 = (item % n_cg) * kSCh;
+    const int nc = C - c0 < kSCh ? C - c0 : kSCh;
+    __syncthreads();                                             // previous item's scatters have read g_s
+    for (int i = tid; i < kSCh * n_cells; i += kBThreads) {
+      const int c = i / n_cells;
+      g_s[i] = c < nc ? __ldg(gout + ((size_t)b * C + c0) * n_cells + i) : 0.f;
+    }
+    if (tid == 0) { request_list(b, 0, (int)(it & 1u)); if (n_chunks > 1) request_list(b, 1, (int)((it + 1) & 1u)); }
+    T* gxb = gx + (int64_t)b * sb + (int64_t)c0 * sc;
+    for (int k = 0; k < n_chunks; ++k, ++it) {
+      const int s = (int)(it & 1u);
+      unsigned char* tile = tiles + s * kTileBytes;
+      if (tid == 0) bulk_wait_read<1>();                         // the store that used this tile two chunks ago has read it
+      __syncthreads();
+      {                                                          // zero fill, 16 bytes per store
+        uint4* t4 = reinterpret_cast<uint4*>(tile);
+        for (int i = tid; i < (int)(kTileBytes / 16); i += kBThreads) t4[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      mbar_wait(lfull + s, (it >> 1) & 1u);
+      __syncthreads();
+      const uint32_t* L = lbuf + (size_t)s * kListStride;
+      const int n_ent = ((int)L[kSCh] - 1) * 32;                 // data rows x 32 (padding entries = kNone)
+      T* tt = reinterpret_cast<T*>(tile);
+      for (int i = tid; i < n_ent; i += kBThreads) {
+        const uint32_t e = L[32 + i];
+        if (e == kNone) continue;
+        const uint32_t cell = e >> kStreamPosBits, pos = e & kPosMask;
+#pragma unroll
+        for (int c = 0; c < kSCh; ++c) tt[c * kStreamChunk + pos] = from_f32<T>(g_s[c * n_cells + cell]);
+      }
+      fence_proxy_async();                                       // generic-proxy writes of the tile -> visible to the bulk copy
+      __syncthreads();
+      if (tid == 0) {
+        const int64_t p0 = (int64_t)k * kStreamChunk;
+        const uint32_t bytes = (uint32_t)((n_pts - p0 < kStreamChunk ? n_pts - p0 : kStreamChunk) * sizeof(T));
+        for (int c = 0; c < nc; ++c) bulk_s2g(gxb + (int64_t)c * sc + p0, tile + c * kChanBytes, bytes, pol_stream);
+        bulk_commit();
+        if (k + 2 < n_chunks) request_list(b, k + 2, s);          // everybody is past this list buffer
+      }
+    }
+  }
+  if (tid == 0) bulk_wait_all<0>();                              // shared memory must outlive the last bulk reads
+}
+
 // ring depth: 2 x 64 KiB tiles for float32, 3 x 32 KiB for 16-bit inputs (leaves room for 8 x 2304 accumulators either way)
 template <typename T> constexpr int stages_for() { return sizeof(T) == 4 ? 2 : 3; }
 
@@ -358,7 +440,44 @@ int launch_stream(const T* x, int64_t sb, int64_t sc, const uint32_t* lists, con
   return MUVO_OK;
 }
 
+template <typename T>
+size_t bwd_stream_smem_bytes(int n_cells) {
+  return 2 * (size_t)kSCh * kStreamChunk * sizeof(T) + 2 * (size_t)kListStride * 4 + align_up16((size_t)kSCh * n_cells * 4) + 16;
+}
+
+template <typename T>
+int launch_bwd_stream(const float* gout, const uint32_t* lists, const uint32_t* steps, int B, int64_t n_pts, int C, int n_cells,
+                      T* gx, int64_t sb, int64_t sc, cudaStream_t st) {
+  const size_t smem = bwd_stream_smem_bytes<T>(n_cells);
+  cudaError_t e = cudaFuncSetAttribute(k_pool_bwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int sms = kNumSMsB200;
+  { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int items = B * ((C + kSCh - 1) / kSCh);
+  const int n_chunks = (int)ceil_div64(n_pts, kStreamChunk);
+  k_pool_bwd_stream<T><<<(unsigned)(items < sms ? items : sms), kBThreads, smem, st>>>(gout, lists, steps, B, n_pts, C, n_cells, n_chunks,
+                                                                                     gx, sb, sc);
+  MUVO_AFTER_LAUNCH("k_pool_bwd_stream", st);
+  return MUVO_OK;
+}
+
 }  // namespace
+
+bool pool_bwd_stream_eligible(int elem_bytes, const void* gx, int64_t sb, int64_t sp, int64_t sc, int B, int64_t n_pts, int C, int n_cells) {
+  if (!pool_stream_eligible(elem_bytes, gx, sb, sp, sc, B, n_pts, C, n_cells)) return false;
+  const size_t smem = elem_bytes == 4 ? bwd_stream_smem_bytes<float>(n_cells) : bwd_stream_smem_bytes<__half>(n_cells);
+  return smem <= 227 * 1024;
+}
+
+int pool_stream_bwd(const float* gout, const uint32_t* lists, const uint32_t* steps, int B, int64_t n_pts, int C, int n_cells, void* gx,
+                    int32_t gx_dtype, int64_t sb, int64_t sc, cudaStream_t st) {
+  switch (gx_dtype) {
+    case MUVO_F32:  return launch_bwd_stream<float>(gout, lists, steps, B, n_pts, C, n_cells, (float*)gx, sb, sc, st);
+    case MUVO_F16:  return launch_bwd_stream<__half>(gout, lists, steps, B, n_pts, C, n_cells, (__half*)gx, sb, sc, st);
+    case MUVO_BF16: return launch_bwd_stream<__nv_bfloat16>(gout, lists, steps, B, n_pts, C, n_cells, (__nv_bfloat16*)gx, sb, sc, st);
+    default: return MUVO_E_ARG;
+  }
+}
 
 size_t stream_lists_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * kListStride * 4; }   // (the plan uses the first 2048 of every 2368)
 size_t stream_steps_bytes(int B, int64_t n_pts) { return (size_t)B * (size_t)ceil_div64(n_pts, kStreamChunk) * 4; }

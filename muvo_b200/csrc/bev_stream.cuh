@@ -27,4 +27,10 @@ int pool_stream_fwd(const void* x, int32_t x_dtype, int64_t sb, int64_t sc, cons
                     int32_t* cell_out, const uint32_t* plan, const uint32_t* plan_n, int B, int64_t n_pts, int C, int n_cells,
                     float* out, uint32_t* lists, uint32_t* steps, cudaStream_t st);
 
+// Streamed backward (same layout conditions, applied to the gradient tensor): `lists` / `steps` are the ones the streamed
+// forward left in its workspace for the same (cell0, mask)
+bool pool_bwd_stream_eligible(int elem_bytes, const void* gx, int64_t sb, int64_t sp, int64_t sc, int B, int64_t n_pts, int C, int n_cells);
+int pool_stream_bwd(const float* gout, const uint32_t* lists, const uint32_t* steps, int B, int64_t n_pts, int C, int n_cells, void* gx,
+                    int32_t gx_dtype, int64_t sb, int64_t sc, cudaStream_t st);
+
 }  // namespace muvo

@@ -100,6 +100,7 @@ class _BevPool(torch.autograd.Function):
         _lib.check(rc, "muvo_bev_pool_fwd")
         ctx.save_for_backward(cell)
         ctx.meta = (tuple(x.shape), x.dtype, n_cells, x.stride())
+        ctx.fwd_ws = ws if lib.muvo_bev_pool_is_streamed(xv.element_size(), _lib.ptr(xv), sb, sp, sc, B, n_pts, Cc, n_cells) else None
         ctx.mark_non_differentiable(cell)
         return out
 
@@ -107,7 +108,7 @@ class _BevPool(torch.autograd.Function):
     def backward(ctx, grad_out):
         (cell,) = ctx.saved_tensors
         shape, dtype, n_cells, xstride = ctx.meta
-        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None
+        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride, ctx.fwd_ws), None, None
 
 
 class _BevPoolMasked(torch.autograd.Function):
@@ -144,13 +145,14 @@ class _BevPoolMasked(torch.autograd.Function):
         _lib.check(rc, "muvo_bev_pool_fwd_masked")
         ctx.save_for_backward(cell)
         ctx.meta = (tuple(x.shape), x.dtype, n_cells, x.stride())
+        ctx.fwd_ws = ws if lib.muvo_bev_pool_is_streamed(xv.element_size(), _lib.ptr(xv), sb, sp, sc, B, n_pts, Cc, n_cells) else None
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         (cell,) = ctx.saved_tensors
         shape, dtype, n_cells, xstride = ctx.meta
-        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride), None, None, None, None
+        return bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride, ctx.fwd_ws), None, None, None, None
 
 
 def build_plan(cell0: torch.Tensor, n_cells: int) -> torch.Tensor:
@@ -169,7 +171,7 @@ def build_plan(cell0: torch.Tensor, n_cells: int) -> torch.Tensor:
     return plan
 
 
-def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
+def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None, fwd_ws=None):
     """``grad_x[b,p,c] = cell[b,p] >= 0 ? grad_out[b,c,cell[b,p]] : 0`` (frustum_pooling.py:52-60 + index backward).
 
     The gradient is written in the producer's memory format: if x was a permuted ``(B,C,D,H,W)`` view
@@ -186,9 +188,13 @@ def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None):
         gx = torch.empty(shape, dtype=dtype, device=dev)
     gv, sb, sp, sc, _ = _strides_bpc(gx)
     with torch.cuda.device(dev):
-        rc = _lib.load().muvo_bev_pool_bwd(go.data_ptr(), _lib.ptr(cell), B, n_pts, Cc, n_cells, gv.data_ptr(),
-                                           _FLOAT_DTYPES[dtype], sb, sp, sc, _lib.current_stream(dev))
-    _lib.check(rc, "muvo_bev_pool_bwd")
+        # fwd_ws: the workspace of a STREAMED forward (its per-chunk cell lists are reused: tiles built in shared memory,
+        # written with TMA bulk stores); otherwise the gather kernel
+        rc = _lib.load().muvo_bev_pool_bwd_streamed(go.data_ptr(), _lib.ptr(cell), B, n_pts, Cc, n_cells, gv.data_ptr(),
+                                                    _FLOAT_DTYPES[dtype], sb, sp, sc,
+                                                    fwd_ws.data_ptr() if fwd_ws is not None else None,
+                                                    fwd_ws.numel() if fwd_ws is not None else 0, _lib.current_stream(dev))
+    _lib.check(rc, "muvo_bev_pool_bwd_streamed")
     return gx
 
 

@@ -315,7 +315,12 @@ def test_streamed_pool_matches_float64_sums(shape, dtype, lib):
             assert torch.all((out.cpu().double() - want.permute(0, 2, 1)).abs() <= TOL * mag.permute(0, 2, 1) + 1e-30)
             assert torch.count_nonzero(out.cpu()[mag.permute(0, 2, 1) == 0]) == 0            # empty cells are exact zeros
             gout = torch.randn(out.shape, generator=g).cuda()
-            (gx,) = torch.autograd.grad(out, x, gout)
+            with _lib.profile(_lib.current_stream(x.device)) as prof:
+                gx_here = out.grad_fn.apply(gout)[0] # the node run on THIS thread (the profile is per host thread; autograd's
+            assert "k_pool_bwd_stream" in [k for k, _ in prof.kernels], prof.kernels        # engine uses its own): TMA-store backward
+            (gx,) = torch.autograd.grad(out, x, gout, retain_graph=True)
+            (gx2,) = torch.autograd.grad(out, x, gout)
+            assert torch.equal(gx, gx2) and torch.equal(gx, gx_here)
             exp = torch.zeros(B, n_pts, C)
             for b in range(B):
                 keep = cc[b] >= 0
