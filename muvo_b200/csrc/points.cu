@@ -458,6 +458,18 @@ k_points_tile(const T* __restrict__ xyz, const uint8_t* __restrict__ sem, const 
 #pragma unroll
         for (int k = 0; k < kKPL; ++k) {
           vold[k] = 1ull; pold[k] = 0ull;
+#ifdef MUVO_TIMING_KNOBS
+          // timing experiments only (results are WRONG): flags bit 1 = no table atomics at all, bit 2 = red.max (no return value)
+          if (flags & 6) {
+            if (flags & 4) {
+              if (DO_VOX && vbit[k] != 0xffffffffu) asm volatile("red.global.max.u64 [%0], %1;" ::"l"(vtab_f + vbit[k]), "l"(vword[k]) : "memory");
+              if (DO_RANGE && ppix[k] != 0xffffffffu) asm volatile("red.global.max.u64 [%0], %1;" ::"l"(pixtab_f + ppix[k]), "l"(pword[k]) : "memory");
+            }
+            n_drop += (unsigned)((vword[k] ^ pword[k] ^ vbit[k] ^ ppix[k]) == 0x123456789abcdefull);
+            vold[k] = 1ull; pold[k] = 0ull;
+            continue;
+          }
+#endif
           if (DO_VOX && vbit[k] != 0xffffffffu) vold[k] = atom_max_global(vtab_f + vbit[k], vword[k]);
           if (DO_RANGE && ppix[k] != 0xffffffffu) pold[k] = atom_max_global(pixtab_f + ppix[k], pword[k]);
         }
@@ -957,7 +969,10 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   const bool need_scan = do_vox && (sparse != nullptr || dense == nullptr);
   const bool dense_fast = do_vox && !need_scan;                  // dense-order bitmap, dense grid (and n_occ) from k_emit_dense
   int64_t* n_occ_emit = dense_fast ? n_occ : nullptr;
-  const int flags = (g_tuning[1] & 1) ? 0 : 1;                   // bit 0: neighbour filter before the voxel atomicMax
+  int flags = (g_tuning[1] & 1) ? 0 : 1;                         // bit 0: neighbour filter before the voxel atomicMax
+#ifdef MUVO_TIMING_KNOBS
+  flags |= g_tuning[1] & 6;
+#endif
   int sms = kNumSMsB200;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
 
