@@ -437,6 +437,16 @@ __device__ __forceinline__ u64 atom_max_global(u64* p, u64 v) {
   asm volatile("atom.global.max.u64 %0, [%1], %2;" : "=l"(old) : "l"(p), "l"(v) : "memory");
   return old;
 }
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ u64 atom_max_global_hint(u64* p, u64 v, uint64_t pol) {
+  u64 old;
+  asm volatile("atom.global.max.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(v), "l"(pol) : "memory");
+  return old;
+}
 __device__ __forceinline__ void red_or_global(uint32_t* p, uint32_t v) {
   asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

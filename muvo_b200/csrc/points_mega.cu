@@ -145,11 +145,7 @@ __device__ __forceinline__ void stat_add(int slot, long long dt) {
 
 // The winner tables (a ring of frame slots, re-used every R frames) are accessed with an L2 evict_last policy, the output
 // streams with evict_first (st.global.cs): the tables stay resident while 0.3 GB of results per step flow past them.
-__device__ __forceinline__ uint64_t l2_evict_last_policy() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
+// (l2_evict_last_policy: points_dev.cuh)
 // atomicMax on table[cell] unless cell == kCellNone (0xffffffff); returns the old word, or `none` when nothing was done.
 // Predicated instead of branched: no divergence bookkeeping around the (very common) claim.
 __device__ __forceinline__ u64 atom_max_if(u64* table, uint32_t cell, u64 word, u64 none, uint64_t pol) {

@@ -22,15 +22,22 @@ ap.add_argument("--set", default="", help="other knobs, e.g. 0=3,1=0")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 lib = _lib.load()
-pts, sem, off = synth.lidar_batch(a.frames, a.nmin, a.nmax, 2000)
-tp, ts, to = torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev), torch.from_numpy(off).to(dev)
+ap_alt = int(os.environ.get("MUVO_SWEEP_ALT", "1"))       # > 1: rotate over that many DIFFERENT batches (no table sector is reused step to step)
+batches = []
+for b in range(ap_alt):
+    pts, sem, off = synth.lidar_batch(a.frames, a.nmin, a.nmax, 2000 + 7919 * b)
+    batches.append((torch.from_numpy(pts).to(dev), torch.from_numpy(sem).to(dev), torch.from_numpy(off).to(dev)))
+tp, ts, to = batches[0]
+step_no = 0
 remap = torch.from_numpy(synth.label_remap256()).to(dev)
 stream = _lib.current_stream(dev)
 out = {}
 
 
 def step():
-    global out
+    global out, step_no, tp, ts, to
+    tp, ts, to = batches[step_no % len(batches)]
+    step_no += 1
     r = sensor_to_grid(tp, ts, to, grid=GridSpec(), range_spec=RangeSpec(lidar_position=(1.0, 0.0, 2.0)), remap=remap,
                        layout="xyzd", out=out)
     out = {k: r[k] for k in ("voxel", "n_occ", "range_xyzd", "range_sem")}
