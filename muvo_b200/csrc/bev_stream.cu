@@ -344,24 +344,28 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
 // grad_out rows in shared memory, builds [8 channels x 2048 points] tiles there -- zero fill with 128-bit stores, then the
 // kept points scattered from the forward pass's chunk lists -- and hands every tile to the TMA (cp.async.bulk shared ->
 // global, 8 KiB per channel row); two tiles alternate, a tile is reused once its bulk group has finished reading it.
+// 16-bit gradients take 16 channels per CTA (the same 64 KiB tiles as float32 with 8): the per-chunk costs -- zero fill, list wait,
+// three barriers -- are per tile, so halving the tiles per byte took the fp16 backward from 0.21 to the float32 rate.  The
+// grad_out rows are kept already converted to T (one conversion per (channel, cell) instead of one per point).
 constexpr int kBThreads = 256;
-template <typename T>
+template <typename T> constexpr int bwd_channels() { return sizeof(T) == 4 ? kSCh : 2 * kSCh; }
+template <typename T, int CH>
 __global__ void __launch_bounds__(kBThreads, 1)
 k_pool_bwd_stream(const float* __restrict__ gout, const uint32_t* __restrict__ lists, const uint32_t* __restrict__ steps, int B,
                   int64_t n_pts, int C, int n_cells, int n_chunks, T* __restrict__ gx, int64_t sb, int64_t sc) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr size_t kChanBytes = (size_t)kStreamChunk * sizeof(T);
-  constexpr size_t kTileBytes = kChanBytes * kSCh;
+  constexpr size_t kTileBytes = kChanBytes * CH;
   constexpr size_t kListBytes = (size_t)kListStride * 4;
-  // [2 tiles] [2 list buffers] [grad_out rows: 8 x n_cells floats] [2 mbarriers]
+  // [2 tiles] [2 list buffers] [grad_out rows: CH x n_cells, as T] [2 mbarriers]
   unsigned char* tiles = smem;
   uint32_t* lbuf = reinterpret_cast<uint32_t*>(smem + 2 * kTileBytes);
-  float* g_s = reinterpret_cast<float*>(smem + 2 * kTileBytes + 2 * kListBytes);
-  uint64_t* lfull = reinterpret_cast<uint64_t*>(smem + 2 * kTileBytes + 2 * kListBytes + align_up16((size_t)kSCh * n_cells * 4));
+  T* g_s = reinterpret_cast<T*>(smem + 2 * kTileBytes + 2 * kListBytes);
+  uint64_t* lfull = reinterpret_cast<uint64_t*>(smem + 2 * kTileBytes + 2 * kListBytes + align_up16((size_t)CH * n_cells * sizeof(T)));
   const int tid = threadIdx.x;
   if (tid == 0) { mbar_init(lfull, 1); mbar_init(lfull + 1, 1); mbar_fence_init(); }
   __syncthreads();
-  const int n_cg = (C + kSCh - 1) / kSCh;
+  const int n_cg = (C + CH - 1) / CH;
   const int items = B * n_cg;
   const uint64_t pol_keep = l2_default_policy(), pol_stream = l2_evict_first_policy();
   uint32_t it = 0;                                               // chunks processed by this CTA so far (list barrier phases)
@@ -371,12 +375,12 @@ k_pool_bwd_stream(const float* __restrict__ gout, const uint32_t* __restrict__ l
     bulk_g2s(lbuf + (size_t)buf * kListStride, lists + ((size_t)b * n_chunks + k) * kListStride, rows * 128u, lfull + buf, pol_keep);
   };
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int b = item / n_cg, c0 = (item % n_cg) * kSCh;
-    const int nc = C - c0 < kSCh ? C - c0 : kSCh;
+    const int b = item / n_cg, c0 = (item % n_cg) * CH;
+    const int nc = C - c0 < CH ? C - c0 : CH;
     __syncthreads();                                             // previous item's scatters have read g_s
-    for (int i = tid; i < kSCh * n_cells; i += kBThreads) {
+    for (int i = tid; i < CH * n_cells; i += kBThreads) {
       const int c = i / n_cells;
-      g_s[i] = c < nc ? __ldg(gout + ((size_t)b * C + c0) * n_cells + i) : 0.f;
+      g_s[i] = from_f32<T>(c < nc ? __ldg(gout + ((size_t)b * C + c0) * n_cells + i) : 0.f);
     }
     if (tid == 0) { request_list(b, 0, (int)(it & 1u)); if (n_chunks > 1) request_list(b, 1, (int)((it + 1) & 1u)); }
     T* gxb = gx + (int64_t)b * sb + (int64_t)c0 * sc;
@@ -399,7 +403,7 @@ k_pool_bwd_stream(const float* __restrict__ gout, const uint32_t* __restrict__ l
         if (e == kNone) continue;
         const uint32_t cell = e >> kStreamPosBits, pos = e & kPosMask;
 #pragma unroll
-        for (int c = 0; c < kSCh; ++c) tt[c * kStreamChunk + pos] = from_f32<T>(g_s[c * n_cells + cell]);
+        for (int c = 0; c < CH; ++c) tt[c * kStreamChunk + pos] = g_s[c * n_cells + cell];
       }
       fence_proxy_async();                                       // generic-proxy writes of the tile -> visible to the bulk copy
       __syncthreads();
@@ -442,20 +446,22 @@ int launch_stream(const T* x, int64_t sb, int64_t sc, const uint32_t* lists, con
 
 template <typename T>
 size_t bwd_stream_smem_bytes(int n_cells) {
-  return 2 * (size_t)kSCh * kStreamChunk * sizeof(T) + 2 * (size_t)kListStride * 4 + align_up16((size_t)kSCh * n_cells * 4) + 16;
+  constexpr int CH = bwd_channels<T>();
+  return 2 * (size_t)CH * kStreamChunk * sizeof(T) + 2 * (size_t)kListStride * 4 + align_up16((size_t)CH * n_cells * sizeof(T)) + 16;
 }
 
 template <typename T>
 int launch_bwd_stream(const float* gout, const uint32_t* lists, const uint32_t* steps, int B, int64_t n_pts, int C, int n_cells,
                       T* gx, int64_t sb, int64_t sc, cudaStream_t st) {
   const size_t smem = bwd_stream_smem_bytes<T>(n_cells);
-  cudaError_t e = cudaFuncSetAttribute(k_pool_bwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  constexpr int CH = bwd_channels<T>();
+  cudaError_t e = cudaFuncSetAttribute(k_pool_bwd_stream<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   int sms = kNumSMsB200;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  const int items = B * ((C + kSCh - 1) / kSCh);
+  const int items = B * ((C + CH - 1) / CH);
   const int n_chunks = (int)ceil_div64(n_pts, kStreamChunk);
-  k_pool_bwd_stream<T><<<(unsigned)(items < sms ? items : sms), kBThreads, smem, st>>>(gout, lists, steps, B, n_pts, C, n_cells, n_chunks,
+  k_pool_bwd_stream<T, CH><<<(unsigned)(items < sms ? items : sms), kBThreads, smem, st>>>(gout, lists, steps, B, n_pts, C, n_cells, n_chunks,
                                                                                      gx, sb, sc);
   MUVO_AFTER_LAUNCH("k_pool_bwd_stream", st);
   return MUVO_OK;
