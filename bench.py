@@ -708,10 +708,14 @@ def other_stages(device, rank, world, hbm_peak, args):
         ms_e = timed(ssc_epoch, max(2, steps // 2)) / 32
         bytes_d = tp.numel() * 9
         key = "ssc_counts" if Cn == 2 else "ssc_counts_c9"
-        res[key] = {"ms": ms_d, "kernel_only_ms": ms_k, "algorithmic_GBps": bytes_d / ms_d / 1e6, "frac": bytes_d / ms_d / 1e6 / hbm_peak,
+        # headline = the mode the trainer's call pattern needs (add_batch per validation step, statistics read at epoch end,
+        # trainer.py:483-490 / 515-567): SSCMetrics(sync_dist="epoch"), one all-reduce per epoch; the per-batch all-reduce
+        # (sync_dist=True: every rank's running statistics global after EVERY batch) is reported beside it
+        res[key] = {"ms": ms_e, "kernel_only_ms": ms_k, "algorithmic_GBps": bytes_d / ms_e / 1e6, "frac": bytes_d / ms_e / 1e6 / hbm_peak,
                     "kernel_only_frac": bytes_d / ms_k / 1e6 / hbm_peak, "n_classes": Cn,
-                    "epoch_sync_ms_per_batch": ms_e, "epoch_sync_frac": bytes_d / ms_e / 1e6 / hbm_peak,
-                    "voxels_per_s": tp.numel() * world / (ms_d * 1e-3), "frames_per_rank": 16,
+                    "mode": "SSCMetrics(sync_dist='epoch').add_batch per batch, 32 batches + one flush (all-reduce + read-back)",
+                    "per_batch_allreduce_ms": ms_d, "per_batch_allreduce_frac": bytes_d / ms_d / 1e6 / hbm_peak,
+                    "voxels_per_s": tp.numel() * world / (ms_e * 1e-3), "frames_per_rank": 16,
                     "allreduce": f"nccl int64[{3 + 3 * Cn}]" if world > 1 else "none (1 rank)"}
         if rank == 0:
             import oracle as O                                     # the checker, not the thing measured

@@ -657,3 +657,30 @@ def test_batched_voxelisation_equals_frame_by_frame(lib):
         want = voxelize_frame(*f, cfg)
         assert g.dtype == np.uint16 and np.array_equal(g, want)
     assert voxelize_frames([], cfg) == []
+
+
+def test_opt_in_dataflow_kernel_equals_default_path(lib):
+    """The single-launch dataflow kernel (points_mega.cu, opt-in with tuning key 3 = 2: measured slower than the multi-launch
+    path) produces the same grids / range views as the default path, repeatedly on a reused workspace,
+    in scan order and with shuffled points (every pixel / voxel contested out of order)."""
+    from muvo_b200 import _lib
+    remap = torch.from_numpy(synth.label_remap256())
+    for seed, F, shuffle in ((2700, 5, False), (2710, 3, True), (2700, 5, False)):
+        pts, sem, off = _batch(F, 4000, 12000, seed)
+        if shuffle:
+            rng = np.random.default_rng(seed)
+            for f in range(F):
+                perm = rng.permutation(off[f + 1] - off[f]) + off[f]
+                pts[off[f]:off[f + 1]], sem[off[f]:off[f + 1]] = pts[perm], sem[perm]
+        tp, ts = torch.from_numpy(pts).to(dev()), torch.from_numpy(sem).to(dev())
+        kw = dict(grid=GridSpec(), range_spec=RangeSpec(lidar_position=tuple(LIDAR)), remap=remap, layout="xyzd")
+        want = sensor_to_grid(tp, ts, off, **kw)
+        assert lib.muvo_debug_set_tuning(3, 2) == 0
+        try:
+            with _lib.profile(_lib.current_stream(tp.device)) as prof:
+                got = sensor_to_grid(tp, ts, off, **kw)
+        finally:
+            assert lib.muvo_debug_set_tuning(3, 0) == 0
+        assert "k_points_tile" not in [k for k, _ in prof.kernels], prof.kernels      # it really was the other kernel
+        for k in ("voxel", "n_occ", "range_xyzd", "range_sem"):
+            assert torch.equal(got[k], want[k]), k
