@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define MUVO_B200_ABI_VERSION 4
+#define MUVO_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MUVO_API __attribute__((visibility("default")))

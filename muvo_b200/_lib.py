@@ -12,7 +12,7 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmuvo_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 # dtype codes (include/muvo_b200.h)
 F32, F64, F16, BF16 = 0, 1, 2, 3
 I64, I32, U8, I16 = 0, 1, 2, 3
