@@ -342,7 +342,9 @@ __device__ __forceinline__ void queue_role(int cta, const QueueArgs<T>& a, const
 template <typename T>
 __global__ void __cluster_dims__(kScanCluster, 1, 1) __launch_bounds__(kScanThreads)
 k_scan_queue(const uint32_t* __restrict__ bitmap, uint32_t* __restrict__ prefix, int gw, int n_scan_frames,
-             int64_t* __restrict__ n_occ_out, QueueArgs<T> qa, GridDev g, RangeDev r) {
+             int64_t* __restrict__ n_occ_out, const __grid_constant__ QueueArgs<T> qa, const __grid_constant__ GridDev g,
+             const __grid_constant__ RangeDev r) {   // (by-value structs whose address is taken were copied to local memory:
+                                                     //  408 bytes of stores per thread before the first useful instruction)
   pdl_wait();
   pdl_launch();
   const int scan_ctas = n_scan_frames * kScanCluster;
