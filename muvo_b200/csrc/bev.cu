@@ -1034,17 +1034,19 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
                                                              w.chunk_kept, w.kp, w.dest, w.dest16);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
-  if (sp == 1) {
-    const size_t rsmem = (size_t)kRowCap * sizeof(float) + (size_t)n_cells * 2 + 16;
-    if (n_cells > 65535 || rsmem > 227 * 1024) return MUVO_E_SHAPE;
-    if (g_tuning[2] == 1 || n_pts % 2 != 0) {        // tuning key 2 = 1: the one-CTA-per-row gather kernel (also: odd row stride)
+  // (B, C, D, H, W) memory: the pipelined row kernel while its cell tables fit next to the staging buffer (<= 3242 cells), the
+  // one-CTA-per-row kernel up to 9720 cells, above that (and for every other layout) the kernel that walks cells
+  const size_t rsmem = (size_t)kRowCap * sizeof(float) + (size_t)n_cells * 2 + 16;
+  const size_t psmem = (size_t)kRowCap * sizeof(float) + (size_t)((n_cells + 1) / 2 + 1) * 4 + (size_t)(n_cells + 1) * 4;
+  const bool rows_ok = n_cells <= 65535 && rsmem <= 227 * 1024;
+  const bool pipe_ok = rows_ok && psmem <= 227 * 1024 && g_tuning[2] != 1 && n_pts % 2 == 0;
+  if (sp == 1 && rows_ok) {
+    if (!pipe_ok) {        // tuning key 2 = 1: the one-CTA-per-row gather kernel (also: odd row stride, 3243..9720 cells)
       cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
       if (e != cudaSuccess) return (int)e;
       k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.kp, w.dest, w.cell_start, w.sorted, B, n_pts,
                                                                            C, n_cells, out);
     } else {
-      const size_t psmem = (size_t)kRowCap * sizeof(float) + (size_t)((n_cells + 1) / 2 + 1) * 4 + (size_t)(n_cells + 1) * 4;
-      if (psmem > 227 * 1024) return MUVO_E_SHAPE;
       cudaError_t e = cudaFuncSetAttribute(k_pool_rows_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
       if (e != cudaSuccess) return (int)e;
       int sms = kNumSMsB200;
@@ -1057,7 +1059,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
     k_pool_channel_major<T><<<(unsigned)((int64_t)B * n_cells), 128, 0, st>>>(x, sb, sp, sc, w.cell_start, w.sorted, B, n_pts,
                                                                              C, n_cells, out);
   }
-  MUVO_AFTER_LAUNCH(sp == 1 ? "k_pool_rows" : "k_pool_channel_major", st);
+  MUVO_AFTER_LAUNCH(sp == 1 && rows_ok ? "k_pool_rows" : "k_pool_channel_major", st);
   return MUVO_OK;
 }
 

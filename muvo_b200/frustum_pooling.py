@@ -200,24 +200,44 @@ def bev_pool_backward(grad_out, cell, shape, dtype, n_cells, xstride=None, fwd_w
 
 def bev_pool(x: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
     """``x (B,N,D,H,W,C)`` any strides, ``cell (B, N*D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
-    _check_cells(n_cells)
-    return _BevPool.apply(x, cell, int(n_cells))
+    n_cells = int(n_cells)
+    if n_cells > max_cells_per_pass():
+        return _pool_in_windows(x, cell, n_cells)
+    return _BevPool.apply(x, cell, n_cells)
 
 
-def _check_cells(n_cells):
-    limit = _lib.load().muvo_bev_pool_max_cells()
-    if int(n_cells) > limit:
-        raise ValueError(f"muvo_b200 BEV pooling supports at most {limit} BEV cells (nx*ny*nz), got {n_cells}: the index sort "
-                         "keeps one histogram per warp in shared memory.  MUVO's shipped configs use 48*48*1 = 2304; see "
-                         "INTEGRATION.md (limits).")
+def max_cells_per_pass() -> int:
+    """Cells one library call handles (the index sort keeps one histogram per warp in shared memory: 12 800).  MUVO's
+    shipped configs use 48*48*1 = 2304; bigger grids (BEV.SIZE 192x192 at FEATURE_DOWNSAMPLE 1, nz > 1, ...) are pooled in
+    windows of that many cells, see ``_pool_in_windows``."""
+    return int(_lib.load().muvo_bev_pool_max_cells())
+
+
+def _pool_in_windows(x, cell, n_cells):
+    """Grids above ``max_cells_per_pass()``: the cell axis is cut into windows [w0, w1) and every window is pooled by its own
+    library call on ``cell - w0`` (points of other windows dropped), i.e. the same kernels, the same per-cell summation order and
+    the same gradients (autograd sums the windows' disjoint contributions to grad_x); the cell ids are re-based with three torch
+    elementwise ops per window.  The reference handles any grid (frustum_pooling.py:131-187); so does this."""
+    step = max_cells_per_pass()
+    B = x.shape[0]
+    cell = cell.reshape(B, -1)
+    outs = []
+    for w0 in range(0, n_cells, step):
+        w1 = min(w0 + step, n_cells)
+        cw = torch.where((cell >= w0) & (cell < w1), cell - w0, torch.full_like(cell, -1))
+        outs.append(_BevPool.apply(x, cw, w1 - w0))
+    return torch.cat(outs, dim=2)
 
 
 def bev_pool_masked(x: torch.Tensor, cell0: torch.Tensor, mask, n_cells: int, plan=None) -> torch.Tensor:
     """``x (B,N,D,H,W,C)``, mask-independent ``cell0 (B, n_pts) int32``, ``mask`` bool/uint8 with n_pts entries per frame (or
     empty / None) -> ``(B, C, n_cells)`` fp32: what ``bev_pool(x, fold_mask(cell0, mask), n_cells)`` returns.  ``plan`` =
     ``build_plan(cell0, n_cells)`` (optional, cached by the caller) removes the per-call sort."""
-    _check_cells(n_cells)
-    return _BevPoolMasked.apply(x, cell0, mask, int(n_cells), plan)
+    n_cells = int(n_cells)
+    if n_cells > max_cells_per_pass():
+        has_mask = mask is not None and mask.numel() > 0
+        return _pool_in_windows(x, fold_mask(cell0, mask) if has_mask else cell0, n_cells)
+    return _BevPoolMasked.apply(x, cell0, mask, n_cells, plan)
 
 
 def fold_mask(cell0: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
@@ -283,6 +303,9 @@ class _LiftSplat(torch.autograd.Function):
 
 def lift_splat(feat: torch.Tensor, depth: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
     """``feat (B,C,H,W)``, ``depth (B,D,H,W)``, ``cell (B, D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
+    if int(n_cells) > max_cells_per_pass():
+        raise ValueError(f"the fused lift-splat handles at most {max_cells_per_pass()} BEV cells (nx*ny*nz), got {n_cells}; "
+                         "FrustumPooling.forward / bev_pool pool bigger grids in windows")
     return _LiftSplat.apply(feat, depth, cell, int(n_cells))
 
 
@@ -444,7 +467,7 @@ class FrustumPooling(nn.Module):
         nx, ny, nz = self.nx_constant
         c = self._geom_cache
         plan = None
-        if c is not None and c["cell0"] is cell0 and cell0.shape[0] == B:
+        if c is not None and c["cell0"] is cell0 and cell0.shape[0] == B and nx * ny * nz <= max_cells_per_pass():
             if c.get("plan") is None:
                 c["plan"] = build_plan(cell0, nx * ny * nz)
             plan = c["plan"]

@@ -258,16 +258,60 @@ def test_geometry_cache_and_mask_fold(lib):
     assert "_geom_cache" not in fp.state_dict() and list(fp.state_dict().keys()) == ["bev_intrinsics"]
 
 
-def test_large_bev_grid_is_rejected_with_a_clear_message(lib):
-    """grids above the shared-memory histogram limit must fail loudly, not with a bare MUVO_E_SHAPE."""
-    limit = lib.muvo_bev_pool_max_cells()
-    assert limit == 12800
-    fp = muvo_b200.FrustumPooling(size=(192, 192), scale=0.2, offsetx=0.0, dbound=[1.0, 5.0, 1.0], downsample=8).cuda()
-    x = torch.zeros((1, 1, 4, 5, 6, 2), device="cuda")
-    K = torch.eye(3, device="cuda")[None, None]
-    E = torch.eye(4, device="cuda")[None, None]
+def test_large_bev_grids_are_pooled_in_windows(lib):
+    """the reference handles any BEV grid (frustum_pooling.py:131-187).  One library call sorts at most 12 800 cells
+    (shared-memory histograms); bigger grids go through the same kernels window by window: forward within the float64 bound,
+    backward the exact gather, masked and unmasked, and the drop-in module on a 192 x 192 grid equals the oracle."""
+    from muvo_b200.frustum_pooling import bev_pool_masked, max_cells_per_pass
+    assert max_cells_per_pass() == lib.muvo_bev_pool_max_cells() == 12800
+    g = torch.Generator().manual_seed(5)
+    B, D, H, W, C = 2, 5, 12, 40, 6
+    n_pts = D * H * W
+    # 30 000 cells = 3 windows; 4 096 / 11 000 cells = one call, but past what the pipelined / one-CTA-per-row kernels hold in
+    # shared memory next to their staging buffer for (B, C, D, H, W) memory (3 242 / 9 720 cells)
+    for n_cells, planar in ((30000, False), (30000, True), (4096, True), (11000, True)):
+      base = torch.randn(B, C, D, H, W, generator=g).cuda() if planar else torch.randn(B, 1, D, H, W, C, generator=g).cuda()
+      x = (base.unsqueeze(1).permute(0, 1, 3, 4, 5, 2) if planar else base).requires_grad_(True)
+      cell = torch.randint(-1, n_cells, (B, n_pts), generator=g, dtype=torch.int32)
+      if n_cells > 12810:
+          cell[:, :200] = torch.randint(12790, 12810, (B, 200), generator=g, dtype=torch.int32)      # runs across a window edge
+      mask = torch.rand(B, n_pts, generator=g) < 0.5
+      for m in (None, mask):
+          out = bev_pool_masked(x, cell.cuda(), m.cuda() if m is not None else None, n_cells)
+          cc = cell.clone().long()
+          if m is not None:
+              cc[~m] = -1
+          xf = x.detach().reshape(B, n_pts, C).double().cpu()
+          want = torch.zeros(B, n_cells, C, dtype=torch.float64)
+          mag = torch.zeros(B, n_cells, C, dtype=torch.float64)
+          for b in range(B):
+              keep = cc[b] >= 0
+              want[b].index_add_(0, cc[b][keep], xf[b][keep])
+              mag[b].index_add_(0, cc[b][keep], xf[b][keep].abs())
+          assert out.shape == (B, C, n_cells)
+          assert torch.all((out.detach().cpu().double() - want.permute(0, 2, 1)).abs() <= TOL * mag.permute(0, 2, 1) + 1e-30)
+          gout = torch.randn(out.shape, generator=g).cuda()
+          (gx,) = torch.autograd.grad(out, x, gout)
+          exp = torch.zeros(B, n_pts, C)
+          for b in range(B):
+              keep = cc[b] >= 0
+              exp[b][keep] = gout.cpu()[b].t()[cc[b][keep]]
+          assert torch.equal(gx.reshape(B, n_pts, C).cpu(), exp)
+          assert torch.equal(bev_pool(x, torch.where(cc >= 0, cc, torch.full_like(cc, -1)).int().cuda(), n_cells), out)
+    # the module: the same area at 192 x 192 cells of 0.2 m (36 864 cells), reference constructor arguments otherwise
+    args = dict(synth.BEV_POOL_ARGS)
+    args.update(size=(192, 192), scale=0.2)
+    feat, depth, mask, K, E = synth.bev_inputs(1, 8, 3100)
+    fp = muvo_b200.FrustumPooling(**args).cuda()
+    assert int(fp.nx_constant[0]) * int(fp.nx_constant[1]) * int(fp.nx_constant[2]) > 12800
+    xl = synth.lift(feat, depth)
+    out = fp(xl.cuda(), K.cuda()[:, None], E.cuda()[:, None], mask.cuda())
+    exact = O.frustum_pooling_forward(xl.double(), K[:, None], E[:, None], mask, exact=True, **args)
+    mag = O.frustum_pooling_forward(xl.double().abs(), K[:, None], E[:, None], mask, exact=True, **args)
+    assert out.shape == exact.shape and torch.count_nonzero(exact) > 0
+    assert torch.all((out.cpu().double() - exact).abs() <= TOL * mag + 1e-30)
     with pytest.raises(ValueError, match="at most 12800 BEV cells"):
-        fp(x, K, E)
+        fp.lift_splat(feat.cuda(), depth.cuda(), K.cuda()[:, None], E.cuda()[:, None], mask.cuda())
 
 
 # ----------------------------------------------------------------------------- streamed forward (bev_stream.cu)
