@@ -401,3 +401,39 @@ def test_streamed_pool_equals_gather_kernels_at_cfg3(lib):
     assert torch.all((out_s - out_g).abs() <= 2 * TOL * mag + 1e-30)
     assert torch.equal(out_s == 0, out_g == 0)
     assert torch.equal(out_s, fp(x, K[:, None], E[:, None], mask))
+
+
+def test_two_cameras_per_frame_match_the_oracle(lib):
+    """The reference pools N cameras per frame into one BEV grid (x (B,N,D,H,W,C), frustum_pooling.py:131-187; MUVO itself
+    uses N = 1): two cameras with different extrinsics, mask over B*N*D*H*W points, forward vs the float64 oracle and the
+    backward vs the oracle's cell ids, for the channels-last tensor and for a permuted (B,N,C,D,H,W) memory view."""
+    B, N, C = 2, 2, 16
+    feat, depth, mask, K, E = synth.bev_inputs(B * N, C, 3300)
+    xl = synth.lift(feat, depth)                                   # (B*N, 1, D, H, W, C) view of (B*N, C, D, H, W) memory
+    D, H, W = xl.shape[2:5]
+    E2 = E.clone()
+    E2[1::2, 0, 3] += 3.0                                          # the second camera of every frame sits elsewhere
+    E2[1::2, 1, 3] -= 1.5
+    Kn, En = K.view(B, N, 3, 3), E2.view(B, N, 4, 4)
+    m = mask.view(B, N, D, H, W)
+    fp = muvo_b200.FrustumPooling(**synth.BEV_POOL_ARGS).cuda()
+    for planar in (False, True):
+        if planar:
+            base = xl[:, 0].permute(0, 4, 1, 2, 3).reshape(B, N, C, D, H, W).contiguous().cuda()     # (B, N, C, D, H, W) memory
+            x = base.permute(0, 1, 3, 4, 5, 2).requires_grad_(True)
+        else:
+            x = xl[:, 0].reshape(B, N, D, H, W, C).contiguous().cuda().requires_grad_(True)
+        for mm in (m, torch.zeros(0)):
+            out = fp(x, Kn.cuda(), En.cuda(), mm.cuda())
+            xd = x.detach().cpu().double()
+            exact = O.frustum_pooling_forward(xd, Kn, En, mm, exact=True, **synth.BEV_POOL_ARGS)
+            mag = O.frustum_pooling_forward(xd.abs(), Kn, En, mm, exact=True, **synth.BEV_POOL_ARGS)
+            assert out.shape == exact.shape and torch.count_nonzero(exact) > 0
+            assert torch.all((out.detach().cpu().double() - exact).abs() <= TOL * mag + 1e-30)
+            # gradient of sum(out * g) w.r.t. x = g at the point's cell (0 for dropped points): compare with float64 autograd of
+            # the oracle
+            g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3))
+            (gx,) = torch.autograd.grad(out, x, g.cuda())
+            xo = xd.clone().requires_grad_(True)
+            (go,) = torch.autograd.grad(O.frustum_pooling_forward(xo, Kn, En, mm, exact=True, **synth.BEV_POOL_ARGS), xo, g.double())
+            assert torch.equal(gx.cpu(), go.float())
