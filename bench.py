@@ -634,7 +634,22 @@ def other_stages(device, rank, world, hbm_peak, args):
     om = fp(xm, Kc, Ec, mask)
     ms_mb = timed(lambda: torch.autograd.grad(om, xm, gout.view(om.shape), retain_graph=True), steps)
     res["bev_module_bwd"] = {"ms": ms_mb, "algorithmic_GBps": bytes_b / ms_mb / 1e6, "frac": bytes_b / ms_mb / 1e6 / hbm_peak}
+    res["bev_module_fwd"]["note"] = ("muvo_b200.FrustumPooling.forward(x, K, E, mask): cached cell ids + per-chunk plan, mask compaction "
+                                     "(k_chunk_compact) + TMA-streamed pool (k_pool_stream)")
     del xm, om
+    # the same module under MUVO's default precision ('16-mixed', config.py:40: the lifted tensor is fp16, 0.71 GB): reported
+    # beside the fp32 figures, not instead of them
+    x16 = x.detach().to(torch.float16)
+    fp(x16, Kc, Ec, mask)
+    ms_m16 = timed(lambda: fp(x16, Kc, Ec, mask), steps)
+    x16g = x16.requires_grad_(True)
+    om16 = fp(x16g, Kc, Ec, mask)
+    ms_mb16 = timed(lambda: torch.autograd.grad(om16, x16g, gout.view(om16.shape).to(om16.dtype), retain_graph=True), steps)
+    by16 = B * n_pts * C * 2
+    res["bev_module_fp16"] = {"fwd_ms": ms_m16, "bwd_ms": ms_mb16, "fwd_dense_GBps": by16 / ms_m16 / 1e6, "bwd_dense_GBps": by16 / ms_mb16 / 1e6,
+                              "fwd_frac": by16 / ms_m16 / 1e6 / hbm_peak, "bwd_frac": by16 / ms_mb16 / 1e6 / hbm_peak,
+                              "note": "fp16 lifted tensor (the reference's default precision); consumer bound, DESIGN.md section 7"}
+    del x16, x16g, om16
     # the reference's own FrustumPooling on the same inputs: stock PyTorch on this B200, and on the host cores (rank 0)
     ns = ref_namespace()
     if ns is not None and rank == 0:
