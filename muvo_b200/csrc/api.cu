@@ -27,7 +27,7 @@ int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char
   p.on = false;
   if (!n_out_h) return MUVO_E_NULL;
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   // marks whose name starts with '<' are baselines (recorded right before the first launch of an entry point):
   // they are not reported, but the next kernel's time is measured from them, so host-side gaps are excluded.
   int n = 0;
@@ -35,7 +35,7 @@ int muvo_profile_end(void* stream, int32_t capacity, float* ms_out_h, const char
     if (p.name[i][0] == '<') continue;
     float ms = 0.f;
     e = cudaEventElapsedTime(&ms, p.ev[i - 1], p.ev[i]);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
     if (ms_out_h) ms_out_h[n] = ms;
     if (names_out_h) names_out_h[n] = p.name[i];
     ++n;

@@ -1020,7 +1020,7 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_cell_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cell_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   }
   const int64_t n_chunks = (int64_t)B * w.n_wc;
   const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
@@ -1034,21 +1034,22 @@ static int run_pool_fwd(const T* x, int64_t sb, int64_t sp, int64_t sc, const in
   k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
                                                              w.chunk_kept, w.kp, w.dest, w.dest16);
   MUVO_AFTER_LAUNCH("k_cell_place", st);
-  // (B, C, D, H, W) memory: the pipelined row kernel while its cell tables fit next to the staging buffer (<= 3242 cells), the
-  // one-CTA-per-row kernel up to 9720 cells, above that (and for every other layout) the kernel that walks cells
+  // (B, C, D, H, W) memory: the pipelined row kernel while its cell tables fit next to the staging buffer (<= 3072 cells), the
+  // one-CTA-per-row kernel up to 9208 cells, above that (and for every other layout) the kernel that walks cells
   const size_t rsmem = (size_t)kRowCap * sizeof(float) + (size_t)n_cells * 2 + 16;
   const size_t psmem = (size_t)kRowCap * sizeof(float) + (size_t)((n_cells + 1) / 2 + 1) * 4 + (size_t)(n_cells + 1) * 4;
-  const bool rows_ok = n_cells <= 65535 && rsmem <= 227 * 1024;
-  const bool pipe_ok = rows_ok && psmem <= 227 * 1024 && g_tuning[2] != 1 && n_pts % 2 == 0;
+  constexpr size_t kSmemCap = 226 * 1024;            // 227 KiB per CTA minus the kernels' static shared memory
+  const bool rows_ok = n_cells <= 65535 && rsmem <= kSmemCap;
+  const bool pipe_ok = rows_ok && psmem <= kSmemCap && g_tuning[2] != 1 && n_pts % 2 == 0;
   if (sp == 1 && rows_ok) {
-    if (!pipe_ok) {        // tuning key 2 = 1: the one-CTA-per-row gather kernel (also: odd row stride, 3243..9720 cells)
+    if (!pipe_ok) {        // tuning key 2 = 1: the one-CTA-per-row gather kernel (also: odd row stride, grids past the pipelined kernel)
       cudaError_t e = cudaFuncSetAttribute(k_pool_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem);
-      if (e != cudaSuccess) return (int)e;
+      if (e != cudaSuccess) return ::muvo::cuda_fail(e);
       k_pool_rows<T><<<(unsigned)((int64_t)B * C), kRowThreads, rsmem, st>>>(x, sb, sc, w.kp, w.dest, w.cell_start, w.sorted, B, n_pts,
                                                                            C, n_cells, out);
     } else {
       cudaError_t e = cudaFuncSetAttribute(k_pool_rows_pipe<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem);
-      if (e != cudaSuccess) return (int)e;
+      if (e != cudaSuccess) return ::muvo::cuda_fail(e);
       int sms = kNumSMsB200;
       { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
       const int64_t rows = (int64_t)B * C;
@@ -1205,7 +1206,7 @@ int muvo_bev_pool_fwd_masked(const void* x, int32_t x_dtype, int64_t x_stride_b,
     if (rc != MUVO_OK) return rc;
   } else if (n > 0) {
     cudaError_t e = cudaMemcpyAsync(cell_out, cell0, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   }
   return muvo_bev_pool_fwd(x, x_dtype, x_stride_b, x_stride_p, x_stride_c, cell_out, B, n_pts, C, n_cells, out, ws, ws_bytes, stream);
 }
@@ -1263,7 +1264,7 @@ int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t*
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_cell_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cell_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   }
   const int64_t n_chunks = (int64_t)B * w.n_wc;
   const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
@@ -1282,7 +1283,7 @@ int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t*
     const int C4 = C / 4, G = kLsThreads / C4;
     const size_t lsmem = (size_t)kLsStage * 8 + (size_t)kLsCells * G * C4 * 16;
     cudaError_t e = cudaFuncSetAttribute(k_lift_splat_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
     k_lift_splat_fwd<<<(unsigned)((int64_t)B * groups), kLsThreads, lsmem, st>>>(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW,
                                                                                  C, n_cells, out);
   } else {

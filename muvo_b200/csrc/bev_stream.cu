@@ -434,7 +434,7 @@ int launch_stream(const T* x, int64_t sb, int64_t sc, const uint32_t* lists, con
   constexpr int NS = stages_for<T>();
   const size_t smem = stream_smem_bytes<T>(n_cells);
   cudaError_t e = cudaFuncSetAttribute(k_pool_stream<T, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   int sms = kNumSMsB200;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int items = B * ((C + kSCh - 1) / kSCh);
@@ -456,7 +456,7 @@ int launch_bwd_stream(const float* gout, const uint32_t* lists, const uint32_t* 
   const size_t smem = bwd_stream_smem_bytes<T>(n_cells);
   constexpr int CH = bwd_channels<T>();
   cudaError_t e = cudaFuncSetAttribute(k_pool_bwd_stream<T, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   int sms = kNumSMsB200;
   { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int items = B * ((C + CH - 1) / CH);

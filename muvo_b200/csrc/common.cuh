@@ -41,6 +41,10 @@ inline void prof_mark(const char* name, cudaStream_t st) {
   ++p.n;
 }
 
+// A failed runtime call (cudaFuncSetAttribute, cudaMemsetAsync, ...) is reported through the return value; the runtime's
+// "last error" is cleared as well, otherwise the NEXT library call's launch check would report it again as its own.
+static inline int cuda_fail(cudaError_t e) { (void)cudaGetLastError(); return (int)e; }
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

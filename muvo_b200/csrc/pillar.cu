@@ -166,7 +166,7 @@ int muvo_pillar_scatter_mean(const float* src, const void* index, int32_t index_
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(ws, 0, sum_bytes + sp_bytes + 256, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(count_out, 0, (size_t)n_out * sizeof(int32_t), st);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   prof_mark("<pillar>", st);
   if (n_src > 0) {
     k_pillar_absmax<<<kNumSMsB200 * 4, kPillarBlock, 0, st>>>(src, n_src * n_feat, absmax);
@@ -210,7 +210,7 @@ int muvo_pillar_scatter_max(const float* src, const void* index, int32_t index_d
   cudaStream_t st = (cudaStream_t)stream;
   unsigned long long* packed = (unsigned long long*)ws;
   cudaError_t e = cudaMemsetAsync(packed, 0, (size_t)n_out * n_feat * 8, st);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   prof_mark("<pillar>", st);
   if (n_src > 0) {
     if (index_dtype == MUVO_I64)

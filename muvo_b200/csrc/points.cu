@@ -998,13 +998,13 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
   {
     cudaError_t e = cudaFuncSetAttribute((const void*)k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k1_per_sm, (const void*)k1, kTileThreads, tsmem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
     if (k1_per_sm < 1) k1_per_sm = 1;
     if (g_tuning[0] > 0 && g_tuning[0] < k1_per_sm) k1_per_sm = g_tuning[0];
   }
   if (dense_fast) {
     cudaError_t e = cudaFuncSetAttribute(k_emit_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(EmitSmem));
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   }
 
   // launch with the programmatic-dependent-launch attribute (see pdl_wait)
@@ -1035,7 +1035,7 @@ static int run_points(const T* xyz, const uint8_t* sem, const int64_t* off, int 
       n_tile_ctas = (int)grid;
     } else if (n_occ_emit) {
       cudaError_t e = cudaMemsetAsync(n_occ_emit + f0, 0, (size_t)(f1 - f0) * sizeof(int64_t), cs);
-      if (e != cudaSuccess) return (int)e;
+      if (e != cudaSuccess) return ::muvo::cuda_fail(e);
     }
     chunk_ctas[chunk] = n_tile_ctas;
     return MUVO_OK;

@@ -998,7 +998,7 @@ int points_mega_f32(const float* xyz, const uint8_t* sem, const int64_t* off, in
   cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMegaSmemBytes);
   int per_sm = 0;
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)kern, kMegaThreads, kMegaSmemBytes);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   if (per_sm < 1) per_sm = 1;
   if (g_tuning[0] > 0 && g_tuning[0] < per_sm) per_sm = g_tuning[0];
   int sms = kNumSMsB200;
@@ -1034,7 +1034,7 @@ int points_mega_f32(const float* xyz, const uint8_t* sem, const int64_t* off, in
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   e = cudaLaunchKernelEx(&cfg, kern, a);
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   MUVO_AFTER_LAUNCH("k_points_mega", st);
   return MUVO_OK;
 }

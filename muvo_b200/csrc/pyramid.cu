@@ -221,7 +221,7 @@ int muvo_densify_sparse(const uint16_t* rows, const int64_t* row_offsets, int32_
   if ((reinterpret_cast<uintptr_t>(dense_out) & 3) || (reinterpret_cast<uintptr_t>(rows) & 7)) return MUVO_E_ALIGN;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(dense_out, 0, (size_t)n_frames * G, st);               // :324 np.zeros
-  if (e != cudaSuccess) return (int)e;
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   if (n_rows == 0) return MUVO_OK;
   const unsigned grid = (unsigned)ceil_div64(n_rows, 256);
   k_densify_mark<<<grid, 256, 0, st>>>(rows, row_offsets, n_frames, n_rows, dx, dy, dz, dense_out, n_bad);

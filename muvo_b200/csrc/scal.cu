@@ -391,7 +391,7 @@ static int launch_scal_fwd(const void* logits, const uint8_t* target, int F, int
   } else {
     const size_t smem = (size_t)(3 * C + 1) * kScalThreads * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(k_scal_fwd_any<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
     grid = scal_grid(k_scal_fwd_any<LT>, smem, F, S);
     k_scal_fwd_any<LT><<<grid, kScalThreads, smem, st>>>(lg, target, F, C, S, ignore, partial);
   }

@@ -366,7 +366,7 @@ template <typename K>
 static int set_smem(K kern, size_t smem) {
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
   }
   return 0;
 }

@@ -268,7 +268,7 @@ def test_large_bev_grids_are_pooled_in_windows(lib):
     B, D, H, W, C = 2, 5, 12, 40, 6
     n_pts = D * H * W
     # 30 000 cells = 3 windows; 4 096 / 11 000 cells = one call, but past what the pipelined / one-CTA-per-row kernels hold in
-    # shared memory next to their staging buffer for (B, C, D, H, W) memory (3 242 / 9 720 cells)
+    # shared memory next to their staging buffer for (B, C, D, H, W) memory (3 072 / 9 208 cells)
     for n_cells, planar in ((30000, False), (30000, True), (4096, True), (11000, True)):
       base = torch.randn(B, C, D, H, W, generator=g).cuda() if planar else torch.randn(B, 1, D, H, W, C, generator=g).cuda()
       x = (base.unsqueeze(1).permute(0, 1, 3, 4, 5, 2) if planar else base).requires_grad_(True)
@@ -437,3 +437,17 @@ def test_two_cameras_per_frame_match_the_oracle(lib):
             xo = xd.clone().requires_grad_(True)
             (go,) = torch.autograd.grad(O.frustum_pooling_forward(xo, Kn, En, mm, exact=True, **synth.BEV_POOL_ARGS), xo, g.double())
             assert torch.equal(gx.cpu(), go.float())
+
+
+def test_randomised_shapes_vs_float64_sums_and_oracle(lib):
+    """tools/fuzz_bev_ssc.py: 60 random shapes / layouts / dtypes / grids (1 .. 20 000 cells, incl. the boundaries of every kernel
+    choice) of bev_pool(_masked) forward + backward against float64 sums and the exact gather, and as many random ssc_counts calls
+    (all prediction dtypes, masks, 1 .. 40 classes) against the oracle.  (This sweep found the 3 073..12 800-cell gap and a stale
+    CUDA error that a failed call left behind for the next one.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_bev_ssc.py"), "60", "9"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "60 cases, 0 mismatches" in p.stdout

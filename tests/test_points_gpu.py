@@ -1,5 +1,6 @@
 """GPU parity for stages (a) voxelisation and (b) range-view projection, through the reference-facing
 wrappers (which call the C ABI).  Bit-exact against the golden vectors and the CPU oracle."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -684,3 +685,14 @@ def test_opt_in_dataflow_kernel_equals_default_path(lib):
         assert "k_points_tile" not in [k for k, _ in prof.kernels], prof.kernels      # it really was the other kernel
         for k in ("voxel", "n_occ", "range_xyzd", "range_sem"):
             assert torch.equal(got[k], want[k]), k
+
+
+def test_randomised_configurations_vs_oracle(lib):
+    """tools/fuzz_points.py: 40 random (grid, resolution, offset, image shape, field of view, sensor position, ragged batch,
+    point order, dtype, layout, remap) configurations of stages (a) + (b), every output bit-equal to the oracle."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_points.py"), "40", "5"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "40 cases, 0 mismatches" in p.stdout
