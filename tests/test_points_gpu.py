@@ -696,3 +696,14 @@ def test_randomised_configurations_vs_oracle(lib):
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_points.py"), "40", "5"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "40 cases, 0 mismatches" in p.stdout
+
+
+def test_randomised_next_rows_vs_oracle(lib):
+    """tools/fuzz_next_rows.py: 40 random shapes each of the scal-loss sums, PointPillar scatter, label pyramids, densify (with
+    duplicate rows), fused argmax + counts, fused lift-splat, against the oracle / the unfused path."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_next_rows.py"), "40", "2"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "40 cases, 0 mismatches" in p.stdout
