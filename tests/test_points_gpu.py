@@ -707,3 +707,14 @@ def test_randomised_next_rows_vs_oracle(lib):
     p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_next_rows.py"), "40", "2"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "40 cases, 0 mismatches" in p.stdout
+
+
+def test_randomised_host_paths_vs_oracle(lib):
+    """tools/fuzz_host_paths.py: HostPipeline with back-to-back ragged batches of very different sizes (sparse / dense, both
+    layouts, device_out, 1-3 slots), merge_pcd on random images / sweeps, lidar_range_view on ragged raw sweeps: bit-equal."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_host_paths.py"), "10", "6"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "10 cases, 0 mismatches" in p.stdout
