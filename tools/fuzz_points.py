@@ -40,6 +40,12 @@ for case in range(n_cases):
     if len(pts) == 0:
         continue
     f64 = rng.random() < 0.25
+    special = rng.random() < 0.2                   # NaN / +-inf / huge / denormal coordinates: the voxeliser drops what is outside
+    if special:                                    # (the reference's range projection raises on them, so voxel-only calls)
+        k = rng.integers(0, len(pts), min(len(pts), 12))
+        vals = np.array([np.nan, np.inf, -np.inf, 1e30, -1e30, 1e-42, -0.0, 3.4e38], np.float32)
+        pts = pts.copy()
+        pts[k, rng.integers(0, 3, len(k))] = vals[rng.integers(0, len(vals), len(k))]
     remap = synth.label_remap256() if rng.random() < 0.5 else None
     grid = GridSpec(voxel_resolution=res, voxel_size=tuple(size), offset=tuple(offset))
     rs = RangeSpec(H=H, W=W, fov_down=fov_down, fov_up=fov_up, lidar_position=tuple(lidar))
@@ -48,7 +54,8 @@ for case in range(n_cases):
     layout = str(rng.choice(["xyzd", "hwc"]))
     sparse = bool(rng.random() < 0.5)
     kw = dict(grid=grid, remap=torch.from_numpy(remap) if remap is not None else None, layout=layout, dense=True, sparse=sparse)
-    if not f64:
+    do_range = not f64 and not special
+    if do_range:
         kw["range_spec"] = rs
     r = sensor_to_grid(tp, ts, off, **kw)
     torch.cuda.synchronize()
@@ -66,7 +73,7 @@ for case in range(n_cases):
         if sparse:
             rows = r["voxel_sparse"].cpu().numpy().view(np.uint16)[off[f]:off[f] + len(v0)]
             ok &= np.array_equal(rows[:, :3], v0) and np.array_equal(rows[:, 3].astype(np.uint8), l0)
-        if not f64:
+        if do_range:
             if len(p) == 0:
                 d0, x0, s0 = -np.ones((H, W), np.float32), np.zeros((H, W, 3), np.float32), np.zeros((H, W), np.uint8)
             else:
