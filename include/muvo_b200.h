@@ -265,6 +265,16 @@ MUVO_API int muvo_bev_pool_bwd_streamed(const float* grad_out, const int32_t* ce
  * written, deterministic (no atomics).                                                     */
 MUVO_API int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t* cell, int32_t B, int32_t D,
                         int32_t HW, int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream);
+/* The same forward with the mask-independent cell sort taken from a cached plan (one per camera rig, built from the cell ids
+ * WITHOUT the mask folded in): plan = muvo_lift_splat_plan_bytes(B, D*HW, n_cells) bytes, 256-byte aligned, filled by
+ * muvo_lift_splat_plan_build (ws = muvo_bev_pool_workspace_bytes).  mask: uint8 [B, D*HW] (0 = dropped) or NULL; a call then
+ * only filters the plan by the mask (two small kernels) instead of sorting.  Same output bits as muvo_lift_splat_fwd on the
+ * folded cell ids.                                                                                                          */
+MUVO_API int muvo_lift_splat_plan_bytes(int32_t B, int64_t n_pts, int32_t n_cells, size_t* bytes_out_h);
+MUVO_API int muvo_lift_splat_plan_build(const int32_t* cell0, int32_t B, int64_t n_pts, int32_t n_cells, void* plan, size_t plan_bytes,
+                      void* ws, size_t ws_bytes, void* stream);
+MUVO_API int muvo_lift_splat_fwd_planned(const float* feat_cl, const float* depth, const void* plan, size_t plan_bytes, const uint8_t* mask,
+                      int32_t B, int32_t D, int32_t HW, int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes, void* stream);
 MUVO_API int muvo_lift_splat_bwd(const float* gout_cl, const float* feat_cl, const float* depth, const int32_t* cell,
                         int32_t B, int32_t D, int32_t HW, int32_t C, int32_t n_cells, float* grad_depth,
                         float* grad_feat_cl, void* stream);

@@ -75,6 +75,9 @@ SIGNATURES = {
     "muvo_bev_pool_bwd_streamed": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _I32, _I64, _I64, _I64, _P, _SZ, _P]),
     "muvo_bev_pool_bwd": (C.c_int, [_P, _P, _I32, _I64, _I32, _I32, _P, _I32, _I64, _I64, _I64, _P]),
     "muvo_lift_splat_fwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _SZ, _P]),
+    "muvo_lift_splat_plan_bytes": (C.c_int, [_I32, _I64, _I32, C.POINTER(_SZ)]),
+    "muvo_lift_splat_plan_build": (C.c_int, [_P, _I32, _I64, _I32, _P, _SZ, _P, _SZ, _P]),
+    "muvo_lift_splat_fwd_planned": (C.c_int, [_P, _P, _P, _SZ, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _SZ, _P]),
     "muvo_lift_splat_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "muvo_segment_sum_workspace_bytes": (C.c_int, [_I64, C.POINTER(_SZ)]),
     "muvo_segment_sum_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P, _P, _SZ, _P]),

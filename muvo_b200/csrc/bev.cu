@@ -1111,6 +1111,175 @@ static SegWs carve_seg(void* base, int64_t n) {
   return w;
 }
 
+
+// ---------------------------------------------------------------- N2: cached cell sort for the fused lift-splat
+// The cell of every frustum point is fixed per camera rig; only the top-k depth mask changes per call.  The plan holds the
+// mask-independent sort (point ids grouped by cell, cell starts, and the cell of every sorted entry); a call filters it by
+// the mask with two small kernels (a stable compaction: per-chunk counts, then placement + re-based cell starts) instead
+// of the four-kernel counting sort (50 us at cfg3 -> 12 us).
+struct LsPlan {
+  uint32_t* cell_start0 = nullptr;  // [B, n_cells + 1]
+  int32_t* sorted0 = nullptr;       // [B, n_pts]   first cell_start0[b][n_cells] entries valid
+  int32_t* scell0 = nullptr;        // [B, n_pts]   cell of sorted0[i]
+  size_t bytes = 0;
+};
+static LsPlan carve_ls_plan(void* base, int B, int64_t n_pts, int n_cells) {
+  LsPlan p;
+  char* b = (char*)base;
+  size_t o = 0;
+  p.cell_start0 = (uint32_t*)(b + o); o = align_up(o + (size_t)B * (n_cells + 1) * 4, 256);
+  p.sorted0 = (int32_t*)(b + o);      o = align_up(o + (size_t)B * n_pts * 4, 256);
+  p.scell0 = (int32_t*)(b + o);       o = align_up(o + (size_t)B * n_pts * 4, 256);
+  p.bytes = o;
+  return p;
+}
+
+__global__ void __launch_bounds__(128)
+k_ls_plan_cells(const uint32_t* __restrict__ cell_start0, int B, int64_t n_pts, int n_cells, int32_t* __restrict__ scell0) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (t >= (int64_t)B * n_cells) return;
+  const int b = (int)(t / n_cells), c = (int)(t % n_cells);
+  const uint32_t* cs = cell_start0 + (size_t)b * (n_cells + 1);
+  int32_t* o = scell0 + (size_t)b * n_pts;
+  for (uint32_t i = cs[c]; i < cs[c + 1]; ++i) o[i] = c;
+}
+
+constexpr int kLfThreads = 256;
+constexpr int kLfPer = 8;
+constexpr int kLfChunk = kLfThreads * kLfPer;      // sorted entries per CTA
+
+__global__ void __launch_bounds__(kLfThreads)
+k_ls_filter_count(const int32_t* __restrict__ sorted0, const uint32_t* __restrict__ cell_start0, const uint8_t* __restrict__ mask,
+                  int64_t n_pts, int n_cells, int n_fc, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t ws[kLfThreads / 32];
+  const int b = blockIdx.y, k = blockIdx.x;
+  const uint32_t n0 = cell_start0[(size_t)b * (n_cells + 1) + n_cells];
+  const int32_t* so = sorted0 + (size_t)b * n_pts;
+  const uint8_t* mb = mask + (size_t)b * n_pts;
+  uint32_t cnt = 0;
+  const uint32_t i0 = (uint32_t)k * kLfChunk + threadIdx.x * kLfPer;
+#pragma unroll
+  for (int e = 0; e < kLfPer; ++e)
+    if (i0 + e < n0) cnt += __ldg(mb + __ldg(so + i0 + e)) != 0 ? 1u : 0u;
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kLfThreads / 32; ++w) t += ws[w];
+    counts[(size_t)b * n_fc + k] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kLfThreads)
+k_ls_filter_write(const int32_t* __restrict__ sorted0, const int32_t* __restrict__ scell0, const uint32_t* __restrict__ cell_start0,
+                  const uint8_t* __restrict__ mask, int64_t n_pts, int n_cells, int n_fc, const uint32_t* __restrict__ counts,
+                  int32_t* __restrict__ sorted, uint32_t* __restrict__ cell_start) {
+  __shared__ uint32_t ws[kLfThreads / 32];
+  __shared__ uint32_t prefix_s;
+  const int b = blockIdx.y, k = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n0 = cell_start0[(size_t)b * (n_cells + 1) + n_cells];
+  uint32_t* cs = cell_start + (size_t)b * (n_cells + 1);
+  if (n0 == 0u) {                                                // nothing in bounds in this frame
+    if (k == 0) for (int c = tid; c <= n_cells; c += kLfThreads) cs[c] = 0u;
+    return;
+  }
+  if ((uint32_t)k * kLfChunk >= n0) return;
+  // kept entries in the chunks before this one
+  uint32_t pre = 0;
+  for (int j = tid; j < k; j += kLfThreads) pre += counts[(size_t)b * n_fc + j];
+  pre = __reduce_add_sync(0xffffffffu, pre);
+  if (lane == 0) ws[warp] = pre;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < kLfThreads / 32; ++w) t += ws[w];
+    prefix_s = t;
+  }
+  __syncthreads();
+  const uint32_t prefix = prefix_s;
+  const int32_t* so = sorted0 + (size_t)b * n_pts;
+  const int32_t* sc = scell0 + (size_t)b * n_pts;
+  const uint8_t* mb = mask + (size_t)b * n_pts;
+  int32_t* out = sorted + (size_t)b * n_pts;
+  const uint32_t i0 = (uint32_t)k * kLfChunk + tid * kLfPer;
+  int32_t pid[kLfPer];
+  uint32_t keep = 0, cnt = 0;
+#pragma unroll
+  for (int e = 0; e < kLfPer; ++e) {
+    pid[e] = 0;
+    if (i0 + e < n0) {
+      pid[e] = __ldg(so + i0 + e);
+      if (__ldg(mb + pid[e]) != 0) { keep |= 1u << e; ++cnt; }
+    }
+  }
+  // block-wide exclusive scan of the per-thread counts
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+  __syncthreads();                                               // ws is reused
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  uint32_t wbase = 0;
+#pragma unroll
+  for (int w = 0; w < kLfThreads / 32; ++w) if (w < warp) wbase += ws[w];
+  uint32_t ex = prefix + wbase + (incl - cnt);                   // new index of this thread's first kept entry
+  int32_t prev = i0 > 0u && i0 < n0 ? __ldg(sc + i0 - 1) : -1;
+#pragma unroll
+  for (int e = 0; e < kLfPer; ++e) {
+    const uint32_t g = i0 + e;
+    if (g >= n0) break;
+    const int32_t cur = __ldg(sc + g);
+    if (cur != prev) for (int32_t c = prev + 1; c <= cur; ++c) cs[c] = ex;      // cells (prev, cur] start here (empty ones included)
+    prev = cur;
+    if ((keep >> e) & 1u) out[ex++] = pid[e];
+    if (g == n0 - 1u) for (int32_t c = cur + 1; c <= n_cells; ++c) cs[c] = ex;  // the cells behind the last entry, and the total
+  }
+}
+
+static int run_cell_sort(const int32_t* cell, int B, int64_t n_pts, int n_cells, const BevWs& w, cudaStream_t st) {
+  const size_t smem = (size_t)kSortWarps * n_cells * 4;
+  if (smem > 200 * 1024) return MUVO_E_SHAPE;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_cell_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cell_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
+  }
+  const int64_t n_chunks = (int64_t)B * w.n_wc;
+  const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
+  k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.chunk_kept);
+  MUVO_AFTER_LAUNCH("k_cell_hist", st);
+  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 64), 64, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
+  MUVO_AFTER_LAUNCH("k_cell_scan", st);
+  k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
+  MUVO_AFTER_LAUNCH("k_cell_starts", st);
+  k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
+                                                             w.chunk_kept, w.kp, w.dest, w.dest16);
+  MUVO_AFTER_LAUNCH("k_cell_place", st);
+  return MUVO_OK;
+}
+
+static int launch_lift_fwd(const float* feat_cl, const float* depth, const uint32_t* cell_start, const int32_t* sorted, int B, int64_t n_pts,
+                           int HW, int C, int n_cells, float* out, cudaStream_t st) {
+  const int groups = (n_cells + kLsCells - 1) / kLsCells;
+  if (C % 4 == 0 && C / 4 <= kLsThreads && (reinterpret_cast<uintptr_t>(feat_cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const int C4 = C / 4, G = kLsThreads / C4;
+    const size_t lsmem = (size_t)kLsStage * 8 + (size_t)kLsCells * G * C4 * 16;
+    cudaError_t e = cudaFuncSetAttribute(k_lift_splat_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
+    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
+    k_lift_splat_fwd<<<(unsigned)((int64_t)B * groups), kLsThreads, lsmem, st>>>(feat_cl, depth, cell_start, sorted, B, n_pts, HW, C, n_cells, out);
+  } else {
+    int threads = ((C + 31) / 32) * 32;
+    if (threads > 512) threads = 512;
+    k_lift_splat_fwd_scalar<<<(unsigned)((int64_t)B * groups), threads, 0, st>>>(feat_cl, depth, cell_start, sorted, B, n_pts, HW, C, n_cells, out);
+  }
+  MUVO_AFTER_LAUNCH("k_lift_splat_fwd", st);
+  return MUVO_OK;
+}
+
 }  // namespace
 }  // namespace muvo
 
@@ -1259,41 +1428,63 @@ int muvo_lift_splat_fwd(const float* feat_cl, const float* depth, const int32_t*
   cudaStream_t st = (cudaStream_t)stream;
   BevWs w = carve_bev(ws, B, n_pts, n_cells);
   if (w.bytes > ws_bytes) return MUVO_E_WORKSPACE;
-  const size_t smem = (size_t)kSortWarps * n_cells * 4;
-  if (smem > 200 * 1024) return MUVO_E_SHAPE;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_cell_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_cell_place, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
-  }
-  const int64_t n_chunks = (int64_t)B * w.n_wc;
-  const unsigned sort_blocks = (unsigned)ceil_div64(n_chunks, kSortWarps);
   prof_mark("<lift_splat_fwd>", st);
-  k_cell_hist<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.chunk_kept);
-  MUVO_AFTER_LAUNCH("k_cell_hist", st);
-  k_cell_scan<<<(unsigned)ceil_div64((int64_t)B * n_cells, 64), 64, 0, st>>>(w.chunk_base, w.cell_total, B, n_cells, w.n_wc);
-  MUVO_AFTER_LAUNCH("k_cell_scan", st);
-  k_cell_starts<<<B, 1024, 0, st>>>(w.cell_total, w.cell_start, n_cells, w.chunk_kept, w.n_wc);
-  MUVO_AFTER_LAUNCH("k_cell_starts", st);
-  k_cell_place<<<sort_blocks, kSortWarps * 32, smem, st>>>(cell, B, n_pts, n_cells, w.n_wc, w.chunk_base, w.cell_start, w.sorted,
-                                                             w.chunk_kept, w.kp, w.dest, w.dest16);
-  MUVO_AFTER_LAUNCH("k_cell_place", st);
-  const int groups = (n_cells + kLsCells - 1) / kLsCells;
-  if (C % 4 == 0 && C / 4 <= kLsThreads && (reinterpret_cast<uintptr_t>(feat_cl) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-    const int C4 = C / 4, G = kLsThreads / C4;
-    const size_t lsmem = (size_t)kLsStage * 8 + (size_t)kLsCells * G * C4 * 16;
-    cudaError_t e = cudaFuncSetAttribute(k_lift_splat_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem);
-    if (e != cudaSuccess) return ::muvo::cuda_fail(e);
-    k_lift_splat_fwd<<<(unsigned)((int64_t)B * groups), kLsThreads, lsmem, st>>>(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW,
-                                                                                 C, n_cells, out);
-  } else {
-    int threads = ((C + 31) / 32) * 32;
-    if (threads > 512) threads = 512;
-    k_lift_splat_fwd_scalar<<<(unsigned)((int64_t)B * groups), threads, 0, st>>>(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW,
-                                                                                 C, n_cells, out);
-  }
-  MUVO_AFTER_LAUNCH("k_lift_splat_fwd", st);
+  const int rc = run_cell_sort(cell, B, n_pts, n_cells, w, st);
+  if (rc != MUVO_OK) return rc;
+  return launch_lift_fwd(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW, C, n_cells, out, st);
+}
+
+int muvo_lift_splat_plan_bytes(int32_t B, int64_t n_pts, int32_t n_cells, size_t* bytes_out_h) {
+  if (!bytes_out_h) return MUVO_E_NULL;
+  if (B < 0 || n_pts < 0 || n_cells <= 0) return MUVO_E_ARG;
+  *bytes_out_h = carve_ls_plan(nullptr, B, n_pts, n_cells).bytes + 256;
   return MUVO_OK;
+}
+
+int muvo_lift_splat_plan_build(const int32_t* cell0, int32_t B, int64_t n_pts, int32_t n_cells, void* plan, size_t plan_bytes, void* ws,
+                               size_t ws_bytes, void* stream) {
+  if (B < 0 || n_pts < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0) return MUVO_OK;
+  if (!cell0 || !plan || !ws) return MUVO_E_NULL;
+  if (n_pts >= ((int64_t)1 << 31) || (int64_t)B * n_cells >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) || (reinterpret_cast<uintptr_t>(plan) & 255)) return MUVO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  BevWs w = carve_bev(ws, B, n_pts, n_cells);
+  LsPlan pl = carve_ls_plan(plan, B, n_pts, n_cells);
+  if (w.bytes > ws_bytes || pl.bytes > plan_bytes) return MUVO_E_WORKSPACE;
+  int rc = run_cell_sort(cell0, B, n_pts, n_cells, w, st);
+  if (rc != MUVO_OK) return rc;
+  cudaError_t e = cudaMemcpyAsync(pl.cell_start0, w.cell_start, (size_t)B * (n_cells + 1) * 4, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pl.sorted0, w.sorted, (size_t)B * n_pts * 4, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return ::muvo::cuda_fail(e);
+  k_ls_plan_cells<<<(unsigned)ceil_div64((int64_t)B * n_cells, 128), 128, 0, st>>>(pl.cell_start0, B, n_pts, n_cells, pl.scell0);
+  MUVO_AFTER_LAUNCH("k_ls_plan_cells", st);
+  return MUVO_OK;
+}
+
+int muvo_lift_splat_fwd_planned(const float* feat_cl, const float* depth, const void* plan, size_t plan_bytes, const uint8_t* mask,
+                                int32_t B, int32_t D, int32_t HW, int32_t C, int32_t n_cells, float* out, void* ws, size_t ws_bytes,
+                                void* stream) {
+  if (B < 0 || D <= 0 || HW <= 0 || C < 0 || n_cells <= 0) return MUVO_E_ARG;
+  if (B == 0 || C == 0) return MUVO_OK;
+  if (!feat_cl || !depth || !plan || !out || !ws) return MUVO_E_NULL;
+  const int64_t n_pts = (int64_t)D * HW;
+  if (n_pts >= ((int64_t)1 << 31) || (int64_t)B * n_cells >= ((int64_t)1 << 31)) return MUVO_E_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(ws) & 255) || (reinterpret_cast<uintptr_t>(plan) & 255)) return MUVO_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  BevWs w = carve_bev(ws, B, n_pts, n_cells);
+  LsPlan pl = carve_ls_plan(const_cast<void*>(plan), B, n_pts, n_cells);
+  if (w.bytes > ws_bytes || pl.bytes > plan_bytes) return MUVO_E_WORKSPACE;
+  prof_mark("<lift_splat_fwd>", st);
+  if (!mask)                                                     // nothing to drop: the plan IS the sort
+    return launch_lift_fwd(feat_cl, depth, pl.cell_start0, pl.sorted0, B, n_pts, HW, C, n_cells, out, st);
+  const int n_fc = (int)ceil_div64(n_pts, kLfChunk);
+  k_ls_filter_count<<<dim3((unsigned)n_fc, (unsigned)B), kLfThreads, 0, st>>>(pl.sorted0, pl.cell_start0, mask, n_pts, n_cells, n_fc, w.chunk_kept);
+  MUVO_AFTER_LAUNCH("k_ls_filter_count", st);
+  k_ls_filter_write<<<dim3((unsigned)n_fc, (unsigned)B), kLfThreads, 0, st>>>(pl.sorted0, pl.scell0, pl.cell_start0, mask, n_pts, n_cells, n_fc,
+                                                                              w.chunk_kept, w.sorted, w.cell_start);
+  MUVO_AFTER_LAUNCH("k_ls_filter_write", st);
+  return launch_lift_fwd(feat_cl, depth, w.cell_start, w.sorted, B, n_pts, HW, C, n_cells, out, st);
 }
 
 int muvo_lift_splat_bwd(const float* gout_cl, const float* feat_cl, const float* depth, const int32_t* cell, int32_t B,

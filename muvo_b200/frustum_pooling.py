@@ -260,7 +260,7 @@ class _LiftSplat(torch.autograd.Function):
     points of the cell -- what ``bev_pool`` returns for the lifted tensor of mile.py:517-521, without building it."""
 
     @staticmethod
-    def forward(ctx, feat, depth, cell, n_cells):
+    def forward(ctx, feat, depth, cell, n_cells, plan=None, mask=None):
         _lib.require_cuda(feat, depth, cell)
         lib = _lib.load()
         B, Cc, H, W = feat.shape
@@ -277,8 +277,12 @@ class _LiftSplat(torch.autograd.Function):
             nb = C.c_size_t(0)
             _lib.check(lib.muvo_bev_pool_workspace_bytes(B, D * H * W, n_cells, C.byref(nb)), "muvo_bev_pool_workspace_bytes")
             ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
-            rc = lib.muvo_lift_splat_fwd(feat_cl.data_ptr(), dep.data_ptr(), _lib.ptr(cell), B, D, H * W, Cc, n_cells,
-                                         out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+            if plan is not None:                 # cached mask-independent sort: only the mask filter runs per call
+                rc = lib.muvo_lift_splat_fwd_planned(feat_cl.data_ptr(), dep.data_ptr(), plan.data_ptr(), plan.numel(), _lib.ptr(mask), B, D,
+                                                     H * W, Cc, n_cells, out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+            else:
+                rc = lib.muvo_lift_splat_fwd(feat_cl.data_ptr(), dep.data_ptr(), _lib.ptr(cell), B, D, H * W, Cc, n_cells,
+                                             out.data_ptr(), ws.data_ptr(), ws.numel(), stream)
         _lib.check(rc, "muvo_lift_splat_fwd")
         ctx.save_for_backward(feat_cl, dep, cell)
         ctx.meta = (B, Cc, D, H, W, n_cells, feat.dtype, depth.dtype)
@@ -298,15 +302,44 @@ class _LiftSplat(torch.autograd.Function):
                                                  H * W, Cc, n_cells, gdepth.data_ptr(), gfeat_cl.data_ptr(),
                                                  _lib.current_stream(dev))
         _lib.check(rc, "muvo_lift_splat_bwd")
-        return gfeat_cl.permute(0, 3, 1, 2).to(fdt), gdepth.to(ddt), None, None
+        return gfeat_cl.permute(0, 3, 1, 2).to(fdt), gdepth.to(ddt), None, None, None, None
 
 
-def lift_splat(feat: torch.Tensor, depth: torch.Tensor, cell: torch.Tensor, n_cells: int) -> torch.Tensor:
-    """``feat (B,C,H,W)``, ``depth (B,D,H,W)``, ``cell (B, D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32."""
+def lift_splat(feat: torch.Tensor, depth: torch.Tensor, cell: torch.Tensor, n_cells: int, plan=None, mask=None) -> torch.Tensor:
+    """``feat (B,C,H,W)``, ``depth (B,D,H,W)``, ``cell (B, D*H*W) int32`` (-1 = dropped) -> ``(B, C, n_cells)`` fp32.
+    With ``plan`` (:func:`build_lift_splat_plan` of the mask-independent cell ids) and the ``mask`` that was folded into
+    ``cell``, the forward skips the per-call cell sort (``cell`` is still what the backward walks)."""
     if int(n_cells) > max_cells_per_pass():
         raise ValueError(f"the fused lift-splat handles at most {max_cells_per_pass()} BEV cells (nx*ny*nz), got {n_cells}; "
                          "FrustumPooling.forward / bev_pool pool bigger grids in windows")
+    if plan is not None:
+        m = None
+        if mask is not None and mask.numel() > 0:
+            m = mask.reshape(-1)
+            m = (m if m.dtype in (torch.bool, torch.uint8) else m.bool()).contiguous().view(torch.uint8)
+            if m.numel() != cell.numel():
+                raise ValueError("mask and cell ids differ in size")
+        return _LiftSplat.apply(feat, depth, cell, int(n_cells), plan, m)
     return _LiftSplat.apply(feat, depth, cell, int(n_cells))
+
+
+def build_lift_splat_plan(cell0: torch.Tensor, n_cells: int) -> torch.Tensor:
+    """The mask-independent cell sort of the fused lift-splat (``muvo_lift_splat_plan_build``), to be cached per camera rig:
+    ``cell0 (B, n_pts) int32`` WITHOUT the mask folded in.  Pass it to :func:`lift_splat` together with the mask."""
+    _lib.require_cuda(cell0)
+    lib = _lib.load()
+    B, n_pts = cell0.shape
+    dev = cell0.device
+    nb, nw = C.c_size_t(0), C.c_size_t(0)
+    _lib.check(lib.muvo_lift_splat_plan_bytes(B, n_pts, int(n_cells), C.byref(nb)), "muvo_lift_splat_plan_bytes")
+    _lib.check(lib.muvo_bev_pool_workspace_bytes(B, n_pts, int(n_cells), C.byref(nw)), "muvo_bev_pool_workspace_bytes")
+    plan = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    ws = torch.empty(nw.value, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.muvo_lift_splat_plan_build(_lib.ptr(cell0.contiguous()), B, n_pts, int(n_cells), plan.data_ptr(), plan.numel(), ws.data_ptr(),
+                                            ws.numel(), _lib.current_stream(dev))
+    _lib.check(rc, "muvo_lift_splat_plan_build")
+    return plan
 
 
 class QuickCumsum(torch.autograd.Function):
@@ -487,7 +520,13 @@ class FrustumPooling(nn.Module):
         cell0 = self.cached_cell_ids(intrinsics, pose, feat.new_zeros((1, 1, 1, H, W, 1)))
         nx, ny, nz = self.nx_constant
         cell = fold_mask(cell0, mask) if len(mask) > 0 else cell0
-        out = lift_splat(feat, depth, cell, nx * ny * nz).view(B, Cc, nz, ny, nx)
+        plan = None
+        c = self._geom_cache
+        if c is not None and c["cell0"] is cell0 and cell0.shape[0] == B and nx * ny * nz <= max_cells_per_pass():
+            if c.get("ls_plan") is None:
+                c["ls_plan"] = build_lift_splat_plan(cell0.reshape(B, -1), nx * ny * nz)
+            plan = c["ls_plan"]
+        out = lift_splat(feat, depth, cell, nx * ny * nz, plan, mask if len(mask) > 0 else None).view(B, Cc, nz, ny, nx)
         out = out.view(B, Cc, ny, nx) if nz == 1 else out.permute(0, 2, 1, 3, 4).reshape(B, nz * Cc, ny, nx)
         return out.type_as(feat)
 

@@ -227,6 +227,20 @@ def test_fused_lift_splat_forward_and_gradients(B, C, use_mask, lib):
     # dropped points get exactly zero depth gradient
     cell = fp.cell_ids(fp.get_geometry(E.cuda()[:, None, :3, :3], E.cuda()[:, None, :3, 3:], K.cuda()[:, None]), m.cuda())
     assert torch.all(d.grad.reshape(B, -1)[cell < 0] == 0)
+    # the call above went through the per-camera plan (mask-independent cell sort cached, the mask only filters it); the plain
+    # entry point that sorts the folded cell ids per call gives the same bits, and so does a second call with another mask
+    from muvo_b200 import _lib
+    from muvo_b200.frustum_pooling import lift_splat
+    assert fp._geom_cache.get("ls_plan") is not None
+    assert torch.equal(lift_splat(f.detach(), d.detach(), cell, 2304).view_as(out), out.detach())
+    if use_mask:
+        m2 = torch.rand(m.shape, generator=torch.Generator().manual_seed(9)) < 0.4
+        with _lib.profile(_lib.current_stream(f.device)) as prof:
+            out2 = fp.lift_splat(f.detach(), d.detach(), K.cuda()[:, None], E.cuda()[:, None], m2.cuda())
+        names = [k for k, _ in prof.kernels]
+        assert "k_ls_filter_write" in names and "k_cell_place" not in names, names
+        cell2 = fp.cell_ids(fp.get_geometry(E.cuda()[:, None, :3, :3], E.cuda()[:, None, :3, 3:], K.cuda()[:, None]), m2.cuda())
+        assert torch.equal(lift_splat(f.detach(), d.detach(), cell2, 2304).view_as(out2), out2)
 
 
 def test_geometry_cache_and_mask_fold(lib):
