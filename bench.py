@@ -683,13 +683,15 @@ def other_stages(device, rank, world, hbm_peak, args):
     # N2: fused lift-splat on the same inputs (feat, depth -> BEV), forward and backward to feat / depth
     from muvo_b200.frustum_pooling import lift_splat
     fl, dl = feat.detach().requires_grad_(True), depth.detach().requires_grad_(True)
-    ms_lf = timed(lambda: lift_splat(fl.detach(), dl.detach(), cell, 2304), steps)
-    ol = lift_splat(fl, dl, cell, 2304)
+    fp.lift_splat(fl.detach(), dl.detach(), Kc, Ec, mask)           # builds the per-camera plan (mask-independent cell sort)
+    ms_lf = timed(lambda: fp.lift_splat(fl.detach(), dl.detach(), Kc, Ec, mask), steps)
+    ol = fp.lift_splat(fl, dl, Kc, Ec, mask).reshape(B, C, 2304)
     ms_lb = timed(lambda: torch.autograd.grad(ol, (fl, dl), gout, retain_graph=True), steps)
     bytes_l = B * (C * H * W * 4 + n_pts * 9 + C * 2304 * 4)       # feat + depth + cell ids + out, each once
     res["lift_splat_fused_fwd"] = {"ms": ms_lf, "algorithmic_GBps": bytes_l / ms_lf / 1e6, "frac": bytes_l / ms_lf / 1e6 / hbm_peak,
-                                   "note": "N2: same output as lift (mile.py:517-521) + bev_pool_fwd, outer product never materialised; "
-                                           "includes the channels-last copy of feat and the cell sort"}
+                                   "note": "N2: FrustumPooling.lift_splat(feat, depth, K, E, mask): same output as lift (mile.py:517-521) + "
+                                           "FrustumPooling.forward, outer product never materialised; includes the channels-last copy of "
+                                           "feat, the mask fold and the mask filter of the cached cell sort"}
     bytes_lb = B * (2 * C * H * W * 4 + n_pts * (4 + 4 + 4) + C * 2304 * 4)      # gout + feat in, grad_feat out, depth + cell in, grad_depth out
     res["lift_splat_fused_bwd"] = {"ms": ms_lb, "algorithmic_GBps": bytes_lb / ms_lb / 1e6, "frac": bytes_lb / ms_lb / 1e6 / hbm_peak,
                                    "note": "grad_feat + grad_depth, includes the [B,cells,C] copy of grad_out"}
