@@ -347,7 +347,7 @@ k_pool_stream(const T* __restrict__ x, int64_t sb, int64_t sc, const uint32_t* _
 // 16-bit gradients take 16 channels per CTA (the same 64 KiB tiles as float32 with 8): the per-chunk costs -- zero fill, list wait,
 // three barriers -- are per tile, so halving the tiles per byte took the fp16 backward from 0.21 to the float32 rate.  The
 // grad_out rows are kept already converted to T (one conversion per (channel, cell) instead of one per point).
-constexpr int kBThreads = 256;
+constexpr int kBThreads = 512;     // (256: 0.250 ms at cfg3, 512: 0.243, 1024: 0.241)
 template <typename T> constexpr int bwd_channels() { return sizeof(T) == 4 ? kSCh : 2 * kSCh; }
 template <typename T, int CH>
 __global__ void __launch_bounds__(kBThreads, 1)
