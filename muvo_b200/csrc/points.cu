@@ -53,7 +53,10 @@ namespace {
 // staged xyz are bank-conflict free).  Tiles that are partial (the last one) or whose source is not 16-byte aligned
 // are read straight from global memory.
 constexpr int kTileThreads = 256;
-constexpr int kKPL = 4;                          // points per thread per tile
+#ifndef MUVO_KPL
+#define MUVO_KPL 4
+#endif
+constexpr int kKPL = MUVO_KPL;                   // points per thread per tile
 constexpr int kTile = kTileThreads * kKPL;       // 1024 points
 
 template <typename T> struct TileLayout {
