@@ -1,3 +1,4 @@
+"""Streamed BEV forward at cfg3 for fp16 and fp32 inputs, with / without the consumer work (tuning key 3 = 1).  python tools/bev_stream_sweep16.py"""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 import muvo_b200

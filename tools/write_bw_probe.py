@@ -1,3 +1,4 @@
+"""Plain write bandwidth of this GPU (torch zero_ / fill_ of 1.42 GB = the bytes of the BEV backward).  python tools/write_bw_probe.py"""
 import torch
 dev = torch.device("cuda", 0)
 x = torch.empty(1418649600 // 4, dtype=torch.float32, device=dev)
