@@ -119,11 +119,6 @@ __device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ ulonglong2 ld_cg_u64x2(const u64* p) {
-  ulonglong2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ uint2 ld_cg_u32x2(const uint2* p) {
   uint2 v;
   asm volatile("ld.global.cg.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
@@ -153,11 +148,6 @@ __device__ __forceinline__ u64 atom_max_if(u64* table, uint32_t cell, u64 word, 
   asm volatile("{\n.reg .pred p;\n.reg .u64 ad;\nsetp.ne.u32 p, %2, 0xffffffff;\nmad.wide.u32 ad, %2, 8, %1;\n"
                "@p atom.global.max.L2::cache_hint.u64 %0, [ad], %3, %4;\n}"
                : "+l"(old) : "l"(table), "r"(cell), "l"(word), "l"(pol) : "memory");
-  return old;
-}
-__device__ __forceinline__ u64 atom_max_hint(u64* p, u64 v, uint64_t pol) {
-  u64 old;
-  asm volatile("atom.global.max.L2::cache_hint.u64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(v), "l"(pol) : "memory");
   return old;
 }
 __device__ __forceinline__ void red_or_if(uint32_t* bitmap, uint32_t bit, bool go, uint64_t pol) {
@@ -743,10 +733,6 @@ constexpr int kSmemDesc = kStages * kStageBytes;
 constexpr int kSmemBars = kSmemDesc + kStages * 64;
 constexpr int kMegaSmemBytes = kSmemBars + 4 * 8;
 static_assert(sizeof(UnitDesc) <= 64, "descriptor slot");
-
-__device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t need) {
-  while (ld_acquire_u32(p) < need) __nanosleep(64);
-}
 
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
   uint32_t v;
